@@ -1,0 +1,247 @@
+/*
+ * pantera_gpu.h -- C ABI of the B200-native particle hot path for PANTERA PIC-DSMC.
+ *
+ * Boundary.  The reference has NO foreign-function interface: its
+ * hot path is a set of argument-less Fortran module procedures called from TIME_LOOP
+ * (src/timecycle.f90:106-362) that act on module globals (src/global.f90).  Each entry
+ * point below replaces one of those procedures (or carries the globals it reads) and is
+ * what an ISO_C_BINDING interface block in the Fortran host binds to (see INTEGRATION.md
+ * for the gpu_bridge module and the #ifdef PANTERA_GPU call-site patch).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no C++/torch types.
+ *   - every function returns 0 (PGPU_OK) on success, non-zero on error; the message is
+ *     available from pgpu_last_error().  The Fortran shim forwards it to ERROR_ABORT
+ *     (src/screen.f90:113-124), which is the reference's only error convention.
+ *   - arrays are passed exactly as Fortran stores them: column-major (first index fastest),
+ *     1-based cell/node/species/physical-group ids, -1 = "none".
+ *   - host arrays are copied during the call; the library never keeps host pointers.
+ *   - one context <-> one CUDA device <-> one host thread; calls are synchronous on return.
+ *   - there is no CPU fallback: every compute entry point fails if no CUDA device is usable.
+ */
+#ifndef PANTERA_GPU_H
+#define PANTERA_GPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PGPU_OK 0
+#define PGPU_ERR_INVALID 1
+#define PGPU_ERR_CUDA 2
+#define PGPU_ERR_STATE 3
+#define PGPU_ERR_UNSUPPORTED 4
+#define PGPU_ERR_NCCL 5
+
+/* ---- enumerations: numeric values are those of the reference's ENUM, BIND(C) blocks ---- */
+/* GRID_TYPE, src/global.f90:102-105 */
+enum { PGPU_RECTILINEAR_UNIFORM = 0, PGPU_RECTILINEAR_NONUNIFORM = 1, PGPU_QUADTREE = 2, PGPU_UNSTRUCTURED = 3 };
+/* particle boundary conditions, src/global.f90:205-207 */
+enum { PGPU_VACUUM = 0, PGPU_SPECULAR = 1, PGPU_DIFFUSE = 2, PGPU_CLL = 3, PGPU_REACT = 4, PGPU_AXIS = 5,
+       PGPU_PERIODIC_MASTER = 6, PGPU_PERIODIC_SLAVE = 7, PGPU_EMIT = 8, PGPU_WB_BC = 9 };
+/* field boundary conditions, src/global.f90:209-212 */
+enum { PGPU_DIRICHLET_BC = 0, PGPU_NEUMANN_BC = 1, PGPU_DIELECTRIC_BC = 2, PGPU_ROBIN_BC = 3,
+       PGPU_PERIODIC_MASTER_BC = 4, PGPU_PERIODIC_SLAVE_BC = 5, PGPU_RF_VOLTAGE_BC = 6,
+       PGPU_DECOUPLED_RF_VOLTAGE_BC = 7, PGPU_NO_BC = 8 };
+/* volume type of a physical group, src/global.f90:214-216 */
+enum { PGPU_FLUID = 0, PGPU_SOLID = 1 };
+/* PIC_TYPE, src/global.f90:302-305 (only NONE and EXPLICIT are on the hot path) */
+enum { PGPU_PIC_NONE = 0, PGPU_PIC_EXPLICIT = 1 };
+/* COLLISION_TYPE, src/global.f90:385-388 */
+enum { PGPU_NO_COLL = 0, PGPU_DSMC = 1, PGPU_BGK = 2, PGPU_MCC = 3, PGPU_MCC_VAHEDI = 4, PGPU_DSMC_VAHEDI = 5 };
+/* reaction TYPE, src/global.f90:538-540 */
+enum { PGPU_FIXED_RATE = 0, PGPU_TCE = 1, PGPU_LXCAT = 2 };
+/* PARTITION_STYLE, src/global.f90:108-111 */
+enum { PGPU_STRIPSX = 0, PGPU_STRIPSY = 1, PGPU_STRIPSZ = 2, PGPU_SLICESX = 3, PGPU_SLICESZ = 4 };
+
+/*
+ * Host particle record = TYPE PARTICLE_DATA_STRUCTURE (src/particle.f90:28-37) as gfortran
+ * lays it out (natural alignment, 96-byte stride).  Fields at byte offsets
+ * X 0, Y 8, Z 16, VX 24, VY 32, VZ 40, EROT 48, EVIB 56, DTRIM 64, IC 72, S_ID 76,
+ * ID 80, DUMP_TRAJ 88.  The upload/download calls take the stride explicitly so that a
+ * host compiled with a different padding can pass STORAGE_SIZE(particles(1))/8.
+ */
+typedef struct pgpu_particle {
+    double X, Y, Z;
+    double VX, VY, VZ;
+    double EROT, EVIB;
+    double DTRIM;
+    int32_t IC;
+    int32_t S_ID;
+    int64_t ID;
+    int32_t DUMP_TRAJ;
+    int32_t pad_;
+} pgpu_particle;
+
+/*
+ * Scalar globals read by the hot path (src/global.f90; input keywords in SURVEY.md App. D).
+ */
+typedef struct pgpu_config {
+    int32_t dims;             /* DIMS         global.f90, Dimensions:            */
+    int32_t axi;              /* AXI          Axisymmetric:                      */
+    int32_t grid_type;        /* GRID_TYPE                                        */
+    int32_t nx, ny;           /* NX, NY       Number_of_cells: (structured)      */
+    double xmin, xmax, ymin, ymax, zmin, zmax; /* Domain_limits:                  */
+    double dt;                /* DT           Timestep:                          */
+    double fnum;              /* FNUM         Fnum:                              */
+    int32_t pic_type;         /* PIC_TYPE                                         */
+    int32_t collision_type;   /* COLLISION_TYPE                                   */
+    int32_t bool_periodic[4]; /* BOOL_PERIODIC(1:4)  xmin,xmax,ymin,ymax sides    */
+    int32_t bool_specular[4]; /* BOOL_SPECULAR(1:4)                               */
+    int32_t bool_diffuse[4];  /* BOOL_DIFFUSE(1:4)                                */
+    int32_t bool_react[4];    /* BOOL_REACT(1:4)                                  */
+    int32_t bool_z_periodic;  /* BOOL_Z_PERIODIC                                  */
+    int32_t bool_y_periodic;  /* BOOL_Y_PERIODIC (DIMS==1 only)                   */
+    double boundtemp;         /* BOUNDTEMP    Boundary_temperature:              */
+    double external_b[3];     /* EXTERNAL_B_FIELD                                 */
+    double eps_scaling;       /* EPS_SCALING                                      */
+    double mcc_bg_dens;       /* MCC_BG_DENS                                      */
+    double mcc_bg_ttra;       /* MCC_BG_TTRA                                      */
+    int64_t rng_seed_global;  /* RNG_SEED_GLOBAL; local seed = seed*(rank+1)      */
+    int32_t rank, nranks;     /* PROC_ID, N_MPI_THREADS                           */
+    int32_t dump_bound_start; /* DUMP_BOUND_START     (tally gating)              */
+    int32_t dump_bound_avg_every; /* DUMP_BOUND_AVG_EVERY; <=0 disables tallies   */
+    int64_t capacity;         /* device particle capacity (0 = 1.5 x first upload)*/
+} pgpu_config;
+
+typedef struct pgpu_ctx pgpu_ctx;
+
+/* ---- life cycle ------------------------------------------------------------------------
+ * created between INITFIELDS and TIME_LOOP in PROGRAM PANTERA (src/pantera.f90:51-87). */
+int pgpu_create(pgpu_ctx** ctx, int device);
+int pgpu_destroy(pgpu_ctx* ctx);
+const char* pgpu_last_error(const pgpu_ctx* ctx);
+/* library/ABI version: major*1000+minor */
+int pgpu_version(void);
+
+/* ---- parameters (module globals the path reads) ---------------------------------------- */
+int pgpu_set_config(pgpu_ctx* ctx, const pgpu_config* cfg);
+
+/* SPECIES(:) -- src/global.f90:488-508: MOLECULAR_MASS, CHARGE, ROTDOF, VIBDOF, ROTREL, VIBREL */
+int pgpu_set_species(pgpu_ctx* ctx, int ns, const double* mass, const double* charge,
+                     const int32_t* rotdof, const int32_t* vibdof,
+                     const double* rotrel, const double* vibrel);
+
+/* VSS_SIGMAS/OMEGAS/ALPHAS/GREFS(NS,NS) and SIGMAMAX -- src/initialization.f90:675-702 */
+int pgpu_set_vss(pgpu_ctx* ctx, int ns, const double* sigmas, const double* omegas,
+                 const double* alphas, const double* grefs, double sigmamax);
+
+/* REACTIONS(:) -- src/global.f90:542-558; C1..C3 from INITREACTIONS (initialization.f90:2681-2724);
+ * LXCat tables concatenated, table of reaction r is tab_e/tab_cs[tab_off[r] .. tab_off[r+1]-1]. */
+int pgpu_set_reactions(pgpu_ctx* ctx, int nr, const int32_t* type,
+                       const int32_t* r1, const int32_t* r2,
+                       const int32_t* p1, const int32_t* p2, const int32_t* p3, const int32_t* p4,
+                       const int32_t* nprod, const int32_t* is_cex,
+                       const double* ea, const double* c1, const double* c2, const double* c3,
+                       const int32_t* tab_off, const double* tab_e, const double* tab_cs);
+
+/* WALL_REACTIONS(:) -- src/fields.f90:4315-4338 reads R_SP_ID, P1_SP_ID, N_PROD, PROB */
+int pgpu_set_wall_reactions(pgpu_ctx* ctx, int n, const int32_t* r_sp, const int32_t* p1_sp,
+                            const int32_t* nprod, const double* prob);
+
+/* MIXTURES(MCC_BG_MIX) components -- src/collisions.f90:1653-1657 */
+int pgpu_set_mcc_background(pgpu_ctx* ctx, int ncomp, const int32_t* sp_id, const double* molfrac);
+
+/* U1D/U2D/U3D_GRID -- src/global.f90:128-193, as computed by READ_*_SU2
+ * (src/grid_and_partition.f90:627-2147).  d = dims.  Shapes (Fortran order):
+ *   node_coords(3,nn) cell_nodes(d+1,nc) cell_neighbors(d+1,nc)
+ *   face_normal(3,d+1,nc) [EDGE_NORMAL in 1-D/2-D] face_tang1/2(3,4,nc) [3-D only, else NULL]
+ *   cell_edges_len(3,nc) [2-D only] cell_faces_pg(d+1,nc) [CELL_EDGES_PG in 1-D/2-D]
+ *   cell_pg(nc) basis_coeffs(d+1,d+1,nc) cell_volumes(nc) cell_procs(nc) [NULL = all 0]
+ *   face_boundary_index(d+1,nc) + boundary_area(nboundcells): boundary sub-mesh element of a
+ *   face and its area for TALLY_PARTICLE_TO_BOUNDARY (postprocess.f90:1098-1147); may be NULL. */
+int pgpu_set_mesh(pgpu_ctx* ctx, int dims, int nn, int nc,
+                  const double* node_coords, const int32_t* cell_nodes, const int32_t* cell_neighbors,
+                  const double* face_normal, const double* face_tang1, const double* face_tang2,
+                  const double* cell_edges_len, const int32_t* cell_faces_pg, const int32_t* cell_pg,
+                  const double* basis_coeffs, const double* cell_volumes, const int32_t* cell_procs,
+                  const int32_t* face_boundary_index, int nboundcells, const double* boundary_area);
+
+/* CELL_PROCS re-cut (load balance, src/timecycle.f90:185-189) */
+int pgpu_set_cell_procs(pgpu_ctx* ctx, int nc, const int32_t* cell_procs);
+
+/* GRID_BC(:) -- src/global.f90:218-253 */
+int pgpu_set_bcs(pgpu_ctx* ctx, int nbc, const int32_t* particle_bc, const int32_t* field_bc,
+                 const int32_t* volume_bc, const double* wall_temp, const double* acc_n,
+                 const double* acc_t, const int32_t* react, const int32_t* dump_fluxes);
+
+/* WALLS(:) interior segments of structured grids -- src/initialization.f90:996-1037 */
+int pgpu_set_walls(pgpu_ctx* ctx, int nw, const double* x1, const double* y1, const double* x2,
+                   const double* y2, const double* normx, const double* normy, const double* temp,
+                   const int32_t* specular, const int32_t* diffuse, const int32_t* porous,
+                   const double* transmissivity, const int32_t* react);
+
+/* XCOORD(NX+1), YCOORD(NY+1) of RECTILINEAR_NONUNIFORM grids -- initialization.f90:1939-2009 */
+int pgpu_set_grid_coords(pgpu_ctx* ctx, int nxp, const double* xcoord, int nyp, const double* ycoord);
+
+/* ---- particle store (particles(1:NP_PROC), src/global.f90:45-47) ----------------------- */
+int pgpu_upload_particles(pgpu_ctx* ctx, const void* aos, int64_t n, int32_t stride_bytes);
+int pgpu_download_particles(pgpu_ctx* ctx, void* aos, int64_t capacity, int64_t* n, int32_t stride_bytes);
+/* ADD_PARTICLE_ARRAY for host-side injection (src/particle.f90:86-136) */
+int pgpu_append_particles(pgpu_ctx* ctx, const void* aos, int64_t n, int32_t stride_bytes);
+int pgpu_num_particles(pgpu_ctx* ctx, int64_t* n);
+
+/* ---- fields ---------------------------------------------------------------------------- */
+/* E_FIELD: unstructured E_FIELD(3,1,NCELLS); structured E_FIELD(3,0:NPY-1,0:NPX-1)  (n doubles) */
+int pgpu_set_efield(pgpu_ctx* ctx, const double* e_field, int64_t n);
+/* B_FIELD(3,1,NNODES) (2-D unstructured nodal, src/fields.f90:4227-4249); NULL/0 clears */
+int pgpu_set_bfield(pgpu_ctx* ctx, const double* b_field, int64_t n);
+/* SURFACE_CHARGE(NNODES) read back / reset (dielectric walls, timecycle.f90:1399-1430) */
+int pgpu_get_surface_charge(pgpu_ctx* ctx, double* sc, int64_t n);
+int pgpu_set_surface_charge(pgpu_ctx* ctx, const double* sc, int64_t n);
+
+/* ---- the hot path ---------------------------------------------------------------------- */
+/* DEPOSIT_CHARGE particle loop + SURFACE_CHARGE + reduction over ranks (src/fields.f90:5440-5535).
+ * rhs_host(0:NNODES-1) receives the all-reduced RHS; the Dirichlet/Neumann row fill and the
+ * PETSc vector load (fields.f90:5538-5561) stay on the host. */
+int pgpu_deposit_charge(pgpu_ctx* ctx, double* rhs_host, int64_t nnodes);
+
+/* ADVECT (src/timecycle.f90:1021-2268): kick (Boris) + move + boundary conditions + removal +
+ * structured re-index.  tID = current timestep (tally gating and RNG stream). */
+int pgpu_advect(pgpu_ctx* ctx, int32_t tID);
+
+/* EXCHANGE (src/grid_and_partition.f90:525-622) over NCCL; no-op for nranks == 1 */
+int pgpu_exchange(pgpu_ctx* ctx);
+
+/* counting sort by cell of DSMC_COLLISIONS (src/collisions.f90:61-112), done as a physical
+ * SoA reorder.  Called implicitly by pgpu_collide when the store is not sorted. */
+int pgpu_sort(pgpu_ctx* ctx);
+
+/* DSMC_COLLISIONS -> VSS_COLLIS (src/collisions.f90:37-558); returns TIMESTEP_COLL/REAC */
+int pgpu_collide(pgpu_ctx* ctx, int32_t tID, int64_t* timestep_coll, int64_t* timestep_reac);
+
+/* MCC_COLLISIONS_VAHEDI (src/collisions.f90:1606-1892) */
+int pgpu_mcc_vahedi(pgpu_ctx* ctx, int32_t tID, int64_t* timestep_coll, int64_t* timestep_reac);
+
+/* REMOVE_PARTICLES_OF_SPECIES (src/timecycle.f90:2340-2353) */
+int pgpu_remove_species(pgpu_ctx* ctx, int32_t sp_id);
+
+/* nsteps x [ADVECT -> EXCHANGE -> DSMC_COLLISIONS] without returning to the host in between
+ * (the PIC_TYPE==NONE branch of TIME_LOOP, src/timecycle.f90:271-299).  First step uses tID0. */
+int pgpu_run_steps(pgpu_ctx* ctx, int32_t tID0, int32_t nsteps,
+                   int64_t* total_coll, int64_t* total_reac);
+
+/* ---- counters / diagnostics ------------------------------------------------------------ */
+/* BOUNDARY_COLL_COUNT(4*NS) and WALL_COLL_COUNT(NW*NS) of the last ADVECT (timecycle.f90:2138-2144) */
+int pgpu_get_boundary_counts(pgpu_ctx* ctx, int64_t* boundary_coll_count, int64_t nb,
+                             int64_t* wall_coll_count, int64_t nw);
+/* TIMESTEP_NIN/NOUT/PXIN.. tallies: 10 arrays x (nboundcells*ns), order
+ * NIN,NOUT,PXIN,PYIN,PZIN,PXOUT,PYOUT,PZOUT,EIN,EOUT (postprocess.f90:1098-1147) */
+int pgpu_get_boundary_tallies(pgpu_ctx* ctx, double* tallies, int64_t n, int32_t reset);
+/* per-cell particle counts NPCALL(1:NCELLS) of the last sort (collisions.f90:63-68) */
+int pgpu_get_cell_counts(pgpu_ctx* ctx, int32_t* npc, int64_t nc);
+/* device-side time [ms] of the kernels of the last hot-path call, by group:
+ * 0 move, 1 sort, 2 collide, 3 deposit, 4 exchange, 5 total; and launch count */
+int pgpu_get_timings(pgpu_ctx* ctx, double* ms, int32_t n, int64_t* launches);
+
+/* ---- multi-GPU plumbing (replaces MPI_COMM_WORLD for the path) ------------------------- */
+/* rank 0 obtains a 128-byte NCCL unique id and the host broadcasts it (MPI_BCAST / torch) */
+int pgpu_comm_unique_id(char id128[128]);
+int pgpu_comm_init(pgpu_ctx* ctx, int nranks, int rank, const char id128[128]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PANTERA_GPU_H */

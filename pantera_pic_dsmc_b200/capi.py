@@ -1,0 +1,460 @@
+"""ctypes binding of the C ABI declared in ``include/pantera_gpu.h``.
+
+The same binding class drives two shared libraries that export the same entry points under
+different prefixes:
+
+* ``libpantera_gpu.so``  (prefix ``pgpu_``) -- the product: hand-written CUDA for sm_100a.
+* ``oracle/_build/liboracle.so`` (prefix ``po_``) -- the CPU oracle, test infrastructure only.
+  It is never loaded from this module unless a test / bench baseline asks for it explicitly
+  through :func:`load_oracle`.
+
+There is no fallback between the two: :func:`load_gpu` raises if the CUDA library is missing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+REPO_ROOT = os.path.dirname(_HERE)
+GPU_LIB_PATH = os.path.join(_HERE, "csrc", "libpantera_gpu.so")
+ORACLE_LIB_PATH = os.path.join(REPO_ROOT, "oracle", "_build", "liboracle.so")
+
+# ---- enumerations (values of the reference's ENUM, BIND(C) blocks; see pantera_gpu.h) ----------
+RECTILINEAR_UNIFORM, RECTILINEAR_NONUNIFORM, QUADTREE, UNSTRUCTURED = 0, 1, 2, 3
+VACUUM, SPECULAR, DIFFUSE, CLL, REACT, AXIS, PERIODIC_MASTER, PERIODIC_SLAVE, EMIT, WB_BC = range(10)
+DIRICHLET_BC, NEUMANN_BC, DIELECTRIC_BC, ROBIN_BC = 0, 1, 2, 3
+NO_BC = 8
+FLUID, SOLID = 0, 1
+PIC_NONE, PIC_EXPLICIT = 0, 1
+NO_COLL, DSMC, BGK, MCC, MCC_VAHEDI, DSMC_VAHEDI = range(6)
+FIXED_RATE, TCE, LXCAT = 0, 1, 2
+
+# host particle record: TYPE PARTICLE_DATA_STRUCTURE, src/particle.f90:28-37 (96-byte stride)
+PARTICLE_DTYPE = np.dtype(
+    {
+        "names": ["X", "Y", "Z", "VX", "VY", "VZ", "EROT", "EVIB", "DTRIM", "IC", "S_ID", "ID", "DUMP_TRAJ"],
+        "formats": ["<f8"] * 9 + ["<i4", "<i4", "<i8", "<i4"],
+        "offsets": [0, 8, 16, 24, 32, 40, 48, 56, 64, 72, 76, 80, 88],
+        "itemsize": 96,
+    }
+)
+
+
+class Config(C.Structure):
+    """``pgpu_config`` -- scalar globals read by the hot path."""
+
+    _fields_ = [
+        ("dims", C.c_int32),
+        ("axi", C.c_int32),
+        ("grid_type", C.c_int32),
+        ("nx", C.c_int32),
+        ("ny", C.c_int32),
+        ("xmin", C.c_double),
+        ("xmax", C.c_double),
+        ("ymin", C.c_double),
+        ("ymax", C.c_double),
+        ("zmin", C.c_double),
+        ("zmax", C.c_double),
+        ("dt", C.c_double),
+        ("fnum", C.c_double),
+        ("pic_type", C.c_int32),
+        ("collision_type", C.c_int32),
+        ("bool_periodic", C.c_int32 * 4),
+        ("bool_specular", C.c_int32 * 4),
+        ("bool_diffuse", C.c_int32 * 4),
+        ("bool_react", C.c_int32 * 4),
+        ("bool_z_periodic", C.c_int32),
+        ("bool_y_periodic", C.c_int32),
+        ("boundtemp", C.c_double),
+        ("external_b", C.c_double * 3),
+        ("eps_scaling", C.c_double),
+        ("mcc_bg_dens", C.c_double),
+        ("mcc_bg_ttra", C.c_double),
+        ("rng_seed_global", C.c_int64),
+        ("rank", C.c_int32),
+        ("nranks", C.c_int32),
+        ("dump_bound_start", C.c_int32),
+        ("dump_bound_avg_every", C.c_int32),
+        ("capacity", C.c_int64),
+    ]
+
+
+def make_config(**kw) -> Config:
+    cfg = Config()
+    cfg.dims = 2
+    cfg.grid_type = RECTILINEAR_UNIFORM
+    cfg.nx = cfg.ny = 1
+    cfg.xmax = cfg.ymax = 1.0
+    cfg.zmin, cfg.zmax = -0.5, 0.5
+    cfg.dt = 1e-6
+    cfg.fnum = 1.0
+    cfg.boundtemp = 300.0
+    cfg.eps_scaling = 1.0
+    cfg.rng_seed_global = 65644  # the example input's seed (reference input:58)
+    cfg.nranks = 1
+    for k, v in kw.items():
+        if k in ("bool_periodic", "bool_specular", "bool_diffuse", "bool_react"):
+            arr = getattr(cfg, k)
+            for i, b in enumerate(v):
+                arr[i] = int(b)
+        elif k == "external_b":
+            for i, b in enumerate(v):
+                cfg.external_b[i] = float(b)
+        else:
+            if not hasattr(cfg, k):
+                raise KeyError(f"unknown config field {k}")
+            setattr(cfg, k, v)
+    return cfg
+
+
+class PanteraError(RuntimeError):
+    pass
+
+
+def _f64(a) -> Optional[np.ndarray]:
+    if a is None:
+        return None
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float64).ravel(order="K"))
+
+
+def _i32(a) -> Optional[np.ndarray]:
+    if a is None:
+        return None
+    return np.ascontiguousarray(np.asarray(a, dtype=np.int32).ravel(order="K"))
+
+
+def _fortran_flat(a, dtype) -> Optional[np.ndarray]:
+    """Flatten an array whose *numpy* shape is the Fortran shape, in Fortran (column-major) order."""
+    if a is None:
+        return None
+    return np.ascontiguousarray(np.asarray(a, dtype=dtype).ravel(order="F"))
+
+
+def _p(a: Optional[np.ndarray]):
+    if a is None:
+        return None
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Lib:
+    """One loaded library + one context; methods mirror the C entry points 1:1."""
+
+    def __init__(self, path: str, prefix: str, device: int = 0):
+        if not os.path.exists(path):
+            raise PanteraError(f"shared library not found: {path} (run `python -c 'import __graft_entry__ as g; g.build()'`)")
+        self.path = path
+        self.prefix = prefix
+        self.lib = C.CDLL(path, mode=C.RTLD_GLOBAL if prefix == "pgpu_" else C.RTLD_LOCAL)
+        self._keep = []
+        self.ctx = C.c_void_p()
+        f = self._fn("create")
+        f.restype = C.c_int
+        rc = f(C.byref(self.ctx), C.c_int(device))
+        if rc != 0:
+            raise PanteraError(f"{prefix}create failed with code {rc} (is a CUDA device visible?)")
+        self._fn("last_error").restype = C.c_char_p
+
+    # -- plumbing ---------------------------------------------------------------------------
+    def _fn(self, name):
+        return getattr(self.lib, self.prefix + name)
+
+    def _call(self, name, *args):
+        f = self._fn(name)
+        f.restype = C.c_int
+        rc = f(self.ctx, *args)
+        if rc != 0:
+            msg = self._fn("last_error")(self.ctx)
+            raise PanteraError(f"{self.prefix}{name} -> {rc}: {msg.decode() if msg else ''}")
+        return rc
+
+    def close(self):
+        if self.ctx:
+            self._fn("destroy")(self.ctx)
+            self.ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- parameters -------------------------------------------------------------------------
+    def set_config(self, cfg: Config):
+        self.cfg = cfg
+        self._call("set_config", C.byref(cfg))
+
+    def set_species(self, mass, charge, rotdof, vibdof, rotrel, vibrel):
+        mass = _f64(mass)
+        self.ns = len(mass)
+        self._call("set_species", C.c_int(self.ns), _p(mass), _p(_f64(charge)), _p(_i32(rotdof)),
+                   _p(_i32(vibdof)), _p(_f64(rotrel)), _p(_f64(vibrel)))
+
+    def set_vss(self, sigmas, omegas, alphas, grefs, sigmamax):
+        ns = self.ns
+        self._call("set_vss", C.c_int(ns), _p(_fortran_flat(sigmas, np.float64)), _p(_fortran_flat(omegas, np.float64)),
+                   _p(_fortran_flat(alphas, np.float64)), _p(_fortran_flat(grefs, np.float64)), C.c_double(sigmamax))
+
+    def set_reactions(self, reactions: Sequence[dict]):
+        nr = len(reactions)
+        if nr == 0:
+            self._call("set_reactions", C.c_int(0), *([None] * 16))
+            return
+        g = lambda k, d=0: [r.get(k, d) for r in reactions]
+        tab_off = [0]
+        tab_e, tab_cs = [], []
+        for r in reactions:
+            te = list(r.get("table_energy", []))
+            tab_e += te
+            tab_cs += list(r.get("table_cs", []))
+            tab_off.append(len(tab_e))
+        arrs = [_i32(g("type")), _i32(g("r1")), _i32(g("r2")), _i32(g("p1")), _i32(g("p2")), _i32(g("p3", -1)),
+                _i32(g("p4", -1)), _i32(g("nprod")), _i32(g("is_cex", 0)), _f64(g("ea", 0.0)), _f64(g("c1", 0.0)),
+                _f64(g("c2", 0.0)), _f64(g("c3", 0.0)), _i32(tab_off), _f64(tab_e if tab_e else [0.0]),
+                _f64(tab_cs if tab_cs else [0.0])]
+        self._call("set_reactions", C.c_int(nr), *[_p(a) for a in arrs])
+
+    def set_wall_reactions(self, r_sp, p1_sp, nprod, prob):
+        n = len(r_sp)
+        self._call("set_wall_reactions", C.c_int(n), _p(_i32(r_sp)), _p(_i32(p1_sp)), _p(_i32(nprod)), _p(_f64(prob)))
+
+    def set_mcc_background(self, sp_id, molfrac):
+        self._call("set_mcc_background", C.c_int(len(sp_id)), _p(_i32(sp_id)), _p(_f64(molfrac)))
+
+    def set_mesh(self, mesh):
+        """``mesh``: an object/dict with the Fortran-shaped arrays produced by ``meshgen``."""
+        m = mesh if isinstance(mesh, dict) else mesh.__dict__
+        d = int(m["dims"])
+        nn, nc = int(m["nn"]), int(m["nc"])
+        self.mesh = m
+        ff = _fortran_flat
+        bidx = m.get("face_boundary_index")
+        self._call(
+            "set_mesh", C.c_int(d), C.c_int(nn), C.c_int(nc),
+            _p(ff(m["node_coords"], np.float64)), _p(ff(m["cell_nodes"], np.int32)),
+            _p(ff(m["cell_neighbors"], np.int32)), _p(ff(m["face_normal"], np.float64)),
+            _p(ff(m.get("face_tang1"), np.float64)), _p(ff(m.get("face_tang2"), np.float64)),
+            _p(ff(m.get("cell_edges_len"), np.float64)), _p(ff(m["cell_faces_pg"], np.int32)),
+            _p(ff(m.get("cell_pg"), np.int32)), _p(ff(m.get("basis_coeffs"), np.float64)),
+            _p(ff(m["cell_volumes"], np.float64)), _p(ff(m.get("cell_procs"), np.int32)),
+            _p(ff(bidx, np.int32)), C.c_int(int(m.get("nboundcells", 0)) if bidx is not None else 0),
+            _p(ff(m.get("boundary_area"), np.float64)),
+        )
+
+    def set_cell_procs(self, cell_procs):
+        a = _i32(cell_procs)
+        self._call("set_cell_procs", C.c_int(len(a)), _p(a))
+
+    def set_bcs(self, particle_bc, field_bc=None, volume_bc=None, wall_temp=None, acc_n=None, acc_t=None,
+                react=None, dump_fluxes=None):
+        n = len(particle_bc)
+        z = lambda a, fill: a if a is not None else [fill] * n
+        self._call("set_bcs", C.c_int(n), _p(_i32(particle_bc)), _p(_i32(z(field_bc, NO_BC))),
+                   _p(_i32(z(volume_bc, FLUID))), _p(_f64(z(wall_temp, 300.0))), _p(_f64(z(acc_n, 1.0))),
+                   _p(_f64(z(acc_t, 1.0))), _p(_i32(z(react, 0))), _p(_i32(z(dump_fluxes, 0))))
+
+    def set_walls(self, x1, y1, x2, y2, normx, normy, temp, specular, diffuse, porous, transmissivity, react):
+        n = len(x1)
+        self._call("set_walls", C.c_int(n), _p(_f64(x1)), _p(_f64(y1)), _p(_f64(x2)), _p(_f64(y2)), _p(_f64(normx)),
+                   _p(_f64(normy)), _p(_f64(temp)), _p(_i32(specular)), _p(_i32(diffuse)), _p(_i32(porous)),
+                   _p(_f64(transmissivity)), _p(_i32(react)))
+
+    def set_grid_coords(self, xcoord, ycoord):
+        x, y = _f64(xcoord), _f64(ycoord)
+        self._call("set_grid_coords", C.c_int(len(x)), _p(x), C.c_int(len(y)), _p(y))
+
+    # -- particles --------------------------------------------------------------------------
+    def upload_particles(self, parts: np.ndarray):
+        assert parts.dtype == PARTICLE_DTYPE
+        parts = np.ascontiguousarray(parts)
+        self._call("upload_particles", _p(parts), C.c_int64(len(parts)), C.c_int32(96))
+
+    def append_particles(self, parts: np.ndarray):
+        assert parts.dtype == PARTICLE_DTYPE
+        parts = np.ascontiguousarray(parts)
+        self._call("append_particles", _p(parts), C.c_int64(len(parts)), C.c_int32(96))
+
+    def num_particles(self) -> int:
+        n = C.c_int64()
+        self._call("num_particles", C.byref(n))
+        return n.value
+
+    def download_particles(self) -> np.ndarray:
+        n = self.num_particles()
+        out = np.zeros(max(n, 1), dtype=PARTICLE_DTYPE)
+        nn = C.c_int64()
+        self._call("download_particles", _p(out), C.c_int64(len(out)), C.byref(nn), C.c_int32(96))
+        return out[: nn.value]
+
+    # -- fields -----------------------------------------------------------------------------
+    def set_efield(self, e):
+        a = _fortran_flat(e, np.float64)
+        self._call("set_efield", _p(a), C.c_int64(len(a)))
+
+    def set_bfield(self, b):
+        a = _fortran_flat(b, np.float64)
+        self._call("set_bfield", _p(a), C.c_int64(len(a)))
+
+    def get_surface_charge(self, n):
+        out = np.zeros(n)
+        self._call("get_surface_charge", _p(out), C.c_int64(n))
+        return out
+
+    def set_surface_charge(self, sc):
+        a = _f64(sc)
+        self._call("set_surface_charge", _p(a), C.c_int64(len(a)))
+
+    # -- hot path ---------------------------------------------------------------------------
+    def deposit_charge(self, nnodes) -> np.ndarray:
+        rhs = np.zeros(nnodes)
+        self._call("deposit_charge", _p(rhs), C.c_int64(nnodes))
+        return rhs
+
+    def advect(self, tID: int):
+        self._call("advect", C.c_int32(tID))
+
+    def exchange(self):
+        self._call("exchange")
+
+    def sort(self):
+        self._call("sort")
+
+    def collide(self, tID: int):
+        a, b = C.c_int64(), C.c_int64()
+        self._call("collide", C.c_int32(tID), C.byref(a), C.byref(b))
+        return a.value, b.value
+
+    def mcc_vahedi(self, tID: int):
+        a, b = C.c_int64(), C.c_int64()
+        self._call("mcc_vahedi", C.c_int32(tID), C.byref(a), C.byref(b))
+        return a.value, b.value
+
+    def remove_species(self, sp):
+        self._call("remove_species", C.c_int32(sp))
+
+    def run_steps(self, tID0: int, nsteps: int):
+        a, b = C.c_int64(), C.c_int64()
+        self._call("run_steps", C.c_int32(tID0), C.c_int32(nsteps), C.byref(a), C.byref(b))
+        return a.value, b.value
+
+    # -- diagnostics ------------------------------------------------------------------------
+    def get_boundary_counts(self, ns, nw=0):
+        b = np.zeros(4 * ns, dtype=np.int64)
+        w = np.zeros(max(nw * ns, 1), dtype=np.int64)
+        self._call("get_boundary_counts", _p(b), C.c_int64(len(b)), _p(w), C.c_int64(nw * ns))
+        return b, w[: nw * ns]
+
+    def get_boundary_tallies(self, nboundcells, ns, reset=False):
+        t = np.zeros(10 * nboundcells * ns)
+        self._call("get_boundary_tallies", _p(t), C.c_int64(len(t)), C.c_int32(int(reset)))
+        return t.reshape(10, ns, nboundcells)
+
+    def get_cell_counts(self, nc):
+        out = np.zeros(nc, dtype=np.int32)
+        self._call("get_cell_counts", _p(out), C.c_int64(nc))
+        return out
+
+
+class GpuLib(Lib):
+    def __init__(self, device: int = 0, path: str = GPU_LIB_PATH):
+        super().__init__(path, "pgpu_", device)
+
+    def get_timings(self):
+        ms = np.zeros(8)
+        n = C.c_int64()
+        self._call("get_timings", _p(ms), C.c_int32(8), C.byref(n))
+        return ms, n.value
+
+    def comm_unique_id(self) -> bytes:
+        buf = C.create_string_buffer(128)
+        f = self.lib.pgpu_comm_unique_id
+        f.restype = C.c_int
+        rc = f(buf)
+        if rc != 0:
+            raise PanteraError(f"pgpu_comm_unique_id -> {rc}")
+        return buf.raw
+
+    def comm_init(self, nranks: int, rank: int, uid: bytes):
+        buf = C.create_string_buffer(uid, 128)
+        self._call("comm_init", C.c_int(nranks), C.c_int(rank), buf)
+
+
+class OracleLib(Lib):
+    """CPU oracle (test infrastructure). rng_mode 0 = MT19937-64 (reference), 1 = Philox (device)."""
+
+    def __init__(self, rng_mode: int = 0, path: str = ORACLE_LIB_PATH):
+        super().__init__(path, "po_", 0)
+        self._call("set_rng_mode", C.c_int(rng_mode))
+
+    def set_rng_mode(self, mode):
+        self._call("set_rng_mode", C.c_int(mode))
+
+    def rf(self) -> float:
+        f = self.lib.po_rf
+        f.restype = C.c_double
+        return f(self.ctx)
+
+    def rng_stream(self, kind, tID, e0, e1=0):
+        self.lib.po_rng_stream(self.ctx, C.c_int(kind), C.c_int(tID), C.c_uint64(e0), C.c_uint64(e1))
+
+    def mt_next_u64(self) -> int:
+        f = self.lib.po_mt_next_u64
+        f.restype = C.c_uint64
+        return f(self.ctx)
+
+    def philox(self, ctr, key):
+        c = (C.c_uint32 * 4)(*ctr)
+        k = (C.c_uint32 * 2)(*key)
+        o = (C.c_uint32 * 4)()
+        self.lib.po_philox4x32_10(c, k, o)
+        return list(o)
+
+    def maxwell(self, u, t, m):
+        v = (C.c_double * 3)()
+        self.lib.po_maxwell(self.ctx, *[C.c_double(x) for x in u], *[C.c_double(x) for x in t], C.c_double(m), v)
+        return list(v)
+
+    def internal_energy(self, dof, temp):
+        f = self.lib.po_internal_energy
+        f.restype = C.c_double
+        return f(self.ctx, C.c_int(dof), C.c_double(temp))
+
+    def flx(self, sn, tinf, m):
+        f = self.lib.po_flx
+        f.restype = C.c_double
+        return f(self.ctx, C.c_double(sn), C.c_double(tinf), C.c_double(m))
+
+    def interp_cs(self, e, te, tcs):
+        f = self.lib.po_interp_cs
+        f.restype = C.c_double
+        te, tcs = _f64(te), _f64(tcs)
+        return f(C.c_double(e), C.c_int(len(te)), _p(te), _p(tcs))
+
+    def deposit_charge_compensated(self, nnodes):
+        rhs, ab = np.zeros(nnodes), np.zeros(nnodes)
+        self._call("deposit_charge_compensated", _p(rhs), _p(ab), C.c_int64(nnodes))
+        return rhs, ab
+
+    def exchange_pack(self, nranks):
+        n = self.num_particles()
+        buf = np.zeros(max(n, 1), dtype=PARTICLE_DTYPE)
+        cnt = np.zeros(nranks, dtype=np.int64)
+        self._call("exchange_pack", _p(buf), C.c_int64(len(buf)), _p(cnt))
+        return buf[: int(cnt.sum())], cnt
+
+    def get_timings(self):
+        s = np.zeros(3)
+        self._call("get_timings", _p(s), C.c_int32(3))
+        return s
+
+
+def load_gpu(device: int = 0) -> GpuLib:
+    """Load the CUDA library. Raises (never falls back) if it is missing or no GPU is usable."""
+    return GpuLib(device)
+
+
+def load_oracle(rng_mode: int = 0) -> OracleLib:
+    return OracleLib(rng_mode)

@@ -1,0 +1,197 @@
+"""Synthetic workloads (BASELINE.json configs C1..C5, concretised in SURVEY.md section 8d).
+
+A workload is a plain description (config struct, species table, mesh, boundary conditions,
+initial particles) that :func:`apply` pushes through the C ABI of either library (the CUDA
+product or the CPU oracle), in the order the Fortran host would: config, species, VSS,
+reactions, mesh, BCs, particles.
+"""
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+import numpy as np
+
+from . import capi, datafiles as df, meshgen as mg
+
+DATA_DIR = os.path.join(capi.REPO_ROOT, "tests", "data")
+KB = df.KB
+
+
+@dataclass
+class Workload:
+    name: str
+    cfg: capi.Config
+    species: df.SpeciesTable
+    particles: np.ndarray
+    mesh: Optional[mg.Mesh] = None
+    bcs: Optional[dict] = None
+    reactions: List[dict] = field(default_factory=list)
+    wall_reactions: Optional[dict] = None
+    walls: Optional[dict] = None
+    mcc_background: Optional[tuple] = None
+    efield: Optional[np.ndarray] = None
+    notes: str = ""
+
+
+def apply(lib: capi.Lib, w: Workload, upload: bool = True):
+    lib.set_config(w.cfg)
+    df.apply_species(lib, w.species)
+    if w.reactions:
+        lib.set_reactions(w.reactions)
+    if w.wall_reactions:
+        lib.set_wall_reactions(**w.wall_reactions)
+    if w.mcc_background:
+        lib.set_mcc_background(*w.mcc_background)
+    if w.mesh is not None:
+        lib.set_mesh(w.mesh)
+    if w.bcs:
+        lib.set_bcs(**w.bcs)
+    if w.walls:
+        lib.set_walls(**w.walls)
+    if w.efield is not None:
+        lib.set_efield(w.efield)
+    if upload:
+        lib.upload_particles(w.particles)
+    return lib
+
+
+def load_species(kind: str, names: Optional[List[str]] = None) -> df.SpeciesTable:
+    sp = df.read_species(os.path.join(DATA_DIR, f"{kind}.species"))
+    df.read_vss(os.path.join(DATA_DIR, f"{kind}.vss"), sp)
+    if names is not None:
+        sp = sp.subset(names)
+    return sp
+
+
+def maxwellian(rng: np.random.Generator, n: int, mass, T, u=(0.0, 0.0, 0.0)) -> np.ndarray:
+    """n velocities from a (possibly anisotropic) Maxwellian; mass scalar or (n,)."""
+    T = np.broadcast_to(np.asarray(T, dtype=np.float64), (3,))
+    sig = np.sqrt(KB * T[None, :] / np.asarray(mass, dtype=np.float64).reshape(-1, 1))
+    return rng.standard_normal((n, 3)) * sig + np.asarray(u)[None, :]
+
+
+def new_particles(n: int) -> np.ndarray:
+    p = np.zeros(n, dtype=capi.PARTICLE_DTYPE)
+    p["ID"] = np.arange(n, dtype=np.int64) << 8  # PROC_ID + ISHFT(counter, 8), src/particle.f90:75
+    return p
+
+
+def sample_in_tets(rng, mesh: mg.Mesh, cells0: np.ndarray) -> np.ndarray:
+    """Uniform points inside the given tets/triangles/segments (INITIAL_SEED's simplex sampling idea,
+    src/initialization.f90:2112-2148; order of draws is not part of the contract)."""
+    d = mesh.dims
+    cn = np.asarray(mesh.cell_nodes)[:, cells0] - 1  # (d+1, n)
+    P = np.asarray(mesh.node_coords)[:, cn]  # (3, d+1, n)
+    e = rng.exponential(size=(d + 1, cells0.size))
+    lam = e / e.sum(axis=0, keepdims=True)
+    return np.einsum("kvn,vn->nk", P, lam)
+
+
+# ------------------------------------------------------------------------------------------------
+# C1: 0-D/1-D argon heat-bath relaxation, VSS collisions only, structured grid, triply periodic
+# ------------------------------------------------------------------------------------------------
+def c1_argon_box(n: int = 100_000, nx: int = 1, ny: int = 1, seed: int = 1, T=(600.0, 300.0, 300.0),
+                 nrho: float = 1e20, dt_frac: float = 0.2, periodic=True, rng_seed_global: int = 65644) -> Workload:
+    sp = load_species("ar", ["Ar"])
+    m = sp.mass[0]
+    # equilibrium VSS collision frequency per molecule, T_eq = mean(T)
+    Teq = float(np.mean(T))
+    d, om, tref = sp.diam[0], sp.omega[0], sp.tref[0]
+    nu = 4.0 * d * d * nrho * np.sqrt(np.pi * KB * tref / m) * (Teq / tref) ** (1.0 - om)
+    dt = dt_frac / nu
+    vol = 1.0
+    fnum = nrho * vol / n
+    cfg = capi.make_config(dims=2, grid_type=capi.RECTILINEAR_UNIFORM, nx=nx, ny=ny, xmin=0.0, xmax=1.0, ymin=0.0,
+                           ymax=1.0, zmin=-0.5, zmax=0.5, dt=dt, fnum=fnum, collision_type=capi.DSMC,
+                           bool_periodic=[periodic] * 4, bool_specular=[not periodic] * 4, bool_z_periodic=1,
+                           rng_seed_global=rng_seed_global)
+    rng = np.random.default_rng(seed)
+    p = new_particles(n)
+    p["X"] = rng.random(n)
+    p["Y"] = rng.random(n)
+    p["Z"] = rng.random(n) - 0.5
+    v = maxwellian(rng, n, m, T)
+    p["VX"], p["VY"], p["VZ"] = v[:, 0], v[:, 1], v[:, 2]
+    p["DTRIM"] = dt
+    p["S_ID"] = 1
+    dx, dy = 1.0 / nx, 1.0 / ny
+    p["IC"] = (p["X"] / dx).astype(np.int32) + nx * (p["Y"] / dy).astype(np.int32) + 1
+    return Workload("C1 argon VSS box", cfg, sp, p, notes=f"nu_eq={nu:.6g} dt={dt:.6g}")
+
+
+# ------------------------------------------------------------------------------------------------
+# C5: 3-D unstructured (structured-to-tet) channel, argon, diffuse walls in y, specular in z and x
+# ------------------------------------------------------------------------------------------------
+def c5_channel(ncx: int = 8, ncy: int = 4, ncz: int = 4, ppc: float = 40.0, seed: int = 2, T0: float = 300.0,
+               nrho: float = 1e20, cell_mfp: float = 0.5, dt_frac: float = 0.2, u_drift: float = 100.0,
+               wall_bc=("specular", "specular", "diffuse", "diffuse", "specular", "specular"), wall_temp=400.0,
+               jitter: float = 0.0, rng_seed_global: int = 65644, collision_type=capi.DSMC,
+               n_override: Optional[int] = None) -> Workload:
+    """Box channel of ncx x ncy x ncz cubes (6 tets each).  Cube edge = cell_mfp mean free paths,
+    dt = dt_frac / nu_eq.  x end caps specular (constant-N run: unstructured grids have no particle-side
+    periodic BC in the reference, timecycle.f90:1611-1614), y walls diffuse at ``wall_temp``, z specular."""
+    sp = load_species("ar", ["Ar"])
+    m = sp.mass[0]
+    d, om, tref = sp.diam[0], sp.omega[0], sp.tref[0]
+    nu = 4.0 * d * d * nrho * np.sqrt(np.pi * KB * tref / m) * (T0 / tref) ** (1.0 - om)
+    cbar = np.sqrt(8.0 * KB * T0 / (np.pi * m))
+    mfp = cbar / nu
+    h = cell_mfp * mfp
+    hi = (ncx * h, ncy * h, ncz * h)
+    mesh = mg.box_tets(ncx, ncy, ncz, lo=(0.0, 0.0, 0.0), hi=hi, jitter=jitter, seed=seed)
+    nc = mesh.nc
+    n = int(n_override) if n_override is not None else int(round(ppc * nc))
+    vol = hi[0] * hi[1] * hi[2]
+    fnum = nrho * vol / n
+    dt = dt_frac / nu
+    cfg = capi.make_config(dims=3, grid_type=capi.UNSTRUCTURED, nx=1, ny=1, xmin=0.0, xmax=hi[0], ymin=0.0, ymax=hi[1],
+                           zmin=0.0, zmax=hi[2], dt=dt, fnum=fnum, collision_type=collision_type,
+                           rng_seed_global=rng_seed_global)
+    kinds = {"vacuum": capi.VACUUM, "specular": capi.SPECULAR, "diffuse": capi.DIFFUSE, "cll": capi.CLL}
+    bcs = dict(particle_bc=[kinds[k] for k in wall_bc], wall_temp=[wall_temp] * 6, acc_n=[0.8] * 6, acc_t=[0.8] * 6)
+    rng = np.random.default_rng(seed)
+    # particles: cells drawn with probability ~ volume, position uniform in the tet
+    cum = np.cumsum(mesh.cell_volumes)
+    cells0 = np.searchsorted(cum, rng.random(n) * cum[-1]).astype(np.int64)
+    cells0 = np.minimum(cells0, nc - 1)
+    xyz = sample_in_tets(rng, mesh, cells0)
+    p = new_particles(n)
+    p["X"], p["Y"], p["Z"] = xyz[:, 0], xyz[:, 1], xyz[:, 2]
+    v = maxwellian(rng, n, m, T0, u=(u_drift, 0.0, 0.0))
+    p["VX"], p["VY"], p["VZ"] = v[:, 0], v[:, 1], v[:, 2]
+    p["DTRIM"] = dt
+    p["S_ID"] = 1
+    p["IC"] = cells0 + 1
+    return Workload("C5 3-D tet channel", cfg, sp, p, mesh=mesh, bcs=bcs,
+                    notes=f"h={h:.4g} mfp={mfp:.4g} nu={nu:.5g} dt={dt:.4g} nc={nc}")
+
+
+# ------------------------------------------------------------------------------------------------
+# C2-like: air (N2/O2) with TCE + Borgnakke-Larsen in a periodic structured box (heat bath)
+# ------------------------------------------------------------------------------------------------
+def c2_air_box(n: int = 50_000, nx: int = 4, ny: int = 4, seed: int = 3, T: float = 8000.0, nrho: float = 1e21,
+               dt: float = 2e-7, species=("O2", "N2", "O", "N", "NO"), frac=(0.21, 0.79, 0.0, 0.0, 0.0),
+               with_reactions: bool = True, rng_seed_global: int = 65644) -> Workload:
+    sp = load_species("air", list(species))
+    reactions = df.read_reactions(os.path.join(DATA_DIR, "air.tce"), sp) if with_reactions else []
+    fnum = nrho * 1.0 / n
+    cfg = capi.make_config(dims=2, grid_type=capi.RECTILINEAR_UNIFORM, nx=nx, ny=ny, xmin=0.0, xmax=1.0, ymin=0.0,
+                           ymax=1.0, zmin=-0.5, zmax=0.5, dt=dt, fnum=fnum, collision_type=capi.DSMC,
+                           bool_periodic=[1] * 4, bool_z_periodic=1, rng_seed_global=rng_seed_global)
+    rng = np.random.default_rng(seed)
+    p = new_particles(n)
+    p["X"], p["Y"], p["Z"] = rng.random(n), rng.random(n), rng.random(n) - 0.5
+    sid = rng.choice(len(species), size=n, p=np.asarray(frac) / np.sum(frac)) + 1
+    mass = sp.mass[sid - 1]
+    v = maxwellian(rng, n, mass, T)
+    p["VX"], p["VY"], p["VZ"] = v[:, 0], v[:, 1], v[:, 2]
+    p["S_ID"] = sid
+    # internal energies at T: dof 2 -> exponential with mean kT
+    for name, dofs in (("EROT", sp.rotdof), ("EVIB", sp.vibdof)):
+        has = dofs[sid - 1] == 2
+        p[name][has] = rng.exponential(KB * T, size=int(has.sum()))
+    p["DTRIM"] = dt
+    p["IC"] = (p["X"] * nx).astype(np.int32) + nx * (p["Y"] * ny).astype(np.int32) + 1
+    return Workload("C2 air TCE/BL box", cfg, sp, p, reactions=reactions)
