@@ -104,6 +104,10 @@ typedef struct pgpu_config {
     int32_t dump_bound_start; /* DUMP_BOUND_START     (tally gating)              */
     int32_t dump_bound_avg_every; /* DUMP_BOUND_AVG_EVERY; <=0 disables tallies   */
     int64_t capacity;         /* device particle capacity (0 = 1.5 x first upload)*/
+    int32_t track_id;         /* 1: keep particles(:)%ID on the device (8 B/particle more, permuted
+                                 by the sort); 0: IDs are regenerated on download, as the reference
+                                 itself does on restart (src/tools.f90:465-517)                  */
+    int32_t reserved_;        /* must be 0                                        */
 } pgpu_config;
 
 typedef struct pgpu_ctx pgpu_ctx;

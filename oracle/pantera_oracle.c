@@ -287,6 +287,9 @@ double po_interp_cs(double e, int n, const double* te, const double* tcs) {
     if (e < TE(L)) return 0;
     if (e > TE(R)) return 0;
     if (R == L + 1) return TC(L) + (TC(R) - TC(L)) * (e - TE(L)) / (TE(R) - TE(L));
+    /* DEVIATION: for e == TE(R) exactly the reference's bisection loops forever (tools.f90:1574-1586);
+     * the table end value is returned instead (same in the CUDA path). */
+    if (e == TE(R)) return TC(R);
     for (;;) {
         idx = (L + R) / 2;
         if (TE(idx) <= e) {
@@ -313,6 +316,8 @@ static int binary_search(double value, const double* a, int n) {
 #define A(i) a[(i)-1]
     if (value < A(L) || value > A(R)) return -1;
     if (R == L + 1) return L;
+    /* DEVIATION: value == ARRAY(R) makes the reference loop forever (tools.f90:1518-1531); last cell returned */
+    if (value == A(R)) return R - 1;
     for (;;) {
         idx = (L + R) / 2;
         if (A(idx) <= value) {

@@ -80,6 +80,8 @@ class Config(C.Structure):
         ("dump_bound_start", C.c_int32),
         ("dump_bound_avg_every", C.c_int32),
         ("capacity", C.c_int64),
+        ("track_id", C.c_int32),
+        ("reserved_", C.c_int32),
     ]
 
 

@@ -1,0 +1,873 @@
+/*
+ * pgpu_advect.cu -- ADVECT on the device: Boris kick + free flight + boundary interaction +
+ * removal + structured re-index + per-cell histogram for the counting sort.
+ *
+ * Replaces: ADVECT (src/timecycle.f90:1021-2268), MOVE_PARTICLE (:2297-2332),
+ * UPDATE_VELOCITY_BORIS (:2271-2291), APPLY_E_FIELD / APPLY_B_FIELD (src/fields.f90:4194-4249),
+ * WALL_REACT (src/fields.f90:4302-4341), TALLY_PARTICLE_TO_BOUNDARY (src/postprocess.f90:1098-1147),
+ * CELL_FROM_POSITION (src/grid_and_partition.f90:34-96).
+ *
+ * Two passes over one kernel template:
+ *   LEAN  one thread per particle slot; free flight with neighbour hops (unstructured) or periodic
+ *         wraps (structured) only.  A particle that reaches any other boundary event is NOT written:
+ *         its slot goes to a compact hit list.  This pass is the HBM-bound bulk: 56 B read, 28 B
+ *         written per particle, mesh records served from L1/L2.
+ *   FULL  one thread per hit-list entry; redoes the particle from its start-of-step state with every
+ *         boundary model enabled (specular, Maxwell diffuse, CLL, wall reactions, porous walls,
+ *         dielectric charging, tallies).  Deterministic arithmetic makes the redo identical up to the
+ *         boundary, so LEAN+FULL == one sequential ADVECT.
+ * No FMA contraction (-fmad=false) and the reference's evaluation order are kept so that positions and
+ * cell indices match the CPU oracle bit for bit away from walls.
+ */
+#include "pgpu_internal.cuh"
+
+namespace {
+
+struct PState {
+    double x, y, z, vx, vy, vz, erot, evib, dtrim;
+    int ic, sid;
+};
+
+enum { DIRTY_V = 1, DIRTY_E = 2, DIRTY_S = 4 };
+
+/* ref: src/timecycle.f90:2297-2332 MOVE_PARTICLE */
+template <bool AXI>
+__device__ __forceinline__ void move_particle(PState& q, double time) {
+    if (AXI) {
+        q.x = q.x + q.vx * time;
+        q.z = 0.0;
+        double yy = q.y + q.vy * time;
+        double zz = q.vz * time;
+        double r = sqrt(yy * yy + zz * zz);
+        double sintheta = q.vz * time / r;
+        double costheta = copysign(sqrt(1. - sintheta * sintheta), yy);
+        q.y = r;
+        double vz = q.vz, vy = q.vy;
+        q.vz = costheta * vz - sintheta * vy;
+        q.vy = sintheta * vz + costheta * vy;
+    } else {
+        q.x = q.x + q.vx * time;
+        q.y = q.y + q.vy * time;
+        q.z = q.z + q.vz * time;
+    }
+}
+
+__device__ __forceinline__ void cross3(const double* a, const double* b, double* c) {
+    c[0] = a[1] * b[2] - a[2] * b[1];
+    c[1] = a[2] * b[0] - a[0] * b[2];
+    c[2] = a[0] * b[1] - a[1] * b[0];
+}
+
+/* NORM2 as gfortran expands it inline (scaled accumulation) -- used by the CLL tangent */
+__device__ __forceinline__ double norm2_3(const double* x) {
+    double result = 0.0, scale = 1.0;
+    for (int i = 0; i < 3; i++) {
+        if (x[i] != 0.0) {
+            double ax = fabs(x[i]);
+            if (scale < ax) {
+                double val = scale / ax;
+                result = 1.0 + result * val * val;
+                scale = ax;
+            } else {
+                double val = ax / scale;
+                result += val * val;
+            }
+        }
+    }
+    return scale * sqrt(result);
+}
+
+/* ref: src/fields.f90:5341-5431 COMPUTE_WEIGHTS (structured grids) */
+__device__ __forceinline__ void compute_weights(const PgDev& d, const PState& q, double* wt, int* indi, int* indj) {
+    int nx = d.nx;
+    int i = (q.ic - 1) % nx;
+    int j = (q.ic - 1) / nx;
+    double hx, hy, cxmin, cymin;
+    if (d.grid_type == PGPU_RECTILINEAR_UNIFORM) {
+        hx = (d.xmax - d.xmin) / (double)nx;
+        hy = (d.ymax - d.ymin) / (double)d.ny;
+        cxmin = i * hx + d.xmin;
+        cymin = j * hy + d.ymin;
+    } else {
+        hx = d.xcoord[i + 1] - d.xcoord[i];
+        hy = d.ycoord[j + 1] - d.ycoord[j];
+        cxmin = d.xcoord[i];
+        cymin = d.ycoord[j];
+    }
+    double fx = (q.x - cxmin) / hx;
+    double fy = (q.y - cymin) / hy;
+    if (d.dims == 2) {
+        indi[0] = i; indi[1] = i + 1; indi[2] = i; indi[3] = i + 1;
+        indj[0] = j; indj[1] = j; indj[2] = j + 1; indj[3] = j + 1;
+        wt[0] = (1. - fx) * (1. - fy);
+        wt[1] = fx * (1. - fy);
+        wt[2] = (1. - fx) * fy;
+        wt[3] = fx * fy;
+    } else {
+        indi[0] = i; indi[1] = i + 1; indi[2] = 0; indi[3] = 0;
+        indj[0] = 0; indj[1] = 0; indj[2] = 0; indj[3] = 0;
+        wt[0] = (1. - fx); wt[1] = fx; wt[2] = 0; wt[3] = 0;
+    }
+}
+
+/* ref: src/fields.f90:4194-4223 APPLY_E_FIELD */
+__device__ __forceinline__ void apply_e_field(const PgDev& d, const PState& q, double* e) {
+    if (!d.e_field) { e[0] = e[1] = e[2] = 0; return; }
+    if (d.grid_type == PGPU_UNSTRUCTURED) {
+        for (int k = 0; k < 3; k++) e[k] = __ldg(&d.e_field[3 * (size_t)(q.ic - 1) + k]);
+    } else {
+        double wt[4];
+        int indi[4], indj[4];
+        compute_weights(d, q, wt, indi, indj);
+        int npy = (d.dims == 2) ? d.ny + 1 : 1;
+#define EF(k, jj, ii) __ldg(&d.e_field[(k) + 3 * ((jj) + (size_t)npy * (ii))])
+        if (d.dims == 2) {
+            for (int k = 0; k < 3; k++)
+                e[k] = wt[0] * EF(k, indj[0], indi[0]) + wt[1] * EF(k, indj[1], indi[1]) +
+                       wt[2] * EF(k, indj[2], indi[2]) + wt[3] * EF(k, indj[3], indi[3]);
+        } else {
+            for (int k = 0; k < 3; k++) e[k] = wt[0] * EF(k, indj[0], indi[0]) + wt[1] * EF(k, indj[1], indi[1]);
+        }
+#undef EF
+    }
+}
+
+/* ref: src/fields.f90:4227-4249 APPLY_B_FIELD (2-D unstructured nodal interpolation) */
+__device__ __forceinline__ void apply_b_field(const PgDev& d, const PState& q, double* b) {
+    b[0] = b[1] = b[2] = 0.0;
+    if (d.grid_type == PGPU_UNSTRUCTURED && d.b_field && d.dims == 2) {
+        size_t c = (size_t)(q.ic - 1);
+        for (int j = 0; j < 3; j++) {
+            int vj = d.cell_nodes[3 * c + j];
+            const double* bs = d.basis + 9 * c + 3 * j;
+            double psij = q.x * bs[0] + q.y * bs[1] + bs[2];
+            for (int k = 0; k < 3; k++) b[k] = b[k] + d.b_field[3 * (size_t)(vj - 1) + k] * psij;
+        }
+    }
+}
+
+/* ref: src/timecycle.f90:2271-2291 UPDATE_VELOCITY_BORIS */
+__device__ __forceinline__ void boris(double dtime, PState& q, double charge, double mass, const double* e,
+                                      const double* b) {
+    double qc = charge * PG_QE;
+    double vo[3] = {q.vx, q.vy, q.vz};
+    double vm[3], t[3], vp[3], s[3], vpl[3], c[3];
+    for (int k = 0; k < 3; k++) vm[k] = vo[k] + 0.5 * qc * e[k] / mass * dtime;
+    for (int k = 0; k < 3; k++) t[k] = 0.5 * qc * b[k] / mass * dtime;
+    cross3(vm, t, c);
+    for (int k = 0; k < 3; k++) vp[k] = vm[k] + c[k];
+    double t2 = 1. + (t[0] * t[0] + t[1] * t[1] + t[2] * t[2]);
+    for (int k = 0; k < 3; k++) s[k] = 2. * t[k] / t2;
+    cross3(vp, s, c);
+    for (int k = 0; k < 3; k++) vpl[k] = vm[k] + c[k];
+    q.vx = vpl[0] + 0.5 * qc * e[0] / mass * dtime;
+    q.vy = vpl[1] + 0.5 * qc * e[1] / mass * dtime;
+    q.vz = vpl[2] + 0.5 * qc * e[2] / mass * dtime;
+}
+
+/* ref: src/fields.f90:4302-4341 WALL_REACT (no EXIT after a successful reaction) */
+__device__ void wall_react(const PgDev& d, PgRng& g, PState& q, int& remove, int& dirty) {
+    int js = q.sid;
+    double prob_scale = 1.;
+    remove = 0;
+    for (int jr = 0; jr < d.nwr; jr++) {
+        if (d.wr_r[jr] == js) {
+            if (g.rf() <= d.wr_prob[jr] / prob_scale) {
+                if (d.wr_nprod[jr] == 0) {
+                    remove = 1;
+                    q.dtrim = 0.;
+                } else if (d.wr_nprod[jr] == 1) {
+                    int jp = d.wr_p1[jr];
+                    q.sid = jp;
+                    double vel_scale = d.mass[js - 1] / d.mass[jp - 1];
+                    q.vx = q.vx * vel_scale;
+                    q.vy = q.vy * vel_scale;
+                    q.vz = q.vz * vel_scale;
+                    dirty |= DIRTY_V | DIRTY_S;
+                }
+            } else {
+                prob_scale = prob_scale - d.wr_prob[jr];
+            }
+        }
+    }
+}
+
+/* ref: src/postprocess.f90:1098-1147; layout [NIN,NOUT,PXIN,PYIN,PZIN,PXOUT,PYOUT,PZOUT,EIN,EOUT][s][b] */
+__device__ void tally(const PgDev& d, int reflected, const PState& q, int ic, int iface) {
+    if (!d.face_bidx || !d.tallies) return;
+    int b = d.face_bidx[(size_t)d.nf * (ic - 1) + iface];
+    if (b < 1) return;
+    size_t nbs = (size_t)d.nboundcells * d.ns;
+    size_t index = (size_t)(b - 1) + (size_t)(q.sid - 1) * d.nboundcells;
+    double area = d.bound_area[b - 1];
+    double molmass = d.mass[q.sid - 1];
+    double K = d.fnum * molmass / area / d.dt;
+    double* T = d.tallies;
+    double v2 = q.vx * q.vx + q.vy * q.vy + q.vz * q.vz;
+    if (reflected) {
+        atomicAdd(&T[1 * nbs + index], -(d.fnum / area / d.dt));
+        atomicAdd(&T[5 * nbs + index], -(K * q.vx));
+        atomicAdd(&T[6 * nbs + index], -(K * q.vy));
+        atomicAdd(&T[7 * nbs + index], -(K * q.vz));
+        atomicAdd(&T[9 * nbs + index], -(K * v2));
+    } else {
+        atomicAdd(&T[0 * nbs + index], d.fnum / area / d.dt);
+        atomicAdd(&T[2 * nbs + index], K * q.vx);
+        atomicAdd(&T[3 * nbs + index], K * q.vy);
+        atomicAdd(&T[4 * nbs + index], K * q.vz);
+        atomicAdd(&T[8 * nbs + index], K * v2);
+    }
+}
+
+/* ref: src/grid_and_partition.f90:34-96 CELL_FROM_POSITION; BINARY_SEARCH src/tools.f90:1499-1535 */
+__device__ __forceinline__ int binary_search(double value, const double* a, int n) {
+    int L = 1, R = n, idx;
+    if (value < a[L - 1] || value > a[R - 1]) return -1;
+    if (R == L + 1) return L;
+    /* DEVIATION: value == ARRAY(R) makes the reference loop forever (src/tools.f90:1518-1531) */
+    if (value == a[R - 1]) return R - 1;
+    for (;;) {
+        idx = (L + R) / 2;
+        if (a[idx - 1] <= value) {
+            if (a[idx] > value) return idx;
+            L = idx;
+        } else {
+            if (a[idx - 2] <= value) return idx - 1;
+            R = idx;
+        }
+    }
+}
+__device__ __forceinline__ int cell_from_position(const PgDev& d, double xp, double yp) {
+    if (d.grid_type == PGPU_RECTILINEAR_UNIFORM) {
+        double dx = (d.xmax - d.xmin) / d.nx;
+        double dy = (d.ymax - d.ymin) / d.ny;
+        int xcell = (int)((xp - d.xmin) / dx);
+        int ycell = (int)((yp - d.ymin) / dy);
+        return xcell + d.nx * ycell + 1;
+    } else {
+        int xcell = binary_search(xp, d.xcoord, d.nxp);
+        int ycell = binary_search(yp, d.ycoord, d.nyp);
+        if (xcell < 0 || ycell < 0) return -1;
+        return xcell + d.nx * (ycell - 1);
+    }
+}
+
+/* diffuse re-emission, structured flavour. ref: src/timecycle.f90:1915-1931, 1983-1999 */
+__device__ void diffuse_structured(const PgDev& d, PgRng& g, PState& q, double temp, double nxw, double nyw) {
+    int s = q.sid;
+    double v3[3];
+    pg_maxwell0(g, temp, d.mass[s - 1], v3);
+    double erot = pg_internal_energy(g, d.rotdof[s - 1], temp);
+    double evib = pg_internal_energy(g, d.vibdof[s - 1], temp);
+    double v_norm = pg_flx(g, 0., temp, d.mass[s - 1]);
+    q.vx = v_norm * nxw - v3[1] * nyw;
+    q.vy = v3[1] * nxw + v_norm * nyw;
+    q.vz = v3[2];
+    q.erot = erot;
+    q.evib = evib;
+}
+
+/* quadratic candidate solver of the axisymmetric variants (ref: :1190-1226, :1690-1712, :1793-1815) */
+__device__ int axi_roots(double coefa, double coefb, double coefc, double dtcoll, double tol, int use_radial_check,
+                         double beta, double alpha, double vx, double y1, double* test) {
+    double delta = coefb * coefb - coefa * coefc;
+    if (!(delta >= 0)) return 0;
+    double sol1 = (-coefb - sqrt(delta)) / coefa;
+    double sol2 = (-coefb + sqrt(delta)) / coefa;
+    int ok1 = (sol1 >= -tol && sol1 < dtcoll && (!use_radial_check || beta + alpha * vx * sol1 + y1 >= 0));
+    int ok2 = (sol2 >= -tol && sol2 < dtcoll && (!use_radial_check || beta + alpha * vx * sol2 + y1 >= 0));
+    if (ok1) {
+        if (ok2) {
+            if (sol1 <= sol2) { test[0] = sol1; test[1] = sol2; }
+            else { test[0] = sol2; test[1] = sol1; }
+            return 2;
+        }
+        test[0] = sol1;
+        return 1;
+    }
+    if (ok2) { test[0] = sol2; return 1; }
+    return 0;
+}
+
+/* boundary interaction on an unstructured grid. ref: src/timecycle.f90:1363-1647 */
+template <int DIMS>
+__device__ void boundary_unstructured(const PgDev& d, PgRng& g, PState& q, int ic, int iface, int code,
+                                      const double* nrm, int& remove, int& dirty) {
+    if (code == 0) { /* ref: :1644-1647 boundary without physical group */
+        remove = 1;
+        q.dtrim = 0.;
+        return;
+    }
+    int gi = -code - 1;
+    double fn[3] = {-nrm[0], -nrm[1], -nrm[2]};
+    if (d.tally_on) tally(d, 0, q, ic, iface);
+
+    /* dielectric surface charge, ref: :1399-1430 */
+    double charge = d.charge[q.sid - 1];
+    if (d.bc_field[gi] == PGPU_DIELECTRIC_BC && fabs(charge) >= 1.e-6 && d.surface_charge) {
+        double K = PG_QE / (PG_EPS0 * (d.eps_scaling * d.eps_scaling));
+        size_t c = (size_t)(ic - 1);
+        if (DIMS == 1) {
+            double rho_q = K * charge * d.fnum / (d.ymax - d.ymin) / (d.zmax - d.zmin);
+            for (int i = 0; i < 2; i++) {
+                int vp = d.cell_nodes[2 * c + i];
+                const double* bs = d.basis + 4 * c + 2 * i;
+                double psip = bs[0] * q.x + bs[1];
+                atomicAdd(&d.surface_charge[vp - 1], rho_q * psip);
+            }
+        } else if (DIMS == 2) {
+            double rho_q = K * charge * d.fnum / (d.zmax - d.zmin);
+            for (int i = 0; i < 3; i++) {
+                int vp = d.cell_nodes[3 * c + i];
+                const double* bs = d.basis + 9 * c + 3 * i;
+                double psip = bs[0] * q.x + bs[1] * q.y + bs[2];
+                atomicAdd(&d.surface_charge[vp - 1], rho_q * psip);
+            }
+        } else {
+            double rho_q = K * charge * d.fnum;
+            for (int i = 0; i < 4; i++) {
+                int vp = d.cell_nodes[4 * c + i];
+                const double* bs = d.basis + 16 * c + 4 * i;
+                double psip = bs[0] * q.x + bs[1] * q.y + bs[2] * q.z + bs[3];
+                atomicAdd(&d.surface_charge[vp - 1], rho_q * psip);
+            }
+        }
+    }
+
+    int pbc = d.bc_particle[gi];
+    if (pbc == PGPU_SPECULAR) {
+        /* ref: :1433-1443 */
+        if (d.bc_react[gi]) wall_react(d, g, q, remove, dirty);
+        double vdotn = q.vx * fn[0] + q.vy * fn[1] + q.vz * fn[2];
+        q.vx = q.vx - 2. * vdotn * fn[0];
+        q.vy = q.vy - 2. * vdotn * fn[1];
+        q.vz = q.vz - 2. * vdotn * fn[2];
+        dirty |= DIRTY_V;
+    } else if (pbc == PGPU_DIFFUSE) {
+        /* ref: :1445-1477 */
+        if (d.bc_react[gi]) wall_react(d, g, q, remove, dirty);
+        double ft1[3], ft2[3];
+        if (DIMS == 1) {
+            ft1[0] = 0.; ft1[1] = fn[0]; ft1[2] = 0.;
+            ft2[0] = 0.; ft2[1] = 0.; ft2[2] = 1.;
+        } else if (DIMS == 2) {
+            ft1[0] = -fn[1]; ft1[1] = fn[0]; ft1[2] = 0.;
+            ft2[0] = 0.; ft2[1] = 0.; ft2[2] = 1.;
+        } else {
+            size_t o = 3 * (4 * (size_t)(ic - 1) + iface);
+            for (int k = 0; k < 3; k++) {
+                ft1[k] = d.face_tang1[o + k];
+                ft2[k] = d.face_tang2[o + k];
+            }
+        }
+        int s = q.sid;
+        double wt = d.bc_temp[gi];
+        double v3[3];
+        pg_maxwell0(g, wt, d.mass[s - 1], v3);
+        double erot = pg_internal_energy(g, d.rotdof[s - 1], wt);
+        double evib = pg_internal_energy(g, d.vibdof[s - 1], wt);
+        double v_perp = pg_flx(g, 0., wt, d.mass[s - 1]);
+        q.vx = v_perp * fn[0] + v3[1] * ft1[0] + v3[2] * ft2[0];
+        q.vy = v_perp * fn[1] + v3[1] * ft1[1] + v3[2] * ft2[1];
+        q.vz = v_perp * fn[2] + v3[1] * ft1[2] + v3[2] * ft2[2];
+        q.erot = erot;
+        q.evib = evib;
+        dirty |= DIRTY_V | DIRTY_E;
+    } else if (pbc == PGPU_CLL) {
+        /* ref: :1485-1550 */
+        if (d.bc_react[gi]) wall_react(d, g, q, remove, dirty);
+        double vdotn = q.vx * fn[0] + q.vy * fn[1] + q.vz * fn[2];
+        double tg1[3], tg2[3];
+        tg1[0] = q.vx - vdotn * fn[0];
+        tg1[1] = q.vy - vdotn * fn[1];
+        tg1[2] = q.vz - vdotn * fn[2];
+        double nrm2 = norm2_3(tg1);
+        for (int k = 0; k < 3; k++) tg1[k] = tg1[k] / nrm2;
+        cross3(fn, tg1, tg2);
+        double vdott1 = q.vx * tg1[0] + q.vy * tg1[1] + q.vz * tg1[2];
+        int s = q.sid;
+        double wt = d.bc_temp[gi];
+        double accn = d.bc_accn[gi], acct = d.bc_acct[gi];
+        double vrm = sqrt(2. * PG_KB * wt / d.mass[s - 1]);
+        double rn = g.rf();
+        while (rn < 1.0e-13) rn = g.rf();
+        double r1 = sqrt(-accn * log(rn));
+        double theta1 = 2. * PG_PI * g.rf();
+        double dot_norm = vdotn / vrm * sqrt(1 - accn);
+        double v_perp = vrm * sqrt(r1 * r1 + dot_norm * dot_norm + 2. * r1 * dot_norm * cos(theta1));
+        rn = g.rf();
+        while (rn < 1.0e-13) rn = g.rf();
+        double r2 = sqrt(-acct * log(rn));
+        double theta2 = 2. * PG_PI * g.rf();
+        double vtangent = vdott1 / vrm * sqrt(1 - acct);
+        double v_tang1 = vrm * (vtangent + r2 * cos(theta2));
+        double v_tang2 = vrm * r2 * sin(theta2);
+        double erot = pg_internal_energy(g, d.rotdof[s - 1], wt);
+        double evib = pg_internal_energy(g, d.vibdof[s - 1], wt);
+        q.vx = v_perp * fn[0] + v_tang1 * tg1[0] + v_tang2 * tg2[0];
+        q.vy = v_perp * fn[1] + v_tang1 * tg1[1] + v_tang2 * tg2[1];
+        q.vz = v_perp * fn[2] + v_tang1 * tg1[2] + v_tang2 * tg2[2];
+        q.erot = erot;
+        q.evib = evib;
+        dirty |= DIRTY_V | DIRTY_E;
+    } else {
+        /* VACUUM, REACT, AXIS, PERIODIC_*, EMIT fall through to removal (ref: :1611-1614);
+         * WB_BC (washboard) is out of scope: its tables are not shipped with the reference. */
+        remove = 1;
+        q.dtrim = 0.;
+    }
+    if (!remove && d.tally_on) tally(d, 1, q, ic, iface);
+}
+
+/* One particle on an unstructured grid. ref: src/timecycle.f90:1166-1657.
+ * Returns false when LEAN and the particle must be deferred to the FULL pass. */
+template <int DIMS, bool AXI, bool LEAN>
+__device__ bool advect_unstructured(const PgDev& d, PgRng& g, PState& q, int& remove, int& dirty) {
+    constexpr int NF = DIMS + 1;
+    const double TOL = 1.0e-15;
+    int ic = q.ic;
+    int hops = 0;
+    while (q.dtrim > 0.) {
+        double dtcoll = q.dtrim;
+        int boundcoll = -1;
+        const double* geo = d.face_geo + (size_t)(ic - 1) * (NF * 6);
+        double nsel[3] = {0., 0., 0.};
+        if (AXI) {
+            /* ref: :1173-1253 */
+#pragma unroll 1
+            for (int i = 0; i < 3; i++) {
+                double test[2];
+                int goodsol;
+                double n1 = __ldg(&geo[6 * i + 0]), n2 = __ldg(&geo[6 * i + 1]);
+                double ex1 = __ldg(&geo[6 * i + 3]), ey1 = __ldg(&geo[6 * i + 4]);
+                if (fabs(n2) < 1.e-10) {
+                    double sol1 = (ex1 - q.x) / q.vx;
+                    if (sol1 >= 0 && sol1 < dtcoll) { goodsol = 1; test[0] = sol1; }
+                    else goodsol = 0;
+                } else {
+                    double alpha = -n1 / n2;
+                    double beta = (q.x - ex1) * alpha;
+                    double coefa = q.vy * q.vy + q.vz * q.vz - alpha * alpha * (q.vx * q.vx);
+                    double coefb = q.y * q.vy - (beta + ey1) * alpha * q.vx;
+                    double coefc = q.y * q.y - (beta + ey1) * (beta + ey1);
+                    goodsol = axi_roots(coefa, coefb, coefc, dtcoll, TOL, 1, beta, alpha, q.vx, ey1, test);
+                }
+                for (int s = 0; s < goodsol; s++) {
+                    move_particle<true>(q, test[s]);
+                    if ((q.vx * n1 + q.vy * n2) > 0) {
+                        double len = d.edge_len[3 * (size_t)(ic - 1) + i];
+                        double colldist = -n2 * (q.x - ex1) / len + n1 * (q.y - ey1) / len;
+                        if (colldist >= 0 && colldist <= 1) {
+                            dtcoll = test[s];
+                            boundcoll = i;
+                            nsel[0] = n1; nsel[1] = n2; nsel[2] = 0.;
+                        }
+                    }
+                    move_particle<true>(q, -test[s]);
+                }
+            }
+        } else {
+            /* ref: :1257-1305 sequential tightening, '>=' tie rule (last wins) */
+#pragma unroll
+            for (int i = 0; i < NF; i++) {
+                double vn, dx;
+                if (DIMS == 1) {
+                    double n1 = __ldg(&geo[6 * i + 0]);
+                    double p1 = __ldg(&geo[6 * i + 3]);
+                    vn = q.vx * n1;
+                    dx = (p1 - q.x) * n1;
+                    if (vn >= 0. && vn * dtcoll >= dx) {
+                        dtcoll = dx / vn; boundcoll = i;
+                        nsel[0] = n1; nsel[1] = 0.; nsel[2] = 0.;
+                    }
+                } else if (DIMS == 2) {
+                    double2 n12 = __ldg(reinterpret_cast<const double2*>(&geo[6 * i + 0]));
+                    double p1 = __ldg(&geo[6 * i + 3]), p2 = __ldg(&geo[6 * i + 4]);
+                    vn = q.vx * n12.x + q.vy * n12.y;
+                    dx = (p1 - q.x) * n12.x + (p2 - q.y) * n12.y;
+                    if (vn >= 0. && vn * dtcoll >= dx) {
+                        dtcoll = dx / vn; boundcoll = i;
+                        nsel[0] = n12.x; nsel[1] = n12.y; nsel[2] = 0.;
+                    }
+                } else {
+                    double2 a = __ldg(reinterpret_cast<const double2*>(&geo[6 * i + 0]));
+                    double2 b = __ldg(reinterpret_cast<const double2*>(&geo[6 * i + 2]));
+                    double2 c = __ldg(reinterpret_cast<const double2*>(&geo[6 * i + 4]));
+                    /* a = (nx,ny) b = (nz,px) c = (py,pz) */
+                    vn = q.vx * a.x + q.vy * a.y + q.vz * b.x;
+                    dx = (b.y - q.x) * a.x + (c.x - q.y) * a.y + (c.y - q.z) * b.x;
+                    if (vn >= 0. && vn * dtcoll >= dx) {
+                        dtcoll = dx / vn; boundcoll = i;
+                        nsel[0] = a.x; nsel[1] = a.y; nsel[2] = b.x;
+                    }
+                }
+            }
+        }
+
+        if (boundcoll != -1) {
+            int code = __ldg(&d.face_code[(size_t)(ic - 1) * NF + boundcoll]);
+            if (code > 0) {
+                /* ref: :1311-1312, :1648-1652 cell hop */
+                move_particle<AXI>(q, dtcoll);
+                q.dtrim = q.dtrim - dtcoll;
+                q.ic = code;
+                ic = code;
+                if (++hops > PG_MAX_HOPS) {
+                    pg_set_err(d, PG_DEVERR_HOPS);
+                    remove = 1;
+                    q.dtrim = 0.;
+                }
+            } else {
+                if (LEAN) return false;
+                move_particle<AXI>(q, dtcoll);
+                q.dtrim = q.dtrim - dtcoll;
+                if (AXI) dirty |= DIRTY_V; /* the axisymmetric move rotates the velocity */
+                boundary_unstructured<DIMS>(d, g, q, ic, boundcoll, code, nsel, remove, dirty);
+                if (++hops > PG_MAX_HOPS) {
+                    pg_set_err(d, PG_DEVERR_HOPS);
+                    remove = 1;
+                    q.dtrim = 0.;
+                }
+            }
+        } else {
+            /* ref: :1653-1657 */
+            move_particle<AXI>(q, q.dtrim);
+            q.dtrim = 0.;
+        }
+    }
+    if (AXI) dirty |= DIRTY_V;
+    return true;
+}
+
+/* One particle on a rectilinear grid. ref: src/timecycle.f90:1659-2015 */
+template <bool AXI, bool LEAN>
+__device__ bool advect_structured(const PgDev& d, PgRng& g, PState& q, int& remove, int& dirty, int* bhits) {
+    const double NORMX[4] = {1., -1., 0., 0.};
+    const double NORMY[4] = {0., 0., 1., -1.};
+    const double XW[4] = {d.xmin, d.xmax, d.xmin, d.xmax};
+    const double YW[4] = {d.ymax, d.ymin, d.ymin, d.ymax};
+    const double BOUNDPOS[4] = {d.xmin, d.xmax, d.ymin, d.ymax};
+    const int dims = d.dims;
+    int iters = 0;
+
+    while (q.dtrim > 0.) {
+        double dtcoll = q.dtrim;
+        int boundcoll = -1;
+        for (int i = 1; i <= 2 * dims; i++) {
+            if (AXI && dims == 2) {
+                /* ref: :1662-1729 */
+                double test[2];
+                int goodsol;
+                if (i == 1 || i == 2) {
+                    double sol1 = (BOUNDPOS[i - 1] - q.x) / q.vx;
+                    if (sol1 >= 0 && sol1 < dtcoll) { goodsol = 1; test[0] = sol1; }
+                    else goodsol = 0;
+                } else {
+                    double coefa = q.vy * q.vy + q.vz * q.vz;
+                    double coefb = q.y * q.vy;
+                    double coefc = q.y * q.y - BOUNDPOS[i - 1] * BOUNDPOS[i - 1];
+                    goodsol = axi_roots(coefa, coefb, coefc, dtcoll, 0.0, 0, 0, 0, 0, 0, test);
+                }
+                for (int s = 0; s < goodsol; s++) {
+                    move_particle<true>(q, test[s]);
+                    if ((q.vx * NORMX[i - 1] + q.vy * NORMY[i - 1]) < 0) {
+                        dtcoll = test[s];
+                        boundcoll = i;
+                    }
+                    move_particle<true>(q, -test[s]);
+                }
+            } else {
+                /* ref: :1733-1752 -- strict '>' here, unlike the unstructured faces */
+                double vn = -(q.vx * NORMX[i - 1] + q.vy * NORMY[i - 1]);
+                double dx = (q.x - XW[i - 1]) * NORMX[i - 1] + (q.y - YW[i - 1]) * NORMY[i - 1];
+                if (vn >= 0. && vn * dtcoll > dx) {
+                    dtcoll = dx / vn;
+                    boundcoll = i;
+                }
+            }
+        }
+
+        /* interior walls, ref: :1760-1865 */
+        int wallcoll = -1;
+        for (int i = 1; i <= d.nw; i++) {
+            int j = i - 1;
+            double wx1 = d.w_x1[j], wy1 = d.w_y1[j], wx2 = d.w_x2[j], wy2 = d.w_y2[j];
+            double wnx = d.w_nx[j], wny = d.w_ny[j];
+            if (AXI) {
+                double test[2];
+                int goodsol;
+                if (wx1 == wx2) {
+                    double sol1 = (wx1 - q.x) / q.vx;
+                    if (sol1 >= 0 && sol1 < dtcoll) { goodsol = 1; test[0] = sol1; }
+                    else goodsol = 0;
+                } else {
+                    double alpha = (wy2 - wy1) / (wx2 - wx1);
+                    double beta = (q.x - wx1) * alpha;
+                    double coefa = q.vy * q.vy + q.vz * q.vz - alpha * alpha * (q.vx * q.vx);
+                    double coefb = q.y * q.vy - (beta + wy1) * alpha * q.vx;
+                    double coefc = q.y * q.y - (beta + wy1) * (beta + wy1);
+                    goodsol = axi_roots(coefa, coefb, coefc, dtcoll, 0.0, 1, beta, alpha, q.vx, wy1, test);
+                }
+                for (int s = 0; s < goodsol; s++) {
+                    move_particle<true>(q, test[s]);
+                    if ((q.vx * wnx + q.vy * wny) < 0) {
+                        double ddx = wx2 - wx1, ddy = wy2 - wy1;
+                        double colldist = ((q.x - wx1) * ddx + (q.y - wy1) * ddy) / (ddx * ddx + ddy * ddy);
+                        if (colldist >= 0 && colldist <= 1) {
+                            dtcoll = test[s];
+                            boundcoll = -1;
+                            wallcoll = i;
+                        }
+                    }
+                    move_particle<true>(q, -test[s]);
+                }
+            } else {
+                double vn = -(q.vx * wnx + q.vy * wny);
+                double dx = (q.x - wx1) * wnx + (q.y - wy1) * wny;
+                if (dx >= 0. && vn * dtcoll >= dx) {
+                    double cand = dx / vn;
+                    double xcoll = q.x + q.vx * cand;
+                    double ycoll = q.y + q.vy * cand;
+                    double ddx = wx2 - wx1, ddy = wy2 - wy1;
+                    double colldist = ((xcoll - wx1) * ddx + (ycoll - wy1) * ddy) / (ddx * ddx + ddy * ddy);
+                    if (colldist >= 0 && colldist <= 1) {
+                        boundcoll = -1;
+                        wallcoll = i;
+                        dtcoll = cand;
+                    }
+                }
+            }
+        }
+
+        if (boundcoll != -1) {
+            /* ref: :1868-1939 */
+            int b = boundcoll - 1;
+            if (LEAN && !d.bper[b]) return false;
+            /* LOCAL_BOUNDARY_COLL_COUNT (ref: :1871-1872).  The LEAN pass may still defer the particle,
+             * so it counts locally and the caller commits once the particle is final. */
+            if (LEAN) bhits[b]++;
+            else atomicAdd(&d.bcount[b + 4 * (q.sid - 1)], 1ULL);
+            if (d.bper[b]) {
+                move_particle<AXI>(q, dtcoll);
+                switch (boundcoll) {
+                    case 1: q.x = q.x + d.xmax - d.xmin; break;
+                    case 2: q.x = q.x - d.xmax + d.xmin; break;
+                    case 3: q.y = q.y + d.ymax - d.ymin; break;
+                    case 4: q.y = q.y - d.ymax + d.ymin; break;
+                }
+                q.dtrim = q.dtrim - dtcoll;
+            } else if (d.bspec[b]) {
+                move_particle<AXI>(q, dtcoll);
+                if (boundcoll <= 2) q.vx = -q.vx;
+                else q.vy = -q.vy;
+                q.dtrim = q.dtrim - dtcoll;
+                dirty |= DIRTY_V;
+                if (d.breact[b]) wall_react(d, g, q, remove, dirty);
+            } else if (d.bdiff[b]) {
+                move_particle<AXI>(q, dtcoll);
+                q.dtrim = q.dtrim - dtcoll;
+                if (d.breact[b]) wall_react(d, g, q, remove, dirty);
+                if (!remove) {
+                    diffuse_structured(d, g, q, d.boundtemp, NORMX[b], NORMY[b]);
+                    dirty |= DIRTY_V | DIRTY_E;
+                }
+            } else {
+                remove = 1;
+                q.dtrim = 0.;
+            }
+        } else if (wallcoll != -1) {
+            /* ref: :1940-2008 */
+            if (LEAN) return false;
+            int j = wallcoll - 1;
+            atomicAdd(&d.wcount[j + (size_t)d.nw * (q.sid - 1)], 1ULL);
+            if (d.w_spec[j]) {
+                double rfp = g.rf();
+                if (d.w_porous[j] && rfp <= d.w_transm[j]) {
+                    remove = 1;
+                    q.dtrim = 0.;
+                } else {
+                    move_particle<AXI>(q, dtcoll);
+                    double vdotn = q.vx * d.w_nx[j] + q.vy * d.w_ny[j];
+                    q.vx = q.vx - 2. * vdotn * d.w_nx[j];
+                    q.vy = q.vy - 2. * vdotn * d.w_ny[j];
+                    q.dtrim = q.dtrim - dtcoll;
+                    dirty |= DIRTY_V;
+                    if (d.w_react[j]) wall_react(d, g, q, remove, dirty);
+                }
+            } else if (d.w_diff[j]) {
+                double rfp = g.rf();
+                if (d.w_porous[j] && rfp <= d.w_transm[j]) {
+                    remove = 1;
+                    q.dtrim = 0.;
+                } else {
+                    move_particle<AXI>(q, dtcoll);
+                    q.dtrim = q.dtrim - dtcoll;
+                    if (d.w_react[j]) wall_react(d, g, q, remove, dirty);
+                    if (!remove) {
+                        diffuse_structured(d, g, q, d.w_temp[j], d.w_nx[j], d.w_ny[j]);
+                        dirty |= DIRTY_V | DIRTY_E;
+                    }
+                }
+            } else {
+                remove = 1;
+                q.dtrim = 0.;
+            }
+        } else {
+            /* ref: :2010-2015 */
+            move_particle<AXI>(q, q.dtrim);
+            q.dtrim = 0.;
+        }
+        if (++iters > PG_MAX_HOPS) {
+            pg_set_err(d, PG_DEVERR_HOPS);
+            remove = 1;
+            q.dtrim = 0.;
+        }
+    }
+    if (AXI) dirty |= DIRTY_V;
+    return true;
+}
+
+/* MODE: 0 structured, 1/2/3 unstructured of that dimension */
+template <int MODE, bool AXI, bool LEAN>
+__global__ void __launch_bounds__(256) advect_kernel(const __grid_constant__ PgDev d, long long n) {
+    long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= n) return;
+    long long slot = LEAN ? tid : (long long)d.hitlist[tid];
+
+    PState q;
+    q.ic = d.p.ic[slot];
+    if (q.ic < 1) return; /* tombstone */
+    q.sid = d.p.sid[slot];
+    q.x = d.p.x[slot]; q.y = d.p.y[slot]; q.z = d.p.z[slot];
+    q.vx = d.p.vx[slot]; q.vy = d.p.vy[slot]; q.vz = d.p.vz[slot];
+    q.dtrim = d.p.dtrim ? d.p.dtrim[slot] : d.dt;
+    q.erot = 0.; q.evib = 0.;
+
+    PgRng g;
+    g.init(d.seed_local, 1, d.tID, (unsigned long long)slot, 0ULL);
+    int dirty = 0, remove = 0;
+
+    /* ref: src/timecycle.f90:1105-1131 kick at the start-of-step position/cell with the particle's DTRIM */
+    if (d.pic != PGPU_PIC_NONE) {
+        double e[3], b[3];
+        apply_e_field(d, q, e);
+        b[0] = b[1] = b[2] = 0.;
+        if (d.b_field) apply_b_field(d, q, b);
+        for (int k = 0; k < 3; k++) b[k] = b[k] + d.extb[k];
+        boris(q.dtrim, q, d.charge[q.sid - 1], d.mass[q.sid - 1], e, b);
+        dirty |= DIRTY_V;
+    }
+
+    bool done;
+    if constexpr (MODE == 0) {
+        int bhits[4] = {0, 0, 0, 0};
+        done = advect_structured<AXI, LEAN>(d, g, q, remove, dirty, bhits);
+        if (LEAN && done) { /* the species cannot change in the LEAN pass */
+            for (int b = 0; b < 4; b++)
+                if (bhits[b]) atomicAdd(&d.bcount[b + 4 * (q.sid - 1)], (unsigned long long)bhits[b]);
+        }
+    } else {
+        done = advect_unstructured<MODE, AXI, LEAN>(d, g, q, remove, dirty);
+    }
+    if (LEAN && !done) {
+        unsigned long long k = atomicAdd(&d.status->n_hits, 1ULL);
+        d.hitlist[k] = (unsigned int)slot;
+        return;
+    }
+
+    if (remove) {
+        d.p.ic[slot] = PG_TOMBSTONE;
+        atomicAdd(&d.status->n_removed, 1ULL);
+        return;
+    }
+
+    /* ref: :2048-2068 */
+    if (d.zper) {
+        while (q.z > d.zmax) q.z = d.zmin + (q.z - d.zmax);
+        while (q.z < d.zmin) q.z = d.zmax + (q.z - d.zmin);
+    }
+    if (d.dims == 1 && d.yper) {
+        while (q.y > d.ymax) q.y = d.ymin + (q.y - d.ymax);
+        while (q.y < d.ymin) q.y = d.ymax + (q.y - d.ymin);
+    }
+
+    /* ref: :2105-2108 structured grids are re-indexed from the final position */
+    if (MODE == 0) q.ic = cell_from_position(d, q.x, q.y);
+    if (q.ic < 1 || q.ic > d.ncells) {
+        pg_set_err(d, PG_DEVERR_CELL_RANGE);
+        d.p.ic[slot] = PG_TOMBSTONE;
+        atomicAdd(&d.status->n_removed, 1ULL);
+        return;
+    }
+
+    d.p.x[slot] = q.x; d.p.y[slot] = q.y; d.p.z[slot] = q.z;
+    d.p.ic[slot] = q.ic;
+    if (dirty & DIRTY_V) { d.p.vx[slot] = q.vx; d.p.vy[slot] = q.vy; d.p.vz[slot] = q.vz; }
+    if (dirty & DIRTY_E) { d.p.erot[slot] = q.erot; d.p.evib[slot] = q.evib; }
+    if (dirty & DIRTY_S) d.p.sid[slot] = q.sid;
+
+    /* histogram + arrival rank for the counting sort (K3/K5 of SURVEY 2.3), warp-aggregated */
+    unsigned int mask = __match_any_sync(__activemask(), q.ic);
+    int leader = __ffs(mask) - 1;
+    int lane = threadIdx.x & 31;
+    unsigned int base = 0;
+    if (lane == leader) base = atomicAdd(&d.cell_count[q.ic - 1], (unsigned int)__popc(mask));
+    base = __shfl_sync(mask, base, leader);
+    d.cell_rank[slot] = base + __popc(mask & ((1u << lane) - 1u));
+}
+
+template <bool LEAN>
+int launch_advect(pgpu_ctx* c, long long n) {
+    if (n <= 0) return PGPU_OK;
+    const PgDev& d = c->dev;
+    unsigned int blocks = (unsigned int)((n + 255) / 256);
+    bool axi = d.axi != 0;
+    if (d.grid_type != PGPU_UNSTRUCTURED) {
+        if (axi) advect_kernel<0, true, LEAN><<<blocks, 256, 0, c->stream>>>(d, n);
+        else advect_kernel<0, false, LEAN><<<blocks, 256, 0, c->stream>>>(d, n);
+    } else if (d.dims == 1) {
+        advect_kernel<1, false, LEAN><<<blocks, 256, 0, c->stream>>>(d, n);
+    } else if (d.dims == 2) {
+        if (axi) advect_kernel<2, true, LEAN><<<blocks, 256, 0, c->stream>>>(d, n);
+        else advect_kernel<2, false, LEAN><<<blocks, 256, 0, c->stream>>>(d, n);
+    } else {
+        advect_kernel<3, false, LEAN><<<blocks, 256, 0, c->stream>>>(d, n);
+    }
+    c->launches++;
+    PG_CUDA(c, cudaGetLastError());
+    return PGPU_OK;
+}
+
+} /* namespace */
+
+/*
+ * ADVECT for all slots [0, np).  Asynchronous except for one read-back of the hit-list length
+ * between the LEAN and the FULL pass.
+ */
+int pg_advect_impl(pgpu_ctx* c, int tID) {
+    int rc;
+    c->dev.tID = tID;
+    c->dev.tally_on = 0;
+    if (c->cfg.dump_bound_avg_every > 0 && c->dev.tallies)
+        c->dev.tally_on = ((tID - c->cfg.dump_bound_start) % c->cfg.dump_bound_avg_every) == 0;
+    if (c->np == 0) return PGPU_OK;
+
+    /* zero the per-call counters and the histogram */
+    PG_CUDA(c, cudaMemsetAsync(c->d_cell_count, 0, sizeof(unsigned int) * (size_t)pg_ncells(c), c->stream));
+    PG_CUDA(c, cudaMemsetAsync(c->d_bcount, 0, sizeof(unsigned long long) * 4 * (size_t)c->ns, c->stream));
+    if (c->nw) PG_CUDA(c, cudaMemsetAsync(c->d_wcount, 0, sizeof(unsigned long long) * (size_t)(c->nw * c->ns), c->stream));
+
+    if ((rc = launch_advect<true>(c, c->np))) return rc;
+    /* hit-list length -> host (the only sync inside ADVECT) */
+    PG_CUDA(c, cudaMemcpyAsync(&c->h_status->n_hits, &c->d_status->n_hits, sizeof(unsigned long long),
+                               cudaMemcpyDeviceToHost, c->stream));
+    PG_CUDA(c, cudaStreamSynchronize(c->stream));
+    long long nh = (long long)c->h_status->n_hits;
+    if (nh > 0 && (rc = launch_advect<false>(c, nh))) return rc;
+
+    c->has_dtrim = false; /* DTRIM = DT for every particle after ADVECT, ref: src/timecycle.f90:2070 */
+    c->sorted = false;
+    c->hist_valid = true;
+    c->maybe_tombstones = true;
+    return PGPU_OK;
+}

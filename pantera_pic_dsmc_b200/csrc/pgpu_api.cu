@@ -1,0 +1,1092 @@
+/*
+ * pgpu_api.cu -- C ABI of libpantera_gpu.so (include/pantera_gpu.h): context life cycle, parameter
+ * setters (the module globals of src/global.f90 the hot path reads), the device particle store
+ * (AoS <-> SoA transposition of TYPE PARTICLE_DATA_STRUCTURE, src/particle.f90:28-37), the counting
+ * sort of DSMC_COLLISIONS (src/collisions.f90:61-112) as a physical SoA reorder, and the per-step
+ * driver that replays the PIC_TYPE==NONE branch of TIME_LOOP (src/timecycle.f90:271-299).
+ *
+ * There is no CPU fallback anywhere in this library: every entry point that computes needs a CUDA
+ * device and fails with PGPU_ERR_CUDA otherwise.
+ */
+#include <cub/device/device_scan.cuh>
+
+#include <algorithm>
+#include <new>
+
+#include "pgpu_internal.cuh"
+
+/* named device-table slots */
+enum {
+    S_MASS, S_CHARGE, S_ROTREL, S_VIBREL, S_ROTDOF, S_VIBDOF,
+    S_SIGMAS, S_OMEGAS, S_ALPHAS, S_GREFS,
+    S_REAC, S_TAB_E, S_TAB_CS,
+    S_WR_R, S_WR_P1, S_WR_NPROD, S_WR_PROB,
+    S_MCC_SP, S_MCC_FRAC,
+    S_FACE_GEO, S_FACE_CODE, S_TANG1, S_TANG2, S_EDGE_LEN, S_FACE_BIDX, S_BOUND_AREA, S_CELL_NODES, S_BASIS,
+    S_CELL_VOL, S_CELL_PROCS,
+    S_BC_PARTICLE, S_BC_FIELD, S_BC_REACT, S_BC_TEMP, S_BC_ACCN, S_BC_ACCT,
+    S_W_X1, S_W_Y1, S_W_X2, S_W_Y2, S_W_NX, S_W_NY, S_W_TEMP, S_W_TRANSM, S_W_SPEC, S_W_DIFF, S_W_POROUS, S_W_REACT,
+    S_XCOORD, S_YCOORD, S_EFIELD, S_BFIELD,
+    S_COUNT
+};
+static_assert(S_COUNT <= 64, "slot table too small");
+
+static thread_local char g_create_err[256] = "";
+
+/* replace the device array held in a slot by a copy of host[0..n) */
+template <class T>
+static int put(pgpu_ctx* c, int slot, const T* host, size_t n, const T** out) {
+    if (c->slot[slot]) {
+        cudaFree(c->slot[slot]);
+        c->slot[slot] = nullptr;
+    }
+    *out = nullptr;
+    if (!host || n == 0) return PGPU_OK;
+    void* p = nullptr;
+    PG_CUDA(c, cudaMalloc(&p, sizeof(T) * n));
+    PG_CUDA(c, cudaMemcpy(p, host, sizeof(T) * n, cudaMemcpyHostToDevice));
+    c->slot[slot] = p;
+    *out = (const T*)p;
+    return PGPU_OK;
+}
+
+template <class T>
+static int dev_alloc(pgpu_ctx* c, T** p, size_t n) {
+    *p = nullptr;
+    if (n == 0) n = 1;
+    PG_CUDA(c, cudaMalloc((void**)p, sizeof(T) * n));
+    return PGPU_OK;
+}
+template <class T>
+static void dev_free(T*& p) {
+    if (p) cudaFree((void*)p);
+    p = nullptr;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * life cycle
+ * ---------------------------------------------------------------------------------------- */
+extern "C" int pgpu_version(void) { return 1000; }
+
+extern "C" int pgpu_create(pgpu_ctx** out, int device) {
+    if (!out) return PGPU_ERR_INVALID;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        snprintf(g_create_err, sizeof(g_create_err), "no usable CUDA device (%s); this library has no CPU fallback",
+                 cudaGetErrorString(e));
+        return PGPU_ERR_CUDA;
+    }
+    if (device < 0 || device >= ndev) return PGPU_ERR_INVALID;
+    if (cudaSetDevice(device) != cudaSuccess) return PGPU_ERR_CUDA;
+    pgpu_ctx* c = new (std::nothrow) pgpu_ctx();
+    if (!c) return PGPU_ERR_INVALID;
+    c->err[0] = 0;
+    c->device = device;
+    c->cfg_set = false;
+    memset(&c->cfg, 0, sizeof(c->cfg));
+    memset(&c->dev, 0, sizeof(c->dev));
+    memset(c->slot, 0, sizeof(c->slot));
+    memset(c->planes, 0, sizeof(c->planes));
+    c->mesh_dims = 0; c->nn = 0; c->nc = 0;
+    c->mesh_set = false; c->mesh_dirty = false;
+    c->cur = 0; c->np = 0; c->capacity = 0;
+    c->has_dtrim = false; c->sorted = false; c->hist_valid = false; c->maybe_tombstones = false;
+    c->id_counter = 0;
+    c->d_cell_count = c->d_rank = c->d_cell_off = c->d_hitlist = nullptr;
+    c->hit_capacity = 0; c->ncells_alloc = 0;
+    c->d_status = nullptr; c->h_status = nullptr;
+    c->d_scan_tmp = nullptr; c->scan_tmp_bytes = 0;
+    c->d_cand = nullptr; c->cand_capacity = 0;
+    c->d_owner = nullptr; c->owner_capacity = 0;
+    c->d_cell_ncoll = nullptr; c->d_cand_off = nullptr; c->d_cell_vrmax = nullptr; c->d_cell_fcorr = nullptr;
+    c->cellscratch_alloc = 0;
+    c->d_stage[0] = c->d_stage[1] = nullptr; c->stage_bytes = 0;
+    c->h_stage[0] = c->h_stage[1] = nullptr;
+    c->d_rhs = nullptr; c->rhs_n = 0;
+    c->ns = 0; c->nw = 0;
+    c->d_bcount = c->d_wcount = nullptr;
+    c->d_tallies = nullptr; c->tallies_n = 0;
+    c->d_surface_charge = nullptr; c->nsc = 0;
+    memset(c->ms, 0, sizeof(c->ms));
+    c->launches = 0;
+    c->nccl_lib = nullptr; c->nccl_comm = nullptr; c->comm_nranks = 1; c->comm_rank = 0;
+    c->d_sendbuf = c->d_recvbuf = nullptr; c->xbuf_capacity = 0; c->d_xcount = nullptr;
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return PGPU_ERR_CUDA; }
+    for (int i = 0; i < 16; i++) cudaEventCreate(&c->ev[i]);
+    if (cudaMalloc((void**)&c->d_status, sizeof(PgStatus)) != cudaSuccess ||
+        cudaMallocHost((void**)&c->h_status, sizeof(PgStatus)) != cudaSuccess) {
+        delete c;
+        return PGPU_ERR_CUDA;
+    }
+    cudaMemset(c->d_status, 0, sizeof(PgStatus));
+    memset(c->h_status, 0, sizeof(PgStatus));
+    c->cfg.nranks = 1;
+    c->cfg.eps_scaling = 1.0;
+    *out = c;
+    return PGPU_OK;
+}
+
+static void free_planes(PgPlanes& p) {
+    dev_free(p.x); dev_free(p.y); dev_free(p.z); dev_free(p.vx); dev_free(p.vy); dev_free(p.vz);
+    dev_free(p.erot); dev_free(p.evib); dev_free(p.ic); dev_free(p.sid); dev_free(p.dtrim); dev_free(p.id);
+}
+
+extern "C" void pg_comm_destroy(pgpu_ctx* c); /* pgpu_exchange.cu */
+
+extern "C" int pgpu_destroy(pgpu_ctx* c) {
+    if (!c) return PGPU_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    pg_comm_destroy(c);
+    for (int i = 0; i < S_COUNT; i++)
+        if (c->slot[i]) cudaFree(c->slot[i]);
+    free_planes(c->planes[0]);
+    free_planes(c->planes[1]);
+    dev_free(c->d_cell_count); dev_free(c->d_rank); dev_free(c->d_cell_off); dev_free(c->d_hitlist);
+    dev_free(c->d_status);
+    if (c->h_status) cudaFreeHost(c->h_status);
+    dev_free(c->d_scan_tmp); dev_free(c->d_cand); dev_free(c->d_owner);
+    dev_free(c->d_cell_ncoll); dev_free(c->d_cand_off); dev_free(c->d_cell_vrmax); dev_free(c->d_cell_fcorr);
+    for (int i = 0; i < 2; i++) {
+        dev_free(c->d_stage[i]);
+        if (c->h_stage[i]) cudaFreeHost(c->h_stage[i]);
+    }
+    dev_free(c->d_rhs); dev_free(c->d_bcount); dev_free(c->d_wcount); dev_free(c->d_tallies);
+    dev_free(c->d_surface_charge);
+    dev_free(c->d_sendbuf); dev_free(c->d_recvbuf); dev_free(c->d_xcount);
+    for (int i = 0; i < 16; i++) cudaEventDestroy(c->ev[i]);
+    cudaStreamDestroy(c->stream);
+    delete c;
+    return PGPU_OK;
+}
+
+extern "C" const char* pgpu_last_error(const pgpu_ctx* c) { return c ? c->err : g_create_err; }
+
+/* ------------------------------------------------------------------------------------------
+ * parameters
+ * ---------------------------------------------------------------------------------------- */
+static int alloc_counters(pgpu_ctx* c) {
+    dev_free(c->d_bcount);
+    dev_free(c->d_wcount);
+    dev_free(c->d_tallies);
+    size_t ns = c->ns > 0 ? (size_t)c->ns : 1;
+    int rc;
+    if ((rc = dev_alloc(c, &c->d_bcount, 4 * ns))) return rc;
+    if ((rc = dev_alloc(c, &c->d_wcount, (size_t)(c->nw > 0 ? c->nw : 1) * ns))) return rc;
+    PG_CUDA(c, cudaMemset(c->d_bcount, 0, sizeof(unsigned long long) * 4 * ns));
+    PG_CUDA(c, cudaMemset(c->d_wcount, 0, sizeof(unsigned long long) * (size_t)(c->nw > 0 ? c->nw : 1) * ns));
+    c->tallies_n = 0;
+    if (c->dev.nboundcells > 0 && c->ns > 0) {
+        c->tallies_n = (long long)10 * c->dev.nboundcells * c->ns;
+        if ((rc = dev_alloc(c, &c->d_tallies, (size_t)c->tallies_n))) return rc;
+        PG_CUDA(c, cudaMemset(c->d_tallies, 0, sizeof(double) * (size_t)c->tallies_n));
+    }
+    return PGPU_OK;
+}
+
+extern "C" int pgpu_set_config(pgpu_ctx* c, const pgpu_config* cfg) {
+    if (!c || !cfg) return PGPU_ERR_INVALID;
+    cudaSetDevice(c->device);
+    if (cfg->dims < 1 || cfg->dims > 3) PG_FAIL(c, PGPU_ERR_INVALID, "set_config: dims must be 1..3");
+    if (cfg->grid_type == PGPU_QUADTREE) PG_FAIL(c, PGPU_ERR_UNSUPPORTED, "set_config: quadtree grids are not supported");
+    if (cfg->grid_type != PGPU_UNSTRUCTURED && (cfg->nx < 1 || cfg->ny < 1))
+        PG_FAIL(c, PGPU_ERR_INVALID, "set_config: nx, ny must be >= 1 on rectilinear grids");
+    if (!(cfg->dt > 0)) PG_FAIL(c, PGPU_ERR_INVALID, "set_config: dt must be > 0");
+    if (cfg->reserved_ != 0) PG_FAIL(c, PGPU_ERR_INVALID, "set_config: reserved_ must be 0");
+    c->cfg = *cfg;
+    if (c->cfg.nranks < 1) c->cfg.nranks = 1;
+    if (c->cfg.eps_scaling == 0.0) c->cfg.eps_scaling = 1.0;
+    c->cfg_set = true;
+    c->mesh_dirty = c->mesh_set;
+    return PGPU_OK;
+}
+
+extern "C" int pgpu_set_species(pgpu_ctx* c, int ns, const double* mass, const double* charge,
+                                const int32_t* rotdof, const int32_t* vibdof, const double* rotrel,
+                                const double* vibrel) {
+    if (!c) return PGPU_ERR_INVALID;
+    cudaSetDevice(c->device);
+    if (ns < 1 || !mass || !charge || !rotdof || !vibdof || !rotrel || !vibrel)
+        PG_FAIL(c, PGPU_ERR_INVALID, "set_species: ns < 1 or null array");
+    int rc;
+    c->ns = ns;
+    c->dev.ns = ns;
+    if ((rc = put(c, S_MASS, mass, ns, &c->dev.mass))) return rc;
+    if ((rc = put(c, S_CHARGE, charge, ns, &c->dev.charge))) return rc;
+    if ((rc = put(c, S_ROTDOF, (const int*)rotdof, ns, &c->dev.rotdof))) return rc;
+    if ((rc = put(c, S_VIBDOF, (const int*)vibdof, ns, &c->dev.vibdof))) return rc;
+    if ((rc = put(c, S_ROTREL, rotrel, ns, &c->dev.rotrel))) return rc;
+    if ((rc = put(c, S_VIBREL, vibrel, ns, &c->dev.vibrel))) return rc;
+    return alloc_counters(c);
+}
+
+extern "C" int pgpu_set_vss(pgpu_ctx* c, int ns, const double* sigmas, const double* omegas, const double* alphas,
+                            const double* grefs, double sigmamax) {
+    if (!c) return PGPU_ERR_INVALID;
+    cudaSetDevice(c->device);
+    if (ns != c->ns) PG_FAIL(c, PGPU_ERR_INVALID, "set_vss: ns (%d) differs from set_species (%lld)", ns, c->ns);
+    int rc;
+    size_t n = (size_t)ns * ns;
+    if ((rc = put(c, S_SIGMAS, sigmas, n, &c->dev.sigmas))) return rc;
+    if ((rc = put(c, S_OMEGAS, omegas, n, &c->dev.omegas))) return rc;
+    if ((rc = put(c, S_ALPHAS, alphas, n, &c->dev.alphas))) return rc;
+    if ((rc = put(c, S_GREFS, grefs, n, &c->dev.grefs))) return rc;
+    c->dev.sigmamax = sigmamax;
+    return PGPU_OK;
+}
+
+extern "C" int pgpu_set_reactions(pgpu_ctx* c, int nr, const int32_t* type, const int32_t* r1, const int32_t* r2,
+                                  const int32_t* p1, const int32_t* p2, const int32_t* p3, const int32_t* p4,
+                                  const int32_t* nprod, const int32_t* is_cex, const double* ea, const double* c1,
+                                  const double* c2, const double* c3, const int32_t* tab_off, const double* tab_e,
+                                  const double* tab_cs) {
+    if (!c) return PGPU_ERR_INVALID;
+    cudaSetDevice(c->device);
+    int rc;
+    c->dev.nr = 0;
+    if (nr <= 0) {
+        if ((rc = put<PgReaction>(c, S_REAC, nullptr, 0, &c->dev.reac))) return rc;
+        return PGPU_OK;
+    }
+    if (!type || !r1 || !r2 || !p1 || !p2 || !nprod || !ea) PG_FAIL(c, PGPU_ERR_INVALID, "set_reactions: null array");
+    std::vector<PgReaction> h((size_t)nr);
+    for (int i = 0; i < nr; i++) {
+        PgReaction& r = h[i];
+        r.type = type[i]; r.r1 = r1[i]; r.r2 = r2[i]; r.p1 = p1[i]; r.p2 = p2[i];
+        r.p3 = p3 ? p3[i] : -1; r.p4 = p4 ? p4[i] : -1;
+        r.nprod = nprod[i]; r.is_cex = is_cex ? is_cex[i] : 0;
+        r.ea = ea[i]; r.c1 = c1 ? c1[i] : 0; r.c2 = c2 ? c2[i] : 0; r.c3 = c3 ? c3[i] : 0;
+        r.tab_off = tab_off ? tab_off[i] : 0;
+        r.tab_n = tab_off ? tab_off[i + 1] - tab_off[i] : 0;
+        r.pad = 0;
+        if (r.nprod < 2 || r.nprod > 4) PG_FAIL(c, PGPU_ERR_INVALID, "set_reactions: reaction %d has %d products", i, r.nprod);
+        if (r.type == PGPU_LXCAT && r.tab_n < 2) PG_FAIL(c, PGPU_ERR_INVALID, "set_reactions: LXCat reaction %d without table", i);
+    }
+    int ntab = tab_off ? tab_off[nr] : 0;
+    if ((rc = put(c, S_REAC, h.data(), (size_t)nr, &c->dev.reac))) return rc;
+    if ((rc = put(c, S_TAB_E, tab_e, (size_t)ntab, &c->dev.tab_e))) return rc;
+    if ((rc = put(c, S_TAB_CS, tab_cs, (size_t)ntab, &c->dev.tab_cs))) return rc;
+    c->dev.nr = nr;
+    return PGPU_OK;
+}
+
+extern "C" int pgpu_set_wall_reactions(pgpu_ctx* c, int n, const int32_t* r_sp, const int32_t* p1_sp,
+                                       const int32_t* nprod, const double* prob) {
+    if (!c) return PGPU_ERR_INVALID;
+    cudaSetDevice(c->device);
+    int rc;
+    c->dev.nwr = 0;
+    if ((rc = put(c, S_WR_R, (const int*)r_sp, (size_t)std::max(n, 0), &c->dev.wr_r))) return rc;
+    if ((rc = put(c, S_WR_P1, (const int*)p1_sp, (size_t)std::max(n, 0), &c->dev.wr_p1))) return rc;
+    if ((rc = put(c, S_WR_NPROD, (const int*)nprod, (size_t)std::max(n, 0), &c->dev.wr_nprod))) return rc;
+    if ((rc = put(c, S_WR_PROB, prob, (size_t)std::max(n, 0), &c->dev.wr_prob))) return rc;
+    c->dev.nwr = std::max(n, 0);
+    return PGPU_OK;
+}
+
+extern "C" int pgpu_set_mcc_background(pgpu_ctx* c, int ncomp, const int32_t* sp_id, const double* molfrac) {
+    if (!c) return PGPU_ERR_INVALID;
+    cudaSetDevice(c->device);
+    int rc;
+    c->dev.mcc_ncomp = 0;
+    if ((rc = put(c, S_MCC_SP, (const int*)sp_id, (size_t)std::max(ncomp, 0), &c->dev.mcc_sp))) return rc;
+    if ((rc = put(c, S_MCC_FRAC, molfrac, (size_t)std::max(ncomp, 0), &c->dev.mcc_frac))) return rc;
+    c->dev.mcc_ncomp = std::max(ncomp, 0);
+    return PGPU_OK;
+}
+
+extern "C" int pgpu_set_mesh(pgpu_ctx* c, int dims, int nn, int nc, const double* node_coords,
+                             const int32_t* cell_nodes, const int32_t* cell_neighbors, const double* face_normal,
+                             const double* face_tang1, const double* face_tang2, const double* cell_edges_len,
+                             const int32_t* cell_faces_pg, const int32_t* cell_pg, const double* basis_coeffs,
+                             const double* cell_volumes, const int32_t* cell_procs,
+                             const int32_t* face_boundary_index, int nboundcells, const double* boundary_area) {
+    if (!c) return PGPU_ERR_INVALID;
+    cudaSetDevice(c->device);
+    if (dims < 1 || dims > 3) PG_FAIL(c, PGPU_ERR_INVALID, "set_mesh: dims must be 1..3");
+    if (nn < 2 || nc < 1) PG_FAIL(c, PGPU_ERR_INVALID, "set_mesh: empty mesh");
+    if (!node_coords || !cell_nodes || !cell_neighbors || !face_normal || !cell_faces_pg || !cell_volumes)
+        PG_FAIL(c, PGPU_ERR_INVALID, "set_mesh: null array");
+    if (dims == 3 && (!face_tang1 || !face_tang2)) PG_FAIL(c, PGPU_ERR_INVALID, "set_mesh: 3-D meshes need FACE_TANG1/2");
+    int nf = dims + 1, rc;
+    c->mesh_dims = dims; c->nn = nn; c->nc = nc;
+    c->h_node_coords.assign(node_coords, node_coords + 3 * (size_t)nn);
+    c->h_cell_nodes.assign(cell_nodes, cell_nodes + (size_t)nf * nc);
+    c->h_cell_neighbors.assign(cell_neighbors, cell_neighbors + (size_t)nf * nc);
+    c->h_face_normal.assign(face_normal, face_normal + 3 * (size_t)nf * nc);
+    c->h_cell_faces_pg.assign(cell_faces_pg, cell_faces_pg + (size_t)nf * nc);
+    if (cell_pg) c->h_cell_pg.assign(cell_pg, cell_pg + nc);
+    else c->h_cell_pg.clear();
+    for (size_t i = 0; i < (size_t)nf * nc; i++) {
+        int v = cell_nodes[i], nb = cell_neighbors[i];
+        if (v < 1 || v > nn) PG_FAIL(c, PGPU_ERR_INVALID, "set_mesh: CELL_NODES entry %zu = %d outside 1..%d", i, v, nn);
+        if (nb != -1 && (nb < 1 || nb > nc)) PG_FAIL(c, PGPU_ERR_INVALID, "set_mesh: CELL_NEIGHBORS entry %zu = %d invalid", i, nb);
+    }
+    PgDev& d = c->dev;
+    d.nn = nn; d.nc = nc; d.nf = nf;
+    if ((rc = put(c, S_TANG1, face_tang1, face_tang1 ? 12 * (size_t)nc : 0, &d.face_tang1))) return rc;
+    if ((rc = put(c, S_TANG2, face_tang2, face_tang2 ? 12 * (size_t)nc : 0, &d.face_tang2))) return rc;
+    if ((rc = put(c, S_EDGE_LEN, cell_edges_len, cell_edges_len ? 3 * (size_t)nc : 0, &d.edge_len))) return rc;
+    if ((rc = put(c, S_CELL_NODES, (const int*)cell_nodes, (size_t)nf * nc, &d.cell_nodes))) return rc;
+    if ((rc = put(c, S_BASIS, basis_coeffs, basis_coeffs ? (size_t)nf * nf * nc : 0, &d.basis))) return rc;
+    if ((rc = put(c, S_CELL_VOL, cell_volumes, (size_t)nc, &d.cell_vol))) return rc;
+    if ((rc = put(c, S_CELL_PROCS, (const int*)cell_procs, cell_procs ? (size_t)nc : 0, &d.cell_procs))) return rc;
+    d.nboundcells = face_boundary_index ? nboundcells : 0;
+    if ((rc = put(c, S_FACE_BIDX, (const int*)face_boundary_index, face_boundary_index ? (size_t)nf * nc : 0, &d.face_bidx))) return rc;
+    if ((rc = put(c, S_BOUND_AREA, boundary_area, (size_t)d.nboundcells, &d.bound_area))) return rc;
+    dev_free(c->d_surface_charge);
+    if ((rc = dev_alloc(c, &c->d_surface_charge, (size_t)nn))) return rc;
+    PG_CUDA(c, cudaMemset(c->d_surface_charge, 0, sizeof(double) * (size_t)nn));
+    c->nsc = nn;
+    c->mesh_set = true;
+    c->mesh_dirty = true;
+    return alloc_counters(c);
+}
+
+extern "C" int pgpu_set_cell_procs(pgpu_ctx* c, int nc, const int32_t* cell_procs) {
+    if (!c) return PGPU_ERR_INVALID;
+    cudaSetDevice(c->device);
+    if (!c->cfg_set) PG_FAIL(c, PGPU_ERR_STATE, "set_cell_procs: set_config first");
+    if (nc != pg_ncells(c)) PG_FAIL(c, PGPU_ERR_INVALID, "set_cell_procs: nc (%d) != number of cells (%d)", nc, pg_ncells(c));
+    return put(c, S_CELL_PROCS, (const int*)cell_procs, (size_t)nc, &c->dev.cell_procs);
+}
+
+extern "C" int pgpu_set_bcs(pgpu_ctx* c, int nbc, const int32_t* particle_bc, const int32_t* field_bc,
+                            const int32_t* volume_bc, const double* wall_temp, const double* acc_n,
+                            const double* acc_t, const int32_t* react, const int32_t* dump_fluxes) {
+    if (!c) return PGPU_ERR_INVALID;
+    cudaSetDevice(c->device);
+    (void)dump_fluxes;
+    if (nbc < 0 || (nbc > 0 && (!particle_bc || !field_bc || !volume_bc || !wall_temp || !acc_n || !acc_t || !react)))
+        PG_FAIL(c, PGPU_ERR_INVALID, "set_bcs: null array");
+    for (int i = 0; i < nbc; i++)
+        if (particle_bc[i] == PGPU_WB_BC)
+            PG_FAIL(c, PGPU_ERR_UNSUPPORTED, "set_bcs: the washboard wall model needs tables the reference does not ship");
+    int rc;
+    PgDev& d = c->dev;
+    d.nbc = nbc;
+    if ((rc = put(c, S_BC_PARTICLE, (const int*)particle_bc, (size_t)nbc, &d.bc_particle))) return rc;
+    if ((rc = put(c, S_BC_FIELD, (const int*)field_bc, (size_t)nbc, &d.bc_field))) return rc;
+    if ((rc = put(c, S_BC_REACT, (const int*)react, (size_t)nbc, &d.bc_react))) return rc;
+    if ((rc = put(c, S_BC_TEMP, wall_temp, (size_t)nbc, &d.bc_temp))) return rc;
+    if ((rc = put(c, S_BC_ACCN, acc_n, (size_t)nbc, &d.bc_accn))) return rc;
+    if ((rc = put(c, S_BC_ACCT, acc_t, (size_t)nbc, &d.bc_acct))) return rc;
+    c->h_bc_volume.assign(volume_bc, volume_bc + nbc);
+    c->mesh_dirty = c->mesh_set;
+    return PGPU_OK;
+}
+
+extern "C" int pgpu_set_walls(pgpu_ctx* c, int nw, const double* x1, const double* y1, const double* x2,
+                              const double* y2, const double* normx, const double* normy, const double* temp,
+                              const int32_t* specular, const int32_t* diffuse, const int32_t* porous,
+                              const double* transmissivity, const int32_t* react) {
+    if (!c) return PGPU_ERR_INVALID;
+    cudaSetDevice(c->device);
+    if (nw < 0) PG_FAIL(c, PGPU_ERR_INVALID, "set_walls: nw < 0");
+    int rc;
+    PgDev& d = c->dev;
+    size_t n = (size_t)nw;
+    if ((rc = put(c, S_W_X1, x1, n, &d.w_x1))) return rc;
+    if ((rc = put(c, S_W_Y1, y1, n, &d.w_y1))) return rc;
+    if ((rc = put(c, S_W_X2, x2, n, &d.w_x2))) return rc;
+    if ((rc = put(c, S_W_Y2, y2, n, &d.w_y2))) return rc;
+    if ((rc = put(c, S_W_NX, normx, n, &d.w_nx))) return rc;
+    if ((rc = put(c, S_W_NY, normy, n, &d.w_ny))) return rc;
+    if ((rc = put(c, S_W_TEMP, temp, n, &d.w_temp))) return rc;
+    if ((rc = put(c, S_W_TRANSM, transmissivity, n, &d.w_transm))) return rc;
+    if ((rc = put(c, S_W_SPEC, (const int*)specular, n, &d.w_spec))) return rc;
+    if ((rc = put(c, S_W_DIFF, (const int*)diffuse, n, &d.w_diff))) return rc;
+    if ((rc = put(c, S_W_POROUS, (const int*)porous, n, &d.w_porous))) return rc;
+    if ((rc = put(c, S_W_REACT, (const int*)react, n, &d.w_react))) return rc;
+    d.nw = nw;
+    c->nw = nw;
+    return alloc_counters(c);
+}
+
+extern "C" int pgpu_set_grid_coords(pgpu_ctx* c, int nxp, const double* xcoord, int nyp, const double* ycoord) {
+    if (!c) return PGPU_ERR_INVALID;
+    cudaSetDevice(c->device);
+    int rc;
+    if ((rc = put(c, S_XCOORD, xcoord, (size_t)std::max(nxp, 0), &c->dev.xcoord))) return rc;
+    if ((rc = put(c, S_YCOORD, ycoord, (size_t)std::max(nyp, 0), &c->dev.ycoord))) return rc;
+    c->dev.nxp = nxp;
+    c->dev.nyp = nyp;
+    return PGPU_OK;
+}
+
+extern "C" int pgpu_set_efield(pgpu_ctx* c, const double* e, int64_t n) {
+    if (!c) return PGPU_ERR_INVALID;
+    cudaSetDevice(c->device);
+    return put(c, S_EFIELD, e, (size_t)std::max<int64_t>(n, 0), &c->dev.e_field);
+}
+extern "C" int pgpu_set_bfield(pgpu_ctx* c, const double* b, int64_t n) {
+    if (!c) return PGPU_ERR_INVALID;
+    cudaSetDevice(c->device);
+    return put(c, S_BFIELD, b, (size_t)std::max<int64_t>(n, 0), &c->dev.b_field);
+}
+extern "C" int pgpu_get_surface_charge(pgpu_ctx* c, double* sc, int64_t n) {
+    if (!c) return PGPU_ERR_INVALID;
+    cudaSetDevice(c->device);
+    if (!c->d_surface_charge) PG_FAIL(c, PGPU_ERR_STATE, "get_surface_charge: no mesh set");
+    PG_CUDA(c, cudaStreamSynchronize(c->stream));
+    PG_CUDA(c, cudaMemcpy(sc, c->d_surface_charge, sizeof(double) * (size_t)std::min<int64_t>(n, c->nsc), cudaMemcpyDeviceToHost));
+    return PGPU_OK;
+}
+extern "C" int pgpu_set_surface_charge(pgpu_ctx* c, const double* sc, int64_t n) {
+    if (!c) return PGPU_ERR_INVALID;
+    cudaSetDevice(c->device);
+    dev_free(c->d_surface_charge);
+    int rc;
+    if ((rc = dev_alloc(c, &c->d_surface_charge, (size_t)n))) return rc;
+    PG_CUDA(c, cudaMemcpy(c->d_surface_charge, sc, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice));
+    c->nsc = n;
+    return PGPU_OK;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * packed device mesh:  per cell and face { outward normal, a point on the face } + one hop code.
+ * The reference reads FACE_NORMAL/EDGE_NORMAL, CELL_NODES -> NODE_COORDS, CELL_NEIGHBORS,
+ * CELL_FACES_PG and the neighbour's CELL_PG/VOLUME_BC separately for every face test
+ * (src/timecycle.f90:1257-1360); here they are resolved once so that the face walk is a single
+ * 48-byte record per face with no dependent index load.  The point of face j is local node j
+ * (src/timecycle.f90:1293-1295), the same operand the reference uses, so the arithmetic is unchanged.
+ * ---------------------------------------------------------------------------------------- */
+static int build_packed_mesh(pgpu_ctx* c) {
+    int nf = c->mesh_dims + 1, nc = c->nc, rc;
+    std::vector<double> geo((size_t)nc * nf * 6);
+    std::vector<int> code((size_t)nc * nf);
+    const int nbc = (int)c->h_bc_volume.size();
+    for (int ic = 0; ic < nc; ic++) {
+        for (int j = 0; j < nf; j++) {
+            size_t f = (size_t)ic * nf + j;
+            int v = c->h_cell_nodes[f];
+            double* g = &geo[f * 6];
+            for (int k = 0; k < 3; k++) {
+                g[k] = c->h_face_normal[3 * f + k];
+                g[3 + k] = c->h_node_coords[3 * (size_t)(v - 1) + k];
+            }
+            int nb = c->h_cell_neighbors[f];
+            bool fluidboundary = false;
+            if (nb == -1) {
+                fluidboundary = true;
+            } else if (!c->h_cell_pg.empty()) {
+                int npg = c->h_cell_pg[nb - 1];
+                if (npg != -1) {
+                    if (npg < 1 || npg > nbc) PG_FAIL(c, PGPU_ERR_INVALID, "mesh: CELL_PG %d has no boundary condition", npg);
+                    if (c->h_bc_volume[npg - 1] == PGPU_SOLID) fluidboundary = true;
+                }
+            }
+            if (!fluidboundary) {
+                code[f] = nb;
+            } else {
+                int pg = c->h_cell_faces_pg[f];
+                if (pg == -1) code[f] = 0;
+                else {
+                    if (pg < 1 || pg > nbc) PG_FAIL(c, PGPU_ERR_INVALID, "mesh: face physical group %d has no boundary condition (set_bcs)", pg);
+                    code[f] = -pg;
+                }
+            }
+        }
+    }
+    if ((rc = put(c, S_FACE_GEO, geo.data(), geo.size(), &c->dev.face_geo))) return rc;
+    if ((rc = put(c, S_FACE_CODE, code.data(), code.size(), &c->dev.face_code))) return rc;
+    c->mesh_dirty = false;
+    return PGPU_OK;
+}
+
+int pg_ensure_cell_arrays(pgpu_ctx* c) {
+    int ncells = pg_ncells(c), rc;
+    if (ncells <= c->ncells_alloc) return PGPU_OK;
+    dev_free(c->d_cell_count);
+    dev_free(c->d_cell_off);
+    if ((rc = dev_alloc(c, &c->d_cell_count, (size_t)ncells + 1))) return rc;
+    if ((rc = dev_alloc(c, &c->d_cell_off, (size_t)ncells + 1))) return rc;
+    PG_CUDA(c, cudaMemset(c->d_cell_count, 0, sizeof(unsigned int) * ((size_t)ncells + 1)));
+    PG_CUDA(c, cudaMemset(c->d_cell_off, 0, sizeof(unsigned int) * ((size_t)ncells + 1)));
+    size_t tmp = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp, c->d_cell_count, c->d_cell_off, ncells + 1, c->stream);
+    dev_free(c->d_scan_tmp);
+    PG_CUDA(c, cudaMalloc(&c->d_scan_tmp, tmp + 16));
+    c->scan_tmp_bytes = tmp + 16;
+    c->ncells_alloc = ncells;
+    c->hist_valid = false;
+    c->sorted = false;
+    return PGPU_OK;
+}
+
+void pg_refresh_dev(pgpu_ctx* c) {
+    PgDev& d = c->dev;
+    const pgpu_config& g = c->cfg;
+    d.dims = g.dims; d.axi = g.axi; d.grid_type = g.grid_type; d.nx = g.nx; d.ny = g.ny;
+    d.xmin = g.xmin; d.xmax = g.xmax; d.ymin = g.ymin; d.ymax = g.ymax; d.zmin = g.zmin; d.zmax = g.zmax;
+    d.dt = g.dt; d.fnum = g.fnum; d.pic = g.pic_type; d.coll_type = g.collision_type;
+    for (int i = 0; i < 4; i++) {
+        d.bper[i] = g.bool_periodic[i]; d.bspec[i] = g.bool_specular[i];
+        d.bdiff[i] = g.bool_diffuse[i]; d.breact[i] = g.bool_react[i];
+    }
+    d.zper = g.bool_z_periodic; d.yper = g.bool_y_periodic;
+    d.boundtemp = g.boundtemp;
+    for (int i = 0; i < 3; i++) d.extb[i] = g.external_b[i];
+    d.eps_scaling = g.eps_scaling; d.mcc_dens = g.mcc_bg_dens; d.mcc_ttra = g.mcc_bg_ttra;
+    d.seed_local = (unsigned long long)g.rng_seed_global * (unsigned long long)(g.rank + 1);
+    d.rank = g.rank; d.nranks = g.nranks;
+    d.surface_charge = c->d_surface_charge;
+    d.bcount = c->d_bcount; d.wcount = c->d_wcount; d.tallies = c->d_tallies;
+    d.status = c->d_status;
+    d.p = c->planes[c->cur];
+    if (!c->has_dtrim) d.p.dtrim = nullptr;
+    d.np = c->np; d.capacity = c->capacity;
+    d.ncells = pg_ncells(c);
+    d.cell_count = c->d_cell_count; d.cell_rank = c->d_rank; d.cell_off = c->d_cell_off; d.hitlist = c->d_hitlist;
+    d.id_base = c->id_counter;
+}
+
+int pg_prepare(pgpu_ctx* c) {
+    cudaSetDevice(c->device);
+    if (!c->cfg_set) PG_FAIL(c, PGPU_ERR_STATE, "pgpu_set_config has not been called");
+    if (c->ns < 1) PG_FAIL(c, PGPU_ERR_STATE, "pgpu_set_species has not been called");
+    int rc;
+    if (c->cfg.grid_type == PGPU_UNSTRUCTURED) {
+        if (!c->mesh_set) PG_FAIL(c, PGPU_ERR_STATE, "unstructured grid without pgpu_set_mesh");
+        if (c->mesh_dims != c->cfg.dims) PG_FAIL(c, PGPU_ERR_INVALID, "mesh dims (%d) != config dims (%d)", c->mesh_dims, c->cfg.dims);
+        if (c->cfg.axi && c->cfg.dims != 2) PG_FAIL(c, PGPU_ERR_INVALID, "axisymmetric runs need dims == 2");
+        if (c->mesh_dirty && (rc = build_packed_mesh(c))) return rc;
+    } else {
+        if (c->cfg.dims == 3) PG_FAIL(c, PGPU_ERR_UNSUPPORTED, "rectilinear grids are 1-D/2-D in the reference (CELL_FROM_POSITION)");
+        if (c->cfg.grid_type == PGPU_RECTILINEAR_NONUNIFORM &&
+            (c->dev.nxp != c->cfg.nx + 1 || c->dev.nyp != c->cfg.ny + 1 || !c->dev.xcoord || !c->dev.ycoord))
+            PG_FAIL(c, PGPU_ERR_STATE, "non-uniform grid without matching pgpu_set_grid_coords");
+    }
+    if ((rc = pg_ensure_cell_arrays(c))) return rc;
+    pg_refresh_dev(c);
+    return PGPU_OK;
+}
+
+int pg_reset_status(pgpu_ctx* c) {
+    PG_CUDA(c, cudaMemsetAsync(c->d_status, 0, sizeof(PgStatus), c->stream));
+    return PGPU_OK;
+}
+
+static const char* deverr_text(int e) {
+    switch (e) {
+        case PG_DEVERR_HOPS: return "a particle exceeded the hop limit (malformed mesh or NaN state)";
+        case PG_DEVERR_CELL_RANGE: return "a particle ended outside the grid (cell index out of range)";
+        case PG_DEVERR_CAPACITY: return "particle capacity exhausted while creating particles (raise pgpu_config.capacity)";
+        default: return "unknown device error";
+    }
+}
+
+int pg_finish(pgpu_ctx* c, const char* what) {
+    PG_CUDA(c, cudaMemcpyAsync(c->h_status, c->d_status, sizeof(PgStatus), cudaMemcpyDeviceToHost, c->stream));
+    PG_CUDA(c, cudaStreamSynchronize(c->stream));
+    PG_CUDA(c, cudaGetLastError());
+    if (c->h_status->n_appended) {
+        c->np += (long long)c->h_status->n_appended;
+        c->id_counter += (long long)c->h_status->n_appended;
+        if (c->np > c->capacity) c->np = c->capacity;
+        c->sorted = false;
+        c->hist_valid = false;
+    }
+    if (c->h_status->err) PG_FAIL(c, PGPU_ERR_STATE, "%s: %s", what, deverr_text(c->h_status->err));
+    return PGPU_OK;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * particle store
+ * ---------------------------------------------------------------------------------------- */
+static int alloc_planes(pgpu_ctx* c, PgPlanes& p, long long cap, bool with_dtrim, bool with_id) {
+    int rc;
+    memset(&p, 0, sizeof(p));
+    size_t n = (size_t)cap;
+    if ((rc = dev_alloc(c, &p.x, n)) || (rc = dev_alloc(c, &p.y, n)) || (rc = dev_alloc(c, &p.z, n)) ||
+        (rc = dev_alloc(c, &p.vx, n)) || (rc = dev_alloc(c, &p.vy, n)) || (rc = dev_alloc(c, &p.vz, n)) ||
+        (rc = dev_alloc(c, &p.erot, n)) || (rc = dev_alloc(c, &p.evib, n)) || (rc = dev_alloc(c, &p.ic, n)) ||
+        (rc = dev_alloc(c, &p.sid, n)))
+        return rc;
+    if (with_dtrim && (rc = dev_alloc(c, &p.dtrim, n))) return rc;
+    if (with_id && (rc = dev_alloc(c, &p.id, n))) return rc;
+    return PGPU_OK;
+}
+
+template <class T>
+static int copy_plane(pgpu_ctx* c, T* dst, const T* src, long long n) {
+    if (dst && src && n > 0) PG_CUDA(c, cudaMemcpyAsync(dst, src, sizeof(T) * (size_t)n, cudaMemcpyDeviceToDevice, c->stream));
+    return PGPU_OK;
+}
+
+int pg_ensure_capacity(pgpu_ctx* c, long long n) {
+    if (n <= c->capacity) return PGPU_OK;
+    long long cap = std::max<long long>(n, (long long)(1.5 * (double)c->capacity));
+    cap = std::max<long long>(cap, 1024);
+    int rc;
+    PgPlanes np0, np1;
+    bool with_id = c->cfg.track_id != 0;
+    if ((rc = alloc_planes(c, np0, cap, true, with_id))) return rc;
+    if ((rc = alloc_planes(c, np1, cap, true, with_id))) return rc;
+    PgPlanes& o = c->planes[c->cur];
+    long long m = c->np;
+    if (m > 0) {
+        copy_plane(c, np0.x, o.x, m); copy_plane(c, np0.y, o.y, m); copy_plane(c, np0.z, o.z, m);
+        copy_plane(c, np0.vx, o.vx, m); copy_plane(c, np0.vy, o.vy, m); copy_plane(c, np0.vz, o.vz, m);
+        copy_plane(c, np0.erot, o.erot, m); copy_plane(c, np0.evib, o.evib, m);
+        copy_plane(c, np0.ic, o.ic, m); copy_plane(c, np0.sid, o.sid, m);
+        copy_plane(c, np0.dtrim, o.dtrim, m); copy_plane(c, np0.id, o.id, m);
+        PG_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
+    free_planes(c->planes[0]);
+    free_planes(c->planes[1]);
+    c->planes[0] = np0;
+    c->planes[1] = np1;
+    c->cur = 0;
+    dev_free(c->d_rank);
+    dev_free(c->d_hitlist);
+    if ((rc = dev_alloc(c, &c->d_rank, (size_t)cap))) return rc;
+    if ((rc = dev_alloc(c, &c->d_hitlist, (size_t)cap))) return rc;
+    c->capacity = cap;
+    c->hist_valid = false;
+    return PGPU_OK;
+}
+
+/* host record offsets, ref: src/particle.f90:28-37 as laid out by gfortran (see pantera_gpu.h) */
+#define OFF_X 0
+#define OFF_V 24
+#define OFF_EROT 48
+#define OFF_EVIB 56
+#define OFF_DTRIM 64
+#define OFF_IC 72
+#define OFF_SID 76
+#define OFF_ID 80
+#define OFF_TRAJ 88
+
+__global__ void __launch_bounds__(256) aos_to_soa_kernel(const unsigned char* __restrict__ aos, int stride, long long n,
+                                                         PgPlanes p, long long base, double dt, int ncells,
+                                                         PgStatus* st) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned char* r = aos + (size_t)i * stride;
+    const double* f = reinterpret_cast<const double*>(r);
+    long long o = base + i;
+    p.x[o] = f[0]; p.y[o] = f[1]; p.z[o] = f[2];
+    p.vx[o] = f[3]; p.vy[o] = f[4]; p.vz[o] = f[5];
+    p.erot[o] = f[6]; p.evib[o] = f[7];
+    double dtrim = f[8];
+    p.dtrim[o] = dtrim;
+    int ic = *reinterpret_cast<const int*>(r + OFF_IC);
+    p.ic[o] = ic;
+    p.sid[o] = *reinterpret_cast<const int*>(r + OFF_SID);
+    if (p.id) p.id[o] = *reinterpret_cast<const long long*>(r + OFF_ID);
+    if (dtrim != dt) st->pad = 1;
+    if (ncells > 0 && (ic < 1 || ic > ncells)) atomicCAS(&st->err, 0, PG_DEVERR_CELL_RANGE);
+}
+
+__global__ void __launch_bounds__(256) soa_to_aos_kernel(unsigned char* __restrict__ aos, int stride, long long n,
+                                                         PgPlanes p, long long base, double dt, int rank,
+                                                         int has_dtrim) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned char* r = aos + (size_t)i * stride;
+    double* f = reinterpret_cast<double*>(r);
+    long long o = base + i;
+    f[0] = p.x[o]; f[1] = p.y[o]; f[2] = p.z[o];
+    f[3] = p.vx[o]; f[4] = p.vy[o]; f[5] = p.vz[o];
+    f[6] = p.erot[o]; f[7] = p.evib[o];
+    f[8] = has_dtrim ? p.dtrim[o] : dt;
+    *reinterpret_cast<int*>(r + OFF_IC) = p.ic[o];
+    *reinterpret_cast<int*>(r + OFF_SID) = p.sid[o];
+    /* ID = PROC_ID + ISHFT(counter, 8), ref: src/particle.f90:75 (regenerated unless cfg.track_id) */
+    *reinterpret_cast<long long*>(r + OFF_ID) = p.id ? p.id[o] : ((long long)rank + (o << 8));
+    *reinterpret_cast<int*>(r + OFF_TRAJ) = 0;
+    if (stride >= 96) *reinterpret_cast<int*>(r + 92) = 0;
+}
+
+__global__ void fill_f64_kernel(double* p, long long n, double v) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+static const long long STAGE_PARTICLES = 1 << 20;
+
+static int ensure_stage(pgpu_ctx* c, int stride) {
+    size_t need = (size_t)STAGE_PARTICLES * (size_t)stride;
+    if (need <= c->stage_bytes) return PGPU_OK;
+    for (int i = 0; i < 2; i++) {
+        dev_free(c->d_stage[i]);
+        PG_CUDA(c, cudaMalloc(&c->d_stage[i], need));
+    }
+    c->stage_bytes = need;
+    return PGPU_OK;
+}
+
+static int append_impl(pgpu_ctx* c, const void* aos, int64_t n, int32_t stride, const char* what) {
+    if (n < 0) PG_FAIL(c, PGPU_ERR_INVALID, "%s: n < 0", what);
+    if (stride < 92 || (stride % 8) != 0) PG_FAIL(c, PGPU_ERR_INVALID, "%s: stride %d must be a multiple of 8 and >= 92", what, stride);
+    if (n > 0 && !aos) PG_FAIL(c, PGPU_ERR_INVALID, "%s: null buffer", what);
+    if (!c->cfg_set) PG_FAIL(c, PGPU_ERR_STATE, "%s: pgpu_set_config first (DT is needed)", what);
+    int rc;
+    cudaSetDevice(c->device);
+    if (c->capacity == 0) {
+        long long cap = c->cfg.capacity > 0 ? (long long)c->cfg.capacity : (long long)(1.5 * (double)n);
+        if ((rc = pg_ensure_capacity(c, std::max<long long>(cap, c->np + n)))) return rc;
+    } else if ((rc = pg_ensure_capacity(c, c->np + n))) {
+        return rc;
+    }
+    if (n == 0) return PGPU_OK;
+    if ((rc = ensure_stage(c, stride))) return rc;
+    if ((rc = pg_reset_status(c))) return rc;
+    int ncells = (c->cfg.grid_type == PGPU_UNSTRUCTURED) ? (c->mesh_set ? c->nc : 0) : c->cfg.nx * c->cfg.ny;
+    PgPlanes p = c->planes[c->cur];
+    cudaEvent_t evs[2] = {c->ev[14], c->ev[15]};
+    bool used[2] = {false, false};
+    int k = 0;
+    for (long long done = 0; done < n; done += STAGE_PARTICLES, k ^= 1) {
+        long long m = std::min<long long>(STAGE_PARTICLES, n - done);
+        if (used[k]) PG_CUDA(c, cudaEventSynchronize(evs[k])); /* staging buffer k is free again */
+        PG_CUDA(c, cudaMemcpyAsync(c->d_stage[k], (const unsigned char*)aos + (size_t)done * stride, (size_t)m * stride,
+                                   cudaMemcpyHostToDevice, c->stream));
+        aos_to_soa_kernel<<<(unsigned int)((m + 255) / 256), 256, 0, c->stream>>>(
+            (const unsigned char*)c->d_stage[k], stride, m, p, c->np + done, c->cfg.dt, ncells, c->d_status);
+        PG_CUDA(c, cudaEventRecord(evs[k], c->stream));
+        used[k] = true;
+    }
+    long long np_old = c->np;
+    c->np += n;
+    c->sorted = false;
+    c->hist_valid = false;
+    if ((rc = pg_finish(c, what))) {
+        c->np = np_old;
+        return rc;
+    }
+    if (c->h_status->pad) c->has_dtrim = true;
+    c->id_counter = std::max(c->id_counter, c->np);
+    return PGPU_OK;
+}
+
+extern "C" int pgpu_upload_particles(pgpu_ctx* c, const void* aos, int64_t n, int32_t stride) {
+    if (!c) return PGPU_ERR_INVALID;
+    c->np = 0;
+    c->has_dtrim = false;
+    c->maybe_tombstones = false;
+    c->id_counter = 0;
+    return append_impl(c, aos, n, stride, "pgpu_upload_particles");
+}
+
+extern "C" int pgpu_append_particles(pgpu_ctx* c, const void* aos, int64_t n, int32_t stride) {
+    if (!c) return PGPU_ERR_INVALID;
+    if (n > 0 && c->np > 0 && !c->has_dtrim) {
+        /* the DTRIM plane is not maintained while every particle has DTRIM == DT: rebuild it so that the
+         * appended particles (DTRIM = rf()*DT after an injection, ref: src/timecycle.f90:463) can differ */
+        cudaSetDevice(c->device);
+        fill_f64_kernel<<<(unsigned int)((c->np + 255) / 256), 256, 0, c->stream>>>(c->planes[c->cur].dtrim, c->np, c->cfg.dt);
+        PG_CUDA(c, cudaGetLastError());
+        c->has_dtrim = true;
+    }
+    return append_impl(c, aos, n, stride, "pgpu_append_particles");
+}
+
+extern "C" int pgpu_num_particles(pgpu_ctx* c, int64_t* n) {
+    if (!c || !n) return PGPU_ERR_INVALID;
+    cudaSetDevice(c->device);
+    if (c->maybe_tombstones && c->np > 0) {
+        int rc;
+        if ((rc = pg_prepare(c))) return rc;
+        if ((rc = pg_reset_status(c))) return rc;
+        if ((rc = pg_sort_impl(c))) return rc;
+        if ((rc = pg_finish(c, "pgpu_num_particles"))) return rc;
+    }
+    *n = c->np;
+    return PGPU_OK;
+}
+
+extern "C" int pgpu_download_particles(pgpu_ctx* c, void* aos, int64_t capacity, int64_t* n, int32_t stride) {
+    if (!c) return PGPU_ERR_INVALID;
+    cudaSetDevice(c->device);
+    if (stride < 92 || (stride % 8) != 0) PG_FAIL(c, PGPU_ERR_INVALID, "download: stride %d must be a multiple of 8 and >= 92", stride);
+    int rc;
+    if (c->maybe_tombstones && c->np > 0) {
+        if ((rc = pg_prepare(c))) return rc;
+        if ((rc = pg_reset_status(c))) return rc;
+        if ((rc = pg_sort_impl(c))) return rc;
+        if ((rc = pg_finish(c, "pgpu_download_particles"))) return rc;
+    }
+    if (capacity < c->np) PG_FAIL(c, PGPU_ERR_INVALID, "download: capacity %lld < %lld particles", (long long)capacity, c->np);
+    if (n) *n = c->np;
+    if (c->np == 0) return PGPU_OK;
+    if (!aos) PG_FAIL(c, PGPU_ERR_INVALID, "download: null buffer");
+    if ((rc = ensure_stage(c, stride))) return rc;
+    PgPlanes p = c->planes[c->cur];
+    cudaEvent_t evs[2] = {c->ev[14], c->ev[15]};
+    bool used[2] = {false, false};
+    int k = 0;
+    for (long long done = 0; done < c->np; done += STAGE_PARTICLES, k ^= 1) {
+        long long m = std::min<long long>(STAGE_PARTICLES, c->np - done);
+        if (used[k]) PG_CUDA(c, cudaEventSynchronize(evs[k]));
+        soa_to_aos_kernel<<<(unsigned int)((m + 255) / 256), 256, 0, c->stream>>>(
+            (unsigned char*)c->d_stage[k], stride, m, p, done, c->cfg.dt, c->cfg.rank, c->has_dtrim ? 1 : 0);
+        PG_CUDA(c, cudaMemcpyAsync((unsigned char*)aos + (size_t)done * stride, c->d_stage[k], (size_t)m * stride,
+                                   cudaMemcpyDeviceToHost, c->stream));
+        PG_CUDA(c, cudaEventRecord(evs[k], c->stream));
+        used[k] = true;
+    }
+    PG_CUDA(c, cudaStreamSynchronize(c->stream));
+    return PGPU_OK;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * counting sort by cell (physical SoA reorder).
+ * The reference builds index permutations NPCALL/IOFALL/INDALL (src/collisions.f90:61-112) and then
+ * gathers through them; here the histogram and the arrival rank are produced by the ADVECT epilogue,
+ * an exclusive scan gives the cell offsets, and ONE scatter pass moves all planes
+ * (72 B read + 72 B written + 8 B of rank/cell per particle).  Tombstones drop out here.
+ * ---------------------------------------------------------------------------------------- */
+__global__ void __launch_bounds__(256) hist_rank_kernel(const int* __restrict__ ic, long long n,
+                                                        unsigned int* __restrict__ cell_count,
+                                                        unsigned int* __restrict__ rank) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int c = ic[i];
+    if (c < 1) return;
+    unsigned int mask = __match_any_sync(__activemask(), c);
+    int leader = __ffs(mask) - 1;
+    int lane = threadIdx.x & 31;
+    unsigned int base = 0;
+    if (lane == leader) base = atomicAdd(&cell_count[c - 1], (unsigned int)__popc(mask));
+    base = __shfl_sync(mask, base, leader);
+    rank[i] = base + __popc(mask & ((1u << lane) - 1u));
+}
+
+__global__ void __launch_bounds__(256) scatter_kernel(PgPlanes src, PgPlanes dst, long long n,
+                                                      const unsigned int* __restrict__ cell_off,
+                                                      const unsigned int* __restrict__ rank) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int c = src.ic[i];
+    if (c < 1) return;
+    size_t o = (size_t)cell_off[c - 1] + rank[i];
+    dst.x[o] = src.x[i]; dst.y[o] = src.y[i]; dst.z[o] = src.z[i];
+    dst.vx[o] = src.vx[i]; dst.vy[o] = src.vy[i]; dst.vz[o] = src.vz[i];
+    dst.erot[o] = src.erot[i]; dst.evib[o] = src.evib[i];
+    dst.ic[o] = c;
+    dst.sid[o] = src.sid[i];
+    if (src.dtrim) dst.dtrim[o] = src.dtrim[i];
+    if (src.id) dst.id[o] = src.id[i];
+}
+
+int pg_sort_impl(pgpu_ctx* c) {
+    int ncells = pg_ncells(c);
+    if (c->np == 0) {
+        PG_CUDA(c, cudaMemsetAsync(c->d_cell_off, 0, sizeof(unsigned int) * ((size_t)ncells + 1), c->stream));
+        c->sorted = true;
+        c->maybe_tombstones = false;
+        return PGPU_OK;
+    }
+    PgPlanes src = c->planes[c->cur], dst = c->planes[c->cur ^ 1];
+    if (!c->has_dtrim) src.dtrim = nullptr;
+    unsigned int blocks = (unsigned int)((c->np + 255) / 256);
+    if (!c->hist_valid) {
+        PG_CUDA(c, cudaMemsetAsync(c->d_cell_count, 0, sizeof(unsigned int) * ((size_t)ncells + 1), c->stream));
+        hist_rank_kernel<<<blocks, 256, 0, c->stream>>>(src.ic, c->np, c->d_cell_count, c->d_rank);
+        c->launches++;
+    }
+    size_t tmp = c->scan_tmp_bytes;
+    PG_CUDA(c, cub::DeviceScan::ExclusiveSum(c->d_scan_tmp, tmp, c->d_cell_count, c->d_cell_off, ncells + 1, c->stream));
+    c->launches++;
+    scatter_kernel<<<blocks, 256, 0, c->stream>>>(src, dst, c->np, c->d_cell_off, c->d_rank);
+    c->launches++;
+    PG_CUDA(c, cudaGetLastError());
+    /* new particle count = total of the histogram */
+    unsigned int* h_total = reinterpret_cast<unsigned int*>(&c->h_status->pad);
+    PG_CUDA(c, cudaMemcpyAsync(h_total, c->d_cell_off + ncells, sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
+    PG_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->np = (long long)*h_total;
+    c->cur ^= 1;
+    c->sorted = true;
+    c->hist_valid = false;
+    c->maybe_tombstones = false;
+    pg_refresh_dev(c);
+    return PGPU_OK;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * timings
+ * ---------------------------------------------------------------------------------------- */
+static void tic(pgpu_ctx* c, int g) { cudaEventRecord(c->ev[2 * g], c->stream); }
+static void toc(pgpu_ctx* c, int g) { cudaEventRecord(c->ev[2 * g + 1], c->stream); }
+static void collect(pgpu_ctx* c, int g) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, c->ev[2 * g], c->ev[2 * g + 1]) == cudaSuccess) c->ms[g] += ms;
+}
+static void reset_timings(pgpu_ctx* c) {
+    memset(c->ms, 0, sizeof(c->ms));
+    c->launches = 0;
+}
+
+extern "C" int pgpu_get_timings(pgpu_ctx* c, double* ms, int32_t n, int64_t* launches) {
+    if (!c) return PGPU_ERR_INVALID;
+    for (int i = 0; i < n && i < 8; i++) ms[i] = c->ms[i];
+    if (launches) *launches = c->launches;
+    return PGPU_OK;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * hot-path entry points
+ * ---------------------------------------------------------------------------------------- */
+extern "C" int pgpu_advect(pgpu_ctx* c, int32_t tID) {
+    if (!c) return PGPU_ERR_INVALID;
+    int rc;
+    if ((rc = pg_prepare(c))) return rc;
+    reset_timings(c);
+    if ((rc = pg_reset_status(c))) return rc;
+    tic(c, 0);
+    if ((rc = pg_advect_impl(c, tID))) return rc;
+    toc(c, 0);
+    rc = pg_finish(c, "pgpu_advect");
+    collect(c, 0);
+    c->ms[5] = c->ms[0];
+    return rc;
+}
+
+extern "C" int pgpu_sort(pgpu_ctx* c) {
+    if (!c) return PGPU_ERR_INVALID;
+    int rc;
+    if ((rc = pg_prepare(c))) return rc;
+    reset_timings(c);
+    if ((rc = pg_reset_status(c))) return rc;
+    tic(c, 1);
+    if ((rc = pg_sort_impl(c))) return rc;
+    toc(c, 1);
+    rc = pg_finish(c, "pgpu_sort");
+    collect(c, 1);
+    c->ms[5] = c->ms[1];
+    return rc;
+}
+
+extern "C" int pgpu_collide(pgpu_ctx* c, int32_t tID, int64_t* timestep_coll, int64_t* timestep_reac) {
+    if (!c) return PGPU_ERR_INVALID;
+    int rc;
+    if ((rc = pg_prepare(c))) return rc;
+    if (!c->dev.sigmas) PG_FAIL(c, PGPU_ERR_STATE, "pgpu_collide: VSS parameters not set");
+    reset_timings(c);
+    if ((rc = pg_reset_status(c))) return rc;
+    bool did_sort = !c->sorted;
+    if (did_sort) {
+        tic(c, 1);
+        if ((rc = pg_sort_impl(c))) return rc;
+        toc(c, 1);
+    }
+    tic(c, 2);
+    if ((rc = pg_collide_impl(c, tID))) return rc;
+    toc(c, 2);
+    rc = pg_finish(c, "pgpu_collide");
+    if (did_sort) collect(c, 1);
+    collect(c, 2);
+    c->ms[5] = c->ms[1] + c->ms[2];
+    if (timestep_coll) *timestep_coll = (int64_t)c->h_status->ncoll;
+    if (timestep_reac) *timestep_reac = (int64_t)c->h_status->nreac;
+    return rc;
+}
+
+extern "C" int pgpu_exchange(pgpu_ctx* c) {
+    if (!c) return PGPU_ERR_INVALID;
+    int rc;
+    if ((rc = pg_prepare(c))) return rc;
+    if (c->cfg.nranks <= 1) return PGPU_OK;
+    reset_timings(c);
+    if ((rc = pg_reset_status(c))) return rc;
+    tic(c, 4);
+    if ((rc = pg_exchange_impl(c))) return rc;
+    toc(c, 4);
+    rc = pg_finish(c, "pgpu_exchange");
+    collect(c, 4);
+    c->ms[5] = c->ms[4];
+    return rc;
+}
+
+int pg_mcc_impl(pgpu_ctx* c, int tID); /* pgpu_pic_mcc.cu */
+
+/* nsteps x [ADVECT -> EXCHANGE -> collisions], ref: src/timecycle.f90:271-299 */
+extern "C" int pgpu_run_steps(pgpu_ctx* c, int32_t tID0, int32_t nsteps, int64_t* total_coll, int64_t* total_reac) {
+    if (!c) return PGPU_ERR_INVALID;
+    int rc;
+    if ((rc = pg_prepare(c))) return rc;
+    if (c->cfg.collision_type == PGPU_DSMC && !c->dev.sigmas) PG_FAIL(c, PGPU_ERR_STATE, "pgpu_run_steps: VSS parameters not set");
+    if (c->cfg.collision_type == PGPU_BGK || c->cfg.collision_type == PGPU_DSMC_VAHEDI || c->cfg.collision_type == PGPU_MCC)
+        PG_FAIL(c, PGPU_ERR_UNSUPPORTED, "pgpu_run_steps: collision type %d is outside the hot path (SURVEY 2.1 rows 22, 24, 25)", c->cfg.collision_type);
+    reset_timings(c);
+    int64_t tc = 0, tr = 0;
+    cudaEvent_t e0 = c->ev[12], e1 = c->ev[13];
+    cudaEventRecord(e0, c->stream);
+    for (int s = 0; s < nsteps; s++) {
+        int tID = tID0 + s;
+        if ((rc = pg_reset_status(c))) return rc;
+        tic(c, 0);
+        if ((rc = pg_advect_impl(c, tID))) return rc;
+        toc(c, 0);
+        if (c->cfg.nranks > 1) {
+            tic(c, 4);
+            if ((rc = pg_exchange_impl(c))) return rc;
+            toc(c, 4);
+        }
+        bool dsmc = c->cfg.collision_type == PGPU_DSMC;
+        bool mcc = c->cfg.collision_type == PGPU_MCC_VAHEDI;
+        tic(c, 1);
+        if ((rc = pg_sort_impl(c))) return rc;
+        toc(c, 1);
+        tic(c, 2);
+        if (dsmc && (rc = pg_collide_impl(c, tID))) return rc;
+        if (mcc && (rc = pg_mcc_impl(c, tID))) return rc;
+        toc(c, 2);
+        rc = pg_finish(c, "pgpu_run_steps");
+        collect(c, 0); collect(c, 1); collect(c, 2);
+        if (c->cfg.nranks > 1) collect(c, 4);
+        if (rc) return rc;
+        tc += (int64_t)c->h_status->ncoll;
+        tr += (int64_t)c->h_status->nreac;
+        pg_refresh_dev(c);
+    }
+    cudaEventRecord(e1, c->stream);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    c->ms[5] = ms;
+    if (total_coll) *total_coll = tc;
+    if (total_reac) *total_reac = tr;
+    return PGPU_OK;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * counters / diagnostics
+ * ---------------------------------------------------------------------------------------- */
+extern "C" int pgpu_get_boundary_counts(pgpu_ctx* c, int64_t* b, int64_t nb, int64_t* w, int64_t nw) {
+    if (!c) return PGPU_ERR_INVALID;
+    cudaSetDevice(c->device);
+    PG_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (b && nb > 0 && c->d_bcount)
+        PG_CUDA(c, cudaMemcpy(b, c->d_bcount, sizeof(int64_t) * (size_t)std::min<int64_t>(nb, 4 * c->ns), cudaMemcpyDeviceToHost));
+    if (w && nw > 0 && c->d_wcount)
+        PG_CUDA(c, cudaMemcpy(w, c->d_wcount, sizeof(int64_t) * (size_t)std::min<int64_t>(nw, c->nw * c->ns), cudaMemcpyDeviceToHost));
+    return PGPU_OK;
+}
+
+extern "C" int pgpu_get_boundary_tallies(pgpu_ctx* c, double* t, int64_t n, int32_t reset) {
+    if (!c) return PGPU_ERR_INVALID;
+    cudaSetDevice(c->device);
+    if (!c->d_tallies) return PGPU_OK;
+    PG_CUDA(c, cudaStreamSynchronize(c->stream));
+    PG_CUDA(c, cudaMemcpy(t, c->d_tallies, sizeof(double) * (size_t)std::min<int64_t>(n, c->tallies_n), cudaMemcpyDeviceToHost));
+    if (reset) PG_CUDA(c, cudaMemset(c->d_tallies, 0, sizeof(double) * (size_t)c->tallies_n));
+    return PGPU_OK;
+}
+
+extern "C" int pgpu_get_cell_counts(pgpu_ctx* c, int32_t* npc, int64_t nc) {
+    if (!c) return PGPU_ERR_INVALID;
+    cudaSetDevice(c->device);
+    if (!c->sorted) PG_FAIL(c, PGPU_ERR_STATE, "get_cell_counts: the store is not sorted (call pgpu_sort or pgpu_collide first)");
+    int64_t m = std::min<int64_t>(nc, pg_ncells(c));
+    std::vector<unsigned int> off((size_t)m + 1);
+    PG_CUDA(c, cudaStreamSynchronize(c->stream));
+    PG_CUDA(c, cudaMemcpy(off.data(), c->d_cell_off, sizeof(unsigned int) * ((size_t)m + 1), cudaMemcpyDeviceToHost));
+    for (int64_t i = 0; i < m; i++) npc[i] = (int32_t)(off[i + 1] - off[i]);
+    return PGPU_OK;
+}

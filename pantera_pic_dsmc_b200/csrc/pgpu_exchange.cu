@@ -1,0 +1,259 @@
+/*
+ * pgpu_exchange.cu -- EXCHANGE over NCCL: ship every particle whose cell belongs to another rank.
+ *
+ * Replaces: EXCHANGE (src/grid_and_partition.f90:525-622) = reverse scan + pack of non-local particles
+ * (:562-583), COUNTING_SORT by destination (:482-518), MPI_ALLTOALL of counts (:590), MPI_ALLTOALLV of
+ * MPI_PARTICLE_DATA_STRUCTURE (:603-605), append of the received particles (:610-612); and the
+ * MPI_REDUCE + MPI_BCAST of RHS in DEPOSIT_CHARGE (src/fields.f90:5529-5535) as one ncclAllReduce.
+ *
+ * One process per GPU; the NCCL unique id is created by rank 0 and broadcast by the host program
+ * (MPI_BCAST in PANTERA, torch.distributed in this repo's harness).  NCCL is dlopen'ed on first use so
+ * that single-GPU runs have no NCCL dependency and so that the copy already loaded by the host process
+ * (e.g. the one bundled with PyTorch) is the one used.
+ *
+ * Wire format: 88-byte records {X,Y,Z,VX,VY,VZ,EROT,EVIB,DTRIM,(IC,S_ID),ID}, grouped by destination.
+ */
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+
+#include "pgpu_internal.cuh"
+
+namespace {
+
+struct NcclApi {
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*);
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int);
+    ncclResult_t (*CommDestroy)(ncclComm_t);
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t);
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+    ncclResult_t (*GroupStart)();
+    ncclResult_t (*GroupEnd)();
+    const char* (*GetErrorString)(ncclResult_t);
+    void* lib;
+};
+NcclApi g_nccl = {};
+
+const char* load_nccl() {
+    if (g_nccl.lib) return nullptr;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    void* h = nullptr;
+    for (const char* n : names) {
+        h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (h) break;
+    }
+    if (!h) return "libnccl.so.2 not found";
+#define SYM(field, name)                                   \
+    *(void**)(&g_nccl.field) = dlsym(h, name);             \
+    if (!g_nccl.field) return "missing NCCL symbol " name;
+    SYM(GetUniqueId, "ncclGetUniqueId")
+    SYM(CommInitRank, "ncclCommInitRank")
+    SYM(CommDestroy, "ncclCommDestroy")
+    SYM(AllGather, "ncclAllGather")
+    SYM(AllReduce, "ncclAllReduce")
+    SYM(Send, "ncclSend")
+    SYM(Recv, "ncclRecv")
+    SYM(GroupStart, "ncclGroupStart")
+    SYM(GroupEnd, "ncclGroupEnd")
+    SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+    g_nccl.lib = h;
+    return nullptr;
+}
+
+#define PG_NCCL(ctx, call)                                                                                  \
+    do {                                                                                                    \
+        ncclResult_t r_ = (call);                                                                           \
+        if (r_ != ncclSuccess) {                                                                            \
+            snprintf((ctx)->err, sizeof((ctx)->err), "NCCL error %s at %s:%d", g_nccl.GetErrorString(r_),   \
+                     __FILE__, __LINE__);                                                                   \
+            return PGPU_ERR_NCCL;                                                                           \
+        }                                                                                                   \
+    } while (0)
+
+#define XREC_DOUBLES 11 /* 88 bytes */
+
+/* pass 1: emigrants per destination rank (COUNTING_SORT's histogram, ref: grid_and_partition.f90:497-500) */
+__global__ void __launch_bounds__(256) xcount_kernel(const __grid_constant__ PgDev d, unsigned long long* __restrict__ xcount) {
+    __shared__ unsigned int s[64];
+    if (threadIdx.x < 64) s[threadIdx.x] = 0;
+    __syncthreads();
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < d.np) {
+        int ic = d.p.ic[i];
+        if (ic >= 1) {
+            int dest = __ldg(&d.cell_procs[ic - 1]);
+            if (dest != d.rank) atomicAdd(&s[dest], 1u);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < d.nranks && s[threadIdx.x]) atomicAdd(&xcount[threadIdx.x], (unsigned long long)s[threadIdx.x]);
+}
+
+/* pass 2: pack emigrants behind their destination's offset and tombstone them locally */
+__global__ void __launch_bounds__(256) xpack_kernel(const __grid_constant__ PgDev d, double* __restrict__ sendbuf,
+                                                    const unsigned long long* __restrict__ xoff,
+                                                    unsigned long long* __restrict__ xcursor) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d.np) return;
+    int ic = d.p.ic[i];
+    if (ic < 1) return;
+    int dest = __ldg(&d.cell_procs[ic - 1]);
+    if (dest == d.rank) return;
+    unsigned long long k = xoff[dest] + atomicAdd(&xcursor[dest], 1ULL);
+    double* r = sendbuf + k * XREC_DOUBLES;
+    r[0] = d.p.x[i]; r[1] = d.p.y[i]; r[2] = d.p.z[i];
+    r[3] = d.p.vx[i]; r[4] = d.p.vy[i]; r[5] = d.p.vz[i];
+    r[6] = d.p.erot[i]; r[7] = d.p.evib[i];
+    r[8] = d.p.dtrim ? d.p.dtrim[i] : d.dt;
+    int2 cs = make_int2(ic, d.p.sid[i]);
+    r[9] = *reinterpret_cast<double*>(&cs);
+    long long id = d.p.id ? d.p.id[i] : 0;
+    r[10] = *reinterpret_cast<double*>(&id);
+    d.p.ic[i] = PG_TOMBSTONE;
+}
+
+/* append the received records (ADD_PARTICLE_ARRAY loop, ref: grid_and_partition.f90:610-612) */
+__global__ void __launch_bounds__(256) xunpack_kernel(const __grid_constant__ PgDev d, const double* __restrict__ recvbuf,
+                                                      long long n, PgPlanes p, long long base) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double* r = recvbuf + i * XREC_DOUBLES;
+    long long o = base + i;
+    p.x[o] = r[0]; p.y[o] = r[1]; p.z[o] = r[2];
+    p.vx[o] = r[3]; p.vy[o] = r[4]; p.vz[o] = r[5];
+    p.erot[o] = r[6]; p.evib[o] = r[7];
+    double dtrim = r[8];
+    p.dtrim[o] = dtrim;
+    if (dtrim != d.dt) d.status->pad = 1;
+    double t = r[9];
+    int2 cs = *reinterpret_cast<int2*>(&t);
+    p.ic[o] = cs.x;
+    p.sid[o] = cs.y;
+    t = r[10];
+    if (p.id) p.id[o] = *reinterpret_cast<long long*>(&t);
+}
+
+__global__ void fill_kernel(double* p, long long n, double v) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+} /* namespace */
+
+extern "C" int pgpu_comm_unique_id(char id128[128]) {
+    const char* e = load_nccl();
+    if (e) return PGPU_ERR_NCCL;
+    ncclUniqueId id;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    if (g_nccl.GetUniqueId(&id) != ncclSuccess) return PGPU_ERR_NCCL;
+    memcpy(id128, &id, 128);
+    return PGPU_OK;
+}
+
+extern "C" int pgpu_comm_init(pgpu_ctx* c, int nranks, int rank, const char id128[128]) {
+    if (!c) return PGPU_ERR_INVALID;
+    cudaSetDevice(c->device);
+    if (nranks < 1 || nranks > 64 || rank < 0 || rank >= nranks) PG_FAIL(c, PGPU_ERR_INVALID, "comm_init: bad rank %d of %d (max 64 ranks)", rank, nranks);
+    const char* e = load_nccl();
+    if (e) PG_FAIL(c, PGPU_ERR_NCCL, "comm_init: %s", e);
+    ncclUniqueId id;
+    memcpy(&id, id128, 128);
+    ncclComm_t comm;
+    PG_NCCL(c, g_nccl.CommInitRank(&comm, nranks, id, rank));
+    c->nccl_comm = (void*)comm;
+    c->comm_nranks = nranks;
+    c->comm_rank = rank;
+    PG_CUDA(c, cudaMalloc((void**)&c->d_xcount, sizeof(unsigned long long) * 64 * 4 + sizeof(unsigned long long) * 64 * 64));
+    return PGPU_OK;
+}
+
+extern "C" void pg_comm_destroy(pgpu_ctx* c) {
+    if (c->nccl_comm && g_nccl.lib) g_nccl.CommDestroy((ncclComm_t)c->nccl_comm);
+    c->nccl_comm = nullptr;
+}
+
+int pg_allreduce_sum_f64(pgpu_ctx* c, double* buf, long long n) {
+    if (!c->nccl_comm) PG_FAIL(c, PGPU_ERR_STATE, "nranks > 1 but pgpu_comm_init has not been called");
+    PG_NCCL(c, g_nccl.AllReduce(buf, buf, (size_t)n, ncclDouble, ncclSum, (ncclComm_t)c->nccl_comm, c->stream));
+    return PGPU_OK;
+}
+
+int pg_exchange_impl(pgpu_ctx* c) {
+    const int nr = c->cfg.nranks;
+    if (nr <= 1) return PGPU_OK;
+    if (!c->nccl_comm) PG_FAIL(c, PGPU_ERR_STATE, "exchange: pgpu_comm_init has not been called");
+    if (nr != c->comm_nranks || c->cfg.rank != c->comm_rank) PG_FAIL(c, PGPU_ERR_STATE, "exchange: config rank/nranks differ from the communicator");
+    if (!c->dev.cell_procs) PG_FAIL(c, PGPU_ERR_STATE, "exchange: CELL_PROCS not set");
+    int rc;
+    pg_refresh_dev(c);
+    ncclComm_t comm = (ncclComm_t)c->nccl_comm;
+    unsigned long long* xcount = c->d_xcount;          /* [64] my counts per destination */
+    unsigned long long* xoff = c->d_xcount + 64;       /* [64] */
+    unsigned long long* xcursor = c->d_xcount + 128;   /* [64] */
+    unsigned long long* xall = c->d_xcount + 256;      /* [nr][64] everyone's counts */
+    PG_CUDA(c, cudaMemsetAsync(c->d_xcount, 0, sizeof(unsigned long long) * 256, c->stream));
+    unsigned int blocks = (unsigned int)((c->np + 255) / 256);
+    if (c->np > 0) {
+        xcount_kernel<<<blocks, 256, 0, c->stream>>>(c->dev, xcount);
+        c->launches++;
+    }
+    /* MPI_ALLTOALL of the counts -> all-gather of the 64-entry rows */
+    PG_NCCL(c, g_nccl.AllGather(xcount, xall, 64, ncclUint64, comm, c->stream));
+    std::vector<unsigned long long> h((size_t)nr * 64);
+    PG_CUDA(c, cudaMemcpyAsync(h.data(), xall, sizeof(unsigned long long) * (size_t)nr * 64, cudaMemcpyDeviceToHost, c->stream));
+    PG_CUDA(c, cudaStreamSynchronize(c->stream));
+    std::vector<unsigned long long> soff(65, 0), roff(65, 0);
+    for (int r = 0; r < nr; r++) {
+        soff[r + 1] = soff[r] + h[(size_t)c->cfg.rank * 64 + r];
+        roff[r + 1] = roff[r] + h[(size_t)r * 64 + c->cfg.rank];
+    }
+    long long nsend = (long long)soff[nr], nrecv = (long long)roff[nr];
+    long long need = std::max(nsend, nrecv);
+    if (need > c->xbuf_capacity) {
+        cudaFree(c->d_sendbuf); cudaFree(c->d_recvbuf);
+        c->d_sendbuf = c->d_recvbuf = nullptr;
+        long long cap = need + need / 2 + 1024;
+        PG_CUDA(c, cudaMalloc(&c->d_sendbuf, sizeof(double) * XREC_DOUBLES * (size_t)cap));
+        PG_CUDA(c, cudaMalloc(&c->d_recvbuf, sizeof(double) * XREC_DOUBLES * (size_t)cap));
+        c->xbuf_capacity = cap;
+    }
+    if ((rc = pg_ensure_capacity(c, c->np + nrecv))) return rc;
+    pg_refresh_dev(c);
+    if (nsend > 0) {
+        PG_CUDA(c, cudaMemcpyAsync(xoff, soff.data(), sizeof(unsigned long long) * 64, cudaMemcpyHostToDevice, c->stream));
+        xpack_kernel<<<blocks, 256, 0, c->stream>>>(c->dev, (double*)c->d_sendbuf, xoff, xcursor);
+        c->launches++;
+        c->maybe_tombstones = true;
+    }
+    /* MPI_ALLTOALLV -> one grouped send/recv to every peer with traffic */
+    PG_NCCL(c, g_nccl.GroupStart());
+    for (int r = 0; r < nr; r++) {
+        if (r == c->cfg.rank) continue;
+        unsigned long long ns = soff[r + 1] - soff[r], nv = roff[r + 1] - roff[r];
+        if (ns) PG_NCCL(c, g_nccl.Send((const double*)c->d_sendbuf + soff[r] * XREC_DOUBLES, (size_t)ns * XREC_DOUBLES, ncclDouble, r, comm, c->stream));
+        if (nv) PG_NCCL(c, g_nccl.Recv((double*)c->d_recvbuf + roff[r] * XREC_DOUBLES, (size_t)nv * XREC_DOUBLES, ncclDouble, r, comm, c->stream));
+    }
+    PG_NCCL(c, g_nccl.GroupEnd());
+    if (nrecv > 0) {
+        PgPlanes p = c->planes[c->cur];
+        xunpack_kernel<<<(unsigned int)((nrecv + 255) / 256), 256, 0, c->stream>>>(c->dev, (const double*)c->d_recvbuf, nrecv, p, c->np);
+        c->launches++;
+        PG_CUDA(c, cudaMemcpyAsync(&c->h_status->pad, &c->d_status->pad, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        PG_CUDA(c, cudaStreamSynchronize(c->stream));
+        if (c->h_status->pad && !c->has_dtrim) {
+            if (c->np > 0) fill_kernel<<<(unsigned int)((c->np + 255) / 256), 256, 0, c->stream>>>(p.dtrim, c->np, c->cfg.dt);
+            c->has_dtrim = true;
+        }
+        c->np += nrecv;
+        c->id_counter = std::max(c->id_counter, c->np);
+    }
+    c->sorted = false;
+    c->hist_valid = false;
+    pg_refresh_dev(c);
+    PG_CUDA(c, cudaGetLastError());
+    return PGPU_OK;
+}

@@ -1,0 +1,408 @@
+/*
+ * pgpu_internal.cuh -- shared declarations of libpantera_gpu.so (CUDA, sm_100a).
+ *
+ * Layout of the device particle store (DESIGN.md "Data layout in HBM"):
+ *   structure of arrays, one FP64 plane per attribute  X Y Z VX VY VZ EROT EVIB  (64 B/particle),
+ *   INT32 planes IC and S_ID (8 B/particle) -> 72 B/particle of streamed state, two copies
+ *   (ping-pong) so that the per-step counting sort is a single scatter pass.
+ *   Optional planes: DTRIM (only while some particle has DTRIM != DT, i.e. right after a host-side
+ *   injection, src/timecycle.f90:463) and ID (cfg.track_id).
+ *   A removed particle is a tombstone IC = -1 until the next sort compacts it away.
+ *
+ * All "ref:" comments cite files of the reference tree (vonkarmaninstitute/pantera-pic-dsmc).
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/pantera_gpu.h"
+
+/* physical constants, ref: src/global.f90:31-37 */
+#define PG_PI 3.1415926535897932
+#define PG_EPS0 8.8541878128e-12
+#define PG_KB 1.380649e-23
+#define PG_QE 1.602176634e-19
+
+#define PG_TOMBSTONE (-1)
+#define PG_MAX_HOPS 1000000 /* guard against a malformed mesh hanging the GPU */
+
+/* status block, device resident, read back at the end of every hot-path call */
+struct PgStatus {
+    unsigned long long n_removed;   /* particles tombstoned by the current call          */
+    unsigned long long n_appended;  /* particles appended past np by the current call    */
+    unsigned long long n_hits;      /* entries in the deferred boundary-hit list         */
+    unsigned long long ncoll;       /* TIMESTEP_COLL                                     */
+    unsigned long long nreac;       /* TIMESTEP_REAC                                     */
+    unsigned long long pending;     /* collision candidates still waiting                */
+    unsigned long long n_emigrants; /* particles leaving this rank                       */
+    int err;                        /* first device-side error code (0 = none)           */
+    int pad;
+};
+enum { PG_DEVERR_NONE = 0, PG_DEVERR_HOPS = 1, PG_DEVERR_CELL_RANGE = 2, PG_DEVERR_CAPACITY = 3 };
+
+struct PgPlanes {
+    double *x, *y, *z, *vx, *vy, *vz, *erot, *evib;
+    int32_t *ic, *sid;
+    double* dtrim; /* may be null */
+    int64_t* id;   /* may be null */
+};
+
+/* one reaction, ref: REACTIONS_DATA_STRUCTURE src/global.f90:542-558 */
+struct PgReaction {
+    int type, r1, r2, p1, p2, p3, p4, nprod, is_cex;
+    int tab_off, tab_n;
+    int pad;
+    double ea, c1, c2, c3;
+};
+
+/* everything a kernel needs, passed by value as a __grid_constant__ argument */
+struct PgDev {
+    /* --- scalars of pgpu_config --- */
+    int dims, axi, grid_type, nx, ny;
+    double xmin, xmax, ymin, ymax, zmin, zmax, dt, fnum;
+    int pic, coll_type;
+    int bper[4], bspec[4], bdiff[4], breact[4];
+    int zper, yper;
+    double boundtemp, extb[3], eps_scaling, mcc_dens, mcc_ttra;
+    unsigned long long seed_local; /* RNG_SEED_GLOBAL*(PROC_ID+1), ref: src/initialization.f90:2294-2296 */
+    int rank, nranks;
+    int tally_on; /* MOD(tID-DUMP_BOUND_START, DUMP_BOUND_AVG_EVERY)==0, ref: src/timecycle.f90:1375 */
+    int tID;
+    /* --- species --- */
+    int ns;
+    const double *mass, *charge, *rotrel, *vibrel;
+    const int *rotdof, *vibdof;
+    /* --- VSS pair tables (IS,JS) column-major --- */
+    const double *sigmas, *omegas, *alphas, *grefs;
+    double sigmamax;
+    /* --- reactions --- */
+    int nr;
+    const PgReaction* reac;
+    const double *tab_e, *tab_cs;
+    /* --- wall reactions --- */
+    int nwr;
+    const int *wr_r, *wr_p1, *wr_nprod;
+    const double* wr_prob;
+    /* --- MCC background --- */
+    int mcc_ncomp;
+    const int* mcc_sp;
+    const double* mcc_frac;
+    /* --- unstructured mesh, device layout --- */
+    int nn, nc, nf;
+    const double* face_geo;  /* [nc][nf][6]: outward normal (3), a point on the face (3) */
+    const int* face_code;    /* [nc][nf]: >0 neighbour cell to hop into; 0 boundary without a physical
+                                group (remove); <0 boundary with physical group -code        */
+    const double *face_tang1, *face_tang2; /* [nc][4][3] (3-D) */
+    const double* edge_len;                /* [nc][3] (2-D) */
+    const int* face_bidx;                  /* [nc][nf] boundary element (1-based) or -1 */
+    const double* bound_area;
+    int nboundcells;
+    const int* cell_nodes;    /* [nc][nf] 1-based */
+    const double* basis;      /* [nc][nf][nf] BASIS_COEFFS(j,i,ic) */
+    const double* cell_vol;   /* [nc] */
+    const int* cell_procs;    /* [ncells] or null */
+    /* --- boundary conditions GRID_BC(:) --- */
+    int nbc;
+    const int *bc_particle, *bc_field, *bc_react;
+    const double *bc_temp, *bc_accn, *bc_acct;
+    /* --- interior walls of structured grids --- */
+    int nw;
+    const double *w_x1, *w_y1, *w_x2, *w_y2, *w_nx, *w_ny, *w_temp, *w_transm;
+    const int *w_spec, *w_diff, *w_porous, *w_react;
+    /* --- non-uniform rectilinear grid --- */
+    int nxp, nyp;
+    const double *xcoord, *ycoord;
+    /* --- fields --- */
+    const double* e_field;
+    const double* b_field;
+    double* surface_charge;
+    /* --- counters / tallies --- */
+    unsigned long long* bcount; /* 4*ns */
+    unsigned long long* wcount; /* nw*ns */
+    double* tallies;            /* 10 * ns * nboundcells */
+    PgStatus* status;
+    /* --- particle store --- */
+    PgPlanes p;
+    long long np;       /* slots in use [0,np) (may contain tombstones) */
+    long long capacity; /* slots allocated */
+    int ncells;         /* nc (unstructured) or nx*ny */
+    unsigned int* cell_count; /* [ncells] histogram of IC filled by the ADVECT epilogue */
+    unsigned int* cell_rank;  /* [capacity] arrival rank of the particle inside its cell */
+    unsigned int* cell_off;   /* [ncells+1] exclusive prefix of cell_count (valid while sorted) */
+    unsigned int* hitlist;    /* slots deferred to the boundary-interaction pass */
+    long long id_base;        /* ID counter for particles created on the device */
+};
+
+/* ------------------------------------------------------------------------------------------
+ * host context
+ * ---------------------------------------------------------------------------------------- */
+template <class T>
+struct DevBuf {
+    T* d = nullptr;
+    size_t n = 0;
+};
+
+struct pgpu_ctx {
+    char err[512];
+    int device;
+    cudaStream_t stream;
+    pgpu_config cfg;
+    bool cfg_set;
+    PgDev dev; /* host mirror of the kernel argument */
+
+    /* raw host copies needed to (re)build the packed mesh when BCs change */
+    int mesh_dims, nn, nc;
+    std::vector<double> h_node_coords, h_face_normal;
+    std::vector<int32_t> h_cell_nodes, h_cell_neighbors, h_cell_faces_pg, h_cell_pg;
+    std::vector<int32_t> h_bc_volume;
+    bool mesh_set, mesh_dirty;
+
+    /* owned device allocations (freed in destroy) */
+    std::vector<void*> owned;
+    /* named table slots so that a setter can replace its arrays */
+    void* slot[64];
+
+    /* particle store */
+    PgPlanes planes[2];
+    int cur;
+    long long np, capacity;
+    bool has_dtrim, sorted, hist_valid, maybe_tombstones;
+    long long id_counter;
+    unsigned int *d_cell_count, *d_rank, *d_cell_off, *d_hitlist;
+    long long hit_capacity;
+    int ncells_alloc;
+    PgStatus* d_status;
+    PgStatus* h_status; /* pinned */
+    void* d_scan_tmp;
+    size_t scan_tmp_bytes;
+
+    /* collision scratch */
+    void* d_cand;      /* uint4 per candidate */
+    long long cand_capacity;
+    unsigned int* d_owner;
+    long long owner_capacity;
+    int* d_cell_ncoll;       /* [ncells] */
+    unsigned int* d_cand_off; /* [ncells+1] */
+    double* d_cell_vrmax;    /* [ncells] */
+    double* d_cell_fcorr;    /* [ncells] */
+    int cellscratch_alloc;
+
+    /* staging for AoS <-> SoA */
+    void* d_stage[2];
+    size_t stage_bytes;
+    void* h_stage[2]; /* pinned bounce buffers for pageable host memory */
+
+    /* deposit */
+    double* d_rhs;
+    long long rhs_n;
+
+    /* counters */
+    long long ns, nw;
+    unsigned long long *d_bcount, *d_wcount;
+    double* d_tallies;
+    long long tallies_n;
+    double* d_surface_charge;
+    long long nsc;
+
+    /* timings */
+    cudaEvent_t ev[16];
+    double ms[8];
+    long long launches;
+
+    /* NCCL (dlopen'ed lazily) */
+    void* nccl_lib;
+    void* nccl_comm;
+    int comm_nranks, comm_rank;
+    void* d_sendbuf;
+    void* d_recvbuf;
+    long long xbuf_capacity; /* particles */
+    unsigned long long* d_xcount; /* [nranks] emigrant counts + cursors */
+};
+
+#define PG_FAIL(ctx, code, ...)                                   \
+    do {                                                          \
+        snprintf((ctx)->err, sizeof((ctx)->err), __VA_ARGS__);    \
+        return (code);                                            \
+    } while (0)
+
+#define PG_CUDA(ctx, call)                                                                          \
+    do {                                                                                            \
+        cudaError_t e_ = (call);                                                                    \
+        if (e_ != cudaSuccess) {                                                                    \
+            snprintf((ctx)->err, sizeof((ctx)->err), "CUDA error %s at %s:%d (%s)",                 \
+                     cudaGetErrorString(e_), __FILE__, __LINE__, #call);                            \
+            return PGPU_ERR_CUDA;                                                                   \
+        }                                                                                           \
+    } while (0)
+
+/* internal entry points shared across translation units */
+int pg_prepare(pgpu_ctx* c);                 /* validate state, rebuild packed mesh, refresh c->dev */
+int pg_finish(pgpu_ctx* c, const char* what); /* sync stream, read back status, map device errors */
+int pg_ensure_capacity(pgpu_ctx* c, long long n);
+int pg_ensure_cell_arrays(pgpu_ctx* c);
+int pg_reset_status(pgpu_ctx* c);
+int pg_sort_impl(pgpu_ctx* c);               /* histogram (if needed) + scan + scatter; async */
+int pg_advect_impl(pgpu_ctx* c, int tID);    /* async */
+int pg_collide_impl(pgpu_ctx* c, int tID);   /* async except for the dependency-round loop */
+int pg_exchange_impl(pgpu_ctx* c);
+void pg_refresh_dev(pgpu_ctx* c);
+
+static inline int pg_ncells(const pgpu_ctx* c) {
+    return (c->cfg.grid_type == PGPU_UNSTRUCTURED) ? c->nc : c->cfg.nx * c->cfg.ny;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * device helpers
+ * ---------------------------------------------------------------------------------------- */
+#ifdef __CUDACC__
+
+/* Philox4x32-10 (Salmon et al., SC'11) */
+__device__ __forceinline__ void pg_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                          uint32_t k1, uint32_t* out) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        uint32_t n0 = hi1 ^ c1 ^ k0;
+        uint32_t n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+/*
+ * Counter-based stream, one per (kind, timestep, entity): replaces the reference's single
+ * sequential MT19937-64 stream rf() (src/tools.f90:33-43).  Contract (also implemented by the
+ * oracle's rng_mode 1):  key = { seed_lo ^ kind*0x632BE5AB, seed_hi ^ tID },
+ * counter = { draw/2, e0_lo, e0_hi, e1 }; each block yields two 53-bit uniforms on [0,1).
+ * kinds: 1 ADVECT (e0 = particle slot), 2 DSMC (e0 = cell 0-based, e1 = candidate), 3 MCC (e0 = slot).
+ */
+struct PgRng {
+    uint32_t k0, k1, e0, e1, e2, ndraw;
+    uint32_t b2, b3;
+    __device__ __forceinline__ void init(unsigned long long seed, int kind, int tID, unsigned long long ent0,
+                                         unsigned long long ent1) {
+        k0 = (uint32_t)seed ^ ((uint32_t)kind * 0x632BE5ABu);
+        k1 = (uint32_t)(seed >> 32) ^ (uint32_t)tID;
+        e0 = (uint32_t)ent0;
+        e1 = (uint32_t)(ent0 >> 32);
+        e2 = (uint32_t)ent1;
+        ndraw = 0;
+        b2 = b3 = 0;
+    }
+    __device__ __forceinline__ double rf() {
+        uint32_t n = ndraw++;
+        uint32_t lo, hi;
+        if ((n & 1u) == 0) {
+            uint32_t o[4];
+            pg_philox(n >> 1, e0, e1, e2, k0, k1, o);
+            lo = o[0]; hi = o[1];
+            b2 = o[2]; b3 = o[3];
+        } else {
+            lo = b2; hi = b3;
+        }
+        unsigned long long u = ((unsigned long long)hi << 32) | lo;
+        return (double)(u >> 11) * (1.0 / 9007199254740992.0);
+    }
+    /* resume a stream at draw n (n may be odd: the block is regenerated) */
+    __device__ __forceinline__ void seek(uint32_t n) {
+        ndraw = n;
+        if (n & 1u) {
+            uint32_t o[4];
+            pg_philox(n >> 1, e0, e1, e2, k0, k1, o);
+            b2 = o[2]; b3 = o[3];
+        }
+    }
+};
+
+/* ref: src/tools.f90:130-187 MAXWELL with zero drift and one temperature on all axes */
+__device__ __forceinline__ void pg_maxwell0(PgRng& g, double t, double m, double* v3) {
+    const double PI2 = 2. * PG_PI;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        if (t == 0.0) {
+            v3[i] = 0.;
+        } else {
+            double r = g.rf();
+            double teta = PI2 * r;
+            double beta = 1. / sqrt(2. * PG_KB / m * t);
+            double r1 = g.rf();
+            while (r1 < 1.0e-13) r1 = g.rf();
+            double ro = sqrt(-log(r1)) / beta;
+            v3[i] = 0. + ro * sin(teta);
+        }
+    }
+}
+
+/* ref: src/tools.f90:245-285 INTERNAL_ENERGY */
+__device__ __forceinline__ double pg_internal_energy(PgRng& g, int dof, double temp) {
+    if (dof == 0) return 0.;
+    if (dof == 2) {
+        double r = g.rf();
+        while (r < 1.0e-13) r = g.rf();
+        return -log(r) * PG_KB * temp;
+    }
+    double param = (dof == 1) ? (double)5.0f : (double)0.01f;
+    double r = g.rf();
+    double x = -log(r);
+    r = g.rf();
+    while (r > pow(x / param, dof / 2. - 1.)) {
+        r = g.rf();
+        x = -log(r);
+        r = g.rf();
+    }
+    return x * PG_KB * temp;
+}
+
+/* ref: src/tools.f90:1150-1186 FLX */
+__device__ __forceinline__ double pg_flx(PgRng& g, double sn, double tinf, double m) {
+    double beta = 1. / sqrt(2. * PG_KB / m * tinf);
+    double acca = sqrt(sn * sn + 2.);
+    double kappa = 2. / (sn + acca) * exp(0.5 + 0.5 * sn * (sn - acca));
+    for (;;) {
+        double r1 = g.rf();
+        double y = -3. + 6. * r1;
+        double r2 = g.rf();
+        double fm = kappa * (y + sn) * exp(-(y * y));
+        if (r2 <= fm) return y / beta;
+    }
+}
+
+/* ref: src/tools.f90:1544-1593 INTERP_CS (1-based bisection on 0-based arrays) */
+__device__ __forceinline__ double pg_interp_cs(double e, int n, const double* __restrict__ te,
+                                               const double* __restrict__ tcs) {
+    int L = 1, R = n, idx;
+    if (e < te[L - 1]) return 0;
+    if (e > te[R - 1]) return 0;
+    if (R == L + 1) return tcs[L - 1] + (tcs[R - 1] - tcs[L - 1]) * (e - te[L - 1]) / (te[R - 1] - te[L - 1]);
+    /* DEVIATION: for e == TABLE_EN(R) exactly the reference's bisection never terminates
+     * (src/tools.f90:1574-1586); the table end value is returned instead. */
+    if (e == te[R - 1]) return tcs[R - 1];
+    for (;;) {
+        idx = (L + R) / 2;
+        if (te[idx - 1] <= e) {
+            if (te[idx] > e) break;
+            L = idx;
+        } else {
+            if (te[idx - 2] <= e) {
+                idx = idx - 1;
+                break;
+            }
+            R = idx;
+        }
+    }
+    L = idx;
+    R = idx + 1;
+    return tcs[L - 1] + (tcs[R - 1] - tcs[L - 1]) * (e - te[L - 1]) / (te[R - 1] - te[L - 1]);
+}
+
+__device__ __forceinline__ void pg_set_err(const PgDev& d, int code) { atomicCAS(&d.status->err, 0, code); }
+
+#endif /* __CUDACC__ */

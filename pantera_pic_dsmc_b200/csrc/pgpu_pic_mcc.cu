@@ -1,0 +1,285 @@
+/*
+ * pgpu_pic_mcc.cu -- PIC charge deposition, null-collision MCC and species removal.
+ *
+ * Replaces: the particle loop of DEPOSIT_CHARGE + SURFACE_CHARGE + the MPI_REDUCE/MPI_BCAST of RHS
+ * (src/fields.f90:5440-5535; COMPUTE_WEIGHTS :5341-5431), MCC_COLLISIONS_VAHEDI
+ * (src/collisions.f90:1606-1892), REMOVE_PARTICLES_OF_SPECIES (src/timecycle.f90:2340-2353).
+ * The Dirichlet/Neumann row fill and the PETSc vector load (src/fields.f90:5538-5561) stay on the host.
+ */
+#include <algorithm>
+
+#include "pgpu_internal.cuh"
+#include "pgpu_physics.cuh"
+
+int pg_allreduce_sum_f64(pgpu_ctx* c, double* buf, long long n); /* pgpu_exchange.cu */
+
+namespace {
+
+/*
+ * One thread per particle.  SMEM: the node array is privatised per block in shared memory (1-D / small
+ * 2-D meshes: millions of particles land on a few hundred nodes, so global atomics would serialise), and
+ * flushed with one FP64 atomic per touched node per block.  Otherwise FP64 atomics go straight to the
+ * L2-resident RHS.
+ */
+template <bool SMEM>
+__global__ void __launch_bounds__(256) deposit_kernel(const __grid_constant__ PgDev d, double* __restrict__ rhs, int nn) {
+    extern __shared__ double srhs[];
+    if (SMEM) {
+        for (int i = threadIdx.x; i < nn; i += blockDim.x) srhs[i] = 0.;
+        __syncthreads();
+    }
+    double* acc = SMEM ? srhs : rhs;
+    const double K = PG_QE / (PG_EPS0 * (d.eps_scaling * d.eps_scaling));
+    for (long long jp = (long long)blockIdx.x * blockDim.x + threadIdx.x; jp < d.np; jp += (long long)gridDim.x * blockDim.x) {
+        int ic = d.p.ic[jp];
+        if (ic < 1) continue;
+        int sid = d.p.sid[jp];
+        double charge = __ldg(&d.charge[sid - 1]);
+        if (fabs(charge) < 1.e-6) continue;
+        double x = d.p.x[jp];
+        if (d.grid_type == PGPU_UNSTRUCTURED) {
+            size_t c = (size_t)(ic - 1);
+            if (d.dims == 1) {
+                double rho_q = K * charge * d.fnum / (d.ymax - d.ymin) / (d.zmax - d.zmin);
+                for (int p = 0; p < 2; p++) {
+                    int vp = __ldg(&d.cell_nodes[2 * c + p]) - 1;
+                    const double* bs = d.basis + 4 * c + 2 * p;
+                    double psip = __ldg(&bs[0]) * x + __ldg(&bs[1]);
+                    atomicAdd(&acc[vp], rho_q * psip);
+                }
+            } else if (d.dims == 2) {
+                double y = d.p.y[jp];
+                double rho_q = K * charge * d.fnum / (d.zmax - d.zmin);
+                for (int p = 0; p < 3; p++) {
+                    int vp = __ldg(&d.cell_nodes[3 * c + p]) - 1;
+                    const double* bs = d.basis + 9 * c + 3 * p;
+                    double psip = __ldg(&bs[0]) * x + __ldg(&bs[1]) * y + __ldg(&bs[2]);
+                    atomicAdd(&acc[vp], rho_q * psip);
+                }
+            } else {
+                double y = d.p.y[jp], z = d.p.z[jp];
+                double rho_q = K * charge * d.fnum;
+                for (int p = 0; p < 4; p++) {
+                    int vp = __ldg(&d.cell_nodes[4 * c + p]) - 1;
+                    const double* bs = d.basis + 16 * c + 4 * p;
+                    double psip = __ldg(&bs[0]) * x + __ldg(&bs[1]) * y + __ldg(&bs[2]) * z + __ldg(&bs[3]);
+                    atomicAdd(&acc[vp], rho_q * psip);
+                }
+            }
+        } else {
+            /* ref: src/fields.f90:5341-5431 COMPUTE_WEIGHTS + :5494-5520 */
+            double y = d.p.y[jp];
+            int nx = d.nx;
+            int i = (ic - 1) % nx, j = (ic - 1) / nx;
+            double hx, hy, cxmin, cymin;
+            if (d.grid_type == PGPU_RECTILINEAR_UNIFORM) {
+                hx = (d.xmax - d.xmin) / (double)nx;
+                hy = (d.ymax - d.ymin) / (double)d.ny;
+                cxmin = i * hx + d.xmin;
+                cymin = j * hy + d.ymin;
+            } else {
+                hx = d.xcoord[i + 1] - d.xcoord[i];
+                hy = d.ycoord[j + 1] - d.ycoord[j];
+                cxmin = d.xcoord[i];
+                cymin = d.ycoord[j];
+            }
+            double fx = (x - cxmin) / hx;
+            double fy = (y - cymin) / hy;
+            double vol = (d.xmax - d.xmin) * (d.ymax - d.ymin) * (d.zmax - d.zmin) / (d.nx * d.ny);
+            double rho_q = -K * charge * d.fnum / vol;
+            if (d.dims == 2) {
+                int i0 = ic + j - 1;
+                atomicAdd(&acc[i0], rho_q * ((1. - fx) * (1. - fy)));
+                atomicAdd(&acc[i0 + 1], rho_q * (fx * (1. - fy)));
+                atomicAdd(&acc[i0 + nx + 1], rho_q * ((1. - fx) * fy));
+                atomicAdd(&acc[i0 + nx + 2], rho_q * (fx * fy));
+            } else {
+                atomicAdd(&acc[ic - 1], rho_q * (1. - fx));
+                atomicAdd(&acc[ic], rho_q * fx);
+            }
+        }
+    }
+    if (SMEM) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < nn; i += blockDim.x) {
+            double v = srhs[i];
+            if (v != 0.) atomicAdd(&rhs[i], v);
+        }
+    }
+}
+
+__global__ void add_surface_charge_kernel(double* __restrict__ rhs, const double* __restrict__ sc, long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) rhs[i] = rhs[i] + sc[i];
+}
+
+/* ref: src/collisions.f90:1646-1890, one thread per particle present at entry */
+__global__ void __launch_bounds__(128) mcc_vahedi_kernel(const __grid_constant__ PgDev d, double p_null) {
+    long long jp1 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (jp1 >= d.np) return;
+    int ic = d.p.ic[jp1];
+    if (ic < 1) return;
+    PgRng g;
+    g.init(d.seed_local, 3, d.tID, (unsigned long long)jp1, 0ULL);
+    if (g.rf() > p_null) return;
+    atomicAdd(&d.status->ncoll, 1ULL);
+    const double dt = d.dt;
+    int s1 = d.p.sid[jp1];
+    double c1[3] = {d.p.vx[jp1], d.p.vy[jp1], d.p.vz[jp1]};
+    for (int j = 0; j < d.mcc_ncomp; j++) {
+        int s2 = d.mcc_sp[j];
+        double bg_nrho = d.mcc_frac[j] * d.mcc_dens;
+        if (bg_nrho == 0) continue;
+        double c2[3];
+        pg_maxwell0(g, d.mcc_ttra, d.mass[s2 - 1], c2);
+        double vr2 = (c2[0] - c1[0]) * (c2[0] - c1[0]) + (c2[1] - c1[1]) * (c2[1] - c1[1]) + (c2[2] - c1[2]) * (c2[2] - c1[2]);
+        double vr = sqrt(vr2);
+        double r_select = g.rf();
+        double m1 = d.mass[s1 - 1], m2 = d.mass[s2 - 1];
+        double mred = m1 * m2 / (m1 + m2);
+        double etr = 0.5 * mred * vr2;
+        double p_cum = 0;
+        for (int jr = 0; jr < d.nr; jr++) {
+            const PgReaction r = d.reac[jr];
+            if (r.r1 != s1 || r.r2 != s2) continue;
+            double ea = r.ea;
+            if (etr <= ea) continue;
+            if (r.type != PGPU_LXCAT) continue;
+            double sigma_r = pg_interp_cs(etr, r.tab_n, d.tab_e + r.tab_off, d.tab_cs + r.tab_off);
+            p_cum = p_cum + (1. - exp(-bg_nrho * sigma_r * vr * dt)) / p_null;
+            if (r_select < p_cum) {
+                /* materialise the background partner at the particle's position (ref: :1726-1741) */
+                double erot2 = pg_internal_energy(g, d.rotdof[s2 - 1], d.mcc_ttra);
+                double evib2 = pg_internal_energy(g, d.vibdof[s2 - 1], d.mcc_ttra);
+                double x = d.p.x[jp1], y = d.p.y[jp1], z = d.p.z[jp1];
+                atomicAdd(&d.status->nreac, 1ULL);
+                double ecoll = etr - ea;
+                double erot1 = d.p.erot[jp1], evib1 = d.p.evib[jp1];
+                int bad = 0;
+                if (!r.is_cex) {
+                    /* products past the second are appended by the redistribution itself; the oracle
+                     * appends the partner first, so creation order differs but not the set of particles */
+                    bad = pg_react_redistribute(d, g, r, ecoll, c1, c2, erot1, evib1, erot2, evib2, x, y, z, ic);
+                    d.p.erot[jp1] = erot1; d.p.evib[jp1] = evib1;
+                    d.p.vx[jp1] = c1[0]; d.p.vy[jp1] = c1[1]; d.p.vz[jp1] = c1[2];
+                }
+                (void)bad;
+                d.p.sid[jp1] = r.p1;
+                pg_append_particle(d, x, y, z, c2[0], c2[1], c2[2], erot2, evib2, r.p2, ic);
+                return;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) remove_species_kernel(const __grid_constant__ PgDev d, int sp) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d.np) return;
+    if (d.p.ic[i] < 1) return;
+    if (d.p.sid[i] == sp) {
+        d.p.ic[i] = PG_TOMBSTONE;
+        atomicAdd(&d.status->n_removed, 1ULL);
+    }
+}
+
+} /* namespace */
+
+static int nnodes_of(const pgpu_ctx* c) {
+    if (c->cfg.grid_type == PGPU_UNSTRUCTURED) return c->nn;
+    return (c->cfg.dims == 1) ? c->cfg.nx + 1 : (c->cfg.nx + 1) * (c->cfg.ny + 1);
+}
+
+extern "C" int pgpu_deposit_charge(pgpu_ctx* c, double* rhs_host, int64_t nnodes) {
+    if (!c) return PGPU_ERR_INVALID;
+    int rc;
+    if ((rc = pg_prepare(c))) return rc;
+    int nn = nnodes_of(c);
+    if (!rhs_host || nnodes < nn) PG_FAIL(c, PGPU_ERR_INVALID, "deposit_charge: rhs too small (%lld < %d)", (long long)nnodes, nn);
+    if (c->cfg.grid_type == PGPU_UNSTRUCTURED && !c->dev.basis) PG_FAIL(c, PGPU_ERR_STATE, "deposit_charge: mesh without BASIS_COEFFS");
+    if (c->rhs_n < nn) {
+        cudaFree(c->d_rhs);
+        c->d_rhs = nullptr;
+        PG_CUDA(c, cudaMalloc((void**)&c->d_rhs, sizeof(double) * (size_t)nn));
+        c->rhs_n = nn;
+    }
+    memset(c->ms, 0, sizeof(c->ms));
+    c->launches = 0;
+    if ((rc = pg_reset_status(c))) return rc;
+    cudaEventRecord(c->ev[6], c->stream);
+    PG_CUDA(c, cudaMemsetAsync(c->d_rhs, 0, sizeof(double) * (size_t)nn, c->stream));
+    if (c->np > 0) {
+        const PgDev& d = c->dev;
+        int blocks = (int)std::min<long long>((c->np + 255) / 256, 148LL * 8);
+        size_t smem = sizeof(double) * (size_t)nn;
+        if (smem <= 48 * 1024) deposit_kernel<true><<<blocks, 256, smem, c->stream>>>(d, c->d_rhs, nn);
+        else deposit_kernel<false><<<blocks, 256, 0, c->stream>>>(d, c->d_rhs, nn);
+        c->launches++;
+    }
+    /* RHS = RHS + SURFACE_CHARGE on the rank that owns it (every rank holds the same replicated array in
+     * the reference; only rank 0 adds it here so that the all-reduce counts it once), ref: :5525 */
+    if (c->d_surface_charge && c->cfg.grid_type == PGPU_UNSTRUCTURED && (c->cfg.nranks <= 1 || c->cfg.rank == 0)) {
+        long long m = std::min<long long>(nn, c->nsc);
+        add_surface_charge_kernel<<<(unsigned int)((m + 255) / 256), 256, 0, c->stream>>>(c->d_rhs, c->d_surface_charge, m);
+        c->launches++;
+    }
+    if (c->cfg.nranks > 1 && (rc = pg_allreduce_sum_f64(c, c->d_rhs, nn))) return rc;
+    PG_CUDA(c, cudaMemcpyAsync(rhs_host, c->d_rhs, sizeof(double) * (size_t)nn, cudaMemcpyDeviceToHost, c->stream));
+    cudaEventRecord(c->ev[7], c->stream);
+    rc = pg_finish(c, "pgpu_deposit_charge");
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, c->ev[6], c->ev[7]) == cudaSuccess) c->ms[3] = ms;
+    c->ms[5] = c->ms[3];
+    return rc;
+}
+
+int pg_mcc_impl(pgpu_ctx* c, int tID) {
+    if (!c->dev.mcc_ncomp) PG_FAIL(c, PGPU_ERR_STATE, "mcc_vahedi: background mixture not set");
+    if (c->np == 0) return PGPU_OK;
+    c->dev.tID = tID;
+    pg_refresh_dev(c);
+    /* ref: src/collisions.f90:1637-1644 (single-precision literal 1e-12) */
+    double dt = c->cfg.dt;
+    double null_coll_freq = c->cfg.mcc_bg_dens * (double)1e-12f;
+    double p_null = 1 - exp(-dt * null_coll_freq);
+    if (p_null > 1) p_null = 1.;
+    mcc_vahedi_kernel<<<(unsigned int)((c->np + 127) / 128), 128, 0, c->stream>>>(c->dev, p_null);
+    c->launches++;
+    PG_CUDA(c, cudaGetLastError());
+    c->sorted = false;
+    c->hist_valid = false;
+    return PGPU_OK;
+}
+
+extern "C" int pgpu_mcc_vahedi(pgpu_ctx* c, int32_t tID, int64_t* timestep_coll, int64_t* timestep_reac) {
+    if (!c) return PGPU_ERR_INVALID;
+    int rc;
+    if ((rc = pg_prepare(c))) return rc;
+    memset(c->ms, 0, sizeof(c->ms));
+    c->launches = 0;
+    if ((rc = pg_reset_status(c))) return rc;
+    cudaEventRecord(c->ev[4], c->stream);
+    if ((rc = pg_mcc_impl(c, tID))) return rc;
+    cudaEventRecord(c->ev[5], c->stream);
+    rc = pg_finish(c, "pgpu_mcc_vahedi");
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]) == cudaSuccess) c->ms[2] = ms;
+    c->ms[5] = c->ms[2];
+    if (timestep_coll) *timestep_coll = (int64_t)c->h_status->ncoll;
+    if (timestep_reac) *timestep_reac = (int64_t)c->h_status->nreac;
+    return rc;
+}
+
+extern "C" int pgpu_remove_species(pgpu_ctx* c, int32_t sp_id) {
+    if (!c) return PGPU_ERR_INVALID;
+    int rc;
+    if ((rc = pg_prepare(c))) return rc;
+    if (sp_id < 1 || sp_id > c->ns) PG_FAIL(c, PGPU_ERR_INVALID, "remove_species: species %d outside 1..%lld", sp_id, c->ns);
+    if (c->np == 0) return PGPU_OK;
+    if ((rc = pg_reset_status(c))) return rc;
+    remove_species_kernel<<<(unsigned int)((c->np + 255) / 256), 256, 0, c->stream>>>(c->dev, sp_id);
+    c->launches++;
+    c->maybe_tombstones = true;
+    c->sorted = false;
+    c->hist_valid = false;
+    return pg_finish(c, "pgpu_remove_species");
+}

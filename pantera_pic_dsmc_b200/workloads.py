@@ -195,3 +195,114 @@ def c2_air_box(n: int = 50_000, nx: int = 4, ny: int = 4, seed: int = 3, T: floa
     p["DTRIM"] = dt
     p["IC"] = (p["X"] * nx).astype(np.int32) + nx * (p["Y"] * ny).astype(np.int32) + 1
     return Workload("C2 air TCE/BL box", cfg, sp, p, reactions=reactions)
+
+
+# ------------------------------------------------------------------------------------------------
+# C3-like: 2-D (optionally axisymmetric) triangulated box with wall models on the four sides
+# ------------------------------------------------------------------------------------------------
+def c3_tri_box(nx: int = 8, ny: int = 6, n: int = 20_000, seed: int = 4, T0: float = 300.0, dt: float = 2e-6,
+               lo=(0.0, 0.0), hi=(0.1, 0.05), axi: bool = False, species=("N2", "O2"),
+               wall_bc=("vacuum", "specular", "cll", "diffuse"), wall_temp=(300.0, 300.0, 500.0, 700.0),
+               acc=(0.8, 0.6), u_drift=(300.0, 0.0, 0.0), wall_reactions: bool = False, react=(0, 0, 0, 0),
+               collision_type=capi.NO_COLL, nrho: float = 1e20, rng_seed_global: int = 65644,
+               dump_bound_avg_every: int = 1) -> Workload:
+    """Triangulated rectangle (2 CCW triangles per quad).  Physical groups 1 xmin, 2 xmax, 3 ymin, 4 ymax.
+    Axisymmetric: y is the radius and ymin should be > 0 or carry a specular 'axis' (the reference's AXIS
+    BC falls through to removal, timecycle.f90:1611-1614)."""
+    sp = load_species("air", list(species))
+    zmin, zmax = (0.0, 1.0) if axi else (-0.5, 0.5)
+    mesh = mg.rect_tris(nx, ny, lo=lo, hi=hi, zmin=zmin, zmax=zmax, axi=axi)
+    vol = float(np.sum(mesh.cell_volumes))
+    fnum = nrho * vol / n
+    cfg = capi.make_config(dims=2, axi=int(axi), grid_type=capi.UNSTRUCTURED, nx=1, ny=1, xmin=lo[0], xmax=hi[0],
+                           ymin=lo[1], ymax=hi[1], zmin=zmin, zmax=zmax, dt=dt, fnum=fnum,
+                           collision_type=collision_type, bool_z_periodic=0 if axi else 1,
+                           rng_seed_global=rng_seed_global, dump_bound_avg_every=dump_bound_avg_every)
+    kinds = {"vacuum": capi.VACUUM, "specular": capi.SPECULAR, "diffuse": capi.DIFFUSE, "cll": capi.CLL}
+    bcs = dict(particle_bc=[kinds[k] for k in wall_bc], wall_temp=list(wall_temp), acc_n=[acc[0]] * 4,
+               acc_t=[acc[1]] * 4, react=list(react))
+    rng = np.random.default_rng(seed)
+    cum = np.cumsum(mesh.cell_volumes)
+    cells0 = np.minimum(np.searchsorted(cum, rng.random(n) * cum[-1]), mesh.nc - 1).astype(np.int64)
+    xyz = sample_in_tets(rng, mesh, cells0)
+    p = new_particles(n)
+    p["X"], p["Y"] = xyz[:, 0], xyz[:, 1]
+    p["Z"] = 0.0 if axi else rng.random(n) - 0.5
+    sid = rng.integers(1, len(species) + 1, size=n)
+    v = maxwellian(rng, n, sp.mass[sid - 1], T0, u=u_drift)
+    p["VX"], p["VY"], p["VZ"] = v[:, 0], v[:, 1], v[:, 2]
+    p["S_ID"] = sid
+    for name, dofs in (("EROT", sp.rotdof), ("EVIB", sp.vibdof)):
+        has = dofs[sid - 1] == 2
+        p[name][has] = rng.exponential(KB * T0, size=int(has.sum()))
+    p["DTRIM"] = dt
+    p["IC"] = cells0 + 1
+    wr = None
+    if wall_reactions:
+        # authored in the reference's wall-reaction format: species 1 -> species 2 with p=0.3, species 2 -> none 0.2
+        wr = dict(r_sp=[1, 2], p1_sp=[2, -1], nprod=[1, 0], prob=[0.3, 0.2])
+    return Workload("C3 2-D tri box" + (" (axisymmetric)" if axi else ""), cfg, sp, p, mesh=mesh, bcs=bcs,
+                    wall_reactions=wr)
+
+
+# ------------------------------------------------------------------------------------------------
+# C4-like: 1-D argon plasma slab, explicit electrostatic PIC + null-collision MCC with LXCat-format tables
+# ------------------------------------------------------------------------------------------------
+def authored_lxcat_reactions(sp: df.SpeciesTable) -> List[dict]:
+    """Cross-section tables authored in the LXCat layout the reference reads (energy[eV] sigma[m^2],
+    src/initialization.f90:1753-1785).  Shapes are smooth stand-ins (the reference ships no table):
+    e-Ar elastic, excitation (11.5 eV), ionisation (15.8 eV); Ar+-Ar isotropic and charge exchange."""
+    QE = df.QE
+    e_grid = np.concatenate([[0.0], np.logspace(-2, 3, 60)])
+    el = 1e-20 * (1.0 + 15.0 * e_grid / (e_grid + 10.0)) / (1.0 + (e_grid / 60.0) ** 1.2)
+    exc = np.where(e_grid > 11.5, 4e-21 * np.log(np.maximum(e_grid, 11.5) / 11.5) / (1 + e_grid / 200.0), 0.0)
+    ion = np.where(e_grid > 15.8, 2.5e-20 * np.log(np.maximum(e_grid, 15.8) / 15.8) / (1 + e_grid / 150.0), 0.0)
+    iso = 4e-19 / (1.0 + e_grid) ** 0.3
+    cex = 6e-19 / (1.0 + e_grid) ** 0.2
+    e, ar, arp = sp.id("e"), sp.id("Ar"), sp.id("Ar+")
+    mk = lambda r1, r2, prods, ea, cs, cex_=0: dict(
+        type=capi.LXCAT, r1=r1, r2=r2, p1=prods[0], p2=prods[1], p3=prods[2] if len(prods) > 2 else -1, p4=-1,
+        nprod=len(prods), is_cex=cex_, ea=ea * QE, table_energy=e_grid * QE, table_cs=cs)
+    return [
+        mk(e, ar, (e, ar), 0.0, el),
+        mk(e, ar, (e, ar), 11.5, exc),
+        mk(e, ar, (e, arp, e), 15.8, ion),
+        mk(arp, ar, (arp, ar), 0.0, iso),
+        mk(arp, ar, (ar, arp), 0.0, cex, 1),
+    ]
+
+
+def c4_ccp_1d(ncells: int = 64, n_per_species: int = 20_000, seed: int = 5, length: float = 0.0254, Te: float = 30000.0,
+              Ti: float = 300.0, nrho: float = 1e15, dt: float = 1e-11, bg_dens: float = 1e21, bg_T: float = 300.0,
+              rng_seed_global: int = 65644, wall_bc=("vacuum", "vacuum"), field_bc=(capi.DIRICHLET_BC, capi.DIRICHLET_BC)
+              ) -> Workload:
+    sp = load_species("ar", ["Ar", "Ar+", "e"])
+    mesh = mg.line_1d(ncells, 0.0, length)
+    n = 2 * n_per_species
+    fnum = nrho * length * 1.0 * 1.0 / n_per_species
+    cfg = capi.make_config(dims=1, grid_type=capi.UNSTRUCTURED, nx=1, ny=1, xmin=0.0, xmax=length, ymin=0.0, ymax=1.0,
+                           zmin=0.0, zmax=1.0, dt=dt, fnum=fnum, pic_type=capi.PIC_EXPLICIT,
+                           collision_type=capi.MCC_VAHEDI, mcc_bg_dens=bg_dens, mcc_bg_ttra=bg_T,
+                           bool_z_periodic=1, bool_y_periodic=1, rng_seed_global=rng_seed_global)
+    kinds = {"vacuum": capi.VACUUM, "specular": capi.SPECULAR, "diffuse": capi.DIFFUSE}
+    bcs = dict(particle_bc=[kinds[k] for k in wall_bc], field_bc=list(field_bc), wall_temp=[300.0, 300.0])
+    rng = np.random.default_rng(seed)
+    p = new_particles(n)
+    p["X"] = rng.random(n) * length
+    p["Y"] = rng.random(n)
+    p["Z"] = rng.random(n)
+    sid = np.where(np.arange(n) % 2 == 0, sp.id("e"), sp.id("Ar+")).astype(np.int32)
+    T = np.where(sid == sp.id("e"), Te, Ti)
+    sig = np.sqrt(KB * T / sp.mass[sid - 1])
+    v = rng.standard_normal((n, 3)) * sig[:, None]
+    p["VX"], p["VY"], p["VZ"] = v[:, 0], v[:, 1], v[:, 2]
+    p["S_ID"] = sid
+    p["DTRIM"] = dt
+    h = length / ncells
+    p["IC"] = np.minimum((p["X"] / h).astype(np.int32), ncells - 1) + 1
+    efield = np.zeros((3, ncells), order="F")
+    efield[0, :] = 2000.0 * np.sin(2 * np.pi * (np.arange(ncells) + 0.5) / ncells)
+    reactions = authored_lxcat_reactions(sp)
+    sp.sigmamax = max(sp.sigmamax, max(float(np.max(r["table_cs"])) for r in reactions))
+    return Workload("C4 1-D argon PIC-MCC", cfg, sp, p, mesh=mesh, bcs=bcs, reactions=reactions,
+                    mcc_background=([sp.id("Ar")], [1.0]), efield=efield)
