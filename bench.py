@@ -1,0 +1,279 @@
+#!/usr/bin/env python
+"""bench.py -- particle-timesteps/s of the move + sort + collide step (BASELINE.json metric).
+
+Workload (config.workload): C5, the 3-D unstructured (structured-to-tet) argon channel of SURVEY 8(d):
+diffuse walls in y, specular in x and z, VSS collisions, 40 particles per tet, cube edge 0.5 mean free
+paths, dt = 0.2 mean collision times.  Each GPU holds one x-strip of 32x128x128 cubes (3.1e6 tets) with
+1.25e8 particles -- the per-GPU share of the 1e9-particle / 8xB200 configuration (weak scaling).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--particles P] [--impl ours|reference]
+
+* value     whole-job particle-timesteps/s with the particles resident in HBM (K steps of
+            pgpu_run_steps, timed with CUDA events on the library's stream, max over ranks).
+* e2e       same metric through the C ABI with HOST buffers: every step uploads the 96-byte AoS records
+            from pinned host memory, runs one step and downloads the records again.
+* roofline  algorithmic bytes (280 B per particle-timestep for argon VSS: move 84 + sort 144 +
+            collide 52) over the measured step time against MEASURED_PEAKS.json's HBM copy bandwidth, and
+            the same for the dominant kernel group.
+* cpu_baseline  the CPU oracle (C restatement of the reference algorithm, `kind: port`; the Fortran+MPI+
+            PETSc reference cannot be built in this image) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+B_MOVE, B_SORT, B_COLLIDE = 84.0, 144.0, 52.0  # SURVEY 8(d), argon VSS
+B_ALG = B_MOVE + B_SORT + B_COLLIDE
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+def build_workload(args, rank, world):
+    from pantera_pic_dsmc_b200 import capi, workloads as wl
+    ncx, ncy, ncz = args.cubes
+    w = wl.c5_channel_strip(ncx, ncy, ncz, n=args.particles, rank=rank, world=world, seed=1234 + rank, pinned=True)
+    return w
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                       "-i", str(device)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            t = [x.strip() for x in line.split(",")]
+            if len(t) < 9:
+                continue
+            try:
+                sm.append(float(t[1]))
+                mx.append(float(t[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, t[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.f.name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_baseline(args, seconds=12.0):
+    """Oracle (single thread) on a bounded sample of the same workload: a smaller box, same cell size,
+    same particles per cell, same dt.  Reported, not the target."""
+    from pantera_pic_dsmc_b200 import capi, workloads as wl
+    w = wl.c5_channel_strip(16, 16, 16, n=16 * 16 * 16 * 6 * 40, rank=0, world=1, seed=99)
+    o = capi.load_oracle(rng_mode=0)
+    wl.apply(o, w)
+    o.run_steps(1, 1)  # warm-up: first touch
+    n = o.num_particles()
+    t0 = time.perf_counter()
+    steps = 0
+    while time.perf_counter() - t0 < seconds:
+        o.run_steps(2 + steps, 2)
+        steps += 2
+    dt = time.perf_counter() - t0
+    sec = o.get_timings()
+    o.close()
+    return {"value": n * steps / dt, "unit": "particle-timesteps/s", "cores": 1, "kind": "port",
+            "sample": f"C5 strip 16x16x16 cubes, {n} particles, {steps} steps, single thread, MT19937-64 stream",
+            "phase_seconds": {"move": float(sec[0]), "sort": float(sec[1]), "collide": float(sec[2])}}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU algorithm (oracle port; see module docstring) on host cores."""
+    if rank != 0:
+        return
+    from pantera_pic_dsmc_b200 import refbench
+    res = refbench.run(steps=args.steps, warmup=args.warmup, world=world)
+    line = {"metric": "particle-timesteps/s (move+sort+collide)", "value": res["value"], "unit": "particle-timesteps/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "impl": "reference", "config": res["config"],
+            "cpu_baseline": {"value": res["value"], "unit": "particle-timesteps/s", "cores": res["cores"], "kind": "port",
+                             "sample": res["sample"]},
+            "e2e": {"value": res["value"], "unit": "particle-timesteps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--particles", type=int, default=125_000_000, help="particles per GPU")
+    ap.add_argument("--cubes", type=int, nargs=3, default=[32, 128, 128], help="cubes per GPU strip (6 tets each)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="timed e2e steps (0 = same as --steps)")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import torch
+    import torch.distributed as dist
+
+    from pantera_pic_dsmc_b200 import capi, workloads as wl
+
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+
+    t_setup = time.perf_counter()
+    w = build_workload(args, rank, world)
+    n_local = len(w.particles)
+    gpu = capi.load_gpu(local_rank)
+    w.cfg.capacity = int(n_local * 1.02) + 1024
+    wl.apply(gpu, w)
+    if world > 1:
+        uid = [gpu.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        gpu.comm_init(world, rank, uid[0])
+    setup_s = time.perf_counter() - t_setup
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---------------- resident run: W warm-up + K timed steps of pgpu_run_steps ------------------
+    gpu.run_steps(1, args.warmup)
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    t0 = time.perf_counter()
+    ncoll, nreac = gpu.run_steps(1 + args.warmup, args.steps)
+    ms, launches = gpu.get_timings()
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    clocks = sampler.stop() if sampler else None
+    total_ms = max_over_ranks(float(ms[5]))
+    n_now = gpu.num_particles()
+    n_total = sum_over_ranks(float(n_now))
+    value = n_total * args.steps / (total_ms * 1e-3)
+    peak, peak_src = measured_peak_gbs()
+    grp = {"move": float(ms[0]) / args.steps, "sort": float(ms[1]) / args.steps, "collide": float(ms[2]) / args.steps,
+           "exchange": float(ms[4]) / args.steps}
+    bytes_grp = {"move": B_MOVE, "sort": B_SORT, "collide": B_COLLIDE}
+    dom = max(bytes_grp, key=lambda k: grp[k])
+    ach_dom = n_now * bytes_grp[dom] / (grp[dom] * 1e-3) / 1e9
+    ach_step = n_now * B_ALG / (total_ms / args.steps * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": ach_dom, "peak": peak, "unit": "GB/s", "frac": ach_dom / peak, "traffic": None,
+                "kernel": dom, "peak_source": peak_src, "algorithmic_bytes_per_particle": bytes_grp[dom],
+                "whole_step": {"achieved": ach_step, "frac": ach_step / peak, "algorithmic_bytes_per_particle": B_ALG},
+                "groups_ms_per_step": grp,
+                "groups_frac": {k: n_now * bytes_grp[k] / (grp[k] * 1e-3) / 1e9 / peak for k in bytes_grp if grp[k] > 0}}
+
+    # ---------------- e2e: host AoS in, one step, host AoS out, every step --------------------------
+    e2e = None
+    if not args.no_e2e:
+        k2 = args.e2e_steps or args.steps
+        out = wl.pinned_particles(n_local)
+        for s in range(3):  # warm-up
+            gpu.upload_particles(w.particles)
+            gpu.run_steps(1000 + s, 1)
+            gpu.download_into(out)
+        barrier()
+        t0 = time.perf_counter()
+        moved = 0
+        for s in range(k2):
+            gpu.upload_particles(w.particles)
+            gpu.run_steps(2000 + s, 1)
+            moved += gpu.download_into(out)
+        barrier()
+        e2e_s = max_over_ranks(time.perf_counter() - t0)
+        e2e = {"value": sum_over_ranks(float(moved)) / e2e_s, "unit": "particle-timesteps/s",
+               "h2d_bytes_per_step": int(n_local * 96 * world), "d2h_bytes_per_step": int(n_local * 96 * world),
+               "steps": k2, "ms_per_step": e2e_s / k2 * 1e3,
+               "what": "pgpu_upload_particles(pinned AoS) + pgpu_run_steps(1) + pgpu_download_particles(pinned AoS) per step"}
+
+    cpu = None
+    if rank == 0 and not args.no_cpu:
+        cpu = cpu_baseline(args)
+
+    if rank == 0:
+        line = {
+            "metric": "particle-timesteps/s (move+sort+collide)", "value": value, "unit": "particle-timesteps/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"C5 3-D unstructured argon channel (VSS/NTC, diffuse y-walls, specular x/z), "
+                                   f"{args.cubes[0]}x{args.cubes[1]}x{args.cubes[2]} cubes x6 tets per GPU, "
+                                   f"{n_local} particles per GPU ({n_local * world} total)",
+                       "particles_per_gpu": n_local, "cells_per_gpu": int(w.mesh.nc // max(world, 1)), "mesh_cells": int(w.mesh.nc),
+                       "ppc": n_local / (w.mesh.nc / max(world, 1)), "partition": f"stripsx x{world}",
+                       "l2_policy": "inputs (9 GB of particle planes per GPU) are far larger than the 126 MB L2",
+                       "rng": "Philox4x32-10 per particle/candidate", "ids": "regenerated on download (track_id=0)"},
+            "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu, "gpu_launches": int(launches),
+            "clocks": clocks, "collisions_per_step": ncoll / args.steps, "wall_ms_per_step": wall_ms / args.steps,
+            "setup_seconds": setup_s,
+        }
+        print(json.dumps(line), flush=True)
+    gpu.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -111,6 +111,10 @@ int po_get_cell_counts(po_ctx* ctx, int32_t* npc, int64_t nc);
 /* per-phase CPU seconds accumulated by po_run_steps: 0 move, 1 sort, 2 collide */
 int po_get_timings(po_ctx* ctx, double* sec, int32_t n);
 
+/* po_mpi_sim.c: nsteps of [ADVECT -> EXCHANGE -> DSMC_COLLISIONS] on nranks contexts, one host thread per
+ * rank (the reference's MPI model); totals = {ncoll, nreac, particles exchanged} */
+int po_sim_run(po_ctx** ranks, int nranks, int tID0, int nsteps, double* seconds, int64_t* totals);
+
 #ifdef __cplusplus
 }
 #endif

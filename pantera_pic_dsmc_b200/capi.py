@@ -271,7 +271,8 @@ class Lib:
     # -- particles --------------------------------------------------------------------------
     def upload_particles(self, parts: np.ndarray):
         assert parts.dtype == PARTICLE_DTYPE
-        parts = np.ascontiguousarray(parts)
+        if not parts.flags["C_CONTIGUOUS"]:
+            parts = np.ascontiguousarray(parts)
         self._call("upload_particles", _p(parts), C.c_int64(len(parts)), C.c_int32(96))
 
     def append_particles(self, parts: np.ndarray):
@@ -290,6 +291,13 @@ class Lib:
         nn = C.c_int64()
         self._call("download_particles", _p(out), C.c_int64(len(out)), C.byref(nn), C.c_int32(96))
         return out[: nn.value]
+
+    def download_into(self, out: np.ndarray) -> int:
+        """pgpu_download_particles into a caller-owned (e.g. pinned) record array; returns the count."""
+        assert out.dtype == PARTICLE_DTYPE and out.flags["C_CONTIGUOUS"]
+        nn = C.c_int64()
+        self._call("download_particles", _p(out), C.c_int64(len(out)), C.byref(nn), C.c_int32(96))
+        return nn.value
 
     # -- fields -----------------------------------------------------------------------------
     def set_efield(self, e):

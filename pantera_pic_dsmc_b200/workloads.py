@@ -306,3 +306,81 @@ def c4_ccp_1d(ncells: int = 64, n_per_species: int = 20_000, seed: int = 5, leng
     sp.sigmamax = max(sp.sigmamax, max(float(np.max(r["table_cs"])) for r in reactions))
     return Workload("C4 1-D argon PIC-MCC", cfg, sp, p, mesh=mesh, bcs=bcs, reactions=reactions,
                     mcc_background=([sp.id("Ar")], [1.0]), efield=efield)
+
+
+# ------------------------------------------------------------------------------------------------
+# bench-scale C5: one x-strip per rank, particles generated in chunks straight into (pinned) AoS records
+# ------------------------------------------------------------------------------------------------
+_PINNED_KEEPALIVE = []
+
+
+def pinned_particles(n: int) -> np.ndarray:
+    """n zeroed particle records in page-locked host memory (falls back to pageable without CUDA)."""
+    import torch
+    nbytes = max(n, 1) * capi.PARTICLE_DTYPE.itemsize
+    try:
+        t = torch.empty(nbytes, dtype=torch.uint8, pin_memory=torch.cuda.is_available())
+    except RuntimeError:
+        t = torch.empty(nbytes, dtype=torch.uint8)
+    _PINNED_KEEPALIVE.append(t)
+    return t.numpy().view(capi.PARTICLE_DTYPE)[:n]
+
+
+def c5_channel_strip(ncx: int, ncy: int, ncz: int, n: int, rank: int = 0, world: int = 1, seed: int = 2,
+                     T0: float = 300.0, nrho: float = 1e20, cell_mfp: float = 0.5, dt_frac: float = 0.2,
+                     u_drift: float = 100.0, wall_temp: float = 400.0, pinned: bool = False,
+                     rng_seed_global: int = 65644, mesh: Optional[mg.Mesh] = None) -> Workload:
+    """C5 at bench scale.  The whole channel is world*ncx x ncy x ncz cubes (mesh replicated on every rank,
+    as the reference does, grid_and_partition.f90:123-353); rank r owns the x-strip r and seeds n particles
+    uniformly in it (all Kuhn tets of the regular box have the same volume)."""
+    sp = load_species("ar", ["Ar"])
+    m = sp.mass[0]
+    d, om, tref = sp.diam[0], sp.omega[0], sp.tref[0]
+    nu = 4.0 * d * d * nrho * np.sqrt(np.pi * KB * tref / m) * (T0 / tref) ** (1.0 - om)
+    cbar = np.sqrt(8.0 * KB * T0 / (np.pi * m))
+    h = cell_mfp * cbar / nu
+    nxt = ncx * world
+    hi = (nxt * h, ncy * h, ncz * h)
+    if mesh is None:
+        mesh = mg.box_tets(nxt, ncy, ncz, lo=(0.0, 0.0, 0.0), hi=hi)
+        if world > 1:
+            mesh.cell_procs = mg.assign_cells_to_procs(mesh, world, 0)
+    vol_strip = ncx * ncy * ncz * h ** 3
+    fnum = nrho * vol_strip / n
+    dt = dt_frac / nu
+    cfg = capi.make_config(dims=3, grid_type=capi.UNSTRUCTURED, nx=1, ny=1, xmin=0.0, xmax=hi[0], ymin=0.0, ymax=hi[1],
+                           zmin=0.0, zmax=hi[2], dt=dt, fnum=fnum, collision_type=capi.DSMC, rank=rank, nranks=world,
+                           rng_seed_global=rng_seed_global, dump_bound_avg_every=0)
+    bcs = dict(particle_bc=[capi.SPECULAR, capi.SPECULAR, capi.DIFFUSE, capi.DIFFUSE, capi.SPECULAR, capi.SPECULAR],
+               wall_temp=[wall_temp] * 6, acc_n=[1.0] * 6, acc_t=[1.0] * 6)
+    p = pinned_particles(n) if pinned else np.zeros(n, dtype=capi.PARTICLE_DTYPE)
+    rng = np.random.default_rng(seed)
+    cn = np.asarray(mesh.cell_nodes)
+    xyz = np.asarray(mesh.node_coords)
+    sig = np.sqrt(KB * T0 / m)
+    chunk = 4_000_000
+    for a in range(0, n, chunk):
+        b = min(n, a + chunk)
+        k = b - a
+        ci = rng.integers(rank * ncx, (rank + 1) * ncx, k)
+        cj = rng.integers(0, ncy, k)
+        ck = rng.integers(0, ncz, k)
+        cell0 = 6 * (ci + nxt * (cj + ncy * ck)) + rng.integers(0, 6, k)
+        lam = rng.exponential(size=(4, k))
+        lam /= lam.sum(axis=0, keepdims=True)
+        nodes = cn[:, cell0] - 1
+        q = p[a:b]
+        for ax, name in enumerate(("X", "Y", "Z")):
+            q[name] = (xyz[ax, nodes] * lam).sum(axis=0)
+        q["VX"] = rng.standard_normal(k) * sig + u_drift
+        q["VY"] = rng.standard_normal(k) * sig
+        q["VZ"] = rng.standard_normal(k) * sig
+        q["EROT"] = 0.0
+        q["EVIB"] = 0.0
+        q["DTRIM"] = dt
+        q["IC"] = cell0 + 1
+        q["S_ID"] = 1
+        q["ID"] = (np.arange(a, b, dtype=np.int64) << 8) + rank
+        q["DUMP_TRAJ"] = 0
+    return Workload("C5 3-D tet channel strip", cfg, sp, p, mesh=mesh, bcs=bcs,
+                    notes=f"h={h:.4g} nu={nu:.5g} dt={dt:.4g} nc={mesh.nc} world={world}")
