@@ -7,11 +7,15 @@
  * WALL_REACT (src/fields.f90:4302-4341), TALLY_PARTICLE_TO_BOUNDARY (src/postprocess.f90:1098-1147),
  * CELL_FROM_POSITION (src/grid_and_partition.f90:34-96).
  *
- * Two passes over one kernel template:
- *   LEAN  one thread per particle slot; free flight with neighbour hops (unstructured) or periodic
- *         wraps (structured) only.  A particle that reaches any other boundary event is NOT written:
- *         its slot goes to a compact hit list.  This pass is the HBM-bound bulk: 56 B read, 28 B
- *         written per particle, mesh records served from L1/L2.
+ * Two passes:
+ *   LEAN  free flight with neighbour hops (unstructured) or periodic wraps (structured) only.  A particle
+ *         that reaches any other boundary event is NOT written: its slot goes to a compact hit list.
+ *         This pass is the bulk: one 32-byte pos record and one 32-byte vel record read, one pos record
+ *         written per particle, mesh records served from L1/L2.  The number of cells a particle crosses
+ *         varies from 0 to a handful, so a warp does not own 32 particles but a CHUNK of them: every
+ *         lane runs ONE cell crossing per trip of the loop and a lane whose particle has finished takes
+ *         the next particle of the chunk (ballot + popc), which keeps the FP64 face tests -- the actual
+ *         bound of this kernel, ncu r01a: 12 of 32 lanes active on average without it -- on full warps.
  *   FULL  one thread per hit-list entry; redoes the particle from its start-of-step state with every
  *         boundary model enabled (specular, Maxwell diffuse, CLL, wall reactions, porous walls,
  *         dielectric charging, tallies).  Deterministic arithmetic makes the redo identical up to the
@@ -419,18 +423,23 @@ __device__ void boundary_unstructured(const PgDev& d, PgRng& g, PState& q, int i
     if (!remove && d.tally_on) tally(d, 1, q, ic, iface);
 }
 
-/* One particle on an unstructured grid. ref: src/timecycle.f90:1166-1657.
- * Returns false when LEAN and the particle must be deferred to the FULL pass. */
+enum { IT_NONE = 0, IT_CONTINUE = 1, IT_DONE = 2, IT_DEFER = 3 };
+
+/* One trip of the ADVECT while-loop (one cell crossing or the final flight) of a particle on an
+ * unstructured grid. ref: src/timecycle.f90:1166-1657.  IT_DEFER: LEAN and the particle reached a
+ * boundary event; it is left untouched for the FULL pass. */
 template <int DIMS, bool AXI, bool LEAN>
-__device__ bool advect_unstructured(const PgDev& d, PgRng& g, PState& q, int& remove, int& dirty) {
+__device__ __forceinline__ int unstructured_iter(const PgDev& d, PgRng& g, PState& q, int& remove, int& dirty, int& hops) {
     constexpr int NF = DIMS + 1;
     const double TOL = 1.0e-15;
     int ic = q.ic;
-    int hops = 0;
-    while (q.dtrim > 0.) {
+    {
         double dtcoll = q.dtrim;
         int boundcoll = -1;
-        const double* geo = d.face_geo + (size_t)(ic - 1) * (NF * 6);
+        const double* geo = d.face_geo + (size_t)(ic - 1) * (NF * 6 + 2);
+        /* hop codes of the cell's faces, fetched together with the geometry (no dependent load) */
+        const int4 codes = __ldg(reinterpret_cast<const int4*>(geo + NF * 6));
+        int codesel = 0; /* hop code of the face selected so far (a predicated move per face, no branch) */
         double nsel[3] = {0., 0., 0.};
         if (AXI) {
             /* ref: :1173-1253 */
@@ -460,6 +469,7 @@ __device__ bool advect_unstructured(const PgDev& d, PgRng& g, PState& q, int& re
                         if (colldist >= 0 && colldist <= 1) {
                             dtcoll = test[s];
                             boundcoll = i;
+                            codesel = (i == 0) ? codes.x : (i == 1) ? codes.y : codes.z;
                             nsel[0] = n1; nsel[1] = n2; nsel[2] = 0.;
                         }
                     }
@@ -478,6 +488,7 @@ __device__ bool advect_unstructured(const PgDev& d, PgRng& g, PState& q, int& re
                     dx = (p1 - q.x) * n1;
                     if (vn >= 0. && vn * dtcoll >= dx) {
                         dtcoll = dx / vn; boundcoll = i;
+                        codesel = (i == 0) ? codes.x : codes.y;
                         nsel[0] = n1; nsel[1] = 0.; nsel[2] = 0.;
                     }
                 } else if (DIMS == 2) {
@@ -485,8 +496,13 @@ __device__ bool advect_unstructured(const PgDev& d, PgRng& g, PState& q, int& re
                     double p1 = __ldg(&geo[6 * i + 3]), p2 = __ldg(&geo[6 * i + 4]);
                     vn = q.vx * n12.x + q.vy * n12.y;
                     dx = (p1 - q.x) * n12.x + (p2 - q.y) * n12.y;
-                    if (vn >= 0. && vn * dtcoll >= dx) {
-                        dtcoll = dx / vn; boundcoll = i;
+                    const bool take = (vn >= 0. && vn * dtcoll >= dx);
+                    double num = take ? dx : 1., den = take ? vn : 1.; /* see the 3-D branch */
+                    asm("" : "+d"(num), "+d"(den));
+                    const double quo = num / den;
+                    if (take) {
+                        dtcoll = quo; boundcoll = i;
+                        codesel = (i == 0) ? codes.x : (i == 1) ? codes.y : codes.z;
                         nsel[0] = n12.x; nsel[1] = n12.y; nsel[2] = 0.;
                     }
                 } else {
@@ -496,8 +512,18 @@ __device__ bool advect_unstructured(const PgDev& d, PgRng& g, PState& q, int& re
                     /* a = (nx,ny) b = (nz,px) c = (py,pz) */
                     vn = q.vx * a.x + q.vy * a.y + q.vz * b.x;
                     dx = (b.y - q.x) * a.x + (c.x - q.y) * a.y + (c.y - q.z) * b.x;
-                    if (vn >= 0. && vn * dtcoll >= dx) {
-                        dtcoll = dx / vn; boundcoll = i;
+                    /* The compiler evaluates the quotient for every lane and selects; a particle that has
+                     * just crossed an axis-aligned face sits EXACTLY on it (dx == 0), which sends the whole
+                     * warp through the slow path of the FP64 division for a result that is discarded (that
+                     * face now has vn < 0).  Feeding 1/1 to the lanes that do not take the face keeps the
+                     * division on its fast path; the lanes that take it divide the same operands as before. */
+                    const bool take = (vn >= 0. && vn * dtcoll >= dx);
+                    double num = take ? dx : 1., den = take ? vn : 1.;
+                    asm("" : "+d"(num), "+d"(den)); /* opaque: keeps the selects in front of the division */
+                    const double quo = num / den;
+                    if (take) {
+                        dtcoll = quo; boundcoll = i;
+                        codesel = (i == 0) ? codes.x : (i == 1) ? codes.y : (i == 2) ? codes.z : codes.w;
                         nsel[0] = a.x; nsel[1] = a.y; nsel[2] = b.x;
                     }
                 }
@@ -505,7 +531,7 @@ __device__ bool advect_unstructured(const PgDev& d, PgRng& g, PState& q, int& re
         }
 
         if (boundcoll != -1) {
-            int code = __ldg(&d.face_code[(size_t)(ic - 1) * NF + boundcoll]);
+            const int code = codesel;
             if (code > 0) {
                 /* ref: :1311-1312, :1648-1652 cell hop */
                 move_particle<AXI>(q, dtcoll);
@@ -518,7 +544,7 @@ __device__ bool advect_unstructured(const PgDev& d, PgRng& g, PState& q, int& re
                     q.dtrim = 0.;
                 }
             } else {
-                if (LEAN) return false;
+                if (LEAN) return IT_DEFER;
                 move_particle<AXI>(q, dtcoll);
                 q.dtrim = q.dtrim - dtcoll;
                 if (AXI) dirty |= DIRTY_V; /* the axisymmetric move rotates the velocity */
@@ -536,21 +562,21 @@ __device__ bool advect_unstructured(const PgDev& d, PgRng& g, PState& q, int& re
         }
     }
     if (AXI) dirty |= DIRTY_V;
-    return true;
+    return (q.dtrim > 0.) ? IT_CONTINUE : IT_DONE;
 }
 
-/* One particle on a rectilinear grid. ref: src/timecycle.f90:1659-2015 */
+/* One trip of the ADVECT while-loop of a particle on a rectilinear grid. ref: src/timecycle.f90:1659-2015 */
 template <bool AXI, bool LEAN>
-__device__ bool advect_structured(const PgDev& d, PgRng& g, PState& q, int& remove, int& dirty, int* bhits) {
+__device__ __forceinline__ int structured_iter(const PgDev& d, PgRng& g, PState& q, int& remove, int& dirty, int* bhits,
+                                               int& iters) {
     const double NORMX[4] = {1., -1., 0., 0.};
     const double NORMY[4] = {0., 0., 1., -1.};
     const double XW[4] = {d.xmin, d.xmax, d.xmin, d.xmax};
     const double YW[4] = {d.ymax, d.ymin, d.ymin, d.ymax};
     const double BOUNDPOS[4] = {d.xmin, d.xmax, d.ymin, d.ymax};
     const int dims = d.dims;
-    int iters = 0;
 
-    while (q.dtrim > 0.) {
+    {
         double dtcoll = q.dtrim;
         int boundcoll = -1;
         for (int i = 1; i <= 2 * dims; i++) {
@@ -642,7 +668,7 @@ __device__ bool advect_structured(const PgDev& d, PgRng& g, PState& q, int& remo
         if (boundcoll != -1) {
             /* ref: :1868-1939 */
             int b = boundcoll - 1;
-            if (LEAN && !d.bper[b]) return false;
+            if (LEAN && !d.bper[b]) return IT_DEFER;
             /* LOCAL_BOUNDARY_COLL_COUNT (ref: :1871-1872).  The LEAN pass may still defer the particle,
              * so it counts locally and the caller commits once the particle is final. */
             if (LEAN) bhits[b]++;
@@ -677,7 +703,7 @@ __device__ bool advect_structured(const PgDev& d, PgRng& g, PState& q, int& remo
             }
         } else if (wallcoll != -1) {
             /* ref: :1940-2008 */
-            if (LEAN) return false;
+            if (LEAN) return IT_DEFER;
             int j = wallcoll - 1;
             atomicAdd(&d.wcount[j + (size_t)d.nw * (q.sid - 1)], 1ULL);
             if (d.w_spec[j]) {
@@ -724,30 +750,24 @@ __device__ bool advect_structured(const PgDev& d, PgRng& g, PState& q, int& remo
         }
     }
     if (AXI) dirty |= DIRTY_V;
-    return true;
+    return (q.dtrim > 0.) ? IT_CONTINUE : IT_DONE;
 }
 
-/* MODE: 0 structured, 1/2/3 unstructured of that dimension */
-template <int MODE, bool AXI, bool LEAN>
-__global__ void __launch_bounds__(256) advect_kernel(const __grid_constant__ PgDev d, long long n) {
-    long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (tid >= n) return;
-    long long slot = LEAN ? tid : (long long)d.hitlist[tid];
+/* ------------------------------------------------------------------------------------------
+ * kernels.  MODE: 0 structured, 1/2/3 unstructured of that dimension
+ * ---------------------------------------------------------------------------------------- */
 
-    PState q;
-    q.ic = d.p.ic[slot];
-    if (q.ic < 1) return; /* tombstone */
-    q.sid = d.p.sid[slot];
-    q.x = d.p.x[slot]; q.y = d.p.y[slot]; q.z = d.p.z[slot];
-    q.vx = d.p.vx[slot]; q.vy = d.p.vy[slot]; q.vz = d.p.vz[slot];
+/* particle slot -> registers; returns false for a tombstone.  Applies the PIC kick at the start-of-step
+ * position/cell with the particle's DTRIM (ref: src/timecycle.f90:1105-1131). */
+__device__ __forceinline__ bool load_particle(const PgDev& d, long long slot, PState& q, int& dirty) {
+    const PgPos P = d.p.pos[slot];
+    if (P.ic < 1) return false;
+    const PgVel V = d.p.vel[slot];
+    q.x = P.x; q.y = P.y; q.z = P.z; q.ic = P.ic; q.sid = P.sid;
+    q.vx = V.vx; q.vy = V.vy; q.vz = V.vz;
     q.dtrim = d.p.dtrim ? d.p.dtrim[slot] : d.dt;
     q.erot = 0.; q.evib = 0.;
-
-    PgRng g;
-    g.init(d.seed_local, 1, d.tID, (unsigned long long)slot, 0ULL);
-    int dirty = 0, remove = 0;
-
-    /* ref: src/timecycle.f90:1105-1131 kick at the start-of-step position/cell with the particle's DTRIM */
+    dirty = 0;
     if (d.pic != PGPU_PIC_NONE) {
         double e[3], b[3];
         apply_e_field(d, q, e);
@@ -757,30 +777,13 @@ __global__ void __launch_bounds__(256) advect_kernel(const __grid_constant__ PgD
         boris(q.dtrim, q, d.charge[q.sid - 1], d.mass[q.sid - 1], e, b);
         dirty |= DIRTY_V;
     }
+    return true;
+}
 
-    bool done;
-    if constexpr (MODE == 0) {
-        int bhits[4] = {0, 0, 0, 0};
-        done = advect_structured<AXI, LEAN>(d, g, q, remove, dirty, bhits);
-        if (LEAN && done) { /* the species cannot change in the LEAN pass */
-            for (int b = 0; b < 4; b++)
-                if (bhits[b]) atomicAdd(&d.bcount[b + 4 * (q.sid - 1)], (unsigned long long)bhits[b]);
-        }
-    } else {
-        done = advect_unstructured<MODE, AXI, LEAN>(d, g, q, remove, dirty);
-    }
-    if (LEAN && !done) {
-        unsigned long long k = atomicAdd(&d.status->n_hits, 1ULL);
-        d.hitlist[k] = (unsigned int)slot;
-        return;
-    }
-
-    if (remove) {
-        d.p.ic[slot] = PG_TOMBSTONE;
-        atomicAdd(&d.status->n_removed, 1ULL);
-        return;
-    }
-
+/* end of ADVECT for one particle that was not removed: periodic wraps, structured re-index.
+ * Returns false (and flags the error) when the particle ends outside the grid. */
+template <int MODE>
+__device__ __forceinline__ bool finish_particle(const PgDev& d, PState& q) {
     /* ref: :2048-2068 */
     if (d.zper) {
         while (q.z > d.zmax) q.z = d.zmin + (q.z - d.zmax);
@@ -790,24 +793,32 @@ __global__ void __launch_bounds__(256) advect_kernel(const __grid_constant__ PgD
         while (q.y > d.ymax) q.y = d.ymin + (q.y - d.ymax);
         while (q.y < d.ymin) q.y = d.ymax + (q.y - d.ymin);
     }
-
     /* ref: :2105-2108 structured grids are re-indexed from the final position */
     if (MODE == 0) q.ic = cell_from_position(d, q.x, q.y);
     if (q.ic < 1 || q.ic > d.ncells) {
         pg_set_err(d, PG_DEVERR_CELL_RANGE);
-        d.p.ic[slot] = PG_TOMBSTONE;
-        atomicAdd(&d.status->n_removed, 1ULL);
-        return;
+        return false;
     }
+    return true;
+}
 
-    d.p.x[slot] = q.x; d.p.y[slot] = q.y; d.p.z[slot] = q.z;
-    d.p.ic[slot] = q.ic;
-    if (dirty & DIRTY_V) { d.p.vx[slot] = q.vx; d.p.vy[slot] = q.vy; d.p.vz[slot] = q.vz; }
-    if (dirty & DIRTY_E) { d.p.erot[slot] = q.erot; d.p.evib[slot] = q.evib; }
-    if (dirty & DIRTY_S) d.p.sid[slot] = q.sid;
-
-    /* histogram + arrival rank for the counting sort (K3/K5 of SURVEY 2.3), warp-aggregated */
-    unsigned int mask = __match_any_sync(__activemask(), q.ic);
+/* registers -> slot, plus the histogram and arrival rank of the counting sort (warp-aggregated: the lanes
+ * of `peers` that land in the same cell share one atomic).  Every lane of `peers` must call this. */
+__device__ __forceinline__ void store_particle(const PgDev& d, long long slot, const PState& q, int dirty, unsigned int peers) {
+    PgPos P;
+    P.x = q.x; P.y = q.y; P.z = q.z; P.ic = q.ic; P.sid = q.sid;
+    d.p.pos[slot] = P;
+    if (dirty & (DIRTY_V | DIRTY_S)) {
+        PgVel V;
+        V.vx = q.vx; V.vy = q.vy; V.vz = q.vz; V.sid = q.sid; V.pad = 0;
+        d.p.vel[slot] = V;
+    }
+    if (dirty & DIRTY_E) {
+        PgIe E;
+        E.erot = q.erot; E.evib = q.evib;
+        d.p.ie[slot] = E;
+    }
+    unsigned int mask = __match_any_sync(peers, q.ic);
     int leader = __ffs(mask) - 1;
     int lane = threadIdx.x & 31;
     unsigned int base = 0;
@@ -816,23 +827,134 @@ __global__ void __launch_bounds__(256) advect_kernel(const __grid_constant__ PgD
     d.cell_rank[slot] = base + __popc(mask & ((1u << lane) - 1u));
 }
 
+__device__ __forceinline__ void tombstone_particle(const PgDev& d, long long slot) {
+    d.p.pos[slot].ic = PG_TOMBSTONE;
+    atomicAdd(&d.status->n_removed, 1ULL);
+}
+
+/*
+ * LEAN pass.  One warp works through PG_ADVECT_CHUNK consecutive slots; see the file header.
+ */
+template <int MODE, bool AXI>
+__global__ void __launch_bounds__(128) advect_lean_kernel(const __grid_constant__ PgDev d, long long n) {
+    const unsigned int FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    long long next = warp * PG_ADVECT_CHUNK;
+    if (next >= n) return;
+    const long long end = (next + PG_ADVECT_CHUNK < n) ? next + PG_ADVECT_CHUNK : n;
+
+    PState q;
+    long long slot = 0;
+    bool have = false;
+    int dirty = 0, hops = 0;
+    int bhits[4] = {0, 0, 0, 0};
+    PgRng g; /* never drawn from in the LEAN pass */
+    g.init(0ULL, 0, 0, 0ULL, 0ULL);
+
+    for (;;) {
+        /* refill: idle lanes take the next slots of the chunk, in order */
+        unsigned int idle = __ballot_sync(FULL, !have);
+        if (idle && next < end) {
+            long long my = next + __popc(idle & ((1u << lane) - 1u));
+            if (!have && my < end) {
+                slot = my;
+                have = load_particle(d, slot, q, dirty);
+                hops = 0;
+                if (MODE == 0) { bhits[0] = bhits[1] = bhits[2] = bhits[3] = 0; }
+            }
+            next += __popc(idle);
+        }
+        if (!__any_sync(FULL, have)) {
+            if (next >= end) break;
+            continue;
+        }
+
+        int st = IT_NONE, remove = 0;
+        if (have) {
+            if constexpr (MODE == 0) st = structured_iter<AXI, true>(d, g, q, remove, dirty, bhits, hops);
+            else st = unstructured_iter<MODE, AXI, true>(d, g, q, remove, dirty, hops);
+        }
+
+        /* deferred to the FULL pass: untouched in the store, slot appended to the hit list */
+        unsigned int dm = __ballot_sync(FULL, st == IT_DEFER);
+        if (dm) {
+            unsigned long long base = 0;
+            int leader = __ffs(dm) - 1;
+            if (lane == leader) base = atomicAdd(&d.status->n_hits, (unsigned long long)__popc(dm));
+            base = __shfl_sync(FULL, base, leader);
+            if (st == IT_DEFER) {
+                d.hitlist[base + __popc(dm & ((1u << lane) - 1u))] = (unsigned int)slot;
+                have = false;
+            }
+        }
+
+        bool keep = false;
+        if (st == IT_DONE) {
+            have = false;
+            keep = !remove && finish_particle<MODE>(d, q);
+            if (!keep) tombstone_particle(d, slot);
+        }
+        unsigned int fm = __ballot_sync(FULL, keep);
+        if (keep) {
+            if (MODE == 0) { /* the species cannot change in the LEAN pass */
+                for (int b = 0; b < 4; b++)
+                    if (bhits[b]) atomicAdd(&d.bcount[b + 4 * (q.sid - 1)], (unsigned long long)bhits[b]);
+            }
+            store_particle(d, slot, q, dirty, fm);
+        }
+    }
+}
+
+/* FULL pass: one thread per hit-list entry, every boundary model enabled. */
+template <int MODE, bool AXI>
+__global__ void __launch_bounds__(128) advect_full_kernel(const __grid_constant__ PgDev d, long long n) {
+    long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    bool have = tid < n;
+    long long slot = have ? (long long)d.hitlist[tid] : 0;
+    PState q;
+    int dirty = 0, remove = 0, hops = 0;
+    if (have) have = load_particle(d, slot, q, dirty);
+    bool keep = false;
+    if (have) {
+        PgRng g;
+        g.init(d.seed_local, 1, d.tID, (unsigned long long)slot, 0ULL);
+        int bhits[4] = {0, 0, 0, 0};
+        while (q.dtrim > 0.) {
+            if constexpr (MODE == 0) structured_iter<AXI, false>(d, g, q, remove, dirty, bhits, hops);
+            else unstructured_iter<MODE, AXI, false>(d, g, q, remove, dirty, hops);
+        }
+        keep = !remove && finish_particle<MODE>(d, q);
+        if (!keep) tombstone_particle(d, slot);
+    }
+    unsigned int fm = __ballot_sync(0xffffffffu, keep);
+    if (keep) store_particle(d, slot, q, dirty, fm);
+}
+
 template <bool LEAN>
 int launch_advect(pgpu_ctx* c, long long n) {
     if (n <= 0) return PGPU_OK;
     const PgDev& d = c->dev;
-    unsigned int blocks = (unsigned int)((n + 255) / 256);
+    const long long per_block = LEAN ? 4LL * PG_ADVECT_CHUNK : 128LL;
+    unsigned int blocks = (unsigned int)((n + per_block - 1) / per_block);
     bool axi = d.axi != 0;
+#define PG_LAUNCH(MODE, AXI)                                                                   \
+    do {                                                                                       \
+        if (LEAN) advect_lean_kernel<MODE, AXI><<<blocks, 128, 0, c->stream>>>(d, n);          \
+        else advect_full_kernel<MODE, AXI><<<blocks, 128, 0, c->stream>>>(d, n);               \
+    } while (0)
     if (d.grid_type != PGPU_UNSTRUCTURED) {
-        if (axi) advect_kernel<0, true, LEAN><<<blocks, 256, 0, c->stream>>>(d, n);
-        else advect_kernel<0, false, LEAN><<<blocks, 256, 0, c->stream>>>(d, n);
+        if (axi) PG_LAUNCH(0, true);
+        else PG_LAUNCH(0, false);
     } else if (d.dims == 1) {
-        advect_kernel<1, false, LEAN><<<blocks, 256, 0, c->stream>>>(d, n);
+        PG_LAUNCH(1, false);
     } else if (d.dims == 2) {
-        if (axi) advect_kernel<2, true, LEAN><<<blocks, 256, 0, c->stream>>>(d, n);
-        else advect_kernel<2, false, LEAN><<<blocks, 256, 0, c->stream>>>(d, n);
+        if (axi) PG_LAUNCH(2, true);
+        else PG_LAUNCH(2, false);
     } else {
-        advect_kernel<3, false, LEAN><<<blocks, 256, 0, c->stream>>>(d, n);
+        PG_LAUNCH(3, false);
     }
+#undef PG_LAUNCH
     c->launches++;
     PG_CUDA(c, cudaGetLastError());
     return PGPU_OK;

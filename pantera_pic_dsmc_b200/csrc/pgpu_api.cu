@@ -94,6 +94,9 @@ extern "C" int pgpu_create(pgpu_ctx** out, int device) {
     c->cur = 0; c->np = 0; c->capacity = 0;
     c->has_dtrim = false; c->sorted = false; c->hist_valid = false; c->maybe_tombstones = false;
     c->id_counter = 0;
+    c->any_internal_dof = false; c->ie_seen = false;
+    c->d_tile_first = nullptr; c->tile_alloc = 0; c->n_big = 0;
+    c->d_big_list = nullptr; c->d_big_bbox = nullptr; c->big_alloc = 0;
     c->d_cell_count = c->d_rank = c->d_cell_off = c->d_hitlist = nullptr;
     c->hit_capacity = 0; c->ncells_alloc = 0;
     c->d_status = nullptr; c->h_status = nullptr;
@@ -129,8 +132,7 @@ extern "C" int pgpu_create(pgpu_ctx** out, int device) {
 }
 
 static void free_planes(PgPlanes& p) {
-    dev_free(p.x); dev_free(p.y); dev_free(p.z); dev_free(p.vx); dev_free(p.vy); dev_free(p.vz);
-    dev_free(p.erot); dev_free(p.evib); dev_free(p.ic); dev_free(p.sid); dev_free(p.dtrim); dev_free(p.id);
+    dev_free(p.pos); dev_free(p.vel); dev_free(p.ie); dev_free(p.dtrim); dev_free(p.id);
 }
 
 extern "C" void pg_comm_destroy(pgpu_ctx* c); /* pgpu_exchange.cu */
@@ -145,6 +147,7 @@ extern "C" int pgpu_destroy(pgpu_ctx* c) {
     free_planes(c->planes[0]);
     free_planes(c->planes[1]);
     dev_free(c->d_cell_count); dev_free(c->d_rank); dev_free(c->d_cell_off); dev_free(c->d_hitlist);
+    dev_free(c->d_tile_first); dev_free(c->d_big_list); dev_free(c->d_big_bbox);
     dev_free(c->d_status);
     if (c->h_status) cudaFreeHost(c->h_status);
     dev_free(c->d_scan_tmp); dev_free(c->d_cand); dev_free(c->d_owner);
@@ -213,6 +216,9 @@ extern "C" int pgpu_set_species(pgpu_ctx* c, int ns, const double* mass, const d
     int rc;
     c->ns = ns;
     c->dev.ns = ns;
+    c->any_internal_dof = false;
+    for (int i = 0; i < ns; i++)
+        if (rotdof[i] != 0 || vibdof[i] != 0) c->any_internal_dof = true;
     if ((rc = put(c, S_MASS, mass, ns, &c->dev.mass))) return rc;
     if ((rc = put(c, S_CHARGE, charge, ns, &c->dev.charge))) return rc;
     if ((rc = put(c, S_ROTDOF, (const int*)rotdof, ns, &c->dev.rotdof))) return rc;
@@ -446,23 +452,24 @@ extern "C" int pgpu_set_surface_charge(pgpu_ctx* c, const double* sc, int64_t n)
 }
 
 /* ------------------------------------------------------------------------------------------
- * packed device mesh:  per cell and face { outward normal, a point on the face } + one hop code.
+ * packed device mesh:  one record per cell = per face { outward normal, a point on the face } + the hop codes.
  * The reference reads FACE_NORMAL/EDGE_NORMAL, CELL_NODES -> NODE_COORDS, CELL_NEIGHBORS,
  * CELL_FACES_PG and the neighbour's CELL_PG/VOLUME_BC separately for every face test
  * (src/timecycle.f90:1257-1360); here they are resolved once so that the face walk is a single
- * 48-byte record per face with no dependent index load.  The point of face j is local node j
+ * 208-byte record per tetrahedron (160 B per triangle) with no dependent index load.  The point of face j is local node j
  * (src/timecycle.f90:1293-1295), the same operand the reference uses, so the arithmetic is unchanged.
  * ---------------------------------------------------------------------------------------- */
 static int build_packed_mesh(pgpu_ctx* c) {
     int nf = c->mesh_dims + 1, nc = c->nc, rc;
-    std::vector<double> geo((size_t)nc * nf * 6);
+    const int gs = nf * 6 + 2; /* doubles per cell record: nf x {normal, point} + 16 bytes of hop codes */
+    std::vector<double> geo((size_t)nc * gs, 0.0);
     std::vector<int> code((size_t)nc * nf);
     const int nbc = (int)c->h_bc_volume.size();
     for (int ic = 0; ic < nc; ic++) {
         for (int j = 0; j < nf; j++) {
             size_t f = (size_t)ic * nf + j;
             int v = c->h_cell_nodes[f];
-            double* g = &geo[f * 6];
+            double* g = &geo[(size_t)ic * gs + 6 * j];
             for (int k = 0; k < 3; k++) {
                 g[k] = c->h_face_normal[3 * f + k];
                 g[3 + k] = c->h_node_coords[3 * (size_t)(v - 1) + k];
@@ -490,6 +497,8 @@ static int build_packed_mesh(pgpu_ctx* c) {
             }
         }
     }
+    for (int ic = 0; ic < nc; ic++) /* the hop codes ride in the same record: no dependent load in the face walk */
+        memcpy(&geo[(size_t)ic * gs + 6 * nf], &code[(size_t)ic * nf], sizeof(int) * (size_t)nf);
     if ((rc = put(c, S_FACE_GEO, geo.data(), geo.size(), &c->dev.face_geo))) return rc;
     if ((rc = put(c, S_FACE_CODE, code.data(), code.size(), &c->dev.face_code))) return rc;
     c->mesh_dirty = false;
@@ -541,6 +550,9 @@ void pg_refresh_dev(pgpu_ctx* c) {
     d.ncells = pg_ncells(c);
     d.cell_count = c->d_cell_count; d.cell_rank = c->d_rank; d.cell_off = c->d_cell_off; d.hitlist = c->d_hitlist;
     d.id_base = c->id_counter;
+    d.use_ie = (c->any_internal_dof || c->dev.nr > 0 || c->ie_seen) ? 1 : 0;
+    d.tile_first = c->d_tile_first;
+    d.ntiles = c->sorted ? (int)((c->np + PG_TILE_S - 1) / PG_TILE_S) : 0;
 }
 
 int pg_prepare(pgpu_ctx* c) {
@@ -600,11 +612,9 @@ static int alloc_planes(pgpu_ctx* c, PgPlanes& p, long long cap, bool with_dtrim
     int rc;
     memset(&p, 0, sizeof(p));
     size_t n = (size_t)cap;
-    if ((rc = dev_alloc(c, &p.x, n)) || (rc = dev_alloc(c, &p.y, n)) || (rc = dev_alloc(c, &p.z, n)) ||
-        (rc = dev_alloc(c, &p.vx, n)) || (rc = dev_alloc(c, &p.vy, n)) || (rc = dev_alloc(c, &p.vz, n)) ||
-        (rc = dev_alloc(c, &p.erot, n)) || (rc = dev_alloc(c, &p.evib, n)) || (rc = dev_alloc(c, &p.ic, n)) ||
-        (rc = dev_alloc(c, &p.sid, n)))
-        return rc;
+    if ((rc = dev_alloc(c, &p.pos, n)) || (rc = dev_alloc(c, &p.vel, n)) || (rc = dev_alloc(c, &p.ie, n))) return rc;
+    /* the ie plane is not reordered while every EROT/EVIB is zero: both copies start out (and stay) zero */
+    PG_CUDA(c, cudaMemsetAsync(p.ie, 0, sizeof(PgIe) * n, c->stream));
     if (with_dtrim && (rc = dev_alloc(c, &p.dtrim, n))) return rc;
     if (with_id && (rc = dev_alloc(c, &p.id, n))) return rc;
     return PGPU_OK;
@@ -628,10 +638,7 @@ int pg_ensure_capacity(pgpu_ctx* c, long long n) {
     PgPlanes& o = c->planes[c->cur];
     long long m = c->np;
     if (m > 0) {
-        copy_plane(c, np0.x, o.x, m); copy_plane(c, np0.y, o.y, m); copy_plane(c, np0.z, o.z, m);
-        copy_plane(c, np0.vx, o.vx, m); copy_plane(c, np0.vy, o.vy, m); copy_plane(c, np0.vz, o.vz, m);
-        copy_plane(c, np0.erot, o.erot, m); copy_plane(c, np0.evib, o.evib, m);
-        copy_plane(c, np0.ic, o.ic, m); copy_plane(c, np0.sid, o.sid, m);
+        copy_plane(c, np0.pos, o.pos, m); copy_plane(c, np0.vel, o.vel, m); copy_plane(c, np0.ie, o.ie, m);
         copy_plane(c, np0.dtrim, o.dtrim, m); copy_plane(c, np0.id, o.id, m);
         PG_CUDA(c, cudaStreamSynchronize(c->stream));
     }
@@ -644,6 +651,14 @@ int pg_ensure_capacity(pgpu_ctx* c, long long n) {
     dev_free(c->d_hitlist);
     if ((rc = dev_alloc(c, &c->d_rank, (size_t)cap))) return rc;
     if ((rc = dev_alloc(c, &c->d_hitlist, (size_t)cap))) return rc;
+    dev_free(c->d_tile_first);
+    dev_free(c->d_big_list);
+    dev_free(c->d_big_bbox);
+    c->tile_alloc = cap / PG_TILE_S + 4;
+    c->big_alloc = cap / PG_TILE_BIG + 4;
+    if ((rc = dev_alloc(c, &c->d_tile_first, (size_t)c->tile_alloc))) return rc;
+    if ((rc = dev_alloc(c, &c->d_big_list, (size_t)c->big_alloc))) return rc;
+    if ((rc = dev_alloc(c, &c->d_big_bbox, (size_t)c->big_alloc * 6))) return rc;
     c->capacity = cap;
     c->hist_valid = false;
     return PGPU_OK;
@@ -668,16 +683,22 @@ __global__ void __launch_bounds__(256) aos_to_soa_kernel(const unsigned char* __
     const unsigned char* r = aos + (size_t)i * stride;
     const double* f = reinterpret_cast<const double*>(r);
     long long o = base + i;
-    p.x[o] = f[0]; p.y[o] = f[1]; p.z[o] = f[2];
-    p.vx[o] = f[3]; p.vy[o] = f[4]; p.vz[o] = f[5];
-    p.erot[o] = f[6]; p.evib[o] = f[7];
+    int ic = *reinterpret_cast<const int*>(r + OFF_IC);
+    int sid = *reinterpret_cast<const int*>(r + OFF_SID);
+    PgPos P;
+    P.x = f[0]; P.y = f[1]; P.z = f[2]; P.ic = ic; P.sid = sid;
+    PgVel V;
+    V.vx = f[3]; V.vy = f[4]; V.vz = f[5]; V.sid = sid; V.pad = 0;
+    PgIe E;
+    E.erot = f[6]; E.evib = f[7];
+    p.pos[o] = P;
+    p.vel[o] = V;
+    p.ie[o] = E;
     double dtrim = f[8];
     p.dtrim[o] = dtrim;
-    int ic = *reinterpret_cast<const int*>(r + OFF_IC);
-    p.ic[o] = ic;
-    p.sid[o] = *reinterpret_cast<const int*>(r + OFF_SID);
     if (p.id) p.id[o] = *reinterpret_cast<const long long*>(r + OFF_ID);
-    if (dtrim != dt) st->pad = 1;
+    if (dtrim != dt) st->flag_dtrim = 1;
+    if (E.erot != 0. || E.evib != 0.) st->flag_ie = 1;
     if (ncells > 0 && (ic < 1 || ic > ncells)) atomicCAS(&st->err, 0, PG_DEVERR_CELL_RANGE);
 }
 
@@ -689,12 +710,15 @@ __global__ void __launch_bounds__(256) soa_to_aos_kernel(unsigned char* __restri
     unsigned char* r = aos + (size_t)i * stride;
     double* f = reinterpret_cast<double*>(r);
     long long o = base + i;
-    f[0] = p.x[o]; f[1] = p.y[o]; f[2] = p.z[o];
-    f[3] = p.vx[o]; f[4] = p.vy[o]; f[5] = p.vz[o];
-    f[6] = p.erot[o]; f[7] = p.evib[o];
+    const PgPos P = p.pos[o];
+    const PgVel V = p.vel[o];
+    const PgIe E = p.ie[o];
+    f[0] = P.x; f[1] = P.y; f[2] = P.z;
+    f[3] = V.vx; f[4] = V.vy; f[5] = V.vz;
+    f[6] = E.erot; f[7] = E.evib;
     f[8] = has_dtrim ? p.dtrim[o] : dt;
-    *reinterpret_cast<int*>(r + OFF_IC) = p.ic[o];
-    *reinterpret_cast<int*>(r + OFF_SID) = p.sid[o];
+    *reinterpret_cast<int*>(r + OFF_IC) = P.ic;
+    *reinterpret_cast<int*>(r + OFF_SID) = P.sid;
     /* ID = PROC_ID + ISHFT(counter, 8), ref: src/particle.f90:75 (regenerated unless cfg.track_id) */
     *reinterpret_cast<long long*>(r + OFF_ID) = p.id ? p.id[o] : ((long long)rank + (o << 8));
     *reinterpret_cast<int*>(r + OFF_TRAJ) = 0;
@@ -758,7 +782,8 @@ static int append_impl(pgpu_ctx* c, const void* aos, int64_t n, int32_t stride, 
         c->np = np_old;
         return rc;
     }
-    if (c->h_status->pad) c->has_dtrim = true;
+    if (c->h_status->flag_dtrim) c->has_dtrim = true;
+    if (c->h_status->flag_ie) c->ie_seen = true;
     c->id_counter = std::max(c->id_counter, c->np);
     return PGPU_OK;
 }
@@ -834,20 +859,21 @@ extern "C" int pgpu_download_particles(pgpu_ctx* c, void* aos, int64_t capacity,
 }
 
 /* ------------------------------------------------------------------------------------------
- * counting sort by cell (physical SoA reorder).
+ * counting sort by cell (physical reorder of the record planes).
  * The reference builds index permutations NPCALL/IOFALL/INDALL (src/collisions.f90:61-112) and then
  * gathers through them; here the histogram and the arrival rank are produced by the ADVECT epilogue,
- * an exclusive scan gives the cell offsets, and ONE scatter pass moves all planes
- * (72 B read + 72 B written + 8 B of rank/cell per particle).  Tombstones drop out here.
+ * an exclusive scan gives the cell offsets, and ONE scatter pass moves whole 32-byte records with
+ * 256-bit loads and stores (every random write is a full HBM sector).  Tombstones drop out here.
+ * The pass that follows the scan also cuts the sorted store into collision tiles (pgpu_collide.cu).
  * ---------------------------------------------------------------------------------------- */
-__global__ void __launch_bounds__(256) hist_rank_kernel(const int* __restrict__ ic, long long n,
+__global__ void __launch_bounds__(256) hist_rank_kernel(const PgPos* __restrict__ pos, long long n,
                                                         unsigned int* __restrict__ cell_count,
                                                         unsigned int* __restrict__ rank) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    int c = ic[i];
+    int c = (i < n) ? pos[i].ic : 0;
+    unsigned int live = __ballot_sync(0xffffffffu, c >= 1);
     if (c < 1) return;
-    unsigned int mask = __match_any_sync(__activemask(), c);
+    unsigned int mask = __match_any_sync(live, c);
     int leader = __ffs(mask) - 1;
     int lane = threadIdx.x & 31;
     unsigned int base = 0;
@@ -858,23 +884,38 @@ __global__ void __launch_bounds__(256) hist_rank_kernel(const int* __restrict__ 
 
 __global__ void __launch_bounds__(256) scatter_kernel(PgPlanes src, PgPlanes dst, long long n,
                                                       const unsigned int* __restrict__ cell_off,
-                                                      const unsigned int* __restrict__ rank) {
+                                                      const unsigned int* __restrict__ rank, int use_ie) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    int c = src.ic[i];
-    if (c < 1) return;
-    size_t o = (size_t)cell_off[c - 1] + rank[i];
-    dst.x[o] = src.x[i]; dst.y[o] = src.y[i]; dst.z[o] = src.z[i];
-    dst.vx[o] = src.vx[i]; dst.vy[o] = src.vy[i]; dst.vz[o] = src.vz[i];
-    dst.erot[o] = src.erot[i]; dst.evib[o] = src.evib[i];
-    dst.ic[o] = c;
-    dst.sid[o] = src.sid[i];
+    const PgPos P = src.pos[i];
+    if (P.ic < 1) return;
+    size_t o = (size_t)__ldg(&cell_off[P.ic - 1]) + rank[i];
+    dst.pos[o] = P;
+    dst.vel[o] = src.vel[i];
+    if (use_ie) dst.ie[o] = src.ie[i];
     if (src.dtrim) dst.dtrim[o] = src.dtrim[i];
     if (src.id) dst.id[o] = src.id[i];
 }
 
+/* first cell of every tile window + the list of cells too large for a tile */
+__global__ void __launch_bounds__(256) tile_index_kernel(const unsigned int* __restrict__ cell_off, int ncells,
+                                                         unsigned int* __restrict__ tile_first, int ntiles_max,
+                                                         unsigned int* __restrict__ big_list, PgStatus* st) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncells) return;
+    unsigned int o = cell_off[c], o1 = cell_off[c + 1];
+    int t0 = (int)(o / PG_TILE_S);
+    int tprev = (c == 0) ? -1 : (int)(cell_off[c - 1] / PG_TILE_S);
+    for (int t = tprev + 1; t <= t0 && t <= ntiles_max; t++) tile_first[t] = (unsigned int)c;
+    if (c == ncells - 1)
+        for (int t = t0 + 1; t <= ntiles_max; t++) tile_first[t] = (unsigned int)ncells;
+    if (o1 - o > PG_TILE_BIG) big_list[atomicAdd(&st->n_big, 1u)] = (unsigned int)c;
+}
+
 int pg_sort_impl(pgpu_ctx* c) {
     int ncells = pg_ncells(c);
+    c->n_big = 0;
+    c->dev.ntiles = 0;
     if (c->np == 0) {
         PG_CUDA(c, cudaMemsetAsync(c->d_cell_off, 0, sizeof(unsigned int) * ((size_t)ncells + 1), c->stream));
         c->sorted = true;
@@ -886,20 +927,27 @@ int pg_sort_impl(pgpu_ctx* c) {
     unsigned int blocks = (unsigned int)((c->np + 255) / 256);
     if (!c->hist_valid) {
         PG_CUDA(c, cudaMemsetAsync(c->d_cell_count, 0, sizeof(unsigned int) * ((size_t)ncells + 1), c->stream));
-        hist_rank_kernel<<<blocks, 256, 0, c->stream>>>(src.ic, c->np, c->d_cell_count, c->d_rank);
+        hist_rank_kernel<<<blocks, 256, 0, c->stream>>>(src.pos, c->np, c->d_cell_count, c->d_rank);
         c->launches++;
     }
     size_t tmp = c->scan_tmp_bytes;
     PG_CUDA(c, cub::DeviceScan::ExclusiveSum(c->d_scan_tmp, tmp, c->d_cell_count, c->d_cell_off, ncells + 1, c->stream));
     c->launches++;
-    scatter_kernel<<<blocks, 256, 0, c->stream>>>(src, dst, c->np, c->d_cell_off, c->d_rank);
+    scatter_kernel<<<blocks, 256, 0, c->stream>>>(src, dst, c->np, c->d_cell_off, c->d_rank, c->dev.use_ie);
+    c->launches++;
+    int ntiles_max = (int)((c->np + PG_TILE_S - 1) / PG_TILE_S);
+    PG_CUDA(c, cudaMemsetAsync(&c->d_status->n_big, 0, sizeof(unsigned int), c->stream));
+    tile_index_kernel<<<(unsigned int)((ncells + 255) / 256), 256, 0, c->stream>>>(c->d_cell_off, ncells, c->d_tile_first,
+                                                                                  ntiles_max, c->d_big_list, c->d_status);
     c->launches++;
     PG_CUDA(c, cudaGetLastError());
-    /* new particle count = total of the histogram */
-    unsigned int* h_total = reinterpret_cast<unsigned int*>(&c->h_status->pad);
-    PG_CUDA(c, cudaMemcpyAsync(h_total, c->d_cell_off + ncells, sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
+    /* new particle count = total of the histogram; number of oversized cells */
+    unsigned int* h = c->h_status->scratch;
+    PG_CUDA(c, cudaMemcpyAsync(&h[0], c->d_cell_off + ncells, sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
+    PG_CUDA(c, cudaMemcpyAsync(&h[1], &c->d_status->n_big, sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
     PG_CUDA(c, cudaStreamSynchronize(c->stream));
-    c->np = (long long)*h_total;
+    c->np = (long long)h[0];
+    c->n_big = h[1];
     c->cur ^= 1;
     c->sorted = true;
     c->hist_valid = false;

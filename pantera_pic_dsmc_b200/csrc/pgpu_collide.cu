@@ -1,21 +1,29 @@
 /*
- * pgpu_collide.cu -- DSMC collisions on the cell-sorted SoA store.
+ * pgpu_collide.cu -- DSMC collisions on the cell-sorted record store.
  *
  * Replaces: the cell loop of DSMC_COLLISIONS (src/collisions.f90:126-138), VSS_COLLIS (:155-558),
  * FUNCTION_I (:892-908), COLL_INTERNAL_ENERGY (:915-937), HS_SCATTER (:956-992).
  *
  * The reference walks the NCOLL candidate pairs of a cell one after another, and a later candidate sees
  * the velocities an earlier accepted one wrote (:259-551).  That order is kept EXACTLY, in parallel:
- *   1. cell_prep     8 lanes per cell: velocity bounding box -> VRMAX, NCOLL, FCORR (:202-253)
- *   2. scan          NCOLL -> first candidate of each cell; a max-scan labels every candidate with its cell
- *   3. pick          one thread per candidate: the pair (JP1, JP2) depends only on the candidate's own
- *                    counter-based Philox stream (:263-271), never on particle state
- *   4. rounds        every waiting candidate atomically claims both of its particles with its sequence
- *                    number (atomicMin); a candidate that holds both claims is the earliest one touching
- *                    either particle, so evaluating it now is what the sequential loop would do.  Evaluate,
- *                    release, repeat until none waits.  Cells, and disjoint pairs inside a cell, proceed in
- *                    parallel; chains of candidates sharing a particle serialise, as they must.
- * With the oracle run on the same Philox streams the results agree value for value (tests/test_collide_*).
+ *   prep    velocity bounding box of the cell -> VRMAX, NCOLL, FCORR (:202-253)
+ *   pick    one thread per candidate: the pair (JP1, JP2) depends only on the candidate's own counter-based
+ *           Philox stream keyed by (cell, candidate) (:263-271), never on particle state
+ *   rounds  every waiting candidate claims both of its particles with its sequence number; a candidate that
+ *           holds both claims is the earliest one touching either particle, so evaluating it now is what the
+ *           sequential loop would do.  Evaluate, repeat until none waits.  Cells, and disjoint pairs inside
+ *           a cell, proceed in parallel; chains of candidates sharing a particle serialise, as they must.
+ *
+ * Two executions of that scheme:
+ *   TILE    (the hot path) one CTA owns the cells whose first sorted slot lies in a window of PG_TILE_S
+ *           slots.  Their vel records are staged in shared memory once (one coalesced 32-byte load per
+ *           particle), prep / pick / rounds run entirely in shared memory with CTA barriers between the
+ *           claim and the evaluate half of a round, and the records are written back once: 32 B read +
+ *           32 B written per particle, no global atomics, no host round trip.
+ *   GLOBAL  cells with more than PG_TILE_BIG particles (e.g. the one-cell heat bath of config C1) do not
+ *           fit a tile; their candidates go through the same rounds with claims in global memory and one
+ *           kernel pair per round.
+ * With the oracle run on the same Philox streams both agree with it value for value (tests/test_gpu_collide.py).
  */
 #include <cub/device/device_scan.cuh>
 
@@ -33,48 +41,15 @@ struct MaxOp {
     __device__ __forceinline__ unsigned int operator()(unsigned int a, unsigned int b) const { return a > b ? a : b; }
 };
 
-/* ref: src/collisions.f90:202-253 */
-__global__ void __launch_bounds__(256) cell_prep_kernel(const __grid_constant__ PgDev d, int* __restrict__ cell_ncoll,
-                                                        double* __restrict__ cell_vrmax,
-                                                        double* __restrict__ cell_fcorr) {
-    const int G = 8;
-    long long gid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
-    int l = threadIdx.x % G;
-    bool valid = gid < d.ncells;
-    unsigned int o0 = 0, o1 = 0;
-    if (valid) {
-        o0 = d.cell_off[gid];
-        o1 = d.cell_off[gid + 1];
-    }
-    int n = (int)(o1 - o0);
-    double vxmax = -1.e+38, vxmin = 1.e+38, vymax = -1.e+38, vymin = 1.e+38, vzmax = -1.e+38, vzmin = 1.e+38;
-    if (n > 1) {
-        for (unsigned int i = o0 + l; i < o1; i += G) {
-            double vx = d.p.vx[i], vy = d.p.vy[i], vz = d.p.vz[i];
-            vxmin = fmin(vxmin, vx); vxmax = fmax(vxmax, vx);
-            vymin = fmin(vymin, vy); vymax = fmax(vymax, vy);
-            vzmin = fmin(vzmin, vz); vzmax = fmax(vzmax, vz);
-        }
-    }
-#pragma unroll
-    for (int s = G / 2; s > 0; s >>= 1) {
-        vxmin = fmin(vxmin, __shfl_xor_sync(0xffffffffu, vxmin, s, G));
-        vxmax = fmax(vxmax, __shfl_xor_sync(0xffffffffu, vxmax, s, G));
-        vymin = fmin(vymin, __shfl_xor_sync(0xffffffffu, vymin, s, G));
-        vymax = fmax(vymax, __shfl_xor_sync(0xffffffffu, vymax, s, G));
-        vzmin = fmin(vzmin, __shfl_xor_sync(0xffffffffu, vzmin, s, G));
-        vzmax = fmax(vzmax, __shfl_xor_sync(0xffffffffu, vzmax, s, G));
-    }
-    if (!valid || l != 0) return;
-    if (n <= 1) { /* ref: src/collisions.f90:129 only cells with more than one particle collide */
-        cell_ncoll[gid] = 0;
-        return;
-    }
-    double vrmax = sqrt((vxmax - vxmin) * (vxmax - vxmin) + (vymax - vymin) * (vymax - vymin) +
-                        (vzmax - vzmin) * (vzmax - vzmin));
+/* ------------------------------------------------------------------------------------------
+ * per-cell majorant, ref: src/collisions.f90:224-253
+ * ---------------------------------------------------------------------------------------- */
+__device__ __forceinline__ int cell_majorant(const PgDev& d, int cell0, int n, double vxmin, double vxmax, double vymin,
+                                             double vymax, double vzmin, double vzmax, double& vrmax, double& fcorr) {
+    vrmax = sqrt((vxmax - vxmin) * (vxmax - vxmin) + (vymax - vymin) * (vymax - vymin) + (vzmax - vzmin) * (vzmax - vzmin));
     /* ref: :224-230 */
     double vol;
-    if (d.grid_type == PGPU_UNSTRUCTURED) vol = d.cell_vol[gid];
+    if (d.grid_type == PGPU_UNSTRUCTURED) vol = __ldg(&d.cell_vol[cell0]);
     else vol = (d.xmax - d.xmin) * (d.ymax - d.ymin) * (d.zmax - d.zmin) / (d.nx * d.ny);
     /* ref: :232  0.5*NPC*(NPC-1) is evaluated in single precision */
     float pairs_f = (0.5f * (float)n) * (float)(n - 1);
@@ -85,68 +60,67 @@ __global__ void __launch_bounds__(256) cell_prep_kernel(const __grid_constant__ 
     if (!(r >= 1.)) ncoll = 1;
     else if (r > (double)half) ncoll = half;
     else ncoll = (long long)r;
-    cell_ncoll[gid] = (int)ncoll;
-    cell_vrmax[gid] = vrmax;
-    cell_fcorr[gid] = ncollmax / (double)ncoll;
+    fcorr = ncollmax / (double)ncoll;
+    return (int)ncoll;
 }
 
-__global__ void __launch_bounds__(256) cand_head_kernel(int ncells, const int* __restrict__ cell_ncoll,
-                                                        const unsigned int* __restrict__ cand_off,
-                                                        unsigned int* __restrict__ cand_cell) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= ncells) return;
-    if (cell_ncoll[c] > 0) cand_cell[cand_off[c]] = (unsigned int)c;
-}
-
-/* ref: src/collisions.f90:263-271 pair selection; also the first claim round */
-__global__ void __launch_bounds__(256) cand_pick_kernel(const __grid_constant__ PgDev d, long long ncand,
-                                                        const unsigned int* __restrict__ cand_cell,
-                                                        const unsigned int* __restrict__ cand_off,
-                                                        uint4* __restrict__ cand, unsigned int* __restrict__ owner) {
-    long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= ncand) return;
-    unsigned int c = cand_cell[g];
-    unsigned int j = (unsigned int)(g - cand_off[c]);
-    unsigned int o0 = d.cell_off[c];
-    int npcj = (int)(d.cell_off[c + 1] - o0);
+/* ref: src/collisions.f90:263-271 pair selection from the candidate's own stream; returns the draws used */
+__device__ __forceinline__ unsigned int pick_pair(const PgDev& d, unsigned int cell0, unsigned int j, int npcj, int& k1, int& k2) {
     PgRng rng;
-    rng.init(d.seed_local, 2, d.tID, (unsigned long long)c, (unsigned long long)j);
-    int k1 = (int)(npcj * rng.rf());
+    rng.init(d.seed_local, 2, d.tID, (unsigned long long)cell0, (unsigned long long)j);
+    k1 = (int)(npcj * rng.rf());
     if (k1 >= npcj) k1 = npcj - 1;
-    int k2 = k1;
+    k2 = k1;
     while (k2 == k1) {
         k2 = (int)(npcj * rng.rf());
         if (k2 >= npcj) k2 = npcj - 1;
     }
-    uint4 rec;
-    rec.x = o0 + (unsigned int)k1;
-    rec.y = o0 + (unsigned int)k2;
-    rec.z = c;
-    rec.w = rng.ndraw;
-    cand[g] = rec;
-    atomicMin(&owner[rec.x], (unsigned int)g);
-    atomicMin(&owner[rec.y], (unsigned int)g);
+    return rng.ndraw;
 }
 
-__global__ void __launch_bounds__(256) cand_mark_kernel(long long ncand, const uint4* __restrict__ cand,
-                                                        unsigned int* __restrict__ owner) {
-    long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= ncand) return;
-    uint4 rec = cand[g];
-    if (rec.z & CAND_DONE) return;
-    atomicMin(&owner[rec.x], (unsigned int)g);
-    atomicMin(&owner[rec.y], (unsigned int)g);
-}
+/* ------------------------------------------------------------------------------------------
+ * one candidate pair of VSS_COLLIS, ref: src/collisions.f90:274-546, on register copies of the pair
+ * ---------------------------------------------------------------------------------------- */
+struct PairIO {
+    double c1[3], c2[3];
+    double erot1, evib1, erot2, evib2;
+    int s1, s2;
+};
+enum { PR_ACCEPTED = 1, PR_REACTED = 2, PR_V = 4, PR_E1 = 8, PR_E2 = 16, PR_S = 32 };
 
 #define VSS2(arr, s1, s2) __ldg(&(arr)[((s1)-1) + (size_t)d.ns * ((s2)-1)])
 
-/* one candidate pair of VSS_COLLIS, ref: src/collisions.f90:274-546 */
-__device__ void collide_pair(const PgDev& d, PgRng& g, unsigned int jp1, unsigned int jp2, int cell0, double vrmax,
-                             double fcorr, int& accepted, int& reacted) {
+/* acceptance test of a candidate, ref: src/collisions.f90:274-325; rfp is the candidate's acceptance draw.
+ * The cross-section power law is first bracketed in single precision (MUFU lg2/ex2, relative error
+ * < 1e-5): only when the draw falls inside the bracket is the FP64 pow() evaluated, so the decision is
+ * the one the full-precision expression gives while almost no candidate pays for an FP64 pow. */
+__device__ __forceinline__ bool pair_accept(const PgDev& d, double rfp, const double* c1, const double* c2, int s1, int s2,
+                                            double vrmax, double fcorr) {
+    double vr2 = (c2[0] - c1[0]) * (c2[0] - c1[0]) + (c2[1] - c1[1]) * (c2[1] - c1[1]) + (c2[2] - c1[2]) * (c2[2] - c1[2]);
+    double vr = sqrt(vr2);
+    double cref = VSS2(d.grefs, s1, s2), sigma = VSS2(d.sigmas, s1, s2);
+    double omega = VSS2(d.omegas, s1, s2);
+    double collsigma;
+    if (fabs(omega - 0.5) < 1.e-6) {
+        collsigma = sigma;
+    } else {
+        if (vr < (double)1e-20f) return false; /* ref: :314 (single-precision literal) */
+        double est = fcorr / (d.sigmamax * vrmax) * vr * (sigma * (double)__powf((float)(vr / cref), (float)(1. - 2. * omega)));
+        if (rfp < est * (1. - 1.e-4)) return true;
+        if (rfp > est * (1. + 1.e-4)) return false;
+        collsigma = sigma * pow(vr / cref, 1. - 2. * omega);
+    }
+    double collprob = fcorr / (d.sigmamax * vrmax) * vr * collsigma;
+    return rfp < collprob;
+}
+
+/* an ACCEPTED candidate: reactions, Borgnakke-Larsen, VSS deflection, ref: src/collisions.f90:327-546.
+ * g continues the candidate's stream right after the acceptance draw. */
+__device__ int pair_collide(const PgDev& d, PgRng& g, PairIO& p, long long gslot2, int cell0) {
     const double PI2 = 2. * PG_PI;
-    double c1[3] = {d.p.vx[jp1], d.p.vy[jp1], d.p.vz[jp1]};
-    double c2[3] = {d.p.vx[jp2], d.p.vy[jp2], d.p.vz[jp2]};
-    int s1 = d.p.sid[jp1], s2 = d.p.sid[jp2];
+    double* c1 = p.c1;
+    double* c2 = p.c2;
+    const int s1 = p.s1, s2 = p.s2;
     double vr2 = (c2[0] - c1[0]) * (c2[0] - c1[0]) + (c2[1] - c1[1]) * (c2[1] - c1[1]) + (c2[2] - c1[2]) * (c2[2] - c1[2]);
     double vr = sqrt(vr2);
     double cref = VSS2(d.grefs, s1, s2), sigma = VSS2(d.sigmas, s1, s2);
@@ -154,27 +128,12 @@ __device__ void collide_pair(const PgDev& d, PgRng& g, unsigned int jp1, unsigne
     double m1 = __ldg(&d.mass[s1 - 1]), m2 = __ldg(&d.mass[s2 - 1]);
     double mred = m1 * m2 / (m1 + m2);
     double etr = 0.5 * mred * vr2;
-
-    double rfp = g.rf();
-    double collsigma;
-    if (fabs(omega - 0.5) < 1.e-6) {
-        collsigma = sigma;
-    } else {
-        if (vr < (double)1e-20f) return; /* ref: :314 (single-precision literal) */
-        collsigma = sigma * pow(vr / cref, 1. - 2. * omega);
-    }
-    double collprob = fcorr / (d.sigmamax * vrmax) * vr * collsigma;
-    if (!(rfp < collprob)) return;
-    accepted = 1;
+    double rfp;
+    int flags = PR_ACCEPTED;
 
     int rd1 = __ldg(&d.rotdof[s1 - 1]), rd2 = __ldg(&d.rotdof[s2 - 1]);
     int vd1 = __ldg(&d.vibdof[s1 - 1]), vd2 = __ldg(&d.vibdof[s2 - 1]);
-    bool internal = (d.nr > 0) || rd1 || rd2 || vd1 || vd2;
-    double erot1 = 0., evib1 = 0., erot2 = 0., evib2 = 0.;
-    if (internal) {
-        erot1 = d.p.erot[jp1]; evib1 = d.p.evib[jp1];
-        erot2 = d.p.erot[jp2]; evib2 = d.p.evib[jp2];
-    }
+    double erot1 = p.erot1, evib1 = p.evib1, erot2 = p.erot2, evib2 = p.evib2;
 
     /* ref: :331-449 TCE / LXCat reaction test */
     double ecoll = etr + erot1 + erot2 + evib1 + evib2;
@@ -198,18 +157,14 @@ __device__ void collide_pair(const PgDev& d, PgRng& g, unsigned int jp1, unsigne
         }
         rfp = g.rf();
         if (rfp < ptce) {
-            reacted = 1;
             ecoll = ecoll - ea;
             /* roles are NOT swapped when the pair order is opposite to the reaction */
-            pg_react_redistribute(d, g, r, ecoll, c1, c2, erot1, evib1, erot2, evib2, d.p.x[jp2], d.p.y[jp2],
-                                  d.p.z[jp2], cell0 + 1);
-            d.p.sid[jp1] = r.p1;
-            d.p.sid[jp2] = r.p2;
-            d.p.erot[jp1] = erot1; d.p.evib[jp1] = evib1;
-            d.p.erot[jp2] = erot2; d.p.evib[jp2] = evib2;
-            d.p.vx[jp1] = c1[0]; d.p.vy[jp1] = c1[1]; d.p.vz[jp1] = c1[2];
-            d.p.vx[jp2] = c2[0]; d.p.vy[jp2] = c2[1]; d.p.vz[jp2] = c2[2];
-            return;
+            const PgPos P2 = d.p.pos[gslot2];
+            pg_react_redistribute(d, g, r, ecoll, c1, c2, erot1, evib1, erot2, evib2, P2.x, P2.y, P2.z, cell0 + 1);
+            p.s1 = r.p1;
+            p.s2 = r.p2;
+            p.erot1 = erot1; p.evib1 = evib1; p.erot2 = erot2; p.evib2 = evib2;
+            return flags | PR_REACTED | PR_V | PR_E1 | PR_E2 | PR_S;
         }
     }
 
@@ -225,22 +180,26 @@ __device__ void collide_pair(const PgDev& d, PgRng& g, unsigned int jp1, unsigne
         ecoll = etr + erot1;
         erot1 = coll_internal_energy(g, ecoll, trdof, rd1);
         etr = ecoll - erot1;
-        d.p.erot[jp1] = erot1;
+        p.erot1 = erot1;
+        flags |= PR_E1;
     } else if (rfp < prot1 + prot2) {
         ecoll = etr + erot2;
         erot2 = coll_internal_energy(g, ecoll, trdof, rd2);
         etr = ecoll - erot2;
-        d.p.erot[jp2] = erot2;
+        p.erot2 = erot2;
+        flags |= PR_E2;
     } else if (rfp < prot1 + prot2 + pvib1) {
         ecoll = etr + evib1;
         evib1 = coll_internal_energy(g, ecoll, trdof, vd1);
         etr = ecoll - evib1;
-        d.p.evib[jp1] = evib1;
+        p.evib1 = evib1;
+        flags |= PR_E1;
     } else if (rfp < prot1 + prot2 + pvib1 + pvib2) {
         ecoll = etr + evib2;
         evib2 = coll_internal_energy(g, ecoll, trdof, vd2);
         etr = ecoll - evib2;
-        d.p.evib[jp2] = evib2;
+        p.evib2 = evib2;
+        flags |= PR_E2;
     }
 
     /* ref: :495-546 VSS deflection */
@@ -273,15 +232,459 @@ __device__ void collide_pair(const PgDev& d, PgRng& g, unsigned int jp1, unsigne
         c1[i] = wc[i] + m2 / (m1 + m2) * grel[i];
         c2[i] = wc[i] - m1 / (m1 + m2) * grel[i];
     }
-    d.p.vx[jp1] = c1[0]; d.p.vy[jp1] = c1[1]; d.p.vz[jp1] = c1[2];
-    d.p.vx[jp2] = c2[0]; d.p.vy[jp2] = c2[1]; d.p.vz[jp2] = c2[2];
+    return flags | PR_V;
+}
+
+/* one candidate pair of VSS_COLLIS start to end (GLOBAL path) */
+__device__ int collide_pair_core(const PgDev& d, PgRng& g, PairIO& p, long long gslot2, int cell0, double vrmax, double fcorr) {
+    if (!pair_accept(d, g.rf(), p.c1, p.c2, p.s1, p.s2, vrmax, fcorr)) return 0;
+    return pair_collide(d, g, p, gslot2, cell0);
+}
+
+/* ==========================================================================================
+ * TILE path
+ * ======================================================================================== */
+/*
+ * Everything about an accepted collision that depends only on the candidate's random stream and on the
+ * species of the pair (fixed while nothing reacts): the acceptance draw, the VSS deflection angles and the
+ * Borgnakke-Larsen selector.  Without internal energy and reactions (!IE) the draws of a candidate sit at
+ * fixed positions of its stream (acceptance, BL selector, chi, theta, [isotropic redirection x2]), so this is
+ * computed for ALL candidates of the tile in one dense pass BEFORE the dependency rounds: the pow / sincos /
+ * Philox work leaves the serial chain, and what remains inside a round is ~60 FP64 operations per pair.
+ */
+struct CandPre {
+    double r_acc, coschi, sinchi, costheta, sintheta;
+};
+
+struct TileSmem {
+    PgVel v[PG_TILE_CAP];
+    double vrmax[PG_TILE_MAXC], fcorr[PG_TILE_MAXC];
+    uint2 cand[PG_TILE_CAP / 2]; /* x: local slot of JP1 | JP2 << 16;  y: tile cell | draws used by the pick << 16
+                                    | inelastic redirection << 31 */
+    unsigned int own[PG_TILE_CAP];
+    unsigned int goff[PG_TILE_MAXC];     /* first global slot of the cell */
+    unsigned int coff[PG_TILE_MAXC + 1]; /* NCOLL, then its exclusive prefix */
+    int cell[PG_TILE_MAXC];              /* global cell, 0-based */
+    unsigned short base[PG_TILE_MAXC], n[PG_TILE_MAXC];
+    unsigned short pend[2][PG_TILE_CAP / 2]; /* candidates still waiting, this round / next round */
+    unsigned short acc[PG_TILE_CAP / 2];     /* candidates accepted in this round */
+    unsigned int ncl, nloc, ncand, npend[2], nacc_round[2], nacc, nreac;
+};
+
+/* the deflection of an accepted pair from precomputed angles; same expressions as pair_collide */
+__device__ __forceinline__ void pair_deflect_fast(const PgDev& d, PgRng& g, const CandPre& q, bool inelastic, double* c1,
+                                                  double* c2, int s1, int s2) {
+    const double PI2 = 2. * PG_PI;
+    double m1 = __ldg(&d.mass[s1 - 1]), m2 = __ldg(&d.mass[s2 - 1]);
+    double gx, gy, gz, gg;
+    if (inelastic) { /* ref: :505-514; only with ROTREL/VIBREL != 0 on a species without internal modes */
+        double vr2 = (c2[0] - c1[0]) * (c2[0] - c1[0]) + (c2[1] - c1[1]) * (c2[1] - c1[1]) + (c2[2] - c1[2]) * (c2[2] - c1[2]);
+        double mred = m1 * m2 / (m1 + m2);
+        double etr = 0.5 * mred * vr2;
+        double ecoll = etr + 0.;
+        etr = ecoll - 0.;
+        gg = sqrt(2. * etr / mred);
+        double cosa = 2. * g.rf() - 1.0;
+        double sina = sqrt(1 - cosa * cosa);
+        double bb = PI2 * g.rf();
+        gx = gg * sina * cos(bb);
+        gy = gg * sina * sin(bb);
+        gz = gg * cosa;
+    } else {
+        gx = c1[0] - c2[0];
+        gy = c1[1] - c2[1];
+        gz = c1[2] - c2[2];
+        gg = sqrt(gx * gx + gy * gy + gz * gz);
+    }
+    const double coschi = q.coschi, sinchi = q.sinchi, costheta = q.costheta, sintheta = q.sintheta;
+    double grel[3], wc[3];
+    double gyz = sqrt(gy * gy + gz * gz);
+    grel[0] = gx * coschi + gyz * sintheta * sinchi;
+    grel[1] = gy * coschi + (gg * gz * costheta - gx * gy * sintheta) / gyz * sinchi;
+    grel[2] = gz * coschi - (gg * gy * costheta + gx * gz * sintheta) / gyz * sinchi;
+    for (int i = 0; i < 3; i++) wc[i] = m1 / (m1 + m2) * c1[i] + m2 / (m1 + m2) * c2[i];
+    for (int i = 0; i < 3; i++) {
+        c1[i] = wc[i] + m2 / (m1 + m2) * grel[i];
+        c2[i] = wc[i] - m1 / (m1 + m2) * grel[i];
+    }
+}
+
+template <bool IE>
+__global__ void __launch_bounds__(PG_TILE_THREADS, 3) tile_collide_kernel(const __grid_constant__ PgDev d) {
+    extern __shared__ __align__(32) unsigned char smem_raw[];
+    TileSmem& S = *reinterpret_cast<TileSmem*>(smem_raw);
+    /* behind the common part: the staged ie records (IE) or the precomputed candidate terms (!IE) */
+    unsigned char* extra = smem_raw + ((sizeof(TileSmem) + 31) & ~(size_t)31);
+    PgIe* se = reinterpret_cast<PgIe*>(extra);
+    CandPre* pre = reinterpret_cast<CandPre*>(extra);
+    constexpr int T = PG_TILE_THREADS;
+    const unsigned int FULL = 0xffffffffu;
+    const int t = threadIdx.x, lane = t & 31;
+    const unsigned int c0 = d.tile_first[blockIdx.x], c1 = d.tile_first[blockIdx.x + 1];
+    if (c0 >= c1) return;
+    if (t == 0) { S.ncl = 0; S.nloc = 0; S.ncand = 0; S.npend[0] = 0; S.npend[1] = 0; S.nacc_round[0] = 0; S.nacc_round[1] = 0; S.nacc = 0; S.nreac = 0; }
+    __syncthreads();
+
+    /* A: cells of this tile that can collide (2..PG_TILE_BIG particles), packed into the staging area */
+    for (unsigned int c = c0 + t; c < c1; c += T) {
+        unsigned int o = d.cell_off[c];
+        unsigned int n = d.cell_off[c + 1] - o;
+        if (n >= 2 && n <= PG_TILE_BIG) {
+            unsigned int k = atomicAdd(&S.ncl, 1u);
+            unsigned int b = atomicAdd(&S.nloc, n);
+            S.cell[k] = (int)c;
+            S.goff[k] = o;
+            S.base[k] = (unsigned short)b;
+            S.n[k] = (unsigned short)n;
+        }
+    }
+    __syncthreads();
+    const int ncl = (int)S.ncl;
+    if (ncl == 0) return;
+
+    /* B: stage the records, velocity bounding box, majorant -- eight lanes per cell */
+    {
+        const int grp = t >> 3, gl = t & 7;
+        for (int k0 = 0; k0 < ncl; k0 += T / 8) { /* trip count uniform over the CTA: the shuffles below are full-warp */
+            const int k = k0 + grp;
+            const bool valid = k < ncl;
+            const int n = valid ? (int)S.n[k] : 0, b = valid ? (int)S.base[k] : 0;
+            const unsigned int o = valid ? S.goff[k] : 0u;
+            double vxmax = -1.e+38, vxmin = 1.e+38, vymax = -1.e+38, vymin = 1.e+38, vzmax = -1.e+38, vzmin = 1.e+38;
+            for (int i = gl; i < n; i += 8) {
+                const PgVel V = d.p.vel[o + i];
+                S.v[b + i] = V;
+                S.own[b + i] = 0u;
+                if (IE) se[b + i] = d.p.ie[o + i];
+                vxmin = fmin(vxmin, V.vx); vxmax = fmax(vxmax, V.vx);
+                vymin = fmin(vymin, V.vy); vymax = fmax(vymax, V.vy);
+                vzmin = fmin(vzmin, V.vz); vzmax = fmax(vzmax, V.vz);
+            }
+#pragma unroll
+            for (int s = 4; s > 0; s >>= 1) {
+                vxmin = fmin(vxmin, __shfl_xor_sync(FULL, vxmin, s, 8));
+                vxmax = fmax(vxmax, __shfl_xor_sync(FULL, vxmax, s, 8));
+                vymin = fmin(vymin, __shfl_xor_sync(FULL, vymin, s, 8));
+                vymax = fmax(vymax, __shfl_xor_sync(FULL, vymax, s, 8));
+                vzmin = fmin(vzmin, __shfl_xor_sync(FULL, vzmin, s, 8));
+                vzmax = fmax(vzmax, __shfl_xor_sync(FULL, vzmax, s, 8));
+            }
+            if (valid && gl == 0) {
+                double vrmax, fcorr;
+                int ncoll = cell_majorant(d, S.cell[k], n, vxmin, vxmax, vymin, vymax, vzmin, vzmax, vrmax, fcorr);
+                S.vrmax[k] = vrmax;
+                S.fcorr[k] = fcorr;
+                S.coff[k] = (unsigned int)ncoll;
+            }
+        }
+    }
+    __syncthreads();
+
+    /* C: candidate offsets (exclusive scan of NCOLL over the tile's cells, warp 0) */
+    if (t < 32) {
+        unsigned int run = 0;
+        for (int k0 = 0; k0 < ncl; k0 += 32) {
+            int k = k0 + lane;
+            unsigned int v = (k < ncl) ? S.coff[k] : 0u, x = v;
+#pragma unroll
+            for (int s = 1; s < 32; s <<= 1) {
+                unsigned int y = __shfl_up_sync(FULL, x, s);
+                if (lane >= s) x += y;
+            }
+            if (k < ncl) S.coff[k] = run + x - v;
+            run += __shfl_sync(FULL, x, 31);
+        }
+        if (lane == 0) { S.coff[ncl] = run; S.ncand = run; S.npend[0] = run; }
+    }
+    __syncthreads();
+    const int ncand = (int)S.ncand;
+
+    /* D: pair selection, the stream-only terms of the collision (!IE), and the claims of round 1.
+     * Claim word = round << 16 | (0xFFFF - candidate): a later round beats stale claims, inside a round the
+     * earliest candidate wins; nothing has to be reset. */
+    for (int g = t; g < ncand; g += T) {
+        int lo = 0, hi = ncl; /* last k with coff[k] <= g */
+        while (hi - lo > 1) {
+            int mid = (lo + hi) >> 1;
+            if (S.coff[mid] <= (unsigned int)g) lo = mid;
+            else hi = mid;
+        }
+        const int k = lo;
+        const unsigned int b = S.base[k];
+        PgRng rng;
+        rng.init(d.seed_local, 2, d.tID, (unsigned long long)(unsigned int)S.cell[k], (unsigned long long)(g - S.coff[k]));
+        /* ref: src/collisions.f90:263-271 */
+        const int npcj = (int)S.n[k];
+        int k1 = (int)(npcj * rng.rf());
+        if (k1 >= npcj) k1 = npcj - 1;
+        int k2 = k1;
+        while (k2 == k1) {
+            k2 = (int)(npcj * rng.rf());
+            if (k2 >= npcj) k2 = npcj - 1;
+        }
+        unsigned int meta = (unsigned int)k | (rng.ndraw << 16);
+        if (!IE) {
+            const double PI2 = 2. * PG_PI;
+            const int s1 = S.v[b + k1].sid, s2 = S.v[b + k2].sid;
+            CandPre q;
+            q.r_acc = rng.rf();
+            /* ref: :454-490 with no internal modes: the selector only decides whether the post-collision
+             * relative velocity is redirected isotropically (:505-514) */
+            const double rbl = rng.rf();
+            const double psum = __ldg(&d.rotrel[s1 - 1]) + __ldg(&d.rotrel[s2 - 1]) + __ldg(&d.vibrel[s1 - 1]) + __ldg(&d.vibrel[s2 - 1]);
+            if (rbl < psum) meta |= 0x80000000u;
+            /* ref: :495-499 */
+            const double alpha = VSS2(d.alphas, s1, s2);
+            q.coschi = 2. * pow(rng.rf(), 1. / alpha) - 1.;
+            q.sinchi = sqrt(1. - q.coschi * q.coschi);
+            const double theta = PI2 * rng.rf();
+            q.costheta = cos(theta);
+            q.sintheta = sin(theta);
+            pre[g] = q;
+        }
+        S.cand[g] = make_uint2((b + k1) | ((b + k2) << 16), meta);
+        S.pend[0][g] = (unsigned short)g;
+        const unsigned int tag = (1u << 16) | (0xFFFFu - (unsigned int)g);
+        atomicMax(&S.own[b + k1], tag);
+        atomicMax(&S.own[b + k2], tag);
+    }
+    __syncthreads();
+
+    int cur = 0, nacc = 0, nreac = 0;
+    for (unsigned int round = 1;; round++) {
+        const int np = (int)S.npend[cur];
+        if (np == 0) break;
+        /* pass A: a candidate holding both claims is next in line for both particles: acceptance test */
+        for (int i = t; i < np; i += T) {
+            const unsigned int g = S.pend[cur][i];
+            const uint2 rec = S.cand[g];
+            const unsigned int j1 = rec.x & 0xFFFFu, j2 = rec.x >> 16;
+            const unsigned int tag = (round << 16) | (0xFFFFu - g);
+            if (S.own[j1] != tag || S.own[j2] != tag) {
+                S.pend[cur ^ 1][atomicAdd(&S.npend[cur ^ 1], 1u)] = (unsigned short)g;
+                continue;
+            }
+            const int k = (int)(rec.y & 0xFFFFu);
+            double rfp;
+            if (IE) {
+                PgRng rng;
+                rng.init(d.seed_local, 2, d.tID, (unsigned long long)(unsigned int)S.cell[k], (unsigned long long)(g - S.coff[k]));
+                rng.seek((rec.y >> 16) & 0x7FFFu); /* the pick consumed that many draws of this candidate's stream */
+                rfp = rng.rf();
+            } else {
+                rfp = pre[g].r_acc;
+            }
+            const PgVel V1 = S.v[j1], V2 = S.v[j2];
+            const double a1[3] = {V1.vx, V1.vy, V1.vz}, a2[3] = {V2.vx, V2.vy, V2.vz};
+            if (pair_accept(d, rfp, a1, a2, V1.sid, V2.sid, S.vrmax[k], S.fcorr[k])) {
+                S.acc[atomicAdd(&S.nacc_round[round & 1u], 1u)] = (unsigned short)g;
+                nacc++;
+            }
+        }
+        __syncthreads();
+        /* pass B: the accepted candidates of this round (disjoint particles), densely packed over the threads;
+         * and the claims of the next round */
+        const int na = (int)S.nacc_round[round & 1u], np2 = (int)S.npend[cur ^ 1];
+        if (t == 0) { /* counters of the next round; their last readers passed the previous barrier */
+            S.npend[cur] = 0;
+            S.nacc_round[(round + 1u) & 1u] = 0;
+        }
+        for (int i = t; i < na; i += T) {
+            const unsigned int g = S.acc[i];
+            const uint2 rec = S.cand[g];
+            const unsigned int j1 = rec.x & 0xFFFFu, j2 = rec.x >> 16;
+            const int k = (int)(rec.y & 0xFFFFu);
+            const unsigned int cell0 = (unsigned int)S.cell[k];
+            const unsigned int nd = (rec.y >> 16) & 0x7FFFu;
+            PgRng rng;
+            rng.init(d.seed_local, 2, d.tID, (unsigned long long)cell0, (unsigned long long)(g - S.coff[k]));
+            const PgVel V1 = S.v[j1], V2 = S.v[j2];
+            PairIO p;
+            p.c1[0] = V1.vx; p.c1[1] = V1.vy; p.c1[2] = V1.vz; p.s1 = V1.sid;
+            p.c2[0] = V2.vx; p.c2[1] = V2.vy; p.c2[2] = V2.vz; p.s2 = V2.sid;
+            if (!IE) {
+                const bool inelastic = (rec.y >> 31) != 0;
+                if (inelastic) rng.seek(nd + 4u); /* pick, acceptance, selector, chi, theta */
+                pair_deflect_fast(d, rng, pre[g], inelastic, p.c1, p.c2, p.s1, p.s2);
+                PgVel W1, W2;
+                W1.vx = p.c1[0]; W1.vy = p.c1[1]; W1.vz = p.c1[2]; W1.sid = p.s1; W1.pad = 0;
+                W2.vx = p.c2[0]; W2.vy = p.c2[1]; W2.vz = p.c2[2]; W2.sid = p.s2; W2.pad = 0;
+                S.v[j1] = W1;
+                S.v[j2] = W2;
+            } else {
+                rng.seek(nd + 1u); /* pick + acceptance draw */
+                const PgIe E1 = se[j1], E2 = se[j2];
+                p.erot1 = E1.erot; p.evib1 = E1.evib; p.erot2 = E2.erot; p.evib2 = E2.evib;
+                const long long g1 = (long long)S.goff[k] + (j1 - S.base[k]), g2 = (long long)S.goff[k] + (j2 - S.base[k]);
+                const int fl = pair_collide(d, rng, p, g2, (int)cell0);
+                if (fl & PR_REACTED) nreac++;
+                if (fl & (PR_V | PR_S)) {
+                    PgVel W1, W2;
+                    W1.vx = p.c1[0]; W1.vy = p.c1[1]; W1.vz = p.c1[2]; W1.sid = p.s1; W1.pad = 0;
+                    W2.vx = p.c2[0]; W2.vy = p.c2[1]; W2.vz = p.c2[2]; W2.sid = p.s2; W2.pad = 0;
+                    S.v[j1] = W1;
+                    S.v[j2] = W2;
+                }
+                if (fl & PR_E1) { PgIe E; E.erot = p.erot1; E.evib = p.evib1; se[j1] = E; }
+                if (fl & PR_E2) { PgIe E; E.erot = p.erot2; E.evib = p.evib2; se[j2] = E; }
+                if (fl & PR_S) { /* the species mirror in the pos records */
+                    d.p.pos[g1].sid = p.s1;
+                    d.p.pos[g2].sid = p.s2;
+                }
+            }
+        }
+        for (int i = t; i < np2; i += T) {
+            const unsigned int g = S.pend[cur ^ 1][i];
+            const unsigned int pr = S.cand[g].x;
+            const unsigned int tag = ((round + 1u) << 16) | (0xFFFFu - g);
+            atomicMax(&S.own[pr & 0xFFFFu], tag);
+            atomicMax(&S.own[pr >> 16], tag);
+        }
+        __syncthreads();
+        cur ^= 1;
+    }
+
+    /* E: write the records back */
+    {
+        const int grp = t >> 3, gl = t & 7;
+        for (int k = grp; k < ncl; k += T / 8) {
+            const int n = S.n[k], b = S.base[k];
+            const unsigned int o = S.goff[k];
+            for (int i = gl; i < n; i += 8) {
+                d.p.vel[o + i] = S.v[b + i];
+                if (IE) d.p.ie[o + i] = se[b + i];
+            }
+        }
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        nacc += __shfl_xor_sync(FULL, nacc, s);
+        nreac += __shfl_xor_sync(FULL, nreac, s);
+    }
+    if (lane == 0) {
+        if (nacc) atomicAdd(&S.nacc, (unsigned int)nacc);
+        if (nreac) atomicAdd(&S.nreac, (unsigned int)nreac);
+    }
+    __syncthreads();
+    if (t == 0) {
+        if (S.nacc) atomicAdd(&d.status->ncoll, (unsigned long long)S.nacc);
+        if (S.nreac) atomicAdd(&d.status->nreac, (unsigned long long)S.nreac);
+    }
+}
+
+/* ==========================================================================================
+ * GLOBAL path: the cells of big_list (more than PG_TILE_BIG particles)
+ * ======================================================================================== */
+__device__ __forceinline__ unsigned long long enc_f64(double x) {
+    unsigned long long u = (unsigned long long)__double_as_longlong(x);
+    return (u >> 63) ? ~u : (u | 0x8000000000000000ULL);
+}
+__device__ __forceinline__ double dec_f64(unsigned long long u) {
+    u = (u >> 63) ? (u & 0x7FFFFFFFFFFFFFFFULL) : ~u;
+    return __longlong_as_double((long long)u);
+}
+
+__global__ void big_init_kernel(unsigned long long* bbox, unsigned int nbig) {
+    unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nbig * 6) return;
+    bbox[i] = ((i % 6) < 3) ? ~0ULL : 0ULL; /* [0..2] minima, [3..5] maxima */
+}
+
+/* grid (nbig, Y): the Y CTAs of a cell stride over its particles */
+__global__ void __launch_bounds__(256) big_bbox_kernel(const __grid_constant__ PgDev d, const unsigned int* __restrict__ big_list,
+                                                       unsigned long long* __restrict__ bbox) {
+    const unsigned int b = blockIdx.x, c = big_list[b];
+    const unsigned int o0 = d.cell_off[c], o1 = d.cell_off[c + 1];
+    double vxmax = -1.e+38, vxmin = 1.e+38, vymax = -1.e+38, vymin = 1.e+38, vzmax = -1.e+38, vzmin = 1.e+38;
+    bool any = false;
+    for (unsigned long long i = (unsigned long long)o0 + blockIdx.y * 256u + threadIdx.x; i < o1; i += (unsigned long long)gridDim.y * 256u) {
+        const PgVel V = d.p.vel[i];
+        vxmin = fmin(vxmin, V.vx); vxmax = fmax(vxmax, V.vx);
+        vymin = fmin(vymin, V.vy); vymax = fmax(vymax, V.vy);
+        vzmin = fmin(vzmin, V.vz); vzmax = fmax(vzmax, V.vz);
+        any = true;
+    }
+    if (!__any_sync(0xffffffffu, any)) return;
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        vxmin = fmin(vxmin, __shfl_xor_sync(0xffffffffu, vxmin, s));
+        vxmax = fmax(vxmax, __shfl_xor_sync(0xffffffffu, vxmax, s));
+        vymin = fmin(vymin, __shfl_xor_sync(0xffffffffu, vymin, s));
+        vymax = fmax(vymax, __shfl_xor_sync(0xffffffffu, vymax, s));
+        vzmin = fmin(vzmin, __shfl_xor_sync(0xffffffffu, vzmin, s));
+        vzmax = fmax(vzmax, __shfl_xor_sync(0xffffffffu, vzmax, s));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        unsigned long long* q = bbox + 6 * (size_t)b;
+        atomicMin(&q[0], enc_f64(vxmin)); atomicMin(&q[1], enc_f64(vymin)); atomicMin(&q[2], enc_f64(vzmin));
+        atomicMax(&q[3], enc_f64(vxmax)); atomicMax(&q[4], enc_f64(vymax)); atomicMax(&q[5], enc_f64(vzmax));
+    }
+}
+
+__global__ void big_prep_kernel(const __grid_constant__ PgDev d, const unsigned int* __restrict__ big_list, unsigned int nbig,
+                                const unsigned long long* __restrict__ bbox, int* __restrict__ big_ncoll,
+                                double* __restrict__ big_vrmax, double* __restrict__ big_fcorr) {
+    unsigned int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b > nbig) return;
+    if (b == nbig) { big_ncoll[b] = 0; return; } /* terminator of the exclusive scan */
+    const unsigned int c = big_list[b];
+    const int n = (int)(d.cell_off[c + 1] - d.cell_off[c]);
+    const unsigned long long* q = bbox + 6 * (size_t)b;
+    double vrmax, fcorr;
+    big_ncoll[b] = cell_majorant(d, (int)c, n, dec_f64(q[0]), dec_f64(q[3]), dec_f64(q[1]), dec_f64(q[4]), dec_f64(q[2]), dec_f64(q[5]),
+                                 vrmax, fcorr);
+    big_vrmax[b] = vrmax;
+    big_fcorr[b] = fcorr;
+}
+
+__global__ void __launch_bounds__(256) cand_head_kernel(unsigned int nbig, const int* __restrict__ big_ncoll,
+                                                        const unsigned int* __restrict__ cand_off,
+                                                        unsigned int* __restrict__ cand_big) {
+    unsigned int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nbig) return;
+    if (big_ncoll[b] > 0) cand_big[cand_off[b]] = b;
+}
+
+/* pair selection; also the first claim round */
+__global__ void __launch_bounds__(256) cand_pick_kernel(const __grid_constant__ PgDev d, long long ncand,
+                                                        const unsigned int* __restrict__ big_list,
+                                                        const unsigned int* __restrict__ cand_big,
+                                                        const unsigned int* __restrict__ cand_off,
+                                                        uint4* __restrict__ cand, unsigned int* __restrict__ owner) {
+    long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= ncand) return;
+    unsigned int b = cand_big[g];
+    unsigned int c = big_list[b];
+    unsigned int j = (unsigned int)(g - cand_off[b]);
+    unsigned int o0 = d.cell_off[c];
+    int npcj = (int)(d.cell_off[c + 1] - o0);
+    int k1, k2;
+    uint4 rec;
+    rec.w = pick_pair(d, c, j, npcj, k1, k2);
+    rec.x = o0 + (unsigned int)k1;
+    rec.y = o0 + (unsigned int)k2;
+    rec.z = b;
+    cand[g] = rec;
+    atomicMin(&owner[rec.x], (unsigned int)g);
+    atomicMin(&owner[rec.y], (unsigned int)g);
+}
+
+__global__ void __launch_bounds__(256) cand_mark_kernel(long long ncand, const uint4* __restrict__ cand,
+                                                        unsigned int* __restrict__ owner) {
+    long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= ncand) return;
+    uint4 rec = cand[g];
+    if (rec.z & CAND_DONE) return;
+    atomicMin(&owner[rec.x], (unsigned int)g);
+    atomicMin(&owner[rec.y], (unsigned int)g);
 }
 
 __global__ void __launch_bounds__(256) cand_process_kernel(const __grid_constant__ PgDev d, long long ncand,
                                                            uint4* __restrict__ cand, unsigned int* __restrict__ owner,
+                                                           const unsigned int* __restrict__ big_list,
                                                            const unsigned int* __restrict__ cand_off,
-                                                           const double* __restrict__ cell_vrmax,
-                                                           const double* __restrict__ cell_fcorr) {
+                                                           const double* __restrict__ big_vrmax,
+                                                           const double* __restrict__ big_fcorr) {
     long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= ncand) return;
     uint4 rec = cand[g];
@@ -292,32 +695,61 @@ __global__ void __launch_bounds__(256) cand_process_kernel(const __grid_constant
         atomicAdd(&d.status->pending, 1ULL);
         return;
     }
-    unsigned int c = rec.z;
+    const unsigned int b = rec.z, c = big_list[b];
     PgRng rng;
-    rng.init(d.seed_local, 2, d.tID, (unsigned long long)c, (unsigned long long)(g - cand_off[c]));
+    rng.init(d.seed_local, 2, d.tID, (unsigned long long)c, (unsigned long long)(g - cand_off[b]));
     rng.seek(rec.w); /* the pick consumed rec.w draws of this candidate's stream */
-    int accepted = 0, reacted = 0;
-    collide_pair(d, rng, rec.x, rec.y, (int)c, cell_vrmax[c], cell_fcorr[c], accepted, reacted);
-    if (accepted) atomicAdd(&d.status->ncoll, 1ULL);
-    if (reacted) atomicAdd(&d.status->nreac, 1ULL);
+    PairIO p;
+    const PgVel V1 = d.p.vel[rec.x], V2 = d.p.vel[rec.y];
+    p.c1[0] = V1.vx; p.c1[1] = V1.vy; p.c1[2] = V1.vz; p.s1 = V1.sid;
+    p.c2[0] = V2.vx; p.c2[1] = V2.vy; p.c2[2] = V2.vz; p.s2 = V2.sid;
+    if (d.use_ie) {
+        const PgIe E1 = d.p.ie[rec.x], E2 = d.p.ie[rec.y];
+        p.erot1 = E1.erot; p.evib1 = E1.evib; p.erot2 = E2.erot; p.evib2 = E2.evib;
+    } else {
+        p.erot1 = p.evib1 = p.erot2 = p.evib2 = 0.;
+    }
+    const int fl = collide_pair_core(d, rng, p, (long long)rec.y, (int)c, big_vrmax[b], big_fcorr[b]);
+    if (fl & PR_ACCEPTED) atomicAdd(&d.status->ncoll, 1ULL);
+    if (fl & PR_REACTED) atomicAdd(&d.status->nreac, 1ULL);
+    if (fl & (PR_V | PR_S)) {
+        PgVel W1, W2;
+        W1.vx = p.c1[0]; W1.vy = p.c1[1]; W1.vz = p.c1[2]; W1.sid = p.s1; W1.pad = 0;
+        W2.vx = p.c2[0]; W2.vy = p.c2[1]; W2.vz = p.c2[2]; W2.sid = p.s2; W2.pad = 0;
+        d.p.vel[rec.x] = W1;
+        d.p.vel[rec.y] = W2;
+    }
+    if (d.use_ie) {
+        if (fl & PR_E1) { PgIe E; E.erot = p.erot1; E.evib = p.evib1; d.p.ie[rec.x] = E; }
+        if (fl & PR_E2) { PgIe E; E.erot = p.erot2; E.evib = p.evib2; d.p.ie[rec.y] = E; }
+    }
+    if (fl & PR_S) {
+        d.p.pos[rec.x].sid = p.s1;
+        d.p.pos[rec.y].sid = p.s2;
+    }
     cand[g].z = rec.z | CAND_DONE;
     owner[rec.x] = OWNER_FREE;
     owner[rec.y] = OWNER_FREE;
 }
 
+size_t tile_smem_bytes(bool ie) {
+    size_t b = (sizeof(TileSmem) + 31) & ~(size_t)31;
+    b += ie ? sizeof(PgIe) * PG_TILE_CAP : sizeof(CandPre) * (PG_TILE_CAP / 2);
+    return b;
+}
+
 } /* namespace */
 
-static int ensure_collide_scratch(pgpu_ctx* c) {
-    int ncells = pg_ncells(c);
-    if (ncells > c->cellscratch_alloc) {
+static int ensure_big_scratch(pgpu_ctx* c) {
+    long long nb = c->big_alloc + 1;
+    if (nb > c->cellscratch_alloc) {
         cudaFree(c->d_cell_ncoll); cudaFree(c->d_cand_off); cudaFree(c->d_cell_vrmax); cudaFree(c->d_cell_fcorr);
         c->d_cell_ncoll = nullptr; c->d_cand_off = nullptr; c->d_cell_vrmax = nullptr; c->d_cell_fcorr = nullptr;
-        PG_CUDA(c, cudaMalloc((void**)&c->d_cell_ncoll, sizeof(int) * ((size_t)ncells + 1)));
-        PG_CUDA(c, cudaMalloc((void**)&c->d_cand_off, sizeof(unsigned int) * ((size_t)ncells + 1)));
-        PG_CUDA(c, cudaMalloc((void**)&c->d_cell_vrmax, sizeof(double) * (size_t)ncells));
-        PG_CUDA(c, cudaMalloc((void**)&c->d_cell_fcorr, sizeof(double) * (size_t)ncells));
-        PG_CUDA(c, cudaMemset(c->d_cell_ncoll, 0, sizeof(int) * ((size_t)ncells + 1)));
-        c->cellscratch_alloc = ncells;
+        PG_CUDA(c, cudaMalloc((void**)&c->d_cell_ncoll, sizeof(int) * (size_t)nb));
+        PG_CUDA(c, cudaMalloc((void**)&c->d_cand_off, sizeof(unsigned int) * (size_t)nb));
+        PG_CUDA(c, cudaMalloc((void**)&c->d_cell_vrmax, sizeof(double) * (size_t)nb));
+        PG_CUDA(c, cudaMalloc((void**)&c->d_cell_fcorr, sizeof(double) * (size_t)nb));
+        c->cellscratch_alloc = (int)nb;
     }
     if (c->capacity > c->owner_capacity) {
         cudaFree(c->d_owner);
@@ -329,27 +761,27 @@ static int ensure_collide_scratch(pgpu_ctx* c) {
     return PGPU_OK;
 }
 
-/* DSMC_COLLISIONS on the sorted store; leaves TIMESTEP_COLL/REAC in the status block */
-int pg_collide_impl(pgpu_ctx* c, int tID) {
+/* the GLOBAL path over big_list; synchronises with the host once per dependency round */
+static int collide_big_cells(pgpu_ctx* c) {
     int rc;
-    if (!c->sorted) PG_FAIL(c, PGPU_ERR_STATE, "collide: store is not sorted");
-    if (c->np < 2) return PGPU_OK;
-    if ((rc = ensure_collide_scratch(c))) return rc;
-    c->dev.tID = tID;
-    pg_refresh_dev(c);
+    if ((rc = ensure_big_scratch(c))) return rc;
     const PgDev& d = c->dev;
-    int ncells = d.ncells;
-    const int G = 8;
-    unsigned int blocks = (unsigned int)(((long long)ncells * G + 255) / 256);
-    cell_prep_kernel<<<blocks, 256, 0, c->stream>>>(d, c->d_cell_ncoll, c->d_cell_vrmax, c->d_cell_fcorr);
-    c->launches++;
-    /* candidate offsets; the scan workspace sized for ncells+1 unsigned ints is reused */
-    size_t tmp = c->scan_tmp_bytes;
+    const unsigned int nbig = c->n_big;
+    big_init_kernel<<<(nbig * 6 + 255) / 256, 256, 0, c->stream>>>(c->d_big_bbox, nbig);
+    big_bbox_kernel<<<dim3(nbig, 32), 256, 0, c->stream>>>(d, c->d_big_list, c->d_big_bbox);
+    big_prep_kernel<<<(nbig + 1 + 255) / 256, 256, 0, c->stream>>>(d, c->d_big_list, nbig, c->d_big_bbox, c->d_cell_ncoll,
+                                                                 c->d_cell_vrmax, c->d_cell_fcorr);
+    c->launches += 3;
+    /* candidate offsets */
+    size_t tmp = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp, (const unsigned int*)c->d_cell_ncoll, c->d_cand_off, (int)nbig + 1, c->stream);
+    if (tmp > c->scan_tmp_bytes) PG_FAIL(c, PGPU_ERR_STATE, "collide: scan workspace too small");
+    tmp = c->scan_tmp_bytes;
     PG_CUDA(c, cub::DeviceScan::ExclusiveSum(c->d_scan_tmp, tmp, (const unsigned int*)c->d_cell_ncoll, c->d_cand_off,
-                                             ncells + 1, c->stream));
+                                             (int)nbig + 1, c->stream));
     c->launches++;
-    unsigned int* h_total = reinterpret_cast<unsigned int*>(&c->h_status->pad);
-    PG_CUDA(c, cudaMemcpyAsync(h_total, c->d_cand_off + ncells, sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
+    unsigned int* h_total = &c->h_status->scratch[2];
+    PG_CUDA(c, cudaMemcpyAsync(h_total, c->d_cand_off + nbig, sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
     PG_CUDA(c, cudaStreamSynchronize(c->stream));
     long long ncand = (long long)*h_total;
     if (ncand == 0) return PGPU_OK;
@@ -366,34 +798,58 @@ int pg_collide_impl(pgpu_ctx* c, int tID) {
         c->cand_capacity = cap;
     }
     uint4* cand = (uint4*)c->d_cand;
-    unsigned int* cand_cell = (unsigned int*)(cand + c->cand_capacity);
-    void* scan_ws = (void*)(cand_cell + c->cand_capacity);
+    unsigned int* cand_big = (unsigned int*)(cand + c->cand_capacity);
+    void* scan_ws = (void*)(cand_big + c->cand_capacity);
     size_t scan_bytes = 0;
-    cub::DeviceScan::InclusiveScan(nullptr, scan_bytes, cand_cell, cand_cell, MaxOp(), (int)ncand, c->stream);
+    cub::DeviceScan::InclusiveScan(nullptr, scan_bytes, cand_big, cand_big, MaxOp(), (int)ncand, c->stream);
     scan_ws = (void*)(((uintptr_t)scan_ws + 255) & ~(uintptr_t)255);
 
-    PG_CUDA(c, cudaMemsetAsync(cand_cell, 0, sizeof(unsigned int) * (size_t)ncand, c->stream));
-    cand_head_kernel<<<(unsigned int)((ncells + 255) / 256), 256, 0, c->stream>>>(ncells, c->d_cell_ncoll, c->d_cand_off, cand_cell);
-    PG_CUDA(c, cub::DeviceScan::InclusiveScan(scan_ws, scan_bytes, cand_cell, cand_cell, MaxOp(), (int)ncand, c->stream));
+    PG_CUDA(c, cudaMemsetAsync(cand_big, 0, sizeof(unsigned int) * (size_t)ncand, c->stream));
+    cand_head_kernel<<<(nbig + 255) / 256, 256, 0, c->stream>>>(nbig, c->d_cell_ncoll, c->d_cand_off, cand_big);
+    PG_CUDA(c, cub::DeviceScan::InclusiveScan(scan_ws, scan_bytes, cand_big, cand_big, MaxOp(), (int)ncand, c->stream));
     unsigned int cblocks = (unsigned int)((ncand + 255) / 256);
-    cand_pick_kernel<<<cblocks, 256, 0, c->stream>>>(d, ncand, cand_cell, c->d_cand_off, cand, c->d_owner);
+    cand_pick_kernel<<<cblocks, 256, 0, c->stream>>>(d, ncand, c->d_big_list, cand_big, c->d_cand_off, cand, c->d_owner);
     c->launches += 3;
 
     /* dependency rounds */
     for (int round = 0;; round++) {
         PG_CUDA(c, cudaMemsetAsync(&c->d_status->pending, 0, sizeof(unsigned long long), c->stream));
-        cand_process_kernel<<<cblocks, 256, 0, c->stream>>>(d, ncand, cand, c->d_owner, c->d_cand_off, c->d_cell_vrmax,
-                                                           c->d_cell_fcorr);
+        cand_process_kernel<<<cblocks, 256, 0, c->stream>>>(d, ncand, cand, c->d_owner, c->d_big_list, c->d_cand_off,
+                                                           c->d_cell_vrmax, c->d_cell_fcorr);
         c->launches++;
         PG_CUDA(c, cudaMemcpyAsync(&c->h_status->pending, &c->d_status->pending, sizeof(unsigned long long),
                                    cudaMemcpyDeviceToHost, c->stream));
         PG_CUDA(c, cudaStreamSynchronize(c->stream));
         PG_CUDA(c, cudaGetLastError());
         if (c->h_status->pending == 0) break;
-        if (round > 100000) PG_FAIL(c, PGPU_ERR_STATE, "collide: dependency rounds do not converge");
+        if (round > 10000000) PG_FAIL(c, PGPU_ERR_STATE, "collide: dependency rounds do not converge");
         cand_mark_kernel<<<cblocks, 256, 0, c->stream>>>(ncand, cand, c->d_owner);
         c->launches++;
     }
+    return PGPU_OK;
+}
+
+/* DSMC_COLLISIONS on the sorted store; leaves TIMESTEP_COLL/REAC in the status block */
+int pg_collide_impl(pgpu_ctx* c, int tID) {
+    int rc;
+    if (!c->sorted) PG_FAIL(c, PGPU_ERR_STATE, "collide: store is not sorted");
+    if (c->np < 2) return PGPU_OK;
+    c->dev.tID = tID;
+    pg_refresh_dev(c);
+    const PgDev& d = c->dev;
+
+    if (d.ntiles > 0) {
+        /* per device, cheap: opt in to more than 48 KB of dynamic shared memory */
+        PG_CUDA(c, cudaFuncSetAttribute(tile_collide_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem_bytes(false)));
+        PG_CUDA(c, cudaFuncSetAttribute(tile_collide_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem_bytes(true)));
+        PG_CUDA(c, cudaFuncSetAttribute(tile_collide_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        PG_CUDA(c, cudaFuncSetAttribute(tile_collide_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        if (d.use_ie) tile_collide_kernel<true><<<d.ntiles, PG_TILE_THREADS, tile_smem_bytes(true), c->stream>>>(d);
+        else tile_collide_kernel<false><<<d.ntiles, PG_TILE_THREADS, tile_smem_bytes(false), c->stream>>>(d);
+        c->launches++;
+        PG_CUDA(c, cudaGetLastError());
+    }
+    if (c->n_big > 0 && (rc = collide_big_cells(c))) return rc;
     c->hist_valid = false;
     return PGPU_OK;
 }

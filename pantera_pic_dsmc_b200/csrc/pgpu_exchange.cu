@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(256) xcount_kernel(const __grid_constant__ PgD
     __syncthreads();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < d.np) {
-        int ic = d.p.ic[i];
+        int ic = d.p.pos[i].ic;
         if (ic >= 1) {
             int dest = __ldg(&d.cell_procs[ic - 1]);
             if (dest != d.rank) atomicAdd(&s[dest], 1u);
@@ -99,21 +99,24 @@ __global__ void __launch_bounds__(256) xpack_kernel(const __grid_constant__ PgDe
                                                     unsigned long long* __restrict__ xcursor) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= d.np) return;
-    int ic = d.p.ic[i];
+    const PgPos P = d.p.pos[i];
+    int ic = P.ic;
     if (ic < 1) return;
     int dest = __ldg(&d.cell_procs[ic - 1]);
     if (dest == d.rank) return;
     unsigned long long k = xoff[dest] + atomicAdd(&xcursor[dest], 1ULL);
     double* r = sendbuf + k * XREC_DOUBLES;
-    r[0] = d.p.x[i]; r[1] = d.p.y[i]; r[2] = d.p.z[i];
-    r[3] = d.p.vx[i]; r[4] = d.p.vy[i]; r[5] = d.p.vz[i];
-    r[6] = d.p.erot[i]; r[7] = d.p.evib[i];
+    const PgVel V = d.p.vel[i];
+    const PgIe E = d.p.ie[i];
+    r[0] = P.x; r[1] = P.y; r[2] = P.z;
+    r[3] = V.vx; r[4] = V.vy; r[5] = V.vz;
+    r[6] = E.erot; r[7] = E.evib;
     r[8] = d.p.dtrim ? d.p.dtrim[i] : d.dt;
-    int2 cs = make_int2(ic, d.p.sid[i]);
+    int2 cs = make_int2(ic, P.sid);
     r[9] = *reinterpret_cast<double*>(&cs);
     long long id = d.p.id ? d.p.id[i] : 0;
     r[10] = *reinterpret_cast<double*>(&id);
-    d.p.ic[i] = PG_TOMBSTONE;
+    d.p.pos[i].ic = PG_TOMBSTONE;
 }
 
 /* append the received records (ADD_PARTICLE_ARRAY loop, ref: grid_and_partition.f90:610-612) */
@@ -123,16 +126,21 @@ __global__ void __launch_bounds__(256) xunpack_kernel(const __grid_constant__ Pg
     if (i >= n) return;
     const double* r = recvbuf + i * XREC_DOUBLES;
     long long o = base + i;
-    p.x[o] = r[0]; p.y[o] = r[1]; p.z[o] = r[2];
-    p.vx[o] = r[3]; p.vy[o] = r[4]; p.vz[o] = r[5];
-    p.erot[o] = r[6]; p.evib[o] = r[7];
-    double dtrim = r[8];
-    p.dtrim[o] = dtrim;
-    if (dtrim != d.dt) d.status->pad = 1;
     double t = r[9];
     int2 cs = *reinterpret_cast<int2*>(&t);
-    p.ic[o] = cs.x;
-    p.sid[o] = cs.y;
+    PgPos P;
+    P.x = r[0]; P.y = r[1]; P.z = r[2]; P.ic = cs.x; P.sid = cs.y;
+    PgVel V;
+    V.vx = r[3]; V.vy = r[4]; V.vz = r[5]; V.sid = cs.y; V.pad = 0;
+    PgIe E;
+    E.erot = r[6]; E.evib = r[7];
+    p.pos[o] = P;
+    p.vel[o] = V;
+    p.ie[o] = E;
+    if (E.erot != 0. || E.evib != 0.) d.status->flag_ie = 1;
+    double dtrim = r[8];
+    p.dtrim[o] = dtrim;
+    if (dtrim != d.dt) d.status->flag_dtrim = 1;
     t = r[10];
     if (p.id) p.id[o] = *reinterpret_cast<long long*>(&t);
 }
@@ -242,9 +250,10 @@ int pg_exchange_impl(pgpu_ctx* c) {
         PgPlanes p = c->planes[c->cur];
         xunpack_kernel<<<(unsigned int)((nrecv + 255) / 256), 256, 0, c->stream>>>(c->dev, (const double*)c->d_recvbuf, nrecv, p, c->np);
         c->launches++;
-        PG_CUDA(c, cudaMemcpyAsync(&c->h_status->pad, &c->d_status->pad, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        PG_CUDA(c, cudaMemcpyAsync(&c->h_status->flag_dtrim, &c->d_status->flag_dtrim, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         PG_CUDA(c, cudaStreamSynchronize(c->stream));
-        if (c->h_status->pad && !c->has_dtrim) {
+        if (c->h_status->flag_ie) c->ie_seen = true;
+        if (c->h_status->flag_dtrim && !c->has_dtrim) {
             if (c->np > 0) fill_kernel<<<(unsigned int)((c->np + 255) / 256), 256, 0, c->stream>>>(p.dtrim, c->np, c->cfg.dt);
             c->has_dtrim = true;
         }

@@ -2,9 +2,16 @@
  * pgpu_internal.cuh -- shared declarations of libpantera_gpu.so (CUDA, sm_100a).
  *
  * Layout of the device particle store (DESIGN.md "Data layout in HBM"):
- *   structure of arrays, one FP64 plane per attribute  X Y Z VX VY VZ EROT EVIB  (64 B/particle),
- *   INT32 planes IC and S_ID (8 B/particle) -> 72 B/particle of streamed state, two copies
- *   (ping-pong) so that the per-step counting sort is a single scatter pass.
+ *   structure of arrays of 32-byte VECTOR records, one HBM sector each, moved with single 256-bit
+ *   loads/stores (LDG.E.ENL2.256 / STG.E.ENL2.256 on sm_100a):
+ *     pos[i] = { X, Y, Z, (IC, S_ID) }      32 B   read+written by ADVECT, read by DEPOSIT
+ *     vel[i] = { VX, VY, VZ, (S_ID, -) }    32 B   read by ADVECT, read+written by the collisions
+ *     ie[i]  = { EROT, EVIB }               16 B   touched only while some particle can hold internal energy
+ *   = 72 B/particle of physics state (the 8 pad bytes of vel replace nothing: S_ID is mirrored there so that
+ *   the collision kernels never touch pos).  Why records and not nine scalar planes: the per-step counting
+ *   sort moves every particle to a data-dependent slot, and a random 8-byte access costs a whole 32-byte
+ *   sector in L2 and HBM; with sector-sized records the reorder moves exactly the bytes it needs.
+ *   Two copies (ping-pong) so that the sort is a single pass.
  *   Optional planes: DTRIM (only while some particle has DTRIM != DT, i.e. right after a host-side
  *   injection, src/timecycle.f90:463) and ID (cfg.track_id).
  *   A removed particle is a tombstone IC = -1 until the next sort compacts it away.
@@ -29,6 +36,15 @@
 #define PG_QE 1.602176634e-19
 
 #define PG_TOMBSTONE (-1)
+/* collision tiles (pgpu_collide.cu): a tile owns the cells whose first sorted slot lies in a window of
+ * PG_TILE_S slots; cells with more than PG_TILE_BIG particles take the global dependency-round path */
+#define PG_TILE_S 512
+#define PG_TILE_BIG 256
+#define PG_TILE_CAP 768   /* >= PG_TILE_S - 1 + PG_TILE_BIG */
+#define PG_TILE_MAXC 384  /* cells of >= 2 particles that fit PG_TILE_CAP slots */
+#define PG_TILE_THREADS 256
+/* particles one warp of the LEAN advect pass works through (lanes refill as their particle finishes) */
+#define PG_ADVECT_CHUNK 256
 #define PG_MAX_HOPS 1000000 /* guard against a malformed mesh hanging the GPU */
 
 /* status block, device resident, read back at the end of every hot-path call */
@@ -40,14 +56,23 @@ struct PgStatus {
     unsigned long long nreac;       /* TIMESTEP_REAC                                     */
     unsigned long long pending;     /* collision candidates still waiting                */
     unsigned long long n_emigrants; /* particles leaving this rank                       */
+    unsigned long long x_overflow;  /* emigrants that did not fit the fused send segments */
     int err;                        /* first device-side error code (0 = none)           */
-    int pad;
+    int flag_dtrim;                 /* some uploaded/received particle has DTRIM != DT   */
+    int flag_ie;                    /* some uploaded/received particle has EROT/EVIB != 0 */
+    unsigned int n_big;             /* cells with more particles than a collision tile holds */
+    unsigned int scratch[4];        /* host landing zone of small read-backs (pinned copy only) */
 };
 enum { PG_DEVERR_NONE = 0, PG_DEVERR_HOPS = 1, PG_DEVERR_CELL_RANGE = 2, PG_DEVERR_CAPACITY = 3 };
 
+struct __align__(32) PgPos { double x, y, z; int ic, sid; };
+struct __align__(32) PgVel { double vx, vy, vz; int sid, pad; };
+struct __align__(16) PgIe { double erot, evib; };
+
 struct PgPlanes {
-    double *x, *y, *z, *vx, *vy, *vz, *erot, *evib;
-    int32_t *ic, *sid;
+    PgPos* pos;
+    PgVel* vel;
+    PgIe* ie;
     double* dtrim; /* may be null */
     int64_t* id;   /* may be null */
 };
@@ -94,7 +119,8 @@ struct PgDev {
     const double* mcc_frac;
     /* --- unstructured mesh, device layout --- */
     int nn, nc, nf;
-    const double* face_geo;  /* [nc][nf][6]: outward normal (3), a point on the face (3) */
+    const double* face_geo;  /* [nc][nf*6+2]: per face outward normal (3) + a point on the face (3), then the
+                                nf hop codes of face_code as int32 (16 bytes) */
     const int* face_code;    /* [nc][nf]: >0 neighbour cell to hop into; 0 boundary without a physical
                                 group (remove); <0 boundary with physical group -code        */
     const double *face_tang1, *face_tang2; /* [nc][4][3] (3-D) */
@@ -136,6 +162,13 @@ struct PgDev {
     unsigned int* cell_off;   /* [ncells+1] exclusive prefix of cell_count (valid while sorted) */
     unsigned int* hitlist;    /* slots deferred to the boundary-interaction pass */
     long long id_base;        /* ID counter for particles created on the device */
+    int use_ie;               /* 1: the ie plane is live (some particle can hold internal energy) */
+    const unsigned int* tile_first; /* [ntiles+1] first cell of every collision tile (valid while sorted) */
+    int ntiles;
+    /* fused emigrant packing in the ADVECT epilogue (multi-GPU run_steps) */
+    double* xseg;                   /* [nranks][xseg_cap][11] send segments, or null */
+    unsigned long long* xseg_count; /* [nranks] */
+    long long xseg_cap;
 };
 
 /* ------------------------------------------------------------------------------------------
@@ -172,6 +205,13 @@ struct pgpu_ctx {
     int cur;
     long long np, capacity;
     bool has_dtrim, sorted, hist_valid, maybe_tombstones;
+    bool any_internal_dof, ie_seen; /* species with ROTDOF/VIBDOF != 0; nonzero EROT/EVIB seen in an upload */
+    unsigned int* d_tile_first;
+    long long tile_alloc;
+    unsigned int n_big;             /* cells beyond PG_TILE_BIG particles in the current sorted store */
+    unsigned int* d_big_list;       /* [n_big] their cell ids */
+    unsigned long long* d_big_bbox; /* [n_big][6] order-encoded velocity bounds */
+    long long big_alloc;
     long long id_counter;
     unsigned int *d_cell_count, *d_rank, *d_cell_off, *d_hitlist;
     long long hit_capacity;

@@ -53,11 +53,15 @@ static __device__ long long pg_append_particle(const PgDev& d, double x, double 
         pg_set_err(d, PG_DEVERR_CAPACITY);
         return -1;
     }
-    d.p.x[o] = x; d.p.y[o] = y; d.p.z[o] = z;
-    d.p.vx[o] = vx; d.p.vy[o] = vy; d.p.vz[o] = vz;
-    d.p.erot[o] = erot; d.p.evib[o] = evib;
-    d.p.sid[o] = sid;
-    d.p.ic[o] = ic;
+    PgPos P;
+    P.x = x; P.y = y; P.z = z; P.ic = ic; P.sid = sid;
+    PgVel V;
+    V.vx = vx; V.vy = vy; V.vz = vz; V.sid = sid; V.pad = 0;
+    PgIe E;
+    E.erot = erot; E.evib = evib;
+    d.p.pos[o] = P;
+    d.p.vel[o] = V;
+    d.p.ie[o] = E;
     if (d.p.dtrim) d.p.dtrim[o] = d.dt;
     if (d.p.id) d.p.id[o] = (long long)d.rank + ((d.id_base + (long long)k) << 8);
     return o;
@@ -68,7 +72,7 @@ static __device__ long long pg_append_particle(const PgDev& d, double x, double 
  * and MCC_COLLISIONS_VAHEDI (:1749-1879).  e1/e2 = (erot, evib) of the two reactant slots, written back
  * by the caller.  Returns 0, or -1 if a product could not be appended.
  */
-static __device__ int pg_react_redistribute(const PgDev& d, PgRng& g, const PgReaction& r, double ecoll, double* c1,
+static __device__ __noinline__ int pg_react_redistribute(const PgDev& d, PgRng& g, const PgReaction& r, double ecoll, double* c1,
                                      double* c2, double& erot1, double& evib1, double& erot2, double& evib2,
                                      double x2, double y2, double z2, int ic2) {
     int p1 = r.p1, p2 = r.p2, p3 = r.p3, p4 = r.p4;

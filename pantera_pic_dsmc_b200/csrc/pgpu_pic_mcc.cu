@@ -31,12 +31,13 @@ __global__ void __launch_bounds__(256) deposit_kernel(const __grid_constant__ Pg
     double* acc = SMEM ? srhs : rhs;
     const double K = PG_QE / (PG_EPS0 * (d.eps_scaling * d.eps_scaling));
     for (long long jp = (long long)blockIdx.x * blockDim.x + threadIdx.x; jp < d.np; jp += (long long)gridDim.x * blockDim.x) {
-        int ic = d.p.ic[jp];
+        const PgPos P = d.p.pos[jp];
+        int ic = P.ic;
         if (ic < 1) continue;
-        int sid = d.p.sid[jp];
+        int sid = P.sid;
         double charge = __ldg(&d.charge[sid - 1]);
         if (fabs(charge) < 1.e-6) continue;
-        double x = d.p.x[jp];
+        double x = P.x;
         if (d.grid_type == PGPU_UNSTRUCTURED) {
             size_t c = (size_t)(ic - 1);
             if (d.dims == 1) {
@@ -48,7 +49,7 @@ __global__ void __launch_bounds__(256) deposit_kernel(const __grid_constant__ Pg
                     atomicAdd(&acc[vp], rho_q * psip);
                 }
             } else if (d.dims == 2) {
-                double y = d.p.y[jp];
+                double y = P.y;
                 double rho_q = K * charge * d.fnum / (d.zmax - d.zmin);
                 for (int p = 0; p < 3; p++) {
                     int vp = __ldg(&d.cell_nodes[3 * c + p]) - 1;
@@ -57,7 +58,7 @@ __global__ void __launch_bounds__(256) deposit_kernel(const __grid_constant__ Pg
                     atomicAdd(&acc[vp], rho_q * psip);
                 }
             } else {
-                double y = d.p.y[jp], z = d.p.z[jp];
+                double y = P.y, z = P.z;
                 double rho_q = K * charge * d.fnum;
                 for (int p = 0; p < 4; p++) {
                     int vp = __ldg(&d.cell_nodes[4 * c + p]) - 1;
@@ -68,7 +69,7 @@ __global__ void __launch_bounds__(256) deposit_kernel(const __grid_constant__ Pg
             }
         } else {
             /* ref: src/fields.f90:5341-5431 COMPUTE_WEIGHTS + :5494-5520 */
-            double y = d.p.y[jp];
+            double y = P.y;
             int nx = d.nx;
             int i = (ic - 1) % nx, j = (ic - 1) / nx;
             double hx, hy, cxmin, cymin;
@@ -117,15 +118,17 @@ __global__ void add_surface_charge_kernel(double* __restrict__ rhs, const double
 __global__ void __launch_bounds__(128) mcc_vahedi_kernel(const __grid_constant__ PgDev d, double p_null) {
     long long jp1 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (jp1 >= d.np) return;
-    int ic = d.p.ic[jp1];
+    const PgPos P1 = d.p.pos[jp1];
+    int ic = P1.ic;
     if (ic < 1) return;
     PgRng g;
     g.init(d.seed_local, 3, d.tID, (unsigned long long)jp1, 0ULL);
     if (g.rf() > p_null) return;
     atomicAdd(&d.status->ncoll, 1ULL);
     const double dt = d.dt;
-    int s1 = d.p.sid[jp1];
-    double c1[3] = {d.p.vx[jp1], d.p.vy[jp1], d.p.vz[jp1]};
+    int s1 = P1.sid;
+    const PgVel V1 = d.p.vel[jp1];
+    double c1[3] = {V1.vx, V1.vy, V1.vz};
     for (int j = 0; j < d.mcc_ncomp; j++) {
         int s2 = d.mcc_sp[j];
         double bg_nrho = d.mcc_frac[j] * d.mcc_dens;
@@ -151,20 +154,25 @@ __global__ void __launch_bounds__(128) mcc_vahedi_kernel(const __grid_constant__
                 /* materialise the background partner at the particle's position (ref: :1726-1741) */
                 double erot2 = pg_internal_energy(g, d.rotdof[s2 - 1], d.mcc_ttra);
                 double evib2 = pg_internal_energy(g, d.vibdof[s2 - 1], d.mcc_ttra);
-                double x = d.p.x[jp1], y = d.p.y[jp1], z = d.p.z[jp1];
+                double x = P1.x, y = P1.y, z = P1.z;
                 atomicAdd(&d.status->nreac, 1ULL);
                 double ecoll = etr - ea;
-                double erot1 = d.p.erot[jp1], evib1 = d.p.evib[jp1];
+                const PgIe E1 = d.p.ie[jp1];
+                double erot1 = E1.erot, evib1 = E1.evib;
                 int bad = 0;
                 if (!r.is_cex) {
                     /* products past the second are appended by the redistribution itself; the oracle
                      * appends the partner first, so creation order differs but not the set of particles */
                     bad = pg_react_redistribute(d, g, r, ecoll, c1, c2, erot1, evib1, erot2, evib2, x, y, z, ic);
-                    d.p.erot[jp1] = erot1; d.p.evib[jp1] = evib1;
-                    d.p.vx[jp1] = c1[0]; d.p.vy[jp1] = c1[1]; d.p.vz[jp1] = c1[2];
+                    PgIe E;
+                    E.erot = erot1; E.evib = evib1;
+                    d.p.ie[jp1] = E;
                 }
                 (void)bad;
-                d.p.sid[jp1] = r.p1;
+                PgVel W;
+                W.vx = c1[0]; W.vy = c1[1]; W.vz = c1[2]; W.sid = r.p1; W.pad = 0;
+                d.p.vel[jp1] = W;
+                d.p.pos[jp1].sid = r.p1;
                 pg_append_particle(d, x, y, z, c2[0], c2[1], c2[2], erot2, evib2, r.p2, ic);
                 return;
             }
@@ -175,9 +183,10 @@ __global__ void __launch_bounds__(128) mcc_vahedi_kernel(const __grid_constant__
 __global__ void __launch_bounds__(256) remove_species_kernel(const __grid_constant__ PgDev d, int sp) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= d.np) return;
-    if (d.p.ic[i] < 1) return;
-    if (d.p.sid[i] == sp) {
-        d.p.ic[i] = PG_TOMBSTONE;
+    const PgPos P = d.p.pos[i];
+    if (P.ic < 1) return;
+    if (P.sid == sp) {
+        d.p.pos[i].ic = PG_TOMBSTONE;
         atomicAdd(&d.status->n_removed, 1ULL);
     }
 }
