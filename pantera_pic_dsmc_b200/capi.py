@@ -20,7 +20,8 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 REPO_ROOT = os.path.dirname(_HERE)
-GPU_LIB_PATH = os.path.join(_HERE, "csrc", "libpantera_gpu.so")
+# PANTERA_GPU_LIB: developer override to A/B-test differently tuned builds of the SAME library (never a fallback)
+GPU_LIB_PATH = os.environ.get("PANTERA_GPU_LIB") or os.path.join(_HERE, "csrc", "libpantera_gpu.so")
 ORACLE_LIB_PATH = os.path.join(REPO_ROOT, "oracle", "_build", "liboracle.so")
 
 # ---- enumerations (values of the reference's ENUM, BIND(C) blocks; see pantera_gpu.h) ----------

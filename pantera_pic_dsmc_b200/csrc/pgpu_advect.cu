@@ -439,6 +439,8 @@ __device__ __forceinline__ int unstructured_iter(const PgDev& d, PgRng& g, PStat
         const double* geo = d.face_geo + (size_t)(ic - 1) * (NF * 6 + 2);
         /* hop codes of the cell's faces, fetched together with the geometry (no dependent load) */
         const int4 codes = __ldg(reinterpret_cast<const int4*>(geo + NF * 6));
+        /* (the code load above touches the tail of the record, so both of its cache lines are in flight
+         *  before the first face is evaluated) */
         int codesel = 0; /* hop code of the face selected so far (a predicated move per face, no branch) */
         double nsel[3] = {0., 0., 0.};
         if (AXI) {
@@ -802,9 +804,17 @@ __device__ __forceinline__ bool finish_particle(const PgDev& d, PState& q) {
     return true;
 }
 
-/* registers -> slot, plus the histogram and arrival rank of the counting sort (warp-aggregated: the lanes
- * of `peers` that land in the same cell share one atomic).  Every lane of `peers` must call this. */
-__device__ __forceinline__ void store_particle(const PgDev& d, long long slot, const PState& q, int dirty, unsigned int peers) {
+/* registers -> slot.  The histogram / arrival rank of the counting sort is warp-aggregated: the lanes of
+ * `peers` that land in the same cell share one atomic.  Every lane of `peers` must call this.  The rank is
+ * NOT written here: the atomic's round trip to L2 would stall the warp, so the caller keeps (base, mask) and
+ * commits the rank one loop trip later with commit_rank(). */
+struct PendingRank {
+    long long slot;
+    unsigned int base, mask;
+    int leader;
+};
+__device__ __forceinline__ void store_particle(const PgDev& d, long long slot, const PState& q, int dirty, unsigned int peers,
+                                               PendingRank& pr) {
     PgPos P;
     P.x = q.x; P.y = q.y; P.z = q.z; P.ic = q.ic; P.sid = q.sid;
     d.p.pos[slot] = P;
@@ -823,8 +833,13 @@ __device__ __forceinline__ void store_particle(const PgDev& d, long long slot, c
     int lane = threadIdx.x & 31;
     unsigned int base = 0;
     if (lane == leader) base = atomicAdd(&d.cell_count[q.ic - 1], (unsigned int)__popc(mask));
-    base = __shfl_sync(mask, base, leader);
-    d.cell_rank[slot] = base + __popc(mask & ((1u << lane) - 1u));
+    pr.slot = slot; pr.base = base; pr.mask = mask; pr.leader = leader;
+}
+/* all lanes of pr.mask call this together */
+__device__ __forceinline__ void commit_rank(const PgDev& d, const PendingRank& pr) {
+    int lane = threadIdx.x & 31;
+    unsigned int base = __shfl_sync(pr.mask, pr.base, pr.leader);
+    d.cell_rank[pr.slot] = base + __popc(pr.mask & ((1u << lane) - 1u));
 }
 
 __device__ __forceinline__ void tombstone_particle(const PgDev& d, long long slot) {
@@ -836,7 +851,7 @@ __device__ __forceinline__ void tombstone_particle(const PgDev& d, long long slo
  * LEAN pass.  One warp works through PG_ADVECT_CHUNK consecutive slots; see the file header.
  */
 template <int MODE, bool AXI>
-__global__ void __launch_bounds__(128) advect_lean_kernel(const __grid_constant__ PgDev d, long long n) {
+__global__ void __launch_bounds__(128, 8) advect_lean_kernel(const __grid_constant__ PgDev d, long long n) {
     const unsigned int FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -851,14 +866,22 @@ __global__ void __launch_bounds__(128) advect_lean_kernel(const __grid_constant_
     int bhits[4] = {0, 0, 0, 0};
     PgRng g; /* never drawn from in the LEAN pass */
     g.init(0ULL, 0, 0, 0ULL, 0ULL);
+    PendingRank pr;
+    pr.mask = 0u;
 
     for (;;) {
+        /* rank of the particle stored in the previous trip (its atomic has had a whole trip to return) */
+        if (pr.mask) { commit_rank(d, pr); pr.mask = 0u; }
         /* refill: idle lanes take the next slots of the chunk, in order */
         unsigned int idle = __ballot_sync(FULL, !have);
         if (idle && next < end) {
             long long my = next + __popc(idle & ((1u << lane) - 1u));
             if (!have && my < end) {
                 slot = my;
+                if (my + 64 < end) { /* the records this lane is likely to take two refills from now */
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(d.p.pos + my + 64));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(d.p.vel + my + 64));
+                }
                 have = load_particle(d, slot, q, dirty);
                 hops = 0;
                 if (MODE == 0) { bhits[0] = bhits[1] = bhits[2] = bhits[3] = 0; }
@@ -866,7 +889,7 @@ __global__ void __launch_bounds__(128) advect_lean_kernel(const __grid_constant_
             next += __popc(idle);
         }
         if (!__any_sync(FULL, have)) {
-            if (next >= end) break;
+            if (next >= end) break; /* (nothing pending: a trip that stored something refills or ends here first) */
             continue;
         }
 
@@ -901,7 +924,7 @@ __global__ void __launch_bounds__(128) advect_lean_kernel(const __grid_constant_
                 for (int b = 0; b < 4; b++)
                     if (bhits[b]) atomicAdd(&d.bcount[b + 4 * (q.sid - 1)], (unsigned long long)bhits[b]);
             }
-            store_particle(d, slot, q, dirty, fm);
+            store_particle(d, slot, q, dirty, fm, pr);
         }
     }
 }
@@ -928,7 +951,11 @@ __global__ void __launch_bounds__(128) advect_full_kernel(const __grid_constant_
         if (!keep) tombstone_particle(d, slot);
     }
     unsigned int fm = __ballot_sync(0xffffffffu, keep);
-    if (keep) store_particle(d, slot, q, dirty, fm);
+    if (keep) {
+        PendingRank pr;
+        store_particle(d, slot, q, dirty, fm, pr);
+        commit_rank(d, pr);
+    }
 }
 
 template <bool LEAN>

@@ -14,15 +14,18 @@
  *           sequential loop would do.  Evaluate, repeat until none waits.  Cells, and disjoint pairs inside
  *           a cell, proceed in parallel; chains of candidates sharing a particle serialise, as they must.
  *
- * Two executions of that scheme:
- *   TILE    (the hot path) one CTA owns the cells whose first sorted slot lies in a window of PG_TILE_S
- *           slots.  Their vel records are staged in shared memory once (one coalesced 32-byte load per
- *           particle), prep / pick / rounds run entirely in shared memory with CTA barriers between the
- *           claim and the evaluate half of a round, and the records are written back once: 32 B read +
- *           32 B written per particle, no global atomics, no host round trip.
- *   GLOBAL  cells with more than PG_TILE_BIG particles (e.g. the one-cell heat bath of config C1) do not
- *           fit a tile; their candidates go through the same rounds with claims in global memory and one
- *           kernel pair per round.
+ * Two executions:
+ *   CELL    (the hot path) one LANE per cell walks that cell's candidates in the reference's order, so the
+ *           sequential semantics hold by construction and there is no bookkeeping at all; a warp covers 32
+ *           cells (~1300 particles) and re-converges for the expensive deflection math.  Measured against a
+ *           shared-memory tile kernel running the dependency rounds below per CTA (r01 profiles), it executes
+ *           ~3x fewer instructions, which is what bounds this phase: it is FP64/Philox issue-bound, not
+ *           HBM-bound.  32 B read + at most 32 B written per particle, no atomics, no host round trip.
+ *   GLOBAL  cells with more than PG_TILE_BIG particles (e.g. the one-cell heat bath of config C1) would
+ *           serialise a lane; their candidates go through dependency rounds: every waiting candidate claims
+ *           both of its particles with its sequence number; a candidate that holds both claims is the
+ *           earliest one touching either particle, so evaluating it now is what the sequential loop would do.
+ *           Evaluate, repeat until none waits (claims in global memory, one kernel pair per round).
  * With the oracle run on the same Philox streams both agree with it value for value (tests/test_gpu_collide.py).
  */
 #include <cub/device/device_scan.cuh>
@@ -242,42 +245,26 @@ __device__ int collide_pair_core(const PgDev& d, PgRng& g, PairIO& p, long long 
 }
 
 /* ==========================================================================================
- * TILE path
+ * CELL path: one lane per cell
  * ======================================================================================== */
-/*
- * Everything about an accepted collision that depends only on the candidate's random stream and on the
- * species of the pair (fixed while nothing reacts): the acceptance draw, the VSS deflection angles and the
- * Borgnakke-Larsen selector.  Without internal energy and reactions (!IE) the draws of a candidate sit at
- * fixed positions of its stream (acceptance, BL selector, chi, theta, [isotropic redirection x2]), so this is
- * computed for ALL candidates of the tile in one dense pass BEFORE the dependency rounds: the pow / sincos /
- * Philox work leaves the serial chain, and what remains inside a round is ~60 FP64 operations per pair.
- */
-struct CandPre {
-    double r_acc, coschi, sinchi, costheta, sintheta;
-};
 
-struct TileSmem {
-    PgVel v[PG_TILE_CAP];
-    double vrmax[PG_TILE_MAXC], fcorr[PG_TILE_MAXC];
-    uint2 cand[PG_TILE_CAP / 2]; /* x: local slot of JP1 | JP2 << 16;  y: tile cell | draws used by the pick << 16
-                                    | inelastic redirection << 31 */
-    unsigned int own[PG_TILE_CAP];
-    unsigned int goff[PG_TILE_MAXC];     /* first global slot of the cell */
-    unsigned int coff[PG_TILE_MAXC + 1]; /* NCOLL, then its exclusive prefix */
-    int cell[PG_TILE_MAXC];              /* global cell, 0-based */
-    unsigned short base[PG_TILE_MAXC], n[PG_TILE_MAXC];
-    unsigned short pend[2][PG_TILE_CAP / 2]; /* candidates still waiting, this round / next round */
-    unsigned short acc[PG_TILE_CAP / 2];     /* candidates accepted in this round */
-    unsigned int ncl, nloc, ncand, npend[2], nacc_round[2], nacc, nreac;
-};
-
-/* the deflection of an accepted pair from precomputed angles; same expressions as pair_collide */
-__device__ __forceinline__ void pair_deflect_fast(const PgDev& d, PgRng& g, const CandPre& q, bool inelastic, double* c1,
-                                                  double* c2, int s1, int s2) {
+/* the deflection of an accepted pair without internal energy or reactions; same expressions as pair_collide.
+ * g continues the candidate's stream right after the acceptance draw. */
+__device__ __forceinline__ void pair_collide_fast(const PgDev& d, PgRng& g, double* c1, double* c2, int s1, int s2) {
     const double PI2 = 2. * PG_PI;
     double m1 = __ldg(&d.mass[s1 - 1]), m2 = __ldg(&d.mass[s2 - 1]);
+    /* ref: :454-490 with no internal modes: the selector only decides whether the post-collision relative
+     * velocity is redirected isotropically (:505-514; ROTREL/VIBREL != 0 on a species without modes) */
+    const double rbl = g.rf();
+    const double psum = __ldg(&d.rotrel[s1 - 1]) + __ldg(&d.rotrel[s2 - 1]) + __ldg(&d.vibrel[s1 - 1]) + __ldg(&d.vibrel[s2 - 1]);
+    /* ref: :495-499 */
+    const double alpha = VSS2(d.alphas, s1, s2);
+    double coschi = 2. * pow(g.rf(), 1. / alpha) - 1.;
+    double sinchi = sqrt(1. - coschi * coschi);
+    double theta = PI2 * g.rf();
+    double costheta = cos(theta), sintheta = sin(theta);
     double gx, gy, gz, gg;
-    if (inelastic) { /* ref: :505-514; only with ROTREL/VIBREL != 0 on a species without internal modes */
+    if (rbl < psum) {
         double vr2 = (c2[0] - c1[0]) * (c2[0] - c1[0]) + (c2[1] - c1[1]) * (c2[1] - c1[1]) + (c2[2] - c1[2]) * (c2[2] - c1[2]);
         double mred = m1 * m2 / (m1 + m2);
         double etr = 0.5 * mred * vr2;
@@ -296,7 +283,6 @@ __device__ __forceinline__ void pair_deflect_fast(const PgDev& d, PgRng& g, cons
         gz = c1[2] - c2[2];
         gg = sqrt(gx * gx + gy * gy + gz * gz);
     }
-    const double coschi = q.coschi, sinchi = q.sinchi, costheta = q.costheta, sintheta = q.sintheta;
     double grel[3], wc[3];
     double gyz = sqrt(gy * gy + gz * gz);
     grel[0] = gx * coschi + gyz * sintheta * sinchi;
@@ -309,266 +295,117 @@ __device__ __forceinline__ void pair_deflect_fast(const PgDev& d, PgRng& g, cons
     }
 }
 
+/*
+ * Every lane walks the candidates of ITS cell in the reference's order (so no dependency bookkeeping at all),
+ * directly on the sorted store: a cell's records are a contiguous 32-byte-aligned run that stays in L1/L2
+ * between the bounding-box sweep and the pair accesses.  The lanes of a warp are kept together where it pays:
+ * each lane first runs the cheap part (pair selection + acceptance test, most candidates are rejected) until it
+ * holds an ACCEPTED candidate, then the warp executes the expensive deflection (pow, sincos) for all of them at
+ * once.  Cells with more than PG_TILE_BIG particles are left to the GLOBAL path.
+ */
 template <bool IE>
-__global__ void __launch_bounds__(PG_TILE_THREADS, 3) tile_collide_kernel(const __grid_constant__ PgDev d) {
-    extern __shared__ __align__(32) unsigned char smem_raw[];
-    TileSmem& S = *reinterpret_cast<TileSmem*>(smem_raw);
-    /* behind the common part: the staged ie records (IE) or the precomputed candidate terms (!IE) */
-    unsigned char* extra = smem_raw + ((sizeof(TileSmem) + 31) & ~(size_t)31);
-    PgIe* se = reinterpret_cast<PgIe*>(extra);
-    CandPre* pre = reinterpret_cast<CandPre*>(extra);
-    constexpr int T = PG_TILE_THREADS;
+__global__ void __launch_bounds__(128, PG_CELL_MINBLOCKS) cell_collide_kernel(const __grid_constant__ PgDev d) {
     const unsigned int FULL = 0xffffffffu;
-    const int t = threadIdx.x, lane = t & 31;
-    const unsigned int c0 = d.tile_first[blockIdx.x], c1 = d.tile_first[blockIdx.x + 1];
-    if (c0 >= c1) return;
-    if (t == 0) { S.ncl = 0; S.nloc = 0; S.ncand = 0; S.npend[0] = 0; S.npend[1] = 0; S.nacc_round[0] = 0; S.nacc_round[1] = 0; S.nacc = 0; S.nreac = 0; }
-    __syncthreads();
-
-    /* A: cells of this tile that can collide (2..PG_TILE_BIG particles), packed into the staging area */
-    for (unsigned int c = c0 + t; c < c1; c += T) {
-        unsigned int o = d.cell_off[c];
-        unsigned int n = d.cell_off[c + 1] - o;
-        if (n >= 2 && n <= PG_TILE_BIG) {
-            unsigned int k = atomicAdd(&S.ncl, 1u);
-            unsigned int b = atomicAdd(&S.nloc, n);
-            S.cell[k] = (int)c;
-            S.goff[k] = o;
-            S.base[k] = (unsigned short)b;
-            S.n[k] = (unsigned short)n;
-        }
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned int o0 = 0;
+    int n = 0;
+    if (c < d.ncells) {
+        o0 = d.cell_off[c];
+        n = (int)(d.cell_off[c + 1] - o0);
     }
-    __syncthreads();
-    const int ncl = (int)S.ncl;
-    if (ncl == 0) return;
+    if (n < 2 || n > PG_TILE_BIG) n = 0; /* ref: src/collisions.f90:129; oversized cells: GLOBAL path */
 
-    /* B: stage the records, velocity bounding box, majorant -- eight lanes per cell */
+    /* velocity bounding box, ref: :202-222 */
+    double vxmax = -1.e+38, vxmin = 1.e+38, vymax = -1.e+38, vymin = 1.e+38, vzmax = -1.e+38, vzmin = 1.e+38;
     {
-        const int grp = t >> 3, gl = t & 7;
-        for (int k0 = 0; k0 < ncl; k0 += T / 8) { /* trip count uniform over the CTA: the shuffles below are full-warp */
-            const int k = k0 + grp;
-            const bool valid = k < ncl;
-            const int n = valid ? (int)S.n[k] : 0, b = valid ? (int)S.base[k] : 0;
-            const unsigned int o = valid ? S.goff[k] : 0u;
-            double vxmax = -1.e+38, vxmin = 1.e+38, vymax = -1.e+38, vymin = 1.e+38, vzmax = -1.e+38, vzmin = 1.e+38;
-            for (int i = gl; i < n; i += 8) {
-                const PgVel V = d.p.vel[o + i];
-                S.v[b + i] = V;
-                S.own[b + i] = 0u;
-                if (IE) se[b + i] = d.p.ie[o + i];
-                vxmin = fmin(vxmin, V.vx); vxmax = fmax(vxmax, V.vx);
-                vymin = fmin(vymin, V.vy); vymax = fmax(vymax, V.vy);
-                vzmin = fmin(vzmin, V.vz); vzmax = fmax(vzmax, V.vz);
-            }
-#pragma unroll
-            for (int s = 4; s > 0; s >>= 1) {
-                vxmin = fmin(vxmin, __shfl_xor_sync(FULL, vxmin, s, 8));
-                vxmax = fmax(vxmax, __shfl_xor_sync(FULL, vxmax, s, 8));
-                vymin = fmin(vymin, __shfl_xor_sync(FULL, vymin, s, 8));
-                vymax = fmax(vymax, __shfl_xor_sync(FULL, vymax, s, 8));
-                vzmin = fmin(vzmin, __shfl_xor_sync(FULL, vzmin, s, 8));
-                vzmax = fmax(vzmax, __shfl_xor_sync(FULL, vzmax, s, 8));
-            }
-            if (valid && gl == 0) {
-                double vrmax, fcorr;
-                int ncoll = cell_majorant(d, S.cell[k], n, vxmin, vxmax, vymin, vymax, vzmin, vzmax, vrmax, fcorr);
-                S.vrmax[k] = vrmax;
-                S.fcorr[k] = fcorr;
-                S.coff[k] = (unsigned int)ncoll;
-            }
+        const PgVel* __restrict__ vp = d.p.vel + o0;
+        int i = 0;
+        for (; i + 4 <= n; i += 4) {
+            const PgVel A = vp[i], B = vp[i + 1], C = vp[i + 2], D = vp[i + 3];
+            vxmin = fmin(fmin(vxmin, A.vx), fmin(B.vx, fmin(C.vx, D.vx)));
+            vxmax = fmax(fmax(vxmax, A.vx), fmax(B.vx, fmax(C.vx, D.vx)));
+            vymin = fmin(fmin(vymin, A.vy), fmin(B.vy, fmin(C.vy, D.vy)));
+            vymax = fmax(fmax(vymax, A.vy), fmax(B.vy, fmax(C.vy, D.vy)));
+            vzmin = fmin(fmin(vzmin, A.vz), fmin(B.vz, fmin(C.vz, D.vz)));
+            vzmax = fmax(fmax(vzmax, A.vz), fmax(B.vz, fmax(C.vz, D.vz)));
+        }
+        for (; i < n; i++) {
+            const PgVel A = vp[i];
+            vxmin = fmin(vxmin, A.vx); vxmax = fmax(vxmax, A.vx);
+            vymin = fmin(vymin, A.vy); vymax = fmax(vymax, A.vy);
+            vzmin = fmin(vzmin, A.vz); vzmax = fmax(vzmax, A.vz);
         }
     }
-    __syncthreads();
+    int ncoll = 0;
+    double vrmax = 0., fcorr = 0.;
+    if (n) ncoll = cell_majorant(d, (int)c, n, vxmin, vxmax, vymin, vymax, vzmin, vzmax, vrmax, fcorr);
 
-    /* C: candidate offsets (exclusive scan of NCOLL over the tile's cells, warp 0) */
-    if (t < 32) {
-        unsigned int run = 0;
-        for (int k0 = 0; k0 < ncl; k0 += 32) {
-            int k = k0 + lane;
-            unsigned int v = (k < ncl) ? S.coff[k] : 0u, x = v;
-#pragma unroll
-            for (int s = 1; s < 32; s <<= 1) {
-                unsigned int y = __shfl_up_sync(FULL, x, s);
-                if (lane >= s) x += y;
-            }
-            if (k < ncl) S.coff[k] = run + x - v;
-            run += __shfl_sync(FULL, x, 31);
-        }
-        if (lane == 0) { S.coff[ncl] = run; S.ncand = run; S.npend[0] = run; }
-    }
-    __syncthreads();
-    const int ncand = (int)S.ncand;
-
-    /* D: pair selection, the stream-only terms of the collision (!IE), and the claims of round 1.
-     * Claim word = round << 16 | (0xFFFF - candidate): a later round beats stale claims, inside a round the
-     * earliest candidate wins; nothing has to be reset. */
-    for (int g = t; g < ncand; g += T) {
-        int lo = 0, hi = ncl; /* last k with coff[k] <= g */
-        while (hi - lo > 1) {
-            int mid = (lo + hi) >> 1;
-            if (S.coff[mid] <= (unsigned int)g) lo = mid;
-            else hi = mid;
-        }
-        const int k = lo;
-        const unsigned int b = S.base[k];
+    int nacc = 0, nreac = 0;
+    int j = 0;
+    while (__any_sync(FULL, j < ncoll)) {
+        /* cheap part: this lane's candidates up to and including its next accepted one */
+        bool hit = false;
+        unsigned int j1 = 0, j2 = 0;
         PgRng rng;
-        rng.init(d.seed_local, 2, d.tID, (unsigned long long)(unsigned int)S.cell[k], (unsigned long long)(g - S.coff[k]));
-        /* ref: src/collisions.f90:263-271 */
-        const int npcj = (int)S.n[k];
-        int k1 = (int)(npcj * rng.rf());
-        if (k1 >= npcj) k1 = npcj - 1;
-        int k2 = k1;
-        while (k2 == k1) {
-            k2 = (int)(npcj * rng.rf());
-            if (k2 >= npcj) k2 = npcj - 1;
-        }
-        unsigned int meta = (unsigned int)k | (rng.ndraw << 16);
-        if (!IE) {
-            const double PI2 = 2. * PG_PI;
-            const int s1 = S.v[b + k1].sid, s2 = S.v[b + k2].sid;
-            CandPre q;
-            q.r_acc = rng.rf();
-            /* ref: :454-490 with no internal modes: the selector only decides whether the post-collision
-             * relative velocity is redirected isotropically (:505-514) */
-            const double rbl = rng.rf();
-            const double psum = __ldg(&d.rotrel[s1 - 1]) + __ldg(&d.rotrel[s2 - 1]) + __ldg(&d.vibrel[s1 - 1]) + __ldg(&d.vibrel[s2 - 1]);
-            if (rbl < psum) meta |= 0x80000000u;
-            /* ref: :495-499 */
-            const double alpha = VSS2(d.alphas, s1, s2);
-            q.coschi = 2. * pow(rng.rf(), 1. / alpha) - 1.;
-            q.sinchi = sqrt(1. - q.coschi * q.coschi);
-            const double theta = PI2 * rng.rf();
-            q.costheta = cos(theta);
-            q.sintheta = sin(theta);
-            pre[g] = q;
-        }
-        S.cand[g] = make_uint2((b + k1) | ((b + k2) << 16), meta);
-        S.pend[0][g] = (unsigned short)g;
-        const unsigned int tag = (1u << 16) | (0xFFFFu - (unsigned int)g);
-        atomicMax(&S.own[b + k1], tag);
-        atomicMax(&S.own[b + k2], tag);
-    }
-    __syncthreads();
-
-    int cur = 0, nacc = 0, nreac = 0;
-    for (unsigned int round = 1;; round++) {
-        const int np = (int)S.npend[cur];
-        if (np == 0) break;
-        /* pass A: a candidate holding both claims is next in line for both particles: acceptance test */
-        for (int i = t; i < np; i += T) {
-            const unsigned int g = S.pend[cur][i];
-            const uint2 rec = S.cand[g];
-            const unsigned int j1 = rec.x & 0xFFFFu, j2 = rec.x >> 16;
-            const unsigned int tag = (round << 16) | (0xFFFFu - g);
-            if (S.own[j1] != tag || S.own[j2] != tag) {
-                S.pend[cur ^ 1][atomicAdd(&S.npend[cur ^ 1], 1u)] = (unsigned short)g;
-                continue;
+        PairIO p;
+        while (j < ncoll && !hit) {
+            rng.init(d.seed_local, 2, d.tID, (unsigned long long)c, (unsigned long long)j);
+            /* ref: :263-271 */
+            int k1 = (int)(n * rng.rf());
+            if (k1 >= n) k1 = n - 1;
+            int k2 = k1;
+            while (k2 == k1) {
+                k2 = (int)(n * rng.rf());
+                if (k2 >= n) k2 = n - 1;
             }
-            const int k = (int)(rec.y & 0xFFFFu);
-            double rfp;
-            if (IE) {
-                PgRng rng;
-                rng.init(d.seed_local, 2, d.tID, (unsigned long long)(unsigned int)S.cell[k], (unsigned long long)(g - S.coff[k]));
-                rng.seek((rec.y >> 16) & 0x7FFFu); /* the pick consumed that many draws of this candidate's stream */
-                rfp = rng.rf();
-            } else {
-                rfp = pre[g].r_acc;
-            }
-            const PgVel V1 = S.v[j1], V2 = S.v[j2];
-            const double a1[3] = {V1.vx, V1.vy, V1.vz}, a2[3] = {V2.vx, V2.vy, V2.vz};
-            if (pair_accept(d, rfp, a1, a2, V1.sid, V2.sid, S.vrmax[k], S.fcorr[k])) {
-                S.acc[atomicAdd(&S.nacc_round[round & 1u], 1u)] = (unsigned short)g;
-                nacc++;
-            }
-        }
-        __syncthreads();
-        /* pass B: the accepted candidates of this round (disjoint particles), densely packed over the threads;
-         * and the claims of the next round */
-        const int na = (int)S.nacc_round[round & 1u], np2 = (int)S.npend[cur ^ 1];
-        if (t == 0) { /* counters of the next round; their last readers passed the previous barrier */
-            S.npend[cur] = 0;
-            S.nacc_round[(round + 1u) & 1u] = 0;
-        }
-        for (int i = t; i < na; i += T) {
-            const unsigned int g = S.acc[i];
-            const uint2 rec = S.cand[g];
-            const unsigned int j1 = rec.x & 0xFFFFu, j2 = rec.x >> 16;
-            const int k = (int)(rec.y & 0xFFFFu);
-            const unsigned int cell0 = (unsigned int)S.cell[k];
-            const unsigned int nd = (rec.y >> 16) & 0x7FFFu;
-            PgRng rng;
-            rng.init(d.seed_local, 2, d.tID, (unsigned long long)cell0, (unsigned long long)(g - S.coff[k]));
-            const PgVel V1 = S.v[j1], V2 = S.v[j2];
-            PairIO p;
+            j1 = o0 + (unsigned int)k1;
+            j2 = o0 + (unsigned int)k2;
+            const PgVel V1 = d.p.vel[j1], V2 = d.p.vel[j2];
             p.c1[0] = V1.vx; p.c1[1] = V1.vy; p.c1[2] = V1.vz; p.s1 = V1.sid;
             p.c2[0] = V2.vx; p.c2[1] = V2.vy; p.c2[2] = V2.vz; p.s2 = V2.sid;
+            hit = pair_accept(d, rng.rf(), p.c1, p.c2, p.s1, p.s2, vrmax, fcorr);
+            j++;
+        }
+        /* expensive part, for all lanes that hold an accepted candidate */
+        if (hit) {
+            nacc++;
             if (!IE) {
-                const bool inelastic = (rec.y >> 31) != 0;
-                if (inelastic) rng.seek(nd + 4u); /* pick, acceptance, selector, chi, theta */
-                pair_deflect_fast(d, rng, pre[g], inelastic, p.c1, p.c2, p.s1, p.s2);
+                pair_collide_fast(d, rng, p.c1, p.c2, p.s1, p.s2);
                 PgVel W1, W2;
                 W1.vx = p.c1[0]; W1.vy = p.c1[1]; W1.vz = p.c1[2]; W1.sid = p.s1; W1.pad = 0;
                 W2.vx = p.c2[0]; W2.vy = p.c2[1]; W2.vz = p.c2[2]; W2.sid = p.s2; W2.pad = 0;
-                S.v[j1] = W1;
-                S.v[j2] = W2;
+                d.p.vel[j1] = W1;
+                d.p.vel[j2] = W2;
             } else {
-                rng.seek(nd + 1u); /* pick + acceptance draw */
-                const PgIe E1 = se[j1], E2 = se[j2];
+                const PgIe E1 = d.p.ie[j1], E2 = d.p.ie[j2];
                 p.erot1 = E1.erot; p.evib1 = E1.evib; p.erot2 = E2.erot; p.evib2 = E2.evib;
-                const long long g1 = (long long)S.goff[k] + (j1 - S.base[k]), g2 = (long long)S.goff[k] + (j2 - S.base[k]);
-                const int fl = pair_collide(d, rng, p, g2, (int)cell0);
+                const int fl = pair_collide(d, rng, p, (long long)j2, (int)c);
                 if (fl & PR_REACTED) nreac++;
                 if (fl & (PR_V | PR_S)) {
                     PgVel W1, W2;
                     W1.vx = p.c1[0]; W1.vy = p.c1[1]; W1.vz = p.c1[2]; W1.sid = p.s1; W1.pad = 0;
                     W2.vx = p.c2[0]; W2.vy = p.c2[1]; W2.vz = p.c2[2]; W2.sid = p.s2; W2.pad = 0;
-                    S.v[j1] = W1;
-                    S.v[j2] = W2;
+                    d.p.vel[j1] = W1;
+                    d.p.vel[j2] = W2;
                 }
-                if (fl & PR_E1) { PgIe E; E.erot = p.erot1; E.evib = p.evib1; se[j1] = E; }
-                if (fl & PR_E2) { PgIe E; E.erot = p.erot2; E.evib = p.evib2; se[j2] = E; }
+                if (fl & PR_E1) { PgIe E; E.erot = p.erot1; E.evib = p.evib1; d.p.ie[j1] = E; }
+                if (fl & PR_E2) { PgIe E; E.erot = p.erot2; E.evib = p.evib2; d.p.ie[j2] = E; }
                 if (fl & PR_S) { /* the species mirror in the pos records */
-                    d.p.pos[g1].sid = p.s1;
-                    d.p.pos[g2].sid = p.s2;
+                    d.p.pos[j1].sid = p.s1;
+                    d.p.pos[j2].sid = p.s2;
                 }
             }
         }
-        for (int i = t; i < np2; i += T) {
-            const unsigned int g = S.pend[cur ^ 1][i];
-            const unsigned int pr = S.cand[g].x;
-            const unsigned int tag = ((round + 1u) << 16) | (0xFFFFu - g);
-            atomicMax(&S.own[pr & 0xFFFFu], tag);
-            atomicMax(&S.own[pr >> 16], tag);
-        }
-        __syncthreads();
-        cur ^= 1;
     }
 
-    /* E: write the records back */
-    {
-        const int grp = t >> 3, gl = t & 7;
-        for (int k = grp; k < ncl; k += T / 8) {
-            const int n = S.n[k], b = S.base[k];
-            const unsigned int o = S.goff[k];
-            for (int i = gl; i < n; i += 8) {
-                d.p.vel[o + i] = S.v[b + i];
-                if (IE) d.p.ie[o + i] = se[b + i];
-            }
-        }
-    }
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) {
         nacc += __shfl_xor_sync(FULL, nacc, s);
         nreac += __shfl_xor_sync(FULL, nreac, s);
     }
-    if (lane == 0) {
-        if (nacc) atomicAdd(&S.nacc, (unsigned int)nacc);
-        if (nreac) atomicAdd(&S.nreac, (unsigned int)nreac);
-    }
-    __syncthreads();
-    if (t == 0) {
-        if (S.nacc) atomicAdd(&d.status->ncoll, (unsigned long long)S.nacc);
-        if (S.nreac) atomicAdd(&d.status->nreac, (unsigned long long)S.nreac);
+    if ((threadIdx.x & 31) == 0) {
+        if (nacc) atomicAdd(&d.status->ncoll, (unsigned long long)nacc);
+        if (nreac) atomicAdd(&d.status->nreac, (unsigned long long)nreac);
     }
 }
 
@@ -732,12 +569,6 @@ __global__ void __launch_bounds__(256) cand_process_kernel(const __grid_constant
     owner[rec.y] = OWNER_FREE;
 }
 
-size_t tile_smem_bytes(bool ie) {
-    size_t b = (sizeof(TileSmem) + 31) & ~(size_t)31;
-    b += ie ? sizeof(PgIe) * PG_TILE_CAP : sizeof(CandPre) * (PG_TILE_CAP / 2);
-    return b;
-}
-
 } /* namespace */
 
 static int ensure_big_scratch(pgpu_ctx* c) {
@@ -838,14 +669,10 @@ int pg_collide_impl(pgpu_ctx* c, int tID) {
     pg_refresh_dev(c);
     const PgDev& d = c->dev;
 
-    if (d.ntiles > 0) {
-        /* per device, cheap: opt in to more than 48 KB of dynamic shared memory */
-        PG_CUDA(c, cudaFuncSetAttribute(tile_collide_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem_bytes(false)));
-        PG_CUDA(c, cudaFuncSetAttribute(tile_collide_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem_bytes(true)));
-        PG_CUDA(c, cudaFuncSetAttribute(tile_collide_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        PG_CUDA(c, cudaFuncSetAttribute(tile_collide_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        if (d.use_ie) tile_collide_kernel<true><<<d.ntiles, PG_TILE_THREADS, tile_smem_bytes(true), c->stream>>>(d);
-        else tile_collide_kernel<false><<<d.ntiles, PG_TILE_THREADS, tile_smem_bytes(false), c->stream>>>(d);
+    {
+        unsigned int blocks = (unsigned int)((d.ncells + 127) / 128);
+        if (d.use_ie) cell_collide_kernel<true><<<blocks, 128, 0, c->stream>>>(d);
+        else cell_collide_kernel<false><<<blocks, 128, 0, c->stream>>>(d);
         c->launches++;
         PG_CUDA(c, cudaGetLastError());
     }

@@ -38,13 +38,22 @@
 #define PG_TOMBSTONE (-1)
 /* collision tiles (pgpu_collide.cu): a tile owns the cells whose first sorted slot lies in a window of
  * PG_TILE_S slots; cells with more than PG_TILE_BIG particles take the global dependency-round path */
+#ifndef PG_TILE_S
 #define PG_TILE_S 512
+#endif
 #define PG_TILE_BIG 256
-#define PG_TILE_CAP 768   /* >= PG_TILE_S - 1 + PG_TILE_BIG */
-#define PG_TILE_MAXC 384  /* cells of >= 2 particles that fit PG_TILE_CAP slots */
+#define PG_TILE_CAP (PG_TILE_S + PG_TILE_BIG)  /* >= PG_TILE_S - 1 + PG_TILE_BIG */
+#define PG_TILE_MAXC (PG_TILE_CAP / 2)         /* cells of >= 2 particles that fit PG_TILE_CAP slots */
+#ifndef PG_TILE_THREADS
 #define PG_TILE_THREADS 256
+#endif
+#ifndef PG_CELL_MINBLOCKS
+#define PG_CELL_MINBLOCKS 6
+#endif
 /* particles one warp of the LEAN advect pass works through (lanes refill as their particle finishes) */
+#ifndef PG_ADVECT_CHUNK
 #define PG_ADVECT_CHUNK 256
+#endif
 #define PG_MAX_HOPS 1000000 /* guard against a malformed mesh hanging the GPU */
 
 /* status block, device resident, read back at the end of every hot-path call */
