@@ -479,56 +479,52 @@ __device__ __forceinline__ int unstructured_iter(const PgDev& d, PgRng& g, PStat
                 }
             }
         } else {
-            /* ref: :1257-1305 sequential tightening, '>=' tie rule (last wins) */
+            /* ref: :1257-1305 sequential tightening, '>=' tie rule (last wins).
+             * VN and DX of a face do not depend on the faces before it, so they are evaluated for all faces
+             * first (independent loads and arithmetic, in flight together) and the tightening then runs over
+             * registers.  Same operations on the same operands as the reference's single loop. */
+            double vn[NF], dx[NF];
 #pragma unroll
             for (int i = 0; i < NF; i++) {
-                double vn, dx;
                 if (DIMS == 1) {
                     double n1 = __ldg(&geo[6 * i + 0]);
                     double p1 = __ldg(&geo[6 * i + 3]);
-                    vn = q.vx * n1;
-                    dx = (p1 - q.x) * n1;
-                    if (vn >= 0. && vn * dtcoll >= dx) {
-                        dtcoll = dx / vn; boundcoll = i;
-                        codesel = (i == 0) ? codes.x : codes.y;
-                        nsel[0] = n1; nsel[1] = 0.; nsel[2] = 0.;
-                    }
+                    vn[i] = q.vx * n1;
+                    dx[i] = (p1 - q.x) * n1;
                 } else if (DIMS == 2) {
                     double2 n12 = __ldg(reinterpret_cast<const double2*>(&geo[6 * i + 0]));
                     double p1 = __ldg(&geo[6 * i + 3]), p2 = __ldg(&geo[6 * i + 4]);
-                    vn = q.vx * n12.x + q.vy * n12.y;
-                    dx = (p1 - q.x) * n12.x + (p2 - q.y) * n12.y;
-                    const bool take = (vn >= 0. && vn * dtcoll >= dx);
-                    double num = take ? dx : 1., den = take ? vn : 1.; /* see the 3-D branch */
-                    asm("" : "+d"(num), "+d"(den));
-                    const double quo = num / den;
-                    if (take) {
-                        dtcoll = quo; boundcoll = i;
-                        codesel = (i == 0) ? codes.x : (i == 1) ? codes.y : codes.z;
-                        nsel[0] = n12.x; nsel[1] = n12.y; nsel[2] = 0.;
-                    }
+                    vn[i] = q.vx * n12.x + q.vy * n12.y;
+                    dx[i] = (p1 - q.x) * n12.x + (p2 - q.y) * n12.y;
                 } else {
                     double2 a = __ldg(reinterpret_cast<const double2*>(&geo[6 * i + 0]));
                     double2 b = __ldg(reinterpret_cast<const double2*>(&geo[6 * i + 2]));
                     double2 c = __ldg(reinterpret_cast<const double2*>(&geo[6 * i + 4]));
                     /* a = (nx,ny) b = (nz,px) c = (py,pz) */
-                    vn = q.vx * a.x + q.vy * a.y + q.vz * b.x;
-                    dx = (b.y - q.x) * a.x + (c.x - q.y) * a.y + (c.y - q.z) * b.x;
-                    /* The compiler evaluates the quotient for every lane and selects; a particle that has
-                     * just crossed an axis-aligned face sits EXACTLY on it (dx == 0), which sends the whole
-                     * warp through the slow path of the FP64 division for a result that is discarded (that
-                     * face now has vn < 0).  Feeding 1/1 to the lanes that do not take the face keeps the
-                     * division on its fast path; the lanes that take it divide the same operands as before. */
-                    const bool take = (vn >= 0. && vn * dtcoll >= dx);
-                    double num = take ? dx : 1., den = take ? vn : 1.;
-                    asm("" : "+d"(num), "+d"(den)); /* opaque: keeps the selects in front of the division */
-                    const double quo = num / den;
-                    if (take) {
-                        dtcoll = quo; boundcoll = i;
-                        codesel = (i == 0) ? codes.x : (i == 1) ? codes.y : (i == 2) ? codes.z : codes.w;
-                        nsel[0] = a.x; nsel[1] = a.y; nsel[2] = b.x;
-                    }
+                    vn[i] = q.vx * a.x + q.vy * a.y + q.vz * b.x;
+                    dx[i] = (b.y - q.x) * a.x + (c.x - q.y) * a.y + (c.y - q.z) * b.x;
                 }
+            }
+#pragma unroll
+            for (int i = 0; i < NF; i++) {
+                /* The compiler evaluates the quotient for every lane and selects; a particle that has just
+                 * crossed an axis-aligned face sits EXACTLY on it (dx == 0), which sends the whole warp
+                 * through the slow path of the FP64 division for a result that is discarded (that face now
+                 * has vn < 0).  Feeding 1/1 to the lanes that do not take the face keeps the division on
+                 * its fast path; the lanes that take it divide the same operands as before. */
+                const bool take = (vn[i] >= 0. && vn[i] * dtcoll >= dx[i]);
+                double num = take ? dx[i] : 1., den = take ? vn[i] : 1.;
+                asm("" : "+d"(num), "+d"(den)); /* opaque: keeps the selects in front of the division */
+                const double quo = num / den;
+                if (take) {
+                    dtcoll = quo; boundcoll = i;
+                    codesel = (i == 0) ? codes.x : (i == 1) ? codes.y : (i == 2) ? codes.z : codes.w;
+                }
+            }
+            if (!LEAN && boundcoll != -1) { /* outward normal of the face that was hit (boundary models) */
+                nsel[0] = __ldg(&geo[6 * boundcoll + 0]);
+                nsel[1] = (DIMS >= 2) ? __ldg(&geo[6 * boundcoll + 1]) : 0.;
+                nsel[2] = (DIMS >= 3) ? __ldg(&geo[6 * boundcoll + 2]) : 0.;
             }
         }
 
@@ -536,6 +532,11 @@ __device__ __forceinline__ int unstructured_iter(const PgDev& d, PgRng& g, PStat
             const int code = codesel;
             if (code > 0) {
                 /* ref: :1311-1312, :1648-1652 cell hop */
+                if (LEAN) { /* the record of the next cell is needed a whole loop trip from now: start it early */
+                    const double* nx = d.face_geo + (size_t)(code - 1) * (NF * 6 + 2);
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(nx));
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(nx + NF * 6));
+                }
                 move_particle<AXI>(q, dtcoll);
                 q.dtrim = q.dtrim - dtcoll;
                 q.ic = code;
@@ -851,7 +852,7 @@ __device__ __forceinline__ void tombstone_particle(const PgDev& d, long long slo
  * LEAN pass.  One warp works through PG_ADVECT_CHUNK consecutive slots; see the file header.
  */
 template <int MODE, bool AXI>
-__global__ void __launch_bounds__(128, 8) advect_lean_kernel(const __grid_constant__ PgDev d, long long n) {
+__global__ void __launch_bounds__(128, PG_ADVECT_MINBLOCKS) advect_lean_kernel(const __grid_constant__ PgDev d, long long n) {
     const unsigned int FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;

@@ -343,12 +343,13 @@ __global__ void __launch_bounds__(128, PG_CELL_MINBLOCKS) cell_collide_kernel(co
     int nacc = 0, nreac = 0;
     int j = 0;
     while (__any_sync(FULL, j < ncoll)) {
-        /* cheap part: this lane's candidates up to and including its next accepted one */
+        /* cheap part: this lane's next candidates, up to and including its next accepted one; bounded, so that
+         * the lanes that already hold an accepted candidate do not idle behind the unluckiest lane */
         bool hit = false;
         unsigned int j1 = 0, j2 = 0;
         PgRng rng;
         PairIO p;
-        while (j < ncoll && !hit) {
+        for (int tries = 0; tries < PG_CELL_TRIES && j < ncoll && !hit; tries++) {
             rng.init(d.seed_local, 2, d.tID, (unsigned long long)c, (unsigned long long)j);
             /* ref: :263-271 */
             int k1 = (int)(n * rng.rf());

@@ -50,6 +50,12 @@
 #ifndef PG_CELL_MINBLOCKS
 #define PG_CELL_MINBLOCKS 6
 #endif
+#ifndef PG_CELL_TRIES
+#define PG_CELL_TRIES 2 /* acceptance tests a lane runs before the warp re-converges for the deflections */
+#endif
+#ifndef PG_ADVECT_MINBLOCKS
+#define PG_ADVECT_MINBLOCKS 6
+#endif
 /* particles one warp of the LEAN advect pass works through (lanes refill as their particle finishes) */
 #ifndef PG_ADVECT_CHUNK
 #define PG_ADVECT_CHUNK 256
