@@ -33,6 +33,17 @@ sys.path.insert(0, ROOT)
 
 B_MOVE, B_SORT, B_COLLIDE = 84.0, 144.0, 52.0  # SURVEY 8(d), argon VSS
 B_ALG = B_MOVE + B_SORT + B_COLLIDE
+B_SORT_RESTATED = 128.0                         # pos + vel records read and written; the all-zero ie plane is skipped
+B_ALG_RESTATED = B_MOVE + B_SORT_RESTATED + B_COLLIDE
+
+
+def ncu_traffic_per_particle(group):
+    """DRAM bytes per particle of the group's main kernel from the committed ncu capture (None if absent)."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        return float(t["dram_bytes_per_particle"][group])
+    except Exception:
+        return None
 
 
 def measured_peak_gbs():
@@ -216,38 +227,79 @@ def main():
     peak, peak_src = measured_peak_gbs()
     grp = {"move": float(ms[0]) / args.steps, "sort": float(ms[1]) / args.steps, "collide": float(ms[2]) / args.steps,
            "exchange": float(ms[4]) / args.steps}
-    bytes_grp = {"move": B_MOVE, "sort": B_SORT, "collide": B_COLLIDE}
+    bytes_grp = {"move": B_MOVE, "sort": B_SORT_RESTATED, "collide": B_COLLIDE}
     dom = max(bytes_grp, key=lambda k: grp[k])
     ach_dom = n_now * bytes_grp[dom] / (grp[dom] * 1e-3) / 1e9
-    ach_step = n_now * B_ALG / (total_ms / args.steps * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "achieved": ach_dom, "peak": peak, "unit": "GB/s", "frac": ach_dom / peak, "traffic": None,
-                "kernel": dom, "peak_source": peak_src, "algorithmic_bytes_per_particle": bytes_grp[dom],
-                "whole_step": {"achieved": ach_step, "frac": ach_step / peak, "algorithmic_bytes_per_particle": B_ALG},
+    ach_step = n_now * B_ALG_RESTATED / (total_ms / args.steps * 1e-3) / 1e9
+    ach_step_survey = n_now * B_ALG / (total_ms / args.steps * 1e-3) / 1e9
+    tpp = ncu_traffic_per_particle(dom)
+    roofline = {"bound": "hbm", "achieved": ach_dom, "peak": peak, "unit": "GB/s", "frac": ach_dom / peak,
+                "traffic": (tpp * n_now if tpp is not None else None),
+                "kernel": {"move": "advect_lean_kernel (+advect_full_kernel)", "sort": "scatter_kernel",
+                           "collide": "cell_collide_kernel"}[dom],
+                "kernel_ms_per_launch": grp[dom], "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs, burst copy)",
+                "algorithmic_bytes_per_particle": bytes_grp[dom], "algorithmic_bytes_per_launch": bytes_grp[dom] * n_now,
+                "note": "this kernel is issue/LSU-bound, not HBM-bound (DESIGN.md section 3, profiles/r01*)",
+                "whole_step": {"achieved": ach_step, "frac": ach_step / peak, "algorithmic_bytes_per_particle": B_ALG_RESTATED,
+                               "survey_8d": {"achieved": ach_step_survey, "frac": ach_step_survey / peak,
+                                             "algorithmic_bytes_per_particle": B_ALG}},
                 "groups_ms_per_step": grp,
                 "groups_frac": {k: n_now * bytes_grp[k] / (grp[k] * 1e-3) / 1e9 / peak for k in bytes_grp if grp[k] > 0}}
 
     # ---------------- e2e: host AoS in, one step, host AoS out, every step --------------------------
+    # Every step: pgpu_upload_particles from pinned host records, one hot-path step, pgpu_download_particles into
+    # pinned host records.  A step is PCIe-bound (2 x 12 GB per GPU against 16 ms of kernels), so at N = 1 two
+    # library contexts on the same GPU, each driven by its own host thread, work on alternating steps: the
+    # download of step s overlaps the upload of step s+1 (PCIe is full duplex).  Each step still makes the full
+    # host -> device -> host round trip through the C ABI.  With N > 1 one context per rank is used (two NCCL
+    # communicators driven from two threads are not ordered against each other).
     e2e = None
     if not args.no_e2e:
+        import threading
         k2 = args.e2e_steps or args.steps
-        out = wl.pinned_particles(n_local)
-        for s in range(3):  # warm-up
-            gpu.upload_particles(w.particles)
-            gpu.run_steps(1000 + s, 1)
-            gpu.download_into(out)
+        ctxs = [gpu]
+        if world == 1:
+            g2 = capi.load_gpu(local_rank)
+            wl.apply(g2, w, upload=False)
+            ctxs.append(g2)
+        outs = [wl.pinned_particles(n_local) for _ in ctxs]
+        moved = [0 for _ in ctxs]
+
+        def drive(i, first, count, tid0, go, nxt):
+            go.wait()  # staggered start: context i+1 begins its upload when context i has finished its first one,
+            for k, s in enumerate(range(first, count, len(ctxs))):  # so uploads meet downloads, not other uploads
+                ctxs[i].upload_particles(w.particles)
+                if k == 0 and nxt is not None:
+                    nxt.set()
+                ctxs[i].run_steps(tid0 + s, 1)
+                moved[i] += ctxs[i].download_into(outs[i])
+            if nxt is not None:
+                nxt.set()
+
+        def run_all(count, tid0):
+            ev = [threading.Event() for _ in ctxs]
+            th = [threading.Thread(target=drive, args=(i, i, count, tid0, ev[i], ev[i + 1] if i + 1 < len(ctxs) else None))
+                  for i in range(len(ctxs))]
+            for t in th:
+                t.start()
+            ev[0].set()
+            for t in th:
+                t.join()
+
+        run_all(3 * len(ctxs), 1000)  # warm-up (first-touch of both contexts' stores and staging buffers)
+        moved = [0 for _ in ctxs]
         barrier()
         t0 = time.perf_counter()
-        moved = 0
-        for s in range(k2):
-            gpu.upload_particles(w.particles)
-            gpu.run_steps(2000 + s, 1)
-            moved += gpu.download_into(out)
+        run_all(k2, 2000)
         barrier()
         e2e_s = max_over_ranks(time.perf_counter() - t0)
-        e2e = {"value": sum_over_ranks(float(moved)) / e2e_s, "unit": "particle-timesteps/s",
+        e2e = {"value": sum_over_ranks(float(sum(moved))) / e2e_s, "unit": "particle-timesteps/s",
                "h2d_bytes_per_step": int(n_local * 96 * world), "d2h_bytes_per_step": int(n_local * 96 * world),
-               "steps": k2, "ms_per_step": e2e_s / k2 * 1e3,
-               "what": "pgpu_upload_particles(pinned AoS) + pgpu_run_steps(1) + pgpu_download_particles(pinned AoS) per step"}
+               "steps": k2, "ms_per_step": e2e_s / k2 * 1e3, "contexts_per_gpu": len(ctxs),
+               "what": "per step: pgpu_upload_particles(pinned 96-byte AoS) + pgpu_run_steps(1) + pgpu_download_particles"
+                       "(pinned AoS); PCIe-bound" + ("; two contexts on alternating steps overlap H2D with D2H" if len(ctxs) > 1 else "")}
+        for g in ctxs[1:]:
+            g.close()
 
     cpu = None
     if rank == 0 and not args.no_cpu:
@@ -263,7 +315,7 @@ def main():
                                    f"{n_local} particles per GPU ({n_local * world} total)",
                        "particles_per_gpu": n_local, "cells_per_gpu": int(w.mesh.nc // max(world, 1)), "mesh_cells": int(w.mesh.nc),
                        "ppc": n_local / (w.mesh.nc / max(world, 1)), "partition": f"stripsx x{world}",
-                       "l2_policy": "inputs (9 GB of particle planes per GPU) are far larger than the 126 MB L2",
+                       "l2_policy": "inputs (8 GB of pos+vel records per GPU, streamed every step) are far larger than the 126 MB L2",
                        "rng": "Philox4x32-10 per particle/candidate", "ids": "regenerated on download (track_id=0)"},
             "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu, "gpu_launches": int(launches),
             "clocks": clocks, "collisions_per_step": ncoll / args.steps, "wall_ms_per_step": wall_ms / args.steps,
