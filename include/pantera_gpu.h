@@ -148,6 +148,10 @@ int pgpu_set_wall_reactions(pgpu_ctx* ctx, int n, const int32_t* r_sp, const int
 /* MIXTURES(MCC_BG_MIX) components -- src/collisions.f90:1653-1657 */
 int pgpu_set_mcc_background(pgpu_ctx* ctx, int ncomp, const int32_t* sp_id, const double* molfrac);
 
+/* MCC_BG_CELL_NRHO(N_SPECIES, NCELLS) -- src/global.f90:392, filled by src/initialization.f90:2752-2788
+ * (BOOL_BG_DENSITY_FILE); column-major as Fortran stores it.  nrho == NULL clears it (uniform background). */
+int pgpu_set_mcc_cell_density(pgpu_ctx* ctx, int ns, int64_t nc, const double* nrho);
+
 /* U1D/U2D/U3D_GRID -- src/global.f90:128-193, as computed by READ_*_SU2
  * (src/grid_and_partition.f90:627-2147).  d = dims.  Shapes (Fortran order):
  *   node_coords(3,nn) cell_nodes(d+1,nc) cell_neighbors(d+1,nc)
@@ -218,6 +222,10 @@ int pgpu_collide(pgpu_ctx* ctx, int32_t tID, int64_t* timestep_coll, int64_t* ti
 
 /* MCC_COLLISIONS_VAHEDI (src/collisions.f90:1606-1892) */
 int pgpu_mcc_vahedi(pgpu_ctx* ctx, int32_t tID, int64_t* timestep_coll, int64_t* timestep_reac);
+
+/* MCC_COLLISIONS (src/collisions.f90:1261-1595): VSS cross-section MCC against the background mixture,
+ * uniform (MCC_BG_DENS x MOLFRAC) or per cell (pgpu_set_mcc_cell_density) */
+int pgpu_mcc_collisions(pgpu_ctx* ctx, int32_t tID, int64_t* timestep_coll, int64_t* timestep_reac);
 
 /* REMOVE_PARTICLES_OF_SPECIES (src/timecycle.f90:2340-2353) */
 int pgpu_remove_species(pgpu_ctx* ctx, int32_t sp_id);

@@ -54,6 +54,8 @@ struct po_ctx {
     int mcc_ncomp;
     int* mcc_sp;
     double* mcc_frac;
+    double* mcc_cell_nrho; /* MCC_BG_CELL_NRHO(N_SPECIES, NCELLS), NULL = BOOL_BG_DENSITY_FILE false */
+    int64_t mcc_cell_nrho_n;
     /* mesh */
     int dims_mesh, nn, nc;
     double* node_coords;
@@ -1208,9 +1210,124 @@ static void react_redistribute(po_ctx* w, const reaction_t* r, int64_t jp1, int6
     }
 }
 
+/* An ACCEPTED pair (jp1, jp2): reaction test, Borgnakke-Larsen exchange, VSS deflection.
+ * ref: src/collisions.f90:327-546 (VSS_COLLIS) and :1362-1590 (MCC_COLLISIONS); s1/s2 are the species the
+ * caller looked up BEFORE the pair was accepted (MCC_COLLISIONS keeps SP_ID1 across background components even
+ * after a reaction changed the particle's S_ID).  Returns 1 when the pair reacted. */
+static int accepted_pair(po_ctx* w, int64_t jp1, int64_t jp2, int s1, int s2, double vr, double vr2, int gate_all) {
+    const double PI2 = 2. * PI;
+    part_t *q1 = &w->p[jp1], *q2 = &w->p[jp2];
+    double cref = VSS2(w->grefs, s1, s2), sigma = VSS2(w->sigmas, s1, s2);
+    double omega = VSS2(w->omegas, s1, s2), alpha = VSS2(w->alphas, s1, s2);
+    double m1 = w->mass[s1 - 1], m2 = w->mass[s2 - 1];
+    double mred = m1 * m2 / (m1 + m2);
+    double etr = 0.5 * mred * vr2;
+    double c1[3] = {q1->VX, q1->VY, q1->VZ}, c2[3] = {q2->VX, q2->VY, q2->VZ};
+    double rfp;
+    int skip = 0;
+    /* ref: :331-449 TCE / LXCat reaction test (MCC_COLLISIONS :1362-1495 is the same code plus an EA gate
+     * in front of the reaction-type switch, :1383-1384) */
+    double ecoll = etr + q1->EROT + q2->EROT + q1->EVIB + q2->EVIB;
+    for (int jr = 0; jr < w->nr; jr++) {
+        const reaction_t* r = &w->reac[jr];
+        if (r->r1 != s1) {
+            if (r->r1 != s2) continue;
+            else if (r->r2 != s1) continue;
+        } else {
+            if (r->r2 != s2) continue;
+        }
+        double ea = r->ea, ptce;
+        if (gate_all && ecoll <= ea) continue;
+        if (r->type == PGPU_TCE) {
+            if (ecoll <= ea) continue;
+            ptce = r->c1 * pow(ecoll - ea, r->c2) * pow(1. - ea / ecoll, r->c3);
+        } else if (r->type == PGPU_LXCAT) {
+            double sigma_r = po_interp_cs(etr, r->tab_n, r->tab_e, r->tab_cs);
+            ptce = sigma_r / (sigma * pow(vr / cref, 1. - 2. * omega));
+        } else {
+            ptce = 0;
+        }
+        rfp = po_rf(w);
+        if (rfp < ptce) {
+            skip = 1;
+            w->timestep_reac++;
+            w->reac[jr].counts++;
+            ecoll = ecoll - ea;
+            /* roles are NOT swapped when the pair order is opposite to the reaction (App. A9) */
+            q1->S_ID = r->p1;
+            q2->S_ID = r->p2;
+            react_redistribute(w, r, jp1, jp2, ecoll, c1, c2, 1);
+            break;
+        }
+    }
+    if (skip) return 1;
+    /* pointers may be stale after a realloc in add_particle only in the reacting branch */
+    q1 = &w->p[jp1];
+    q2 = &w->p[jp2];
+
+    /* ref: :454-490 Borgnakke-Larsen, at most one mode */
+    double trdof = 3.;
+    double prot1 = (trdof + w->rotdof[s1 - 1]) / trdof * w->rotrel[s1 - 1];
+    double prot2 = (trdof + w->rotdof[s2 - 1]) / trdof * w->rotrel[s2 - 1];
+    double pvib1 = (trdof + w->vibdof[s1 - 1]) / trdof * w->vibrel[s1 - 1];
+    double pvib2 = (trdof + w->vibdof[s2 - 1]) / trdof * w->vibrel[s2 - 1];
+    trdof = 5. - 2. * omega;
+    rfp = po_rf(w);
+    if (rfp < prot1) {
+        ecoll = etr + q1->EROT;
+        q1->EROT = coll_internal_energy(w, ecoll, trdof, w->rotdof[s1 - 1]);
+        etr = ecoll - q1->EROT;
+    } else if (rfp < prot1 + prot2) {
+        ecoll = etr + q2->EROT;
+        q2->EROT = coll_internal_energy(w, ecoll, trdof, w->rotdof[s2 - 1]);
+        etr = ecoll - q2->EROT;
+    } else if (rfp < prot1 + prot2 + pvib1) {
+        ecoll = etr + q1->EVIB;
+        q1->EVIB = coll_internal_energy(w, ecoll, trdof, w->vibdof[s1 - 1]);
+        etr = ecoll - q1->EVIB;
+    } else if (rfp < prot1 + prot2 + pvib1 + pvib2) {
+        ecoll = etr + q2->EVIB;
+        q2->EVIB = coll_internal_energy(w, ecoll, trdof, w->vibdof[s2 - 1]);
+        etr = ecoll - q2->EVIB;
+    }
+
+    /* ref: :495-546 VSS deflection */
+    double coschi = 2. * pow(po_rf(w), 1. / alpha) - 1.;
+    double sinchi = sqrt(1. - coschi * coschi);
+    double theta = PI2 * po_rf(w);
+    double costheta = cos(theta), sintheta = sin(theta);
+    double gx, gy, gz, g;
+    if (rfp < prot1 + prot2 + pvib1 + pvib2) {
+        g = sqrt(2. * etr / mred);
+        double cosa = 2. * po_rf(w) - 1.0;
+        double sina = sqrt(1 - cosa * cosa);
+        double bb = PI2 * po_rf(w);
+        gx = g * sina * cos(bb);
+        gy = g * sina * sin(bb);
+        gz = g * cosa;
+    } else {
+        gx = c1[0] - c2[0];
+        gy = c1[1] - c2[1];
+        gz = c1[2] - c2[2];
+        g = sqrt(gx * gx + gy * gy + gz * gz);
+    }
+    double grel[3], wc[3];
+    double gyz = sqrt(gy * gy + gz * gz);
+    grel[0] = gx * coschi + gyz * sintheta * sinchi;
+    grel[1] = gy * coschi + (g * gz * costheta - gx * gy * sintheta) / gyz * sinchi;
+    grel[2] = gz * coschi - (g * gy * costheta + gx * gz * sintheta) / gyz * sinchi;
+    for (int i = 0; i < 3; i++) wc[i] = m1 / (m1 + m2) * c1[i] + m2 / (m1 + m2) * c2[i];
+    for (int i = 0; i < 3; i++) {
+        c1[i] = wc[i] + m2 / (m1 + m2) * grel[i];
+        c2[i] = wc[i] - m1 / (m1 + m2) * grel[i];
+    }
+    q1->VX = c1[0]; q1->VY = c1[1]; q1->VZ = c1[2];
+    q2->VX = c2[0]; q2->VY = c2[1]; q2->VZ = c2[2];
+    return 0;
+}
+
 /* ref: src/collisions.f90:155-558 VSS_COLLIS for cell jc (1-based); ind = INDALL slice (0-based particle ids) */
 static int64_t vss_collis(po_ctx* w, int jc, int tID, int npcj, const int32_t* ind) {
-    const double PI2 = 2. * PI;
     double cfnum = w->c.fnum; /* BOOL_RADIAL_WEIGHTING not on the path */
     double vxmax = -1.e+38, vxmin = 1.e+38, vymax = -1.e+38, vymin = 1.e+38, vzmax = -1.e+38, vzmin = 1.e+38;
     for (int j = 0; j < npcj; j++) {
@@ -1240,7 +1357,6 @@ static int64_t vss_collis(po_ctx* w, int jc, int tID, int npcj, const int32_t* i
 
     for (long jcol = 0; jcol < ncoll; jcol++) {
         po_rng_stream(w, 2, tID, (uint64_t)(jc - 1), (uint64_t)jcol);
-        int skip = 0;
         /* ref: :263-271; rf() is [0,1] so INT(NPCJ*rf()) may equal NPCJ with probability 2^-53 (App. B4):
          * clamped here, cannot happen with the [0,1) Philox stream */
         int k1 = (int)(npcj * po_rf(w));
@@ -1258,11 +1374,7 @@ static int64_t vss_collis(po_ctx* w, int jc, int tID, int npcj, const int32_t* i
         double vr = sqrt(vr2);
         int s1 = q1->S_ID, s2 = q2->S_ID;
         double cref = VSS2(w->grefs, s1, s2), sigma = VSS2(w->sigmas, s1, s2);
-        double omega = VSS2(w->omegas, s1, s2), alpha = VSS2(w->alphas, s1, s2);
-        double m1 = w->mass[s1 - 1], m2 = w->mass[s2 - 1];
-        double mred = m1 * m2 / (m1 + m2);
-        double etr = 0.5 * mred * vr2;
-        double c1[3] = {q1->VX, q1->VY, q1->VZ}, c2[3] = {q2->VX, q2->VY, q2->VZ};
+        double omega = VSS2(w->omegas, s1, s2);
 
         double rfp = po_rf(w);
         double collsigma;
@@ -1276,102 +1388,7 @@ static int64_t vss_collis(po_ctx* w, int jc, int tID, int npcj, const int32_t* i
         if (!(rfp < collprob)) continue;
         ncollreal++;
 
-        /* ref: :331-449 TCE / LXCat reaction test */
-        double ecoll = etr + q1->EROT + q2->EROT + q1->EVIB + q2->EVIB;
-        for (int jr = 0; jr < w->nr; jr++) {
-            const reaction_t* r = &w->reac[jr];
-            if (r->r1 != s1) {
-                if (r->r1 != s2) continue;
-                else if (r->r2 != s1) continue;
-            } else {
-                if (r->r2 != s2) continue;
-            }
-            double ea = r->ea, ptce;
-            if (r->type == PGPU_TCE) {
-                if (ecoll <= ea) continue;
-                ptce = r->c1 * pow(ecoll - ea, r->c2) * pow(1. - ea / ecoll, r->c3);
-            } else if (r->type == PGPU_LXCAT) {
-                double sigma_r = po_interp_cs(etr, r->tab_n, r->tab_e, r->tab_cs);
-                ptce = sigma_r / (sigma * pow(vr / cref, 1. - 2. * omega));
-            } else {
-                ptce = 0;
-            }
-            rfp = po_rf(w);
-            if (rfp < ptce) {
-                skip = 1;
-                w->timestep_reac++;
-                w->reac[jr].counts++;
-                ecoll = ecoll - ea;
-                /* roles are NOT swapped when the pair order is opposite to the reaction (App. A9) */
-                q1->S_ID = r->p1;
-                q2->S_ID = r->p2;
-                react_redistribute(w, r, jp1, jp2, ecoll, c1, c2, 1);
-                break;
-            }
-        }
-        if (skip) continue;
-        /* pointers may be stale after a realloc in add_particle only in the reacting branch */
-        q1 = &w->p[jp1];
-        q2 = &w->p[jp2];
-
-        /* ref: :454-490 Borgnakke-Larsen, at most one mode */
-        double trdof = 3.;
-        double prot1 = (trdof + w->rotdof[s1 - 1]) / trdof * w->rotrel[s1 - 1];
-        double prot2 = (trdof + w->rotdof[s2 - 1]) / trdof * w->rotrel[s2 - 1];
-        double pvib1 = (trdof + w->vibdof[s1 - 1]) / trdof * w->vibrel[s1 - 1];
-        double pvib2 = (trdof + w->vibdof[s2 - 1]) / trdof * w->vibrel[s2 - 1];
-        trdof = 5. - 2. * omega;
-        rfp = po_rf(w);
-        if (rfp < prot1) {
-            ecoll = etr + q1->EROT;
-            q1->EROT = coll_internal_energy(w, ecoll, trdof, w->rotdof[s1 - 1]);
-            etr = ecoll - q1->EROT;
-        } else if (rfp < prot1 + prot2) {
-            ecoll = etr + q2->EROT;
-            q2->EROT = coll_internal_energy(w, ecoll, trdof, w->rotdof[s2 - 1]);
-            etr = ecoll - q2->EROT;
-        } else if (rfp < prot1 + prot2 + pvib1) {
-            ecoll = etr + q1->EVIB;
-            q1->EVIB = coll_internal_energy(w, ecoll, trdof, w->vibdof[s1 - 1]);
-            etr = ecoll - q1->EVIB;
-        } else if (rfp < prot1 + prot2 + pvib1 + pvib2) {
-            ecoll = etr + q2->EVIB;
-            q2->EVIB = coll_internal_energy(w, ecoll, trdof, w->vibdof[s2 - 1]);
-            etr = ecoll - q2->EVIB;
-        }
-
-        /* ref: :495-546 VSS deflection */
-        double coschi = 2. * pow(po_rf(w), 1. / alpha) - 1.;
-        double sinchi = sqrt(1. - coschi * coschi);
-        double theta = PI2 * po_rf(w);
-        double costheta = cos(theta), sintheta = sin(theta);
-        double gx, gy, gz, g;
-        if (rfp < prot1 + prot2 + pvib1 + pvib2) {
-            g = sqrt(2. * etr / mred);
-            double cosa = 2. * po_rf(w) - 1.0;
-            double sina = sqrt(1 - cosa * cosa);
-            double bb = PI2 * po_rf(w);
-            gx = g * sina * cos(bb);
-            gy = g * sina * sin(bb);
-            gz = g * cosa;
-        } else {
-            gx = c1[0] - c2[0];
-            gy = c1[1] - c2[1];
-            gz = c1[2] - c2[2];
-            g = sqrt(gx * gx + gy * gy + gz * gz);
-        }
-        double grel[3], wc[3];
-        double gyz = sqrt(gy * gy + gz * gz);
-        grel[0] = gx * coschi + gyz * sintheta * sinchi;
-        grel[1] = gy * coschi + (g * gz * costheta - gx * gy * sintheta) / gyz * sinchi;
-        grel[2] = gz * coschi - (g * gy * costheta + gx * gz * sintheta) / gyz * sinchi;
-        for (int i = 0; i < 3; i++) wc[i] = m1 / (m1 + m2) * c1[i] + m2 / (m1 + m2) * c2[i];
-        for (int i = 0; i < 3; i++) {
-            c1[i] = wc[i] + m2 / (m1 + m2) * grel[i];
-            c2[i] = wc[i] - m1 / (m1 + m2) * grel[i];
-        }
-        q1->VX = c1[0]; q1->VY = c1[1]; q1->VZ = c1[2];
-        q2->VX = c2[0]; q2->VY = c2[1]; q2->VZ = c2[2];
+        accepted_pair(w, jp1, jp2, s1, s2, vr, vr2, 0);
     }
     return ncollreal;
 }
@@ -1489,6 +1506,50 @@ int po_mcc_vahedi(po_ctx* w, int32_t tID, int64_t* timestep_coll, int64_t* times
                 }
             }
             if (has_reacted) break;
+        }
+    }
+    if (timestep_coll) *timestep_coll = w->timestep_coll;
+    if (timestep_reac) *timestep_reac = w->timestep_reac;
+    return PGPU_OK;
+}
+
+/* ref: src/collisions.f90:1261-1595 MCC_COLLISIONS: every particle present at entry tests one collision per
+ * background component against a partner sampled from the background Maxwellian; an accepted partner becomes
+ * a real particle (appended) and the pair goes through the same reaction / Borgnakke-Larsen / VSS code as a
+ * DSMC pair.  Philox mode: one stream per particle, kind 4, keyed by the particle's index. */
+int po_mcc_collisions(po_ctx* w, int32_t tID, int64_t* timestep_coll, int64_t* timestep_reac) {
+    if (!w->mcc_ncomp) FAIL(w, PGPU_ERR_STATE, "po_mcc_collisions: background mixture not set");
+    if (!w->sigmas) FAIL(w, PGPU_ERR_STATE, "po_mcc_collisions: VSS tables not set");
+    w->timestep_coll = 0;
+    w->timestep_reac = 0;
+    for (int jr = 0; jr < w->nr; jr++) w->reac[jr].counts = 0;
+    double dt = w->c.dt, ttra = w->c.mcc_bg_ttra;
+    int64_t np_initial = w->np; /* ref: :1289-1290 */
+    for (int64_t jp1 = 0; jp1 < np_initial; jp1++) {
+        po_rng_stream(w, 4, tID, (uint64_t)jp1, 0);
+        int s1 = w->p[jp1].S_ID; /* ref: :1291, NOT refreshed after a reaction */
+        for (int j = 0; j < w->mcc_ncomp; j++) {
+            int s2 = w->mcc_sp[j];
+            double bg_nrho;
+            if (w->mcc_cell_nrho) bg_nrho = w->mcc_cell_nrho[(s2 - 1) + (size_t)w->ns * (w->p[jp1].IC - 1)]; /* :1296-1297 */
+            else bg_nrho = w->mcc_frac[j] * w->c.mcc_bg_dens;                                              /* :1299-1300 */
+            if (bg_nrho == 0) continue;
+            double cref = VSS2(w->grefs, s1, s2), sigma = VSS2(w->sigmas, s1, s2), omega = VSS2(w->omegas, s1, s2);
+            double c2[3];
+            po_maxwell(w, 0., 0., 0., ttra, ttra, ttra, w->mass[s2 - 1], c2); /* :1314-1316 */
+            part_t* q1 = &w->p[jp1];
+            double vr2 = (c2[0] - q1->VX) * (c2[0] - q1->VX) + (c2[1] - q1->VY) * (c2[1] - q1->VY) +
+                         (c2[2] - q1->VZ) * (c2[2] - q1->VZ);
+            double vr = sqrt(vr2);
+            double p_coll = 1 - exp(-dt * bg_nrho * vr * sigma * pow(vr / cref, 1. - 2. * omega)); /* :1327 */
+            if (!(po_rf(w) < p_coll)) continue;
+            w->timestep_coll++;
+            /* the partner becomes a particle at the position of JP1, ref: :1344-1351 */
+            double erot = po_internal_energy(w, w->rotdof[s2 - 1], ttra);
+            double evib = po_internal_energy(w, w->vibdof[s2 - 1], ttra);
+            add_particle(w, q1->X, q1->Y, q1->Z, c2[0], c2[1], c2[2], erot, evib, s2, q1->IC, dt);
+            int64_t jp2 = w->np - 1;
+            accepted_pair(w, jp1, jp2, s1, s2, vr, vr2, 1);
         }
     }
     if (timestep_coll) *timestep_coll = w->timestep_coll;
@@ -1637,6 +1698,11 @@ int po_run_steps(po_ctx* w, int32_t tID0, int32_t nsteps, int64_t* total_coll, i
             rc = po_mcc_vahedi(w, tID0 + s, &a, &b);
             if (rc) return rc;
             tc += a; tr += b;
+        } else if (w->c.collision_type == PGPU_MCC) {
+            int64_t a = 0, b = 0;
+            rc = po_mcc_collisions(w, tID0 + s, &a, &b);
+            if (rc) return rc;
+            tc += a; tr += b;
         }
     }
     if (total_coll) *total_coll = tc;
@@ -1663,7 +1729,7 @@ int po_destroy(po_ctx* w) {
     free(w->sigmas); free(w->omegas); free(w->alphas); free(w->grefs);
     free(w->reac); free(w->tab_off); free(w->tab_e); free(w->tab_cs);
     free(w->wr_r); free(w->wr_p1); free(w->wr_nprod); free(w->wr_prob);
-    free(w->mcc_sp); free(w->mcc_frac);
+    free(w->mcc_sp); free(w->mcc_frac); free(w->mcc_cell_nrho);
     free(w->node_coords); free(w->cell_nodes); free(w->cell_neighbors); free(w->face_normal);
     free(w->face_tang1); free(w->face_tang2); free(w->cell_edges_len); free(w->cell_faces_pg);
     free(w->cell_pg); free(w->basis_coeffs); free(w->cell_volumes); free(w->cell_procs);
@@ -1768,6 +1834,19 @@ int po_set_mcc_background(po_ctx* w, int ncomp, const int32_t* sp_id, const doub
     return PGPU_OK;
 }
 
+/* MCC_BG_CELL_NRHO(SP_ID, IC), ref: src/initialization.f90:2752-2788; n = 0 clears it */
+int po_set_mcc_cell_density(po_ctx* w, int ns, int64_t nc, const double* nrho) {
+    if (!nrho || ns <= 0 || nc <= 0) {
+        free(w->mcc_cell_nrho);
+        w->mcc_cell_nrho = NULL;
+        w->mcc_cell_nrho_n = 0;
+        return PGPU_OK;
+    }
+    if (ns != w->ns) FAIL(w, PGPU_ERR_INVALID, "po_set_mcc_cell_density: ns %d != %d", ns, w->ns);
+    REPL(w->mcc_cell_nrho, nrho, (size_t)ns * nc);
+    w->mcc_cell_nrho_n = (int64_t)ns * nc;
+    return PGPU_OK;
+}
 int po_set_mesh(po_ctx* w, int dims, int nn, int nc, const double* node_coords, const int32_t* cell_nodes,
                 const int32_t* cell_neighbors, const double* face_normal, const double* face_tang1,
                 const double* face_tang2, const double* cell_edges_len, const int32_t* cell_faces_pg,

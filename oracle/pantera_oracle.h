@@ -65,6 +65,7 @@ int po_set_reactions(po_ctx* ctx, int nr, const int32_t* type,
 int po_set_wall_reactions(po_ctx* ctx, int n, const int32_t* r_sp, const int32_t* p1_sp,
                           const int32_t* nprod, const double* prob);
 int po_set_mcc_background(po_ctx* ctx, int ncomp, const int32_t* sp_id, const double* molfrac);
+int po_set_mcc_cell_density(po_ctx* ctx, int ns, int64_t nc, const double* nrho);
 int po_set_mesh(po_ctx* ctx, int dims, int nn, int nc,
                 const double* node_coords, const int32_t* cell_nodes, const int32_t* cell_neighbors,
                 const double* face_normal, const double* face_tang1, const double* face_tang2,
@@ -101,6 +102,7 @@ int po_exchange_pack(po_ctx* ctx, void* sendbuf, int64_t capacity, int64_t* send
 int po_sort(po_ctx* ctx); /* no-op: the reference builds index arrays inside DSMC_COLLISIONS */
 int po_collide(po_ctx* ctx, int32_t tID, int64_t* timestep_coll, int64_t* timestep_reac);
 int po_mcc_vahedi(po_ctx* ctx, int32_t tID, int64_t* timestep_coll, int64_t* timestep_reac);
+int po_mcc_collisions(po_ctx* ctx, int32_t tID, int64_t* timestep_coll, int64_t* timestep_reac);
 int po_remove_species(po_ctx* ctx, int32_t sp_id);
 int po_run_steps(po_ctx* ctx, int32_t tID0, int32_t nsteps, int64_t* total_coll, int64_t* total_reac);
 

@@ -227,6 +227,14 @@ class Lib:
     def set_mcc_background(self, sp_id, molfrac):
         self._call("set_mcc_background", C.c_int(len(sp_id)), _p(_i32(sp_id)), _p(_f64(molfrac)))
 
+    def set_mcc_cell_density(self, nrho):
+        """``nrho``: MCC_BG_CELL_NRHO as an (ns, nc) array (Fortran order), or None to clear it."""
+        if nrho is None:
+            self._call("set_mcc_cell_density", C.c_int(0), C.c_int64(0), None)
+            return
+        a = np.asfortranarray(nrho, dtype=np.float64)
+        self._call("set_mcc_cell_density", C.c_int(a.shape[0]), C.c_int64(a.shape[1]), _p(a))
+
     def set_mesh(self, mesh):
         """``mesh``: an object/dict with the Fortran-shaped arrays produced by ``meshgen``."""
         m = mesh if isinstance(mesh, dict) else mesh.__dict__
@@ -341,6 +349,11 @@ class Lib:
     def mcc_vahedi(self, tID: int):
         a, b = C.c_int64(), C.c_int64()
         self._call("mcc_vahedi", C.c_int32(tID), C.byref(a), C.byref(b))
+        return a.value, b.value
+
+    def mcc_collisions(self, tID: int):
+        a, b = C.c_int64(), C.c_int64()
+        self._call("mcc_collisions", C.c_int32(tID), C.byref(a), C.byref(b))
         return a.value, b.value
 
     def remove_species(self, sp):

@@ -436,11 +436,24 @@ __device__ __forceinline__ int unstructured_iter(const PgDev& d, PgRng& g, PStat
     {
         double dtcoll = q.dtrim;
         int boundcoll = -1;
-        const double* geo = d.face_geo + (size_t)(ic - 1) * (NF * 6 + 2);
-        /* hop codes of the cell's faces, fetched together with the geometry (no dependent load) */
-        const int4 codes = __ldg(reinterpret_cast<const int4*>(geo + NF * 6));
-        /* (the code load above touches the tail of the record, so both of its cache lines are in flight
-         *  before the first face is evaluated) */
+        /* The packed cell records are stored in BLOCKS of 8 cells, chunk-major inside a block (pgpu_internal.cuh
+         * PG_GEO_*): chunk k (16 bytes) of the 8 cells of a block forms one 128-byte line.  After their first hop
+         * the lanes of a warp sit in different cells, every load instruction costs one L1 wavefront per distinct
+         * LINE it touches, and this kernel is bound by exactly that pipe (ncu: l1tex__data_pipe_lsu_wavefronts
+         * ~75 % with cell-major records).  Neighbouring cells are numbered close to each other by any mesh
+         * generator, so with this layout lanes in nearby cells share their wavefronts.  The hop codes ride in the
+         * last chunk of the record (no dependent load). */
+        constexpr int NCH = PG_GEO_CHUNKS(NF);
+        const char* gb = pg_geo_base(d.face_geo, ic - 1, NCH);
+        double G[NF * 6];
+        if (!AXI) {
+#pragma unroll
+            for (int k = 0; k < NF * 3; k++) {
+                const double2 v = __ldg(reinterpret_cast<const double2*>(gb + k * PG_GEO_LINE));
+                G[2 * k] = v.x; G[2 * k + 1] = v.y;
+            }
+        }
+        const int4 codes = __ldg(reinterpret_cast<const int4*>(gb + (NF * 3) * PG_GEO_LINE));
         int codesel = 0; /* hop code of the face selected so far (a predicated move per face, no branch) */
         double nsel[3] = {0., 0., 0.};
         if (AXI) {
@@ -449,8 +462,8 @@ __device__ __forceinline__ int unstructured_iter(const PgDev& d, PgRng& g, PStat
             for (int i = 0; i < 3; i++) {
                 double test[2];
                 int goodsol;
-                double n1 = __ldg(&geo[6 * i + 0]), n2 = __ldg(&geo[6 * i + 1]);
-                double ex1 = __ldg(&geo[6 * i + 3]), ey1 = __ldg(&geo[6 * i + 4]);
+                double n1 = pg_geo_at(gb, 6 * i + 0), n2 = pg_geo_at(gb, 6 * i + 1);
+                double ex1 = pg_geo_at(gb, 6 * i + 3), ey1 = pg_geo_at(gb, 6 * i + 4);
                 if (fabs(n2) < 1.e-10) {
                     double sol1 = (ex1 - q.x) / q.vx;
                     if (sol1 >= 0 && sol1 < dtcoll) { goodsol = 1; test[0] = sol1; }
@@ -486,25 +499,46 @@ __device__ __forceinline__ int unstructured_iter(const PgDev& d, PgRng& g, PStat
             double vn[NF], dx[NF];
 #pragma unroll
             for (int i = 0; i < NF; i++) {
+                const double* f = &G[6 * i]; /* (nx, ny, nz, px, py, pz) of face i */
                 if (DIMS == 1) {
-                    double n1 = __ldg(&geo[6 * i + 0]);
-                    double p1 = __ldg(&geo[6 * i + 3]);
-                    vn[i] = q.vx * n1;
-                    dx[i] = (p1 - q.x) * n1;
+                    vn[i] = q.vx * f[0];
+                    dx[i] = (f[3] - q.x) * f[0];
                 } else if (DIMS == 2) {
-                    double2 n12 = __ldg(reinterpret_cast<const double2*>(&geo[6 * i + 0]));
-                    double p1 = __ldg(&geo[6 * i + 3]), p2 = __ldg(&geo[6 * i + 4]);
-                    vn[i] = q.vx * n12.x + q.vy * n12.y;
-                    dx[i] = (p1 - q.x) * n12.x + (p2 - q.y) * n12.y;
+                    vn[i] = q.vx * f[0] + q.vy * f[1];
+                    dx[i] = (f[3] - q.x) * f[0] + (f[4] - q.y) * f[1];
                 } else {
-                    double2 a = __ldg(reinterpret_cast<const double2*>(&geo[6 * i + 0]));
-                    double2 b = __ldg(reinterpret_cast<const double2*>(&geo[6 * i + 2]));
-                    double2 c = __ldg(reinterpret_cast<const double2*>(&geo[6 * i + 4]));
-                    /* a = (nx,ny) b = (nz,px) c = (py,pz) */
-                    vn[i] = q.vx * a.x + q.vy * a.y + q.vz * b.x;
-                    dx[i] = (b.y - q.x) * a.x + (c.x - q.y) * a.y + (c.y - q.z) * b.x;
+                    vn[i] = q.vx * f[0] + q.vy * f[1] + q.vz * f[2];
+                    dx[i] = (f[3] - q.x) * f[0] + (f[4] - q.y) * f[1] + (f[5] - q.z) * f[2];
                 }
             }
+#if PG_ADV_PARDIV
+            /* The quotient DX/VN of a face does not depend on the faces before it either, only the DECISION to
+             * take it does (through DTCOLL).  DTCOLL only ever shrinks from DTRIM and VN >= 0, so by monotonicity
+             * of the rounded product  VN*DTCOLL >= DX  implies  VN*DTRIM >= DX : the faces that can be taken are
+             * known up front, their four divisions are independent (in flight together instead of chained through
+             * DTCOLL), and the sequential tightening is left with a multiply and a compare per face.  Lanes that
+             * cannot take a face divide 1/1: a particle that has just crossed a face sits EXACTLY on it (dx == 0),
+             * which would send the whole warp through the slow path of the FP64 division for a discarded result.
+             * Same operations on the same operands as the reference for every face that is taken. */
+            double quo[NF];
+            bool cand[NF];
+            const double dt0 = dtcoll;
+#pragma unroll
+            for (int i = 0; i < NF; i++) {
+                cand[i] = (vn[i] >= 0. && vn[i] * dt0 >= dx[i]);
+                double num = cand[i] ? dx[i] : 1., den = cand[i] ? vn[i] : 1.;
+                asm("" : "+d"(num), "+d"(den)); /* opaque: keeps the selects in front of the division */
+                quo[i] = num / den;
+            }
+#pragma unroll
+            for (int i = 0; i < NF; i++) {
+                const bool take = cand[i] && (vn[i] * dtcoll >= dx[i]);
+                if (take) {
+                    dtcoll = quo[i]; boundcoll = i;
+                    codesel = (i == 0) ? codes.x : (i == 1) ? codes.y : (i == 2) ? codes.z : codes.w;
+                }
+            }
+#else
 #pragma unroll
             for (int i = 0; i < NF; i++) {
                 /* The compiler evaluates the quotient for every lane and selects; a particle that has just
@@ -521,10 +555,11 @@ __device__ __forceinline__ int unstructured_iter(const PgDev& d, PgRng& g, PStat
                     codesel = (i == 0) ? codes.x : (i == 1) ? codes.y : (i == 2) ? codes.z : codes.w;
                 }
             }
+#endif
             if (!LEAN && boundcoll != -1) { /* outward normal of the face that was hit (boundary models) */
-                nsel[0] = __ldg(&geo[6 * boundcoll + 0]);
-                nsel[1] = (DIMS >= 2) ? __ldg(&geo[6 * boundcoll + 1]) : 0.;
-                nsel[2] = (DIMS >= 3) ? __ldg(&geo[6 * boundcoll + 2]) : 0.;
+                nsel[0] = pg_geo_at(gb, 6 * boundcoll + 0);
+                nsel[1] = (DIMS >= 2) ? pg_geo_at(gb, 6 * boundcoll + 1) : 0.;
+                nsel[2] = (DIMS >= 3) ? pg_geo_at(gb, 6 * boundcoll + 2) : 0.;
             }
         }
 
@@ -532,11 +567,6 @@ __device__ __forceinline__ int unstructured_iter(const PgDev& d, PgRng& g, PStat
             const int code = codesel;
             if (code > 0) {
                 /* ref: :1311-1312, :1648-1652 cell hop */
-                if (LEAN) { /* the record of the next cell is needed a whole loop trip from now: start it early */
-                    const double* nx = d.face_geo + (size_t)(code - 1) * (NF * 6 + 2);
-                    asm volatile("prefetch.global.L1 [%0];" ::"l"(nx));
-                    asm volatile("prefetch.global.L1 [%0];" ::"l"(nx + NF * 6));
-                }
                 move_particle<AXI>(q, dtcoll);
                 q.dtrim = q.dtrim - dtcoll;
                 q.ic = code;
@@ -816,9 +846,8 @@ struct PendingRank {
 };
 __device__ __forceinline__ void store_particle(const PgDev& d, long long slot, const PState& q, int dirty, unsigned int peers,
                                                PendingRank& pr) {
-    PgPos P;
-    P.x = q.x; P.y = q.y; P.z = q.z; P.ic = q.ic; P.sid = q.sid;
-    d.p.pos[slot] = P;
+    /* one 256-bit store (the compiler splits a struct assignment with int members into three stores) */
+    pg_store_sector(d.p.pos + slot, q.x, q.y, q.z, q.ic, q.sid);
     if (dirty & (DIRTY_V | DIRTY_S)) {
         PgVel V;
         V.vx = q.vx; V.vy = q.vy; V.vz = q.vz; V.sid = q.sid; V.pad = 0;
@@ -870,19 +899,38 @@ __global__ void __launch_bounds__(128, PG_ADVECT_MINBLOCKS) advect_lean_kernel(c
     PendingRank pr;
     pr.mask = 0u;
 
+#if PG_ADV_PF
+    long long pf = next; /* slots below pf have been requested into L1 */
+#endif
     for (;;) {
+#if !PG_ADV_LATECOMMIT
         /* rank of the particle stored in the previous trip (its atomic has had a whole trip to return) */
         if (pr.mask) { commit_rank(d, pr); pr.mask = 0u; }
+#endif
+#if PG_ADV_PF
+        /* keep the records of the next 64..96 slots of the chunk on their way into L1: a refill (below) then
+         * costs an L1 hit instead of an exposed trip to L2/HBM.  One line-sized request per lane. */
+        if (pf < end && pf < next + 64) {
+            const long long s = pf + lane;
+            if (s < end) {
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(d.p.pos + s));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(d.p.vel + s));
+            }
+            pf += 32;
+        }
+#endif
         /* refill: idle lanes take the next slots of the chunk, in order */
         unsigned int idle = __ballot_sync(FULL, !have);
         if (idle && next < end) {
             long long my = next + __popc(idle & ((1u << lane) - 1u));
             if (!have && my < end) {
                 slot = my;
+#if !PG_ADV_PF
                 if (my + 64 < end) { /* the records this lane is likely to take two refills from now */
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(d.p.pos + my + 64));
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(d.p.vel + my + 64));
                 }
+#endif
                 have = load_particle(d, slot, q, dirty);
                 hops = 0;
                 if (MODE == 0) { bhits[0] = bhits[1] = bhits[2] = bhits[3] = 0; }
@@ -890,6 +938,9 @@ __global__ void __launch_bounds__(128, PG_ADVECT_MINBLOCKS) advect_lean_kernel(c
             next += __popc(idle);
         }
         if (!__any_sync(FULL, have)) {
+#if PG_ADV_LATECOMMIT
+            if (pr.mask) { commit_rank(d, pr); pr.mask = 0u; }
+#endif
             if (next >= end) break; /* (nothing pending: a trip that stored something refills or ends here first) */
             continue;
         }
@@ -920,6 +971,11 @@ __global__ void __launch_bounds__(128, PG_ADVECT_MINBLOCKS) advect_lean_kernel(c
             if (!keep) tombstone_particle(d, slot);
         }
         unsigned int fm = __ballot_sync(FULL, keep);
+#if PG_ADV_LATECOMMIT
+        /* rank of the particle stored in the previous trip: its atomic has had this whole trip (a refill and a
+         * cell crossing) to return, so the read of its result does not stall the warp */
+        if (pr.mask) { commit_rank(d, pr); pr.mask = 0u; }
+#endif
         if (keep) {
             if (MODE == 0) { /* the species cannot change in the LEAN pass */
                 for (int b = 0; b < 4; b++)

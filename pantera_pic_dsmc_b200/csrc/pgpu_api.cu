@@ -21,7 +21,7 @@ enum {
     S_SIGMAS, S_OMEGAS, S_ALPHAS, S_GREFS,
     S_REAC, S_TAB_E, S_TAB_CS,
     S_WR_R, S_WR_P1, S_WR_NPROD, S_WR_PROB,
-    S_MCC_SP, S_MCC_FRAC,
+    S_MCC_SP, S_MCC_FRAC, S_MCC_CELL_NRHO,
     S_FACE_GEO, S_FACE_CODE, S_TANG1, S_TANG2, S_EDGE_LEN, S_FACE_BIDX, S_BOUND_AREA, S_CELL_NODES, S_BASIS,
     S_CELL_VOL, S_CELL_PROCS,
     S_BC_PARTICLE, S_BC_FIELD, S_BC_REACT, S_BC_TEMP, S_BC_ACCN, S_BC_ACCT,
@@ -303,6 +303,23 @@ extern "C" int pgpu_set_mcc_background(pgpu_ctx* c, int ncomp, const int32_t* sp
     return PGPU_OK;
 }
 
+/* MCC_BG_CELL_NRHO(SP_ID, IC), ref: src/initialization.f90:2752-2788 (BOOL_BG_DENSITY_FILE); nrho == NULL clears it */
+extern "C" int pgpu_set_mcc_cell_density(pgpu_ctx* c, int ns, int64_t nc, const double* nrho) {
+    if (!c) return PGPU_ERR_INVALID;
+    cudaSetDevice(c->device);
+    int rc;
+    if (!nrho || ns <= 0 || nc <= 0) {
+        if ((rc = put(c, S_MCC_CELL_NRHO, (const double*)nullptr, 0, &c->dev.mcc_cell_nrho))) return rc;
+        c->dev.mcc_cell_nrho = nullptr;
+        c->mcc_cell_nrho_cells = 0;
+        return PGPU_OK;
+    }
+    if (c->ns && ns != c->ns) PG_FAIL(c, PGPU_ERR_INVALID, "set_mcc_cell_density: ns %d != %lld species", ns, (long long)c->ns);
+    if ((rc = put(c, S_MCC_CELL_NRHO, nrho, (size_t)ns * (size_t)nc, &c->dev.mcc_cell_nrho))) return rc;
+    c->mcc_cell_nrho_cells = nc;
+    return PGPU_OK;
+}
+
 extern "C" int pgpu_set_mesh(pgpu_ctx* c, int dims, int nn, int nc, const double* node_coords,
                              const int32_t* cell_nodes, const int32_t* cell_neighbors, const double* face_normal,
                              const double* face_tang1, const double* face_tang2, const double* cell_edges_len,
@@ -461,18 +478,21 @@ extern "C" int pgpu_set_surface_charge(pgpu_ctx* c, const double* sc, int64_t n)
  * ---------------------------------------------------------------------------------------- */
 static int build_packed_mesh(pgpu_ctx* c) {
     int nf = c->mesh_dims + 1, nc = c->nc, rc;
-    const int gs = nf * 6 + 2; /* doubles per cell record: nf x {normal, point} + 16 bytes of hop codes */
-    std::vector<double> geo((size_t)nc * gs, 0.0);
+    /* blocks of 8 cells, chunk-major inside a block (pgpu_internal.cuh PG_GEO_*) */
+    const int bd = PG_GEO_BLOCK_DOUBLES(nf);
+    std::vector<double> geo((size_t)((nc + 7) / 8) * bd, 0.0);
+    auto slot = [&](int ic, int e) -> double* { /* double e of cell ic's record */
+        return &geo[(size_t)(ic >> 3) * bd + (size_t)(e >> 1) * 16 + (size_t)(ic & 7) * 2 + (e & 1)];
+    };
     std::vector<int> code((size_t)nc * nf);
     const int nbc = (int)c->h_bc_volume.size();
     for (int ic = 0; ic < nc; ic++) {
         for (int j = 0; j < nf; j++) {
             size_t f = (size_t)ic * nf + j;
             int v = c->h_cell_nodes[f];
-            double* g = &geo[(size_t)ic * gs + 6 * j];
             for (int k = 0; k < 3; k++) {
-                g[k] = c->h_face_normal[3 * f + k];
-                g[3 + k] = c->h_node_coords[3 * (size_t)(v - 1) + k];
+                *slot(ic, 6 * j + k) = c->h_face_normal[3 * f + k];
+                *slot(ic, 6 * j + 3 + k) = c->h_node_coords[3 * (size_t)(v - 1) + k];
             }
             int nb = c->h_cell_neighbors[f];
             bool fluidboundary = false;
@@ -498,7 +518,7 @@ static int build_packed_mesh(pgpu_ctx* c) {
         }
     }
     for (int ic = 0; ic < nc; ic++) /* the hop codes ride in the same record: no dependent load in the face walk */
-        memcpy(&geo[(size_t)ic * gs + 6 * nf], &code[(size_t)ic * nf], sizeof(int) * (size_t)nf);
+        memcpy(slot(ic, 6 * nf), &code[(size_t)ic * nf], sizeof(int) * (size_t)nf);
     if ((rc = put(c, S_FACE_GEO, geo.data(), geo.size(), &c->dev.face_geo))) return rc;
     if ((rc = put(c, S_FACE_CODE, code.data(), code.size(), &c->dev.face_code))) return rc;
     c->mesh_dirty = false;
@@ -1051,7 +1071,8 @@ extern "C" int pgpu_exchange(pgpu_ctx* c) {
     return rc;
 }
 
-int pg_mcc_impl(pgpu_ctx* c, int tID); /* pgpu_pic_mcc.cu */
+int pg_mcc_impl(pgpu_ctx* c, int tID);     /* pgpu_pic_mcc.cu */
+int pg_mcc_vss_impl(pgpu_ctx* c, int tID); /* pgpu_collide.cu */
 
 /* nsteps x [ADVECT -> EXCHANGE -> collisions], ref: src/timecycle.f90:271-299 */
 extern "C" int pgpu_run_steps(pgpu_ctx* c, int32_t tID0, int32_t nsteps, int64_t* total_coll, int64_t* total_reac) {
@@ -1059,8 +1080,8 @@ extern "C" int pgpu_run_steps(pgpu_ctx* c, int32_t tID0, int32_t nsteps, int64_t
     int rc;
     if ((rc = pg_prepare(c))) return rc;
     if (c->cfg.collision_type == PGPU_DSMC && !c->dev.sigmas) PG_FAIL(c, PGPU_ERR_STATE, "pgpu_run_steps: VSS parameters not set");
-    if (c->cfg.collision_type == PGPU_BGK || c->cfg.collision_type == PGPU_DSMC_VAHEDI || c->cfg.collision_type == PGPU_MCC)
-        PG_FAIL(c, PGPU_ERR_UNSUPPORTED, "pgpu_run_steps: collision type %d is outside the hot path (SURVEY 2.1 rows 22, 24, 25)", c->cfg.collision_type);
+    if (c->cfg.collision_type == PGPU_BGK || c->cfg.collision_type == PGPU_DSMC_VAHEDI)
+        PG_FAIL(c, PGPU_ERR_UNSUPPORTED, "pgpu_run_steps: collision type %d is outside the hot path (SURVEY 2.1 rows 22, 25)", c->cfg.collision_type);
     reset_timings(c);
     int64_t tc = 0, tr = 0;
     cudaEvent_t e0 = c->ev[12], e1 = c->ev[13];
@@ -1078,12 +1099,14 @@ extern "C" int pgpu_run_steps(pgpu_ctx* c, int32_t tID0, int32_t nsteps, int64_t
         }
         bool dsmc = c->cfg.collision_type == PGPU_DSMC;
         bool mcc = c->cfg.collision_type == PGPU_MCC_VAHEDI;
+        bool mccv = c->cfg.collision_type == PGPU_MCC;
         tic(c, 1);
         if ((rc = pg_sort_impl(c))) return rc;
         toc(c, 1);
         tic(c, 2);
         if (dsmc && (rc = pg_collide_impl(c, tID))) return rc;
         if (mcc && (rc = pg_mcc_impl(c, tID))) return rc;
+        if (mccv && (rc = pg_mcc_vss_impl(c, tID))) return rc;
         toc(c, 2);
         rc = pg_finish(c, "pgpu_run_steps");
         collect(c, 0); collect(c, 1); collect(c, 2);

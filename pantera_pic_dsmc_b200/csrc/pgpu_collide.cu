@@ -119,7 +119,9 @@ __device__ __forceinline__ bool pair_accept(const PgDev& d, double rfp, const do
 
 /* an ACCEPTED candidate: reactions, Borgnakke-Larsen, VSS deflection, ref: src/collisions.f90:327-546.
  * g continues the candidate's stream right after the acceptance draw. */
-__device__ int pair_collide(const PgDev& d, PgRng& g, PairIO& p, long long gslot2, int cell0) {
+/* gate_all: MCC_COLLISIONS skips a reaction whose activation energy is not exceeded whatever its type
+ * (ref: :1383-1384); VSS_COLLIS applies that test to TCE reactions only (ref: :349-350). */
+__device__ int pair_collide(const PgDev& d, PgRng& g, PairIO& p, long long gslot2, int cell0, bool gate_all = false) {
     const double PI2 = 2. * PG_PI;
     double* c1 = p.c1;
     double* c2 = p.c2;
@@ -149,6 +151,7 @@ __device__ int pair_collide(const PgDev& d, PgRng& g, PairIO& p, long long gslot
             if (r.r2 != s2) continue;
         }
         double ea = r.ea, ptce;
+        if (gate_all && ecoll <= ea) continue;
         if (r.type == PGPU_TCE) {
             if (ecoll <= ea) continue;
             ptce = r.c1 * pow(ecoll - ea, r.c2) * pow(1. - ea / ecoll, r.c3);
@@ -408,6 +411,68 @@ __global__ void __launch_bounds__(128, PG_CELL_MINBLOCKS) cell_collide_kernel(co
         if (nacc) atomicAdd(&d.status->ncoll, (unsigned long long)nacc);
         if (nreac) atomicAdd(&d.status->nreac, (unsigned long long)nreac);
     }
+}
+
+/* ==========================================================================================
+ * MCC_COLLISIONS (VSS cross-section MCC against a background gas), ref: src/collisions.f90:1261-1595.
+ * One thread per particle present at entry: per background component a partner is sampled from the background
+ * Maxwellian (:1314-1316), the collision is accepted with P = 1 - exp(-DT n VR sigma (VR/CREF)^(1-2w)) (:1327),
+ * and an accepted partner becomes a real particle (:1344-1351) that goes with the particle through the same
+ * reaction / Borgnakke-Larsen / VSS code as a DSMC pair.  Everything is per particle, so there is no ordering
+ * to preserve beyond the particle's own draw sequence: Philox stream kind 4 keyed by the slot.
+ * ======================================================================================== */
+__global__ void __launch_bounds__(128) mcc_vss_kernel(const __grid_constant__ PgDev d) {
+    long long jp1 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (jp1 >= d.np) return;
+    const PgPos P1 = d.p.pos[jp1];
+    const int ic = P1.ic;
+    if (ic < 1) return;
+    PgRng g;
+    g.init(d.seed_local, 4, d.tID, (unsigned long long)jp1, 0ULL);
+    const int sp1 = P1.sid; /* SP_ID1 is read once (:1291) and NOT refreshed after a reaction */
+    int sid_now = sp1;
+    const PgVel V1 = d.p.vel[jp1];
+    const PgIe E1 = d.p.ie[jp1];
+    PairIO p;
+    p.c1[0] = V1.vx; p.c1[1] = V1.vy; p.c1[2] = V1.vz;
+    p.erot1 = E1.erot; p.evib1 = E1.evib;
+    int dirty = 0, ncoll = 0, nreac = 0;
+    for (int j = 0; j < d.mcc_ncomp; j++) {
+        const int s2 = d.mcc_sp[j];
+        double bg_nrho;
+        if (d.mcc_cell_nrho) bg_nrho = __ldg(&d.mcc_cell_nrho[(s2 - 1) + (size_t)d.ns * (size_t)(ic - 1)]); /* :1296-1297 */
+        else bg_nrho = d.mcc_frac[j] * d.mcc_dens;                                                           /* :1299-1300 */
+        if (bg_nrho == 0) continue;
+        const double cref = VSS2(d.grefs, sp1, s2), sigma = VSS2(d.sigmas, sp1, s2), omega = VSS2(d.omegas, sp1, s2);
+        pg_maxwell0(g, d.mcc_ttra, d.mass[s2 - 1], p.c2);
+        const double vr2 = (p.c2[0] - p.c1[0]) * (p.c2[0] - p.c1[0]) + (p.c2[1] - p.c1[1]) * (p.c2[1] - p.c1[1]) +
+                           (p.c2[2] - p.c1[2]) * (p.c2[2] - p.c1[2]);
+        const double vr = sqrt(vr2);
+        const double p_coll = 1 - exp(-d.dt * bg_nrho * vr * sigma * pow(vr / cref, 1. - 2. * omega));
+        if (!(g.rf() < p_coll)) continue;
+        ncoll++;
+        p.erot2 = pg_internal_energy(g, d.rotdof[s2 - 1], d.mcc_ttra);
+        p.evib2 = pg_internal_energy(g, d.vibdof[s2 - 1], d.mcc_ttra);
+        p.s1 = sp1;
+        p.s2 = s2;
+        /* the partner sits at the particle's own position and cell (:1346-1347), which is where a third
+         * product is created (:1478-1479) */
+        const int fl = pair_collide(d, g, p, jp1, ic - 1, true);
+        if (fl & PR_REACTED) nreac++;
+        if (fl & PR_S) sid_now = p.s1;
+        dirty |= fl;
+        /* the partner is appended with its final state; the reference appends it first and then edits it */
+        pg_append_particle(d, P1.x, P1.y, P1.z, p.c2[0], p.c2[1], p.c2[2], p.erot2, p.evib2, p.s2, ic);
+    }
+    if (dirty & (PR_V | PR_S)) {
+        PgVel W;
+        W.vx = p.c1[0]; W.vy = p.c1[1]; W.vz = p.c1[2]; W.sid = sid_now; W.pad = 0;
+        d.p.vel[jp1] = W;
+    }
+    if (dirty & PR_E1) { PgIe E; E.erot = p.erot1; E.evib = p.evib1; d.p.ie[jp1] = E; }
+    if (dirty & PR_S) d.p.pos[jp1].sid = sid_now;
+    if (ncoll) atomicAdd(&d.status->ncoll, (unsigned long long)ncoll);
+    if (nreac) atomicAdd(&d.status->nreac, (unsigned long long)nreac);
 }
 
 /* ==========================================================================================
@@ -680,4 +745,41 @@ int pg_collide_impl(pgpu_ctx* c, int tID) {
     if (c->n_big > 0 && (rc = collide_big_cells(c))) return rc;
     c->hist_valid = false;
     return PGPU_OK;
+}
+
+/* MCC_COLLISIONS for all slots [0, np); products and partners go to the append region */
+int pg_mcc_vss_impl(pgpu_ctx* c, int tID) {
+    if (!c->dev.mcc_ncomp) PG_FAIL(c, PGPU_ERR_STATE, "mcc_collisions: background mixture not set");
+    if (!c->dev.sigmas) PG_FAIL(c, PGPU_ERR_STATE, "mcc_collisions: VSS tables not set");
+    if (c->dev.mcc_cell_nrho && c->mcc_cell_nrho_cells < (int64_t)pg_ncells(c))
+        PG_FAIL(c, PGPU_ERR_STATE, "mcc_collisions: background density table covers %lld of %d cells",
+                (long long)c->mcc_cell_nrho_cells, pg_ncells(c));
+    if (c->np == 0) return PGPU_OK;
+    c->dev.tID = tID;
+    pg_refresh_dev(c);
+    mcc_vss_kernel<<<(unsigned int)((c->np + 127) / 128), 128, 0, c->stream>>>(c->dev);
+    c->launches++;
+    PG_CUDA(c, cudaGetLastError());
+    c->sorted = false;
+    c->hist_valid = false;
+    return PGPU_OK;
+}
+
+extern "C" int pgpu_mcc_collisions(pgpu_ctx* c, int32_t tID, int64_t* timestep_coll, int64_t* timestep_reac) {
+    if (!c) return PGPU_ERR_INVALID;
+    int rc;
+    if ((rc = pg_prepare(c))) return rc;
+    memset(c->ms, 0, sizeof(c->ms));
+    c->launches = 0;
+    if ((rc = pg_reset_status(c))) return rc;
+    cudaEventRecord(c->ev[4], c->stream);
+    if ((rc = pg_mcc_vss_impl(c, tID))) return rc;
+    cudaEventRecord(c->ev[5], c->stream);
+    rc = pg_finish(c, "pgpu_mcc_collisions");
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]) == cudaSuccess) c->ms[2] = ms;
+    c->ms[5] = c->ms[2];
+    if (timestep_coll) *timestep_coll = (int64_t)c->h_status->ncoll;
+    if (timestep_reac) *timestep_reac = (int64_t)c->h_status->nreac;
+    return rc;
 }

@@ -60,6 +60,17 @@
 #ifndef PG_ADVECT_CHUNK
 #define PG_ADVECT_CHUNK 256
 #endif
+/* independent face divisions in the unstructured face walk (pgpu_advect.cu) */
+#ifndef PG_ADV_PARDIV
+#define PG_ADV_PARDIV 1
+#endif
+/* LEAN advect: commit the arrival rank at the end of the NEXT trip; warp-wide L1 prefetch of upcoming slots */
+#ifndef PG_ADV_LATECOMMIT
+#define PG_ADV_LATECOMMIT 1
+#endif
+#ifndef PG_ADV_PF
+#define PG_ADV_PF 1
+#endif
 #define PG_MAX_HOPS 1000000 /* guard against a malformed mesh hanging the GPU */
 
 /* status block, device resident, read back at the end of every hot-path call */
@@ -83,6 +94,30 @@ enum { PG_DEVERR_NONE = 0, PG_DEVERR_HOPS = 1, PG_DEVERR_CELL_RANGE = 2, PG_DEVE
 struct __align__(32) PgPos { double x, y, z; int ic, sid; };
 struct __align__(32) PgVel { double vx, vy, vz; int sid, pad; };
 struct __align__(16) PgIe { double erot, evib; };
+/* Packed cell records (pgpu_api.cu build_packed_mesh): per face {outward normal(3), point(3)} = nf*6 doubles, then
+ * 16 bytes of hop codes, cut into 16-byte chunks (tetrahedron 13, triangle 10, segment 7).  Cells are stored in
+ * blocks of 8, chunk-major inside the block: chunk k of the block's 8 cells is one 128-byte line, so that lanes
+ * working in nearby cells share their L1 wavefronts (see pgpu_advect.cu unstructured_iter). */
+#define PG_GEO_LINE 128
+#define PG_GEO_CHUNKS(nf) ((nf) * 3 + 1)
+#define PG_GEO_BLOCK_DOUBLES(nf) (PG_GEO_CHUNKS(nf) * 16)
+#ifdef __CUDACC__
+/* address of chunk 0 of cell cell0 (0-based) */
+__device__ __forceinline__ const char* pg_geo_base(const double* geo, int cell0, int nch) {
+    return reinterpret_cast<const char*>(geo) + (size_t)(cell0 >> 3) * (size_t)(nch * PG_GEO_LINE) + (size_t)((cell0 & 7) * 16);
+}
+/* a 32-byte particle record {3 doubles, 2 ints} as ONE 256-bit store (STG.E.ENL2.256) */
+__device__ __forceinline__ void pg_store_sector(void* p, double a, double b, double c, int i0, int i1) {
+    const unsigned long long w = ((unsigned long long)(unsigned int)i1 << 32) | (unsigned long long)(unsigned int)i0;
+    asm volatile("st.global.v4.b64 [%0], {%1,%2,%3,%4};" ::"l"(p), "l"(__double_as_longlong(a)),
+                 "l"(__double_as_longlong(b)), "l"(__double_as_longlong(c)), "l"(w)
+                 : "memory");
+}
+/* double e of the record (e = 6*face + {0,1,2: normal, 3,4,5: point}) */
+__device__ __forceinline__ double pg_geo_at(const char* gb, int e) {
+    return __ldg(reinterpret_cast<const double*>(gb + (e >> 1) * PG_GEO_LINE + (e & 1) * 8));
+}
+#endif
 
 struct PgPlanes {
     PgPos* pos;
@@ -132,9 +167,10 @@ struct PgDev {
     int mcc_ncomp;
     const int* mcc_sp;
     const double* mcc_frac;
+    const double* mcc_cell_nrho; /* [nc][ns] MCC_BG_CELL_NRHO(SP_ID, IC) or null */
     /* --- unstructured mesh, device layout --- */
     int nn, nc, nf;
-    const double* face_geo;  /* [nc][nf*6+2]: per face outward normal (3) + a point on the face (3), then the
+    const double* face_geo;  /* [ceil(nc/8)] blocks of PG_GEO_BLOCK_DOUBLES(nf): per face outward normal (3) + a point on the face (3), then the
                                 nf hop codes of face_code as int32 (16 bytes) */
     const int* face_code;    /* [nc][nf]: >0 neighbour cell to hop into; 0 boundary without a physical
                                 group (remove); <0 boundary with physical group -code        */
@@ -205,6 +241,7 @@ struct pgpu_ctx {
 
     /* raw host copies needed to (re)build the packed mesh when BCs change */
     int mesh_dims, nn, nc;
+    int64_t mcc_cell_nrho_cells = 0; /* cells covered by dev.mcc_cell_nrho */
     std::vector<double> h_node_coords, h_face_normal;
     std::vector<int32_t> h_cell_nodes, h_cell_neighbors, h_cell_faces_pg, h_cell_pg;
     std::vector<int32_t> h_bc_volume;

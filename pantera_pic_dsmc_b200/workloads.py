@@ -31,6 +31,7 @@ class Workload:
     wall_reactions: Optional[dict] = None
     walls: Optional[dict] = None
     mcc_background: Optional[tuple] = None
+    mcc_cell_density: Optional[np.ndarray] = None
     efield: Optional[np.ndarray] = None
     notes: str = ""
 
@@ -44,6 +45,7 @@ def apply(lib: capi.Lib, w: Workload, upload: bool = True):
         lib.set_wall_reactions(**w.wall_reactions)
     if w.mcc_background:
         lib.set_mcc_background(*w.mcc_background)
+    lib.set_mcc_cell_density(w.mcc_cell_density)
     if w.mesh is not None:
         lib.set_mesh(w.mesh)
     if w.bcs:
@@ -195,6 +197,38 @@ def c2_air_box(n: int = 50_000, nx: int = 4, ny: int = 4, seed: int = 3, T: floa
     p["DTRIM"] = dt
     p["IC"] = (p["X"] * nx).astype(np.int32) + nx * (p["Y"] * ny).astype(np.int32) + 1
     return Workload("C2 air TCE/BL box", cfg, sp, p, reactions=reactions)
+
+
+def mcc_box(kind: str = "ar", n: int = 40_000, nx: int = 4, ny: int = 4, seed: int = 11, T: float = 3000.0,
+            bg_T: float = 300.0, bg_dens: float = 2e21, dt: float = 2e-7, cell_density: bool = False,
+            rng_seed_global: int = 65644) -> Workload:
+    """Test particles in a periodic box colliding with a background gas through MCC_COLLISIONS
+    (Collision_type: MCC, src/collisions.f90:1261-1595).  kind "ar": argon in argon (elastic VSS only);
+    kind "air": O2/N2/O/N/NO test particles in an O2/N2 background with the TCE reactions of data/air.tce and
+    Borgnakke-Larsen exchange.  cell_density: per-cell background (BOOL_BG_DENSITY_FILE) with empty cells."""
+    if kind == "ar":
+        w = c1_argon_box(n, nx=nx, ny=ny, seed=seed, T=(T, T, T))
+        sp = w.species
+        bg = ([sp.id("Ar")], [1.0])
+    else:
+        w = c2_air_box(n, nx=nx, ny=ny, seed=seed, T=T, dt=dt, frac=(0.2, 0.5, 0.1, 0.1, 0.1))
+        sp = w.species
+        bg = ([sp.id("O2"), sp.id("N2")], [0.21, 0.79])
+    w.cfg.collision_type = capi.MCC
+    w.cfg.mcc_bg_dens = bg_dens
+    w.cfg.mcc_bg_ttra = bg_T
+    w.cfg.dt = dt
+    w.cfg.rng_seed_global = rng_seed_global
+    w.particles["DTRIM"] = dt
+    w.mcc_background = bg
+    if cell_density:
+        nc = nx * ny
+        dens = np.zeros((len(sp.mass), nc), order="F")
+        for k, s in enumerate(bg[0]):
+            dens[s - 1, :] = bg[1][k] * bg_dens * (np.arange(nc) % 3)   # every third cell is empty
+        w.mcc_cell_density = dens
+    w.name = f"MCC {kind} box"
+    return w
 
 
 # ------------------------------------------------------------------------------------------------

@@ -144,6 +144,42 @@ def test_mcc_vahedi_value_for_value(gpu, oracle_philox):
         assert np.allclose(ao[f], ag[f], rtol=1e-10, atol=1e-7)
 
 
+@pytest.mark.parametrize("kind,cell_density", [("ar", False), ("ar", True), ("air", False)])
+def test_mcc_collisions_value_for_value(gpu, oracle_philox, kind, cell_density):
+    """MCC_COLLISIONS (collisions.f90:1261-1595): same Philox stream per particle on both
+    sides -> the same particles collide, the same partners/products are created, velocities and internal
+    energies agree to 1e-10 (libm pow/exp/sincos differ by a few ulp)."""
+    if kind == "ar":
+        w = wl.mcc_box("ar", n=40_000, cell_density=cell_density)
+    else:
+        w = wl.mcc_box("air", n=40_000, T=15000.0, bg_dens=5e21)
+    util.setup_pair(gpu, oracle_philox, w)
+    n0 = len(w.particles)
+    co, cg = oracle_philox.mcc_collisions(7), gpu.mcc_collisions(7)
+    assert co == cg and cg[0] > 1000
+    if kind == "air":
+        assert cg[1] > 20
+    po, pg = oracle_philox.download_particles(), gpu.download_particles()
+    assert len(po) == len(pg) > n0
+    util.assert_particles_match(util.by_id(po[:n0]), util.by_id(pg[pg["ID"] < (n0 << 8)]), rtol=1e-10, atol=1e-9,
+                                what="MCC-VSS existing")
+    key = lambda p: np.lexsort((p["VZ"], p["VY"], p["VX"], p["S_ID"], p["X"]))
+    ao, ag = po[n0:], pg[pg["ID"] >= (n0 << 8)]
+    ao, ag = ao[key(ao)], ag[key(ag)]
+    assert np.array_equal(ao["S_ID"], ag["S_ID"]) and np.array_equal(ao["X"], ag["X"]) and np.array_equal(ao["IC"], ag["IC"])
+    for f in ("VX", "VY", "VZ", "EROT", "EVIB"):
+        assert np.allclose(ao[f], ag[f], rtol=1e-9, atol=1e-7 if f[0] == "V" else 1e-30), f
+
+
+def test_run_steps_mcc_collision_type(gpu, oracle_philox):
+    """Collision_type MCC inside the step loop (timecycle.f90:288-296): ADVECT -> sort -> MCC_COLLISIONS."""
+    w = wl.mcc_box("ar", n=20_000)
+    util.setup_pair(gpu, oracle_philox, w)
+    cg = gpu.run_steps(1, 2)
+    assert cg[0] > 100 and cg[1] == 0
+    assert gpu.num_particles() == len(w.particles) + cg[0]
+
+
 def test_remove_species(gpu, oracle_philox):
     w = wl.c4_ccp_1d(16, 5000)
     util.setup_pair(gpu, oracle_philox, w)

