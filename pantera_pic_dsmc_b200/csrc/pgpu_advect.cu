@@ -511,7 +511,6 @@ __device__ __forceinline__ int unstructured_iter(const PgDev& d, PgRng& g, PStat
                     dx[i] = (f[3] - q.x) * f[0] + (f[4] - q.y) * f[1] + (f[5] - q.z) * f[2];
                 }
             }
-#if PG_ADV_PARDIV
             /* The quotient DX/VN of a face does not depend on the faces before it either, only the DECISION to
              * take it does (through DTCOLL).  DTCOLL only ever shrinks from DTRIM and VN >= 0, so by monotonicity
              * of the rounded product  VN*DTCOLL >= DX  implies  VN*DTRIM >= DX : the faces that can be taken are
@@ -538,24 +537,6 @@ __device__ __forceinline__ int unstructured_iter(const PgDev& d, PgRng& g, PStat
                     codesel = (i == 0) ? codes.x : (i == 1) ? codes.y : (i == 2) ? codes.z : codes.w;
                 }
             }
-#else
-#pragma unroll
-            for (int i = 0; i < NF; i++) {
-                /* The compiler evaluates the quotient for every lane and selects; a particle that has just
-                 * crossed an axis-aligned face sits EXACTLY on it (dx == 0), which sends the whole warp
-                 * through the slow path of the FP64 division for a result that is discarded (that face now
-                 * has vn < 0).  Feeding 1/1 to the lanes that do not take the face keeps the division on
-                 * its fast path; the lanes that take it divide the same operands as before. */
-                const bool take = (vn[i] >= 0. && vn[i] * dtcoll >= dx[i]);
-                double num = take ? dx[i] : 1., den = take ? vn[i] : 1.;
-                asm("" : "+d"(num), "+d"(den)); /* opaque: keeps the selects in front of the division */
-                const double quo = num / den;
-                if (take) {
-                    dtcoll = quo; boundcoll = i;
-                    codesel = (i == 0) ? codes.x : (i == 1) ? codes.y : (i == 2) ? codes.z : codes.w;
-                }
-            }
-#endif
             if (!LEAN && boundcoll != -1) { /* outward normal of the face that was hit (boundary models) */
                 nsel[0] = pg_geo_at(gb, 6 * boundcoll + 0);
                 nsel[1] = (DIMS >= 2) ? pg_geo_at(gb, 6 * boundcoll + 1) : 0.;
@@ -899,38 +880,19 @@ __global__ void __launch_bounds__(128, PG_ADVECT_MINBLOCKS) advect_lean_kernel(c
     PendingRank pr;
     pr.mask = 0u;
 
-#if PG_ADV_PF
-    long long pf = next; /* slots below pf have been requested into L1 */
-#endif
     for (;;) {
-#if !PG_ADV_LATECOMMIT
         /* rank of the particle stored in the previous trip (its atomic has had a whole trip to return) */
         if (pr.mask) { commit_rank(d, pr); pr.mask = 0u; }
-#endif
-#if PG_ADV_PF
-        /* keep the records of the next 64..96 slots of the chunk on their way into L1: a refill (below) then
-         * costs an L1 hit instead of an exposed trip to L2/HBM.  One line-sized request per lane. */
-        if (pf < end && pf < next + 64) {
-            const long long s = pf + lane;
-            if (s < end) {
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(d.p.pos + s));
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(d.p.vel + s));
-            }
-            pf += 32;
-        }
-#endif
         /* refill: idle lanes take the next slots of the chunk, in order */
         unsigned int idle = __ballot_sync(FULL, !have);
         if (idle && next < end) {
             long long my = next + __popc(idle & ((1u << lane) - 1u));
             if (!have && my < end) {
                 slot = my;
-#if !PG_ADV_PF
                 if (my + 64 < end) { /* the records this lane is likely to take two refills from now */
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(d.p.pos + my + 64));
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(d.p.vel + my + 64));
                 }
-#endif
                 have = load_particle(d, slot, q, dirty);
                 hops = 0;
                 if (MODE == 0) { bhits[0] = bhits[1] = bhits[2] = bhits[3] = 0; }
@@ -938,9 +900,6 @@ __global__ void __launch_bounds__(128, PG_ADVECT_MINBLOCKS) advect_lean_kernel(c
             next += __popc(idle);
         }
         if (!__any_sync(FULL, have)) {
-#if PG_ADV_LATECOMMIT
-            if (pr.mask) { commit_rank(d, pr); pr.mask = 0u; }
-#endif
             if (next >= end) break; /* (nothing pending: a trip that stored something refills or ends here first) */
             continue;
         }
@@ -971,11 +930,6 @@ __global__ void __launch_bounds__(128, PG_ADVECT_MINBLOCKS) advect_lean_kernel(c
             if (!keep) tombstone_particle(d, slot);
         }
         unsigned int fm = __ballot_sync(FULL, keep);
-#if PG_ADV_LATECOMMIT
-        /* rank of the particle stored in the previous trip: its atomic has had this whole trip (a refill and a
-         * cell crossing) to return, so the read of its result does not stall the warp */
-        if (pr.mask) { commit_rank(d, pr); pr.mask = 0u; }
-#endif
         if (keep) {
             if (MODE == 0) { /* the species cannot change in the LEAN pass */
                 for (int b = 0; b < 4; b++)

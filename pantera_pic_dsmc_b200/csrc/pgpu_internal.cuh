@@ -60,17 +60,6 @@
 #ifndef PG_ADVECT_CHUNK
 #define PG_ADVECT_CHUNK 256
 #endif
-/* independent face divisions in the unstructured face walk (pgpu_advect.cu) */
-#ifndef PG_ADV_PARDIV
-#define PG_ADV_PARDIV 1
-#endif
-/* LEAN advect: commit the arrival rank at the end of the NEXT trip; warp-wide L1 prefetch of upcoming slots */
-#ifndef PG_ADV_LATECOMMIT
-#define PG_ADV_LATECOMMIT 1
-#endif
-#ifndef PG_ADV_PF
-#define PG_ADV_PF 1
-#endif
 #define PG_MAX_HOPS 1000000 /* guard against a malformed mesh hanging the GPU */
 
 /* status block, device resident, read back at the end of every hot-path call */

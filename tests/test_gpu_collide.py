@@ -153,6 +153,7 @@ def test_mcc_collisions_value_for_value(gpu, oracle_philox, kind, cell_density):
         w = wl.mcc_box("ar", n=40_000, cell_density=cell_density)
     else:
         w = wl.mcc_box("air", n=40_000, T=15000.0, bg_dens=5e21)
+    w.cfg.capacity = 5 * len(w.particles)   # room for one partner per background component + third products
     util.setup_pair(gpu, oracle_philox, w)
     n0 = len(w.particles)
     co, cg = oracle_philox.mcc_collisions(7), gpu.mcc_collisions(7)
