@@ -182,7 +182,8 @@ def main():
     w = build_workload(args, rank, world)
     n_local = len(w.particles)
     gpu = capi.load_gpu(local_rank)
-    w.cfg.capacity = int(n_local * 1.02) + 1024
+    # head-room for the append region and, with N > 1, for a strip that gains more immigrants than it loses
+    w.cfg.capacity = int(n_local * (1.02 if world == 1 else 1.06)) + 1024
     wl.apply(gpu, w)
     if world > 1:
         uid = [gpu.comm_unique_id() if rank == 0 else None]
@@ -262,19 +263,27 @@ def main():
             g2 = capi.load_gpu(local_rank)
             wl.apply(g2, w, upload=False)
             ctxs.append(g2)
-        outs = [wl.pinned_particles(n_local) for _ in ctxs]
+        outs = [wl.pinned_particles(int(w.cfg.capacity)) for _ in ctxs]   # a strip's population changes with N > 1
         moved = [0 for _ in ctxs]
+        errors = []
 
         def drive(i, first, count, tid0, go, nxt):
             go.wait()  # staggered start: context i+1 begins its upload when context i has finished its first one,
-            for k, s in enumerate(range(first, count, len(ctxs))):  # so uploads meet downloads, not other uploads
-                ctxs[i].upload_particles(w.particles)
-                if k == 0 and nxt is not None:
+            try:       # so uploads meet downloads, not other uploads
+                for k, s in enumerate(range(first, count, len(ctxs))):
+                    ctxs[i].upload_particles(w.particles)
+                    if k == 0 and nxt is not None:
+                        nxt.set()
+                    ctxs[i].run_steps(tid0 + s, 1)
+                    moved[i] += ctxs[i].download_into(outs[i])
+            except Exception as e:  # never leave the other ranks waiting at the barrier
+                errors.append(repr(e))
+                if world > 1:       # the peers wait for this rank inside the exchange: fail the whole job at once
+                    print(f"bench.py rank {rank}: e2e leg failed: {e!r}", file=sys.stderr, flush=True)
+                    os._exit(3)
+            finally:
+                if nxt is not None:
                     nxt.set()
-                ctxs[i].run_steps(tid0 + s, 1)
-                moved[i] += ctxs[i].download_into(outs[i])
-            if nxt is not None:
-                nxt.set()
 
         def run_all(count, tid0):
             ev = [threading.Event() for _ in ctxs]
@@ -293,6 +302,8 @@ def main():
         run_all(k2, 2000)
         barrier()
         e2e_s = max_over_ranks(time.perf_counter() - t0)
+        if errors:
+            raise RuntimeError("e2e leg failed: " + "; ".join(errors))
         e2e = {"value": sum_over_ranks(float(sum(moved))) / e2e_s, "unit": "particle-timesteps/s",
                "h2d_bytes_per_step": int(n_local * 96 * world), "d2h_bytes_per_step": int(n_local * 96 * world),
                "steps": k2, "ms_per_step": e2e_s / k2 * 1e3, "contexts_per_gpu": len(ctxs),
