@@ -145,6 +145,22 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+class StdoutGuard:
+    """The driver reads ONE JSON line from rank 0's stdout.  Libraries write there too (NCCL prints its version
+    banner on stdout at communicator creation), so file descriptor 1 points at stderr while the benchmark runs and
+    is restored for the result line only."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def restore(self):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -166,6 +182,7 @@ def main():
         return
     if args.warmup < 3:
         args.warmup = 3
+    guard = StdoutGuard()
 
     import torch
     import torch.distributed as dist
@@ -332,6 +349,7 @@ def main():
             "clocks": clocks, "collisions_per_step": ncoll / args.steps, "wall_ms_per_step": wall_ms / args.steps,
             "setup_seconds": setup_s,
         }
+        guard.restore()
         print(json.dumps(line), flush=True)
     gpu.close()
     if world > 1:

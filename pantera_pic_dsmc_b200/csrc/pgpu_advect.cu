@@ -839,12 +839,36 @@ __device__ __forceinline__ void store_particle(const PgDev& d, long long slot, c
         E.erot = q.erot; E.evib = q.evib;
         d.p.ie[slot] = E;
     }
+    int lane = threadIdx.x & 31;
+    /* nranks > 1: a particle that ends in a cell of another rank is an emigrant.  It is not histogrammed (the sort
+     * of this rank will not see it); its slot and destination are recorded for EXCHANGE instead. */
+    bool emig = false;
+    int dest = 0;
+    if (d.emig_list) {
+        dest = __ldg(&d.cell_procs[q.ic - 1]);
+        emig = dest != d.rank;
+        const unsigned int em = __ballot_sync(peers, emig);
+        if (em) {
+            unsigned long long ebase = 0;
+            const int el = __ffs(em) - 1;
+            if (lane == el) ebase = atomicAdd(&d.xrow[PG_XROW_LEN], (unsigned long long)__popc(em));
+            ebase = __shfl_sync(peers, ebase, el);
+            if (emig) {
+                const unsigned long long k = ebase + __popc(em & ((1u << lane) - 1u));
+                if (k < (unsigned long long)d.emig_cap) d.emig_list[k] = (unsigned int)slot;
+                else atomicAdd(&d.xrow[PG_XROW_OVF], 1ULL);
+                atomicAdd(&d.xrow[dest], 1ULL);
+            }
+            peers &= ~em;
+        }
+    }
+    pr.slot = slot; pr.base = 0; pr.mask = 0u; pr.leader = 0;
+    if (emig) return;
     unsigned int mask = __match_any_sync(peers, q.ic);
     int leader = __ffs(mask) - 1;
-    int lane = threadIdx.x & 31;
     unsigned int base = 0;
     if (lane == leader) base = atomicAdd(&d.cell_count[q.ic - 1], (unsigned int)__popc(mask));
-    pr.slot = slot; pr.base = base; pr.mask = mask; pr.leader = leader;
+    pr.base = base; pr.mask = mask; pr.leader = leader;
 }
 /* all lanes of pr.mask call this together */
 __device__ __forceinline__ void commit_rank(const PgDev& d, const PendingRank& pr) {
@@ -965,7 +989,7 @@ __global__ void __launch_bounds__(128) advect_full_kernel(const __grid_constant_
     if (keep) {
         PendingRank pr;
         store_particle(d, slot, q, dirty, fm, pr);
-        commit_rank(d, pr);
+        if (pr.mask) commit_rank(d, pr);
     }
 }
 
@@ -1017,6 +1041,16 @@ int pg_advect_impl(pgpu_ctx* c, int tID) {
     PG_CUDA(c, cudaMemsetAsync(c->d_bcount, 0, sizeof(unsigned long long) * 4 * (size_t)c->ns, c->stream));
     if (c->nw) PG_CUDA(c, cudaMemsetAsync(c->d_wcount, 0, sizeof(unsigned long long) * (size_t)(c->nw * c->ns), c->stream));
 
+    /* nranks > 1: the epilogue records the emigrants (slot list + count per destination) for EXCHANGE */
+    c->emig_valid = false;
+    const bool track = c->cfg.nranks > 1 && c->dev.cell_procs && c->d_xcount && c->d_emig_list;
+    if (track) {
+        PG_CUDA(c, cudaMemsetAsync(c->d_xcount, 0, sizeof(unsigned long long) * PG_XROW, c->stream));
+        c->dev.emig_list = c->d_emig_list;
+        c->dev.emig_cap = c->emig_cap;
+        c->dev.xrow = c->d_xcount;
+    }
+
     if ((rc = launch_advect<true>(c, c->np))) return rc;
     /* hit-list length -> host (the only sync inside ADVECT) */
     PG_CUDA(c, cudaMemcpyAsync(&c->h_status->n_hits, &c->d_status->n_hits, sizeof(unsigned long long),
@@ -1025,6 +1059,9 @@ int pg_advect_impl(pgpu_ctx* c, int tID) {
     long long nh = (long long)c->h_status->n_hits;
     if (nh > 0 && (rc = launch_advect<false>(c, nh))) return rc;
 
+    c->dev.emig_list = nullptr;
+    c->dev.xrow = nullptr;
+    c->emig_valid = track;
     c->has_dtrim = false; /* DTRIM = DT for every particle after ADVECT, ref: src/timecycle.f90:2070 */
     c->sorted = false;
     c->hist_valid = true;

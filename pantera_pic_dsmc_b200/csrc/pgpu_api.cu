@@ -116,6 +116,7 @@ extern "C" int pgpu_create(pgpu_ctx** out, int device) {
     c->launches = 0;
     c->nccl_lib = nullptr; c->nccl_comm = nullptr; c->comm_nranks = 1; c->comm_rank = 0;
     c->d_sendbuf = c->d_recvbuf = nullptr; c->xbuf_capacity = 0; c->d_xcount = nullptr;
+    c->d_emig_list = nullptr; c->emig_cap = 0; c->emig_valid = false;
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return PGPU_ERR_CUDA; }
     for (int i = 0; i < 16; i++) cudaEventCreate(&c->ev[i]);
     if (cudaMalloc((void**)&c->d_status, sizeof(PgStatus)) != cudaSuccess ||
@@ -158,7 +159,7 @@ extern "C" int pgpu_destroy(pgpu_ctx* c) {
     }
     dev_free(c->d_rhs); dev_free(c->d_bcount); dev_free(c->d_wcount); dev_free(c->d_tallies);
     dev_free(c->d_surface_charge);
-    dev_free(c->d_sendbuf); dev_free(c->d_recvbuf); dev_free(c->d_xcount);
+    dev_free(c->d_sendbuf); dev_free(c->d_recvbuf); dev_free(c->d_xcount); dev_free(c->d_emig_list);
     for (int i = 0; i < 16; i++) cudaEventDestroy(c->ev[i]);
     cudaStreamDestroy(c->stream);
     delete c;
@@ -373,6 +374,7 @@ extern "C" int pgpu_set_cell_procs(pgpu_ctx* c, int nc, const int32_t* cell_proc
     cudaSetDevice(c->device);
     if (!c->cfg_set) PG_FAIL(c, PGPU_ERR_STATE, "set_cell_procs: set_config first");
     if (nc != pg_ncells(c)) PG_FAIL(c, PGPU_ERR_INVALID, "set_cell_procs: nc (%d) != number of cells (%d)", nc, pg_ncells(c));
+    c->emig_valid = false; /* the emigrant list of the last ADVECT was made with the old ownership */
     return put(c, S_CELL_PROCS, (const int*)cell_procs, (size_t)nc, &c->dev.cell_procs);
 }
 
@@ -569,6 +571,7 @@ void pg_refresh_dev(pgpu_ctx* c) {
     d.np = c->np; d.capacity = c->capacity;
     d.ncells = pg_ncells(c);
     d.cell_count = c->d_cell_count; d.cell_rank = c->d_rank; d.cell_off = c->d_cell_off; d.hitlist = c->d_hitlist;
+    d.emig_list = nullptr; d.emig_cap = c->emig_cap; d.xrow = nullptr; /* switched on by ADVECT when it tracks emigrants */
     d.id_base = c->id_counter;
     d.use_ie = (c->any_internal_dof || c->dev.nr > 0 || c->ie_seen) ? 1 : 0;
     d.tile_first = c->d_tile_first;
@@ -671,6 +674,10 @@ int pg_ensure_capacity(pgpu_ctx* c, long long n) {
     dev_free(c->d_hitlist);
     if ((rc = dev_alloc(c, &c->d_rank, (size_t)cap))) return rc;
     if ((rc = dev_alloc(c, &c->d_hitlist, (size_t)cap))) return rc;
+    dev_free(c->d_emig_list);
+    c->emig_cap = cap / 8 + 1024;
+    if ((rc = dev_alloc(c, &c->d_emig_list, (size_t)c->emig_cap))) return rc;
+    c->emig_valid = false;
     dev_free(c->d_tile_first);
     dev_free(c->d_big_list);
     dev_free(c->d_big_bbox);
@@ -945,6 +952,10 @@ int pg_sort_impl(pgpu_ctx* c) {
     PgPlanes src = c->planes[c->cur], dst = c->planes[c->cur ^ 1];
     if (!c->has_dtrim) src.dtrim = nullptr;
     unsigned int blocks = (unsigned int)((c->np + 255) / 256);
+    if (c->emig_valid) { /* ADVECT left the emigrants out of its histogram and no EXCHANGE has shipped them: recount */
+        c->hist_valid = false;
+        c->emig_valid = false;
+    }
     if (!c->hist_valid) {
         PG_CUDA(c, cudaMemsetAsync(c->d_cell_count, 0, sizeof(unsigned int) * ((size_t)ncells + 1), c->stream));
         hist_rank_kernel<<<blocks, 256, 0, c->stream>>>(src.pos, c->np, c->d_cell_count, c->d_rank);

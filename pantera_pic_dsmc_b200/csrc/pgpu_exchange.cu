@@ -119,9 +119,38 @@ __global__ void __launch_bounds__(256) xpack_kernel(const __grid_constant__ PgDe
     d.p.pos[i].ic = PG_TOMBSTONE;
 }
 
-/* append the received records (ADD_PARTICLE_ARRAY loop, ref: grid_and_partition.f90:610-612) */
+/* pass 2, fast path: the emigrants are the entries of the list the ADVECT epilogue wrote (pgpu_advect.cu
+ * store_particle), so packing touches the emigrants only instead of sweeping the whole store */
+__global__ void __launch_bounds__(256) xpack_list_kernel(const __grid_constant__ PgDev d, const unsigned int* __restrict__ list,
+                                                         long long n, double* __restrict__ sendbuf,
+                                                         const unsigned long long* __restrict__ xoff,
+                                                         unsigned long long* __restrict__ xcursor) {
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const long long i = (long long)list[t];
+    const PgPos P = d.p.pos[i];
+    const int ic = P.ic;
+    const int dest = __ldg(&d.cell_procs[ic - 1]);
+    unsigned long long k = xoff[dest] + atomicAdd(&xcursor[dest], 1ULL);
+    double* r = sendbuf + k * XREC_DOUBLES;
+    const PgVel V = d.p.vel[i];
+    const PgIe E = d.p.ie[i];
+    r[0] = P.x; r[1] = P.y; r[2] = P.z;
+    r[3] = V.vx; r[4] = V.vy; r[5] = V.vz;
+    r[6] = E.erot; r[7] = E.evib;
+    r[8] = d.p.dtrim ? d.p.dtrim[i] : d.dt;
+    int2 cs = make_int2(ic, P.sid);
+    r[9] = *reinterpret_cast<double*>(&cs);
+    long long id = d.p.id ? d.p.id[i] : 0;
+    r[10] = *reinterpret_cast<double*>(&id);
+    d.p.pos[i].ic = PG_TOMBSTONE;
+}
+
+/* append the received records (ADD_PARTICLE_ARRAY loop, ref: grid_and_partition.f90:610-612).  with_rank: the
+ * histogram of the ADVECT epilogue is still valid; the immigrant joins it (count + arrival rank in its cell), so
+ * the counting sort that follows needs no recount. */
 __global__ void __launch_bounds__(256) xunpack_kernel(const __grid_constant__ PgDev d, const double* __restrict__ recvbuf,
-                                                      long long n, PgPlanes p, long long base) {
+                                                      long long n, PgPlanes p, long long base, int with_rank) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const double* r = recvbuf + i * XREC_DOUBLES;
@@ -143,6 +172,7 @@ __global__ void __launch_bounds__(256) xunpack_kernel(const __grid_constant__ Pg
     if (dtrim != d.dt) d.status->flag_dtrim = 1;
     t = r[10];
     if (p.id) p.id[o] = *reinterpret_cast<long long*>(&t);
+    if (with_rank) d.cell_rank[o] = atomicAdd(&d.cell_count[cs.x - 1], 1u);
 }
 
 __global__ void fill_kernel(double* p, long long n, double v) {
@@ -175,7 +205,8 @@ extern "C" int pgpu_comm_init(pgpu_ctx* c, int nranks, int rank, const char id12
     c->nccl_comm = (void*)comm;
     c->comm_nranks = nranks;
     c->comm_rank = rank;
-    PG_CUDA(c, cudaMalloc((void**)&c->d_xcount, sizeof(unsigned long long) * 64 * 4 + sizeof(unsigned long long) * 64 * 64));
+    PG_CUDA(c, cudaMalloc((void**)&c->d_xcount, sizeof(unsigned long long) * PG_XROW * (4 + 64)));
+    c->emig_valid = false;
     return PGPU_OK;
 }
 
@@ -199,25 +230,40 @@ int pg_exchange_impl(pgpu_ctx* c) {
     int rc;
     pg_refresh_dev(c);
     ncclComm_t comm = (ncclComm_t)c->nccl_comm;
-    unsigned long long* xcount = c->d_xcount;          /* [64] my counts per destination */
-    unsigned long long* xoff = c->d_xcount + 64;       /* [64] */
-    unsigned long long* xcursor = c->d_xcount + 128;   /* [64] */
-    unsigned long long* xall = c->d_xcount + 256;      /* [nr][64] everyone's counts */
-    PG_CUDA(c, cudaMemsetAsync(c->d_xcount, 0, sizeof(unsigned long long) * 256, c->stream));
+    unsigned long long* xcount = c->d_xcount;                 /* [PG_XROW] my counts per destination (+ list length, overflow) */
+    unsigned long long* xoff = c->d_xcount + PG_XROW;         /* [PG_XROW] */
+    unsigned long long* xcursor = c->d_xcount + 2 * PG_XROW;  /* [PG_XROW] */
+    unsigned long long* xall = c->d_xcount + 4 * PG_XROW;     /* [nr][PG_XROW] everyone's rows */
     unsigned int blocks = (unsigned int)((c->np + 255) / 256);
-    if (c->np > 0) {
-        xcount_kernel<<<blocks, 256, 0, c->stream>>>(c->dev, xcount);
-        c->launches++;
+    /* fast path: ADVECT has just recorded the emigrants (list + counts) and the histogram of the survivors is
+     * valid; nothing has touched the store since.  Every rank takes the same branch (same call sequence). */
+    bool fast = c->emig_valid && c->hist_valid;
+    c->emig_valid = false;
+    std::vector<unsigned long long> h((size_t)nr * PG_XROW);
+    for (int attempt = 0; attempt < 2; attempt++) {
+        PG_CUDA(c, cudaMemsetAsync(xoff, 0, sizeof(unsigned long long) * 2 * PG_XROW, c->stream));
+        if (!fast) {
+            PG_CUDA(c, cudaMemsetAsync(xcount, 0, sizeof(unsigned long long) * PG_XROW, c->stream));
+            if (c->np > 0) {
+                xcount_kernel<<<blocks, 256, 0, c->stream>>>(c->dev, xcount);
+                c->launches++;
+            }
+        }
+        /* MPI_ALLTOALL of the counts -> all-gather of the rows */
+        PG_NCCL(c, g_nccl.AllGather(xcount, xall, PG_XROW, ncclUint64, comm, c->stream));
+        PG_CUDA(c, cudaMemcpyAsync(h.data(), xall, sizeof(unsigned long long) * (size_t)nr * PG_XROW, cudaMemcpyDeviceToHost, c->stream));
+        PG_CUDA(c, cudaStreamSynchronize(c->stream));
+        if (!fast) break;
+        /* a rank whose emigrants did not fit its list sends everybody (itself included) through the full sweep */
+        bool overflow = false;
+        for (int r = 0; r < nr; r++) overflow |= h[(size_t)r * PG_XROW + PG_XROW_OVF] != 0;
+        if (!overflow) break;
+        fast = false;
     }
-    /* MPI_ALLTOALL of the counts -> all-gather of the 64-entry rows */
-    PG_NCCL(c, g_nccl.AllGather(xcount, xall, 64, ncclUint64, comm, c->stream));
-    std::vector<unsigned long long> h((size_t)nr * 64);
-    PG_CUDA(c, cudaMemcpyAsync(h.data(), xall, sizeof(unsigned long long) * (size_t)nr * 64, cudaMemcpyDeviceToHost, c->stream));
-    PG_CUDA(c, cudaStreamSynchronize(c->stream));
     std::vector<unsigned long long> soff(65, 0), roff(65, 0);
     for (int r = 0; r < nr; r++) {
-        soff[r + 1] = soff[r] + h[(size_t)c->cfg.rank * 64 + r];
-        roff[r + 1] = roff[r] + h[(size_t)r * 64 + c->cfg.rank];
+        soff[r + 1] = soff[r] + h[(size_t)c->cfg.rank * PG_XROW + r];
+        roff[r + 1] = roff[r] + h[(size_t)r * PG_XROW + c->cfg.rank];
     }
     long long nsend = (long long)soff[nr], nrecv = (long long)roff[nr];
     long long need = std::max(nsend, nrecv);
@@ -229,14 +275,21 @@ int pg_exchange_impl(pgpu_ctx* c) {
         PG_CUDA(c, cudaMalloc(&c->d_recvbuf, sizeof(double) * XREC_DOUBLES * (size_t)cap));
         c->xbuf_capacity = cap;
     }
-    if ((rc = pg_ensure_capacity(c, c->np + nrecv))) return rc;
-    pg_refresh_dev(c);
     if (nsend > 0) {
+        /* (packed before the store can be re-allocated below: the list holds slots of the current planes) */
         PG_CUDA(c, cudaMemcpyAsync(xoff, soff.data(), sizeof(unsigned long long) * 64, cudaMemcpyHostToDevice, c->stream));
-        xpack_kernel<<<blocks, 256, 0, c->stream>>>(c->dev, (double*)c->d_sendbuf, xoff, xcursor);
+        if (fast) {
+            xpack_list_kernel<<<(unsigned int)((nsend + 255) / 256), 256, 0, c->stream>>>(c->dev, c->d_emig_list, nsend,
+                                                                                          (double*)c->d_sendbuf, xoff, xcursor);
+        } else {
+            xpack_kernel<<<blocks, 256, 0, c->stream>>>(c->dev, (double*)c->d_sendbuf, xoff, xcursor);
+        }
         c->launches++;
         c->maybe_tombstones = true;
     }
+    if (!fast) c->hist_valid = false;
+    if ((rc = pg_ensure_capacity(c, c->np + nrecv))) return rc; /* (a re-allocation drops the histogram) */
+    pg_refresh_dev(c);
     /* MPI_ALLTOALLV -> one grouped send/recv to every peer with traffic */
     PG_NCCL(c, g_nccl.GroupStart());
     for (int r = 0; r < nr; r++) {
@@ -248,7 +301,8 @@ int pg_exchange_impl(pgpu_ctx* c) {
     PG_NCCL(c, g_nccl.GroupEnd());
     if (nrecv > 0) {
         PgPlanes p = c->planes[c->cur];
-        xunpack_kernel<<<(unsigned int)((nrecv + 255) / 256), 256, 0, c->stream>>>(c->dev, (const double*)c->d_recvbuf, nrecv, p, c->np);
+        xunpack_kernel<<<(unsigned int)((nrecv + 255) / 256), 256, 0, c->stream>>>(c->dev, (const double*)c->d_recvbuf, nrecv, p, c->np,
+                                                                                   c->hist_valid ? 1 : 0);
         c->launches++;
         PG_CUDA(c, cudaMemcpyAsync(&c->h_status->flag_dtrim, &c->d_status->flag_dtrim, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         PG_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -261,7 +315,6 @@ int pg_exchange_impl(pgpu_ctx* c) {
         c->id_counter = std::max(c->id_counter, c->np);
     }
     c->sorted = false;
-    c->hist_valid = false;
     pg_refresh_dev(c);
     PG_CUDA(c, cudaGetLastError());
     return PGPU_OK;

@@ -70,8 +70,8 @@ struct PgStatus {
     unsigned long long ncoll;       /* TIMESTEP_COLL                                     */
     unsigned long long nreac;       /* TIMESTEP_REAC                                     */
     unsigned long long pending;     /* collision candidates still waiting                */
-    unsigned long long n_emigrants; /* particles leaving this rank                       */
-    unsigned long long x_overflow;  /* emigrants that did not fit the fused send segments */
+    unsigned long long n_emigrants; /* (unused, kept for layout)                          */
+    unsigned long long x_overflow;  /* (unused, kept for layout)                          */
     int err;                        /* first device-side error code (0 = none)           */
     int flag_dtrim;                 /* some uploaded/received particle has DTRIM != DT   */
     int flag_ie;                    /* some uploaded/received particle has EROT/EVIB != 0 */
@@ -205,11 +205,17 @@ struct PgDev {
     int use_ie;               /* 1: the ie plane is live (some particle can hold internal energy) */
     const unsigned int* tile_first; /* [ntiles+1] first cell of every collision tile (valid while sorted) */
     int ntiles;
-    /* fused emigrant packing in the ADVECT epilogue (multi-GPU run_steps) */
-    double* xseg;                   /* [nranks][xseg_cap][11] send segments, or null */
-    unsigned long long* xseg_count; /* [nranks] */
-    long long xseg_cap;
+    /* emigrant bookkeeping in the ADVECT epilogue (nranks > 1): a particle whose final cell belongs to another
+     * rank is not histogrammed; its slot goes to emig_list and its destination is counted in xrow, so that
+     * EXCHANGE touches the emigrants only (pgpu_exchange.cu).  Null when not tracking. */
+    unsigned int* emig_list;        /* [emig_cap] */
+    long long emig_cap;
+    unsigned long long* xrow;       /* [PG_XROW]: [0..63] emigrants per destination, [PG_XROW_LEN] list length,
+                                       [PG_XROW_OVF] entries that did not fit the list */
 };
+#define PG_XROW 72
+#define PG_XROW_LEN 64
+#define PG_XROW_OVF 65
 
 /* ------------------------------------------------------------------------------------------
  * host context
@@ -302,7 +308,10 @@ struct pgpu_ctx {
     void* d_sendbuf;
     void* d_recvbuf;
     long long xbuf_capacity; /* particles */
-    unsigned long long* d_xcount; /* [nranks] emigrant counts + cursors */
+    unsigned long long* d_xcount; /* 4 rows of PG_XROW (counts, offsets, cursors, spare) + [nranks] gathered rows */
+    unsigned int* d_emig_list;    /* [emig_cap] slots of the emigrants found by the last ADVECT */
+    long long emig_cap;
+    bool emig_valid;              /* d_emig_list / count row describe the current store */
 };
 
 #define PG_FAIL(ctx, code, ...)                                   \

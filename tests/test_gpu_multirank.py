@@ -46,12 +46,27 @@ def _worker(rank, world, port, out_dir):
     dist.broadcast_object_list(uid, src=0)
     gpu.comm_init(world, rank, uid[0])
     ncoll, _ = gpu.run_steps(1, STEPS)
+    # the same step as separate calls, in the order TIME_LOOP makes them (timecycle.f90:271-299): ADVECT leaves the
+    # emigrant list for EXCHANGE (fast path) ...
+    gpu.advect(100)
+    gpu.exchange()
+    c1, _ = gpu.collide(100)
+    # ... and ADVECT followed by a sort BEFORE the exchange: the emigrants are still in the store and must survive
+    # the sort (recount), the exchange then takes the full sweep
+    n_before = gpu.num_particles()
+    gpu.advect(101)
+    gpu.sort()
+    n_sorted = gpu.num_particles()
+    gpu.exchange()
+    c2, _ = gpu.collide(101)
+    ncoll += 0 * (c1 + c2)
     p = gpu.download_particles()
     owner = np.asarray(w.mesh.cell_procs)[p["IC"] - 1]
     came = int(np.sum((p["ID"] & 0xFF) != rank))       # ID = PROC_ID + ISHFT(counter, 8): born on the other rank
     tot = torch.tensor([len(p), ncoll, came], dtype=torch.int64)
     dist.all_reduce(tot)
-    ok = bool(np.all(owner == rank)) and int(tot[0]) == world * n and int(tot[2]) > 0
+    ok = bool(np.all(owner == rank)) and int(tot[0]) == world * n and int(tot[2]) > 0 and n_sorted == n_before \
+        and c1 > 0 and c2 > 0
     with open(os.path.join(out_dir, f"ok{rank}"), "w") as f:
         f.write(f"{int(ok)} {int(tot[0])} {int(tot[1])} {int(tot[2])} {world * n}")
     gpu.close()
