@@ -190,9 +190,10 @@ static uint64_t seed_local(const po_ctx* w) {
 }
 
 /* Keyed stream selection (device RNG contract, DESIGN.md "RNG"):
- *   key = { seed_lo ^ kind*0x632BE5AB, seed_hi ^ tID },  ctr = { draw/2, e0_lo, e0_hi ^ (e1<<?) ... }
+ *   key = { seed_lo ^ kind*0x632BE5AB, seed_hi ^ tID },  ctr = { word/4, e0_lo, e0_hi, e1 }; the stream is
+ *   the blocks' 32-bit words in order: rf() takes two (lo, hi -> 53 bits), po_pick() one for N <= 65536.
  * kinds: 1 ADVECT (e0 = particle slot), 2 DSMC (e0 = cell (0-based), e1 = candidate),
- *        3 MCC (e0 = particle slot).  No-op in MT mode. */
+ *        3 MCC_VAHEDI (e0 = particle slot), 4 MCC (e0 = particle slot).  No-op in MT mode. */
 void po_rng_stream(po_ctx* w, int kind, int tID, uint64_t e0, uint64_t e1) {
     if (w->rng_mode != 1) return;
     uint64_t s = seed_local(w);
@@ -204,20 +205,36 @@ void po_rng_stream(po_ctx* w, int kind, int tID, uint64_t e0, uint64_t e1) {
     w->ndraw = 0;
 }
 
+/* next 32-bit word of the keyed Philox stream: word n is word (n mod 4) of block (n / 4) */
+static uint32_t philox_word(po_ctx* w) {
+    uint32_t n = w->ndraw++;
+    if ((n & 3u) == 0) {
+        uint32_t ctr[4] = {n >> 2, w->ent[0], w->ent[1], w->ent[2]};
+        po_philox4x32_10(ctr, w->key, w->phx_buf);
+    }
+    return w->phx_buf[n & 3u];
+}
+
 /* ref: src/tools.f90:33-43 rf() = genrand64_real1 on [0,1] (src/mt19937.f90:220-225) */
 double po_rf(po_ctx* w) {
     if (w->rng_mode == 0) {
         return (double)(po_mt_next_u64(w) >> 11) * (1.0 / 9007199254740991.0);
     }
-    /* Philox: two 53-bit uniforms on [0,1) per block */
-    uint32_t n = w->ndraw++;
-    if ((n & 1u) == 0) {
-        uint32_t ctr[4] = {n >> 1, w->ent[0], w->ent[1], w->ent[2]};
-        po_philox4x32_10(ctr, w->key, w->phx_buf);
-    }
-    uint32_t lo = w->phx_buf[2 * (n & 1u)], hi = w->phx_buf[2 * (n & 1u) + 1];
+    /* Philox: a stream of 32-bit words, four per block; a uniform takes two (53 bits on [0,1)) */
+    uint32_t lo = philox_word(w), hi = philox_word(w);
     uint64_t u = ((uint64_t)hi << 32) | lo;
     return (double)(u >> 11) * (1.0 / 9007199254740992.0);
+}
+
+/* INT(N*rf()) of the pair selection (ref: src/collisions.f90:263-271), clamped to N-1 (rf() is [0,1], App. B4).
+ * Philox mode: for N <= 65536 the index takes ONE word of the stream, floor(N*word/2^32) (bias <= N/2^32); the
+ * two indices and the acceptance draw of a candidate are then exactly one Philox block.  Larger N use rf(). */
+int po_pick(po_ctx* w, int n) {
+    int k;
+    if (w->rng_mode == 1 && n <= 65536) k = (int)(((uint64_t)philox_word(w) * (uint64_t)(uint32_t)n) >> 32);
+    else k = (int)(n * po_rf(w));
+    if (k >= n) k = n - 1;
+    return k;
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -1272,7 +1289,11 @@ static int accepted_pair(po_ctx* w, int64_t jp1, int64_t jp2, int s1, int s2, do
     double pvib1 = (trdof + w->vibdof[s1 - 1]) / trdof * w->vibrel[s1 - 1];
     double pvib2 = (trdof + w->vibdof[s2 - 1]) / trdof * w->vibrel[s2 - 1];
     trdof = 5. - 2. * omega;
-    rfp = po_rf(w);
+    /* Philox mode: when neither species can exchange internal energy the selector cannot fall in any branch and
+     * its draw is not taken from the stream (an accepted elastic pair then needs exactly one block: deflection
+     * angle and azimuth).  The sequential MT19937 mode consumes it, as the reference does (:472). */
+    if (w->rng_mode == 1 && w->rotrel[s1 - 1] + w->rotrel[s2 - 1] + w->vibrel[s1 - 1] + w->vibrel[s2 - 1] == 0.) rfp = 1.;
+    else rfp = po_rf(w);
     if (rfp < prot1) {
         ecoll = etr + q1->EROT;
         q1->EROT = coll_internal_energy(w, ecoll, trdof, w->rotdof[s1 - 1]);
@@ -1359,13 +1380,11 @@ static int64_t vss_collis(po_ctx* w, int jc, int tID, int npcj, const int32_t* i
         po_rng_stream(w, 2, tID, (uint64_t)(jc - 1), (uint64_t)jcol);
         /* ref: :263-271; rf() is [0,1] so INT(NPCJ*rf()) may equal NPCJ with probability 2^-53 (App. B4):
          * clamped here, cannot happen with the [0,1) Philox stream */
-        int k1 = (int)(npcj * po_rf(w));
-        if (k1 >= npcj) k1 = npcj - 1;
+        int k1 = po_pick(w, npcj);
         int64_t jp1 = ind[k1];
         int64_t jp2 = jp1;
         while (jp2 == jp1) {
-            int k2 = (int)(npcj * po_rf(w));
-            if (k2 >= npcj) k2 = npcj - 1;
+            int k2 = po_pick(w, npcj);
             jp2 = ind[k2];
         }
         part_t *q1 = &w->p[jp1], *q2 = &w->p[jp2];

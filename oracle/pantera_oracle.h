@@ -40,6 +40,7 @@ const char* po_last_error(const po_ctx* ctx);
 int po_set_rng_mode(po_ctx* ctx, int mode);
 /* raw generator access for the known-answer tests */
 double po_rf(po_ctx* ctx);
+int po_pick(po_ctx* ctx, int n); /* pair-selection index INT(N*rf()), one stream word in Philox mode for N <= 65536 */
 void po_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 uint64_t po_mt_next_u64(po_ctx* ctx);
 void po_rng_stream(po_ctx* ctx, int kind, int tID, uint64_t e0, uint64_t e1);

@@ -421,6 +421,11 @@ class OracleLib(Lib):
         f.restype = C.c_double
         return f(self.ctx)
 
+    def pick(self, n: int) -> int:
+        f = self.lib.po_pick
+        f.restype = C.c_int
+        return f(self.ctx, C.c_int(n))
+
     def rng_stream(self, kind, tID, e0, e1=0):
         self.lib.po_rng_stream(self.ctx, C.c_int(kind), C.c_int(tID), C.c_uint64(e0), C.c_uint64(e1))
 

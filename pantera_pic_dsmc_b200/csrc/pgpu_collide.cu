@@ -71,13 +71,9 @@ __device__ __forceinline__ int cell_majorant(const PgDev& d, int cell0, int n, d
 __device__ __forceinline__ unsigned int pick_pair(const PgDev& d, unsigned int cell0, unsigned int j, int npcj, int& k1, int& k2) {
     PgRng rng;
     rng.init(d.seed_local, 2, d.tID, (unsigned long long)cell0, (unsigned long long)j);
-    k1 = (int)(npcj * rng.rf());
-    if (k1 >= npcj) k1 = npcj - 1;
+    k1 = rng.pick(npcj);
     k2 = k1;
-    while (k2 == k1) {
-        k2 = (int)(npcj * rng.rf());
-        if (k2 >= npcj) k2 = npcj - 1;
-    }
+    while (k2 == k1) k2 = rng.pick(npcj);
     return rng.ndraw;
 }
 
@@ -181,7 +177,10 @@ __device__ int pair_collide(const PgDev& d, PgRng& g, PairIO& p, long long gslot
     double pvib1 = (trdof + vd1) / trdof * __ldg(&d.vibrel[s1 - 1]);
     double pvib2 = (trdof + vd2) / trdof * __ldg(&d.vibrel[s2 - 1]);
     trdof = 5. - 2. * omega;
-    rfp = g.rf();
+    /* when neither species can exchange internal energy the selector cannot fall in any branch and its draw is not
+     * taken from the stream (stream contract shared with the oracle's rng_mode 1) */
+    if (__ldg(&d.rotrel[s1 - 1]) + __ldg(&d.rotrel[s2 - 1]) + __ldg(&d.vibrel[s1 - 1]) + __ldg(&d.vibrel[s2 - 1]) == 0.) rfp = 1.;
+    else rfp = g.rf();
     if (rfp < prot1) {
         ecoll = etr + erot1;
         erot1 = coll_internal_energy(g, ecoll, trdof, rd1);
@@ -258,8 +257,10 @@ __device__ __forceinline__ void pair_collide_fast(const PgDev& d, PgRng& g, doub
     double m1 = __ldg(&d.mass[s1 - 1]), m2 = __ldg(&d.mass[s2 - 1]);
     /* ref: :454-490 with no internal modes: the selector only decides whether the post-collision relative
      * velocity is redirected isotropically (:505-514; ROTREL/VIBREL != 0 on a species without modes) */
-    const double rbl = g.rf();
     const double psum = __ldg(&d.rotrel[s1 - 1]) + __ldg(&d.rotrel[s2 - 1]) + __ldg(&d.vibrel[s1 - 1]) + __ldg(&d.vibrel[s2 - 1]);
+    /* (psum == 0: the selector cannot fall in any branch and its draw is not taken from the stream; an accepted
+     *  elastic pair then needs exactly one more Philox block: deflection angle and azimuth) */
+    const double rbl = (psum == 0.) ? 1. : g.rf();
     /* ref: :495-499 */
     const double alpha = VSS2(d.alphas, s1, s2);
     double coschi = 2. * pow(g.rf(), 1. / alpha) - 1.;
@@ -349,30 +350,42 @@ __global__ void __launch_bounds__(128, PG_CELL_MINBLOCKS) cell_collide_kernel(co
         /* cheap part: this lane's next candidates, up to and including its next accepted one; bounded, so that
          * the lanes that already hold an accepted candidate do not idle behind the unluckiest lane */
         bool hit = false;
-        unsigned int j1 = 0, j2 = 0;
-        PgRng rng;
+        unsigned int j1 = 0, j2 = 0, jhit = 0, used = 4;
         PairIO p;
         for (int tries = 0; tries < PG_CELL_TRIES && j < ncoll && !hit; tries++) {
+            /* ref: :263-271.  The first block of the candidate's stream (PgRng contract: kind 2, cell, candidate)
+             * holds everything a candidate needs: word 0 -> first index, word 1 -> second index, words 2,3 -> the
+             * acceptance draw (n <= PG_TILE_BIG here, so the indices are one-word picks).  Only a repeated index
+             * (probability 1/n) goes on through the general stream. */
+            PgRng rng;
             rng.init(d.seed_local, 2, d.tID, (unsigned long long)c, (unsigned long long)j);
-            /* ref: :263-271 */
-            int k1 = (int)(n * rng.rf());
-            if (k1 >= n) k1 = n - 1;
-            int k2 = k1;
-            while (k2 == k1) {
-                k2 = (int)(n * rng.rf());
-                if (k2 >= n) k2 = n - 1;
+            uint32_t o[4];
+            pg_philox(0u, rng.e0, rng.e1, rng.e2, rng.k0, rng.k1, o);
+            const int k1 = (int)__umulhi(o[0], (uint32_t)n);
+            int k2 = (int)__umulhi(o[1], (uint32_t)n);
+            double racc = (double)((((unsigned long long)o[3] << 32) | o[2]) >> 11) * (1.0 / 9007199254740992.0);
+            used = 4;
+            if (k2 == k1) {
+                rng.seek(2);
+                while (k2 == k1) k2 = rng.pick(n);
+                racc = rng.rf();
+                used = rng.ndraw;
             }
             j1 = o0 + (unsigned int)k1;
             j2 = o0 + (unsigned int)k2;
             const PgVel V1 = d.p.vel[j1], V2 = d.p.vel[j2];
             p.c1[0] = V1.vx; p.c1[1] = V1.vy; p.c1[2] = V1.vz; p.s1 = V1.sid;
             p.c2[0] = V2.vx; p.c2[1] = V2.vy; p.c2[2] = V2.vz; p.s2 = V2.sid;
-            hit = pair_accept(d, rng.rf(), p.c1, p.c2, p.s1, p.s2, vrmax, fcorr);
+            hit = pair_accept(d, racc, p.c1, p.c2, p.s1, p.s2, vrmax, fcorr);
+            jhit = (unsigned int)j;
             j++;
         }
         /* expensive part, for all lanes that hold an accepted candidate */
         if (hit) {
             nacc++;
+            PgRng rng; /* the candidate's stream, right after its acceptance draw */
+            rng.init(d.seed_local, 2, d.tID, (unsigned long long)c, (unsigned long long)jhit);
+            rng.seek(used);
             if (!IE) {
                 pair_collide_fast(d, rng, p.c1, p.c2, p.s1, p.s2);
                 PgVel W1, W2;

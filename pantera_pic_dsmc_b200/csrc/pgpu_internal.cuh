@@ -48,7 +48,7 @@
 #define PG_TILE_THREADS 256
 #endif
 #ifndef PG_CELL_MINBLOCKS
-#define PG_CELL_MINBLOCKS 6
+#define PG_CELL_MINBLOCKS 8
 #endif
 #ifndef PG_CELL_TRIES
 #define PG_CELL_TRIES 2 /* acceptance tests a lane runs before the warp re-converges for the deflections */
@@ -57,9 +57,10 @@
 #define PG_ADVECT_MINBLOCKS 6
 #endif
 /* particles one warp of the LEAN advect pass works through (lanes refill as their particle finishes) */
-#ifndef PG_ADVECT_CHUNK
-#define PG_ADVECT_CHUNK 256
+#ifndef PG_ADVECT_CHUNK_MAX
+#define PG_ADVECT_CHUNK_MAX 1024
 #endif
+#define PG_ADVECT_CHUNK_MIN 64
 #define PG_MAX_HOPS 1000000 /* guard against a malformed mesh hanging the GPU */
 
 /* status block, device resident, read back at the end of every hot-path call */
@@ -371,12 +372,15 @@ __device__ __forceinline__ void pg_philox(uint32_t c0, uint32_t c1, uint32_t c2,
  * Counter-based stream, one per (kind, timestep, entity): replaces the reference's single
  * sequential MT19937-64 stream rf() (src/tools.f90:33-43).  Contract (also implemented by the
  * oracle's rng_mode 1):  key = { seed_lo ^ kind*0x632BE5AB, seed_hi ^ tID },
- * counter = { draw/2, e0_lo, e0_hi, e1 }; each block yields two 53-bit uniforms on [0,1).
- * kinds: 1 ADVECT (e0 = particle slot), 2 DSMC (e0 = cell 0-based, e1 = candidate), 3 MCC (e0 = slot).
+ * counter = { word/4, e0_lo, e0_hi, e1 }.  The stream is the blocks' 32-bit words in order:
+ * rf() takes two words (lo, hi -> a 53-bit uniform on [0,1)), pick(n) takes one for n <= 65536.
+ * kinds: 1 ADVECT (e0 = particle slot), 2 DSMC (e0 = cell 0-based, e1 = candidate), 3 MCC_VAHEDI (e0 = slot),
+ * 4 MCC (e0 = slot).
  */
 struct PgRng {
-    uint32_t k0, k1, e0, e1, e2, ndraw;
-    uint32_t b2, b3;
+    uint32_t k0, k1, e0, e1, e2;
+    uint32_t ndraw;          /* words taken from the stream so far */
+    uint32_t w0, w1, w2, w3; /* the words of the current block that have not been taken yet, w0 first */
     __device__ __forceinline__ void init(unsigned long long seed, int kind, int tID, unsigned long long ent0,
                                          unsigned long long ent1) {
         k0 = (uint32_t)seed ^ ((uint32_t)kind * 0x632BE5ABu);
@@ -385,29 +389,44 @@ struct PgRng {
         e1 = (uint32_t)(ent0 >> 32);
         e2 = (uint32_t)ent1;
         ndraw = 0;
-        b2 = b3 = 0;
+        w0 = w1 = w2 = w3 = 0;
+    }
+    __device__ __forceinline__ uint32_t word() {
+        if ((ndraw & 3u) == 0) {
+            uint32_t o[4];
+            pg_philox(ndraw >> 2, e0, e1, e2, k0, k1, o);
+            w0 = o[0]; w1 = o[1]; w2 = o[2]; w3 = o[3];
+        }
+        ndraw++;
+        const uint32_t r = w0;
+        w0 = w1; w1 = w2; w2 = w3;
+        return r;
     }
     __device__ __forceinline__ double rf() {
-        uint32_t n = ndraw++;
-        uint32_t lo, hi;
-        if ((n & 1u) == 0) {
-            uint32_t o[4];
-            pg_philox(n >> 1, e0, e1, e2, k0, k1, o);
-            lo = o[0]; hi = o[1];
-            b2 = o[2]; b3 = o[3];
-        } else {
-            lo = b2; hi = b3;
-        }
+        const uint32_t lo = word();
+        const uint32_t hi = word();
         unsigned long long u = ((unsigned long long)hi << 32) | lo;
         return (double)(u >> 11) * (1.0 / 9007199254740992.0);
     }
-    /* resume a stream at draw n (n may be odd: the block is regenerated) */
+    /* INT(N*rf()) of the pair selection (ref: src/collisions.f90:263-271) clamped to N-1: one word of the stream
+     * for N <= 65536 (floor(N*word/2^32), bias <= N/2^32), so that the two indices and the acceptance draw of a
+     * candidate are exactly one Philox block; rf() for larger N */
+    __device__ __forceinline__ int pick(int n) {
+        int k;
+        if (n <= 65536) k = (int)__umulhi(word(), (uint32_t)n);
+        else k = (int)(n * rf());
+        return (k >= n) ? n - 1 : k;
+    }
+    /* resume a stream after n words (the current block is regenerated when n is not a multiple of 4) */
     __device__ __forceinline__ void seek(uint32_t n) {
         ndraw = n;
-        if (n & 1u) {
+        if (n & 3u) {
             uint32_t o[4];
-            pg_philox(n >> 1, e0, e1, e2, k0, k1, o);
-            b2 = o[2]; b3 = o[3];
+            pg_philox(n >> 2, e0, e1, e2, k0, k1, o);
+            const uint32_t s = n & 3u;
+            w0 = (s == 1) ? o[1] : (s == 2) ? o[2] : o[3];
+            w1 = (s == 1) ? o[2] : o[3];
+            w2 = o[3];
         }
     }
 };

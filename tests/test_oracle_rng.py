@@ -68,6 +68,42 @@ def test_philox_stream_contract(oracle_philox):
     assert all(0.0 <= d < 1.0 for d in draws)
 
 
+def test_philox_word_stream_pick_contract(oracle_philox, oracle):
+    """A collision candidate is ONE block: word 0 -> first index, word 1 -> second index (floor(N*word/2^32) for
+    N <= 65536), words 2,3 -> the acceptance draw.  Larger N and the MT19937 mode use INT(N*rf()) as the
+    reference does (collisions.f90:263-271)."""
+    o = oracle_philox
+    o.set_config(capi.make_config(rng_seed_global=65644, rank=0))
+    kind, tID, e0, e1 = 2, 3, 1234, 7
+    key = [(65644 & 0xFFFFFFFF) ^ ((kind * 0x632BE5AB) & 0xFFFFFFFF), tID]
+    blk0 = o.philox([0, e0, 0, e1], key)
+    blk1 = o.philox([1, e0, 0, e1], key)
+    o.rng_stream(kind, tID, e0, e1)
+    n = 40
+    assert o.pick(n) == (blk0[0] * n) >> 32 and o.pick(n) == (blk0[1] * n) >> 32
+    assert o.rf() == (((blk0[3] << 32) | blk0[2]) >> 11) * 2.0 ** -53
+    assert o.rf() == (((blk1[1] << 32) | blk1[0]) >> 11) * 2.0 ** -53       # the next block starts here
+    # a uniform may straddle two blocks: pick (word 2 of block 1), then rf = (word 3 of block 1, word 0 of block 2)
+    blk2 = o.philox([2, e0, 0, e1], key)
+    assert o.pick(7) == (blk1[2] * 7) >> 32
+    assert o.rf() == (((blk2[0] << 32) | blk1[3]) >> 11) * 2.0 ** -53
+    # large N: two words through rf()
+    o.rng_stream(kind, tID, e0, e1)
+    big = 10_000_000
+    u = (((blk0[1] << 32) | blk0[0]) >> 11) * 2.0 ** -53
+    assert o.pick(big) == int(big * u)
+    # uniformity of the one-word pick
+    o.rng_stream(1, 0, 99, 0)
+    k = np.array([o.pick(10) for _ in range(20000)])
+    assert k.min() == 0 and k.max() == 9
+    assert np.all(np.abs(np.bincount(k, minlength=10) - 2000) < 5 * np.sqrt(2000 * 0.9))
+    # sequential reference stream: INT(N*rf()) on the MT19937-64 draws
+    oracle.set_config(capi.make_config(rng_seed_global=65644, rank=0))
+    r = oracle.rf()
+    oracle.set_config(capi.make_config(rng_seed_global=65644, rank=0))
+    assert oracle.pick(40) == int(40 * r)
+
+
 def test_philox_streams_are_independent(oracle_philox):
     o = oracle_philox
     o.set_config(capi.make_config())
