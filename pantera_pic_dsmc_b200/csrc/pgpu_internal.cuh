@@ -86,15 +86,21 @@ struct __align__(32) PgVel { double vx, vy, vz; int sid, pad; };
 struct __align__(16) PgIe { double erot, evib; };
 /* Packed cell records (pgpu_api.cu build_packed_mesh): per face {outward normal(3), point(3)} = nf*6 doubles, then
  * 16 bytes of hop codes, cut into 16-byte chunks (tetrahedron 13, triangle 10, segment 7).  Cells are stored in
- * blocks of 8, chunk-major inside the block: chunk k of the block's 8 cells is one 128-byte line, so that lanes
- * working in nearby cells share their L1 wavefronts (see pgpu_advect.cu unstructured_iter). */
-#define PG_GEO_LINE 128
+ * blocks of PG_GEO_B, chunk-major inside the block: chunk k of the block's cells is contiguous (PG_GEO_B*16 bytes),
+ * so that lanes working in nearby cells share their L1 wavefronts (see pgpu_advect.cu unstructured_iter).  A larger
+ * block shares more wavefronts but spreads a record over more 128-byte lines (L1 capacity); PG_GEO_B = 1 is the
+ * plain cell-major record. */
+#ifndef PG_GEO_B
+#define PG_GEO_B 8
+#endif
+#define PG_GEO_LINE (16 * PG_GEO_B) /* bytes between consecutive chunks of a cell */
 #define PG_GEO_CHUNKS(nf) ((nf) * 3 + 1)
-#define PG_GEO_BLOCK_DOUBLES(nf) (PG_GEO_CHUNKS(nf) * 16)
+#define PG_GEO_BLOCK_DOUBLES(nf) (PG_GEO_CHUNKS(nf) * 2 * PG_GEO_B)
 #ifdef __CUDACC__
 /* address of chunk 0 of cell cell0 (0-based) */
 __device__ __forceinline__ const char* pg_geo_base(const double* geo, int cell0, int nch) {
-    return reinterpret_cast<const char*>(geo) + (size_t)(cell0 >> 3) * (size_t)(nch * PG_GEO_LINE) + (size_t)((cell0 & 7) * 16);
+    return reinterpret_cast<const char*>(geo) + (size_t)(cell0 / PG_GEO_B) * (size_t)(nch * PG_GEO_LINE) +
+           (size_t)((cell0 % PG_GEO_B) * 16);
 }
 /* a 32-byte particle record {3 doubles, 2 ints} as ONE 256-bit store (STG.E.ENL2.256) */
 __device__ __forceinline__ void pg_store_sector(void* p, double a, double b, double c, int i0, int i1) {
@@ -103,6 +109,17 @@ __device__ __forceinline__ void pg_store_sector(void* p, double a, double b, dou
                  "l"(__double_as_longlong(b)), "l"(__double_as_longlong(c)), "l"(w)
                  : "memory");
 }
+/* 32-byte records with a cache-streaming hint (LDG/STG.E.EF.ENL2.256): evict-first in L2 */
+struct __align__(32) PgRec32 { double a, b, c; unsigned long long w; };
+__device__ __forceinline__ PgRec32 pg_ld_stream(const void* p) {
+    PgRec32 v;
+    asm volatile("ld.global.cs.v4.b64 {%0,%1,%2,%3}, [%4];" : "=d"(v.a), "=d"(v.b), "=d"(v.c), "=l"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void pg_st_stream(void* p, const PgRec32& v) {
+    asm volatile("st.global.cs.v4.b64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v.a), "d"(v.b), "d"(v.c), "l"(v.w) : "memory");
+}
+
 /* double e of the record (e = 6*face + {0,1,2: normal, 3,4,5: point}) */
 __device__ __forceinline__ double pg_geo_at(const char* gb, int e) {
     return __ldg(reinterpret_cast<const double*>(gb + (e >> 1) * PG_GEO_LINE + (e & 1) * 8));
