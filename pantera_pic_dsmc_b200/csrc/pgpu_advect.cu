@@ -557,12 +557,32 @@ __device__ __forceinline__ int unstructured_iter(const PgDev& d, PgRng& g, PStat
                     remove = 1;
                     q.dtrim = 0.;
                 }
+            } else if (LEAN) {
+                /* A plain specular wall (no reactions, no charging, no tally this step) involves no random numbers
+                 * and no side effects: reflect here (ref: :1433-1443, same expressions as boundary_unstructured)
+                 * and go on.  Everything else is left untouched for the FULL pass. */
+                if (AXI || code > -PG_CODE_SPEC || d.tally_on) return IT_DEFER;
+                move_particle<AXI>(q, dtcoll);
+                q.dtrim = q.dtrim - dtcoll;
+                const double f0 = -pg_geo_at(gb, 6 * boundcoll + 0);
+                const double f1 = (DIMS >= 2) ? -pg_geo_at(gb, 6 * boundcoll + 1) : -0.;
+                const double f2 = (DIMS >= 3) ? -pg_geo_at(gb, 6 * boundcoll + 2) : -0.;
+                const double vdotn = q.vx * f0 + q.vy * f1 + q.vz * f2;
+                q.vx = q.vx - 2. * vdotn * f0;
+                q.vy = q.vy - 2. * vdotn * f1;
+                q.vz = q.vz - 2. * vdotn * f2;
+                dirty |= DIRTY_V;
+                if (++hops > PG_MAX_HOPS) {
+                    pg_set_err(d, PG_DEVERR_HOPS);
+                    remove = 1;
+                    q.dtrim = 0.;
+                }
             } else {
-                if (LEAN) return IT_DEFER;
                 move_particle<AXI>(q, dtcoll);
                 q.dtrim = q.dtrim - dtcoll;
                 if (AXI) dirty |= DIRTY_V; /* the axisymmetric move rotates the velocity */
-                boundary_unstructured<DIMS>(d, g, q, ic, boundcoll, code, nsel, remove, dirty);
+                boundary_unstructured<DIMS>(d, g, q, ic, boundcoll, (code <= -PG_CODE_SPEC) ? code + PG_CODE_SPEC : code, nsel,
+                                            remove, dirty);
                 if (++hops > PG_MAX_HOPS) {
                     pg_set_err(d, PG_DEVERR_HOPS);
                     remove = 1;

@@ -399,6 +399,9 @@ extern "C" int pgpu_set_bcs(pgpu_ctx* c, int nbc, const int32_t* particle_bc, co
     if ((rc = put(c, S_BC_ACCN, acc_n, (size_t)nbc, &d.bc_accn))) return rc;
     if ((rc = put(c, S_BC_ACCT, acc_t, (size_t)nbc, &d.bc_acct))) return rc;
     c->h_bc_volume.assign(volume_bc, volume_bc + nbc);
+    c->h_bc_particle.assign(particle_bc, particle_bc + nbc);
+    c->h_bc_field.assign(field_bc, field_bc + nbc);
+    c->h_bc_react.assign(react, react + nbc);
     c->mesh_dirty = c->mesh_set;
     return PGPU_OK;
 }
@@ -519,8 +522,21 @@ static int build_packed_mesh(pgpu_ctx* c) {
             }
         }
     }
-    for (int ic = 0; ic < nc; ic++) /* the hop codes ride in the same record: no dependent load in the face walk */
-        memcpy(slot(ic, 6 * nf), &code[(size_t)ic * nf], sizeof(int) * (size_t)nf);
+    /* the hop codes ride in the same record (no dependent load in the face walk); plain specular walls are
+     * marked so that the LEAN pass can reflect in line instead of deferring the particle (PG_CODE_SPEC) */
+    for (int ic = 0; ic < nc; ic++) {
+        int rec[4] = {0, 0, 0, 0};
+        for (int j = 0; j < nf; j++) {
+            int cd = code[(size_t)ic * nf + j];
+            if (cd < 0) {
+                int gi = -cd - 1;
+                if (c->h_bc_particle[gi] == PGPU_SPECULAR && !c->h_bc_react[gi] && c->h_bc_field[gi] != PGPU_DIELECTRIC_BC)
+                    cd -= PG_CODE_SPEC;
+            }
+            rec[j] = cd;
+        }
+        memcpy(slot(ic, 6 * nf), rec, sizeof(int) * (size_t)nf);
+    }
     if ((rc = put(c, S_FACE_GEO, geo.data(), geo.size(), &c->dev.face_geo))) return rc;
     if ((rc = put(c, S_FACE_CODE, code.data(), code.size(), &c->dev.face_code))) return rc;
     c->mesh_dirty = false;

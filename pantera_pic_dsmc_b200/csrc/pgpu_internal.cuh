@@ -61,6 +61,10 @@
 #define PG_ADVECT_CHUNK_MAX 1024
 #endif
 #define PG_ADVECT_CHUNK_MIN 64
+/* hop codes of the packed cell records: > 0 neighbour cell, 0 boundary without a physical group (remove),
+ * -pg boundary with physical group pg; -pg - PG_CODE_SPEC when that group is a plain specular wall (no wall
+ * reactions, no dielectric charging), which the LEAN advect pass reflects in line */
+#define PG_CODE_SPEC 0x40000000
 #define PG_MAX_HOPS 1000000 /* guard against a malformed mesh hanging the GPU */
 
 /* status block, device resident, read back at the end of every hot-path call */
@@ -257,7 +261,7 @@ struct pgpu_ctx {
     int64_t mcc_cell_nrho_cells = 0; /* cells covered by dev.mcc_cell_nrho */
     std::vector<double> h_node_coords, h_face_normal;
     std::vector<int32_t> h_cell_nodes, h_cell_neighbors, h_cell_faces_pg, h_cell_pg;
-    std::vector<int32_t> h_bc_volume;
+    std::vector<int32_t> h_bc_volume, h_bc_particle, h_bc_field, h_bc_react;
     bool mesh_set, mesh_dirty;
 
     /* owned device allocations (freed in destroy) */
