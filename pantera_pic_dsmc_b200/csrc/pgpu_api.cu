@@ -96,6 +96,7 @@ extern "C" int pgpu_create(pgpu_ctx** out, int device) {
     c->id_counter = 0;
     c->any_internal_dof = false; c->ie_seen = false;
     c->d_tile_first = nullptr; c->tile_alloc = 0; c->n_big = 0;
+    c->d_cell_order = nullptr; c->d_cell_bucket = nullptr;
     c->d_big_list = nullptr; c->d_big_bbox = nullptr; c->big_alloc = 0;
     c->d_cell_count = c->d_rank = c->d_cell_off = c->d_hitlist = nullptr;
     c->hit_capacity = 0; c->ncells_alloc = 0;
@@ -149,6 +150,7 @@ extern "C" int pgpu_destroy(pgpu_ctx* c) {
     free_planes(c->planes[1]);
     dev_free(c->d_cell_count); dev_free(c->d_rank); dev_free(c->d_cell_off); dev_free(c->d_hitlist);
     dev_free(c->d_tile_first); dev_free(c->d_big_list); dev_free(c->d_big_bbox);
+    dev_free(c->d_cell_order); dev_free(c->d_cell_bucket);
     dev_free(c->d_status);
     if (c->h_status) cudaFreeHost(c->h_status);
     dev_free(c->d_scan_tmp); dev_free(c->d_cand); dev_free(c->d_owner);
@@ -550,6 +552,10 @@ int pg_ensure_cell_arrays(pgpu_ctx* c) {
     dev_free(c->d_cell_off);
     if ((rc = dev_alloc(c, &c->d_cell_count, (size_t)ncells + 1))) return rc;
     if ((rc = dev_alloc(c, &c->d_cell_off, (size_t)ncells + 1))) return rc;
+    dev_free(c->d_cell_order);
+    dev_free(c->d_cell_bucket);
+    if ((rc = dev_alloc(c, &c->d_cell_order, (size_t)ncells))) return rc;
+    if ((rc = dev_alloc(c, &c->d_cell_bucket, (size_t)2 * PG_NBUCKET))) return rc;
     PG_CUDA(c, cudaMemset(c->d_cell_count, 0, sizeof(unsigned int) * ((size_t)ncells + 1)));
     PG_CUDA(c, cudaMemset(c->d_cell_off, 0, sizeof(unsigned int) * ((size_t)ncells + 1)));
     size_t tmp = 0;
@@ -591,6 +597,7 @@ void pg_refresh_dev(pgpu_ctx* c) {
     d.id_base = c->id_counter;
     d.use_ie = (c->any_internal_dof || c->dev.nr > 0 || c->ie_seen) ? 1 : 0;
     d.tile_first = c->d_tile_first;
+    d.cell_order = c->sorted ? c->d_cell_order : nullptr;
     d.ntiles = c->sorted ? (int)((c->np + PG_TILE_S - 1) / PG_TILE_S) : 0;
 }
 
@@ -960,6 +967,59 @@ __global__ void __launch_bounds__(256) tile_index_kernel(const unsigned int* __r
     if (o1 - o > PG_TILE_BIG) big_list[atomicAdd(&st->n_big, 1u)] = (unsigned int)c;
 }
 
+/* The collision kernel gives one lane to a cell, and a warp idles behind the lane with the most candidates.  The
+ * number of candidates goes with the square of the particle count, so the cells are handed out grouped by particle
+ * count (fullest first): three small kernels over the cell offsets -- sizes of the groups, their offsets, and a
+ * block-level counting-sort scatter of the cell ids.  Results do not depend on which lane takes which cell. */
+__global__ void __launch_bounds__(256) cell_bucket_count_kernel(const unsigned int* __restrict__ cell_off, int ncells,
+                                                                unsigned int* __restrict__ bucket) {
+    __shared__ unsigned int h[PG_NBUCKET];
+    for (int i = threadIdx.x; i < PG_NBUCKET; i += blockDim.x) h[i] = 0;
+    __syncthreads();
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < ncells) {
+        unsigned int n = cell_off[c + 1] - cell_off[c];
+        atomicAdd(&h[(n < 2 || n > PG_TILE_BIG) ? 0 : n], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < PG_NBUCKET; i += blockDim.x)
+        if (h[i]) atomicAdd(&bucket[i], h[i]);
+}
+/* bucket[0..NB) sizes -> bucket[NB..2NB) start of each group, groups laid out from the fullest cells down */
+__global__ void __launch_bounds__(288) cell_bucket_scan_kernel(unsigned int* __restrict__ bucket) {
+    __shared__ unsigned int h[PG_NBUCKET], o[PG_NBUCKET];
+    for (int i = threadIdx.x; i < PG_NBUCKET; i += blockDim.x) h[i] = bucket[i];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int run = 0;
+        for (int b = PG_NBUCKET - 1; b >= 0; b--) {
+            o[b] = run;
+            run += h[b];
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < PG_NBUCKET; i += blockDim.x) bucket[PG_NBUCKET + i] = o[i];
+}
+__global__ void __launch_bounds__(256) cell_bucket_fill_kernel(const unsigned int* __restrict__ cell_off, int ncells,
+                                                               unsigned int* __restrict__ bucket,
+                                                               unsigned int* __restrict__ order) {
+    __shared__ unsigned int h[PG_NBUCKET], base[PG_NBUCKET];
+    for (int i = threadIdx.x; i < PG_NBUCKET; i += blockDim.x) h[i] = 0;
+    __syncthreads();
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned int b = 0, r = 0;
+    if (c < ncells) {
+        unsigned int n = cell_off[c + 1] - cell_off[c];
+        b = (n < 2 || n > PG_TILE_BIG) ? 0 : n;
+        r = atomicAdd(&h[b], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < PG_NBUCKET; i += blockDim.x)
+        if (h[i]) base[i] = atomicAdd(&bucket[PG_NBUCKET + i], h[i]);
+    __syncthreads();
+    if (c < ncells) order[base[b] + r] = (unsigned int)c;
+}
+
 int pg_sort_impl(pgpu_ctx* c) {
     int ncells = pg_ncells(c);
     c->n_big = 0;
@@ -992,6 +1052,14 @@ int pg_sort_impl(pgpu_ctx* c) {
     tile_index_kernel<<<(unsigned int)((ncells + 255) / 256), 256, 0, c->stream>>>(c->d_cell_off, ncells, c->d_tile_first,
                                                                                   ntiles_max, c->d_big_list, c->d_status);
     c->launches++;
+    {
+        unsigned int cb = (unsigned int)((ncells + 255) / 256);
+        PG_CUDA(c, cudaMemsetAsync(c->d_cell_bucket, 0, sizeof(unsigned int) * 2 * PG_NBUCKET, c->stream));
+        cell_bucket_count_kernel<<<cb, 256, 0, c->stream>>>(c->d_cell_off, ncells, c->d_cell_bucket);
+        cell_bucket_scan_kernel<<<1, 288, 0, c->stream>>>(c->d_cell_bucket);
+        cell_bucket_fill_kernel<<<cb, 256, 0, c->stream>>>(c->d_cell_off, ncells, c->d_cell_bucket, c->d_cell_order);
+        c->launches += 3;
+    }
     PG_CUDA(c, cudaGetLastError());
     /* new particle count = total of the histogram; number of oversized cells */
     unsigned int* h = c->h_status->scratch;

@@ -310,7 +310,10 @@ __device__ __forceinline__ void pair_collide_fast(const PgDev& d, PgRng& g, doub
 template <bool IE>
 __global__ void __launch_bounds__(128, PG_CELL_MINBLOCKS) cell_collide_kernel(const __grid_constant__ PgDev d) {
     const unsigned int FULL = 0xffffffffu;
-    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    /* cells are handed out grouped by particle count (pg_sort_impl): the lanes of a warp then walk similar numbers
+     * of candidates instead of idling behind the fullest cell */
+    const long long c = (tid < d.ncells) ? (d.cell_order ? (long long)__ldg(&d.cell_order[tid]) : tid) : (long long)d.ncells;
     unsigned int o0 = 0;
     int n = 0;
     if (c < d.ncells) {

@@ -42,6 +42,7 @@
 #define PG_TILE_S 512
 #endif
 #define PG_TILE_BIG 256
+#define PG_NBUCKET (PG_TILE_BIG + 1) /* cells grouped by particle count 0..PG_TILE_BIG (oversized and <2 -> bucket 0) */
 #define PG_TILE_CAP (PG_TILE_S + PG_TILE_BIG)  /* >= PG_TILE_S - 1 + PG_TILE_BIG */
 #define PG_TILE_MAXC (PG_TILE_CAP / 2)         /* cells of >= 2 particles that fit PG_TILE_CAP slots */
 #ifndef PG_TILE_THREADS
@@ -226,6 +227,7 @@ struct PgDev {
     long long id_base;        /* ID counter for particles created on the device */
     int use_ie;               /* 1: the ie plane is live (some particle can hold internal energy) */
     const unsigned int* tile_first; /* [ntiles+1] first cell of every collision tile (valid while sorted) */
+    const unsigned int* cell_order; /* [ncells] the cells grouped by particle count, fullest first (valid while sorted) */
     int ntiles;
     /* emigrant bookkeeping in the ADVECT epilogue (nranks > 1): a particle whose final cell belongs to another
      * rank is not histogrammed; its slot goes to emig_list and its destination is counted in xrow, so that
@@ -276,6 +278,8 @@ struct pgpu_ctx {
     bool has_dtrim, sorted, hist_valid, maybe_tombstones;
     bool any_internal_dof, ie_seen; /* species with ROTDOF/VIBDOF != 0; nonzero EROT/EVIB seen in an upload */
     unsigned int* d_tile_first;
+    unsigned int* d_cell_order;  /* [ncells] */
+    unsigned int* d_cell_bucket; /* [2][PG_NBUCKET] bucket sizes, then bucket cursors */
     long long tile_alloc;
     unsigned int n_big;             /* cells beyond PG_TILE_BIG particles in the current sorted store */
     unsigned int* d_big_list;       /* [n_big] their cell ids */
