@@ -200,7 +200,9 @@ def main():
     n_local = len(w.particles)
     gpu = capi.load_gpu(local_rank)
     # head-room for the append region and, with N > 1, for a strip that gains more immigrants than it loses
-    w.cfg.capacity = int(n_local * (1.02 if world == 1 else 1.06)) + 1024
+    # (the channel has a 100 m/s drift towards specular end caps: the downstream strip gains ~0.3 % per step at full
+    #  size, and a store that outgrows its capacity is re-allocated in the middle of a timed step)
+    w.cfg.capacity = int(n_local * (1.02 if world == 1 else 1.25)) + 1024
     wl.apply(gpu, w)
     if world > 1:
         uid = [gpu.comm_unique_id() if rank == 0 else None]

@@ -74,15 +74,16 @@ def _worker(rank, world, port, out_dir):
 
 
 @pytest.mark.timeout(600)
-def test_two_gpu_run_steps_with_nccl_exchange(tmp_path):
+@pytest.mark.parametrize("world", [2, 4])
+def test_multi_gpu_run_steps_with_nccl_exchange(tmp_path, world):
+    """world = 4: the interior strips exchange with two neighbours each (grouped send/recv with two segments)."""
     import torch
     import torch.multiprocessing as mp
 
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
     from pantera_pic_dsmc_b200 import capi, workloads as wl
 
-    world = 2
     mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     res = [open(tmp_path / f"ok{r}").read().split() for r in range(world)]
     assert all(r[0] == "1" for r in res), res
