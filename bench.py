@@ -259,7 +259,8 @@ def main():
                            "collide": "cell_collide_kernel"}[dom],
                 "kernel_ms_per_launch": grp[dom], "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs, burst copy)",
                 "algorithmic_bytes_per_particle": bytes_grp[dom], "algorithmic_bytes_per_launch": bytes_grp[dom] * n_now,
-                "note": "this kernel is issue/LSU-bound, not HBM-bound (DESIGN.md section 3, profiles/r01*)",
+                "note": ("only the sort is HBM-bound (DRAM traffic at 85 % of the measured peak); ADVECT is bound by the L1 data pipe "
+                         "(wavefronts 76-82 %), the collisions by DRAM latency (DESIGN.md section 3, profiles/r01o_*)"),
                 "whole_step": {"achieved": ach_step, "frac": ach_step / peak, "algorithmic_bytes_per_particle": B_ALG_RESTATED,
                                "survey_8d": {"achieved": ach_step_survey, "frac": ach_step_survey / peak,
                                              "algorithmic_bytes_per_particle": B_ALG}},
