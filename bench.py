@@ -333,7 +333,7 @@ def main():
             g.close()
 
     cpu = None
-    if rank == 0 and not args.no_cpu:
+    if rank == 0 and world == 1 and not args.no_cpu:  # the CPU baseline is reported at N = 1 only
         cpu = cpu_baseline(args)
 
     if rank == 0:

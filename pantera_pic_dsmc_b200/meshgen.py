@@ -92,10 +92,9 @@ def _finish_boundary(m: Mesh):
     m.boundary_area = m.face_area.ravel(order="F")[flat].copy() if m.face_area is not None else np.ones(n)
 
 
-def derive_3d(xyz: np.ndarray, tets0: np.ndarray, face_pg: np.ndarray, cell_pg: Optional[np.ndarray] = None) -> Mesh:
-    """xyz (nn,3); tets0 (nc,4) 0-based, positively oriented; face_pg (nc,4) 1-based pg or -1."""
-    nn, nc = xyz.shape[0], tets0.shape[0]
-    P = xyz[tets0]  # (nc,4,3)
+def _tet_geometry(P: np.ndarray, fn, t1, t2, area, bc, vol):
+    """Face normals/tangents/areas, volume and P1 basis coefficients of the tets P (n,4,3), written into the output
+    slices.  Formulas: src/grid_and_partition.f90:1843-1850, 1932-1983, 1992-2039."""
     A = P[:, 1] - P[:, 0]
     B = P[:, 2] - P[:, 0]
     Cc = P[:, 3] - P[:, 0]
@@ -103,26 +102,26 @@ def derive_3d(xyz: np.ndarray, tets0: np.ndarray, face_pg: np.ndarray, cell_pg: 
         Cc[:, 2] * (A[:, 0] * B[:, 1] - A[:, 1] * B[:, 0])
     if np.any(det <= 0):
         raise ValueError("tets must be positively oriented (SURVEY App. E)")
-    vol = np.abs(det) / 6.0
-    nb = _neighbors_from_faces(tets0, FACE_LOCAL_3D, nn)
-    fn = np.zeros((nc, 4, 3))
-    t1 = np.zeros((nc, 4, 3))
-    t2 = np.zeros((nc, 4, 3))
-    area = np.zeros((nc, 4))
+    vol[:] = np.abs(det) / 6.0
+    col = [[np.ascontiguousarray(P[:, v, k]) for k in range(3)] for v in range(4)]  # col[node][axis], contiguous
     for j in range(4):
-        a, b, c = (P[:, FACE_LOCAL_3D[j, i]] for i in range(3))
-        cr = np.cross(b - a, c - a)
-        nrm = np.linalg.norm(cr, axis=1)
-        fn[:, j] = cr / nrm[:, None]
+        # explicit component formulas on contiguous columns; same operations, in the same order, as
+        # np.cross / np.linalg.norm on the (n,3) arrays, so the values are bit-identical
+        ia, ib, ic_ = (int(FACE_LOCAL_3D[j, i]) for i in range(3))
+        u = [col[ib][k] - col[ia][k] for k in range(3)]
+        w = [col[ic_][k] - col[ia][k] for k in range(3)]
+        cr = [u[1] * w[2] - u[2] * w[1], u[2] * w[0] - u[0] * w[2], u[0] * w[1] - u[1] * w[0]]
+        nrm = np.sqrt(cr[0] * cr[0] + cr[1] * cr[1] + cr[2] * cr[2])
+        f = [cr[k] / nrm for k in range(3)]
         area[:, j] = 0.5 * nrm
-        ba = b - a
-        t1[:, j] = ba / np.linalg.norm(ba, axis=1)[:, None]
-        t2[:, j] = np.cross(fn[:, j], t1[:, j])
-    x, y, z = (P[:, :, i] for i in range(3))
-    X1, X2, X3, X4 = (x[:, i] for i in range(4))
-    Y1, Y2, Y3, Y4 = (y[:, i] for i in range(4))
-    Z1, Z2, Z3, Z4 = (z[:, i] for i in range(4))
-    bc = np.zeros((nc, 4, 4))  # [cell, basis i, coeff j]
+        un = np.sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2])
+        ta = [u[k] / un for k in range(3)]
+        tb = [f[1] * ta[2] - f[2] * ta[1], f[2] * ta[0] - f[0] * ta[2], f[0] * ta[1] - f[1] * ta[0]]
+        for k in range(3):
+            fn[:, j, k] = f[k]
+            t1[:, j, k] = ta[k]
+            t2[:, j, k] = tb[k]
+    (X1, Y1, Z1), (X2, Y2, Z2), (X3, Y3, Z3), (X4, Y4, Z4) = col
     bc[:, 0, 0] = Y2 * Z3 - Y3 * Z2 - Y2 * Z4 + Y4 * Z2 + Y3 * Z4 - Y4 * Z3
     bc[:, 0, 1] = -X2 * Z3 + X3 * Z2 + X2 * Z4 - X4 * Z2 - X3 * Z4 + X4 * Z3
     bc[:, 0, 2] = X2 * Y3 - X3 * Y2 - X2 * Y4 + X4 * Y2 + X3 * Y4 - X4 * Y3
@@ -139,7 +138,25 @@ def derive_3d(xyz: np.ndarray, tets0: np.ndarray, face_pg: np.ndarray, cell_pg: 
     bc[:, 3, 1] = X1 * Z2 - X2 * Z1 - X1 * Z3 + X3 * Z1 + X2 * Z3 - X3 * Z2
     bc[:, 3, 2] = -X1 * Y2 + X2 * Y1 + X1 * Y3 - X3 * Y1 - X2 * Y3 + X3 * Y2
     bc[:, 3, 3] = X1 * Y2 * Z3 - X2 * Y1 * Z3 - X1 * Y3 * Z2 + X3 * Y1 * Z2 + X2 * Y3 * Z1 - X3 * Y2 * Z1
-    bc = -bc / 6.0 / vol[:, None, None]
+    bc[:] = -bc / 6.0 / vol[:, None, None]
+
+
+def derive_3d(xyz: np.ndarray, tets0: np.ndarray, face_pg: np.ndarray, cell_pg: Optional[np.ndarray] = None) -> Mesh:
+    """xyz (nn,3); tets0 (nc,4) 0-based, positively oriented; face_pg (nc,4) 1-based pg or -1."""
+    nn, nc = xyz.shape[0], tets0.shape[0]
+    nb = _neighbors_from_faces(tets0, FACE_LOCAL_3D, nn)
+    fn = np.zeros((nc, 4, 3))
+    t1 = np.zeros((nc, 4, 3))
+    t2 = np.zeros((nc, 4, 3))
+    area = np.zeros((nc, 4))
+    bc = np.zeros((nc, 4, 4))  # [cell, basis i, coeff j]
+    vol = np.zeros(nc)
+    # in chunks: the ~450 element-wise operations per cell are memory-bound, and with cache-sized temporaries they
+    # run ~4x faster than on 10^7-element arrays (element-wise, so the values do not depend on the chunking)
+    CH = 1 << 14
+    for a in range(0, nc, CH):
+        b = min(nc, a + CH)
+        _tet_geometry(xyz[tets0[a:b]], fn[a:b], t1[a:b], t2[a:b], area[a:b], bc[a:b], vol[a:b])
     nbr1 = np.where(nb >= 0, nb + 1, -1).astype(np.int32)
     m = Mesh(
         dims=3, nn=nn, nc=nc,
