@@ -388,14 +388,17 @@ def c5_channel_strip(ncx: int, ncy: int, ncz: int, n: int, rank: int = 0, world:
     bcs = dict(particle_bc=[capi.SPECULAR, capi.SPECULAR, capi.DIFFUSE, capi.DIFFUSE, capi.SPECULAR, capi.SPECULAR],
                wall_temp=[wall_temp] * 6, acc_n=[1.0] * 6, acc_t=[1.0] * 6)
     p = pinned_particles(n) if pinned else np.zeros(n, dtype=capi.PARTICLE_DTYPE)
-    rng = np.random.default_rng(seed)
     cn = np.asarray(mesh.cell_nodes)
     xyz = np.asarray(mesh.node_coords)
     sig = np.sqrt(KB * T0 / m)
-    chunk = 4_000_000
-    for a in range(0, n, chunk):
+    chunk = 2_000_000
+
+    def fill(a):
+        # one generator per chunk (seeded by (seed, chunk index)): chunks are independent, so they are filled by a
+        # few host threads -- NumPy releases the GIL in the generators, the gathers and the element-wise kernels
         b = min(n, a + chunk)
         k = b - a
+        rng = np.random.default_rng([seed, a // chunk])
         ci = rng.integers(rank * ncx, (rank + 1) * ncx, k)
         cj = rng.integers(0, ncy, k)
         ck = rng.integers(0, ncz, k)
@@ -416,5 +419,20 @@ def c5_channel_strip(ncx: int, ncy: int, ncz: int, n: int, rank: int = 0, world:
         q["S_ID"] = 1
         q["ID"] = (np.arange(a, b, dtype=np.int64) << 8) + rank
         q["DUMP_TRAJ"] = 0
+
+    starts = list(range(0, n, chunk))
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    local_world = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
+    nthreads = max(1, min(8, cores // local_world, len(starts)))
+    if nthreads > 1:
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(nthreads) as ex:
+            list(ex.map(fill, starts))
+    else:
+        for a in starts:
+            fill(a)
     return Workload("C5 3-D tet channel strip", cfg, sp, p, mesh=mesh, bcs=bcs,
                     notes=f"h={h:.4g} nu={nu:.5g} dt={dt:.4g} nc={mesh.nc} world={world}")
