@@ -308,7 +308,7 @@ __device__ __forceinline__ void pair_collide_fast(const PgDev& d, PgRng& g, doub
  * once.  Cells with more than PG_TILE_BIG particles are left to the GLOBAL path.
  */
 template <bool IE>
-__global__ void __launch_bounds__(128, PG_CELL_MINBLOCKS) cell_collide_kernel(const __grid_constant__ PgDev d) {
+__global__ void __launch_bounds__(128, IE ? PG_CELL_MINBLOCKS_IE : PG_CELL_MINBLOCKS) cell_collide_kernel(const __grid_constant__ PgDev d) {
     const unsigned int FULL = 0xffffffffu;
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     /* cells are handed out grouped by particle count (pg_sort_impl): the lanes of a warp then walk similar numbers

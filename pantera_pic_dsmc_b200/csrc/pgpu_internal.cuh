@@ -51,6 +51,11 @@
 #ifndef PG_CELL_MINBLOCKS
 #define PG_CELL_MINBLOCKS 8
 #endif
+/* the instantiation with internal energy, reactions and product creation needs more registers: at 8 blocks/SM (64
+ * registers) it spills 500 bytes, at 6 (80 registers) almost nothing */
+#ifndef PG_CELL_MINBLOCKS_IE
+#define PG_CELL_MINBLOCKS_IE 6
+#endif
 #ifndef PG_CELL_TRIES
 #define PG_CELL_TRIES 2 /* acceptance tests a lane runs before the warp re-converges for the deflections */
 #endif
