@@ -111,7 +111,7 @@ def cpu_baseline(args, seconds=12.0):
     """Oracle (single thread) on a bounded sample of the same workload: a smaller box, same cell size,
     same particles per cell, same dt.  Reported, not the target."""
     from pantera_pic_dsmc_b200 import capi, workloads as wl
-    w = wl.c5_channel_strip(16, 16, 16, n=16 * 16 * 16 * 6 * 40, rank=0, world=1, seed=99)
+    w = wl.c5_channel_strip(24, 24, 24, n=24 * 24 * 24 * 6 * 40, rank=0, world=1, seed=99)  # 3.3e6 particles, 318 MB: out of cache
     o = capi.load_oracle(rng_mode=0)
     wl.apply(o, w)
     o.run_steps(1, 1)  # warm-up: first touch
@@ -125,7 +125,7 @@ def cpu_baseline(args, seconds=12.0):
     sec = o.get_timings()
     o.close()
     return {"value": n * steps / dt, "unit": "particle-timesteps/s", "cores": 1, "kind": "port",
-            "sample": f"C5 strip 16x16x16 cubes, {n} particles, {steps} steps, single thread, MT19937-64 stream",
+            "sample": f"C5 strip 24x24x24 cubes, {n} particles, {steps} steps, single thread, MT19937-64 stream",
             "phase_seconds": {"move": float(sec[0]), "sort": float(sec[1]), "collide": float(sec[2])}}
 
 
