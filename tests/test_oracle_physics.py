@@ -214,6 +214,26 @@ def test_vss_collision_frequency_matches_kinetic_theory(oracle):
     assert abs(ncoll - expect) < 4 * np.sqrt(expect) + 0.01 * expect
 
 
+@pytest.mark.parametrize("nx,ny", [(1, 1), (8, 8)])
+def test_vss_collision_frequency_on_the_device_stream_contract(oracle_philox, nx, ny):
+    """Same kinetic-theory check on the counter-based stream the CUDA kernels use (rng_mode 1): one-word index picks
+    for cells of up to 65536 particles (8x8 cells of ~300), two-word picks above (one cell of 20000... below the
+    limit too, so a 70000-particle cell is run as well), selector draw skipped for argon."""
+    n, steps = (70000, 6) if (nx, ny) == (1, 1) else (20000, 20)
+    w = wl.c1_argon_box(n, nx=nx, ny=ny, T=(400.0, 400.0, 400.0))
+    wl.apply(oracle_philox, w)
+    m = w.species.mass
+    e0, p0 = util.kinetic_energy(w.particles, m), util.momentum(w.particles, m)
+    ncoll, _ = oracle_philox.run_steps(1, steps)
+    # NTC on few-particle cells is biased low by O(1/N_cell) (pairs N(N-1)/2 against N^2/2): correct the estimate
+    npc = n / (nx * ny)
+    expect = 0.1 * n * steps * (1.0 - 1.0 / npc)
+    assert abs(ncoll - expect) < 4 * np.sqrt(expect) + 0.015 * expect, (ncoll, expect)
+    q = oracle_philox.download_particles()
+    assert util.kinetic_energy(q, m) == pytest.approx(e0, rel=1e-11)
+    assert np.allclose(util.momentum(q, m), p0, atol=1e-11 * np.sqrt(e0 * m[0] * n))
+
+
 def test_vss_conserves_momentum_energy_and_relaxes(oracle):
     n = 20000
     w = wl.c1_argon_box(n, T=(600.0, 300.0, 300.0))
