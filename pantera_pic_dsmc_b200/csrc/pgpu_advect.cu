@@ -425,6 +425,100 @@ __device__ void boundary_unstructured(const PgDev& d, PgRng& g, PState& q, int i
 
 enum { IT_NONE = 0, IT_CONTINUE = 1, IT_DONE = 2, IT_DEFER = 3 };
 
+/*
+ * Face selection of one trip on a non-axisymmetric unstructured grid, ref: src/timecycle.f90:1257-1305:
+ *     DO I = 1, NFACES:  VN = V.n_I;  DX = (P_I - X).n_I;  IF (VN >= 0 .AND. VN*DTCOLL >= DX) DTCOLL = DX/VN; BOUNDCOLL = I
+ * (sequential tightening, '>=' tie rule, last one wins).  The kernel is bound by the L1 data pipe -- the bytes each
+ * lane pulls per trip (ncu r01o: l1tex__data_pipe_lsu_wavefronts 76 %) -- so the 48 bytes per face of FP64 operands
+ * are not read for every face.  A 16-byte single-precision FILTER record per face {float(n), float(P.n)} gives VN and
+ * DX with rigorous error bounds, which classify every face as
+ *     fail   it cannot pass the test for any DTCOLL <= DTRIM (VN < 0 for certain, or VN*DTRIM < DX for certain);
+ *     pass   it passes the test against DTRIM for certain; its crossing time is then at most t_hi;
+ *     open   anything else.
+ * With T = min t_hi over the `pass` faces, a face whose crossing time is certainly > T (t_lo > T, relative margin
+ * 1e-6) cannot change the outcome of the sequential loop: tested after the face of T it fails against the tightened
+ * DTCOLL, tested before it whatever it does leaves DTCOLL above T, where the face of T still passes and overwrites
+ * it (the rounded product VN*DTCOLL is monotone in DTCOLL, and the margins are nine orders of magnitude above the
+ * FP64 rounding of the test).  So the reference loop restricted to the remaining RELEVANT faces, run on the exact
+ * FP64 operands in the original face order, returns the same (DTCOLL, BOUNDCOLL) bit for bit; that is what is
+ * executed.  On average one face per crossing is relevant and none on the final flight (5 instead of 13 sixteen-byte
+ * loads, or 8 with one exact face); a particle near an edge or a vertex, NaNs and degenerate inputs simply make more
+ * faces relevant.  Bounds (u = 2^-24): |VN_f - VN| <= 5u.sum|v_k||n_k| <= 1e-6.(|vx|+|vy|+|vz|) =: EV and
+ * |DX_f - DX| <= 6u.sum|x_k| + 2u.|P.n| <= 1e-6.(|x|+|y|+|z| + |c_f|) =: ED, each with a 2.8x margin over the worst case
+ * of rounding the inputs and evaluating in single precision in any order.
+ */
+template <int DIMS>
+__device__ __forceinline__ void select_face(const PgDev& d, const PState& q, int ic, double& dtcoll, int& boundcoll,
+                                            int& codesel, double* nsel) {
+    constexpr int NF = DIMS + 1;
+    const char* fb = pg_filt_base(d.face_filt, ic - 1, NF + 1);
+    float4 F[NF];
+#pragma unroll
+    for (int i = 0; i < NF; i++) F[i] = __ldg(reinterpret_cast<const float4*>(fb + i * PG_GEO_LINE));
+    const int4 codes = __ldg(reinterpret_cast<const int4*>(fb + NF * PG_GEO_LINE));
+
+    const float INF = __int_as_float(0x7f800000);
+    const float vxf = (float)q.vx, vyf = (float)q.vy, vzf = (float)q.vz;
+    const float xf = (float)q.x, yf = (float)q.y, zf = (float)q.z;
+    float V1 = fabsf(vxf), X1 = fabsf(xf);
+    if (DIMS >= 2) { V1 += fabsf(vyf); X1 += fabsf(yf); }
+    if (DIMS >= 3) { V1 += fabsf(vzf); X1 += fabsf(zf); }
+    const float EV = 1.e-6f * V1;
+    const float dtf = (float)dtcoll;
+    const float dt_hi = dtf * (1.f + 1.e-6f), dt_lo = dtf * (1.f - 1.e-6f);
+    float t_lo[NF];
+    float T = INF;
+    unsigned int open = 0u;
+#pragma unroll
+    for (int i = 0; i < NF; i++) {
+        float vnf = vxf * F[i].x, xn = xf * F[i].x;
+        if (DIMS >= 2) { vnf += vyf * F[i].y; xn += yf * F[i].y; }
+        if (DIMS >= 3) { vnf += vzf * F[i].z; xn += zf * F[i].z; }
+        const float dxf = F[i].w - xn;
+        const float ED = 1.e-6f * (X1 + fabsf(F[i].w));
+        const float vn_hi = vnf + EV, vn_lo = vnf - EV, dx_lo = dxf - ED, dx_hi = dxf + ED;
+        const bool fail = (vn_hi < 0.f) || (dx_lo > 0.f && vn_hi * dt_hi * (1.f + 1.e-6f) < dx_lo);
+        const bool pass = (vn_lo > 0.f) && (vn_lo * dt_lo * (1.f - 1.e-6f) > dx_hi);
+        t_lo[i] = (dx_lo > 0.f) ? (dx_lo / vn_hi) * (1.f - 1.e-6f) : -INF;
+        if (pass) T = fminf(T, (fmaxf(dx_hi, 0.f) / vn_lo) * (1.f + 1.e-6f));
+        if (!fail) open |= 1u << i; /* (a NaN anywhere compares false: the face stays open) */
+    }
+    unsigned int rel = 0u;
+#pragma unroll
+    for (int i = 0; i < NF; i++)
+        if (((open >> i) & 1u) && !(t_lo[i] > T)) rel |= 1u << i;
+
+    /* the reference loop on the exact operands, relevant faces only, original order */
+    const double* ex = d.face_exact + (size_t)(ic - 1) * (size_t)(NF * 6);
+    while (rel) {
+        const int i = __ffs((int)rel) - 1;
+        rel &= rel - 1u;
+        const double2 a = __ldg(reinterpret_cast<const double2*>(ex + 6 * i));
+        const double2 b = __ldg(reinterpret_cast<const double2*>(ex + 6 * i + 2));
+        const double2 c = __ldg(reinterpret_cast<const double2*>(ex + 6 * i + 4));
+        /* normal (a.x, a.y, b.x), face node (b.y, c.x, c.y) */
+        double vn, dx;
+        if (DIMS == 1) {
+            vn = q.vx * a.x;
+            dx = (b.y - q.x) * a.x;
+        } else if (DIMS == 2) {
+            vn = q.vx * a.x + q.vy * a.y;
+            dx = (b.y - q.x) * a.x + (c.x - q.y) * a.y;
+        } else {
+            vn = q.vx * a.x + q.vy * a.y + q.vz * b.x;
+            dx = (b.y - q.x) * a.x + (c.x - q.y) * a.y + (c.y - q.z) * b.x;
+        }
+        if (vn >= 0. && vn * dtcoll >= dx) {
+            dtcoll = dx / vn;
+            boundcoll = i;
+            nsel[0] = a.x;
+            nsel[1] = (DIMS >= 2) ? a.y : 0.;
+            nsel[2] = (DIMS >= 3) ? b.x : 0.;
+        }
+    }
+    codesel = (boundcoll == 0) ? codes.x : (boundcoll == 1) ? codes.y : (boundcoll == 2) ? codes.z : codes.w;
+}
+
 /* One trip of the ADVECT while-loop (one cell crossing or the final flight) of a particle on an
  * unstructured grid. ref: src/timecycle.f90:1166-1657.  IT_DEFER: LEAN and the particle reached a
  * boundary event; it is left untouched for the FULL pass. */
@@ -436,28 +530,14 @@ __device__ __forceinline__ int unstructured_iter(const PgDev& d, PgRng& g, PStat
     {
         double dtcoll = q.dtrim;
         int boundcoll = -1;
-        /* The packed cell records are stored in BLOCKS of 8 cells, chunk-major inside a block (pgpu_internal.cuh
-         * PG_GEO_*): chunk k (16 bytes) of the 8 cells of a block forms one 128-byte line.  After their first hop
-         * the lanes of a warp sit in different cells, every load instruction costs one L1 wavefront per distinct
-         * LINE it touches, and this kernel is bound by exactly that pipe (ncu: l1tex__data_pipe_lsu_wavefronts
-         * ~75 % with cell-major records).  Neighbouring cells are numbered close to each other by any mesh
-         * generator, so with this layout lanes in nearby cells share their wavefronts.  The hop codes ride in the
-         * last chunk of the record (no dependent load). */
-        constexpr int NCH = PG_GEO_CHUNKS(NF);
-        const char* gb = pg_geo_base(d.face_geo, ic - 1, NCH);
-        double G[NF * 6];
-        if (!AXI) {
-#pragma unroll
-            for (int k = 0; k < NF * 3; k++) {
-                const double2 v = __ldg(reinterpret_cast<const double2*>(gb + k * PG_GEO_LINE));
-                G[2 * k] = v.x; G[2 * k + 1] = v.y;
-            }
-        }
-        const int4 codes = __ldg(reinterpret_cast<const int4*>(gb + (NF * 3) * PG_GEO_LINE));
-        int codesel = 0; /* hop code of the face selected so far (a predicated move per face, no branch) */
-        double nsel[3] = {0., 0., 0.};
+        int codesel = 0; /* hop code of the face selected so far */
+        double nsel[3] = {0., 0., 0.}; /* its outward normal */
         if (AXI) {
-            /* ref: :1173-1253 */
+            /* ref: :1173-1253.  The axisymmetric walk reads the double-precision chunked record (PG_GEO_*): blocks of
+             * 8 cells, chunk-major, so that lanes in nearby cells share their L1 wavefronts. */
+            constexpr int NCH = PG_GEO_CHUNKS(NF);
+            const char* gb = pg_geo_base(d.face_geo, ic - 1, NCH);
+            const int4 codes = __ldg(reinterpret_cast<const int4*>(gb + (NF * 3) * PG_GEO_LINE));
 #pragma unroll 1
             for (int i = 0; i < 3; i++) {
                 double test[2];
@@ -492,56 +572,7 @@ __device__ __forceinline__ int unstructured_iter(const PgDev& d, PgRng& g, PStat
                 }
             }
         } else {
-            /* ref: :1257-1305 sequential tightening, '>=' tie rule (last wins).
-             * VN and DX of a face do not depend on the faces before it, so they are evaluated for all faces
-             * first (independent loads and arithmetic, in flight together) and the tightening then runs over
-             * registers.  Same operations on the same operands as the reference's single loop. */
-            double vn[NF], dx[NF];
-#pragma unroll
-            for (int i = 0; i < NF; i++) {
-                const double* f = &G[6 * i]; /* (nx, ny, nz, px, py, pz) of face i */
-                if (DIMS == 1) {
-                    vn[i] = q.vx * f[0];
-                    dx[i] = (f[3] - q.x) * f[0];
-                } else if (DIMS == 2) {
-                    vn[i] = q.vx * f[0] + q.vy * f[1];
-                    dx[i] = (f[3] - q.x) * f[0] + (f[4] - q.y) * f[1];
-                } else {
-                    vn[i] = q.vx * f[0] + q.vy * f[1] + q.vz * f[2];
-                    dx[i] = (f[3] - q.x) * f[0] + (f[4] - q.y) * f[1] + (f[5] - q.z) * f[2];
-                }
-            }
-            /* The quotient DX/VN of a face does not depend on the faces before it either, only the DECISION to
-             * take it does (through DTCOLL).  DTCOLL only ever shrinks from DTRIM and VN >= 0, so by monotonicity
-             * of the rounded product  VN*DTCOLL >= DX  implies  VN*DTRIM >= DX : the faces that can be taken are
-             * known up front, their four divisions are independent (in flight together instead of chained through
-             * DTCOLL), and the sequential tightening is left with a multiply and a compare per face.  Lanes that
-             * cannot take a face divide 1/1: a particle that has just crossed a face sits EXACTLY on it (dx == 0),
-             * which would send the whole warp through the slow path of the FP64 division for a discarded result.
-             * Same operations on the same operands as the reference for every face that is taken. */
-            double quo[NF];
-            bool cand[NF];
-            const double dt0 = dtcoll;
-#pragma unroll
-            for (int i = 0; i < NF; i++) {
-                cand[i] = (vn[i] >= 0. && vn[i] * dt0 >= dx[i]);
-                double num = cand[i] ? dx[i] : 1., den = cand[i] ? vn[i] : 1.;
-                asm("" : "+d"(num), "+d"(den)); /* opaque: keeps the selects in front of the division */
-                quo[i] = num / den;
-            }
-#pragma unroll
-            for (int i = 0; i < NF; i++) {
-                const bool take = cand[i] && (vn[i] * dtcoll >= dx[i]);
-                if (take) {
-                    dtcoll = quo[i]; boundcoll = i;
-                    codesel = (i == 0) ? codes.x : (i == 1) ? codes.y : (i == 2) ? codes.z : codes.w;
-                }
-            }
-            if (!LEAN && boundcoll != -1) { /* outward normal of the face that was hit (boundary models) */
-                nsel[0] = pg_geo_at(gb, 6 * boundcoll + 0);
-                nsel[1] = (DIMS >= 2) ? pg_geo_at(gb, 6 * boundcoll + 1) : 0.;
-                nsel[2] = (DIMS >= 3) ? pg_geo_at(gb, 6 * boundcoll + 2) : 0.;
-            }
+            select_face<DIMS>(d, q, ic, dtcoll, boundcoll, codesel, nsel);
         }
 
         if (boundcoll != -1) {
@@ -564,9 +595,9 @@ __device__ __forceinline__ int unstructured_iter(const PgDev& d, PgRng& g, PStat
                 if (AXI || code > -PG_CODE_SPEC || d.tally_on) return IT_DEFER;
                 move_particle<AXI>(q, dtcoll);
                 q.dtrim = q.dtrim - dtcoll;
-                const double f0 = -pg_geo_at(gb, 6 * boundcoll + 0);
-                const double f1 = (DIMS >= 2) ? -pg_geo_at(gb, 6 * boundcoll + 1) : -0.;
-                const double f2 = (DIMS >= 3) ? -pg_geo_at(gb, 6 * boundcoll + 2) : -0.;
+                const double f0 = -nsel[0];
+                const double f1 = (DIMS >= 2) ? -nsel[1] : -0.;
+                const double f2 = (DIMS >= 3) ? -nsel[2] : -0.;
                 const double vdotn = q.vx * f0 + q.vy * f1 + q.vz * f2;
                 q.vx = q.vx - 2. * vdotn * f0;
                 q.vy = q.vy - 2. * vdotn * f1;
@@ -985,32 +1016,36 @@ __global__ void __launch_bounds__(128, PG_ADVECT_MINBLOCKS) advect_lean_kernel(c
     }
 }
 
-/* FULL pass: one thread per hit-list entry, every boundary model enabled. */
+/* FULL pass: one thread per hit-list entry, every boundary model enabled.  The length of the list is read from the
+ * status block on the device (no host round trip between the two passes); the grid strides over it. */
 template <int MODE, bool AXI>
-__global__ void __launch_bounds__(128) advect_full_kernel(const __grid_constant__ PgDev d, long long n, int) {
-    long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    bool have = tid < n;
-    long long slot = have ? (long long)d.hitlist[tid] : 0;
-    PState q;
-    int dirty = 0, remove = 0, hops = 0;
-    if (have) have = load_particle(d, slot, q, dirty);
-    bool keep = false;
-    if (have) {
-        PgRng g;
-        g.init(d.seed_local, 1, d.tID, (unsigned long long)slot, 0ULL);
-        int bhits[4] = {0, 0, 0, 0};
-        while (q.dtrim > 0.) {
-            if constexpr (MODE == 0) structured_iter<AXI, false>(d, g, q, remove, dirty, bhits, hops);
-            else unstructured_iter<MODE, AXI, false>(d, g, q, remove, dirty, hops);
+__global__ void __launch_bounds__(128) advect_full_kernel(const __grid_constant__ PgDev d, long long, int) {
+    const long long n = (long long)d.status->n_hits;
+    for (long long base = (long long)blockIdx.x * blockDim.x; base < n; base += (long long)gridDim.x * blockDim.x) {
+        const long long tid = base + threadIdx.x;
+        bool have = tid < n;
+        long long slot = have ? (long long)d.hitlist[tid] : 0;
+        PState q;
+        int dirty = 0, remove = 0, hops = 0;
+        if (have) have = load_particle(d, slot, q, dirty);
+        bool keep = false;
+        if (have) {
+            PgRng g;
+            g.init(d.seed_local, 1, d.tID, (unsigned long long)slot, 0ULL);
+            int bhits[4] = {0, 0, 0, 0};
+            while (q.dtrim > 0.) {
+                if constexpr (MODE == 0) structured_iter<AXI, false>(d, g, q, remove, dirty, bhits, hops);
+                else unstructured_iter<MODE, AXI, false>(d, g, q, remove, dirty, hops);
+            }
+            keep = !remove && finish_particle<MODE>(d, q);
+            if (!keep) tombstone_particle(d, slot);
         }
-        keep = !remove && finish_particle<MODE>(d, q);
-        if (!keep) tombstone_particle(d, slot);
-    }
-    unsigned int fm = __ballot_sync(0xffffffffu, keep);
-    if (keep) {
-        PendingRank pr;
-        store_particle(d, slot, q, dirty, fm, pr);
-        if (pr.mask) commit_rank(d, pr);
+        unsigned int fm = __ballot_sync(0xffffffffu, keep);
+        if (keep) {
+            PendingRank pr;
+            store_particle(d, slot, q, dirty, fm, pr);
+            if (pr.mask) commit_rank(d, pr);
+        }
     }
 }
 
@@ -1023,8 +1058,10 @@ int launch_advect(pgpu_ctx* c, long long n) {
      * grid must still fill the machine several times over */
     int chunk = PG_ADVECT_CHUNK_MAX;
     while (chunk > PG_ADVECT_CHUNK_MIN && n / (4LL * chunk) < 148LL * PG_ADVECT_MINBLOCKS * 8) chunk >>= 1;
+    if (c->advect_chunk_override > 0) chunk = c->advect_chunk_override; /* tests: the bench-size chunk on a small store */
     const long long per_block = LEAN ? 4LL * chunk : 128LL;
     unsigned int blocks = (unsigned int)((n + per_block - 1) / per_block);
+    if (!LEAN && blocks > 148u * 16u) blocks = 148u * 16u; /* the FULL pass strides over the device-side list length */
     bool axi = d.axi != 0;
 #define PG_LAUNCH(MODE, AXI)                                                                   \
     do {                                                                                       \
@@ -1051,8 +1088,7 @@ int launch_advect(pgpu_ctx* c, long long n) {
 } /* namespace */
 
 /*
- * ADVECT for all slots [0, np).  Asynchronous except for one read-back of the hit-list length
- * between the LEAN and the FULL pass.
+ * ADVECT for all slots [0, np).  Asynchronous.
  */
 int pg_advect_impl(pgpu_ctx* c, int tID) {
     int rc;
@@ -1078,12 +1114,8 @@ int pg_advect_impl(pgpu_ctx* c, int tID) {
     }
 
     if ((rc = launch_advect<true>(c, c->np))) return rc;
-    /* hit-list length -> host (the only sync inside ADVECT) */
-    PG_CUDA(c, cudaMemcpyAsync(&c->h_status->n_hits, &c->d_status->n_hits, sizeof(unsigned long long),
-                               cudaMemcpyDeviceToHost, c->stream));
-    PG_CUDA(c, cudaStreamSynchronize(c->stream));
-    long long nh = (long long)c->h_status->n_hits;
-    if (nh > 0 && (rc = launch_advect<false>(c, nh))) return rc;
+    /* the FULL pass reads the hit-list length on the device: no host round trip inside ADVECT */
+    if ((rc = launch_advect<false>(c, c->np))) return rc;
 
     c->dev.emig_list = nullptr;
     c->dev.xrow = nullptr;

@@ -22,7 +22,7 @@ enum {
     S_REAC, S_TAB_E, S_TAB_CS,
     S_WR_R, S_WR_P1, S_WR_NPROD, S_WR_PROB,
     S_MCC_SP, S_MCC_FRAC, S_MCC_CELL_NRHO,
-    S_FACE_GEO, S_FACE_CODE, S_TANG1, S_TANG2, S_EDGE_LEN, S_FACE_BIDX, S_BOUND_AREA, S_CELL_NODES, S_BASIS,
+    S_FACE_GEO, S_FACE_FILT, S_FACE_EXACT, S_FACE_CODE, S_TANG1, S_TANG2, S_EDGE_LEN, S_FACE_BIDX, S_BOUND_AREA, S_CELL_NODES, S_BASIS,
     S_CELL_VOL, S_CELL_PROCS,
     S_BC_PARTICLE, S_BC_FIELD, S_BC_REACT, S_BC_TEMP, S_BC_ACCN, S_BC_ACCT,
     S_W_X1, S_W_Y1, S_W_X2, S_W_Y2, S_W_NX, S_W_NY, S_W_TEMP, S_W_TRANSM, S_W_SPEC, S_W_DIFF, S_W_POROUS, S_W_REACT,
@@ -129,6 +129,10 @@ extern "C" int pgpu_create(pgpu_ctx** out, int device) {
     memset(c->h_status, 0, sizeof(PgStatus));
     c->cfg.nranks = 1;
     c->cfg.eps_scaling = 1.0;
+    if (const char* e = getenv("PANTERA_GPU_ADVECT_CHUNK")) {
+        int v = atoi(e);
+        if (v >= 32 && v <= 65536 && (v & (v - 1)) == 0) c->advect_chunk_override = v;
+    }
     *out = c;
     return PGPU_OK;
 }
@@ -358,6 +362,12 @@ extern "C" int pgpu_set_mesh(pgpu_ctx* c, int dims, int nn, int nc, const double
     if ((rc = put(c, S_CELL_NODES, (const int*)cell_nodes, (size_t)nf * nc, &d.cell_nodes))) return rc;
     if ((rc = put(c, S_BASIS, basis_coeffs, basis_coeffs ? (size_t)nf * nf * nc : 0, &d.basis))) return rc;
     if ((rc = put(c, S_CELL_VOL, cell_volumes, (size_t)nc, &d.cell_vol))) return rc;
+    if (cell_procs)
+        for (int i = 0; i < nc; i++)
+            if (cell_procs[i] < 0 || cell_procs[i] >= 64)
+                PG_FAIL(c, PGPU_ERR_INVALID, "set_mesh: CELL_PROCS(%d) = %d outside 0..63", i + 1, cell_procs[i]);
+    c->cell_procs_max = 0;
+    if (cell_procs) c->cell_procs_max = *std::max_element(cell_procs, cell_procs + nc);
     if ((rc = put(c, S_CELL_PROCS, (const int*)cell_procs, cell_procs ? (size_t)nc : 0, &d.cell_procs))) return rc;
     d.nboundcells = face_boundary_index ? nboundcells : 0;
     if ((rc = put(c, S_FACE_BIDX, (const int*)face_boundary_index, face_boundary_index ? (size_t)nf * nc : 0, &d.face_bidx))) return rc;
@@ -377,6 +387,13 @@ extern "C" int pgpu_set_cell_procs(pgpu_ctx* c, int nc, const int32_t* cell_proc
     if (!c->cfg_set) PG_FAIL(c, PGPU_ERR_STATE, "set_cell_procs: set_config first");
     if (nc != pg_ncells(c)) PG_FAIL(c, PGPU_ERR_INVALID, "set_cell_procs: nc (%d) != number of cells (%d)", nc, pg_ncells(c));
     c->emig_valid = false; /* the emigrant list of the last ADVECT was made with the old ownership */
+    if (cell_procs) {
+        const int nr = c->cfg.nranks > 1 ? c->cfg.nranks : 1;
+        for (int i = 0; i < nc; i++)
+            if (cell_procs[i] < 0 || cell_procs[i] >= nr)
+                PG_FAIL(c, PGPU_ERR_INVALID, "set_cell_procs: CELL_PROCS(%d) = %d outside 0..%d", i + 1, cell_procs[i], nr - 1);
+        c->cell_procs_max = *std::max_element(cell_procs, cell_procs + nc);
+    }
     return put(c, S_CELL_PROCS, (const int*)cell_procs, (size_t)nc, &c->dev.cell_procs);
 }
 
@@ -485,22 +502,13 @@ extern "C" int pgpu_set_surface_charge(pgpu_ctx* c, const double* sc, int64_t n)
  * ---------------------------------------------------------------------------------------- */
 static int build_packed_mesh(pgpu_ctx* c) {
     int nf = c->mesh_dims + 1, nc = c->nc, rc;
-    /* blocks of PG_GEO_B cells, chunk-major inside a block (pgpu_internal.cuh PG_GEO_*) */
-    const int bd = PG_GEO_BLOCK_DOUBLES(nf);
-    std::vector<double> geo((size_t)((nc + PG_GEO_B - 1) / PG_GEO_B) * bd, 0.0);
-    auto slot = [&](int ic, int e) -> double* { /* double e of cell ic's record */
-        return &geo[(size_t)(ic / PG_GEO_B) * bd + (size_t)(e >> 1) * (2 * PG_GEO_B) + (size_t)(ic % PG_GEO_B) * 2 + (e & 1)];
-    };
+    /* hop codes: neighbour cell, or boundary physical group, resolved once from CELL_NEIGHBORS, CELL_FACES_PG and the
+     * neighbour's CELL_PG / VOLUME_BC (ref: src/timecycle.f90:1307-1360) */
     std::vector<int> code((size_t)nc * nf);
     const int nbc = (int)c->h_bc_volume.size();
     for (int ic = 0; ic < nc; ic++) {
         for (int j = 0; j < nf; j++) {
             size_t f = (size_t)ic * nf + j;
-            int v = c->h_cell_nodes[f];
-            for (int k = 0; k < 3; k++) {
-                *slot(ic, 6 * j + k) = c->h_face_normal[3 * f + k];
-                *slot(ic, 6 * j + 3 + k) = c->h_node_coords[3 * (size_t)(v - 1) + k];
-            }
             int nb = c->h_cell_neighbors[f];
             bool fluidboundary = false;
             if (nb == -1) {
@@ -524,10 +532,10 @@ static int build_packed_mesh(pgpu_ctx* c) {
             }
         }
     }
-    /* the hop codes ride in the same record (no dependent load in the face walk); plain specular walls are
-     * marked so that the LEAN pass can reflect in line instead of deferring the particle (PG_CODE_SPEC) */
-    for (int ic = 0; ic < nc; ic++) {
-        int rec[4] = {0, 0, 0, 0};
+    /* the codes ride in the cell records (no dependent load in the face walk); plain specular walls are marked so
+     * that the LEAN pass can reflect in line instead of deferring the particle (PG_CODE_SPEC) */
+    auto packed_codes = [&](int ic, int* rec) {
+        rec[0] = rec[1] = rec[2] = rec[3] = 0;
         for (int j = 0; j < nf; j++) {
             int cd = code[(size_t)ic * nf + j];
             if (cd < 0) {
@@ -537,9 +545,61 @@ static int build_packed_mesh(pgpu_ctx* c) {
             }
             rec[j] = cd;
         }
-        memcpy(slot(ic, 6 * nf), rec, sizeof(int) * (size_t)nf);
+    };
+    /* Filter + exact records of the non-axisymmetric face walk.  The filter holds float(n) and float(P.n) (P.n
+     * evaluated in double); pgpu_advect.cu bounds their rounding, so nothing here has to be exact except face_exact,
+     * which carries the very operands the reference reads (FACE_NORMAL / EDGE_NORMAL and NODE_COORDS(:,CELL_NODES),
+     * the point of face j being local node j, src/timecycle.f90:1293-1295). */
+    {
+        const int nchf = nf + 1;
+        std::vector<float> filt((size_t)((nc + PG_GEO_B - 1) / PG_GEO_B) * (size_t)(nchf * PG_GEO_B * 4), 0.0f);
+        std::vector<double> exact((size_t)nc * nf * 6);
+        for (int ic = 0; ic < nc; ic++) {
+            float* blk = &filt[(size_t)(ic / PG_GEO_B) * (size_t)(nchf * PG_GEO_B * 4)];
+            for (int j = 0; j < nf; j++) {
+                size_t f = (size_t)ic * nf + j;
+                int v = c->h_cell_nodes[f];
+                const double* n = &c->h_face_normal[3 * f];
+                const double* P = &c->h_node_coords[3 * (size_t)(v - 1)];
+                double* e = &exact[6 * f];
+                for (int k = 0; k < 3; k++) { e[k] = n[k]; e[3 + k] = P[k]; }
+                float* q = blk + (size_t)j * (PG_GEO_B * 4) + (size_t)(ic % PG_GEO_B) * 4;
+                double pn = 0.0;
+                for (int k = 0; k < c->mesh_dims; k++) pn += P[k] * n[k];
+                q[0] = (float)n[0]; q[1] = (float)n[1]; q[2] = (float)n[2]; q[3] = (float)pn;
+            }
+            int rec[4];
+            packed_codes(ic, rec);
+            memcpy(blk + (size_t)nf * (PG_GEO_B * 4) + (size_t)(ic % PG_GEO_B) * 4, rec, 16);
+        }
+        if ((rc = put(c, S_FACE_FILT, filt.data(), filt.size(), &c->dev.face_filt))) return rc;
+        if ((rc = put(c, S_FACE_EXACT, exact.data(), exact.size(), &c->dev.face_exact))) return rc;
     }
-    if ((rc = put(c, S_FACE_GEO, geo.data(), geo.size(), &c->dev.face_geo))) return rc;
+    /* the double-precision chunked record (blocks of PG_GEO_B cells, chunk-major, pgpu_internal.cuh PG_GEO_*) is read
+     * by the axisymmetric walk only, which exists for 2-D meshes */
+    if (c->mesh_dims == 2) {
+        const int bd = PG_GEO_BLOCK_DOUBLES(nf);
+        std::vector<double> geo((size_t)((nc + PG_GEO_B - 1) / PG_GEO_B) * bd, 0.0);
+        auto slot = [&](int ic, int e) -> double* { /* double e of cell ic's record */
+            return &geo[(size_t)(ic / PG_GEO_B) * bd + (size_t)(e >> 1) * (2 * PG_GEO_B) + (size_t)(ic % PG_GEO_B) * 2 + (e & 1)];
+        };
+        for (int ic = 0; ic < nc; ic++) {
+            for (int j = 0; j < nf; j++) {
+                size_t f = (size_t)ic * nf + j;
+                int v = c->h_cell_nodes[f];
+                for (int k = 0; k < 3; k++) {
+                    *slot(ic, 6 * j + k) = c->h_face_normal[3 * f + k];
+                    *slot(ic, 6 * j + 3 + k) = c->h_node_coords[3 * (size_t)(v - 1) + k];
+                }
+            }
+            int rec[4];
+            packed_codes(ic, rec);
+            memcpy(slot(ic, 6 * nf), rec, sizeof(int) * (size_t)nf);
+        }
+        if ((rc = put(c, S_FACE_GEO, geo.data(), geo.size(), &c->dev.face_geo))) return rc;
+    } else {
+        if ((rc = put(c, S_FACE_GEO, (const double*)nullptr, 0, &c->dev.face_geo))) return rc;
+    }
     if ((rc = put(c, S_FACE_CODE, code.data(), code.size(), &c->dev.face_code))) return rc;
     c->mesh_dirty = false;
     return PGPU_OK;
@@ -844,6 +904,9 @@ extern "C" int pgpu_upload_particles(pgpu_ctx* c, const void* aos, int64_t n, in
     c->has_dtrim = false;
     c->maybe_tombstones = false;
     c->id_counter = 0;
+    c->sorted = false; /* (also for n == 0: the offsets of the previous population must not stay marked valid) */
+    c->hist_valid = false;
+    c->emig_valid = false;
     return append_impl(c, aos, n, stride, "pgpu_upload_particles");
 }
 

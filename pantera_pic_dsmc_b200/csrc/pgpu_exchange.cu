@@ -227,6 +227,7 @@ int pg_exchange_impl(pgpu_ctx* c) {
     if (!c->nccl_comm) PG_FAIL(c, PGPU_ERR_STATE, "exchange: pgpu_comm_init has not been called");
     if (nr != c->comm_nranks || c->cfg.rank != c->comm_rank) PG_FAIL(c, PGPU_ERR_STATE, "exchange: config rank/nranks differ from the communicator");
     if (!c->dev.cell_procs) PG_FAIL(c, PGPU_ERR_STATE, "exchange: CELL_PROCS not set");
+    if (c->cell_procs_max >= nr) PG_FAIL(c, PGPU_ERR_INVALID, "exchange: CELL_PROCS holds rank %d but there are %d ranks", c->cell_procs_max, nr);
     int rc;
     pg_refresh_dev(c);
     ncclComm_t comm = (ncclComm_t)c->nccl_comm;

@@ -130,6 +130,11 @@ __device__ __forceinline__ void pg_st_stream(void* p, const PgRec32& v) {
     asm volatile("st.global.cs.v4.b64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v.a), "d"(v.b), "d"(v.c), "l"(v.w) : "memory");
 }
 
+/* address of chunk 0 of cell cell0's filter record (nf + 1 chunks) */
+__device__ __forceinline__ const char* pg_filt_base(const float* filt, int cell0, int nch) {
+    return reinterpret_cast<const char*>(filt) + (size_t)(cell0 / PG_GEO_B) * (size_t)(nch * PG_GEO_LINE) +
+           (size_t)((cell0 % PG_GEO_B) * 16);
+}
 /* double e of the record (e = 6*face + {0,1,2: normal, 3,4,5: point}) */
 __device__ __forceinline__ double pg_geo_at(const char* gb, int e) {
     return __ldg(reinterpret_cast<const double*>(gb + (e >> 1) * PG_GEO_LINE + (e & 1) * 8));
@@ -189,6 +194,13 @@ struct PgDev {
     int nn, nc, nf;
     const double* face_geo;  /* [ceil(nc/8)] blocks of PG_GEO_BLOCK_DOUBLES(nf): per face outward normal (3) + a point on the face (3), then the
                                 nf hop codes of face_code as int32 (16 bytes) */
+    /* non-axisymmetric face walk (pgpu_advect.cu unstructured_iter): a single-precision FILTER record per cell --
+     * nf x {normal (3 floats), plane offset P.n (1 float)} + the 16 bytes of hop codes, stored in blocks of PG_GEO_B
+     * cells chunk-major like face_geo -- that brackets every face test rigorously, and the EXACT operands
+     * {outward normal (3 doubles), face node (3 doubles)} cell-major, read only for the faces the bracket cannot
+     * decide (on average one per crossing, none on the final flight) */
+    const float* face_filt;   /* [ceil(nc/8)] blocks of (nf+1)*PG_GEO_B*4 floats */
+    const double* face_exact; /* [nc][nf][6] */
     const int* face_code;    /* [nc][nf]: >0 neighbour cell to hop into; 0 boundary without a physical
                                 group (remove); <0 boundary with physical group -code        */
     const double *face_tang1, *face_tang2; /* [nc][4][3] (3-D) */
@@ -265,6 +277,8 @@ struct pgpu_ctx {
 
     /* raw host copies needed to (re)build the packed mesh when BCs change */
     int mesh_dims, nn, nc;
+    int advect_chunk_override = 0; /* PANTERA_GPU_ADVECT_CHUNK (tuning / test knob; results do not depend on it) */
+    int cell_procs_max = 0; /* largest CELL_PROCS entry (validated against nranks before an exchange) */
     int64_t mcc_cell_nrho_cells = 0; /* cells covered by dev.mcc_cell_nrho */
     std::vector<double> h_node_coords, h_face_normal;
     std::vector<int32_t> h_cell_nodes, h_cell_neighbors, h_cell_faces_pg, h_cell_pg;

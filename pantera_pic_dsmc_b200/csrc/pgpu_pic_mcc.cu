@@ -224,9 +224,11 @@ extern "C" int pgpu_deposit_charge(pgpu_ctx* c, double* rhs_host, int64_t nnodes
         else deposit_kernel<false><<<blocks, 256, 0, c->stream>>>(d, c->d_rhs, nn);
         c->launches++;
     }
-    /* RHS = RHS + SURFACE_CHARGE on the rank that owns it (every rank holds the same replicated array in
-     * the reference; only rank 0 adds it here so that the all-reduce counts it once), ref: :5525 */
-    if (c->d_surface_charge && c->cfg.grid_type == PGPU_UNSTRUCTURED && (c->cfg.nranks <= 1 || c->cfg.rank == 0)) {
+    /* RHS = RHS + SURFACE_CHARGE on EVERY rank before the reduction: SURFACE_CHARGE is a per-rank partial in the
+     * reference (each rank accumulates the dielectric hits of its own particles in ADVECT, src/timecycle.f90:1399-1430,
+     * and adds its array before MPI_REDUCE(SUM), src/fields.f90:5525-5535), and d_surface_charge here is filled per
+     * rank by boundary_unstructured in the same way */
+    if (c->d_surface_charge && c->cfg.grid_type == PGPU_UNSTRUCTURED) {
         long long m = std::min<long long>(nn, c->nsc);
         add_surface_charge_kernel<<<(unsigned int)((m + 255) / 256), 256, 0, c->stream>>>(c->d_rhs, c->d_surface_charge, m);
         c->launches++;

@@ -204,6 +204,49 @@ def test_structured_pic_cic_gather(gpu, oracle_philox):
     util.assert_particles_match(a, b, exact_fields=MOVE_FIELDS, what="structured PIC")
 
 
+def test_triangles_pic_nodal_bfield(gpu, oracle_philox):
+    """APPLY_B_FIELD (src/fields.f90:4227-4249): nodal P1 interpolation of B_FIELD(3,1,NNODES) on a 2-D triangle mesh
+    through pgpu_set_bfield, plus a uniform external field and a cell-constant E (APPLY_E_FIELD, unstructured branch).
+    No stochastic wall is involved (specular box), so the Boris kick and the flight must be bit-identical."""
+    w = wl.c3_tri_box(nx=10, ny=8, n=25_000, lo=(0.0, 0.0), hi=(0.1, 0.08), dt=3e-10, species=("N2", "O2"),
+                      wall_bc=("specular",) * 4, T0=20000.0, u_drift=(0.0, 0.0, 0.0))
+    sp = wl.load_species("ar", ["Ar+", "e"])
+    rng = np.random.default_rng(12)
+    n = len(w.particles)
+    w.species = sp
+    w.particles["S_ID"] = rng.integers(1, 3, n)
+    v = wl.maxwellian(rng, n, sp.mass[w.particles["S_ID"] - 1], 20000.0)
+    w.particles["VX"], w.particles["VY"], w.particles["VZ"] = v[:, 0], v[:, 1], v[:, 2]
+    w.particles["EROT"] = 0.0
+    w.particles["EVIB"] = 0.0
+    w.cfg.pic_type = capi.PIC_EXPLICIT
+    for i, b in enumerate([0.0, 0.005, 0.01]):
+        w.cfg.external_b[i] = b
+    m = w.mesh
+    xy = np.asarray(m.node_coords)
+    bf = np.zeros((3, m.nn), order="F")
+    bf[0] = 0.02 * np.sin(40.0 * xy[0]) + 0.003 * rng.standard_normal(m.nn)
+    bf[1] = 0.02 * np.cos(55.0 * xy[1])
+    bf[2] = 0.05 * (1.0 + 10.0 * xy[0] - 7.0 * xy[1])
+    w.efield = np.asfortranarray(rng.standard_normal((3, m.nc)) * 2e4)
+    util.setup_pair(gpu, oracle_philox, w)
+    gpu.set_bfield(bf)
+    oracle_philox.set_bfield(bf)
+    p0 = util.by_id(w.particles)
+    for s in range(3):
+        gpu.advect(1 + s)
+        oracle_philox.advect(1 + s)
+    a, b = util.by_id(oracle_philox.download_particles()), util.by_id(gpu.download_particles())
+    util.assert_particles_match(a, b, exact_fields=MOVE_FIELDS, what="2-D PIC with nodal B")
+    # the nodal field matters: the same run without it ends elsewhere
+    gpu.upload_particles(p0)
+    gpu.set_bfield(np.zeros((3, m.nn), order="F"))
+    for s in range(3):
+        gpu.advect(1 + s)
+    c = util.by_id(gpu.download_particles())
+    assert np.abs(c["VZ"] - b["VZ"]).max() > 1e-3 * np.abs(b["VZ"]).max()
+
+
 def test_solid_cells_act_as_walls(gpu, oracle_philox):
     w = wl.c3_tri_box(nx=8, ny=8, n=20_000, lo=(0, 0), hi=(0.08, 0.08), dt=6e-6, wall_bc=("specular",) * 4)
     m = w.mesh
