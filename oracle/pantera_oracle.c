@@ -103,6 +103,9 @@ struct po_ctx {
     int seeded;
     uint32_t key[2], ent[3], ndraw;
     uint32_t phx_buf[4];
+    /* rng_mode 2: rf() returns the next value of a caller-supplied script (tests/golden/fortran_pins.py) */
+    double* script;
+    int64_t script_n, script_pos;
 };
 
 #define FAIL(ctx, code, ...)                                  \
@@ -217,6 +220,13 @@ static uint32_t philox_word(po_ctx* w) {
 
 /* ref: src/tools.f90:33-43 rf() = genrand64_real1 on [0,1] (src/mt19937.f90:220-225) */
 double po_rf(po_ctx* w) {
+    if (w->rng_mode == 2) {
+        /* injected draws: every rf() of the restated routines consumes the script in call order, exactly as the
+         * reference consumes its sequential stream; past the end the script repeats 0.5 (and the overrun is counted) */
+        if (w->script_pos < w->script_n) return w->script[w->script_pos++];
+        w->script_pos++;
+        return 0.5;
+    }
     if (w->rng_mode == 0) {
         return (double)(po_mt_next_u64(w) >> 11) * (1.0 / 9007199254740991.0);
     }
@@ -1758,7 +1768,7 @@ int po_destroy(po_ctx* w) {
     free(w->w_x1); free(w->w_y1); free(w->w_x2); free(w->w_y2); free(w->w_nx); free(w->w_ny);
     free(w->w_temp); free(w->w_transm); free(w->w_spec); free(w->w_diff); free(w->w_porous); free(w->w_react);
     free(w->xcoord); free(w->ycoord);
-    free(w->e_field); free(w->b_field); free(w->surface_charge);
+    free(w->e_field); free(w->b_field); free(w->surface_charge); free(w->script);
     free(w->p); free(w->bcount); free(w->wcount); free(w->tallies); free(w->npcall);
     free(w);
     return PGPU_OK;
@@ -1767,11 +1777,20 @@ int po_destroy(po_ctx* w) {
 const char* po_last_error(const po_ctx* w) { return w ? w->err : "null context"; }
 
 int po_set_rng_mode(po_ctx* w, int mode) {
-    if (mode != 0 && mode != 1) FAIL(w, PGPU_ERR_INVALID, "rng mode must be 0 (MT19937-64) or 1 (Philox)");
+    if (mode < 0 || mode > 2) FAIL(w, PGPU_ERR_INVALID, "rng mode must be 0 (MT19937-64), 1 (Philox) or 2 (scripted draws)");
     w->rng_mode = mode;
     w->seeded = 0;
     return PGPU_OK;
 }
+
+/* rng_mode 2: the sequence rf() will return; po_rng_script_used() = draws consumed so far (may exceed n) */
+int po_set_rng_script(po_ctx* w, const double* draws, int64_t n) {
+    REPL(w->script, draws, n);
+    w->script_n = n;
+    w->script_pos = 0;
+    return PGPU_OK;
+}
+int64_t po_rng_script_used(const po_ctx* w) { return w->script_pos; }
 
 int po_set_config(po_ctx* w, const pgpu_config* cfg) {
     w->c = *cfg;

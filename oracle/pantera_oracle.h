@@ -22,6 +22,9 @@
  *      initialization.f90:2294-2296).
  *   1  counter-based Philox4x32-10 keyed per (kind, timestep, entity): the stream the CUDA
  *      kernels use; lets device results be compared value-by-value with the oracle.
+ *   2  scripted: rf() replays a caller-supplied sequence, so that single events (one CLL reflection, one
+ *      VSS/Borgnakke-Larsen pair, one TCE dissociation) can be compared with a plain-Python evaluation of the
+ *      Fortran expressions on the same draws (tests/golden/fortran_pins.py).
  */
 #ifndef PANTERA_ORACLE_H
 #define PANTERA_ORACLE_H
@@ -38,6 +41,9 @@ int po_create(po_ctx** ctx, int device_ignored);
 int po_destroy(po_ctx* ctx);
 const char* po_last_error(const po_ctx* ctx);
 int po_set_rng_mode(po_ctx* ctx, int mode);
+/* rng mode 2: rf() replays a caller-supplied sequence (independent pins of tests/golden/fortran_pins.py) */
+int po_set_rng_script(po_ctx* ctx, const double* draws, int64_t n);
+int64_t po_rng_script_used(const po_ctx* ctx);
 /* raw generator access for the known-answer tests */
 double po_rf(po_ctx* ctx);
 int po_pick(po_ctx* ctx, int n); /* pair-selection index INT(N*rf()), one stream word in Philox mode for N <= 65536 */

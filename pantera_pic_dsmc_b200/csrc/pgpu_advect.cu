@@ -465,22 +465,27 @@ __device__ __forceinline__ void select_face(const PgDev& d, const PState& q, int
     if (DIMS >= 3) { V1 += fabsf(vzf); X1 += fabsf(zf); }
     const float EV = 1.e-6f * V1;
     const float dtf = (float)dtcoll;
-    const float dt_hi = dtf * (1.f + 1.e-6f), dt_lo = dtf * (1.f - 1.e-6f);
+    const float dt_hi = dtf * (1.f + 2.e-6f), dt_lo = dtf * (1.f - 2.e-6f);
     float t_lo[NF];
     float T = INF;
     unsigned int open = 0u;
 #pragma unroll
     for (int i = 0; i < NF; i++) {
+        /* (explicit fused multiply-adds: the bounds hold for any single-precision evaluation order) */
         float vnf = vxf * F[i].x, xn = xf * F[i].x;
-        if (DIMS >= 2) { vnf += vyf * F[i].y; xn += yf * F[i].y; }
-        if (DIMS >= 3) { vnf += vzf * F[i].z; xn += zf * F[i].z; }
+        if (DIMS >= 2) { vnf = __fmaf_rn(vyf, F[i].y, vnf); xn = __fmaf_rn(yf, F[i].y, xn); }
+        if (DIMS >= 3) { vnf = __fmaf_rn(vzf, F[i].z, vnf); xn = __fmaf_rn(zf, F[i].z, xn); }
         const float dxf = F[i].w - xn;
         const float ED = 1.e-6f * (X1 + fabsf(F[i].w));
         const float vn_hi = vnf + EV, vn_lo = vnf - EV, dx_lo = dxf - ED, dx_hi = dxf + ED;
-        const bool fail = (vn_hi < 0.f) || (dx_lo > 0.f && vn_hi * dt_hi * (1.f + 1.e-6f) < dx_lo);
-        const bool pass = (vn_lo > 0.f) && (vn_lo * dt_lo * (1.f - 1.e-6f) > dx_hi);
-        t_lo[i] = (dx_lo > 0.f) ? (dx_lo / vn_hi) * (1.f - 1.e-6f) : -INF;
-        if (pass) T = fminf(T, (fmaxf(dx_hi, 0.f) / vn_lo) * (1.f + 1.e-6f));
+        const bool fail = (vn_hi < 0.f) || (dx_lo > 0.f && vn_hi * dt_hi < dx_lo);
+        const bool pass = (vn_lo > 1.e-30f) && (vn_lo < 1.e30f) && (vn_lo * dt_lo > dx_hi);
+        /* crossing-time bracket with the approximate reciprocal (__fdividef: 2 ulp, no slow path; covered by the
+         * 2e-6 margins).  A denominator outside its accurate range leaves the face relevant / unbounded. */
+        const float tl = __fdividef(dx_lo, vn_hi) * (1.f - 2.e-6f);
+        t_lo[i] = (dx_lo > 0.f && vn_hi > 1.e-30f && vn_hi < 1.e30f) ? tl : -INF;
+        const float th = __fdividef(fmaxf(dx_hi, 0.f), vn_lo) * (1.f + 2.e-6f);
+        T = pass ? fminf(T, th) : T;
         if (!fail) open |= 1u << i; /* (a NaN anywhere compares false: the face stays open) */
     }
     unsigned int rel = 0u;

@@ -1,0 +1,559 @@
+#!/usr/bin/env python
+"""Independent pins of the oracle: single events of the hot path evaluated in PLAIN PYTHON, written from the
+Fortran source of the reference (file:line cited at every routine), NOT from oracle/pantera_oracle.c.
+
+Why: the oracle and the CUDA kernels were written by the same hand, so a misreading of the Fortran would be
+duplicated on both sides and every device-vs-oracle test would still pass (VERDICT r01 "What's weak").  These
+vectors are a second, independent reading: each routine below is a line-by-line Python evaluation of the cited
+Fortran statements on IEEE doubles (Python floats; no FMA, left-to-right like gfortran -O3 without -ffast-math),
+with the random draws supplied as a SCRIPT -- the sequence rf() returns, in call order.  The oracle replays the same
+script (rng_mode 2, po_set_rng_script) and must land on the same numbers; the CUDA path is tied to the oracle by
+the value-for-value device tests, and directly to these vectors for the deterministic events (tests/
+test_fortran_pins.py, -m gpu).
+
+    python tests/golden/fortran_pins.py        # regenerates tests/golden/fortran_pins.json
+
+Covered reference lines:
+  tet_walk      src/timecycle.f90:1257-1305 (3-D face loop incl. the '>=' tie: last face wins), :1311-1312, :1349-1357,
+                :1433-1443 (specular), :1648-1657; face geometry src/grid_and_partition.f90:1932-1957
+  axi_move      src/timecycle.f90:2297-2332 (MOVE_PARTICLE, axisymmetric branch)
+  cll_reflect   src/timecycle.f90:1485-1550 (CLL), src/tools.f90:245-285 (INTERNAL_ENERGY)
+  vss_pair_bl   src/collisions.f90:202-253 (majorant), :259-325 (selection, acceptance), :454-546 (Borgnakke-Larsen + VSS
+                deflection), :892-937 (FUNCTION_I, COLL_INTERNAL_ENERGY)
+  tce_3prod     src/collisions.f90:331-449 (TCE test, 3-product redistribution), :956-992 (HS_SCATTER)
+  tce_coeffs    src/initialization.f90:2681-2724 (INITREACTIONS C1, C2, C3)
+"""
+import json
+import math
+import os
+import struct
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+
+PI = 3.1415926535897932   # src/global.f90:31
+KB = 1.380649e-23         # src/global.f90:34
+F32 = lambda x: float(np.float32(x))   # a default-REAL (single precision) literal or expression promoted to REAL(8)
+
+
+def hx(x):
+    return float(x).hex()
+
+
+class Script:
+    """rf() of src/tools.f90:33-43 replaced by a scripted sequence."""
+
+    def __init__(self, draws):
+        self.d, self.k = list(draws), 0
+
+    def __call__(self):
+        v = self.d[self.k]
+        self.k += 1
+        return v
+
+
+# ------------------------------------------------------------------------------------------ species / VSS input
+def read_species(kind):
+    """NAME MOLWT MOLECULAR_MASS ROTDOF ROTREL VIBDOF VIBREL VIBTEMP SPWT CHARGE (src/initialization.f90:560-600);
+    NAME DIAM OMEGA TREF ALPHA (src/initialization.f90:640-660)."""
+    sp = {}
+    for line in open(os.path.join(ROOT, "tests", "data", f"{kind}.species")):
+        t = line.split("!")[0].split()
+        if len(t) >= 10:
+            sp[t[0]] = dict(mass=float(t[2]), rotdof=int(t[3]), rotrel=float(t[4]), vibdof=int(t[5]), vibrel=float(t[6]))
+    for line in open(os.path.join(ROOT, "tests", "data", f"{kind}.vss")):
+        t = line.split("!")[0].split()
+        if len(t) >= 5 and t[0] in sp:
+            sp[t[0]].update(diam=float(t[1]), omega=float(t[2]), tref=float(t[3]), alpha=float(t[4]))
+    return sp
+
+
+def vss_pair(a, b):
+    """src/initialization.f90:675-698."""
+    om = 0.5 * (a["omega"] + b["omega"])
+    tref = 0.5 * (a["tref"] + b["tref"])
+    mr = a["mass"] * b["mass"] / (a["mass"] + b["mass"])
+    cref = math.sqrt(2 * KB * tref / mr)
+    cref *= F32(1.2354) if abs(om - 0.5) < 1e-6 else math.gamma(2.5 - om) ** (-0.5 / (om - 0.5))
+    return dict(sigma=PI * (0.5 * (a["diam"] + b["diam"])) ** 2, omega=om, alpha=0.5 * (a["alpha"] + b["alpha"]), cref=cref)
+
+
+# ------------------------------------------------------------------------------------------ tet geometry
+def cross(a, b):
+    return [a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]]
+
+
+def norm2(a):
+    return math.sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2])
+
+
+IND = [[1, 3, 2], [1, 2, 4], [2, 3, 4], [1, 4, 3]]   # src/grid_and_partition.f90:1932-1935
+
+
+def tet_mesh():
+    """Two tetrahedra sharing the face {2,3,4}.  Face J of a cell is IND(J,:), its reference point is local node J
+    (src/timecycle.f90:1293-1295), normals/tangents as src/grid_and_partition.f90:1943-1957.  Boundary faces carry the
+    physical groups 1 (z = 0), 2 (y = 0), 3 (x = 0), 4 (the outer faces of the second cell)."""
+    nodes = [[0.0, 0.0, 0.0], [1.0, 0.0, 0.0], [0.0, 1.0, 0.0], [0.0, 0.0, 1.0], [0.9, 1.1, 1.2]]
+    cells = [[1, 2, 3, 4], [2, 3, 4, 5]]
+    nc = len(cells)
+    normal = [[None] * 4 for _ in range(nc)]
+    tang1 = [[None] * 4 for _ in range(nc)]
+    tang2 = [[None] * 4 for _ in range(nc)]
+    for i, cn in enumerate(cells):
+        cen = [sum(nodes[v - 1][k] for v in cn) / 4.0 for k in range(3)]
+        for j in range(4):
+            v1, v2, v3 = (cn[IND[j][m] - 1] for m in range(3))
+            A, B, C = nodes[v1 - 1], nodes[v2 - 1], nodes[v3 - 1]
+            ba, ca = [B[k] - A[k] for k in range(3)], [C[k] - A[k] for k in range(3)]
+            cp = cross(ba, ca)
+            n = [cp[k] / norm2(cp) for k in range(3)]
+            assert sum((A[k] - cen[k]) * n[k] for k in range(3)) > 0, "cell is not positively oriented"
+            normal[i][j] = n
+            t1 = [ba[k] / norm2(ba) for k in range(3)]
+            tang1[i][j] = t1
+            tang2[i][j] = cross(n, t1)
+    # face 3 of cell 1 = nodes {2,3,4}; in cell 2 = (2,3,4,5) it is IND(1,:) = local nodes 1,3,2
+    neighbors = [[-1, -1, 2, -1], [1, -1, -1, -1]]
+    faces_pg = [[1, 2, -1, 3], [-1, 4, 4, 4]]
+    vol = []
+    for cn in cells:
+        a, b, c, d = (nodes[v - 1] for v in cn)
+        e1, e2, e3 = ([b[k] - a[k] for k in range(3)], [c[k] - a[k] for k in range(3)], [d[k] - a[k] for k in range(3)])
+        cp = cross(e2, e3)
+        vol.append(abs(e1[0] * cp[0] + e1[1] * cp[1] + e1[2] * cp[2]) / 6.0)
+    return dict(nodes=nodes, cells=cells, normal=normal, tang1=tang1, tang2=tang2, neighbors=neighbors, faces_pg=faces_pg, vol=vol)
+
+
+def internal_energy(rf, dof, temp):
+    """src/tools.f90:245-285."""
+    if dof == 0:
+        return 0.0
+    if dof == 2:
+        r = rf()
+        while r < 1.0e-13:
+            r = rf()
+        return -math.log(r) * KB * temp
+    param = F32(5.0) if dof == 1 else F32(0.01)
+    r = rf()
+    x = -math.log(r)
+    r = rf()
+    while r > (x / param) ** (dof / 2.0 - 1.0):
+        r = rf()
+        x = -math.log(r)
+        r = rf()
+    return x * KB * temp
+
+
+def advect_tet(mesh, bc, species, p, dt, rf):
+    """One particle through ADVECT on the 3-D unstructured grid (no PIC, no axisymmetry, no tallies).
+    src/timecycle.f90:1166-1170, 1257-1305, 1309-1360, 1433-1443 (specular), 1485-1550 (CLL), 1644-1657.
+    p = dict(x, y, z, vx, vy, vz, erot, evib, ic (1-based), sid (name)); bc[pg] = ('specular',) or ('cll', Tw, acc_n, acc_t).
+    Returns the particle at the end of the step and the list of (cell, face) it crossed."""
+    x, y, z, vx, vy, vz = p["x"], p["y"], p["z"], p["vx"], p["vy"], p["vz"]
+    erot, evib, ic = p["erot"], p["evib"], p["ic"]
+    dtrim = dt
+    trace = []
+    while dtrim > 0.0:
+        dtcoll = dtrim
+        boundcoll = -1
+        for i in range(1, 5):
+            n = mesh["normal"][ic - 1][i - 1]
+            P = mesh["nodes"][mesh["cells"][ic - 1][i - 1] - 1]
+            vn = vx * n[0] + vy * n[1] + vz * n[2]
+            dx = (P[0] - x) * n[0] + (P[1] - y) * n[1] + (P[2] - z) * n[2]
+            if vn >= 0.0 and vn * dtcoll >= dx:
+                dtcoll = dx / vn
+                boundcoll = i
+        if boundcoll != -1:
+            x, y, z = x + vx * dtcoll, y + vy * dtcoll, z + vz * dtcoll   # MOVE_PARTICLE, :2326-2328
+            dtrim = dtrim - dtcoll
+            trace.append([ic, boundcoll])
+            neighbor = mesh["neighbors"][ic - 1][boundcoll - 1]
+            if neighbor == -1:
+                pg = mesh["faces_pg"][ic - 1][boundcoll - 1]
+                fn = [-c for c in mesh["normal"][ic - 1][boundcoll - 1]]        # FACE_NORMAL = -U3D_GRID%FACE_NORMAL, :1357
+                kind = bc[pg]
+                if kind[0] == "specular":
+                    vdotn = vx * fn[0] + vy * fn[1] + vz * fn[2]
+                    vx = vx - 2.0 * vdotn * fn[0]
+                    vy = vy - 2.0 * vdotn * fn[1]
+                    vz = vz - 2.0 * vdotn * fn[2]
+                elif kind[0] == "cll":
+                    _, wall_temp, acc_n, acc_t = kind
+                    vdotn = vx * fn[0] + vy * fn[1] + vz * fn[2]
+                    t1 = [vx - vdotn * fn[0], vy - vdotn * fn[1], vz - vdotn * fn[2]]
+                    nt = norm2(t1)   # NORM2 intrinsic, here by its definition sqrt(sum of squares): the pin allows 1e-13
+                    t1 = [c / nt for c in t1]
+                    t2 = cross(fn, t1)
+                    vdott1 = vx * t1[0] + vy * t1[1] + vz * t1[2]
+                    m = species[p["sid"]]["mass"]
+                    vrm = math.sqrt(2.0 * KB * wall_temp / m)
+                    rn = rf()
+                    while rn < 1.0e-13:
+                        rn = rf()
+                    r1 = math.sqrt(-acc_n * math.log(rn))
+                    theta1 = 2.0 * PI * rf()
+                    dot_norm = vdotn / vrm * math.sqrt(1 - acc_n)
+                    v_perp = vrm * math.sqrt(r1 * r1 + dot_norm * dot_norm + 2.0 * r1 * dot_norm * math.cos(theta1))
+                    rn = rf()
+                    while rn < 1.0e-13:
+                        rn = rf()
+                    r2 = math.sqrt(-acc_t * math.log(rn))
+                    theta2 = 2.0 * PI * rf()
+                    vtangent = vdott1 / vrm * math.sqrt(1 - acc_t)
+                    v_tang1 = vrm * (vtangent + r2 * math.cos(theta2))
+                    v_tang2 = vrm * r2 * math.sin(theta2)
+                    erot = internal_energy(rf, species[p["sid"]]["rotdof"], wall_temp)
+                    evib = internal_energy(rf, species[p["sid"]]["vibdof"], wall_temp)
+                    vx = v_perp * fn[0] + v_tang1 * t1[0] + v_tang2 * t2[0]
+                    vy = v_perp * fn[1] + v_tang1 * t1[1] + v_tang2 * t2[1]
+                    vz = v_perp * fn[2] + v_tang1 * t1[2] + v_tang2 * t2[2]
+                else:
+                    raise ValueError(kind)
+            else:
+                ic = neighbor
+        else:
+            x, y, z = x + vx * dtrim, y + vy * dtrim, z + vz * dtrim
+            dtrim = 0.0
+    return dict(x=x, y=y, z=z, vx=vx, vy=vy, vz=vz, erot=erot, evib=evib, ic=ic, sid=p["sid"]), trace
+
+
+def move_particle_axi(p, time):
+    """src/timecycle.f90:2311-2324."""
+    x = p["x"] + p["vx"] * time
+    r = math.sqrt((p["y"] + p["vy"] * time) ** 2 + (p["vz"] * time) ** 2)
+    sintheta = p["vz"] * time / r
+    costheta = math.copysign(math.sqrt(1.0 - sintheta * sintheta), p["y"] + p["vy"] * time)
+    vz, vy = p["vz"], p["vy"]
+    return dict(x=x, y=r, z=0.0, vx=p["vx"], vz=costheta * vz - sintheta * vy, vy=sintheta * vz + costheta * vy)
+
+
+# ------------------------------------------------------------------------------------------ collisions
+def function_i(ecoll, ei, trdof, idof):
+    """src/collisions.f90:892-908."""
+    if idof == 2:
+        return (1.0 - ei / ecoll) ** (trdof / 2.0 - 1.0)
+    return (((trdof + idof - 4.0) / (idof - 2.0)) ** (idof / 2.0 - 1.0) * ((trdof + idof - 4.0) / (trdof - 2.0)) ** (trdof / 2.0 - 1.0)
+            * (ei / ecoll) ** (idof / 2.0 - 1.0) * (1.0 - ei / ecoll) ** (trdof / 2.0 - 1.0))
+
+
+def coll_internal_energy(rf, ecoll, trdof, intdof):
+    """src/collisions.f90:915-937."""
+    if trdof < 1.0e-6:
+        return ecoll
+    if intdof == 0:
+        return 0.0
+    while True:
+        r1 = rf()
+        ei = r1 * ecoll
+        r2 = rf()
+        if r2 <= function_i(ecoll, ei, trdof, intdof):
+            return ei
+
+
+def hs_scatter(rf, ecoll, m1, m2, c1, c2):
+    """src/collisions.f90:956-992; returns new (c1, c2)."""
+    pi2 = 2.0 * PI
+    mred = m1 * m2 / (m1 + m2)
+    g = math.sqrt(2.0 * ecoll / mred)
+    cosphi = 2.0 * rf() - 1.0
+    sinphi = math.sqrt(1 - cosphi * cosphi)
+    theta = pi2 * rf()
+    grel = [g * sinphi * math.cos(theta), g * sinphi * math.sin(theta), g * cosphi]
+    w = [m1 / (m1 + m2) * c1[i] + m2 / (m1 + m2) * c2[i] for i in range(3)]
+    return ([w[i] + m2 / (m1 + m2) * grel[i] for i in range(3)], [w[i] - m1 / (m1 + m2) * grel[i] for i in range(3)])
+
+
+def vss_collis_cell(species, names, parts, reactions, sigmamax, fnum, dt, vol, rf):
+    """VSS_COLLIS for ONE cell holding `parts` (list of dicts v=[vx,vy,vz], erot, evib, sid=name, pos), in cell order
+    (IND is the identity).  src/collisions.f90:155-558.  reactions: dicts r1, r2, p1, p2, p3 (names), nprod, ea, c1, c2, c3
+    (TCE).  Returns (ncollreal, nreac, created particles)."""
+    pi2 = 2.0 * PI
+    npcj = len(parts)
+    vmin = [min(q["v"][k] for q in parts) for k in range(3)]
+    vmax = [max(q["v"][k] for q in parts) for k in range(3)]
+    vrmax = math.sqrt((vmax[0] - vmin[0]) ** 2 + (vmax[1] - vmin[1]) ** 2 + (vmax[2] - vmin[2]) ** 2)
+    # :232  0.5*NPC*(NPC-1) is REAL(4) arithmetic (0.5 is a default-REAL literal, NPC an INTEGER)
+    pairs = float(np.float32(np.float32(0.5) * np.float32(npcj)) * np.float32(npcj - 1))
+    ncollmax = pairs * sigmamax * vrmax * fnum * dt / vol
+    ncollmax_int = math.floor(ncollmax + 0.5)
+    half = math.floor(float(np.float32(0.5) * np.float32(npcj)))
+    if ncollmax_int < 1:
+        ncoll = 1
+    elif ncollmax_int > half:
+        ncoll = half
+    else:
+        ncoll = ncollmax_int
+    fcorr = ncollmax / ncoll
+    ncollreal, nreac, created = 0, 0, []
+    for _ in range(ncoll):
+        jp1 = int(npcj * rf())
+        jp2 = jp1
+        while jp2 == jp1:
+            jp2 = int(npcj * rf())
+        a, b = parts[jp1], parts[jp2]
+        vr2 = (b["v"][0] - a["v"][0]) ** 2 + (b["v"][1] - a["v"][1]) ** 2 + (b["v"][2] - a["v"][2]) ** 2
+        vr = math.sqrt(vr2)
+        s1, s2 = species[a["sid"]], species[b["sid"]]
+        pr = vss_pair(s1, s2)
+        cref, sigma, omega, alpha = pr["cref"], pr["sigma"], pr["omega"], pr["alpha"]
+        m1, m2 = s1["mass"], s2["mass"]
+        mred = m1 * m2 / (m1 + m2)
+        etr = 0.5 * mred * vr2
+        c1, c2 = list(a["v"]), list(b["v"])
+        rfp = rf()
+        if abs(omega - 0.5) < 1.0e-6:
+            collsigma = sigma
+        else:
+            if vr < F32(1e-20):
+                continue
+            collsigma = sigma * (vr / cref) ** (1.0 - 2.0 * omega)
+        collprob = fcorr / (sigmamax * vrmax) * vr * collsigma
+        if not (rfp < collprob):
+            continue
+        ncollreal += 1
+        ecoll = etr + a["erot"] + b["erot"] + a["evib"] + b["evib"]
+        skip = False
+        for r in reactions:
+            if r["r1"] != a["sid"]:
+                if r["r1"] != b["sid"]:
+                    continue
+                elif r["r2"] != a["sid"]:
+                    continue
+            elif r["r2"] != b["sid"]:
+                continue
+            ea = r["ea"]
+            if ecoll <= ea:
+                continue
+            ptce = r["c1"] * (ecoll - ea) ** r["c2"] * (1.0 - ea / ecoll) ** r["c3"]
+            rfp = rf()
+            if rfp < ptce:
+                skip = True
+                nreac += 1
+                ecoll = ecoll - ea
+                p1, p2 = species[r["p1"]], species[r["p2"]]
+                a["sid"], b["sid"] = r["p1"], r["p2"]
+                totdof = 3.0 + p2["rotdof"] + p2["vibdof"] + p1["rotdof"]
+                if r["nprod"] == 3:
+                    p3 = species[r["p3"]]
+                    totdof = totdof + 3.0 + p3["rotdof"] + p3["vibdof"]
+                ei = coll_internal_energy(rf, ecoll, totdof, p1["vibdof"])
+                a["evib"] = ei
+                ecoll = ecoll - ei
+                totdof = totdof - p1["rotdof"]
+                ei = coll_internal_energy(rf, ecoll, totdof, p1["rotdof"])
+                a["erot"] = ei
+                ecoll = ecoll - ei
+                totdof = totdof - p2["vibdof"]
+                ei = coll_internal_energy(rf, ecoll, totdof, p2["vibdof"])
+                b["evib"] = ei
+                ecoll = ecoll - ei
+                totdof = totdof - p2["rotdof"]
+                ei = coll_internal_energy(rf, ecoll, totdof, p2["rotdof"])
+                b["erot"] = ei
+                ecoll = ecoll - ei
+                mm1 = p1["mass"]
+                mm2 = p2["mass"] if r["nprod"] == 2 else p2["mass"] + p3["mass"]
+                totdof = totdof - 3.0
+                ei = coll_internal_energy(rf, ecoll, totdof, 3)
+                c1, c2 = hs_scatter(rf, ei, mm1, mm2, c1, c2)
+                ecoll = ecoll - ei
+                a["v"] = list(c1)
+                if r["nprod"] == 2:
+                    b["v"] = list(c2)
+                else:
+                    totdof = totdof - p3["vibdof"]
+                    evib = coll_internal_energy(rf, ecoll, totdof, p3["vibdof"])
+                    ecoll = ecoll - evib
+                    totdof = totdof - p3["rotdof"]
+                    erot = coll_internal_energy(rf, ecoll, totdof, p3["rotdof"])
+                    ecoll = ecoll - erot
+                    c1 = list(c2)
+                    c1, c2 = hs_scatter(rf, ecoll, p2["mass"], p3["mass"], c1, c2)
+                    b["v"] = list(c1)
+                    created.append(dict(v=list(c2), erot=erot, evib=evib, sid=r["p3"], pos=list(b["pos"])))
+                break
+        if skip:
+            continue
+        trdof = 3.0
+        prot1 = (trdof + s1["rotdof"]) / trdof * s1["rotrel"]
+        prot2 = (trdof + s2["rotdof"]) / trdof * s2["rotrel"]
+        pvib1 = (trdof + s1["vibdof"]) / trdof * s1["vibrel"]
+        pvib2 = (trdof + s2["vibdof"]) / trdof * s2["vibrel"]
+        trdof = 5.0 - 2.0 * omega
+        rfp = rf()
+        if rfp < prot1:
+            ecoll = etr + a["erot"]
+            a["erot"] = coll_internal_energy(rf, ecoll, trdof, s1["rotdof"])
+            etr = ecoll - a["erot"]
+        elif rfp < prot1 + prot2:
+            ecoll = etr + b["erot"]
+            b["erot"] = coll_internal_energy(rf, ecoll, trdof, s2["rotdof"])
+            etr = ecoll - b["erot"]
+        elif rfp < prot1 + prot2 + pvib1:
+            ecoll = etr + a["evib"]
+            a["evib"] = coll_internal_energy(rf, ecoll, trdof, s1["vibdof"])
+            etr = ecoll - a["evib"]
+        elif rfp < prot1 + prot2 + pvib1 + pvib2:
+            ecoll = etr + b["evib"]
+            b["evib"] = coll_internal_energy(rf, ecoll, trdof, s2["vibdof"])
+            etr = ecoll - b["evib"]
+        coschi = 2.0 * rf() ** (1.0 / alpha) - 1.0
+        sinchi = math.sqrt(1.0 - coschi * coschi)
+        theta = pi2 * rf()
+        costheta, sintheta = math.cos(theta), math.sin(theta)
+        if rfp < prot1 + prot2 + pvib1 + pvib2:
+            g = math.sqrt(2.0 * etr / mred)
+            cosa = 2.0 * rf() - 1.0
+            sina = math.sqrt(1 - cosa * cosa)
+            bb = pi2 * rf()
+            gx, gy, gz = g * sina * math.cos(bb), g * sina * math.sin(bb), g * cosa
+        else:
+            gx, gy, gz = c1[0] - c2[0], c1[1] - c2[1], c1[2] - c2[2]
+            g = math.sqrt(gx * gx + gy * gy + gz * gz)
+        grel = [gx * coschi + math.sqrt(gy * gy + gz * gz) * sintheta * sinchi,
+                gy * coschi + (g * gz * costheta - gx * gy * sintheta) / math.sqrt(gy * gy + gz * gz) * sinchi,
+                gz * coschi - (g * gy * costheta + gx * gz * sintheta) / math.sqrt(gy * gy + gz * gz) * sinchi]
+        w = [m1 / (m1 + m2) * c1[i] + m2 / (m1 + m2) * c2[i] for i in range(3)]
+        a["v"] = [w[i] + m2 / (m1 + m2) * grel[i] for i in range(3)]
+        b["v"] = [w[i] - m1 / (m1 + m2) * grel[i] for i in range(3)]
+    return ncollreal, nreac, created
+
+
+def tce_coeffs(species, r1, r2, A, n, ea):
+    """src/initialization.f90:2696-2716."""
+    a, b = species[r1], species[r2]
+    zeta = 0.5 * (a["rotdof"] + a["vibdof"] + b["rotdof"] + b["vibdof"])
+    omega = 0.5 * (a["omega"] + b["omega"])
+    sigma = 0.25 * PI * (a["diam"] + b["diam"]) ** 2
+    tref = 0.5 * (a["tref"] + b["tref"])
+    mr = a["mass"] * b["mass"] / (a["mass"] + b["mass"])
+    eps = 2.0 if r1 == r2 else 1.0
+    c1 = (math.sqrt(PI) * eps * A / (2.0 * sigma) * math.gamma(zeta + 2.5 - omega) / math.gamma(zeta + n + 1.5)
+          * math.sqrt(mr / (2.0 * KB * tref)) * tref ** (1.0 - omega) / KB ** (n - 1.0 + omega))
+    return c1, n - 1.0 + omega, zeta + 1.5 - omega
+
+
+def read_tce(species):
+    """`A + B --> C + D [+ E]` then `tce A n Ea[eV]` (src/initialization.f90:1689-1742); EA is stored in Joule."""
+    out, pend = [], None
+    for line in open(os.path.join(ROOT, "tests", "data", "air.tce")):
+        t = line.split("!")[0].split()
+        if not t:
+            continue
+        if "-->" in t:
+            k = t.index("-->")
+            pend = dict(react=[x for x in t[:k] if x != "+"], prod=[x for x in t[k + 1:] if x != "+"])
+        elif t[0] == "tce" and pend:
+            A, n, ea_ev = float(t[1]), float(t[2]), float(t[3])
+            pend.update(A=A, n=n, ea=ea_ev * 1.602176634e-19)
+            out.append(pend)
+            pend = None
+    return out
+
+
+# ------------------------------------------------------------------------------------------ vectors
+def pdict(q):
+    return {k: (hx(v) if isinstance(v, float) else v) for k, v in q.items()}
+
+
+def main():
+    out = {}
+    air = read_species("air")
+    mesh = tet_mesh()
+    out["tet_mesh"] = mesh
+    dt = 0.5
+    bc_spec = {1: ("specular",), 2: ("specular",), 3: ("specular",), 4: ("specular",)}
+
+    # ---- tet_walk: deterministic; case 0 is the '>=' tie (faces 2 and 4 of cell 1 at exactly t = 0.25: face 4 wins)
+    cases = [
+        dict(x=0.25, y=0.25, z=0.25, vx=-1.0, vy=-1.0, vz=0.0, erot=0.0, evib=0.0, ic=1, sid="N2"),
+        dict(x=0.2, y=0.3, z=0.1, vx=1.3, vy=0.9, vz=1.7, erot=0.0, evib=0.0, ic=1, sid="N2"),
+        dict(x=0.31, y=0.22, z=0.4, vx=0.7, vy=1.9, vz=2.3, erot=0.0, evib=0.0, ic=1, sid="N2"),
+        dict(x=0.6, y=0.7, z=0.65, vx=-2.1, vy=-0.4, vz=-3.3, erot=0.0, evib=0.0, ic=2, sid="N2"),
+        dict(x=0.05, y=0.05, z=0.85, vx=3.9, vy=3.1, vz=-4.7, erot=0.0, evib=0.0, ic=1, sid="N2"),
+    ]
+    walk = []
+    for p in cases:
+        q, trace = advect_tet(mesh, bc_spec, air, p, dt, Script([]))
+        walk.append(dict(inp=pdict(p), out=pdict(q), trace=trace))
+    assert walk[0]["trace"][0] == [1, 4], walk[0]["trace"]          # the tie went to the LAST face
+    assert any(len(w["trace"]) >= 3 for w in walk) and any(w["out"]["ic"] != w["inp"]["ic"] for w in walk)
+    out["tet_walk"] = dict(dt=hx(dt), cases=walk)
+
+    # ---- axi_move
+    ax = []
+    for p, t in [(dict(x=0.031, y=0.027, z=0.0, vx=310.0, vy=-120.0, vz=95.0), 1.0e-6),
+                 (dict(x=0.052, y=0.031, z=0.0, vx=-40.0, vy=250.0, vz=-333.0), 2.5e-6),
+                 (dict(x=0.047, y=0.024, z=0.0, vx=5.0, vy=-810.0, vz=12.0), 1.5e-6)]:
+        ax.append(dict(inp=pdict(p), time=hx(t), out=pdict(move_particle_axi(p, t))))
+    out["axi_move"] = ax
+
+    # ---- cll_reflect: N2 (ROTDOF = VIBDOF = 2) against a CLL wall on z = 0; draws: RN, THETA1, RN, THETA2, EROT, EVIB
+    bc_cll = dict(bc_spec)
+    bc_cll[1] = ("cll", 500.0, 0.8, 0.6)
+    draws = [0.37, 0.81, 0.12, 0.45, 0.66, 0.23]
+    p = dict(x=0.3, y=0.2, z=0.2, vx=210.0, vy=-95.0, vz=-480.0, erot=1.0e-21, evib=2.0e-21, ic=1, sid="N2")
+    s = Script(draws)
+    q, trace = advect_tet(mesh, bc_cll, air, p, 1.0e-3, s)
+    assert s.k == len(draws) and trace[0] == [1, 1]
+    out["cll_reflect"] = dict(dt=hx(1.0e-3), wall=dict(temp=500.0, acc_n=0.8, acc_t=0.6), draws=draws, inp=pdict(p), out=pdict(q),
+                              trace=trace)
+
+    # ---- collisions in one structured cell (Dimensions 2, NX = NY = 1, VOL = CELL_VOL)
+    names = ["O2", "N2", "O", "N", "NO"]
+    sigmamax = max(vss_pair(air[a], air[b])["sigma"] for a in names for b in names)
+    fnum, dtc, vol = 1.0e16, 1.0e-6, 1.0
+
+    def two(sa, sb):
+        return [dict(v=[1800.0, -350.0, 420.0], erot=3.1e-20, evib=1.2e-20, sid=sa, pos=[0.2, 0.3, 0.1]),
+                dict(v=[-2200.0, 610.0, -150.0], erot=2.4e-20, evib=0.7e-20, sid=sb, pos=[0.6, 0.7, -0.2])]
+
+    # vss_pair_bl: JP1 = 0 (N2), JP2 = 0 -> retry -> 1 (O2); accept; BL selector picks the rotational mode of particle 1;
+    # COLL_INTERNAL_ENERGY rejects once then accepts; deflection; inelastic -> isotropic relative velocity
+    draws = [0.2, 0.3, 0.9, 1.0e-9, 0.001, 0.95, 0.99, 0.4, 0.3, 0.7, 0.15, 0.62, 0.33]
+    parts = two("N2", "O2")
+    s = Script(draws)
+    nc, nr, created = vss_collis_cell(air, names, parts, [], sigmamax, fnum, dtc, vol, s)
+    assert (nc, nr) == (1, 0) and s.k == len(draws), (nc, nr, s.k)
+    out["vss_pair_bl"] = dict(species=names, sigmamax=hx(sigmamax), fnum=hx(fnum), dt=hx(dtc), draws=draws, used=s.k,
+                              inp=[dict(v=[hx(c) for c in q["v"]], erot=hx(q["erot"]), evib=hx(q["evib"]), sid=q["sid"], pos=q["pos"]) for q in two("N2", "O2")],
+                              out=[dict(v=[hx(c) for c in q["v"]], erot=hx(q["erot"]), evib=hx(q["evib"]), sid=q["sid"]) for q in parts])
+
+    # tce_3prod: N2 + O2 --> N2 + O + O (TCE), pair order (N2, O2) as the reaction lists it
+    tce = read_tce(air)
+    reactions = []
+    coeffs = {}
+    for r in tce:
+        c1, c2, c3 = tce_coeffs(air, r["react"][0], r["react"][1], r["A"], r["n"], r["ea"])
+        coeffs[" + ".join(r["react"]) + " --> " + " + ".join(r["prod"])] = [hx(c1), hx(c2), hx(c3), hx(r["ea"])]
+        if all(x in names for x in r["react"] + r["prod"]):
+            reactions.append(dict(r1=r["react"][0], r2=r["react"][1], p1=r["prod"][0], p2=r["prod"][1],
+                                  p3=r["prod"][2] if len(r["prod"]) > 2 else None, nprod=len(r["prod"]), ea=r["ea"], c1=c1, c2=c2, c3=c3))
+    out["tce_coeffs"] = coeffs
+    hot = two("N2", "O2")
+    for q in hot:                      # fast pair: E_coll well above the O2 dissociation energy
+        q["v"] = [c * 4.0 for c in q["v"]]
+    hot_in = json.loads(json.dumps(hot))
+    draws = [0.1, 0.8, 1.0e-9, 1.0e-12,
+             0.3, 0.2, 0.4, 0.1, 0.5, 0.3,      # EVIB1, EROT1 (N2)
+             0.6, 0.05,                          # EI for the relative translation (DOF 3)
+             0.25, 0.8,                          # HS_SCATTER 1
+             0.35, 0.6, 0.7, 0.2,                # spare draws for rejections
+             0.45, 0.9, 0.55, 0.15, 0.65, 0.5, 0.75, 0.85]
+    s = Script(draws)
+    nc, nr, created = vss_collis_cell(air, names, hot, reactions, sigmamax, fnum, dtc, vol, s)
+    assert (nc, nr) == (1, 1) and len(created) == 1 and created[0]["sid"] == "O", (nc, nr, created)
+    out["tce_3prod"] = dict(species=names, sigmamax=hx(sigmamax), fnum=hx(fnum), dt=hx(dtc), draws=draws[:s.k], used=s.k,
+                            inp=[dict(v=[hx(c) for c in q["v"]], erot=hx(q["erot"]), evib=hx(q["evib"]), sid=q["sid"], pos=q["pos"]) for q in hot_in],
+                            out=[dict(v=[hx(c) for c in q["v"]], erot=hx(q["erot"]), evib=hx(q["evib"]), sid=q["sid"]) for q in hot],
+                            created=[dict(v=[hx(c) for c in q["v"]], erot=hx(q["erot"]), evib=hx(q["evib"]), sid=q["sid"], pos=q["pos"]) for q in created])
+    json.dump(out, open(os.path.join(HERE, "fortran_pins.json"), "w"), indent=1)
+    print("wrote fortran_pins.json:", {k: (len(v) if isinstance(v, (list, dict)) else v) for k, v in out.items()})
+
+
+if __name__ == "__main__":
+    main()
