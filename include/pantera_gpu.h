@@ -213,6 +213,13 @@ int pgpu_advect(pgpu_ctx* ctx, int32_t tID);
 /* EXCHANGE (src/grid_and_partition.f90:525-622) over NCCL; no-op for nranks == 1 */
 int pgpu_exchange(pgpu_ctx* ctx);
 
+/* EXCHANGE, local half only, for a host that carries the all-to-all itself (the reference's MPI_ALLTOALL +
+ * MPI_ALLTOALLV, grid_and_partition.f90:590-605): removes every particle whose cell belongs to another rank and
+ * returns them as 96-byte host records grouped by destination rank, sendcount(0:NRANKS-1) = records per
+ * destination (the pack + COUNTING_SORT of :562-588).  The receiving side is pgpu_append_particles
+ * (the ADD_PARTICLE_ARRAY loop of :610-612).  Needs no communicator. */
+int pgpu_exchange_pack(pgpu_ctx* ctx, void* sendbuf_aos, int64_t capacity, int64_t* sendcount);
+
 /* counting sort by cell of DSMC_COLLISIONS (src/collisions.f90:61-112), done as a physical
  * SoA reorder.  Called implicitly by pgpu_collide when the store is not sorted. */
 int pgpu_sort(pgpu_ctx* ctx);

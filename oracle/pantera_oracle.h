@@ -44,6 +44,7 @@ int po_set_rng_mode(po_ctx* ctx, int mode);
 /* rng mode 2: rf() replays a caller-supplied sequence (independent pins of tests/golden/fortran_pins.py) */
 int po_set_rng_script(po_ctx* ctx, const double* draws, int64_t n);
 int64_t po_rng_script_used(const po_ctx* ctx);
+int po_collision_type(const po_ctx* ctx);
 /* raw generator access for the known-answer tests */
 double po_rf(po_ctx* ctx);
 int po_pick(po_ctx* ctx, int n); /* pair-selection index INT(N*rf()), one stream word in Philox mode for N <= 65536 */

@@ -19,6 +19,7 @@
 typedef struct {
     po_ctx** ranks;
     int nranks, rank, tID0, nsteps;
+    int collide; /* 0: NO_COLL runs (ADVECT + EXCHANGE only, src/timecycle.f90:288) */
     pthread_barrier_t* bar;
     pgpu_particle** sendbuf; /* [nranks] */
     int64_t* sendcap;        /* [nranks] */
@@ -55,7 +56,7 @@ static void* worker(void* arg) {
             pthread_barrier_wait(w->bar);
         }
         int64_t a = 0, b = 0;
-        if ((w->rc = po_collide(me, tID, &a, &b))) break;
+        if (w->collide && (w->rc = po_collide(me, tID, &a, &b))) break;
         w->ncoll += a;
         w->nreac += b;
     }
@@ -76,7 +77,7 @@ int po_sim_run(po_ctx** ranks, int nranks, int tID0, int nsteps, double* seconds
     clock_gettime(CLOCK_MONOTONIC, &t0);
     for (int r = 0; r < nranks; r++) {
         ws[r].ranks = ranks; ws[r].nranks = nranks; ws[r].rank = r; ws[r].tID0 = tID0; ws[r].nsteps = nsteps;
-        ws[r].bar = &bar; ws[r].sendbuf = sendbuf; ws[r].sendcap = sendcap; ws[r].sendcount = sendcount;
+        ws[r].collide = po_collision_type(ranks[r]) != PGPU_NO_COLL; ws[r].bar = &bar; ws[r].sendbuf = sendbuf; ws[r].sendcap = sendcap; ws[r].sendcount = sendcount;
         pthread_create(&th[r], NULL, worker, &ws[r]);
     }
     int rc = 0;

@@ -338,6 +338,13 @@ class Lib:
     def exchange(self):
         self._call("exchange")
 
+    def exchange_pack(self, nranks):
+        """EXCHANGE, local half: (records grouped by destination rank, count per destination)."""
+        buf = np.zeros(max(self.num_particles(), 1), dtype=PARTICLE_DTYPE)
+        cnt = np.zeros(nranks, dtype=np.int64)
+        self._call("exchange_pack", _p(buf), C.c_int64(len(buf)), _p(cnt))
+        return buf[: int(cnt.sum())], cnt
+
     def sort(self):
         self._call("sort")
 
@@ -466,13 +473,6 @@ class OracleLib(Lib):
         rhs, ab = np.zeros(nnodes), np.zeros(nnodes)
         self._call("deposit_charge_compensated", _p(rhs), _p(ab), C.c_int64(nnodes))
         return rhs, ab
-
-    def exchange_pack(self, nranks):
-        n = self.num_particles()
-        buf = np.zeros(max(n, 1), dtype=PARTICLE_DTYPE)
-        cnt = np.zeros(nranks, dtype=np.int64)
-        self._call("exchange_pack", _p(buf), C.c_int64(len(buf)), _p(cnt))
-        return buf[: int(cnt.sum())], cnt
 
     def get_timings(self):
         s = np.zeros(3)

@@ -493,32 +493,42 @@ __device__ __forceinline__ void select_face(const PgDev& d, const PState& q, int
     for (int i = 0; i < NF; i++)
         if (((open >> i) & 1u) && !(t_lo[i] > T)) rel |= 1u << i;
 
+    /* A single relevant face that passes for certain WILL be taken: its neighbour is the next cell.  Ask for that
+     * cell's filter lines now, so that their latency overlaps the exact-operand load below instead of following it. */
+    if (PG_ADVECT_PREFETCH && rel && !(rel & (rel - 1u))) {
+        const int f = __ffs((int)rel) - 1;
+        const int cn = (f == 0) ? codes.x : (f == 1) ? codes.y : (f == 2) ? codes.z : codes.w;
+        if (cn > 0) {
+            const char* nb = pg_filt_base(d.face_filt, cn - 1, NF + 1);
+#pragma unroll
+            for (int i = 0; i <= NF; i++) asm volatile("prefetch.global.L1 [%0];" ::"l"(nb + i * PG_GEO_LINE));
+        }
+    }
+
     /* the reference loop on the exact operands, relevant faces only, original order */
-    const double* ex = d.face_exact + (size_t)(ic - 1) * (size_t)(NF * 6);
+    const double* ex = d.face_exact + (size_t)(ic - 1) * (size_t)(NF * 8);
     while (rel) {
         const int i = __ffs((int)rel) - 1;
         rel &= rel - 1u;
-        const double2 a = __ldg(reinterpret_cast<const double2*>(ex + 6 * i));
-        const double2 b = __ldg(reinterpret_cast<const double2*>(ex + 6 * i + 2));
-        const double2 c = __ldg(reinterpret_cast<const double2*>(ex + 6 * i + 4));
-        /* normal (a.x, a.y, b.x), face node (b.y, c.x, c.y) */
+        const PgF64x4 a = pg_ldg256(ex + 8 * i);                                           /* nx, ny, nz, Px */
+        const double2 b = __ldg(reinterpret_cast<const double2*>(ex + 8 * i + 4));        /* Py, Pz */
         double vn, dx;
         if (DIMS == 1) {
-            vn = q.vx * a.x;
-            dx = (b.y - q.x) * a.x;
+            vn = q.vx * a.a;
+            dx = (a.d - q.x) * a.a;
         } else if (DIMS == 2) {
-            vn = q.vx * a.x + q.vy * a.y;
-            dx = (b.y - q.x) * a.x + (c.x - q.y) * a.y;
+            vn = q.vx * a.a + q.vy * a.b;
+            dx = (a.d - q.x) * a.a + (b.x - q.y) * a.b;
         } else {
-            vn = q.vx * a.x + q.vy * a.y + q.vz * b.x;
-            dx = (b.y - q.x) * a.x + (c.x - q.y) * a.y + (c.y - q.z) * b.x;
+            vn = q.vx * a.a + q.vy * a.b + q.vz * a.c;
+            dx = (a.d - q.x) * a.a + (b.x - q.y) * a.b + (b.y - q.z) * a.c;
         }
         if (vn >= 0. && vn * dtcoll >= dx) {
             dtcoll = dx / vn;
             boundcoll = i;
-            nsel[0] = a.x;
-            nsel[1] = (DIMS >= 2) ? a.y : 0.;
-            nsel[2] = (DIMS >= 3) ? b.x : 0.;
+            nsel[0] = a.a;
+            nsel[1] = (DIMS >= 2) ? a.b : 0.;
+            nsel[2] = (DIMS >= 3) ? a.c : 0.;
         }
     }
     codesel = (boundcoll == 0) ? codes.x : (boundcoll == 1) ? codes.y : (boundcoll == 2) ? codes.z : codes.w;
@@ -872,17 +882,10 @@ __device__ __forceinline__ bool finish_particle(const PgDev& d, PState& q) {
     return true;
 }
 
-/* registers -> slot.  The histogram / arrival rank of the counting sort is warp-aggregated: the lanes of
- * `peers` that land in the same cell share one atomic.  Every lane of `peers` must call this.  The rank is
- * NOT written here: the atomic's round trip to L2 would stall the warp, so the caller keeps (base, mask) and
- * commits the rank one loop trip later with commit_rank(). */
-struct PendingRank {
-    long long slot;
-    unsigned int base, mask;
-    int leader;
-};
-__device__ __forceinline__ void store_particle(const PgDev& d, long long slot, const PState& q, int dirty, unsigned int peers,
-                                               PendingRank& pr) {
+/* registers -> slot, and the particle's cell is counted for the counting sort: one fire-and-forget reduction
+ * (RED.ADD, nothing waits for it); the arrival rank inside the cell is taken by the scatter pass, where the atomic's
+ * latency hides behind HBM traffic (pgpu_api.cu scatter_kernel).  Every lane of `peers` must call this. */
+__device__ __forceinline__ void store_particle(const PgDev& d, long long slot, const PState& q, int dirty, unsigned int peers) {
     /* one 256-bit store (the compiler splits a struct assignment with int members into three stores) */
     pg_store_sector(d.p.pos + slot, q.x, q.y, q.z, q.ic, q.sid);
     if (dirty & (DIRTY_V | DIRTY_S)) {
@@ -895,14 +898,12 @@ __device__ __forceinline__ void store_particle(const PgDev& d, long long slot, c
         E.erot = q.erot; E.evib = q.evib;
         d.p.ie[slot] = E;
     }
-    int lane = threadIdx.x & 31;
-    /* nranks > 1: a particle that ends in a cell of another rank is an emigrant.  It is not histogrammed (the sort
-     * of this rank will not see it); its slot and destination are recorded for EXCHANGE instead. */
-    bool emig = false;
-    int dest = 0;
+    /* nranks > 1: a particle that ends in a cell of another rank is an emigrant.  It is not counted (the sort of this
+     * rank will not see it); its slot and destination are recorded for EXCHANGE instead. */
     if (d.emig_list) {
-        dest = __ldg(&d.cell_procs[q.ic - 1]);
-        emig = dest != d.rank;
+        const int lane = threadIdx.x & 31;
+        const int dest = __ldg(&d.cell_procs[q.ic - 1]);
+        const bool emig = dest != d.rank;
         const unsigned int em = __ballot_sync(peers, emig);
         if (em) {
             unsigned long long ebase = 0;
@@ -914,23 +915,11 @@ __device__ __forceinline__ void store_particle(const PgDev& d, long long slot, c
                 if (k < (unsigned long long)d.emig_cap) d.emig_list[k] = (unsigned int)slot;
                 else atomicAdd(&d.xrow[PG_XROW_OVF], 1ULL);
                 atomicAdd(&d.xrow[dest], 1ULL);
+                return;
             }
-            peers &= ~em;
         }
     }
-    pr.slot = slot; pr.base = 0; pr.mask = 0u; pr.leader = 0;
-    if (emig) return;
-    unsigned int mask = __match_any_sync(peers, q.ic);
-    int leader = __ffs(mask) - 1;
-    unsigned int base = 0;
-    if (lane == leader) base = atomicAdd(&d.cell_count[q.ic - 1], (unsigned int)__popc(mask));
-    pr.base = base; pr.mask = mask; pr.leader = leader;
-}
-/* all lanes of pr.mask call this together */
-__device__ __forceinline__ void commit_rank(const PgDev& d, const PendingRank& pr) {
-    int lane = threadIdx.x & 31;
-    unsigned int base = __shfl_sync(pr.mask, pr.base, pr.leader);
-    d.cell_rank[pr.slot] = base + __popc(pr.mask & ((1u << lane) - 1u));
+    atomicAdd(&d.cell_count[q.ic - 1], 1u);
 }
 
 __device__ __forceinline__ void tombstone_particle(const PgDev& d, long long slot) {
@@ -958,12 +947,8 @@ __global__ void __launch_bounds__(128, PG_ADVECT_MINBLOCKS) advect_lean_kernel(c
     int bhits[4] = {0, 0, 0, 0};
     PgRng g; /* never drawn from in the LEAN pass */
     g.init(0ULL, 0, 0, 0ULL, 0ULL);
-    PendingRank pr;
-    pr.mask = 0u;
 
     for (;;) {
-        /* rank of the particle stored in the previous trip (its atomic has had a whole trip to return) */
-        if (pr.mask) { commit_rank(d, pr); pr.mask = 0u; }
         /* refill: idle lanes take the next slots of the chunk, in order */
         unsigned int idle = __ballot_sync(FULL, !have);
         if (idle && next < end) {
@@ -1016,7 +1001,7 @@ __global__ void __launch_bounds__(128, PG_ADVECT_MINBLOCKS) advect_lean_kernel(c
                 for (int b = 0; b < 4; b++)
                     if (bhits[b]) atomicAdd(&d.bcount[b + 4 * (q.sid - 1)], (unsigned long long)bhits[b]);
             }
-            store_particle(d, slot, q, dirty, fm, pr);
+            store_particle(d, slot, q, dirty, fm);
         }
     }
 }
@@ -1046,11 +1031,7 @@ __global__ void __launch_bounds__(128) advect_full_kernel(const __grid_constant_
             if (!keep) tombstone_particle(d, slot);
         }
         unsigned int fm = __ballot_sync(0xffffffffu, keep);
-        if (keep) {
-            PendingRank pr;
-            store_particle(d, slot, q, dirty, fm, pr);
-            if (pr.mask) commit_rank(d, pr);
-        }
+        if (keep) store_particle(d, slot, q, dirty, fm);
     }
 }
 
@@ -1102,6 +1083,7 @@ int pg_advect_impl(pgpu_ctx* c, int tID) {
     if (c->cfg.dump_bound_avg_every > 0 && c->dev.tallies)
         c->dev.tally_on = ((tID - c->cfg.dump_bound_start) % c->cfg.dump_bound_avg_every) == 0;
     if (c->np == 0) return PGPU_OK;
+    if ((rc = pg_resolve_vel(c))) return rc;
 
     /* zero the per-call counters and the histogram */
     PG_CUDA(c, cudaMemsetAsync(c->d_cell_count, 0, sizeof(unsigned int) * (size_t)pg_ncells(c), c->stream));

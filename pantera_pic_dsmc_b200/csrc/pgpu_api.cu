@@ -98,7 +98,8 @@ extern "C" int pgpu_create(pgpu_ctx** out, int device) {
     c->d_tile_first = nullptr; c->tile_alloc = 0; c->n_big = 0;
     c->d_cell_order = nullptr; c->d_cell_bucket = nullptr;
     c->d_big_list = nullptr; c->d_big_bbox = nullptr; c->big_alloc = 0;
-    c->d_cell_count = c->d_rank = c->d_cell_off = c->d_hitlist = nullptr;
+    c->d_cell_count = c->d_cell_off = c->d_hitlist = nullptr;
+    c->d_src_of = nullptr; c->vel_deferred = false;
     c->hit_capacity = 0; c->ncells_alloc = 0;
     c->d_status = nullptr; c->h_status = nullptr;
     c->d_scan_tmp = nullptr; c->scan_tmp_bytes = 0;
@@ -129,6 +130,10 @@ extern "C" int pgpu_create(pgpu_ctx** out, int device) {
     memset(c->h_status, 0, sizeof(PgStatus));
     c->cfg.nranks = 1;
     c->cfg.eps_scaling = 1.0;
+    /* deferred vel reorder (pg_sort_impl defer_vel): off by default -- measured r02c at full size: the sort drops from
+     * 2.82 to 1.97 ms but the lane-per-cell gather costs the collision kernel 3.5 ms (29 GB of DRAM reads for 4 GB of
+     * records: scattered 32-byte reads do not merge the way the scatter's writes do) */
+    if (const char* e = getenv("PANTERA_GPU_DEFER_VEL")) c->defer_vel = atoi(e) != 0;
     if (const char* e = getenv("PANTERA_GPU_ADVECT_CHUNK")) {
         int v = atoi(e);
         if (v >= 32 && v <= 65536 && (v & (v - 1)) == 0) c->advect_chunk_override = v;
@@ -152,7 +157,7 @@ extern "C" int pgpu_destroy(pgpu_ctx* c) {
         if (c->slot[i]) cudaFree(c->slot[i]);
     free_planes(c->planes[0]);
     free_planes(c->planes[1]);
-    dev_free(c->d_cell_count); dev_free(c->d_rank); dev_free(c->d_cell_off); dev_free(c->d_hitlist);
+    dev_free(c->d_cell_count); dev_free(c->d_cell_off); dev_free(c->d_hitlist); dev_free(c->d_src_of);
     dev_free(c->d_tile_first); dev_free(c->d_big_list); dev_free(c->d_big_bbox);
     dev_free(c->d_cell_order); dev_free(c->d_cell_bucket);
     dev_free(c->d_status);
@@ -553,7 +558,7 @@ static int build_packed_mesh(pgpu_ctx* c) {
     {
         const int nchf = nf + 1;
         std::vector<float> filt((size_t)((nc + PG_GEO_B - 1) / PG_GEO_B) * (size_t)(nchf * PG_GEO_B * 4), 0.0f);
-        std::vector<double> exact((size_t)nc * nf * 6);
+        std::vector<double> exact((size_t)nc * nf * 8, 0.0);
         for (int ic = 0; ic < nc; ic++) {
             float* blk = &filt[(size_t)(ic / PG_GEO_B) * (size_t)(nchf * PG_GEO_B * 4)];
             for (int j = 0; j < nf; j++) {
@@ -561,7 +566,7 @@ static int build_packed_mesh(pgpu_ctx* c) {
                 int v = c->h_cell_nodes[f];
                 const double* n = &c->h_face_normal[3 * f];
                 const double* P = &c->h_node_coords[3 * (size_t)(v - 1)];
-                double* e = &exact[6 * f];
+                double* e = &exact[8 * f]; /* {nx, ny, nz, Px | Py, Pz, 0, 0}: a 256-bit and a 128-bit load */
                 for (int k = 0; k < 3; k++) { e[k] = n[k]; e[3 + k] = P[k]; }
                 float* q = blk + (size_t)j * (PG_GEO_B * 4) + (size_t)(ic % PG_GEO_B) * 4;
                 double pn = 0.0;
@@ -652,9 +657,11 @@ void pg_refresh_dev(pgpu_ctx* c) {
     if (!c->has_dtrim) d.p.dtrim = nullptr;
     d.np = c->np; d.capacity = c->capacity;
     d.ncells = pg_ncells(c);
-    d.cell_count = c->d_cell_count; d.cell_rank = c->d_rank; d.cell_off = c->d_cell_off; d.hitlist = c->d_hitlist;
+    d.cell_count = c->d_cell_count; d.cell_off = c->d_cell_off; d.hitlist = c->d_hitlist;
     d.emig_list = nullptr; d.emig_cap = c->emig_cap; d.xrow = nullptr; /* switched on by ADVECT when it tracks emigrants */
     d.id_base = c->id_counter;
+    d.vel_src = c->vel_deferred ? c->planes[c->cur ^ 1].vel : nullptr;
+    d.src_of = c->vel_deferred ? c->d_src_of : nullptr;
     d.use_ie = (c->any_internal_dof || c->dev.nr > 0 || c->ie_seen) ? 1 : 0;
     d.tile_first = c->d_tile_first;
     d.cell_order = c->sorted ? c->d_cell_order : nullptr;
@@ -734,6 +741,7 @@ static int copy_plane(pgpu_ctx* c, T* dst, const T* src, long long n) {
 
 int pg_ensure_capacity(pgpu_ctx* c, long long n) {
     if (n <= c->capacity) return PGPU_OK;
+    { int rc0; if ((rc0 = pg_resolve_vel(c))) return rc0; }
     long long cap = std::max<long long>(n, (long long)(1.5 * (double)c->capacity));
     cap = std::max<long long>(cap, 1024);
     int rc;
@@ -753,10 +761,10 @@ int pg_ensure_capacity(pgpu_ctx* c, long long n) {
     c->planes[0] = np0;
     c->planes[1] = np1;
     c->cur = 0;
-    dev_free(c->d_rank);
     dev_free(c->d_hitlist);
-    if ((rc = dev_alloc(c, &c->d_rank, (size_t)cap))) return rc;
+    dev_free(c->d_src_of);
     if ((rc = dev_alloc(c, &c->d_hitlist, (size_t)cap))) return rc;
+    if ((rc = dev_alloc(c, &c->d_src_of, (size_t)cap))) return rc;
     dev_free(c->d_emig_list);
     c->emig_cap = cap / 8 + 1024;
     if ((rc = dev_alloc(c, &c->d_emig_list, (size_t)c->emig_cap))) return rc;
@@ -948,6 +956,7 @@ extern "C" int pgpu_download_particles(pgpu_ctx* c, void* aos, int64_t capacity,
         if ((rc = pg_sort_impl(c))) return rc;
         if ((rc = pg_finish(c, "pgpu_download_particles"))) return rc;
     }
+    if ((rc = pg_resolve_vel(c))) return rc;
     if (capacity < c->np) PG_FAIL(c, PGPU_ERR_INVALID, "download: capacity %lld < %lld particles", (long long)capacity, c->np);
     if (n) *n = c->np;
     if (c->np == 0) return PGPU_OK;
@@ -979,37 +988,51 @@ extern "C" int pgpu_download_particles(pgpu_ctx* c, void* aos, int64_t capacity,
  * 256-bit loads and stores (every random write is a full HBM sector).  Tombstones drop out here.
  * The pass that follows the scan also cuts the sorted store into collision tiles (pgpu_collide.cu).
  * ---------------------------------------------------------------------------------------- */
-__global__ void __launch_bounds__(256) hist_rank_kernel(const PgPos* __restrict__ pos, long long n,
-                                                        unsigned int* __restrict__ cell_count,
-                                                        unsigned int* __restrict__ rank) {
+__global__ void __launch_bounds__(256) hist_kernel(const PgPos* __restrict__ pos, long long n, unsigned int* __restrict__ cell_count) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     int c = (i < n) ? pos[i].ic : 0;
     unsigned int live = __ballot_sync(0xffffffffu, c >= 1);
     if (c < 1) return;
     unsigned int mask = __match_any_sync(live, c);
-    int leader = __ffs(mask) - 1;
-    int lane = threadIdx.x & 31;
-    unsigned int base = 0;
-    if (lane == leader) base = atomicAdd(&cell_count[c - 1], (unsigned int)__popc(mask));
-    base = __shfl_sync(mask, base, leader);
-    rank[i] = base + __popc(mask & ((1u << lane) - 1u));
+    if ((threadIdx.x & 31) == __ffs(mask) - 1) atomicAdd(&cell_count[c - 1], (unsigned int)__popc(mask));
 }
 
+/* dst[cell_off[IC-1] + rank] = src: the rank of a particle inside its cell is its arrival order at the cell's cursor
+ * (one warp-aggregated atomic per (warp, cell); the store is cell-sorted from the previous step, so the lanes of a warp
+ * go to a handful of cells).  The kernel is HBM-bound with most of the issue slots idle, so the atomic's round trip
+ * costs nothing here -- it used to sit in the ADVECT epilogue, together with a 4-byte rank per particle written there
+ * and read back here. */
 __global__ void __launch_bounds__(256) scatter_kernel(PgPlanes src, PgPlanes dst, long long n,
                                                       const unsigned int* __restrict__ cell_off,
-                                                      const unsigned int* __restrict__ rank, int use_ie) {
+                                                      unsigned int* __restrict__ cursor, int use_ie,
+                                                      unsigned int* __restrict__ src_of) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
     /* The source records are read exactly once: streaming (evict-first) loads keep them from displacing the
      * destination lines that L2 is still assembling from the scattered 32-byte stores (measured: -19 % at
      * 3.1e7 particles; streaming the stores as well, or two records per thread, gains nothing more). */
-    const PgRec32 P = pg_ld_stream(src.pos + i);
-    const int ic = (int)(P.w & 0xffffffffULL);
+    PgRec32 P;
+    int ic = 0;
+    if (i < n) {
+        P = pg_ld_stream(src.pos + i);
+        ic = (int)(P.w & 0xffffffffULL);
+    }
+    const unsigned int live = __ballot_sync(0xffffffffu, ic >= 1);
     if (ic < 1) return;
-    size_t o = (size_t)__ldg(&cell_off[ic - 1]) + __ldcs(rank + i);
-    const PgRec32 V = pg_ld_stream(src.vel + i);
+    const unsigned int mask = __match_any_sync(live, ic);
+    const int leader = __ffs(mask) - 1, lane = threadIdx.x & 31;
+    unsigned int base = 0;
+    if (lane == leader) base = atomicAdd(&cursor[ic - 1], (unsigned int)__popc(mask));
+    base = __shfl_sync(mask, base, leader);
+    const size_t o = (size_t)__ldg(&cell_off[ic - 1]) + base + __popc(mask & ((1u << lane) - 1u));
     *reinterpret_cast<PgRec32*>(dst.pos + o) = P;
-    *reinterpret_cast<PgRec32*>(dst.vel + o) = V;
+    if (src_of) {
+        /* deferred: the velocity record stays where it is; the collision kernel fetches it through this index when
+         * it sweeps the cell anyway, and writes the sorted plane once (saves a 32-byte read and write per particle) */
+        src_of[o] = (unsigned int)i;
+    } else {
+        const PgRec32 V = pg_ld_stream(src.vel + i);
+        *reinterpret_cast<PgRec32*>(dst.vel + o) = V;
+    }
     if (use_ie) dst.ie[o] = src.ie[i];
     if (src.dtrim) dst.dtrim[o] = src.dtrim[i];
     if (src.id) dst.id[o] = src.id[i];
@@ -1083,8 +1106,31 @@ __global__ void __launch_bounds__(256) cell_bucket_fill_kernel(const unsigned in
     if (c < ncells) order[base[b] + r] = (unsigned int)c;
 }
 
-int pg_sort_impl(pgpu_ctx* c) {
+__global__ void __launch_bounds__(256) resolve_vel_kernel(const PgVel* __restrict__ vel_src, const unsigned int* __restrict__ src_of,
+                                                          PgVel* __restrict__ vel, long long n) {
+    long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= n) return;
+    const PgRec32 V = pg_ld_stream(vel_src + __ldcs(src_of + o));
+    *reinterpret_cast<PgRec32*>(vel + o) = V;
+}
+
+/* a deferred vel reorder that no collision kernel consumed (e.g. a download right after pgpu_sort) */
+int pg_resolve_vel(pgpu_ctx* c) {
+    if (!c->vel_deferred) return PGPU_OK;
+    if (c->np > 0) {
+        resolve_vel_kernel<<<(unsigned int)((c->np + 255) / 256), 256, 0, c->stream>>>(c->planes[c->cur ^ 1].vel, c->d_src_of,
+                                                                                       c->planes[c->cur].vel, c->np);
+        c->launches++;
+        PG_CUDA(c, cudaGetLastError());
+    }
+    c->vel_deferred = false;
+    pg_refresh_dev(c);
+    return PGPU_OK;
+}
+
+int pg_sort_impl(pgpu_ctx* c, bool defer_vel) {
     int ncells = pg_ncells(c);
+    { int rc0; if ((rc0 = pg_resolve_vel(c))) return rc0; }
     c->n_big = 0;
     c->dev.ntiles = 0;
     if (c->np == 0) {
@@ -1102,13 +1148,16 @@ int pg_sort_impl(pgpu_ctx* c) {
     }
     if (!c->hist_valid) {
         PG_CUDA(c, cudaMemsetAsync(c->d_cell_count, 0, sizeof(unsigned int) * ((size_t)ncells + 1), c->stream));
-        hist_rank_kernel<<<blocks, 256, 0, c->stream>>>(src.pos, c->np, c->d_cell_count, c->d_rank);
+        hist_kernel<<<blocks, 256, 0, c->stream>>>(src.pos, c->np, c->d_cell_count);
         c->launches++;
     }
     size_t tmp = c->scan_tmp_bytes;
     PG_CUDA(c, cub::DeviceScan::ExclusiveSum(c->d_scan_tmp, tmp, c->d_cell_count, c->d_cell_off, ncells + 1, c->stream));
     c->launches++;
-    scatter_kernel<<<blocks, 256, 0, c->stream>>>(src, dst, c->np, c->d_cell_off, c->d_rank, c->dev.use_ie);
+    /* the histogram has been scanned into cell_off: its array now serves as the per-cell cursor of the scatter */
+    PG_CUDA(c, cudaMemsetAsync(c->d_cell_count, 0, sizeof(unsigned int) * ((size_t)ncells + 1), c->stream));
+    scatter_kernel<<<blocks, 256, 0, c->stream>>>(src, dst, c->np, c->d_cell_off, c->d_cell_count, c->dev.use_ie,
+                                                  defer_vel ? c->d_src_of : nullptr);
     c->launches++;
     int ntiles_max = (int)((c->np + PG_TILE_S - 1) / PG_TILE_S);
     PG_CUDA(c, cudaMemsetAsync(&c->d_status->n_big, 0, sizeof(unsigned int), c->stream));
@@ -1135,6 +1184,7 @@ int pg_sort_impl(pgpu_ctx* c) {
     c->sorted = true;
     c->hist_valid = false;
     c->maybe_tombstones = false;
+    c->vel_deferred = defer_vel;
     pg_refresh_dev(c);
     return PGPU_OK;
 }
@@ -1203,7 +1253,7 @@ extern "C" int pgpu_collide(pgpu_ctx* c, int32_t tID, int64_t* timestep_coll, in
     bool did_sort = !c->sorted;
     if (did_sort) {
         tic(c, 1);
-        if ((rc = pg_sort_impl(c))) return rc;
+        if ((rc = pg_sort_impl(c, c->defer_vel))) return rc; /* deferred: the collision kernel finishes the vel reorder */
         toc(c, 1);
     }
     tic(c, 2);
@@ -1264,7 +1314,7 @@ extern "C" int pgpu_run_steps(pgpu_ctx* c, int32_t tID0, int32_t nsteps, int64_t
         bool mcc = c->cfg.collision_type == PGPU_MCC_VAHEDI;
         bool mccv = c->cfg.collision_type == PGPU_MCC;
         tic(c, 1);
-        if ((rc = pg_sort_impl(c))) return rc;
+        if ((rc = pg_sort_impl(c, dsmc && c->defer_vel))) return rc; /* deferred: the collision kernel finishes the vel reorder */
         toc(c, 1);
         tic(c, 2);
         if (dsmc && (rc = pg_collide_impl(c, tID))) return rc;

@@ -307,7 +307,7 @@ __device__ __forceinline__ void pair_collide_fast(const PgDev& d, PgRng& g, doub
  * holds an ACCEPTED candidate, then the warp executes the expensive deflection (pow, sincos) for all of them at
  * once.  Cells with more than PG_TILE_BIG particles are left to the GLOBAL path.
  */
-template <bool IE>
+template <bool IE, bool GATHER>
 __global__ void __launch_bounds__(128, IE ? PG_CELL_MINBLOCKS_IE : PG_CELL_MINBLOCKS) cell_collide_kernel(const __grid_constant__ PgDev d) {
     const unsigned int FULL = 0xffffffffu;
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -320,15 +320,26 @@ __global__ void __launch_bounds__(128, IE ? PG_CELL_MINBLOCKS_IE : PG_CELL_MINBL
         o0 = d.cell_off[c];
         n = (int)(d.cell_off[c + 1] - o0);
     }
-    if (n < 2 || n > PG_TILE_BIG) n = 0; /* ref: src/collisions.f90:129; oversized cells: GLOBAL path */
+    if (n > PG_TILE_BIG) n = 0; /* oversized cells: GLOBAL path (which also finishes their vel reorder) */
+    if (!GATHER && n < 2) n = 0; /* ref: src/collisions.f90:129 */
 
-    /* velocity bounding box, ref: :202-222 */
+    /* velocity bounding box, ref: :202-222.  GATHER: the sort left the velocity records where they were; this sweep
+     * fetches them through the source index and writes the sorted plane (pg_sort_impl defer_vel), so a velocity
+     * record crosses HBM once on its way to its cell instead of twice. */
     double vxmax = -1.e+38, vxmin = 1.e+38, vymax = -1.e+38, vymin = 1.e+38, vzmax = -1.e+38, vzmin = 1.e+38;
     {
-        const PgVel* __restrict__ vp = d.p.vel + o0;
+        PgVel* __restrict__ vp = d.p.vel + o0;
+        const unsigned int* __restrict__ so = d.src_of + o0;
         int i = 0;
         for (; i + 4 <= n; i += 4) {
-            const PgVel A = vp[i], B = vp[i + 1], C = vp[i + 2], D = vp[i + 3];
+            PgVel A, B, C, D;
+            if (GATHER) {
+                const unsigned int ia = __ldcs(so + i), ib = __ldcs(so + i + 1), ic = __ldcs(so + i + 2), id = __ldcs(so + i + 3);
+                A = d.vel_src[ia]; B = d.vel_src[ib]; C = d.vel_src[ic]; D = d.vel_src[id];
+                vp[i] = A; vp[i + 1] = B; vp[i + 2] = C; vp[i + 3] = D;
+            } else {
+                A = vp[i]; B = vp[i + 1]; C = vp[i + 2]; D = vp[i + 3];
+            }
             vxmin = fmin(fmin(vxmin, A.vx), fmin(B.vx, fmin(C.vx, D.vx)));
             vxmax = fmax(fmax(vxmax, A.vx), fmax(B.vx, fmax(C.vx, D.vx)));
             vymin = fmin(fmin(vymin, A.vy), fmin(B.vy, fmin(C.vy, D.vy)));
@@ -337,12 +348,15 @@ __global__ void __launch_bounds__(128, IE ? PG_CELL_MINBLOCKS_IE : PG_CELL_MINBL
             vzmax = fmax(fmax(vzmax, A.vz), fmax(B.vz, fmax(C.vz, D.vz)));
         }
         for (; i < n; i++) {
-            const PgVel A = vp[i];
+            PgVel A;
+            if (GATHER) { A = d.vel_src[__ldcs(so + i)]; vp[i] = A; }
+            else A = vp[i];
             vxmin = fmin(vxmin, A.vx); vxmax = fmax(vxmax, A.vx);
             vymin = fmin(vymin, A.vy); vymax = fmax(vymax, A.vy);
             vzmin = fmin(vzmin, A.vz); vzmax = fmax(vzmax, A.vz);
         }
     }
+    if (GATHER && n < 2) n = 0; /* ref: src/collisions.f90:129 (a lone particle was only moved to its slot) */
     int ncoll = 0;
     double vrmax = 0., fcorr = 0.;
     if (n) ncoll = cell_majorant(d, (int)c, n, vxmin, vxmax, vymin, vymax, vzmin, vzmax, vrmax, fcorr);
@@ -517,7 +531,9 @@ __global__ void __launch_bounds__(256) big_bbox_kernel(const __grid_constant__ P
     double vxmax = -1.e+38, vxmin = 1.e+38, vymax = -1.e+38, vymin = 1.e+38, vzmax = -1.e+38, vzmin = 1.e+38;
     bool any = false;
     for (unsigned long long i = (unsigned long long)o0 + blockIdx.y * 256u + threadIdx.x; i < o1; i += (unsigned long long)gridDim.y * 256u) {
-        const PgVel V = d.p.vel[i];
+        PgVel V;
+        if (d.src_of) { V = d.vel_src[d.src_of[i]]; d.p.vel[i] = V; } /* deferred vel reorder, see cell_collide_kernel */
+        else V = d.p.vel[i];
         vxmin = fmin(vxmin, V.vx); vxmax = fmax(vxmax, V.vx);
         vymin = fmin(vymin, V.vy); vymax = fmax(vymax, V.vy);
         vzmin = fmin(vzmin, V.vz); vzmax = fmax(vzmax, V.vz);
@@ -746,19 +762,29 @@ static int collide_big_cells(pgpu_ctx* c) {
 int pg_collide_impl(pgpu_ctx* c, int tID) {
     int rc;
     if (!c->sorted) PG_FAIL(c, PGPU_ERR_STATE, "collide: store is not sorted");
-    if (c->np < 2) return PGPU_OK;
+    if (c->np < 2) return pg_resolve_vel(c);
     c->dev.tID = tID;
     pg_refresh_dev(c);
     const PgDev& d = c->dev;
 
     {
         unsigned int blocks = (unsigned int)((d.ncells + 127) / 128);
-        if (d.use_ie) cell_collide_kernel<true><<<blocks, 128, 0, c->stream>>>(d);
-        else cell_collide_kernel<false><<<blocks, 128, 0, c->stream>>>(d);
+        const bool gather = c->vel_deferred;
+        if (d.use_ie) {
+            if (gather) cell_collide_kernel<true, true><<<blocks, 128, 0, c->stream>>>(d);
+            else cell_collide_kernel<true, false><<<blocks, 128, 0, c->stream>>>(d);
+        } else {
+            if (gather) cell_collide_kernel<false, true><<<blocks, 128, 0, c->stream>>>(d);
+            else cell_collide_kernel<false, false><<<blocks, 128, 0, c->stream>>>(d);
+        }
         c->launches++;
         PG_CUDA(c, cudaGetLastError());
     }
     if (c->n_big > 0 && (rc = collide_big_cells(c))) return rc;
+    if (c->vel_deferred) { /* every cell has been swept: the sorted vel plane is complete */
+        c->vel_deferred = false;
+        pg_refresh_dev(c);
+    }
     c->hist_valid = false;
     return PGPU_OK;
 }
@@ -771,6 +797,7 @@ int pg_mcc_vss_impl(pgpu_ctx* c, int tID) {
         PG_FAIL(c, PGPU_ERR_STATE, "mcc_collisions: background density table covers %lld of %d cells",
                 (long long)c->mcc_cell_nrho_cells, pg_ncells(c));
     if (c->np == 0) return PGPU_OK;
+    { int rc0; if ((rc0 = pg_resolve_vel(c))) return rc0; }
     c->dev.tID = tID;
     pg_refresh_dev(c);
     mcc_vss_kernel<<<(unsigned int)((c->np + 127) / 128), 128, 0, c->stream>>>(c->dev);

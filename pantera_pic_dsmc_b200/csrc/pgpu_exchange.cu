@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(256) xpack_list_kernel(const __grid_constant__
 }
 
 /* append the received records (ADD_PARTICLE_ARRAY loop, ref: grid_and_partition.f90:610-612).  with_rank: the
- * histogram of the ADVECT epilogue is still valid; the immigrant joins it (count + arrival rank in its cell), so
+ * histogram of the ADVECT epilogue is still valid; the immigrant joins it, so
  * the counting sort that follows needs no recount. */
 __global__ void __launch_bounds__(256) xunpack_kernel(const __grid_constant__ PgDev d, const double* __restrict__ recvbuf,
                                                       long long n, PgPlanes p, long long base, int with_rank) {
@@ -172,7 +172,23 @@ __global__ void __launch_bounds__(256) xunpack_kernel(const __grid_constant__ Pg
     if (dtrim != d.dt) d.status->flag_dtrim = 1;
     t = r[10];
     if (p.id) p.id[o] = *reinterpret_cast<long long*>(&t);
-    if (with_rank) d.cell_rank[o] = atomicAdd(&d.cell_count[cs.x - 1], 1u);
+    if (with_rank) atomicAdd(&d.cell_count[cs.x - 1], 1u);
+}
+
+/* 88-byte wire records -> 96-byte host records (TYPE PARTICLE_DATA_STRUCTURE, src/particle.f90:28-37) */
+__global__ void __launch_bounds__(256) xrec_to_aos_kernel(const double* __restrict__ rec, long long n, unsigned char* __restrict__ aos,
+                                                          int rank, long long id_base, int keep_id) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double* r = rec + i * XREC_DOUBLES;
+    double* f = reinterpret_cast<double*>(aos + (size_t)i * 96);
+    for (int k = 0; k < 9; k++) f[k] = r[k];
+    f[9] = r[9]; /* (IC, S_ID) */
+    double t = r[10];
+    long long id = *reinterpret_cast<long long*>(&t);
+    if (!keep_id) id = (long long)rank + ((id_base + i) << 8);
+    *reinterpret_cast<long long*>(aos + (size_t)i * 96 + 80) = id;
+    *reinterpret_cast<long long*>(aos + (size_t)i * 96 + 88) = 0;
 }
 
 __global__ void fill_kernel(double* p, long long n, double v) {
@@ -221,6 +237,63 @@ int pg_allreduce_sum_f64(pgpu_ctx* c, double* buf, long long n) {
     return PGPU_OK;
 }
 
+static int ensure_xbuf(pgpu_ctx* c, long long need) {
+    if (need <= c->xbuf_capacity) return PGPU_OK;
+    cudaFree(c->d_sendbuf); cudaFree(c->d_recvbuf);
+    c->d_sendbuf = c->d_recvbuf = nullptr;
+    long long cap = need + need / 2 + 1024;
+    /* (96 bytes per slot: the buffers also stage host-format records for pgpu_exchange_pack) */
+    PG_CUDA(c, cudaMalloc(&c->d_sendbuf, 96 * (size_t)cap));
+    PG_CUDA(c, cudaMalloc(&c->d_recvbuf, 96 * (size_t)cap));
+    c->xbuf_capacity = cap;
+    return PGPU_OK;
+}
+
+extern "C" int pgpu_exchange_pack(pgpu_ctx* c, void* sendbuf_aos, int64_t capacity, int64_t* sendcount) {
+    if (!c || !sendcount) return PGPU_ERR_INVALID;
+    int rc;
+    if ((rc = pg_prepare(c))) return rc;
+    const int nr = c->cfg.nranks > 1 ? c->cfg.nranks : 1;
+    for (int r = 0; r < nr; r++) sendcount[r] = 0;
+    if (nr == 1 || c->np == 0) return PGPU_OK;
+    if (!c->dev.cell_procs) PG_FAIL(c, PGPU_ERR_STATE, "exchange_pack: CELL_PROCS not set");
+    if (c->cell_procs_max >= nr) PG_FAIL(c, PGPU_ERR_INVALID, "exchange_pack: CELL_PROCS holds rank %d but there are %d ranks", c->cell_procs_max, nr);
+    if (!c->d_xcount) PG_CUDA(c, cudaMalloc((void**)&c->d_xcount, sizeof(unsigned long long) * PG_XROW * (4 + 64)));
+    if ((rc = pg_reset_status(c))) return rc;
+    if ((rc = pg_resolve_vel(c))) return rc;
+    pg_refresh_dev(c);
+    unsigned long long* xcount = c->d_xcount;
+    unsigned long long* xoff = c->d_xcount + PG_XROW;
+    unsigned long long* xcursor = c->d_xcount + 2 * PG_XROW;
+    const unsigned int blocks = (unsigned int)((c->np + 255) / 256);
+    PG_CUDA(c, cudaMemsetAsync(xcount, 0, sizeof(unsigned long long) * 3 * PG_XROW, c->stream));
+    xcount_kernel<<<blocks, 256, 0, c->stream>>>(c->dev, xcount);
+    unsigned long long h[PG_XROW];
+    PG_CUDA(c, cudaMemcpyAsync(h, xcount, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    PG_CUDA(c, cudaStreamSynchronize(c->stream));
+    unsigned long long soff[65] = {0};
+    for (int r = 0; r < nr; r++) {
+        sendcount[r] = (int64_t)h[r];
+        soff[r + 1] = soff[r] + h[r];
+    }
+    const long long nsend = (long long)soff[nr];
+    c->emig_valid = false;
+    if (nsend == 0) return PGPU_OK;
+    if (nsend > capacity) PG_FAIL(c, PGPU_ERR_INVALID, "exchange_pack: %lld emigrants do not fit the buffer (%lld records)", nsend, (long long)capacity);
+    if (!sendbuf_aos) PG_FAIL(c, PGPU_ERR_INVALID, "exchange_pack: null buffer");
+    if ((rc = ensure_xbuf(c, nsend))) return rc;
+    PG_CUDA(c, cudaMemcpyAsync(xoff, soff, sizeof(unsigned long long) * 64, cudaMemcpyHostToDevice, c->stream));
+    xpack_kernel<<<blocks, 256, 0, c->stream>>>(c->dev, (double*)c->d_sendbuf, xoff, xcursor);
+    xrec_to_aos_kernel<<<(unsigned int)((nsend + 255) / 256), 256, 0, c->stream>>>((const double*)c->d_sendbuf, nsend, (unsigned char*)c->d_recvbuf,
+                                                                                 c->cfg.rank, c->id_counter, c->cfg.track_id ? 1 : 0);
+    PG_CUDA(c, cudaMemcpyAsync(sendbuf_aos, c->d_recvbuf, 96 * (size_t)nsend, cudaMemcpyDeviceToHost, c->stream));
+    c->launches += 3;
+    c->maybe_tombstones = true;
+    c->sorted = false;
+    c->hist_valid = false;
+    return pg_finish(c, "pgpu_exchange_pack");
+}
+
 int pg_exchange_impl(pgpu_ctx* c) {
     const int nr = c->cfg.nranks;
     if (nr <= 1) return PGPU_OK;
@@ -229,6 +302,7 @@ int pg_exchange_impl(pgpu_ctx* c) {
     if (!c->dev.cell_procs) PG_FAIL(c, PGPU_ERR_STATE, "exchange: CELL_PROCS not set");
     if (c->cell_procs_max >= nr) PG_FAIL(c, PGPU_ERR_INVALID, "exchange: CELL_PROCS holds rank %d but there are %d ranks", c->cell_procs_max, nr);
     int rc;
+    if ((rc = pg_resolve_vel(c))) return rc;
     pg_refresh_dev(c);
     ncclComm_t comm = (ncclComm_t)c->nccl_comm;
     unsigned long long* xcount = c->d_xcount;                 /* [PG_XROW] my counts per destination (+ list length, overflow) */
@@ -268,14 +342,7 @@ int pg_exchange_impl(pgpu_ctx* c) {
     }
     long long nsend = (long long)soff[nr], nrecv = (long long)roff[nr];
     long long need = std::max(nsend, nrecv);
-    if (need > c->xbuf_capacity) {
-        cudaFree(c->d_sendbuf); cudaFree(c->d_recvbuf);
-        c->d_sendbuf = c->d_recvbuf = nullptr;
-        long long cap = need + need / 2 + 1024;
-        PG_CUDA(c, cudaMalloc(&c->d_sendbuf, sizeof(double) * XREC_DOUBLES * (size_t)cap));
-        PG_CUDA(c, cudaMalloc(&c->d_recvbuf, sizeof(double) * XREC_DOUBLES * (size_t)cap));
-        c->xbuf_capacity = cap;
-    }
+    if ((rc = ensure_xbuf(c, need))) return rc;
     if (nsend > 0) {
         /* (packed before the store can be re-allocated below: the list holds slots of the current planes) */
         PG_CUDA(c, cudaMemcpyAsync(xoff, soff.data(), sizeof(unsigned long long) * 64, cudaMemcpyHostToDevice, c->stream));

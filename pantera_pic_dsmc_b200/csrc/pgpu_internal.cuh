@@ -60,7 +60,10 @@
 #define PG_CELL_TRIES 2 /* acceptance tests a lane runs before the warp re-converges for the deflections */
 #endif
 #ifndef PG_ADVECT_MINBLOCKS
-#define PG_ADVECT_MINBLOCKS 6
+#define PG_ADVECT_MINBLOCKS 7 /* 72 registers; swept 6/7/8/10 at full size (r02b): 9.00/8.70/9.39/13.4 ms */
+#endif
+#ifndef PG_ADVECT_PREFETCH
+#define PG_ADVECT_PREFETCH 0 /* next-cell filter prefetch: measured r02b, +3 % move time (more L1 traffic than latency saved) */
 #endif
 /* particles one warp of the LEAN advect pass works through (lanes refill as their particle finishes) */
 #ifndef PG_ADVECT_CHUNK_MAX
@@ -135,6 +138,13 @@ __device__ __forceinline__ const char* pg_filt_base(const float* filt, int cell0
     return reinterpret_cast<const char*>(filt) + (size_t)(cell0 / PG_GEO_B) * (size_t)(nch * PG_GEO_LINE) +
            (size_t)((cell0 % PG_GEO_B) * 16);
 }
+/* 32 read-only bytes as ONE load (LDG.E.256.CONSTANT) */
+struct __align__(32) PgF64x4 { double a, b, c, d; };
+__device__ __forceinline__ PgF64x4 pg_ldg256(const void* p) {
+    PgF64x4 v;
+    asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.a), "=d"(v.b), "=d"(v.c), "=d"(v.d) : "l"(p));
+    return v;
+}
 /* double e of the record (e = 6*face + {0,1,2: normal, 3,4,5: point}) */
 __device__ __forceinline__ double pg_geo_at(const char* gb, int e) {
     return __ldg(reinterpret_cast<const double*>(gb + (e >> 1) * PG_GEO_LINE + (e & 1) * 8));
@@ -200,7 +210,7 @@ struct PgDev {
      * {outward normal (3 doubles), face node (3 doubles)} cell-major, read only for the faces the bracket cannot
      * decide (on average one per crossing, none on the final flight) */
     const float* face_filt;   /* [ceil(nc/8)] blocks of (nf+1)*PG_GEO_B*4 floats */
-    const double* face_exact; /* [nc][nf][6] */
+    const double* face_exact; /* [nc][nf][8]: {nx, ny, nz, Px | Py, Pz, -, -}, one 64-byte slot per face */
     const int* face_code;    /* [nc][nf]: >0 neighbour cell to hop into; 0 boundary without a physical
                                 group (remove); <0 boundary with physical group -code        */
     const double *face_tang1, *face_tang2; /* [nc][4][3] (3-D) */
@@ -238,9 +248,13 @@ struct PgDev {
     long long capacity; /* slots allocated */
     int ncells;         /* nc (unstructured) or nx*ny */
     unsigned int* cell_count; /* [ncells] histogram of IC filled by the ADVECT epilogue */
-    unsigned int* cell_rank;  /* [capacity] arrival rank of the particle inside its cell */
     unsigned int* cell_off;   /* [ncells+1] exclusive prefix of cell_count (valid while sorted) */
     unsigned int* hitlist;    /* slots deferred to the boundary-interaction pass */
+    /* deferred velocity reorder (pg_sort_impl defer_vel): the sort has moved pos (and ie, dtrim, id) but not vel;
+     * sorted slot o takes its velocity record from vel_src[src_of[o]].  The collision kernels do that gather while
+     * they sweep a cell for its velocity bounding box, and write the sorted vel plane once.  Null when not deferred. */
+    const PgVel* vel_src;
+    const unsigned int* src_of;
     long long id_base;        /* ID counter for particles created on the device */
     int use_ie;               /* 1: the ie plane is live (some particle can hold internal energy) */
     const unsigned int* tile_first; /* [ntiles+1] first cell of every collision tile (valid while sorted) */
@@ -305,7 +319,10 @@ struct pgpu_ctx {
     unsigned long long* d_big_bbox; /* [n_big][6] order-encoded velocity bounds */
     long long big_alloc;
     long long id_counter;
-    unsigned int *d_cell_count, *d_rank, *d_cell_off, *d_hitlist;
+    unsigned int *d_cell_count, *d_cell_off, *d_hitlist;
+    unsigned int* d_src_of; /* [capacity] source slot of every sorted slot while the vel reorder is deferred */
+    bool vel_deferred;
+    bool defer_vel = false; /* PANTERA_GPU_DEFER_VEL (experiment knob, see pgpu_create) */
     long long hit_capacity;
     int ncells_alloc;
     PgStatus* d_status;
@@ -381,7 +398,8 @@ int pg_finish(pgpu_ctx* c, const char* what); /* sync stream, read back status, 
 int pg_ensure_capacity(pgpu_ctx* c, long long n);
 int pg_ensure_cell_arrays(pgpu_ctx* c);
 int pg_reset_status(pgpu_ctx* c);
-int pg_sort_impl(pgpu_ctx* c);               /* histogram (if needed) + scan + scatter; async */
+int pg_sort_impl(pgpu_ctx* c, bool defer_vel = false); /* histogram (if needed) + scan + scatter; async */
+int pg_resolve_vel(pgpu_ctx* c);             /* finishes a deferred vel reorder (no-op otherwise); async */
 int pg_advect_impl(pgpu_ctx* c, int tID);    /* async */
 int pg_collide_impl(pgpu_ctx* c, int tID);   /* async except for the dependency-round loop */
 int pg_exchange_impl(pgpu_ctx* c);

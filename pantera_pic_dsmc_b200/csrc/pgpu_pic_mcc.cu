@@ -246,6 +246,7 @@ extern "C" int pgpu_deposit_charge(pgpu_ctx* c, double* rhs_host, int64_t nnodes
 int pg_mcc_impl(pgpu_ctx* c, int tID) {
     if (!c->dev.mcc_ncomp) PG_FAIL(c, PGPU_ERR_STATE, "mcc_vahedi: background mixture not set");
     if (c->np == 0) return PGPU_OK;
+    { int rc0; if ((rc0 = pg_resolve_vel(c))) return rc0; }
     c->dev.tID = tID;
     pg_refresh_dev(c);
     /* ref: src/collisions.f90:1637-1644 (single-precision literal 1e-12) */

@@ -66,6 +66,41 @@ def test_vss_collisions_value_for_value(gpu, oracle_philox, nx, ny, n):
     util.assert_particles_match(a, b, rtol=1e-12, atol=1e-9, what="VSS argon")
 
 
+@pytest.mark.parametrize("nx,ny,n", [(16, 8, 100_000), (2, 1, 40_000)])
+def test_deferred_velocity_reorder_value_for_value(oracle_philox, monkeypatch, nx, ny, n):
+    """PANTERA_GPU_DEFER_VEL=1: the sort moves pos only, the collision kernels (CELL path, and the GLOBAL path for the
+    20000-particle cells of the second case) fetch the velocities through the source index.  Same results, and a
+    download between a sort and a collide resolves the pending reorder."""
+    monkeypatch.setenv("PANTERA_GPU_DEFER_VEL", "1")
+    gpu = capi.load_gpu(0)
+    try:
+        w = wl.c1_argon_box(n, nx=nx, ny=ny)
+        w.cfg.track_id = 1
+        wl.apply(gpu, w)
+        wl.apply(oracle_philox, w, upload=False)
+        for tID in (1, 2):
+            gpu.advect(tID)
+            gpu.sort()
+            ps = gpu.download_particles()
+            gpu.advect(10 + tID)                         # leaves the store unsorted: pgpu_collide sorts (deferred) itself
+            ps = gpu.download_particles()
+            gpu.upload_particles(ps)
+            cg = gpu.collide(tID)                        # sort with deferred vel + gather in the collision kernels
+            mid = gpu.download_particles()
+            order = np.argsort(mid["IC"], kind="stable")
+            assert np.all(np.diff(mid["IC"]) >= 0)
+            # the oracle collides the device's sorted order, from the pre-collision velocities
+            pre = util.by_id(ps)
+            srt = pre[np.searchsorted(pre["ID"], mid["ID"])]
+            srt["IC"] = mid["IC"]
+            oracle_philox.upload_particles(srt)
+            co = oracle_philox.collide(tID)
+            assert co == cg and cg[0] > 0, (co, cg)
+            util.assert_particles_match(oracle_philox.download_particles(), mid, rtol=1e-12, atol=1e-9, what="deferred vel")
+    finally:
+        gpu.close()
+
+
 def test_air_bl_tce_value_for_value(gpu, oracle_philox):
     w = wl.c2_air_box(60_000, nx=6, ny=5, T=12000.0, dt=3e-7)
     sorted_pair(gpu, oracle_philox, w)
