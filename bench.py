@@ -57,7 +57,9 @@ def measured_peak_gbs():
 def build_workload(args, rank, world):
     from pantera_pic_dsmc_b200 import capi, workloads as wl
     ncx, ncy, ncz = args.cubes
-    w = wl.c5_channel_strip(ncx, ncy, ncz, n=args.particles, rank=rank, world=world, seed=1234 + rank, pinned=True)
+    # no mean drift (SURVEY 8d's C5 has none): the strips stay balanced, so the scaling numbers measure the code and
+    # not a population that piles up against the downstream end cap
+    w = wl.c5_channel_strip(ncx, ncy, ncz, n=args.particles, rank=rank, world=world, seed=1234 + rank, pinned=True, u_drift=0.0)
     return w
 
 
@@ -111,7 +113,7 @@ def cpu_baseline(args, seconds=12.0):
     """Oracle (single thread) on a bounded sample of the same workload: a smaller box, same cell size,
     same particles per cell, same dt.  Reported, not the target."""
     from pantera_pic_dsmc_b200 import capi, workloads as wl
-    w = wl.c5_channel_strip(24, 24, 24, n=24 * 24 * 24 * 6 * 40, rank=0, world=1, seed=99)  # 3.3e6 particles, 318 MB: out of cache
+    w = wl.c5_channel_strip(24, 24, 24, n=24 * 24 * 24 * 6 * 40, rank=0, world=1, seed=99, u_drift=0.0)  # 3.3e6 particles, 318 MB: out of cache
     o = capi.load_oracle(rng_mode=0)
     wl.apply(o, w)
     o.run_steps(1, 1)  # warm-up: first touch
@@ -223,6 +225,15 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def gather_rows(row):
+        """one row of floats per rank -> list of rows (rank order)"""
+        if world == 1:
+            return [list(map(float, row))]
+        t = torch.tensor(list(map(float, row)), dtype=torch.float64, device="cuda")
+        out = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(out, t)
+        return [o.tolist() for o in out]
+
     def sum_over_ranks(x):
         if world == 1:
             return x
@@ -244,6 +255,8 @@ def main():
     n_now = gpu.num_particles()
     n_total = sum_over_ranks(float(n_now))
     value = n_total * args.steps / (total_ms * 1e-3)
+    per_rank = gather_rows([n_now, float(ms[0]) / args.steps, float(ms[1]) / args.steps, float(ms[2]) / args.steps,
+                            float(ms[4]) / args.steps, float(ms[5]) / args.steps])
     peak, peak_src = measured_peak_gbs()
     grp = {"move": float(ms[0]) / args.steps, "sort": float(ms[1]) / args.steps, "collide": float(ms[2]) / args.steps,
            "exchange": float(ms[4]) / args.steps}
@@ -349,6 +362,8 @@ def main():
                        "l2_policy": "inputs (8 GB of pos+vel records per GPU, streamed every step) are far larger than the 126 MB L2",
                        "rng": "Philox4x32-10 per particle/candidate", "ids": "regenerated on download (track_id=0)"},
             "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu, "gpu_launches": int(launches),
+            "per_rank": [{"rank": r, "particles": int(v[0]), "move": v[1], "sort": v[2], "collide": v[3], "exchange": v[4],
+                          "step": v[5]} for r, v in enumerate(per_rank)],
             "clocks": clocks, "collisions_per_step": ncoll / args.steps, "wall_ms_per_step": wall_ms / args.steps,
             "setup_seconds": setup_s,
         }

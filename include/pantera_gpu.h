@@ -242,6 +242,16 @@ int pgpu_remove_species(pgpu_ctx* ctx, int32_t sp_id);
 int pgpu_run_steps(pgpu_ctx* ctx, int32_t tID0, int32_t nsteps,
                    int64_t* total_coll, int64_t* total_reac);
 
+/* ---- dump / restart -------------------------------------------------- */
+/* DUMP_PARTICLES_FILE (src/tools.f90:327-365) / READ_PARTICLES_FILE (src/tools.f90:465-517): the file
+ * <path_prefix>proc_<rank:05d>_time_<timestep:08d> in the reference's binary layout (Fortran sequential unformatted,
+ * big-endian, one 80-byte record per particle: X Y Z VX VY VZ EROT EVIB S_ID IC DTRIM), written from / read into the
+ * device store without a host copy of the particle array.  binary must be non-zero (Binary_output: .TRUE., the
+ * reference's default); the file must not exist when dumping (STATUS='NEW').  Reading appends and, like the
+ * reference, gives every restarted particle DTRIM = DT. */
+int pgpu_dump_particles_file(pgpu_ctx* ctx, const char* path_prefix, int32_t timestep, int32_t binary);
+int pgpu_read_particles_file(pgpu_ctx* ctx, const char* path_prefix, int32_t timestep, int32_t binary);
+
 /* ---- counters / diagnostics ------------------------------------------------------------ */
 /* BOUNDARY_COLL_COUNT(4*NS) and WALL_COLL_COUNT(NW*NS) of the last ADVECT (timecycle.f90:2138-2144) */
 int pgpu_get_boundary_counts(pgpu_ctx* ctx, int64_t* boundary_coll_count, int64_t nb,

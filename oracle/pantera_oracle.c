@@ -1711,6 +1711,69 @@ int po_exchange_pack(po_ctx* w, void* sendbuf, int64_t capacity, int64_t* sendco
     return PGPU_OK;
 }
 
+/* ------------------------------------------------------------------------------------------
+ * DUMP_PARTICLES_FILE / READ_PARTICLES_FILE, binary flavour. ref: src/tools.f90:327-365, 465-517.
+ * gfortran SEQUENTIAL UNFORMATTED with CONVERT='BIG_ENDIAN': every WRITE is one record framed by its byte length as
+ * a 4-byte integer before and after, markers and payload all byte-swapped.
+ * ---------------------------------------------------------------------------------------- */
+static void put_be(unsigned char* dst, const void* src, int nbytes) {
+    const unsigned char* s = (const unsigned char*)src;
+    for (int i = 0; i < nbytes; i++) dst[i] = s[nbytes - 1 - i];
+}
+static void dump_file_name(const po_ctx* w, char* out, size_t n, const char* prefix, int timestep) {
+    snprintf(out, n, "%sproc_%05d_time_%08d", prefix ? prefix : "", w->c.rank, timestep); /* "(A,A,I0.5,A6,I0.8)" */
+}
+int po_dump_particles_file(po_ctx* w, const char* path_prefix, int32_t timestep, int32_t binary) {
+    if (!binary) FAIL(w, PGPU_ERR_UNSUPPORTED, "po_dump_particles_file: binary flavour only");
+    char name[1024];
+    dump_file_name(w, name, sizeof(name), path_prefix, timestep);
+    FILE* probe = fopen(name, "rb");
+    if (probe) { fclose(probe); FAIL(w, PGPU_ERR_INVALID, "po_dump_particles_file: %.200s exists (STATUS='NEW')", name); }
+    FILE* fp = fopen(name, "wb");
+    if (!fp) FAIL(w, PGPU_ERR_INVALID, "po_dump_particles_file: cannot create %.200s", name);
+    for (int64_t ip = 0; ip < w->np; ip++) {
+        const part_t* q = &w->p[ip];
+        unsigned char rec[88];
+        const int32_t len = 80;
+        const double f[8] = {q->X, q->Y, q->Z, q->VX, q->VY, q->VZ, q->EROT, q->EVIB};
+        put_be(rec, &len, 4);
+        for (int k = 0; k < 8; k++) put_be(rec + 4 + 8 * k, &f[k], 8);
+        put_be(rec + 68, &q->S_ID, 4);
+        put_be(rec + 72, &q->IC, 4);
+        put_be(rec + 76, &q->DTRIM, 8);
+        put_be(rec + 84, &len, 4);
+        if (fwrite(rec, 1, 88, fp) != 88) { fclose(fp); FAIL(w, PGPU_ERR_INVALID, "po_dump_particles_file: short write"); }
+    }
+    fclose(fp);
+    return PGPU_OK;
+}
+int po_read_particles_file(po_ctx* w, const char* path_prefix, int32_t timestep, int32_t binary) {
+    if (!binary) FAIL(w, PGPU_ERR_UNSUPPORTED, "po_read_particles_file: binary flavour only");
+    char name[1024];
+    dump_file_name(w, name, sizeof(name), path_prefix, timestep);
+    FILE* fp = fopen(name, "rb");
+    if (!fp) FAIL(w, PGPU_ERR_INVALID, "po_read_particles_file: particle restart file %.200s not found", name);
+    unsigned char rec[88];
+    while (fread(rec, 1, 88, fp) == 88) {
+        pgpu_particle q;
+        memset(&q, 0, sizeof(q));
+        double f[8];
+        for (int k = 0; k < 8; k++) put_be((unsigned char*)&f[k], rec + 4 + 8 * k, 8);
+        int32_t sid, ic;
+        put_be((unsigned char*)&sid, rec + 68, 4);
+        put_be((unsigned char*)&ic, rec + 72, 4);
+        q.X = f[0]; q.Y = f[1]; q.Z = f[2]; q.VX = f[3]; q.VY = f[4]; q.VZ = f[5]; q.EROT = f[6]; q.EVIB = f[7];
+        q.S_ID = sid; q.IC = ic;
+        q.DTRIM = w->c.dt; /* INIT_PARTICLE(..., DT, ...), ref: src/tools.f90:497 */
+        q.ID = (int64_t)w->c.rank + (w->id_counter << 8);
+        int rc = po_append_particles(w, &q, 1, (int32_t)sizeof(q));
+        if (rc) { fclose(fp); return rc; }
+        w->id_counter++;
+    }
+    fclose(fp);
+    return PGPU_OK;
+}
+
 /* ref: src/timecycle.f90:271-299 (PIC_TYPE==NONE branch of TIME_LOOP), single rank */
 int po_run_steps(po_ctx* w, int32_t tID0, int32_t nsteps, int64_t* total_coll, int64_t* total_reac) {
     int64_t tc = 0, tr = 0;

@@ -112,6 +112,8 @@ int po_collide(po_ctx* ctx, int32_t tID, int64_t* timestep_coll, int64_t* timest
 int po_mcc_vahedi(po_ctx* ctx, int32_t tID, int64_t* timestep_coll, int64_t* timestep_reac);
 int po_mcc_collisions(po_ctx* ctx, int32_t tID, int64_t* timestep_coll, int64_t* timestep_reac);
 int po_remove_species(po_ctx* ctx, int32_t sp_id);
+int po_dump_particles_file(po_ctx* ctx, const char* path_prefix, int32_t timestep, int32_t binary);
+int po_read_particles_file(po_ctx* ctx, const char* path_prefix, int32_t timestep, int32_t binary);
 int po_run_steps(po_ctx* ctx, int32_t tID0, int32_t nsteps, int64_t* total_coll, int64_t* total_reac);
 
 int po_get_boundary_counts(po_ctx* ctx, int64_t* boundary_coll_count, int64_t nb,

@@ -366,6 +366,12 @@ class Lib:
     def remove_species(self, sp):
         self._call("remove_species", C.c_int32(sp))
 
+    def dump_particles_file(self, path_prefix: str, timestep: int, binary: bool = True):
+        self._call("dump_particles_file", C.c_char_p(path_prefix.encode()), C.c_int32(timestep), C.c_int32(int(binary)))
+
+    def read_particles_file(self, path_prefix: str, timestep: int, binary: bool = True):
+        self._call("read_particles_file", C.c_char_p(path_prefix.encode()), C.c_int32(timestep), C.c_int32(int(binary)))
+
     def run_steps(self, tID0: int, nsteps: int):
         a, b = C.c_int64(), C.c_int64()
         self._call("run_steps", C.c_int32(tID0), C.c_int32(nsteps), C.byref(a), C.byref(b))

@@ -30,6 +30,7 @@ namespace {
 struct PState {
     double x, y, z, vx, vy, vz, erot, evib, dtrim;
     int ic, sid;
+    int foreign; /* the current cell belongs to another rank (carried by the hop codes, PG_CODE_FOREIGN) */
 };
 
 enum { DIRTY_V = 1, DIRTY_E = 2, DIRTY_S = 4 };
@@ -499,7 +500,7 @@ __device__ __forceinline__ void select_face(const PgDev& d, const PState& q, int
         const int f = __ffs((int)rel) - 1;
         const int cn = (f == 0) ? codes.x : (f == 1) ? codes.y : (f == 2) ? codes.z : codes.w;
         if (cn > 0) {
-            const char* nb = pg_filt_base(d.face_filt, cn - 1, NF + 1);
+            const char* nb = pg_filt_base(d.face_filt, (cn & PG_CODE_CELL_MASK) - 1, NF + 1);
 #pragma unroll
             for (int i = 0; i <= NF; i++) asm volatile("prefetch.global.L1 [%0];" ::"l"(nb + i * PG_GEO_LINE));
         }
@@ -596,8 +597,9 @@ __device__ __forceinline__ int unstructured_iter(const PgDev& d, PgRng& g, PStat
                 /* ref: :1311-1312, :1648-1652 cell hop */
                 move_particle<AXI>(q, dtcoll);
                 q.dtrim = q.dtrim - dtcoll;
-                q.ic = code;
-                ic = code;
+                q.ic = code & PG_CODE_CELL_MASK;
+                q.foreign = (code & PG_CODE_FOREIGN) != 0;
+                ic = q.ic;
                 if (++hops > PG_MAX_HOPS) {
                     pg_set_err(d, PG_DEVERR_HOPS);
                     remove = 1;
@@ -847,6 +849,7 @@ __device__ __forceinline__ bool load_particle(const PgDev& d, long long slot, PS
     q.vx = V.vx; q.vy = V.vy; q.vz = V.vz;
     q.dtrim = d.p.dtrim ? d.p.dtrim[slot] : d.dt;
     q.erot = 0.; q.evib = 0.;
+    q.foreign = 0;
     dirty = 0;
     if (d.pic != PGPU_PIC_NONE) {
         double e[3], b[3];
@@ -902,7 +905,10 @@ __device__ __forceinline__ void store_particle(const PgDev& d, long long slot, c
      * rank will not see it); its slot and destination are recorded for EXCHANGE instead. */
     if (d.emig_list) {
         const int lane = threadIdx.x & 31;
-        const int dest = __ldg(&d.cell_procs[q.ic - 1]);
+        /* emig_trust: every particle started the step in a cell of this rank, so the ownership flag carried along the
+         * face walk decides, and only the emigrants (about 1 %) read CELL_PROCS; otherwise every particle does */
+        int dest = d.rank;
+        if (!d.emig_trust || q.foreign) dest = __ldg(&d.cell_procs[q.ic - 1]);
         const bool emig = dest != d.rank;
         const unsigned int em = __ballot_sync(peers, emig);
         if (em) {
@@ -1082,7 +1088,9 @@ int pg_advect_impl(pgpu_ctx* c, int tID) {
     c->dev.tally_on = 0;
     if (c->cfg.dump_bound_avg_every > 0 && c->dev.tallies)
         c->dev.tally_on = ((tID - c->cfg.dump_bound_start) % c->cfg.dump_bound_avg_every) == 0;
-    if (c->np == 0) return PGPU_OK;
+    /* (with several ranks an empty rank still goes through the emigrant bookkeeping: every rank must take the same
+     *  branch of the EXCHANGE that follows) */
+    if (c->np == 0 && !(c->cfg.nranks > 1 && c->dev.cell_procs && c->d_xcount && c->d_emig_list)) return PGPU_OK;
     if ((rc = pg_resolve_vel(c))) return rc;
 
     /* zero the per-call counters and the histogram */
@@ -1094,7 +1102,12 @@ int pg_advect_impl(pgpu_ctx* c, int tID) {
     c->emig_valid = false;
     const bool track = c->cfg.nranks > 1 && c->dev.cell_procs && c->d_xcount && c->d_emig_list;
     if (track) {
+        /* room for the immigrants of the EXCHANGE that follows, made BEFORE the emigrant list is recorded (a
+         * re-allocation drops it) */
+        if ((rc = pg_ensure_capacity(c, c->np + pg_exchange_recv_slots(c)))) return rc;
+        pg_refresh_dev(c);
         PG_CUDA(c, cudaMemsetAsync(c->d_xcount, 0, sizeof(unsigned long long) * PG_XROW, c->stream));
+        c->dev.emig_trust = (c->owned_clean && c->cfg.grid_type == PGPU_UNSTRUCTURED && !c->cfg.axi) ? 1 : 0;
         c->dev.emig_list = c->d_emig_list;
         c->dev.emig_cap = c->emig_cap;
         c->dev.xrow = c->d_xcount;

@@ -93,6 +93,7 @@ extern "C" int pgpu_create(pgpu_ctx** out, int device) {
     c->mesh_set = false; c->mesh_dirty = false;
     c->cur = 0; c->np = 0; c->capacity = 0;
     c->has_dtrim = false; c->sorted = false; c->hist_valid = false; c->maybe_tombstones = false;
+    c->np_ub = 0; c->np_dev_valid = false; c->owned_clean = false;
     c->id_counter = 0;
     c->any_internal_dof = false; c->ie_seen = false;
     c->d_tile_first = nullptr; c->tile_alloc = 0; c->n_big = 0;
@@ -134,6 +135,9 @@ extern "C" int pgpu_create(pgpu_ctx** out, int device) {
      * 2.82 to 1.97 ms but the lane-per-cell gather costs the collision kernel 3.5 ms (29 GB of DRAM reads for 4 GB of
      * records: scattered 32-byte reads do not merge the way the scatter's writes do) */
     if (const char* e = getenv("PANTERA_GPU_DEFER_VEL")) c->defer_vel = atoi(e) != 0;
+    c->x_counts_valid = false;
+    c->x_headroom = 1.25;
+    if (const char* e = getenv("PANTERA_GPU_XCHG_HEADROOM")) { double v = atof(e); if (v >= 1.0 && v <= 64.0) c->x_headroom = v; }
     if (const char* e = getenv("PANTERA_GPU_ADVECT_CHUNK")) {
         int v = atoi(e);
         if (v >= 32 && v <= 65536 && (v & (v - 1)) == 0) c->advect_chunk_override = v;
@@ -372,7 +376,13 @@ extern "C" int pgpu_set_mesh(pgpu_ctx* c, int dims, int nn, int nc, const double
             if (cell_procs[i] < 0 || cell_procs[i] >= 64)
                 PG_FAIL(c, PGPU_ERR_INVALID, "set_mesh: CELL_PROCS(%d) = %d outside 0..63", i + 1, cell_procs[i]);
     c->cell_procs_max = 0;
-    if (cell_procs) c->cell_procs_max = *std::max_element(cell_procs, cell_procs + nc);
+    if (cell_procs) {
+        c->cell_procs_max = *std::max_element(cell_procs, cell_procs + nc);
+        c->h_cell_procs.assign(cell_procs, cell_procs + nc);
+    } else {
+        c->h_cell_procs.clear();
+    }
+    c->owned_clean = false;
     if ((rc = put(c, S_CELL_PROCS, (const int*)cell_procs, cell_procs ? (size_t)nc : 0, &d.cell_procs))) return rc;
     d.nboundcells = face_boundary_index ? nboundcells : 0;
     if ((rc = put(c, S_FACE_BIDX, (const int*)face_boundary_index, face_boundary_index ? (size_t)nf * nc : 0, &d.face_bidx))) return rc;
@@ -398,7 +408,13 @@ extern "C" int pgpu_set_cell_procs(pgpu_ctx* c, int nc, const int32_t* cell_proc
             if (cell_procs[i] < 0 || cell_procs[i] >= nr)
                 PG_FAIL(c, PGPU_ERR_INVALID, "set_cell_procs: CELL_PROCS(%d) = %d outside 0..%d", i + 1, cell_procs[i], nr - 1);
         c->cell_procs_max = *std::max_element(cell_procs, cell_procs + nc);
+        c->h_cell_procs.assign(cell_procs, cell_procs + nc);
+    } else {
+        c->h_cell_procs.clear();
     }
+    c->owned_clean = false;
+    c->x_counts_valid = false;
+    c->mesh_dirty = c->mesh_set; /* the hop codes carry the ownership flags */
     return put(c, S_CELL_PROCS, (const int*)cell_procs, (size_t)nc, &c->dev.cell_procs);
 }
 
@@ -526,6 +542,7 @@ static int build_packed_mesh(pgpu_ctx* c) {
                 }
             }
             if (!fluidboundary) {
+                if (nb > PG_CODE_CELL_MASK) PG_FAIL(c, PGPU_ERR_UNSUPPORTED, "mesh: more than %d cells", PG_CODE_CELL_MASK);
                 code[f] = nb;
             } else {
                 int pg = c->h_cell_faces_pg[f];
@@ -539,10 +556,12 @@ static int build_packed_mesh(pgpu_ctx* c) {
     }
     /* the codes ride in the cell records (no dependent load in the face walk); plain specular walls are marked so
      * that the LEAN pass can reflect in line instead of deferring the particle (PG_CODE_SPEC) */
+    const bool owner_flags = c->cfg.nranks > 1 && !c->h_cell_procs.empty();
     auto packed_codes = [&](int ic, int* rec) {
         rec[0] = rec[1] = rec[2] = rec[3] = 0;
         for (int j = 0; j < nf; j++) {
             int cd = code[(size_t)ic * nf + j];
+            if (cd > 0 && owner_flags && c->h_cell_procs[cd - 1] != c->cfg.rank) cd |= PG_CODE_FOREIGN;
             if (cd < 0) {
                 int gi = -cd - 1;
                 if (c->h_bc_particle[gi] == PGPU_SPECULAR && !c->h_bc_react[gi] && c->h_bc_field[gi] != PGPU_DIELECTRIC_BC)
@@ -689,8 +708,20 @@ int pg_prepare(pgpu_ctx* c) {
     return PGPU_OK;
 }
 
+__global__ void status_init_kernel(PgStatus* st, unsigned long long np) {
+    if (threadIdx.x == 0) st->np_cur = np;
+}
+
+int pg_set_np_cur(pgpu_ctx* c) {
+    status_init_kernel<<<1, 32, 0, c->stream>>>(c->d_status, (unsigned long long)c->np);
+    return PGPU_OK;
+}
+
 int pg_reset_status(pgpu_ctx* c) {
     PG_CUDA(c, cudaMemsetAsync(c->d_status, 0, sizeof(PgStatus), c->stream));
+    status_init_kernel<<<1, 32, 0, c->stream>>>(c->d_status, (unsigned long long)c->np);
+    c->np_ub = c->np;
+    c->np_dev_valid = false;
     return PGPU_OK;
 }
 
@@ -699,6 +730,7 @@ static const char* deverr_text(int e) {
         case PG_DEVERR_HOPS: return "a particle exceeded the hop limit (malformed mesh or NaN state)";
         case PG_DEVERR_CELL_RANGE: return "a particle ended outside the grid (cell index out of range)";
         case PG_DEVERR_CAPACITY: return "particle capacity exhausted while creating particles (raise pgpu_config.capacity)";
+        case PG_DEVERR_XCAP: return "EXCHANGE: more emigrants than the message sized from the previous step holds (PANTERA_GPU_XCHG_HEADROOM)";
         default: return "unknown device error";
     }
 }
@@ -707,6 +739,21 @@ int pg_finish(pgpu_ctx* c, const char* what) {
     PG_CUDA(c, cudaMemcpyAsync(c->h_status, c->d_status, sizeof(PgStatus), cudaMemcpyDeviceToHost, c->stream));
     PG_CUDA(c, cudaStreamSynchronize(c->stream));
     PG_CUDA(c, cudaGetLastError());
+    if (c->np_dev_valid) { /* the count moved on the device (EXCHANGE immigrants, compaction by the sort) */
+        c->np = (long long)c->h_status->np_cur;
+        c->n_big = c->h_status->n_big;
+        c->np_dev_valid = false;
+        if (c->h_status->flag_ie) c->ie_seen = true;
+    }
+    if (c->x_plan_pending) { /* EXCHANGE fast path: this step's counts size the next step's messages */
+        const int nr = c->cfg.nranks;
+        for (int r = 0; r < nr && r < 64; r++) {
+            c->x_prev_send[r] = (long long)c->h_status->x_sent[r];
+            c->x_prev_recv[r] = (long long)c->h_status->x_recv[r];
+        }
+        c->x_plan_pending = false;
+        if (c->h_status->err == PG_DEVERR_XCAP) c->x_counts_valid = false; /* (the error is reported below) */
+    }
     if (c->h_status->n_appended) {
         c->np += (long long)c->h_status->n_appended;
         c->id_counter += (long long)c->h_status->n_appended;
@@ -896,6 +943,7 @@ static int append_impl(pgpu_ctx* c, const void* aos, int64_t n, int32_t stride, 
     c->np += n;
     c->sorted = false;
     c->hist_valid = false;
+    c->owned_clean = false; /* host-supplied particles may sit in cells of other ranks until the next EXCHANGE */
     if ((rc = pg_finish(c, what))) {
         c->np = np_old;
         return rc;
@@ -988,7 +1036,9 @@ extern "C" int pgpu_download_particles(pgpu_ctx* c, void* aos, int64_t capacity,
  * 256-bit loads and stores (every random write is a full HBM sector).  Tombstones drop out here.
  * The pass that follows the scan also cuts the sorted store into collision tiles (pgpu_collide.cu).
  * ---------------------------------------------------------------------------------------- */
-__global__ void __launch_bounds__(256) hist_kernel(const PgPos* __restrict__ pos, long long n, unsigned int* __restrict__ cell_count) {
+__global__ void __launch_bounds__(256) hist_kernel(const PgPos* __restrict__ pos, const PgStatus* __restrict__ st,
+                                                   unsigned int* __restrict__ cell_count) {
+    const long long n = (long long)st->np_cur;
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     int c = (i < n) ? pos[i].ic : 0;
     unsigned int live = __ballot_sync(0xffffffffu, c >= 1);
@@ -1002,10 +1052,11 @@ __global__ void __launch_bounds__(256) hist_kernel(const PgPos* __restrict__ pos
  * go to a handful of cells).  The kernel is HBM-bound with most of the issue slots idle, so the atomic's round trip
  * costs nothing here -- it used to sit in the ADVECT epilogue, together with a 4-byte rank per particle written there
  * and read back here. */
-__global__ void __launch_bounds__(256) scatter_kernel(PgPlanes src, PgPlanes dst, long long n,
+__global__ void __launch_bounds__(256) scatter_kernel(PgPlanes src, PgPlanes dst, const PgStatus* __restrict__ st,
                                                       const unsigned int* __restrict__ cell_off,
                                                       unsigned int* __restrict__ cursor, int use_ie,
                                                       unsigned int* __restrict__ src_of) {
+    const long long n = (long long)st->np_cur; /* (the grid covers the host's upper bound of it) */
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     /* The source records are read exactly once: streaming (evict-first) loads keep them from displacing the
      * destination lines that L2 is still assembling from the scattered 32-byte stores (measured: -19 % at
@@ -1038,19 +1089,18 @@ __global__ void __launch_bounds__(256) scatter_kernel(PgPlanes src, PgPlanes dst
     if (src.id) dst.id[o] = src.id[i];
 }
 
-/* first cell of every tile window + the list of cells too large for a tile */
-__global__ void __launch_bounds__(256) tile_index_kernel(const unsigned int* __restrict__ cell_off, int ncells,
-                                                         unsigned int* __restrict__ tile_first, int ntiles_max,
-                                                         unsigned int* __restrict__ big_list, PgStatus* st) {
+/* after the scan: the list of cells too large for one lane of the collision kernel (GLOBAL path), and the new particle
+ * count -- the total of the histogram, tombstones left out -- which stays on the device until the call's final read-back */
+__global__ void __launch_bounds__(256) cell_tail_kernel(const unsigned int* __restrict__ cell_off, int ncells,
+                                                        unsigned int* __restrict__ big_list, long long big_cap, PgStatus* st) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= ncells) return;
     unsigned int o = cell_off[c], o1 = cell_off[c + 1];
-    int t0 = (int)(o / PG_TILE_S);
-    int tprev = (c == 0) ? -1 : (int)(cell_off[c - 1] / PG_TILE_S);
-    for (int t = tprev + 1; t <= t0 && t <= ntiles_max; t++) tile_first[t] = (unsigned int)c;
-    if (c == ncells - 1)
-        for (int t = t0 + 1; t <= ntiles_max; t++) tile_first[t] = (unsigned int)ncells;
-    if (o1 - o > PG_TILE_BIG) big_list[atomicAdd(&st->n_big, 1u)] = (unsigned int)c;
+    if (o1 - o > PG_TILE_BIG) {
+        unsigned int k = atomicAdd(&st->n_big, 1u);
+        if ((long long)k < big_cap) big_list[k] = (unsigned int)c;
+    }
+    if (c == ncells - 1) st->np_cur = (unsigned long long)o1;
 }
 
 /* The collision kernel gives one lane to a cell, and a warp idles behind the lane with the most candidates.  The
@@ -1128,12 +1178,12 @@ int pg_resolve_vel(pgpu_ctx* c) {
     return PGPU_OK;
 }
 
-int pg_sort_impl(pgpu_ctx* c, bool defer_vel) {
+int pg_sort_impl(pgpu_ctx* c, bool defer_vel, bool sync_np) {
     int ncells = pg_ncells(c);
     { int rc0; if ((rc0 = pg_resolve_vel(c))) return rc0; }
     c->n_big = 0;
     c->dev.ntiles = 0;
-    if (c->np == 0) {
+    if (c->np_ub == 0) {
         PG_CUDA(c, cudaMemsetAsync(c->d_cell_off, 0, sizeof(unsigned int) * ((size_t)ncells + 1), c->stream));
         c->sorted = true;
         c->maybe_tombstones = false;
@@ -1141,14 +1191,16 @@ int pg_sort_impl(pgpu_ctx* c, bool defer_vel) {
     }
     PgPlanes src = c->planes[c->cur], dst = c->planes[c->cur ^ 1];
     if (!c->has_dtrim) src.dtrim = nullptr;
-    unsigned int blocks = (unsigned int)((c->np + 255) / 256);
+    /* the particle count may have moved on the device since the call began (immigrants): the grids cover the host's
+     * upper bound and the kernels read the count itself from the status block */
+    unsigned int blocks = (unsigned int)((c->np_ub + 255) / 256);
     if (c->emig_valid) { /* ADVECT left the emigrants out of its histogram and no EXCHANGE has shipped them: recount */
         c->hist_valid = false;
         c->emig_valid = false;
     }
     if (!c->hist_valid) {
         PG_CUDA(c, cudaMemsetAsync(c->d_cell_count, 0, sizeof(unsigned int) * ((size_t)ncells + 1), c->stream));
-        hist_kernel<<<blocks, 256, 0, c->stream>>>(src.pos, c->np, c->d_cell_count);
+        hist_kernel<<<blocks, 256, 0, c->stream>>>(src.pos, c->d_status, c->d_cell_count);
         c->launches++;
     }
     size_t tmp = c->scan_tmp_bytes;
@@ -1156,35 +1208,36 @@ int pg_sort_impl(pgpu_ctx* c, bool defer_vel) {
     c->launches++;
     /* the histogram has been scanned into cell_off: its array now serves as the per-cell cursor of the scatter */
     PG_CUDA(c, cudaMemsetAsync(c->d_cell_count, 0, sizeof(unsigned int) * ((size_t)ncells + 1), c->stream));
-    scatter_kernel<<<blocks, 256, 0, c->stream>>>(src, dst, c->np, c->d_cell_off, c->d_cell_count, c->dev.use_ie,
+    scatter_kernel<<<blocks, 256, 0, c->stream>>>(src, dst, c->d_status, c->d_cell_off, c->d_cell_count, c->dev.use_ie,
                                                   defer_vel ? c->d_src_of : nullptr);
-    c->launches++;
-    int ntiles_max = (int)((c->np + PG_TILE_S - 1) / PG_TILE_S);
-    PG_CUDA(c, cudaMemsetAsync(&c->d_status->n_big, 0, sizeof(unsigned int), c->stream));
-    tile_index_kernel<<<(unsigned int)((ncells + 255) / 256), 256, 0, c->stream>>>(c->d_cell_off, ncells, c->d_tile_first,
-                                                                                  ntiles_max, c->d_big_list, c->d_status);
     c->launches++;
     {
         unsigned int cb = (unsigned int)((ncells + 255) / 256);
+        cell_tail_kernel<<<cb, 256, 0, c->stream>>>(c->d_cell_off, ncells, c->d_big_list, c->big_alloc, c->d_status);
         PG_CUDA(c, cudaMemsetAsync(c->d_cell_bucket, 0, sizeof(unsigned int) * 2 * PG_NBUCKET, c->stream));
         cell_bucket_count_kernel<<<cb, 256, 0, c->stream>>>(c->d_cell_off, ncells, c->d_cell_bucket);
         cell_bucket_scan_kernel<<<1, 288, 0, c->stream>>>(c->d_cell_bucket);
         cell_bucket_fill_kernel<<<cb, 256, 0, c->stream>>>(c->d_cell_off, ncells, c->d_cell_bucket, c->d_cell_order);
-        c->launches += 3;
+        c->launches += 4;
     }
     PG_CUDA(c, cudaGetLastError());
-    /* new particle count = total of the histogram; number of oversized cells */
-    unsigned int* h = c->h_status->scratch;
-    PG_CUDA(c, cudaMemcpyAsync(&h[0], c->d_cell_off + ncells, sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
-    PG_CUDA(c, cudaMemcpyAsync(&h[1], &c->d_status->n_big, sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
-    PG_CUDA(c, cudaStreamSynchronize(c->stream));
-    c->np = (long long)h[0];
-    c->n_big = h[1];
     c->cur ^= 1;
     c->sorted = true;
     c->hist_valid = false;
     c->maybe_tombstones = false;
     c->vel_deferred = defer_vel;
+    c->np_dev_valid = true; /* the new count (total of the histogram) is in status->np_cur; np_ub still bounds it */
+    if (sync_np) {
+        /* callers that need the count on the host right away (everything but the per-step loop) */
+        unsigned int* h = c->h_status->scratch;
+        unsigned long long* hn = reinterpret_cast<unsigned long long*>(&c->h_status->scratch[2]);
+        PG_CUDA(c, cudaMemcpyAsync(hn, &c->d_status->np_cur, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+        PG_CUDA(c, cudaMemcpyAsync(&h[1], &c->d_status->n_big, sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
+        PG_CUDA(c, cudaStreamSynchronize(c->stream));
+        c->np = (long long)*hn;
+        c->np_ub = c->np;
+        c->n_big = h[1];
+    }
     pg_refresh_dev(c);
     return PGPU_OK;
 }
@@ -1313,11 +1366,15 @@ extern "C" int pgpu_run_steps(pgpu_ctx* c, int32_t tID0, int32_t nsteps, int64_t
         bool dsmc = c->cfg.collision_type == PGPU_DSMC;
         bool mcc = c->cfg.collision_type == PGPU_MCC_VAHEDI;
         bool mccv = c->cfg.collision_type == PGPU_MCC;
+        /* The whole step is queued without a host round trip: the particle count lives in the status block while the
+         * step runs (immigrants, compaction), and ONE read-back at the end brings it, the counters and any device
+         * error to the host.  Oversized cells (GLOBAL collision path, host-driven dependency rounds) are only known
+         * then; they are rare (the one-cell heat bath), and run after the read-back. */
         tic(c, 1);
-        if ((rc = pg_sort_impl(c, dsmc && c->defer_vel))) return rc; /* deferred: the collision kernel finishes the vel reorder */
+        if ((rc = pg_sort_impl(c, dsmc && c->defer_vel, false))) return rc;
         toc(c, 1);
         tic(c, 2);
-        if (dsmc && (rc = pg_collide_impl(c, tID))) return rc;
+        if (dsmc && (rc = pg_collide_impl(c, tID, false))) return rc;
         if (mcc && (rc = pg_mcc_impl(c, tID))) return rc;
         if (mccv && (rc = pg_mcc_vss_impl(c, tID))) return rc;
         toc(c, 2);
@@ -1325,6 +1382,14 @@ extern "C" int pgpu_run_steps(pgpu_ctx* c, int32_t tID0, int32_t nsteps, int64_t
         collect(c, 0); collect(c, 1); collect(c, 2);
         if (c->cfg.nranks > 1) collect(c, 4);
         if (rc) return rc;
+        if (dsmc && (c->n_big > 0 || c->vel_deferred)) {
+            tic(c, 2);
+            if ((rc = pg_collide_big(c))) return rc;
+            toc(c, 2);
+            rc = pg_finish(c, "pgpu_run_steps");
+            collect(c, 2);
+            if (rc) return rc;
+        }
         tc += (int64_t)c->h_status->ncoll;
         tr += (int64_t)c->h_status->nreac;
         pg_refresh_dev(c);

@@ -453,7 +453,7 @@ __global__ void __launch_bounds__(128, IE ? PG_CELL_MINBLOCKS_IE : PG_CELL_MINBL
  * ======================================================================================== */
 __global__ void __launch_bounds__(128) mcc_vss_kernel(const __grid_constant__ PgDev d) {
     long long jp1 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (jp1 >= d.np) return;
+    if (jp1 >= (long long)d.status->np_cur) return; /* the particles present at entry (ref: :1646-1647) */
     const PgPos P1 = d.p.pos[jp1];
     const int ic = P1.ic;
     if (ic < 1) return;
@@ -759,10 +759,22 @@ static int collide_big_cells(pgpu_ctx* c) {
 }
 
 /* DSMC_COLLISIONS on the sorted store; leaves TIMESTEP_COLL/REAC in the status block */
-int pg_collide_impl(pgpu_ctx* c, int tID) {
+int pg_collide_big(pgpu_ctx* c) {
     int rc;
+    pg_refresh_dev(c);
+    if (c->n_big > 0 && (rc = collide_big_cells(c))) return rc;
+    if (c->vel_deferred) { /* every cell has been swept: the sorted vel plane is complete */
+        c->vel_deferred = false;
+        pg_refresh_dev(c);
+    }
+    return PGPU_OK;
+}
+
+/* big_now: the number of oversized cells is known on the host (the sort synchronised); otherwise the caller runs
+ * pg_collide_big after the step's read-back */
+int pg_collide_impl(pgpu_ctx* c, int tID, bool big_now) {
     if (!c->sorted) PG_FAIL(c, PGPU_ERR_STATE, "collide: store is not sorted");
-    if (c->np < 2) return pg_resolve_vel(c);
+    if (c->np_ub < 2) return pg_resolve_vel(c);
     c->dev.tID = tID;
     pg_refresh_dev(c);
     const PgDev& d = c->dev;
@@ -780,12 +792,8 @@ int pg_collide_impl(pgpu_ctx* c, int tID) {
         c->launches++;
         PG_CUDA(c, cudaGetLastError());
     }
-    if (c->n_big > 0 && (rc = collide_big_cells(c))) return rc;
-    if (c->vel_deferred) { /* every cell has been swept: the sorted vel plane is complete */
-        c->vel_deferred = false;
-        pg_refresh_dev(c);
-    }
     c->hist_valid = false;
+    if (big_now) return pg_collide_big(c);
     return PGPU_OK;
 }
 
@@ -796,11 +804,11 @@ int pg_mcc_vss_impl(pgpu_ctx* c, int tID) {
     if (c->dev.mcc_cell_nrho && c->mcc_cell_nrho_cells < (int64_t)pg_ncells(c))
         PG_FAIL(c, PGPU_ERR_STATE, "mcc_collisions: background density table covers %lld of %d cells",
                 (long long)c->mcc_cell_nrho_cells, pg_ncells(c));
-    if (c->np == 0) return PGPU_OK;
+    if (c->np_ub == 0) return PGPU_OK;
     { int rc0; if ((rc0 = pg_resolve_vel(c))) return rc0; }
     c->dev.tID = tID;
     pg_refresh_dev(c);
-    mcc_vss_kernel<<<(unsigned int)((c->np + 127) / 128), 128, 0, c->stream>>>(c->dev);
+    mcc_vss_kernel<<<(unsigned int)((c->np_ub + 127) / 128), 128, 0, c->stream>>>(c->dev);
     c->launches++;
     PG_CUDA(c, cudaGetLastError());
     c->sorted = false;

@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(256) xcount_kernel(const __grid_constant__ PgD
     if (threadIdx.x < 64) s[threadIdx.x] = 0;
     __syncthreads();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < d.np) {
+    if (i < (long long)d.status->np_cur) {
         int ic = d.p.pos[i].ic;
         if (ic >= 1) {
             int dest = __ldg(&d.cell_procs[ic - 1]);
@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(256) xpack_kernel(const __grid_constant__ PgDe
                                                     const unsigned long long* __restrict__ xoff,
                                                     unsigned long long* __restrict__ xcursor) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= d.np) return;
+    if (i >= (long long)d.status->np_cur) return;
     const PgPos P = d.p.pos[i];
     int ic = P.ic;
     if (ic < 1) return;
@@ -189,6 +189,127 @@ __global__ void __launch_bounds__(256) xrec_to_aos_kernel(const double* __restri
     if (!keep_id) id = (long long)rank + ((id_base + i) << 8);
     *reinterpret_cast<long long*>(aos + (size_t)i * 96 + 80) = id;
     *reinterpret_cast<long long*>(aos + (size_t)i * 96 + 88) = 0;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * EXCHANGE without host round trips (the per-step path).  Every pair of ranks exchanges ONE fixed-capacity message per
+ * step: record 0 is a header holding the number of particle records that follow, the capacity comes from the counts of
+ * the previous step (known to both ends: what one sent is what the other received), so neither the counts nor the
+ * sizes have to visit the host before ncclSend/ncclRecv can be queued.  ("fixed-capacity per-neighbour
+ * send slots with the count in the header".)
+ * ---------------------------------------------------------------------------------------- */
+struct XPlan {
+    unsigned int off[64]; /* first record (the header) of the message for / from rank r, in records */
+    unsigned int cap[64]; /* particle records the message holds                                       */
+    int nr, rank;
+};
+
+/* emigrant list -> messages; grid-stride over the list, whose length lives on the device */
+__global__ void __launch_bounds__(256) xpack_fast_kernel(const __grid_constant__ PgDev d, const unsigned int* __restrict__ list,
+                                                         const unsigned long long* __restrict__ xrow, double* __restrict__ sendbuf,
+                                                         const __grid_constant__ XPlan plan, unsigned long long* __restrict__ xcursor) {
+    unsigned long long n = xrow[PG_XROW_LEN];
+    if (n > (unsigned long long)d.emig_cap) n = (unsigned long long)d.emig_cap;
+    for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (unsigned long long)gridDim.x * blockDim.x) {
+        const long long i = (long long)list[t];
+        const PgPos P = d.p.pos[i];
+        const int ic = P.ic;
+        const int dest = __ldg(&d.cell_procs[ic - 1]);
+        const unsigned long long k = atomicAdd(&xcursor[dest], 1ULL);
+        d.p.pos[i].ic = PG_TOMBSTONE;
+        if (k >= (unsigned long long)plan.cap[dest]) { /* does not fit: the step fails loudly at its read-back */
+            atomicAdd(&d.status->x_overflow, 1ULL);
+            pg_set_err(d, PG_DEVERR_XCAP);
+            continue;
+        }
+        double* r = sendbuf + ((size_t)plan.off[dest] + 1 + k) * XREC_DOUBLES;
+        const PgVel V = d.p.vel[i];
+        const PgIe E = d.p.ie[i];
+        r[0] = P.x; r[1] = P.y; r[2] = P.z;
+        r[3] = V.vx; r[4] = V.vy; r[5] = V.vz;
+        r[6] = E.erot; r[7] = E.evib;
+        r[8] = d.p.dtrim ? d.p.dtrim[i] : d.dt;
+        int2 cs = make_int2(ic, P.sid);
+        r[9] = *reinterpret_cast<double*>(&cs);
+        long long id = d.p.id ? d.p.id[i] : 0;
+        r[10] = *reinterpret_cast<double*>(&id);
+    }
+}
+
+/* headers of the outgoing messages; also the per-destination counts for the host's next plan */
+__global__ void xheader_kernel(const __grid_constant__ PgDev d, const unsigned long long* __restrict__ xrow, double* __restrict__ sendbuf,
+                               const __grid_constant__ XPlan plan) {
+    const int r = threadIdx.x;
+    if (r == 0 && xrow[PG_XROW_OVF]) { /* the emigrant list itself overflowed: particles would be lost */
+        atomicAdd(&d.status->x_overflow, xrow[PG_XROW_OVF]);
+        pg_set_err(d, PG_DEVERR_XCAP);
+    }
+    if (r >= plan.nr) return;
+    unsigned long long n = (r == plan.rank) ? 0ULL : xrow[r];
+    d.status->x_sent[r] = n;
+    if (r == plan.rank) return;
+    if (n > plan.cap[r]) n = plan.cap[r];
+    unsigned long long* h = reinterpret_cast<unsigned long long*>(sendbuf + (size_t)plan.off[r] * XREC_DOUBLES);
+    h[0] = n;
+}
+
+/* incoming messages -> append region; grid (capacity blocks, source rank).  The immigrants join the histogram of the
+ * ADVECT epilogue, so the counting sort that follows needs no recount. */
+__global__ void __launch_bounds__(256) xunpack_fast_kernel(const __grid_constant__ PgDev d, const double* __restrict__ recvbuf,
+                                                           const __grid_constant__ XPlan plan, PgPlanes p) {
+    const int src = blockIdx.y;
+    if (src == plan.rank) return;
+    const unsigned long long* hdr = reinterpret_cast<const unsigned long long*>(recvbuf + (size_t)plan.off[src] * XREC_DOUBLES);
+    unsigned long long n = hdr[0];
+    if (n > plan.cap[src]) n = plan.cap[src];
+    unsigned long long base = d.status->np_cur;
+    for (int q = 0; q < src; q++) {
+        if (q == plan.rank) continue;
+        unsigned long long m = *reinterpret_cast<const unsigned long long*>(recvbuf + (size_t)plan.off[q] * XREC_DOUBLES);
+        base += (m > plan.cap[q]) ? plan.cap[q] : m;
+    }
+    for (unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (unsigned long long)gridDim.x * blockDim.x) {
+        const double* r = recvbuf + ((size_t)plan.off[src] + 1 + k) * XREC_DOUBLES;
+        const long long o = (long long)(base + k);
+        if (o >= d.capacity) { pg_set_err(d, PG_DEVERR_CAPACITY); continue; }
+        double t = r[9];
+        int2 cs = *reinterpret_cast<int2*>(&t);
+        PgPos P;
+        P.x = r[0]; P.y = r[1]; P.z = r[2]; P.ic = cs.x; P.sid = cs.y;
+        PgVel V;
+        V.vx = r[3]; V.vy = r[4]; V.vz = r[5]; V.sid = cs.y; V.pad = 0;
+        PgIe E;
+        E.erot = r[6]; E.evib = r[7];
+        p.pos[o] = P;
+        p.vel[o] = V;
+        p.ie[o] = E;
+        if (E.erot != 0. || E.evib != 0.) d.status->flag_ie = 1;
+        if (p.dtrim) p.dtrim[o] = r[8];
+        t = r[10];
+        if (p.id) p.id[o] = *reinterpret_cast<long long*>(&t);
+        atomicAdd(&d.cell_count[cs.x - 1], 1u);
+    }
+}
+
+/* after the unpack: the particle count moves on the device; per-source counts for the host's next plan */
+__global__ void xfinish_kernel(const __grid_constant__ PgDev d, const double* __restrict__ recvbuf, const __grid_constant__ XPlan plan) {
+    if (threadIdx.x != 0) return;
+    unsigned long long tot = 0;
+    for (int q = 0; q < plan.nr; q++) {
+        unsigned long long m = 0;
+        if (q != plan.rank) {
+            m = *reinterpret_cast<const unsigned long long*>(recvbuf + (size_t)plan.off[q] * XREC_DOUBLES);
+            d.status->x_recv[q] = m; /* (the uncapped count: the next plan must grow with it) */
+            if (m > plan.cap[q]) m = plan.cap[q];
+        } else {
+            d.status->x_recv[q] = 0;
+        }
+        tot += m;
+    }
+    d.status->n_immigrants = tot;
+    unsigned long long np = d.status->np_cur + tot;
+    if (np > (unsigned long long)d.capacity) { pg_set_err(d, PG_DEVERR_CAPACITY); np = (unsigned long long)d.capacity; }
+    d.status->np_cur = np;
 }
 
 __global__ void fill_kernel(double* p, long long n, double v) {
@@ -313,7 +434,65 @@ int pg_exchange_impl(pgpu_ctx* c) {
     /* fast path: ADVECT has just recorded the emigrants (list + counts) and the histogram of the survivors is
      * valid; nothing has touched the store since.  Every rank takes the same branch (same call sequence). */
     bool fast = c->emig_valid && c->hist_valid;
+    if (fast && c->x_counts_valid && !c->has_dtrim) {
+        /* ---- the per-step path: no host round trip (see the XPlan kernels above) ---- */
+        c->emig_valid = false;
+        XPlan sp, rp;
+        memset(&sp, 0, sizeof(sp));
+        memset(&rp, 0, sizeof(rp));
+        sp.nr = rp.nr = nr;
+        sp.rank = rp.rank = c->cfg.rank;
+        unsigned long long so = 0, ro = 0;
+        for (int r = 0; r < nr; r++) {
+            if (r == c->cfg.rank) continue;
+            sp.off[r] = (unsigned int)so;
+            rp.off[r] = (unsigned int)ro;
+            sp.cap[r] = (unsigned int)std::min<double>(4.0e9, c->x_headroom * (double)c->x_prev_send[r] + 8192.0);
+            rp.cap[r] = (unsigned int)std::min<double>(4.0e9, c->x_headroom * (double)c->x_prev_recv[r] + 8192.0);
+            so += (unsigned long long)sp.cap[r] + 1;
+            ro += (unsigned long long)rp.cap[r] + 1;
+        }
+        if ((rc = ensure_xbuf(c, (long long)std::max(so, ro)))) return rc;
+        /* (pg_advect_impl has made room for the immigrants before it recorded the emigrant list: a re-allocation
+         *  here would drop that list) */
+        if (c->np_ub + (long long)ro > c->capacity)
+            PG_FAIL(c, PGPU_ERR_STATE, "exchange: %lld slots in use + %llu message slots exceed the capacity %lld (raise pgpu_config.capacity)",
+                    c->np_ub, ro, c->capacity);
+        pg_refresh_dev(c);
+        c->dev.emig_list = c->d_emig_list; /* (emig_cap is read by the pack kernel) */
+        PG_CUDA(c, cudaMemsetAsync(xcursor, 0, sizeof(unsigned long long) * PG_XROW, c->stream));
+        xpack_fast_kernel<<<148 * 8, 256, 0, c->stream>>>(c->dev, c->d_emig_list, xcount, (double*)c->d_sendbuf, sp, xcursor);
+        xheader_kernel<<<1, 64, 0, c->stream>>>(c->dev, xcount, (double*)c->d_sendbuf, sp);
+        c->dev.emig_list = nullptr;
+        PG_NCCL(c, g_nccl.GroupStart());
+        for (int r = 0; r < nr; r++) {
+            if (r == c->cfg.rank) continue;
+            PG_NCCL(c, g_nccl.Send((const double*)c->d_sendbuf + (size_t)sp.off[r] * XREC_DOUBLES, ((size_t)sp.cap[r] + 1) * XREC_DOUBLES,
+                                   ncclDouble, r, comm, c->stream));
+            PG_NCCL(c, g_nccl.Recv((double*)c->d_recvbuf + (size_t)rp.off[r] * XREC_DOUBLES, ((size_t)rp.cap[r] + 1) * XREC_DOUBLES,
+                                   ncclDouble, r, comm, c->stream));
+        }
+        PG_NCCL(c, g_nccl.GroupEnd());
+        unsigned int maxcap = 1;
+        for (int r = 0; r < nr; r++) maxcap = std::max(maxcap, rp.cap[r]);
+        PgPlanes p = c->planes[c->cur];
+        p.dtrim = nullptr; /* every particle has DTRIM == DT right after ADVECT */
+        dim3 grid(std::min<unsigned int>((maxcap + 255) / 256, 148u * 4u), (unsigned int)nr);
+        xunpack_fast_kernel<<<grid, 256, 0, c->stream>>>(c->dev, (const double*)c->d_recvbuf, rp, p);
+        xfinish_kernel<<<1, 32, 0, c->stream>>>(c->dev, (const double*)c->d_recvbuf, rp);
+        c->launches += 4;
+        c->np_ub += (long long)ro;
+        c->np_dev_valid = true;
+        c->x_plan_pending = true; /* pg_finish turns status->x_sent / x_recv into the next plan */
+        c->maybe_tombstones = true;
+        c->sorted = false;
+        c->owned_clean = true;
+        c->id_counter = std::max(c->id_counter, c->np_ub);
+        PG_CUDA(c, cudaGetLastError());
+        return PGPU_OK;
+    }
     c->emig_valid = false;
+    c->x_counts_valid = false;
     std::vector<unsigned long long> h((size_t)nr * PG_XROW);
     for (int attempt = 0; attempt < 2; attempt++) {
         PG_CUDA(c, cudaMemsetAsync(xoff, 0, sizeof(unsigned long long) * 2 * PG_XROW, c->stream));
@@ -340,6 +519,12 @@ int pg_exchange_impl(pgpu_ctx* c) {
         soff[r + 1] = soff[r] + h[(size_t)c->cfg.rank * PG_XROW + r];
         roff[r + 1] = roff[r] + h[(size_t)r * PG_XROW + c->cfg.rank];
     }
+    for (int r = 0; r < nr; r++) { /* the counts that size the next step's fixed-capacity messages */
+        c->x_prev_send[r] = (long long)h[(size_t)c->cfg.rank * PG_XROW + r];
+        c->x_prev_recv[r] = (long long)h[(size_t)r * PG_XROW + c->cfg.rank];
+    }
+    c->x_counts_valid = true;
+    c->owned_clean = true;
     long long nsend = (long long)soff[nr], nrecv = (long long)roff[nr];
     long long need = std::max(nsend, nrecv);
     if ((rc = ensure_xbuf(c, need))) return rc;
@@ -383,7 +568,18 @@ int pg_exchange_impl(pgpu_ctx* c) {
         c->id_counter = std::max(c->id_counter, c->np);
     }
     c->sorted = false;
+    c->np_ub = c->np;
+    pg_set_np_cur(c); /* the count changed on the host: bring the device's copy along */
     pg_refresh_dev(c);
     PG_CUDA(c, cudaGetLastError());
     return PGPU_OK;
+}
+
+/* slots the next fast EXCHANGE may append (sum of the receive capacities); 0 when the slow path will run */
+long long pg_exchange_recv_slots(const pgpu_ctx* c) {
+    if (c->cfg.nranks <= 1 || !c->x_counts_valid) return 0;
+    double ro = 0;
+    for (int r = 0; r < c->cfg.nranks; r++)
+        if (r != c->cfg.rank) ro += std::min<double>(4.0e9, c->x_headroom * (double)c->x_prev_recv[r] + 8192.0) + 1.0;
+    return (long long)ro;
 }

@@ -74,6 +74,10 @@
  * -pg boundary with physical group pg; -pg - PG_CODE_SPEC when that group is a plain specular wall (no wall
  * reactions, no dielectric charging), which the LEAN advect pass reflects in line */
 #define PG_CODE_SPEC 0x40000000
+/* a neighbour code (> 0) carries the cell id in its low 29 bits and this flag when the neighbour belongs to another
+ * rank: ownership is then tracked along the face walk for free and only emigrants look up CELL_PROCS */
+#define PG_CODE_FOREIGN 0x20000000
+#define PG_CODE_CELL_MASK 0x1FFFFFFF
 #define PG_MAX_HOPS 1000000 /* guard against a malformed mesh hanging the GPU */
 
 /* status block, device resident, read back at the end of every hot-path call */
@@ -84,15 +88,20 @@ struct PgStatus {
     unsigned long long ncoll;       /* TIMESTEP_COLL                                     */
     unsigned long long nreac;       /* TIMESTEP_REAC                                     */
     unsigned long long pending;     /* collision candidates still waiting                */
-    unsigned long long n_emigrants; /* (unused, kept for layout)                          */
-    unsigned long long x_overflow;  /* (unused, kept for layout)                          */
+    unsigned long long np_cur;      /* slots in use [0, np_cur): set to the host's count when a call starts, then kept
+                                       on the device (immigrants appended by EXCHANGE, the compaction of the sort), so
+                                       that a whole timestep needs ONE host synchronisation, at its end            */
+    unsigned long long n_immigrants; /* particles received by the last EXCHANGE                                     */
+    unsigned long long x_overflow;  /* emigrants that did not fit the fixed-capacity message of their destination  */
     int err;                        /* first device-side error code (0 = none)           */
     int flag_dtrim;                 /* some uploaded/received particle has DTRIM != DT   */
     int flag_ie;                    /* some uploaded/received particle has EROT/EVIB != 0 */
     unsigned int n_big;             /* cells with more particles than a collision tile holds */
     unsigned int scratch[4];        /* host landing zone of small read-backs (pinned copy only) */
+    unsigned long long x_sent[64];  /* EXCHANGE fast path: emigrants per destination ...                            */
+    unsigned long long x_recv[64];  /* ... and immigrants per source (they size the next step's messages)          */
 };
-enum { PG_DEVERR_NONE = 0, PG_DEVERR_HOPS = 1, PG_DEVERR_CELL_RANGE = 2, PG_DEVERR_CAPACITY = 3 };
+enum { PG_DEVERR_NONE = 0, PG_DEVERR_HOPS = 1, PG_DEVERR_CELL_RANGE = 2, PG_DEVERR_CAPACITY = 3, PG_DEVERR_XCAP = 4 };
 
 struct __align__(32) PgPos { double x, y, z; int ic, sid; };
 struct __align__(32) PgVel { double vx, vy, vz; int sid, pad; };
@@ -244,7 +253,7 @@ struct PgDev {
     PgStatus* status;
     /* --- particle store --- */
     PgPlanes p;
-    long long np;       /* slots in use [0,np) (may contain tombstones) */
+    long long np;       /* host's view of the slots in use (an upper bound inside a call: kernels read status->np_cur) */
     long long capacity; /* slots allocated */
     int ncells;         /* nc (unstructured) or nx*ny */
     unsigned int* cell_count; /* [ncells] histogram of IC filled by the ADVECT epilogue */
@@ -263,6 +272,7 @@ struct PgDev {
     /* emigrant bookkeeping in the ADVECT epilogue (nranks > 1): a particle whose final cell belongs to another
      * rank is not histogrammed; its slot goes to emig_list and its destination is counted in xrow, so that
      * EXCHANGE touches the emigrants only (pgpu_exchange.cu).  Null when not tracking. */
+    int emig_trust;                 /* 1: ownership flags of the hop codes are authoritative (owned_clean at step start) */
     unsigned int* emig_list;        /* [emig_cap] */
     long long emig_cap;
     unsigned long long* xrow;       /* [PG_XROW]: [0..63] emigrants per destination, [PG_XROW_LEN] list length,
@@ -295,7 +305,7 @@ struct pgpu_ctx {
     int cell_procs_max = 0; /* largest CELL_PROCS entry (validated against nranks before an exchange) */
     int64_t mcc_cell_nrho_cells = 0; /* cells covered by dev.mcc_cell_nrho */
     std::vector<double> h_node_coords, h_face_normal;
-    std::vector<int32_t> h_cell_nodes, h_cell_neighbors, h_cell_faces_pg, h_cell_pg;
+    std::vector<int32_t> h_cell_nodes, h_cell_neighbors, h_cell_faces_pg, h_cell_pg, h_cell_procs;
     std::vector<int32_t> h_bc_volume, h_bc_particle, h_bc_field, h_bc_react;
     bool mesh_set, mesh_dirty;
 
@@ -308,6 +318,9 @@ struct pgpu_ctx {
     PgPlanes planes[2];
     int cur;
     long long np, capacity;
+    long long np_ub;      /* upper bound of the device-side count inside a call (sizes the launch grids) */
+    bool np_dev_valid;    /* the device-side count differs from np: pg_finish adopts it */
+    bool owned_clean;     /* every particle sits in a cell this rank owns (true after an EXCHANGE) */
     bool has_dtrim, sorted, hist_valid, maybe_tombstones;
     bool any_internal_dof, ie_seen; /* species with ROTDOF/VIBDOF != 0; nonzero EROT/EVIB seen in an upload */
     unsigned int* d_tile_first;
@@ -374,6 +387,10 @@ struct pgpu_ctx {
     unsigned int* d_emig_list;    /* [emig_cap] slots of the emigrants found by the last ADVECT */
     long long emig_cap;
     bool emig_valid;              /* d_emig_list / count row describe the current store */
+    /* EXCHANGE without host round trips: fixed-capacity messages sized from the previous step's counts */
+    bool x_counts_valid, x_plan_pending = false;
+    long long x_prev_send[64], x_prev_recv[64];
+    double x_headroom; /* message capacity = headroom * previous count + 8192 records (PANTERA_GPU_XCHG_HEADROOM) */
 };
 
 #define PG_FAIL(ctx, code, ...)                                   \
@@ -398,10 +415,13 @@ int pg_finish(pgpu_ctx* c, const char* what); /* sync stream, read back status, 
 int pg_ensure_capacity(pgpu_ctx* c, long long n);
 int pg_ensure_cell_arrays(pgpu_ctx* c);
 int pg_reset_status(pgpu_ctx* c);
-int pg_sort_impl(pgpu_ctx* c, bool defer_vel = false); /* histogram (if needed) + scan + scatter; async */
+int pg_set_np_cur(pgpu_ctx* c);              /* status->np_cur = c->np (after the host changed the count inside a call) */
+long long pg_exchange_recv_slots(const pgpu_ctx* c);
+int pg_sort_impl(pgpu_ctx* c, bool defer_vel = false, bool sync_np = true); /* histogram (if needed) + scan + scatter */
 int pg_resolve_vel(pgpu_ctx* c);             /* finishes a deferred vel reorder (no-op otherwise); async */
 int pg_advect_impl(pgpu_ctx* c, int tID);    /* async */
-int pg_collide_impl(pgpu_ctx* c, int tID);   /* async except for the dependency-round loop */
+int pg_collide_impl(pgpu_ctx* c, int tID, bool big_now = true); /* CELL path (async) [+ GLOBAL path, which syncs] */
+int pg_collide_big(pgpu_ctx* c);             /* GLOBAL path for the oversized cells + end of a deferred vel reorder */
 int pg_exchange_impl(pgpu_ctx* c);
 void pg_refresh_dev(pgpu_ctx* c);
 

@@ -48,7 +48,7 @@ static __device__ void hs_scatter(PgRng& g, double ecoll, double m1, double m2, 
 static __device__ long long pg_append_particle(const PgDev& d, double x, double y, double z, double vx, double vy, double vz,
                                         double erot, double evib, int sid, int ic) {
     unsigned long long k = atomicAdd(&d.status->n_appended, 1ULL);
-    long long o = d.np + (long long)k;
+    long long o = (long long)d.status->np_cur + (long long)k; /* (np_cur does not move while a collision kernel runs) */
     if (o >= d.capacity) {
         pg_set_err(d, PG_DEVERR_CAPACITY);
         return -1;

@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(256) deposit_kernel(const __grid_constant__ Pg
     }
     double* acc = SMEM ? srhs : rhs;
     const double K = PG_QE / (PG_EPS0 * (d.eps_scaling * d.eps_scaling));
-    for (long long jp = (long long)blockIdx.x * blockDim.x + threadIdx.x; jp < d.np; jp += (long long)gridDim.x * blockDim.x) {
+    for (long long jp = (long long)blockIdx.x * blockDim.x + threadIdx.x; jp < (long long)d.status->np_cur; jp += (long long)gridDim.x * blockDim.x) {
         const PgPos P = d.p.pos[jp];
         int ic = P.ic;
         if (ic < 1) continue;
@@ -117,7 +117,7 @@ __global__ void add_surface_charge_kernel(double* __restrict__ rhs, const double
 /* ref: src/collisions.f90:1646-1890, one thread per particle present at entry */
 __global__ void __launch_bounds__(128) mcc_vahedi_kernel(const __grid_constant__ PgDev d, double p_null) {
     long long jp1 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (jp1 >= d.np) return;
+    if (jp1 >= (long long)d.status->np_cur) return; /* the particles present at entry */
     const PgPos P1 = d.p.pos[jp1];
     int ic = P1.ic;
     if (ic < 1) return;
@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(128) mcc_vahedi_kernel(const __grid_constant__
 
 __global__ void __launch_bounds__(256) remove_species_kernel(const __grid_constant__ PgDev d, int sp) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= d.np) return;
+    if (i >= (long long)d.status->np_cur) return;
     const PgPos P = d.p.pos[i];
     if (P.ic < 1) return;
     if (P.sid == sp) {
@@ -245,7 +245,7 @@ extern "C" int pgpu_deposit_charge(pgpu_ctx* c, double* rhs_host, int64_t nnodes
 
 int pg_mcc_impl(pgpu_ctx* c, int tID) {
     if (!c->dev.mcc_ncomp) PG_FAIL(c, PGPU_ERR_STATE, "mcc_vahedi: background mixture not set");
-    if (c->np == 0) return PGPU_OK;
+    if (c->np_ub == 0) return PGPU_OK;
     { int rc0; if ((rc0 = pg_resolve_vel(c))) return rc0; }
     c->dev.tID = tID;
     pg_refresh_dev(c);
@@ -254,7 +254,7 @@ int pg_mcc_impl(pgpu_ctx* c, int tID) {
     double null_coll_freq = c->cfg.mcc_bg_dens * (double)1e-12f;
     double p_null = 1 - exp(-dt * null_coll_freq);
     if (p_null > 1) p_null = 1.;
-    mcc_vahedi_kernel<<<(unsigned int)((c->np + 127) / 128), 128, 0, c->stream>>>(c->dev, p_null);
+    mcc_vahedi_kernel<<<(unsigned int)((c->np_ub + 127) / 128), 128, 0, c->stream>>>(c->dev, p_null);
     c->launches++;
     PG_CUDA(c, cudaGetLastError());
     c->sorted = false;

@@ -23,14 +23,14 @@ def usable_cores() -> int:
         return max(1, os.cpu_count() or 1)
 
 
-def make_ranks(nranks: int, cubes=(8, 32, 32), ppc: int = 40, seed: int = 7):
+def make_ranks(nranks: int, cubes=(8, 32, 32), ppc: int = 40, seed: int = 7, u_drift: float = 100.0):
     """nranks oracle contexts, each seeded with its own strip of the C5 channel (same cell size, particles
     per cell, dt and wall models as the GPU arm's workload)."""
     ncx, ncy, ncz = cubes
     n = ncx * ncy * ncz * 6 * ppc
     libs, mesh = [], None
     for r in range(nranks):
-        w = wl.c5_channel_strip(ncx, ncy, ncz, n=n, rank=r, world=nranks, seed=seed + r, mesh=mesh)
+        w = wl.c5_channel_strip(ncx, ncy, ncz, n=n, rank=r, world=nranks, seed=seed + r, mesh=mesh, u_drift=u_drift)
         mesh = w.mesh
         o = capi.load_oracle(rng_mode=0)
         wl.apply(o, w)
@@ -55,7 +55,7 @@ def run(steps: int = 10, warmup: int = 3, world: int = 1, cubes=(8, 32, 32), ppc
     # 2.0e6 particles (189 MB of AoS records) per strip: like the real workload, a strip does not fit the caches
     # (a 2.5e5-particle strip runs 1.8x faster per particle on this build container's cores)
     cores = usable_cores()
-    libs, n_per_rank, mesh = make_ranks(cores, cubes, ppc)
+    libs, n_per_rank, mesh = make_ranks(cores, cubes, ppc, u_drift=0.0)  # same config as the GPU arm: no mean drift
     sim_run(libs, 1, max(warmup, 1))
     sec, tot = sim_run(libs, 1 + warmup, steps)
     n_total = sum(l.num_particles() for l in libs)
