@@ -252,6 +252,21 @@ int pgpu_run_steps(pgpu_ctx* ctx, int32_t tID0, int32_t nsteps,
 int pgpu_dump_particles_file(pgpu_ctx* ctx, const char* path_prefix, int32_t timestep, int32_t binary);
 int pgpu_read_particles_file(pgpu_ctx* ctx, const char* path_prefix, int32_t timestep, int32_t binary);
 
+/* ---- sampling and conservation checks ------------------------------- */
+/* GRID_AVG (src/postprocess.f90:34-416, BOOL_DUMP_MOMENTS = .FALSE.): one more sample of the per (cell, species)
+ * number, mean velocity, translational temperatures per axis, rotational and vibrational temperature into the running
+ * averages AVG_*, which stay on the device.  GRID_RESET (:1070-1094) clears them. */
+int pgpu_grid_avg(pgpu_ctx* ctx);
+int pgpu_grid_reset(pgpu_ctx* ctx);
+/* the running averages, arrays of n >= NCELLS*N_SPECIES doubles indexed JC + NCELLS*(JS-1) (0-based JC, JS here);
+ * null pointers are skipped; avg_cumulated = AVG_CUMULATED.  Summed over the ranks (a cell is sampled by its owner). */
+int pgpu_get_grid_avg(pgpu_ctx* ctx, int64_t n, double* avg_np, double* avg_vx, double* avg_vy, double* avg_vz,
+                      double* avg_ttrx, double* avg_ttry, double* avg_ttrz, double* avg_ttr, double* avg_trot,
+                      double* avg_tvib, int32_t* avg_cumulated);
+/* CHECKS, particle loop + reduction over ranks (src/postprocess.f90:1752-1796): TOT_NUM(NS), TOT_MOMENTUM(3,NS),
+ * TOT_KE_PART(NS), TOT_IE.  The electrostatic terms stay with the field solver on the host. */
+int pgpu_checks(pgpu_ctx* ctx, int64_t* tot_num, double* tot_momentum, double* tot_ke_part, double* tot_ie);
+
 /* ---- counters / diagnostics ------------------------------------------------------------ */
 /* BOUNDARY_COLL_COUNT(4*NS) and WALL_COLL_COUNT(NW*NS) of the last ADVECT (timecycle.f90:2138-2144) */
 int pgpu_get_boundary_counts(pgpu_ctx* ctx, int64_t* boundary_coll_count, int64_t nb,

@@ -103,6 +103,11 @@ struct po_ctx {
     int seeded;
     uint32_t key[2], ent[3], ndraw;
     uint32_t phx_buf[4];
+    /* GRID_AVG running averages */
+    double* gavg;   /* [9][nbins]: NP, VX, VY, VZ, TTRX, TTRY, TTRZ, TROT, TVIB */
+    int *gcum1, *gcum2;
+    int64_t gbins;
+    int avg_cumulated;
     /* rng_mode 2: rf() returns the next value of a caller-supplied script (tests/golden/fortran_pins.py) */
     double* script;
     int64_t script_n, script_pos;
@@ -1774,6 +1779,142 @@ int po_read_particles_file(po_ctx* w, const char* path_prefix, int32_t timestep,
     return PGPU_OK;
 }
 
+/* ------------------------------------------------------------------------------------------
+ * GRID_AVG / GRID_RESET / CHECKS. ref: src/postprocess.f90:34-416 (BOOL_DUMP_MOMENTS = .FALSE.), :1070-1094, :1722-1800
+ * ---------------------------------------------------------------------------------------- */
+static int64_t ncells_of(const po_ctx* w) {
+    return (w->c.grid_type == PGPU_UNSTRUCTURED) ? w->nc : (int64_t)w->c.nx * w->c.ny;
+}
+static int gavg_alloc(po_ctx* w) {
+    int64_t nb = ncells_of(w) * w->ns;
+    if (w->gavg && w->gbins == nb) return PGPU_OK;
+    free(w->gavg); free(w->gcum1); free(w->gcum2);
+    w->gavg = (double*)calloc((size_t)(9 * nb), sizeof(double));
+    w->gcum1 = (int*)calloc((size_t)nb, sizeof(int));
+    w->gcum2 = (int*)calloc((size_t)nb, sizeof(int));
+    w->gbins = nb;
+    w->avg_cumulated = 0;
+    return PGPU_OK;
+}
+int po_grid_reset(po_ctx* w) {
+    gavg_alloc(w);
+    memset(w->gavg, 0, sizeof(double) * (size_t)(9 * w->gbins));
+    memset(w->gcum1, 0, sizeof(int) * (size_t)w->gbins);
+    memset(w->gcum2, 0, sizeof(int) * (size_t)w->gbins);
+    w->avg_cumulated = 0;
+    return PGPU_OK;
+}
+int po_grid_avg(po_ctx* w) {
+    gavg_alloc(w);
+    const int64_t nb = w->gbins, ncells = ncells_of(w);
+    int* tnp = (int*)calloc((size_t)nb, sizeof(int));
+    double* t = (double*)calloc((size_t)(12 * nb), sizeof(double));
+    double *vx = t, *vy = t + nb, *vz = t + 2 * nb, *vx2 = t + 3 * nb, *vy2 = t + 4 * nb, *vz2 = t + 5 * nb, *erot = t + 6 * nb,
+           *evib = t + 7 * nb, *ttrx = t + 8 * nb, *ttry = t + 9 * nb, *ttrz = t + 10 * nb;
+    double* trotvib = (double*)calloc((size_t)(2 * nb), sizeof(double));
+    double *trot = trotvib, *tvib = trotvib + nb;
+    char* one = (char*)calloc((size_t)nb, 1);
+    char* two = (char*)calloc((size_t)nb, 1);
+    for (int64_t jp = 0; jp < w->np; jp++) { /* :133-138 */
+        int64_t idx = (w->p[jp].IC - 1) + ncells * (w->p[jp].S_ID - 1);
+        tnp[idx]++;
+    }
+    for (int64_t jp = 0; jp < w->np; jp++) { /* :141-148 */
+        int64_t idx = (w->p[jp].IC - 1) + ncells * (w->p[jp].S_ID - 1);
+        vx[idx] += w->p[jp].VX; vy[idx] += w->p[jp].VY; vz[idx] += w->p[jp].VZ;
+    }
+    for (int64_t i = 0; i < nb; i++) /* :151-158 */
+        if (tnp[i] > 0) {
+            one[i] = 1;
+            vx[i] = vx[i] / (double)tnp[i]; vy[i] = vy[i] / (double)tnp[i]; vz[i] = vz[i] / (double)tnp[i];
+        }
+    for (int64_t jp = 0; jp < w->np; jp++) { /* :161-171 */
+        const part_t* q = &w->p[jp];
+        int64_t idx = (q->IC - 1) + ncells * (q->S_ID - 1);
+        vx2[idx] += q->VX * q->VX; vy2[idx] += q->VY * q->VY; vz2[idx] += q->VZ * q->VZ;
+        erot[idx] += q->EROT; evib[idx] += q->EVIB;
+    }
+    for (int64_t jc = 0; jc < ncells; jc++) /* :262-297 */
+        for (int js = 0; js < w->ns; js++) {
+            int64_t i = jc + ncells * js;
+            if (tnp[i] > 0) {
+                if (w->rotdof[js] == 0) trot[i] = 0.0;
+                else trot[i] = (double)(2.f / (float)w->rotdof[js]) / KB * (erot[i] / (double)tnp[i]);
+                if (w->vibdof[js] == 0) tvib[i] = 0.0;
+                else tvib[i] = (double)(2.f / (float)w->vibdof[js]) / KB * (evib[i] / (double)tnp[i]);
+                if (tnp[i] > 1) {
+                    two[i] = 1;
+                    double numpart = (double)tnp[i], sampledof = numpart;
+                    ttrx[i] = w->mass[js] / KB * (vx2[i] - numpart * vx[i] * vx[i]) / sampledof;
+                    ttry[i] = w->mass[js] / KB * (vy2[i] - numpart * vy[i] * vy[i]) / sampledof;
+                    ttrz[i] = w->mass[js] / KB * (vz2[i] - numpart * vz[i] * vz[i]) / sampledof;
+                }
+            }
+        }
+    /* :338-381 running averages */
+    double* A = w->gavg;
+    double dcum = (double)w->avg_cumulated;
+    for (int64_t i = 0; i < nb; i++) A[i] = (A[i] * dcum + (double)tnp[i]) / (double)((float)w->avg_cumulated + 1.f);
+    w->avg_cumulated++;
+    for (int64_t i = 0; i < nb; i++) {
+        if (one[i]) {
+            double k = (double)w->gcum1[i], den = (double)((float)w->gcum1[i] + 1.f);
+            A[1 * nb + i] = (A[1 * nb + i] * k + vx[i]) / den;
+            A[2 * nb + i] = (A[2 * nb + i] * k + vy[i]) / den;
+            A[3 * nb + i] = (A[3 * nb + i] * k + vz[i]) / den;
+            A[7 * nb + i] = (A[7 * nb + i] * k + trot[i]) / den;
+            A[8 * nb + i] = (A[8 * nb + i] * k + tvib[i]) / den;
+            w->gcum1[i]++;
+        }
+        if (two[i]) {
+            double k = (double)w->gcum2[i], den = (double)((float)w->gcum2[i] + 1.f);
+            A[4 * nb + i] = (A[4 * nb + i] * k + ttrx[i]) / den;
+            A[5 * nb + i] = (A[5 * nb + i] * k + ttry[i]) / den;
+            A[6 * nb + i] = (A[6 * nb + i] * k + ttrz[i]) / den;
+            w->gcum2[i]++;
+        }
+    }
+    free(tnp); free(t); free(trotvib); free(one); free(two);
+    return PGPU_OK;
+}
+int po_get_grid_avg(po_ctx* w, int64_t n, double* avg_np, double* avg_vx, double* avg_vy, double* avg_vz, double* avg_ttrx,
+                    double* avg_ttry, double* avg_ttrz, double* avg_ttr, double* avg_trot, double* avg_tvib, int32_t* avg_cumulated) {
+    if (!w->gavg) FAIL(w, PGPU_ERR_STATE, "po_get_grid_avg: po_grid_avg has not been called");
+    const int64_t nb = w->gbins;
+    if (n < nb) FAIL(w, PGPU_ERR_INVALID, "po_get_grid_avg: arrays too small");
+    double* dst[9] = {avg_np, avg_vx, avg_vy, avg_vz, avg_ttrx, avg_ttry, avg_ttrz, avg_trot, avg_tvib};
+    for (int k = 0; k < 9; k++)
+        if (dst[k]) memcpy(dst[k], w->gavg + (size_t)k * nb, sizeof(double) * (size_t)nb);
+    if (avg_ttr)
+        for (int64_t i = 0; i < nb; i++) avg_ttr[i] = (w->gavg[4 * nb + i] + w->gavg[5 * nb + i] + w->gavg[6 * nb + i]) / (double)3.0f;
+    if (avg_cumulated) *avg_cumulated = w->avg_cumulated;
+    return PGPU_OK;
+}
+/* CHECKS particle loop, ref: src/postprocess.f90:1752-1786 */
+int po_checks(po_ctx* w, int64_t* tot_num, double* tot_momentum, double* tot_ke_part, double* tot_ie) {
+    for (int js = 0; js < w->ns; js++) {
+        if (tot_num) tot_num[js] = 0;
+        if (tot_ke_part) tot_ke_part[js] = 0;
+        if (tot_momentum) tot_momentum[3 * js] = tot_momentum[3 * js + 1] = tot_momentum[3 * js + 2] = 0;
+    }
+    double ie = 0;
+    for (int64_t jp = 0; jp < w->np; jp++) {
+        const part_t* q = &w->p[jp];
+        int js = q->S_ID - 1;
+        double cfnum = w->c.fnum, m = w->mass[js];
+        if (tot_num) tot_num[js]++;
+        if (tot_momentum) {
+            tot_momentum[0 + 3 * js] += m * q->VX * cfnum;
+            tot_momentum[1 + 3 * js] += m * q->VY * cfnum;
+            tot_momentum[2 + 3 * js] += m * q->VZ * cfnum;
+        }
+        if (tot_ke_part) tot_ke_part[js] += 0.5 * m * (q->VX * q->VX + q->VY * q->VY + q->VZ * q->VZ) * cfnum;
+        ie += (q->EROT + q->EVIB) * cfnum;
+    }
+    if (tot_ie) *tot_ie = ie;
+    return PGPU_OK;
+}
+
 /* ref: src/timecycle.f90:271-299 (PIC_TYPE==NONE branch of TIME_LOOP), single rank */
 int po_run_steps(po_ctx* w, int32_t tID0, int32_t nsteps, int64_t* total_coll, int64_t* total_reac) {
     int64_t tc = 0, tr = 0;
@@ -1831,7 +1972,7 @@ int po_destroy(po_ctx* w) {
     free(w->w_x1); free(w->w_y1); free(w->w_x2); free(w->w_y2); free(w->w_nx); free(w->w_ny);
     free(w->w_temp); free(w->w_transm); free(w->w_spec); free(w->w_diff); free(w->w_porous); free(w->w_react);
     free(w->xcoord); free(w->ycoord);
-    free(w->e_field); free(w->b_field); free(w->surface_charge); free(w->script);
+    free(w->e_field); free(w->b_field); free(w->surface_charge); free(w->script); free(w->gavg); free(w->gcum1); free(w->gcum2);
     free(w->p); free(w->bcount); free(w->wcount); free(w->tallies); free(w->npcall);
     free(w);
     return PGPU_OK;

@@ -112,6 +112,11 @@ int po_collide(po_ctx* ctx, int32_t tID, int64_t* timestep_coll, int64_t* timest
 int po_mcc_vahedi(po_ctx* ctx, int32_t tID, int64_t* timestep_coll, int64_t* timestep_reac);
 int po_mcc_collisions(po_ctx* ctx, int32_t tID, int64_t* timestep_coll, int64_t* timestep_reac);
 int po_remove_species(po_ctx* ctx, int32_t sp_id);
+int po_grid_avg(po_ctx* ctx);
+int po_grid_reset(po_ctx* ctx);
+int po_get_grid_avg(po_ctx* ctx, int64_t n, double* avg_np, double* avg_vx, double* avg_vy, double* avg_vz, double* avg_ttrx,
+                    double* avg_ttry, double* avg_ttrz, double* avg_ttr, double* avg_trot, double* avg_tvib, int32_t* avg_cumulated);
+int po_checks(po_ctx* ctx, int64_t* tot_num, double* tot_momentum, double* tot_ke_part, double* tot_ie);
 int po_dump_particles_file(po_ctx* ctx, const char* path_prefix, int32_t timestep, int32_t binary);
 int po_read_particles_file(po_ctx* ctx, const char* path_prefix, int32_t timestep, int32_t binary);
 int po_run_steps(po_ctx* ctx, int32_t tID0, int32_t nsteps, int64_t* total_coll, int64_t* total_reac);

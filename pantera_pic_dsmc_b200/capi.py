@@ -366,6 +366,32 @@ class Lib:
     def remove_species(self, sp):
         self._call("remove_species", C.c_int32(sp))
 
+    def grid_avg(self):
+        self._call("grid_avg")
+
+    def grid_reset(self):
+        self._call("grid_reset")
+
+    def get_grid_avg(self, ncells: int):
+        """dict of (ns, ncells) arrays: np, vx, vy, vz, ttrx, ttry, ttrz, ttr, trot, tvib; and 'cumulated'."""
+        n = ncells * self.ns
+        names = ["np", "vx", "vy", "vz", "ttrx", "ttry", "ttrz", "ttr", "trot", "tvib"]
+        arrs = [np.zeros(n) for _ in names]
+        cum = C.c_int32()
+        self._call("get_grid_avg", C.c_int64(n), *[_p(a) for a in arrs], C.byref(cum))
+        out = {k: a.reshape(self.ns, ncells) for k, a in zip(names, arrs)}
+        out["cumulated"] = cum.value
+        return out
+
+    def checks(self):
+        """CHECKS: (tot_num[ns], tot_momentum[ns, 3], tot_ke_part[ns], tot_ie)."""
+        num = np.zeros(self.ns, dtype=np.int64)
+        mom = np.zeros(3 * self.ns)
+        ke = np.zeros(self.ns)
+        ie = C.c_double()
+        self._call("checks", _p(num), _p(mom), _p(ke), C.byref(ie))
+        return num, mom.reshape(self.ns, 3), ke, ie.value
+
     def dump_particles_file(self, path_prefix: str, timestep: int, binary: bool = True):
         self._call("dump_particles_file", C.c_char_p(path_prefix.encode()), C.c_int32(timestep), C.c_int32(int(binary)))
 

@@ -174,6 +174,7 @@ extern "C" int pgpu_destroy(pgpu_ctx* c) {
     }
     dev_free(c->d_rhs); dev_free(c->d_bcount); dev_free(c->d_wcount); dev_free(c->d_tallies);
     dev_free(c->d_surface_charge);
+    dev_free(c->d_gavg); dev_free(c->d_gavg_np); dev_free(c->d_gavg_sums); dev_free(c->d_gavg_cum);
     dev_free(c->d_sendbuf); dev_free(c->d_recvbuf); dev_free(c->d_xcount); dev_free(c->d_emig_list);
     for (int i = 0; i < 16; i++) cudaEventDestroy(c->ev[i]);
     cudaStreamDestroy(c->stream);

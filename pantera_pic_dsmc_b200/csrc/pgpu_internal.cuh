@@ -371,6 +371,14 @@ struct pgpu_ctx {
     double* d_surface_charge;
     long long nsc;
 
+    /* GRID_AVG running averages (pgpu_sample.cu) */
+    double* d_gavg = nullptr;
+    unsigned int* d_gavg_np = nullptr;
+    double* d_gavg_sums = nullptr;
+    int* d_gavg_cum = nullptr;
+    long long gavg_bins = 0;
+    int avg_cumulated = 0;
+
     /* timings */
     cudaEvent_t ev[16];
     double ms[8];
