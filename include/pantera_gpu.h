@@ -242,6 +242,33 @@ int pgpu_remove_species(pgpu_ctx* ctx, int32_t sp_id);
 int pgpu_run_steps(pgpu_ctx* ctx, int32_t tID0, int32_t nsteps,
                    int64_t* total_coll, int64_t* total_reac);
 
+/* ---- particle creation on the device -------------------------------- */
+/* SPECIES(:)%SPWT (default 1) and MIXTURES(:): components of mixture k (0-based) are comp_sp (1-based species ids) /
+ * comp_molfrac [comp_off[k], comp_off[k+1]) */
+int pgpu_set_species_weights(pgpu_ctx* ctx, int ns, const double* spwt);
+int pgpu_set_mixtures(pgpu_ctx* ctx, int nmix, const int32_t* comp_off, const int32_t* comp_sp, const double* comp_molfrac);
+/* INITIAL_PARTICLES_TASKS / VOLUME_INJECT_TASKS (src/global.f90:275-294), mix_id 0-based */
+int pgpu_set_initial_particles_tasks(pgpu_ctx* ctx, int n, const int32_t* mix_id, const double* nrho,
+                                     const double* ux, const double* uy, const double* uz,
+                                     const double* ttrax, const double* ttray, const double* ttraz,
+                                     const double* trot, const double* tvib);
+int pgpu_set_volume_inject_tasks(pgpu_ctx* ctx, int n, const int32_t* mix_id, const double* nrhodot,
+                                 const double* ux, const double* uy, const double* uz,
+                                 const double* ttrax, const double* ttray, const double* ttraz,
+                                 const double* trot, const double* tvib);
+/* EMIT_TASKS (src/global.f90:257-267) as INITINJECTION leaves them (src/initialization.f90:2575-2675): cell, face
+ * (1-based), face nodes IV1/IV2 (1-D/2-D), U_NORM, and NFS(component) = particles per step per rank at
+ * nfs[nfs_off[task] + component] */
+int pgpu_set_emit_tasks(pgpu_ctx* ctx, int n, const int32_t* mix_id, const int32_t* ic, const int32_t* iv1,
+                        const int32_t* iv2, const int32_t* iface, const int32_t* nfs_off, const double* nfs,
+                        const double* ux, const double* uy, const double* uz, const double* u_norm,
+                        const double* ttra, const double* trot, const double* tvib);
+/* INITIAL_SEED (src/initialization.f90:2017-2233) without its trailing EXCHANGE; VOLUME_INJECT (src/timecycle.f90:553-737);
+ * BOUNDARIES_EMIT (src/timecycle.f90:368-547).  The particles are created in the append region of the device store. */
+int pgpu_initial_seed(pgpu_ctx* ctx);
+int pgpu_volume_inject(pgpu_ctx* ctx, int32_t tID);
+int pgpu_boundaries_emit(pgpu_ctx* ctx, int32_t tID);
+
 /* ---- dump / restart -------------------------------------------------- */
 /* DUMP_PARTICLES_FILE (src/tools.f90:327-365) / READ_PARTICLES_FILE (src/tools.f90:465-517): the file
  * <path_prefix>proc_<rank:05d>_time_<timestep:08d> in the reference's binary layout (Fortran sequential unformatted,

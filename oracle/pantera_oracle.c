@@ -103,6 +103,15 @@ struct po_ctx {
     int seeded;
     uint32_t key[2], ent[3], ndraw;
     uint32_t phx_buf[4];
+    /* injection / seeding tasks */
+    double* spwt;
+    int nmix;
+    int* mix_off; int* mix_sp; double* mix_frac;
+    int n_seed, n_vinj, n_emit;
+    double* seed_par; int* seed_mix;   /* [n][9]: rate, UX, UY, UZ, TTRAX, TTRAY, TTRAZ, TROT, TVIB */
+    double* vinj_par; int* vinj_mix;
+    double* emit_par; int* emit_int;   /* [n][7]: UX, UY, UZ, U_NORM, TTRA, TROT, TVIB; [n][6]: MIX_ID, IC, IV1, IV2, IFACE, nfs offset */
+    double* emit_nfs;
     /* GRID_AVG running averages */
     double* gavg;   /* [9][nbins]: NP, VX, VY, VZ, TTRX, TTRY, TTRZ, TROT, TVIB */
     int *gcum1, *gcum2;
@@ -1780,6 +1789,245 @@ int po_read_particles_file(po_ctx* w, const char* path_prefix, int32_t timestep,
 }
 
 /* ------------------------------------------------------------------------------------------
+ * INITIAL_SEED (src/initialization.f90:2017-2233), VOLUME_INJECT (src/timecycle.f90:553-737), BOUNDARIES_EMIT
+ * (src/timecycle.f90:368-547); RANDINT src/tools.f90:1304-1311.  COLOCATED_ELECTRONS, BOOL_INJECT_FROM_FILE and the
+ * kappa distribution are outside the scope.
+ * MT mode: the draws come from the rank's sequential stream in the reference's loop order.  Philox mode (device
+ * contract): one stream per (cell | emit task, task, component) -- kind 5 INITIAL_SEED, 6 VOLUME_INJECT, 7
+ * BOUNDARIES_EMIT; e0 = cell (0-based) or emit task; e1 = task * 256 + component -- whose draws are consumed in the
+ * reference's order for that loop body: the RANDINT draw, then per particle position, MAXWELL, INTERNAL_ENERGY (x2).
+ * On rectilinear grids the whole domain is one loop; there the count comes from stream (e0 = 0) and particle ip draws
+ * from stream (e0 = 1 + ip).
+ * ---------------------------------------------------------------------------------------- */
+static int randint(po_ctx* w, double x) {
+    int r = (int)x;
+    if (x - r > po_rf(w)) r = r + 1;
+    return r;
+}
+static const int FACE_IND[4][3] = {{1, 3, 2}, {1, 2, 4}, {2, 3, 4}, {1, 4, 3}}; /* src/grid_and_partition.f90:1932-1935 */
+
+/* kind: 5 seed (rate = NRHO, owned fluid cells only, no division by the rank count on unstructured grids),
+ *       6 volume inject (rate = DT*NRHODOT, all cells, divided by N_MPI_THREADS) */
+static int cell_source(po_ctx* w, int kind, int tID, int ntask, const double* par, const int* mixid) {
+    const int nranks = w->c.nranks > 0 ? w->c.nranks : 1;
+    for (int it = 0; it < ntask; it++) {
+        const double* tp = par + 9 * it;
+        const int mix = mixid[it];
+        for (int i = w->mix_off[mix]; i < w->mix_off[mix + 1]; i++) {
+            const int icomp = i - w->mix_off[mix];
+            const int s_id = w->mix_sp[i];
+            const double frac = w->mix_frac[i], m = w->mass[s_id - 1];
+            const double spwt = w->spwt ? w->spwt[s_id - 1] : 1.0;
+            const double rate = (kind == 5) ? tp[0] : w->c.dt * tp[0];
+            if (w->c.grid_type == PGPU_UNSTRUCTURED) {
+                const int d = w->dims_mesh;
+                for (int ic = 1; ic <= w->nc; ic++) {
+                    if (kind == 5) {
+                        if (w->cell_procs && w->cell_procs[ic - 1] != w->c.rank) continue;
+                        if (w->cell_pg && w->cell_pg[ic - 1] != -1 && w->bc_volume && w->bc_volume[w->cell_pg[ic - 1] - 1] == PGPU_SOLID) continue;
+                    }
+                    po_rng_stream(w, kind, tID, (uint64_t)(ic - 1), (uint64_t)(it * 256 + icomp));
+                    const double vol = w->cell_volumes[ic - 1];
+                    int np_init;
+                    if (kind == 5) np_init = randint(w, rate / (w->c.fnum * spwt) * vol * frac);
+                    else np_init = randint(w, rate / (w->c.fnum * spwt) * vol * frac / nranks);
+                    if (np_init == 0) continue;
+                    double V[4][3] = {{0}};
+                    for (int k = 0; k <= d; k++)
+                        for (int a = 0; a < 3; a++) V[k][a] = w->node_coords[3 * (w->cell_nodes[(d + 1) * (ic - 1) + k] - 1) + a];
+                    for (int ip = 0; ip < np_init; ip++) {
+                        double S = po_rf(w), T = po_rf(w), U = po_rf(w), xp, yp, zp;
+                        if (S + T > 1) { S = 1 - S; T = 1 - T; }
+                        if (d == 1) {
+                            xp = V[0][0] + (V[1][0] - V[0][0]) * S;
+                            yp = w->c.ymin + (w->c.ymax - w->c.ymin) * T;
+                            zp = w->c.zmin + (w->c.zmax - w->c.zmin) * U;
+                        } else if (d == 2) {
+                            xp = V[0][0] + (V[1][0] - V[0][0]) * S + (V[2][0] - V[0][0]) * T;
+                            yp = V[0][1] + (V[1][1] - V[0][1]) * S + (V[2][1] - V[0][1]) * T;
+                            zp = w->c.axi ? 0.0 : w->c.zmin + (w->c.zmax - w->c.zmin) * U;
+                        } else {
+                            double P, Q, R;
+                            if (S + T + U <= 1) { P = S; Q = T; R = U; }
+                            else if (T + U > 1) { P = S; Q = 1 - U; R = 1 - S - T; }
+                            else { P = 1 - T - U; Q = T; R = S + T + U - 1; }
+                            xp = V[0][0] + (V[1][0] - V[0][0]) * P + (V[2][0] - V[0][0]) * Q + (V[3][0] - V[0][0]) * R;
+                            yp = V[0][1] + (V[1][1] - V[0][1]) * P + (V[2][1] - V[0][1]) * Q + (V[3][1] - V[0][1]) * R;
+                            zp = V[0][2] + (V[1][2] - V[0][2]) * P + (V[2][2] - V[0][2]) * Q + (V[3][2] - V[0][2]) * R;
+                        }
+                        double v3[3];
+                        po_maxwell(w, tp[1], tp[2], tp[3], tp[4], tp[5], tp[6], m, v3);
+                        double erot = po_internal_energy(w, w->rotdof[s_id - 1], tp[7]);
+                        double evib = po_internal_energy(w, w->vibdof[s_id - 1], tp[8]);
+                        add_particle(w, xp, yp, zp, v3[0], v3[1], v3[2], erot, evib, s_id, ic, w->c.dt);
+                    }
+                }
+            } else {
+                double domain_volume;
+                if (w->c.axi) domain_volume = 0.5 * (w->c.xmax - w->c.xmin) * (w->c.ymax * w->c.ymax - w->c.ymin * w->c.ymin) * (w->c.zmax - w->c.zmin);
+                else domain_volume = (w->c.xmax - w->c.xmin) * (w->c.ymax - w->c.ymin) * (w->c.zmax - w->c.zmin);
+                po_rng_stream(w, kind, tID, 0ULL, (uint64_t)(it * 256 + icomp));
+                int np_init = randint(w, rate / (w->c.fnum * spwt) * domain_volume * frac / nranks);
+                for (int ip = 0; ip < np_init; ip++) {
+                    po_rng_stream(w, kind, tID, (uint64_t)(1 + ip), (uint64_t)(it * 256 + icomp));
+                    double xp = w->c.xmin + (w->c.xmax - w->c.xmin) * po_rf(w), yp, zp;
+                    if (w->c.axi) {
+                        yp = sqrt(w->c.ymin * w->c.ymin + po_rf(w) * (w->c.ymax * w->c.ymax - w->c.ymin * w->c.ymin));
+                        zp = 0;
+                    } else {
+                        yp = w->c.ymin + (w->c.ymax - w->c.ymin) * po_rf(w);
+                        zp = w->c.zmin + (w->c.zmax - w->c.zmin) * po_rf(w);
+                    }
+                    double v3[3];
+                    po_maxwell(w, tp[1], tp[2], tp[3], tp[4], tp[5], tp[6], m, v3);
+                    double erot = po_internal_energy(w, w->rotdof[s_id - 1], tp[7]);
+                    double evib = po_internal_energy(w, w->vibdof[s_id - 1], tp[8]);
+                    int cid = cell_from_position(w, xp, yp);
+                    add_particle(w, xp, yp, zp, v3[0], v3[1], v3[2], erot, evib, s_id, cid, w->c.dt);
+                }
+            }
+        }
+    }
+    return PGPU_OK;
+}
+int po_initial_seed(po_ctx* w) {
+    if (!w->mix_off) FAIL(w, PGPU_ERR_STATE, "po_initial_seed: mixtures not set");
+    return cell_source(w, 5, 0, w->n_seed, w->seed_par, w->seed_mix);
+}
+int po_volume_inject(po_ctx* w, int32_t tID) {
+    if (!w->mix_off) FAIL(w, PGPU_ERR_STATE, "po_volume_inject: mixtures not set");
+    return cell_source(w, 6, tID, w->n_vinj, w->vinj_par, w->vinj_mix);
+}
+/* ref: src/timecycle.f90:368-547 */
+int po_boundaries_emit(po_ctx* w, int32_t tID) {
+    if (w->n_emit && !w->mix_off) FAIL(w, PGPU_ERR_STATE, "po_boundaries_emit: mixtures not set");
+    const int d = w->dims_mesh;
+    for (int it = 0; it < w->n_emit; it++) {
+        const double* tp = w->emit_par + 7 * it;
+        const int* ti = w->emit_int + 6 * it;
+        const int mix = ti[0], ic = ti[1], iv1 = ti[2], iv2 = ti[3], iface = ti[4];
+        double fn[3] = {0, 0, 0}, t1[3], t2[3], x1 = 0, y1 = 0, x2 = 0, y2 = 0, V1[3] = {0}, V2[3] = {0}, V3[3] = {0};
+        const size_t f = (size_t)(d + 1) * (ic - 1) + (iface - 1);
+        for (int a = 0; a < 3; a++) fn[a] = w->face_normal[3 * f + a];
+        if (d == 1) {
+            x1 = w->node_coords[3 * (iv1 - 1)]; x2 = w->node_coords[3 * (iv2 - 1)];
+            t1[0] = 0; t1[1] = fn[0]; t1[2] = 0; t2[0] = 0; t2[1] = 0; t2[2] = 1;
+        } else if (d == 2) {
+            x1 = w->node_coords[3 * (iv1 - 1)]; y1 = w->node_coords[3 * (iv1 - 1) + 1];
+            x2 = w->node_coords[3 * (iv2 - 1)]; y2 = w->node_coords[3 * (iv2 - 1) + 1];
+            t1[0] = -fn[1]; t1[1] = fn[0]; t1[2] = 0; t2[0] = 0; t2[1] = 0; t2[2] = 1;
+        } else {
+            for (int a = 0; a < 3; a++) {
+                t1[a] = w->face_tang1[3 * f + a];
+                t2[a] = w->face_tang2[3 * f + a];
+                V1[a] = w->node_coords[3 * (w->cell_nodes[4 * (ic - 1) + FACE_IND[iface - 1][0] - 1] - 1) + a];
+                V2[a] = w->node_coords[3 * (w->cell_nodes[4 * (ic - 1) + FACE_IND[iface - 1][1] - 1] - 1) + a];
+                V3[a] = w->node_coords[3 * (w->cell_nodes[4 * (ic - 1) + FACE_IND[iface - 1][2] - 1] - 1) + a];
+            }
+        }
+        for (int i = w->mix_off[mix]; i < w->mix_off[mix + 1]; i++) {
+            const int icomp = i - w->mix_off[mix];
+            const int s_id = w->mix_sp[i];
+            const double m = w->mass[s_id - 1];
+            po_rng_stream(w, 7, tID, (uint64_t)it, (uint64_t)icomp);
+            const double nfs_x = w->emit_nfs[ti[5] + icomp];
+            int nfs = (int)floor(nfs_x);
+            if (nfs_x - (double)nfs >= po_rf(w)) nfs = nfs + 1;
+            double beta = 0;
+            if (tp[4] != 0) beta = 1. / sqrt(2. * KB / m * tp[4]);
+            for (int ip = 0; ip < nfs; ip++) {
+                double v3[3];
+                po_maxwell(w, 0., 0., 0., tp[4], tp[4], tp[4], m, v3);
+                double erot = po_internal_energy(w, w->rotdof[s_id - 1], tp[5]);
+                double evib = po_internal_energy(w, w->vibdof[s_id - 1], tp[6]);
+                double v_norm = 0;
+                if (tp[4] != 0) v_norm = po_flx(w, tp[3] * beta, tp[4], m);
+                double vx = tp[0] - v_norm * fn[0] - v3[1] * t1[0] - v3[2] * t2[0];
+                double vy = tp[1] - v_norm * fn[1] - v3[1] * t1[1] - v3[2] * t2[1];
+                double vz = tp[2] - v_norm * fn[2] - v3[1] * t1[2] - v3[2] * t2[2];
+                double dtfrac = po_rf(w) * w->c.dt;
+                double x, y, z;
+                if (d == 1) {
+                    double R = po_rf(w);
+                    x = x1 + R * (x2 - x1);
+                    y = w->c.ymin + (w->c.ymax - w->c.ymin) * po_rf(w);
+                    z = w->c.zmin + (w->c.zmax - w->c.zmin) * po_rf(w);
+                } else if (d == 2) {
+                    double R = po_rf(w);
+                    if (w->c.axi) {
+                        if (y1 == y2) { y = y1; x = x1 + R * (x2 - x1); z = 0; }
+                        else if (y1 < y2) { y = sqrt(y1 * y1 + R * (y2 * y2 - y1 * y1)); x = x1 + (y - y1) / (y2 - y1) * (x2 - x1); z = 0; }
+                        else { y = sqrt(y2 * y2 + R * (y1 * y1 - y2 * y2)); x = x2 + (y - y2) / (y1 - y2) * (x1 - x2); z = 0; }
+                    } else {
+                        x = x1 + R * (x2 - x1);
+                        y = y1 + R * (y2 - y1);
+                        z = w->c.zmin + (w->c.zmax - w->c.zmin) * po_rf(w);
+                    }
+                } else {
+                    double S = po_rf(w), T = po_rf(w), P, Q;
+                    if (S > 1 - T) { Q = 1 - T; P = 1 - S; }
+                    else { Q = T; P = S; }
+                    x = V1[0] + (V2[0] - V1[0]) * P + (V3[0] - V1[0]) * Q;
+                    y = V1[1] + (V2[1] - V1[1]) * P + (V3[1] - V1[1]) * Q;
+                    z = V1[2] + (V2[2] - V1[2]) * P + (V3[2] - V1[2]) * Q;
+                }
+                add_particle(w, x, y, z, vx, vy, vz, erot, evib, s_id, ic, dtfrac);
+            }
+        }
+    }
+    return PGPU_OK;
+}
+int po_set_species_weights(po_ctx* w, int ns, const double* spwt) { REPL(w->spwt, spwt, ns); return PGPU_OK; }
+int po_set_mixtures(po_ctx* w, int nmix, const int32_t* comp_off, const int32_t* comp_sp, const double* comp_molfrac) {
+    REPL(w->mix_off, comp_off, nmix + 1);
+    REPL(w->mix_sp, comp_sp, comp_off[nmix]);
+    REPL(w->mix_frac, comp_molfrac, comp_off[nmix]);
+    w->nmix = nmix;
+    return PGPU_OK;
+}
+static int set_source_tasks(double** par, int** mix, int* count, int n, const int32_t* mix_id, const double* rate, const double* ux,
+                            const double* uy, const double* uz, const double* tx, const double* ty, const double* tz,
+                            const double* trot, const double* tvib) {
+    free(*par); free(*mix);
+    *par = (double*)calloc((size_t)(9 * (n > 0 ? n : 1)), sizeof(double));
+    *mix = (int*)calloc((size_t)(n > 0 ? n : 1), sizeof(int));
+    for (int i = 0; i < n; i++) {
+        double* t = *par + 9 * i;
+        t[0] = rate[i]; t[1] = ux[i]; t[2] = uy[i]; t[3] = uz[i]; t[4] = tx[i]; t[5] = ty[i]; t[6] = tz[i]; t[7] = trot[i]; t[8] = tvib[i];
+        (*mix)[i] = mix_id[i];
+    }
+    *count = n;
+    return PGPU_OK;
+}
+int po_set_initial_particles_tasks(po_ctx* w, int n, const int32_t* mix_id, const double* nrho, const double* ux, const double* uy,
+                                   const double* uz, const double* ttrax, const double* ttray, const double* ttraz,
+                                   const double* trot, const double* tvib) {
+    return set_source_tasks(&w->seed_par, &w->seed_mix, &w->n_seed, n, mix_id, nrho, ux, uy, uz, ttrax, ttray, ttraz, trot, tvib);
+}
+int po_set_volume_inject_tasks(po_ctx* w, int n, const int32_t* mix_id, const double* nrhodot, const double* ux, const double* uy,
+                               const double* uz, const double* ttrax, const double* ttray, const double* ttraz,
+                               const double* trot, const double* tvib) {
+    return set_source_tasks(&w->vinj_par, &w->vinj_mix, &w->n_vinj, n, mix_id, nrhodot, ux, uy, uz, ttrax, ttray, ttraz, trot, tvib);
+}
+int po_set_emit_tasks(po_ctx* w, int n, const int32_t* mix_id, const int32_t* ic, const int32_t* iv1, const int32_t* iv2,
+                      const int32_t* iface, const int32_t* nfs_off, const double* nfs, const double* ux, const double* uy,
+                      const double* uz, const double* u_norm, const double* ttra, const double* trot, const double* tvib) {
+    free(w->emit_par); free(w->emit_int); free(w->emit_nfs);
+    w->emit_par = (double*)calloc((size_t)(7 * (n > 0 ? n : 1)), sizeof(double));
+    w->emit_int = (int*)calloc((size_t)(6 * (n > 0 ? n : 1)), sizeof(int));
+    int total = n > 0 ? nfs_off[n] : 0;
+    w->emit_nfs = (double*)dupmem(nfs, sizeof(double) * (size_t)(total > 0 ? total : 1));
+    for (int i = 0; i < n; i++) {
+        double* t = w->emit_par + 7 * i;
+        t[0] = ux[i]; t[1] = uy[i]; t[2] = uz[i]; t[3] = u_norm[i]; t[4] = ttra[i]; t[5] = trot[i]; t[6] = tvib[i];
+        int* k = w->emit_int + 6 * i;
+        k[0] = mix_id[i]; k[1] = ic[i]; k[2] = iv1[i]; k[3] = iv2[i]; k[4] = iface[i]; k[5] = nfs_off[i];
+    }
+    w->n_emit = n;
+    return PGPU_OK;
+}
+
+/* ------------------------------------------------------------------------------------------
  * GRID_AVG / GRID_RESET / CHECKS. ref: src/postprocess.f90:34-416 (BOOL_DUMP_MOMENTS = .FALSE.), :1070-1094, :1722-1800
  * ---------------------------------------------------------------------------------------- */
 static int64_t ncells_of(const po_ctx* w) {
@@ -1972,7 +2220,9 @@ int po_destroy(po_ctx* w) {
     free(w->w_x1); free(w->w_y1); free(w->w_x2); free(w->w_y2); free(w->w_nx); free(w->w_ny);
     free(w->w_temp); free(w->w_transm); free(w->w_spec); free(w->w_diff); free(w->w_porous); free(w->w_react);
     free(w->xcoord); free(w->ycoord);
-    free(w->e_field); free(w->b_field); free(w->surface_charge); free(w->script); free(w->gavg); free(w->gcum1); free(w->gcum2);
+    free(w->e_field); free(w->b_field); free(w->surface_charge); free(w->spwt); free(w->mix_off); free(w->mix_sp); free(w->mix_frac); free(w->seed_par); free(w->seed_mix);
+    free(w->vinj_par); free(w->vinj_mix); free(w->emit_par); free(w->emit_int); free(w->emit_nfs);
+    free(w->script); free(w->gavg); free(w->gcum1); free(w->gcum2);
     free(w->p); free(w->bcount); free(w->wcount); free(w->tallies); free(w->npcall);
     free(w);
     return PGPU_OK;

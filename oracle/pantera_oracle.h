@@ -112,6 +112,20 @@ int po_collide(po_ctx* ctx, int32_t tID, int64_t* timestep_coll, int64_t* timest
 int po_mcc_vahedi(po_ctx* ctx, int32_t tID, int64_t* timestep_coll, int64_t* timestep_reac);
 int po_mcc_collisions(po_ctx* ctx, int32_t tID, int64_t* timestep_coll, int64_t* timestep_reac);
 int po_remove_species(po_ctx* ctx, int32_t sp_id);
+int po_set_species_weights(po_ctx* ctx, int ns, const double* spwt);
+int po_set_mixtures(po_ctx* ctx, int nmix, const int32_t* comp_off, const int32_t* comp_sp, const double* comp_molfrac);
+int po_set_initial_particles_tasks(po_ctx* ctx, int n, const int32_t* mix_id, const double* nrho, const double* ux, const double* uy,
+                                   const double* uz, const double* ttrax, const double* ttray, const double* ttraz,
+                                   const double* trot, const double* tvib);
+int po_set_volume_inject_tasks(po_ctx* ctx, int n, const int32_t* mix_id, const double* nrhodot, const double* ux, const double* uy,
+                               const double* uz, const double* ttrax, const double* ttray, const double* ttraz,
+                               const double* trot, const double* tvib);
+int po_set_emit_tasks(po_ctx* ctx, int n, const int32_t* mix_id, const int32_t* ic, const int32_t* iv1, const int32_t* iv2,
+                      const int32_t* iface, const int32_t* nfs_off, const double* nfs, const double* ux, const double* uy,
+                      const double* uz, const double* u_norm, const double* ttra, const double* trot, const double* tvib);
+int po_initial_seed(po_ctx* ctx);
+int po_volume_inject(po_ctx* ctx, int32_t tID);
+int po_boundaries_emit(po_ctx* ctx, int32_t tID);
 int po_grid_avg(po_ctx* ctx);
 int po_grid_reset(po_ctx* ctx);
 int po_get_grid_avg(po_ctx* ctx, int64_t n, double* avg_np, double* avg_vx, double* avg_vy, double* avg_vz, double* avg_ttrx,

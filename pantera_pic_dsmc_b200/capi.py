@@ -366,6 +366,55 @@ class Lib:
     def remove_species(self, sp):
         self._call("remove_species", C.c_int32(sp))
 
+    # -- particle creation -----------------------------------------------------------------
+    def set_species_weights(self, spwt):
+        a = _f64(spwt)
+        self._call("set_species_weights", C.c_int(len(a)), _p(a))
+
+    def set_mixtures(self, mixtures):
+        """mixtures: list of lists of (species id 1-based, molar fraction)."""
+        off, sp, fr = [0], [], []
+        for m in mixtures:
+            for s_id, f in m:
+                sp.append(s_id)
+                fr.append(f)
+            off.append(len(sp))
+        self._call("set_mixtures", C.c_int(len(mixtures)), _p(_i32(off)), _p(_i32(sp if sp else [0])), _p(_f64(fr if fr else [0.0])))
+
+    def _source_tasks(self, name, tasks):
+        g = lambda k, d=0.0: _f64([t.get(k, d) for t in tasks] or [0.0])
+        self._call(name, C.c_int(len(tasks)), _p(_i32([t["mix_id"] for t in tasks] or [0])), _p(g("rate")), _p(g("ux")), _p(g("uy")),
+                   _p(g("uz")), _p(g("ttrax")), _p(g("ttray")), _p(g("ttraz")), _p(g("trot")), _p(g("tvib")))
+
+    def set_initial_particles_tasks(self, tasks):
+        """tasks: dicts mix_id, rate (= NRHO), ux, uy, uz, ttrax, ttray, ttraz, trot, tvib."""
+        self._source_tasks("set_initial_particles_tasks", tasks)
+
+    def set_volume_inject_tasks(self, tasks):
+        """rate = NRHODOT"""
+        self._source_tasks("set_volume_inject_tasks", tasks)
+
+    def set_emit_tasks(self, tasks):
+        """tasks: dicts mix_id, ic, iv1, iv2, iface, nfs (list per component), ux, uy, uz, u_norm, ttra, trot, tvib."""
+        off, nfs = [0], []
+        for t in tasks:
+            nfs += list(t["nfs"])
+            off.append(len(nfs))
+        gi = lambda k, d=1: _i32([t.get(k, d) for t in tasks] or [0])
+        gf = lambda k: _f64([t.get(k, 0.0) for t in tasks] or [0.0])
+        self._call("set_emit_tasks", C.c_int(len(tasks)), _p(gi("mix_id", 0)), _p(gi("ic")), _p(gi("iv1")), _p(gi("iv2")), _p(gi("iface")),
+                   _p(_i32(off)), _p(_f64(nfs or [0.0])), _p(gf("ux")), _p(gf("uy")), _p(gf("uz")), _p(gf("u_norm")), _p(gf("ttra")),
+                   _p(gf("trot")), _p(gf("tvib")))
+
+    def initial_seed(self):
+        self._call("initial_seed")
+
+    def volume_inject(self, tID: int):
+        self._call("volume_inject", C.c_int32(tID))
+
+    def boundaries_emit(self, tID: int):
+        self._call("boundaries_emit", C.c_int32(tID))
+
     def grid_avg(self):
         self._call("grid_avg")
 

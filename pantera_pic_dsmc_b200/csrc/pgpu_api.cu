@@ -157,6 +157,8 @@ extern "C" int pgpu_destroy(pgpu_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     pg_comm_destroy(c);
+    pg_inject_destroy(c);
+    dev_free(c->d_node_coords); dev_free(c->d_cell_solid);
     for (int i = 0; i < S_COUNT; i++)
         if (c->slot[i]) cudaFree(c->slot[i]);
     free_planes(c->planes[0]);
@@ -388,6 +390,11 @@ extern "C" int pgpu_set_mesh(pgpu_ctx* c, int dims, int nn, int nc, const double
     d.nboundcells = face_boundary_index ? nboundcells : 0;
     if ((rc = put(c, S_FACE_BIDX, (const int*)face_boundary_index, face_boundary_index ? (size_t)nf * nc : 0, &d.face_bidx))) return rc;
     if ((rc = put(c, S_BOUND_AREA, boundary_area, (size_t)d.nboundcells, &d.bound_area))) return rc;
+    dev_free(c->d_node_coords);
+    if ((rc = dev_alloc(c, &c->d_node_coords, 3 * (size_t)nn))) return rc;
+    PG_CUDA(c, cudaMemcpy(c->d_node_coords, node_coords, sizeof(double) * 3 * (size_t)nn, cudaMemcpyHostToDevice));
+    c->volume_total = 0;
+    for (int i = 0; i < nc; i++) c->volume_total += cell_volumes[i];
     dev_free(c->d_surface_charge);
     if ((rc = dev_alloc(c, &c->d_surface_charge, (size_t)nn))) return rc;
     PG_CUDA(c, cudaMemset(c->d_surface_charge, 0, sizeof(double) * (size_t)nn));
@@ -626,6 +633,20 @@ static int build_packed_mesh(pgpu_ctx* c) {
         if ((rc = put(c, S_FACE_GEO, (const double*)nullptr, 0, &c->dev.face_geo))) return rc;
     }
     if ((rc = put(c, S_FACE_CODE, code.data(), code.size(), &c->dev.face_code))) return rc;
+    /* cells of a SOLID volume group: INITIAL_SEED skips them (src/initialization.f90:2072-2074) */
+    dev_free(c->d_cell_solid);
+    if (!c->h_cell_pg.empty()) {
+        std::vector<unsigned char> solid((size_t)nc, 0);
+        bool any = false;
+        for (int ic = 0; ic < nc; ic++) {
+            int pg = c->h_cell_pg[ic];
+            if (pg != -1 && pg >= 1 && pg <= nbc && c->h_bc_volume[pg - 1] == PGPU_SOLID) { solid[ic] = 1; any = true; }
+        }
+        if (any) {
+            if ((rc = dev_alloc(c, &c->d_cell_solid, (size_t)nc))) return rc;
+            PG_CUDA(c, cudaMemcpy(c->d_cell_solid, solid.data(), (size_t)nc, cudaMemcpyHostToDevice));
+        }
+    }
     c->mesh_dirty = false;
     return PGPU_OK;
 }
@@ -967,14 +988,20 @@ extern "C" int pgpu_upload_particles(pgpu_ctx* c, const void* aos, int64_t n, in
     return append_impl(c, aos, n, stride, "pgpu_upload_particles");
 }
 
+int pg_fill_dtrim(pgpu_ctx* c) {
+    cudaSetDevice(c->device);
+    if (c->np > 0) fill_f64_kernel<<<(unsigned int)((c->np + 255) / 256), 256, 0, c->stream>>>(c->planes[c->cur].dtrim, c->np, c->cfg.dt);
+    PG_CUDA(c, cudaGetLastError());
+    return PGPU_OK;
+}
+
 extern "C" int pgpu_append_particles(pgpu_ctx* c, const void* aos, int64_t n, int32_t stride) {
     if (!c) return PGPU_ERR_INVALID;
     if (n > 0 && c->np > 0 && !c->has_dtrim) {
         /* the DTRIM plane is not maintained while every particle has DTRIM == DT: rebuild it so that the
          * appended particles (DTRIM = rf()*DT after an injection, ref: src/timecycle.f90:463) can differ */
-        cudaSetDevice(c->device);
-        fill_f64_kernel<<<(unsigned int)((c->np + 255) / 256), 256, 0, c->stream>>>(c->planes[c->cur].dtrim, c->np, c->cfg.dt);
-        PG_CUDA(c, cudaGetLastError());
+        int rc0;
+        if ((rc0 = pg_fill_dtrim(c))) return rc0;
         c->has_dtrim = true;
     }
     return append_impl(c, aos, n, stride, "pgpu_append_particles");

@@ -371,6 +371,12 @@ struct pgpu_ctx {
     double* d_surface_charge;
     long long nsc;
 
+    /* injection (pgpu_inject.cu) */
+    void* inject = nullptr;
+    double* d_node_coords = nullptr;     /* [nn][3] */
+    unsigned char* d_cell_solid = nullptr; /* [nc] cells of a SOLID volume group */
+    double volume_total = 0;             /* sum of CELL_VOLUMES */
+
     /* GRID_AVG running averages (pgpu_sample.cu) */
     double* d_gavg = nullptr;
     unsigned int* d_gavg_np = nullptr;
@@ -432,6 +438,8 @@ int pg_collide_impl(pgpu_ctx* c, int tID, bool big_now = true); /* CELL path (as
 int pg_collide_big(pgpu_ctx* c);             /* GLOBAL path for the oversized cells + end of a deferred vel reorder */
 int pg_exchange_impl(pgpu_ctx* c);
 void pg_refresh_dev(pgpu_ctx* c);
+int pg_fill_dtrim(pgpu_ctx* c);               /* DTRIM plane = DT for the particles in the store */
+void pg_inject_destroy(pgpu_ctx* c);
 
 static inline int pg_ncells(const pgpu_ctx* c) {
     return (c->cfg.grid_type == PGPU_UNSTRUCTURED) ? c->nc : c->cfg.nx * c->cfg.ny;

@@ -343,6 +343,63 @@ def c4_ccp_1d(ncells: int = 64, n_per_species: int = 20_000, seed: int = 5, leng
 
 
 # ------------------------------------------------------------------------------------------------
+# injection tasks (host side of SURVEY 8(f) row 1): what READINPUT + INITINJECTION leave in EMIT_TASKS
+# ------------------------------------------------------------------------------------------------
+_FACE_IND = ((1, 3, 2), (1, 2, 4), (2, 3, 4), (1, 4, 3))   # src/grid_and_partition.f90:1932-1935
+
+
+def erf1(x: float) -> float:
+    """ERF1, src/tools.f90:1126-1143 (Abramowitz-Stegun 7.1.26 with single-precision literals)."""
+    f = lambda v: float(np.float32(v))
+    p, a1, a2, a3, a4, a5 = f(0.3275911), f(0.254829592), f(-0.284496736), f(1.421413741), f(-1.453152027), f(1.061405429)
+    t = 1.0 / (1.0 + p * abs(x))
+    out = 1 - (a1 * t + a2 * t ** 2 + a3 * t ** 3 + a4 * t ** 4 + a5 * t ** 5) * np.exp(-x ** 2)
+    return float(np.copysign(out, x))
+
+
+def emit_tasks_for_group(mesh: mg.Mesh, cfg, species: df.SpeciesTable, mixture, pg: int, nrho: float, u=(0.0, 0.0, 0.0),
+                         ttra: float = 300.0, trot: float = 300.0, tvib: float = 300.0, mix_id: int = 0, nranks: int = 1):
+    """One EMIT task per boundary face of physical group `pg`, with NFS per mixture component as INITINJECTION
+    computes it (src/initialization.f90:2575-2675): Maxwellian flux through the face x area x DT / FNUM / ranks.
+    mixture: list of (species id 1-based, molar fraction)."""
+    d = mesh.dims
+    fpg = np.asarray(mesh.cell_faces_pg)
+    nb = np.asarray(mesh.cell_neighbors)
+    cn = np.asarray(mesh.cell_nodes)
+    xyz = np.asarray(mesh.node_coords)
+    fn = np.asarray(mesh.face_normal)
+    tasks = []
+    faces, cells = np.nonzero((fpg == pg) & (nb == -1))
+    for j, ic0 in zip(faces, cells):
+        normal = -fn[:, j, ic0]
+        iv1 = iv2 = 1
+        if d == 1:
+            area = (cfg.ymax - cfg.ymin) * (cfg.zmax - cfg.zmin)
+            iv1 = iv2 = int(cn[j, ic0])
+        elif d == 2:
+            iv1, iv2 = int(cn[j, ic0]), int(cn[(j + 1) % 3, ic0])     # edge j joins local nodes j, j+1
+            x1, y1, x2, y2 = xyz[0, iv1 - 1], xyz[1, iv1 - 1], xyz[0, iv2 - 1], xyz[1, iv2 - 1]
+            length = np.sqrt((x2 - x1) ** 2 + (y2 - y1) ** 2)
+            area = (cfg.zmax - cfg.zmin) * 0.5 * (y1 + y2) * length if cfg.axi else length * (cfg.zmax - cfg.zmin)
+        else:
+            area = float(np.asarray(mesh.face_area)[j, ic0])
+        u_norm = u[0] * normal[0] + u[1] * normal[1] + u[2] * normal[2]
+        nfs = []
+        for s_id, frac in mixture:
+            m = species.mass[s_id - 1]
+            if ttra == 0:
+                flux = nrho * frac * u_norm
+            else:
+                beta = 1.0 / np.sqrt(2.0 * KB / m * ttra)
+                sn = u_norm * beta
+                flux = nrho * frac / (beta * 2.0 * np.sqrt(np.pi)) * (np.exp(-sn ** 2) + np.sqrt(np.pi) * sn * (1.0 + erf1(sn)))
+            nfs.append(flux * area * cfg.dt / cfg.fnum / float(nranks))
+        tasks.append(dict(mix_id=mix_id, ic=int(ic0) + 1, iv1=iv1, iv2=iv2, iface=int(j) + 1, nfs=nfs, ux=u[0], uy=u[1], uz=u[2],
+                          u_norm=float(u_norm), ttra=ttra, trot=trot, tvib=tvib))
+    return tasks
+
+
+# ------------------------------------------------------------------------------------------------
 # bench-scale C5: one x-strip per rank, particles generated in chunks straight into (pinned) AoS records
 # ------------------------------------------------------------------------------------------------
 _PINNED_KEEPALIVE = []
