@@ -269,6 +269,19 @@ int pgpu_initial_seed(pgpu_ctx* ctx);
 int pgpu_volume_inject(pgpu_ctx* ctx, int32_t tID);
 int pgpu_boundaries_emit(pgpu_ctx* ctx, int32_t tID);
 
+/* ---- field step on the device ---------------------------------------- */
+/* GRID_BC(:)%WALL_POTENTIAL, %WALL_RF_POTENTIAL, %RF_FREQUENCY, %WALL_EFIELD, %EPS_REL (src/global.f90:225-233), one
+ * entry per physical group as in pgpu_set_bcs; NULL arrays mean 0 (EPS_REL: 1) */
+int pgpu_set_field_bcs(pgpu_ctx* ctx, int nbc, const double* wall_potential, const double* wall_rf_potential,
+                       const double* rf_frequency, const double* wall_efield, const double* eps_rel);
+/* COMPUTE_E_FIELD (src/fields.f90:5237-5296) on an unstructured mesh from the host's PHI_FIELD(NNODES): the PETSc solve
+ * stays on the host, only phi comes down; E_FIELD(3,1,NCELLS) becomes the field of the next ADVECT (e_host optional) */
+int pgpu_compute_e_field(pgpu_ctx* ctx, const double* phi_host, int64_t nnodes, double* e_host);
+/* 1-D line meshes: SET_WALL_POTENTIAL (src/fields.f90:5566-5607) + the Poisson system of ASSEMBLE_POISSON
+ * (:137-253, 758-760) with the right-hand side rows of DEPOSIT_CHARGE (:5538-5561) + COMPUTE_E_FIELD, all on the
+ * device.  rhs_host == NULL uses the RHS of the last pgpu_deposit_charge.  phi_host, e_host optional outputs. */
+int pgpu_field_solve_1d(pgpu_ctx* ctx, int32_t tID, const double* rhs_host, double* phi_host, double* e_host);
+
 /* ---- dump / restart -------------------------------------------------- */
 /* DUMP_PARTICLES_FILE (src/tools.f90:327-365) / READ_PARTICLES_FILE (src/tools.f90:465-517): the file
  * <path_prefix>proc_<rank:05d>_time_<timestep:08d> in the reference's binary layout (Fortran sequential unformatted,

@@ -112,6 +112,8 @@ struct po_ctx {
     double* vinj_par; int* vinj_mix;
     double* emit_par; int* emit_int;   /* [n][7]: UX, UY, UZ, U_NORM, TTRA, TROT, TVIB; [n][6]: MIX_ID, IC, IV1, IV2, IFACE, nfs offset */
     double* emit_nfs;
+    /* field boundary parameters (GRID_BC%WALL_POTENTIAL, ...) */
+    double *fb_pot, *fb_rfpot, *fb_freq, *fb_efield, *fb_eps;
     /* GRID_AVG running averages */
     double* gavg;   /* [9][nbins]: NP, VX, VY, VZ, TTRX, TTRY, TTRZ, TROT, TVIB */
     int *gcum1, *gcum2;
@@ -2028,6 +2030,119 @@ int po_set_emit_tasks(po_ctx* w, int n, const int32_t* mix_id, const int32_t* ic
 }
 
 /* ------------------------------------------------------------------------------------------
+ * Field step: ASSEMBLE_POISSON for 1-D line meshes (src/fields.f90:137-253, 758-760), SET_WALL_POTENTIAL (:5566-5607),
+ * the right-hand side rows of DEPOSIT_CHARGE (:5538-5561), COMPUTE_E_FIELD (:5237-5296).  The reference solves with
+ * PETSc's KSP; here the assembled matrix (dense, MatSetValue semantics) is solved by Gaussian elimination with partial
+ * pivoting -- deliberately not the device's tridiagonal sweep.
+ * ---------------------------------------------------------------------------------------- */
+int po_set_field_bcs(po_ctx* w, int nbc, const double* wall_potential, const double* wall_rf_potential, const double* rf_frequency,
+                     const double* wall_efield, const double* eps_rel) {
+    double** dst[5] = {&w->fb_pot, &w->fb_rfpot, &w->fb_freq, &w->fb_efield, &w->fb_eps};
+    const double* src[5] = {wall_potential, wall_rf_potential, rf_frequency, wall_efield, eps_rel};
+    for (int k = 0; k < 5; k++) {
+        free(*dst[k]);
+        *dst[k] = (double*)calloc((size_t)(nbc > 0 ? nbc : 1), sizeof(double));
+        for (int i = 0; i < nbc; i++) (*dst[k])[i] = src[k] ? src[k][i] : (k == 4 ? 1.0 : 0.0);
+    }
+    return PGPU_OK;
+}
+static void compute_e_field(const po_ctx* w, const double* phi, double* e) {
+    const int d = w->dims_mesh, nf = d + 1;
+    for (int i = 0; i < w->nc; i++) {
+        double ev[3] = {0, 0, 0};
+        for (int id = 0; id < d; id++)
+            for (int p = 0; p < nf; p++) {
+                int vp = w->cell_nodes[nf * i + p];
+                ev[id] = ev[id] - phi[vp - 1] * w->basis_coeffs[(size_t)nf * nf * i + nf * p + id];
+            }
+        e[3 * i] = ev[0]; e[3 * i + 1] = ev[1]; e[3 * i + 2] = ev[2];
+    }
+}
+int po_compute_e_field(po_ctx* w, const double* phi, int64_t nnodes, double* e_out) {
+    if (w->c.grid_type != PGPU_UNSTRUCTURED || !w->basis_coeffs) FAIL(w, PGPU_ERR_STATE, "po_compute_e_field: unstructured mesh with BASIS_COEFFS needed");
+    if (nnodes < w->nn) FAIL(w, PGPU_ERR_INVALID, "po_compute_e_field: phi too short");
+    double* e = (double*)calloc((size_t)(3 * w->nc), sizeof(double));
+    compute_e_field(w, phi, e);
+    REPL(w->e_field, e, 3 * w->nc);
+    w->ne = 3 * w->nc;
+    if (e_out) memcpy(e_out, e, sizeof(double) * (size_t)(3 * w->nc));
+    free(e);
+    return PGPU_OK;
+}
+int po_field_solve_1d(po_ctx* w, int32_t tID, const double* rhs, double* phi_out, double* e_out) {
+    if (w->c.grid_type != PGPU_UNSTRUCTURED || w->dims_mesh != 1) FAIL(w, PGPU_ERR_UNSUPPORTED, "po_field_solve_1d: 1-D meshes only");
+    if (!rhs) FAIL(w, PGPU_ERR_INVALID, "po_field_solve_1d: the oracle needs the RHS passed in");
+    const int nn = w->nn, nc = w->nc;
+    double* A = (double*)calloc((size_t)nn * nn, sizeof(double));
+    double* b = (double*)calloc((size_t)nn, sizeof(double));
+    double* dir = (double*)calloc((size_t)nn, sizeof(double));
+    double* neu = (double*)calloc((size_t)nn, sizeof(double));
+    char* isd = (char*)calloc((size_t)nn, 1);
+    char* isn = (char*)calloc((size_t)nn, 1);
+    for (int i = 0; i < nc; i++) /* :143-176 with SET_WALL_POTENTIAL's time-dependent value */
+        for (int j = 0; j < 2; j++) {
+            int pg = w->cell_faces_pg[2 * i + j];
+            if (pg == -1) continue;
+            int fbc = w->bc_field[pg - 1], v = w->cell_nodes[2 * i + j] - 1;
+            if (fbc == PGPU_DIRICHLET_BC || fbc == PGPU_RF_VOLTAGE_BC || fbc == PGPU_DECOUPLED_RF_VOLTAGE_BC) {
+                double pot = w->fb_pot ? w->fb_pot[pg - 1] : 0.0;
+                if (fbc != PGPU_DIRICHLET_BC)
+                    pot = (w->fb_pot ? w->fb_pot[pg - 1] : 0.0) + 0.5 * (w->fb_rfpot ? w->fb_rfpot[pg - 1] : 0.0) * cos(2 * PI * (w->fb_freq ? w->fb_freq[pg - 1] : 0.0) * tID * w->c.dt);
+                dir[v] = pot;
+                isd[v] = 1;
+            }
+            if (fbc == PGPU_NEUMANN_BC) isn[v] = 1;
+        }
+    for (int i = 0; i < nc; i++) { /* :198-251 */
+        double eps_rel = 1.0;
+        if (w->cell_pg && w->cell_pg[i] != -1 && w->fb_eps) eps_rel = w->fb_eps[w->cell_pg[i] - 1];
+        int v1 = w->cell_nodes[2 * i] - 1, v2 = w->cell_nodes[2 * i + 1] - 1;
+        double length = fabs(w->node_coords[3 * v2] - w->node_coords[3 * v1]);
+        double k11 = 1.0 / length * eps_rel, k22 = 1.0 / length * eps_rel, k12 = -1.0 / length * eps_rel;
+        if (!isd[v1]) { A[(size_t)v1 * nn + v1] += k11; A[(size_t)v1 * nn + v2] += k12; }
+        if (!isd[v2]) { A[(size_t)v2 * nn + v1] += k12; A[(size_t)v2 * nn + v2] += k22; }
+        for (int j = 0; j < 2; j++) {
+            int pg = w->cell_faces_pg[2 * i + j];
+            if (pg == -1) continue;
+            if (w->bc_field[pg - 1] == PGPU_NEUMANN_BC) {
+                int v = j == 0 ? v1 : v2;
+                if (!isd[v]) neu[v] = neu[v] + (w->fb_efield ? w->fb_efield[pg - 1] : 0.0);
+            }
+        }
+    }
+    for (int v = 0; v < nn; v++) { /* :758-760 and :5538-5547 */
+        if (isd[v]) { for (int k = 0; k < nn; k++) A[(size_t)v * nn + k] = 0; A[(size_t)v * nn + v] = 1.0; b[v] = dir[v]; }
+        else if (isn[v]) b[v] = rhs[v] + neu[v];
+        else b[v] = rhs[v];
+    }
+    for (int k = 0; k < nn; k++) { /* Gaussian elimination, partial pivoting */
+        int piv = k;
+        for (int r = k + 1; r < nn; r++)
+            if (fabs(A[(size_t)r * nn + k]) > fabs(A[(size_t)piv * nn + k])) piv = r;
+        if (A[(size_t)piv * nn + k] == 0.0) { free(A); free(b); free(dir); free(neu); free(isd); free(isn); FAIL(w, PGPU_ERR_INVALID, "po_field_solve_1d: singular system"); }
+        if (piv != k) {
+            for (int cidx = 0; cidx < nn; cidx++) { double t = A[(size_t)k * nn + cidx]; A[(size_t)k * nn + cidx] = A[(size_t)piv * nn + cidx]; A[(size_t)piv * nn + cidx] = t; }
+            double t = b[k]; b[k] = b[piv]; b[piv] = t;
+        }
+        for (int r = k + 1; r < nn; r++) {
+            double m = A[(size_t)r * nn + k] / A[(size_t)k * nn + k];
+            if (m == 0.0) continue;
+            for (int cidx = k; cidx < nn; cidx++) A[(size_t)r * nn + cidx] -= m * A[(size_t)k * nn + cidx];
+            b[r] -= m * b[k];
+        }
+    }
+    for (int k = nn - 1; k >= 0; k--) {
+        double sum = b[k];
+        for (int cidx = k + 1; cidx < nn; cidx++) sum -= A[(size_t)k * nn + cidx] * b[cidx];
+        b[k] = sum / A[(size_t)k * nn + k];
+    }
+    if (phi_out) memcpy(phi_out, b, sizeof(double) * (size_t)nn);
+    int rc = po_compute_e_field(w, b, nn, e_out);
+    free(A); free(b); free(dir); free(neu); free(isd); free(isn);
+    return rc;
+}
+
+/* ------------------------------------------------------------------------------------------
  * GRID_AVG / GRID_RESET / CHECKS. ref: src/postprocess.f90:34-416 (BOOL_DUMP_MOMENTS = .FALSE.), :1070-1094, :1722-1800
  * ---------------------------------------------------------------------------------------- */
 static int64_t ncells_of(const po_ctx* w) {
@@ -2222,6 +2337,7 @@ int po_destroy(po_ctx* w) {
     free(w->xcoord); free(w->ycoord);
     free(w->e_field); free(w->b_field); free(w->surface_charge); free(w->spwt); free(w->mix_off); free(w->mix_sp); free(w->mix_frac); free(w->seed_par); free(w->seed_mix);
     free(w->vinj_par); free(w->vinj_mix); free(w->emit_par); free(w->emit_int); free(w->emit_nfs);
+    free(w->fb_pot); free(w->fb_rfpot); free(w->fb_freq); free(w->fb_efield); free(w->fb_eps);
     free(w->script); free(w->gavg); free(w->gcum1); free(w->gcum2);
     free(w->p); free(w->bcount); free(w->wcount); free(w->tallies); free(w->npcall);
     free(w);

@@ -126,6 +126,10 @@ int po_set_emit_tasks(po_ctx* ctx, int n, const int32_t* mix_id, const int32_t* 
 int po_initial_seed(po_ctx* ctx);
 int po_volume_inject(po_ctx* ctx, int32_t tID);
 int po_boundaries_emit(po_ctx* ctx, int32_t tID);
+int po_set_field_bcs(po_ctx* ctx, int nbc, const double* wall_potential, const double* wall_rf_potential, const double* rf_frequency,
+                     const double* wall_efield, const double* eps_rel);
+int po_compute_e_field(po_ctx* ctx, const double* phi, int64_t nnodes, double* e_out);
+int po_field_solve_1d(po_ctx* ctx, int32_t tID, const double* rhs, double* phi_out, double* e_out);
 int po_grid_avg(po_ctx* ctx);
 int po_grid_reset(po_ctx* ctx);
 int po_get_grid_avg(po_ctx* ctx, int64_t n, double* avg_np, double* avg_vx, double* avg_vy, double* avg_vz, double* avg_ttrx,

@@ -28,6 +28,7 @@ ORACLE_LIB_PATH = os.path.join(REPO_ROOT, "oracle", "_build", "liboracle.so")
 RECTILINEAR_UNIFORM, RECTILINEAR_NONUNIFORM, QUADTREE, UNSTRUCTURED = 0, 1, 2, 3
 VACUUM, SPECULAR, DIFFUSE, CLL, REACT, AXIS, PERIODIC_MASTER, PERIODIC_SLAVE, EMIT, WB_BC = range(10)
 DIRICHLET_BC, NEUMANN_BC, DIELECTRIC_BC, ROBIN_BC = 0, 1, 2, 3
+RF_VOLTAGE_BC, DECOUPLED_RF_VOLTAGE_BC = 6, 7
 NO_BC = 8
 FLUID, SOLID = 0, 1
 PIC_NONE, PIC_EXPLICIT = 0, 1
@@ -414,6 +415,24 @@ class Lib:
 
     def boundaries_emit(self, tID: int):
         self._call("boundaries_emit", C.c_int32(tID))
+
+    # -- field step ------------------------------------------------------------------------
+    def set_field_bcs(self, wall_potential=None, wall_rf_potential=None, rf_frequency=None, wall_efield=None, eps_rel=None):
+        arrs = [wall_potential, wall_rf_potential, rf_frequency, wall_efield, eps_rel]
+        n = max(len(a) for a in arrs if a is not None)
+        self._call("set_field_bcs", C.c_int(n), *[_p(_f64(a)) if a is not None else None for a in arrs])
+
+    def compute_e_field(self, phi, ncells):
+        phi = _f64(phi)
+        e = np.zeros(3 * ncells)
+        self._call("compute_e_field", _p(phi), C.c_int64(len(phi)), _p(e))
+        return e.reshape(ncells, 3).T
+
+    def field_solve_1d(self, tID, nnodes, ncells, rhs=None):
+        phi, e = np.zeros(nnodes), np.zeros(3 * ncells)
+        r = _f64(rhs) if rhs is not None else None
+        self._call("field_solve_1d", C.c_int32(tID), _p(r), _p(phi), _p(e))
+        return phi, e.reshape(ncells, 3).T
 
     def grid_avg(self):
         self._call("grid_avg")

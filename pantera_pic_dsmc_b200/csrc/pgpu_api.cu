@@ -158,6 +158,7 @@ extern "C" int pgpu_destroy(pgpu_ctx* c) {
     cudaStreamSynchronize(c->stream);
     pg_comm_destroy(c);
     pg_inject_destroy(c);
+    pg_field_destroy(c);
     dev_free(c->d_node_coords); dev_free(c->d_cell_solid);
     for (int i = 0; i < S_COUNT; i++)
         if (c->slot[i]) cudaFree(c->slot[i]);
@@ -496,6 +497,12 @@ extern "C" int pgpu_set_efield(pgpu_ctx* c, const double* e, int64_t n) {
     if (!c) return PGPU_ERR_INVALID;
     cudaSetDevice(c->device);
     return put(c, S_EFIELD, e, (size_t)std::max<int64_t>(n, 0), &c->dev.e_field);
+}
+int pg_adopt_efield(pgpu_ctx* c, double* d_e) {
+    if (c->slot[S_EFIELD]) cudaFree(c->slot[S_EFIELD]);
+    c->slot[S_EFIELD] = d_e;
+    c->dev.e_field = d_e;
+    return PGPU_OK;
 }
 extern "C" int pgpu_set_bfield(pgpu_ctx* c, const double* b, int64_t n) {
     if (!c) return PGPU_ERR_INVALID;

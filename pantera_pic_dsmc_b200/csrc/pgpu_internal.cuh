@@ -371,8 +371,9 @@ struct pgpu_ctx {
     double* d_surface_charge;
     long long nsc;
 
-    /* injection (pgpu_inject.cu) */
+    /* injection (pgpu_inject.cu), field step (pgpu_field.cu) */
     void* inject = nullptr;
+    void* field = nullptr;
     double* d_node_coords = nullptr;     /* [nn][3] */
     unsigned char* d_cell_solid = nullptr; /* [nc] cells of a SOLID volume group */
     double volume_total = 0;             /* sum of CELL_VOLUMES */
@@ -440,6 +441,8 @@ int pg_exchange_impl(pgpu_ctx* c);
 void pg_refresh_dev(pgpu_ctx* c);
 int pg_fill_dtrim(pgpu_ctx* c);               /* DTRIM plane = DT for the particles in the store */
 void pg_inject_destroy(pgpu_ctx* c);
+void pg_field_destroy(pgpu_ctx* c);
+int pg_adopt_efield(pgpu_ctx* c, double* d_e); /* a device array becomes E_FIELD (owned by the context from then on) */
 
 static inline int pg_ncells(const pgpu_ctx* c) {
     return (c->cfg.grid_type == PGPU_UNSTRUCTURED) ? c->nc : c->cfg.nx * c->cfg.ny;
