@@ -200,6 +200,16 @@ int pgpu_set_bfield(pgpu_ctx* ctx, const double* b_field, int64_t n);
 int pgpu_get_surface_charge(pgpu_ctx* ctx, double* sc, int64_t n);
 int pgpu_set_surface_charge(pgpu_ctx* ctx, const double* sc, int64_t n);
 
+/* Record-plane transfers: the particle state in the device's own layout -- a plane of 32-byte position records
+ * and a plane of 32-byte velocity records (+ optionally a plane of {EROT, EVIB}) -- so that an upload / download is
+ * plain copies at PCIe speed: 64 (80) bytes per particle instead of the 96-byte AoS record.  ID, DUMP_TRAJ and DTRIM
+ * (= DT) stay on the host side.  Semantics of upload / download as pgpu_upload_particles / pgpu_download_particles. */
+typedef struct pgpu_pos_record { double X, Y, Z; int32_t IC, S_ID; } pgpu_pos_record;      /* 32 bytes */
+typedef struct pgpu_vel_record { double VX, VY, VZ; int32_t S_ID, pad_; } pgpu_vel_record; /* 32 bytes */
+typedef struct pgpu_ie_record { double EROT, EVIB; } pgpu_ie_record;                       /* 16 bytes */
+int pgpu_upload_planes(pgpu_ctx* ctx, const void* pos, const void* vel, const void* ie_or_null, int64_t n);
+int pgpu_download_planes(pgpu_ctx* ctx, void* pos, void* vel, void* ie_or_null, int64_t capacity, int64_t* n);
+
 /* ---- the hot path ---------------------------------------------------------------------- */
 /* DEPOSIT_CHARGE particle loop + SURFACE_CHARGE + reduction over ranks (src/fields.f90:5440-5535).
  * rhs_host(0:NNODES-1) receives the all-reduced RHS; the Dirichlet/Neumann row fill and the

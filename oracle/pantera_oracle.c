@@ -2547,6 +2547,39 @@ int po_download_particles(po_ctx* w, void* aos, int64_t capacity, int64_t* n, in
 }
 
 int po_num_particles(po_ctx* w, int64_t* n) { *n = w->np; return PGPU_OK; }
+/* record-plane transfers (see pantera_gpu.h): the oracle keeps AoS records, so these are plain transpositions */
+int po_upload_planes(po_ctx* w, const void* pos, const void* vel, const void* ie, int64_t n) {
+    const pgpu_pos_record* P = (const pgpu_pos_record*)pos;
+    const pgpu_vel_record* V = (const pgpu_vel_record*)vel;
+    const pgpu_ie_record* E = (const pgpu_ie_record*)ie;
+    reserve(w, n);
+    for (int64_t i = 0; i < n; i++) {
+        part_t* q = &w->p[i];
+        memset(q, 0, sizeof(*q));
+        q->X = P[i].X; q->Y = P[i].Y; q->Z = P[i].Z; q->IC = P[i].IC; q->S_ID = P[i].S_ID;
+        q->VX = V[i].VX; q->VY = V[i].VY; q->VZ = V[i].VZ;
+        if (E) { q->EROT = E[i].EROT; q->EVIB = E[i].EVIB; }
+        q->DTRIM = w->c.dt;
+        q->ID = (int64_t)w->c.rank + (i << 8);
+    }
+    w->np = n;
+    w->id_counter = n;
+    return PGPU_OK;
+}
+int po_download_planes(po_ctx* w, void* pos, void* vel, void* ie, int64_t capacity, int64_t* n) {
+    if (capacity < w->np) FAIL(w, PGPU_ERR_INVALID, "po_download_planes: capacity too small");
+    pgpu_pos_record* P = (pgpu_pos_record*)pos;
+    pgpu_vel_record* V = (pgpu_vel_record*)vel;
+    pgpu_ie_record* E = (pgpu_ie_record*)ie;
+    for (int64_t i = 0; i < w->np; i++) {
+        const part_t* q = &w->p[i];
+        P[i].X = q->X; P[i].Y = q->Y; P[i].Z = q->Z; P[i].IC = q->IC; P[i].S_ID = q->S_ID;
+        V[i].VX = q->VX; V[i].VY = q->VY; V[i].VZ = q->VZ; V[i].S_ID = q->S_ID; V[i].pad_ = 0;
+        if (E) { E[i].EROT = q->EROT; E[i].EVIB = q->EVIB; }
+    }
+    if (n) *n = w->np;
+    return PGPU_OK;
+}
 
 int po_set_efield(po_ctx* w, const double* e, int64_t n) { REPL(w->e_field, e, n); w->ne = n; return PGPU_OK; }
 int po_set_bfield(po_ctx* w, const double* b, int64_t n) { REPL(w->b_field, b, n); w->nb = n; return PGPU_OK; }

@@ -94,6 +94,8 @@ int po_upload_particles(po_ctx* ctx, const void* aos, int64_t n, int32_t stride_
 int po_download_particles(po_ctx* ctx, void* aos, int64_t capacity, int64_t* n, int32_t stride_bytes);
 int po_append_particles(po_ctx* ctx, const void* aos, int64_t n, int32_t stride_bytes);
 int po_num_particles(po_ctx* ctx, int64_t* n);
+int po_upload_planes(po_ctx* ctx, const void* pos, const void* vel, const void* ie_or_null, int64_t n);
+int po_download_planes(po_ctx* ctx, void* pos, void* vel, void* ie_or_null, int64_t capacity, int64_t* n);
 
 int po_set_efield(po_ctx* ctx, const double* e_field, int64_t n);
 int po_set_bfield(po_ctx* ctx, const double* b_field, int64_t n);

@@ -46,6 +46,25 @@ PARTICLE_DTYPE = np.dtype(
 )
 
 
+POS_DTYPE = np.dtype({"names": ["X", "Y", "Z", "IC", "S_ID"], "formats": ["<f8", "<f8", "<f8", "<i4", "<i4"], "offsets": [0, 8, 16, 24, 28], "itemsize": 32})
+VEL_DTYPE = np.dtype({"names": ["VX", "VY", "VZ", "S_ID", "pad_"], "formats": ["<f8", "<f8", "<f8", "<i4", "<i4"], "offsets": [0, 8, 16, 24, 28], "itemsize": 32})
+IE_DTYPE = np.dtype({"names": ["EROT", "EVIB"], "formats": ["<f8", "<f8"], "offsets": [0, 8], "itemsize": 16})
+
+
+def to_planes(parts: np.ndarray, pos=None, vel=None):
+    """AoS records -> (pos, vel, ie) record planes (host-side helper of the harness)."""
+    n = len(parts)
+    pos = np.zeros(n, dtype=POS_DTYPE) if pos is None else pos[:n]
+    vel = np.zeros(n, dtype=VEL_DTYPE) if vel is None else vel[:n]
+    ie = np.zeros(n, dtype=IE_DTYPE)
+    for f in ("X", "Y", "Z", "IC", "S_ID"):
+        pos[f] = parts[f]
+    for f in ("VX", "VY", "VZ", "S_ID"):
+        vel[f] = parts[f]
+    ie["EROT"], ie["EVIB"] = parts["EROT"], parts["EVIB"]
+    return pos, vel, ie
+
+
 class Config(C.Structure):
     """``pgpu_config`` -- scalar globals read by the hot path."""
 
@@ -307,6 +326,16 @@ class Lib:
         assert out.dtype == PARTICLE_DTYPE and out.flags["C_CONTIGUOUS"]
         nn = C.c_int64()
         self._call("download_particles", _p(out), C.c_int64(len(out)), C.byref(nn), C.c_int32(96))
+        return nn.value
+
+    # -- record planes (device layout on the host) ------------------------------------------
+    def upload_planes(self, pos: np.ndarray, vel: np.ndarray, ie: Optional[np.ndarray] = None):
+        assert pos.dtype == POS_DTYPE and vel.dtype == VEL_DTYPE and len(pos) == len(vel)
+        self._call("upload_planes", _p(pos), _p(vel), _p(ie) if ie is not None else None, C.c_int64(len(pos)))
+
+    def download_planes_into(self, pos: np.ndarray, vel: np.ndarray, ie: Optional[np.ndarray] = None) -> int:
+        nn = C.c_int64()
+        self._call("download_planes", _p(pos), _p(vel), _p(ie) if ie is not None else None, C.c_int64(len(pos)), C.byref(nn))
         return nn.value
 
     # -- fields -----------------------------------------------------------------------------

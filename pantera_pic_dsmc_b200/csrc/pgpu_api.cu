@@ -1014,6 +1014,84 @@ extern "C" int pgpu_append_particles(pgpu_ctx* c, const void* aos, int64_t n, in
     return append_impl(c, aos, n, stride, "pgpu_append_particles");
 }
 
+/* ------------------------------------------------------------------------------------------
+ * record-plane transfers: the host keeps the particle state in the device's own layout (two planes of 32-byte records,
+ * pgpu_pos_record / pgpu_vel_record in pantera_gpu.h, + an optional 16-byte internal-energy plane), so an upload or a
+ * download is two or three plain copies at PCIe speed -- 64 bytes per particle instead of the 96-byte AoS record plus
+ * a staging transposition.  ID, DUMP_TRAJ and DTRIM (= DT outside an injection step) stay with the host, as SURVEY
+ * 8(d) counts them.
+ * ---------------------------------------------------------------------------------------- */
+__global__ void __launch_bounds__(256) planes_check_kernel(const PgPos* __restrict__ pos, const PgIe* __restrict__ ie, long long n, int ncells,
+                                                           PgStatus* st) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int ic = pos[i].ic;
+    if (ncells > 0 && (ic < 1 || ic > ncells)) atomicCAS(&st->err, 0, PG_DEVERR_CELL_RANGE);
+    if (ie) {
+        const PgIe E = ie[i];
+        if (E.erot != 0. || E.evib != 0.) st->flag_ie = 1;
+    }
+}
+
+extern "C" int pgpu_upload_planes(pgpu_ctx* c, const void* pos, const void* vel, const void* ie, int64_t n) {
+    if (!c) return PGPU_ERR_INVALID;
+    if (n < 0 || (n > 0 && (!pos || !vel))) PG_FAIL(c, PGPU_ERR_INVALID, "upload_planes: null plane");
+    if (!c->cfg_set) PG_FAIL(c, PGPU_ERR_STATE, "upload_planes: pgpu_set_config first");
+    cudaSetDevice(c->device);
+    int rc;
+    c->np = 0;
+    c->has_dtrim = false;
+    c->maybe_tombstones = false;
+    c->id_counter = 0;
+    c->sorted = false; c->hist_valid = false; c->emig_valid = false; c->vel_deferred = false; c->owned_clean = false;
+    if (c->capacity == 0) {
+        long long cap = c->cfg.capacity > 0 ? (long long)c->cfg.capacity : (long long)(1.5 * (double)n);
+        if ((rc = pg_ensure_capacity(c, std::max<long long>(cap, n)))) return rc;
+    } else if ((rc = pg_ensure_capacity(c, n))) {
+        return rc;
+    }
+    if (n == 0) return PGPU_OK;
+    if ((rc = pg_reset_status(c))) return rc;
+    PgPlanes p = c->planes[c->cur];
+    PG_CUDA(c, cudaMemcpyAsync(p.pos, pos, sizeof(PgPos) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    PG_CUDA(c, cudaMemcpyAsync(p.vel, vel, sizeof(PgVel) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    if (ie) PG_CUDA(c, cudaMemcpyAsync(p.ie, ie, sizeof(PgIe) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    else if (c->ie_seen || c->any_internal_dof || c->dev.nr > 0) PG_CUDA(c, cudaMemsetAsync(p.ie, 0, sizeof(PgIe) * (size_t)n, c->stream));
+    const int ncells = (c->cfg.grid_type == PGPU_UNSTRUCTURED) ? (c->mesh_set ? c->nc : 0) : c->cfg.nx * c->cfg.ny;
+    planes_check_kernel<<<(unsigned int)((n + 255) / 256), 256, 0, c->stream>>>(p.pos, ie ? p.ie : nullptr, n, ncells, c->d_status);
+    c->np = n;
+    if ((rc = pg_finish(c, "pgpu_upload_planes"))) {
+        c->np = 0;
+        return rc;
+    }
+    if (c->h_status->flag_ie) c->ie_seen = true;
+    c->id_counter = c->np;
+    return PGPU_OK;
+}
+
+extern "C" int pgpu_download_planes(pgpu_ctx* c, void* pos, void* vel, void* ie, int64_t capacity, int64_t* n) {
+    if (!c) return PGPU_ERR_INVALID;
+    cudaSetDevice(c->device);
+    int rc;
+    if (c->maybe_tombstones && c->np > 0) {
+        if ((rc = pg_prepare(c))) return rc;
+        if ((rc = pg_reset_status(c))) return rc;
+        if ((rc = pg_sort_impl(c))) return rc;
+        if ((rc = pg_finish(c, "pgpu_download_planes"))) return rc;
+    }
+    if ((rc = pg_resolve_vel(c))) return rc;
+    if (capacity < c->np) PG_FAIL(c, PGPU_ERR_INVALID, "download_planes: capacity %lld < %lld particles", (long long)capacity, c->np);
+    if (n) *n = c->np;
+    if (c->np == 0) return PGPU_OK;
+    if (!pos || !vel) PG_FAIL(c, PGPU_ERR_INVALID, "download_planes: null plane");
+    PgPlanes p = c->planes[c->cur];
+    PG_CUDA(c, cudaMemcpyAsync(pos, p.pos, sizeof(PgPos) * (size_t)c->np, cudaMemcpyDeviceToHost, c->stream));
+    PG_CUDA(c, cudaMemcpyAsync(vel, p.vel, sizeof(PgVel) * (size_t)c->np, cudaMemcpyDeviceToHost, c->stream));
+    if (ie) PG_CUDA(c, cudaMemcpyAsync(ie, p.ie, sizeof(PgIe) * (size_t)c->np, cudaMemcpyDeviceToHost, c->stream));
+    PG_CUDA(c, cudaStreamSynchronize(c->stream));
+    return PGPU_OK;
+}
+
 extern "C" int pgpu_num_particles(pgpu_ctx* c, int64_t* n) {
     if (!c || !n) return PGPU_ERR_INVALID;
     cudaSetDevice(c->device);

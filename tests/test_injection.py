@@ -20,7 +20,14 @@ def canon(p):
     return p[np.lexsort((p["Z"], p["Y"], p["X"], p["S_ID"], p["IC"]))]
 
 
-def assert_same_set(a, b, what):
+def assert_same_set(a, b, what, exact_positions=True):
+    if not exact_positions:   # after a flight the positions carry the 1e-12 of the velocities: order by rounded keys
+        key = lambda p: p[np.lexsort((np.round(p["Y"], 9), np.round(p["X"], 9), p["S_ID"], p["IC"]))]
+        a, b = key(a), key(b)
+        assert len(a) == len(b) and np.array_equal(a["IC"], b["IC"]) and np.array_equal(a["S_ID"], b["S_ID"]), what
+        for f in ("X", "Y", "Z", "VX", "VY", "VZ"):
+            assert np.allclose(a[f], b[f], rtol=1e-10, atol=1e-12), (what, f)
+        return
     a, b = canon(a), canon(b)
     assert len(a) == len(b) and len(a) > 0, (what, len(a), len(b))
     for f in ("IC", "S_ID", "X", "Y", "Z"):
@@ -137,7 +144,7 @@ def test_device_sources_match_oracle_value_for_value(gpu, oracle_philox, case):
     oracle_philox.advect(5)
     pa, pb = oracle_philox.download_particles(), gpu.download_particles()
     assert len(pa) == len(pb)
-    assert_same_set(pa, pb, case + " after advect")
+    assert_same_set(pa, pb, case + " after advect", exact_positions=False)
 
 
 @pytest.mark.gpu
