@@ -10,8 +10,9 @@ paths, dt = 0.2 mean collision times.  Each GPU holds one x-strip of 32x128x128 
 
 * value     whole-job particle-timesteps/s with the particles resident in HBM (K steps of
             pgpu_run_steps, timed with CUDA events on the library's stream, max over ranks).
-* e2e       same metric through the C ABI with HOST buffers: every step uploads the 96-byte AoS records
-            from pinned host memory, runs one step and downloads the records again.
+* e2e       same metric through the C ABI with HOST buffers: every step uploads the particle state from pinned host
+            memory (record planes, 64 B per particle), runs one step and downloads it again; `sequential` gives the
+            un-pipelined numbers for the record planes and for the 96-byte AoS records of the Fortran TYPE.
 * roofline  algorithmic bytes (280 B per particle-timestep for argon VSS: move 84 + sort 144 +
             collide 52) over the measured step time against MEASURED_PEAKS.json's HBM copy bandwidth, and
             the same for the dominant kernel group.
@@ -147,6 +148,159 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------------------------------
+# the other configs of BASELINE.json (single GPU; `--workload c1|c1-grid|c2|c4`).  The default driver invocation stays C5.
+# ------------------------------------------------------------------------------------------------------------------
+ALT = {
+    # name: (description, algorithmic bytes per particle-timestep [SURVEY 8d], builder kwargs)
+    "c1": ("C1 0-D argon heat bath: ONE cell, VSS collisions (the GLOBAL dependency-round path), periodic box", 280.0),
+    "c1-grid": ("C1 argon heat bath on a 1024x1024 structured grid, VSS collisions, periodic", 280.0),
+    "c2": ("C2-like air box: N2/O2/O/N/NO with TCE reactions and Borgnakke-Larsen, 1024x1024 structured grid, periodic", 312.0),
+    "c4": ("C4 1-D argon PIC-MCC (Vahedi null collision, LXCat-format tables), 512 segments: DEPOSIT_CHARGE + Poisson + "
+           "E + ADVECT (Boris) + MCC per step, all on the device", None),
+}
+
+
+def build_alt(name, n):
+    from pantera_pic_dsmc_b200 import capi, workloads as wl
+    if name == "c1":
+        w = wl.c1_argon_box(n, nx=1, ny=1)
+    elif name == "c1-grid":
+        w = wl.c1_argon_box(n, nx=1024, ny=1024)
+    elif name == "c2":
+        w = wl.c2_air_box(n, nx=1024, ny=1024, T=9000.0, nrho=1e21, dt=2e-7)
+    else:
+        w = wl.c4_ccp_1d(512, n // 2, wall_bc=("vacuum", "vacuum"), field_bc=(capi.RF_VOLTAGE_BC, capi.DIRICHLET_BC))
+        w.efield = None
+    w.cfg.capacity = int(1.3 * len(w.particles)) + 4096
+    return w
+
+
+def alt_step_fn(name, lib, w):
+    """returns f(tid0, nsteps) -> (collisions, per-group seconds dict or None)"""
+    if name != "c4":
+        return lambda t0, k: (lib.run_steps(t0, k)[0], None)
+
+    def f(t0, k):
+        nc = 0
+        grp = {"deposit": 0.0, "field": 0.0, "move": 0.0, "collide": 0.0}
+        for t in range(t0, t0 + k):
+            a = time.perf_counter()
+            lib.deposit_charge(w.mesh.nn)
+            b = time.perf_counter()
+            lib.field_solve_1d(t, w.mesh.nn, w.mesh.nc)
+            c = time.perf_counter()
+            lib.advect(t)
+            d = time.perf_counter()
+            nc += lib.mcc_vahedi(t)[0]
+            e = time.perf_counter()
+            grp["deposit"] += b - a; grp["field"] += c - b; grp["move"] += d - c; grp["collide"] += e - d
+        return nc, grp
+    return f
+
+
+def run_alt(args):
+    """One JSON line for a non-default workload (same keys as the C5 line; e2e through the record planes)."""
+    import torch
+    from pantera_pic_dsmc_b200 import capi, workloads as wl
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    name = args.workload
+    desc, b_alg = ALT[name]
+    n = args.particles if args.particles != 125_000_000 else {"c1": 10_000_000, "c1-grid": 100_000_000, "c2": 50_000_000, "c4": 10_000_000}[name]
+    w = build_alt(name, n)
+    gpu = capi.load_gpu(0)
+    wl.apply(gpu, w)
+    if name == "c4":
+        gpu.set_field_bcs(wall_potential=[0.0, 0.0], wall_rf_potential=[200.0, 0.0], rf_frequency=[13.56e6, 0.0])
+    step = alt_step_fn(name, gpu, w)
+    step(1, max(args.warmup, 3))
+    torch.cuda.synchronize()
+    sampler = ClockSampler(0)
+    n0 = gpu.num_particles()
+    t0 = time.perf_counter()
+    ncoll, grp = step(1 + args.warmup, args.steps)
+    torch.cuda.synchronize()
+    dt_s = time.perf_counter() - t0
+    clocks = sampler.stop()
+    ms, launches = gpu.get_timings()
+    n1 = gpu.num_particles()
+    n_avg = 0.5 * (n0 + n1)
+    value = n_avg * args.steps / dt_s
+    if name == "c4":
+        p_mcc = ncoll / max(n_avg * args.steps, 1)
+        b_alg = 108.0 + 32.0 + 52.0 * p_mcc   # move with the Boris kick + deposit (not fused) + MCC; no sort on this path
+        groups = {k: v / args.steps * 1e3 for k, v in grp.items()}
+    else:
+        groups = {"move": float(ms[0]) / args.steps, "sort": float(ms[1]) / args.steps, "collide": float(ms[2]) / args.steps}
+    peak, peak_src = measured_peak_gbs()
+    ach = n_avg * b_alg / (dt_s / args.steps) / 1e9
+    dom = max(groups, key=lambda k: groups[k])
+    roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                "kernel": f"whole step (largest group: {dom})", "algorithmic_bytes_per_particle": b_alg,
+                "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs, burst copy)", "groups_ms_per_step": groups,
+                "note": "timed on the host clock around synchronous C-ABI calls (device synchronised on both sides)"}
+    # e2e: record planes up, the same step, record planes down (sequential, one context)
+    e2e = None
+    if not args.no_e2e and name != "c4":
+        pos0, vel0, ie0 = capi.to_planes(w.particles, wl.pinned_array(len(w.particles), capi.POS_DTYPE), wl.pinned_array(len(w.particles), capi.VEL_DTYPE))
+        use_ie = bool(np.any(w.particles["EROT"]) or np.any(w.particles["EVIB"]))
+        cap = int(w.cfg.capacity)
+        op, ov, oe = wl.pinned_array(cap, capi.POS_DTYPE), wl.pinned_array(cap, capi.VEL_DTYPE), (wl.pinned_array(cap, capi.IE_DTYPE) if use_ie else None)
+        ie_in = None
+        if use_ie:
+            ie_in = wl.pinned_array(len(w.particles), capi.IE_DTYPE)
+            ie_in[:] = ie0
+        k2 = max(2, min(args.e2e_steps or args.steps, 5))
+        def one(t):
+            gpu.upload_planes(pos0, vel0, ie_in)
+            gpu.run_steps(t, 1)
+            return gpu.download_planes_into(op, ov, oe)
+        one(900)
+        t1 = time.perf_counter()
+        m = sum(one(901 + k) for k in range(k2))
+        es = time.perf_counter() - t1
+        bpp = 80 if use_ie else 64
+        e2e = {"value": m / es, "unit": "particle-timesteps/s", "h2d_bytes_per_step": int(len(w.particles) * bpp),
+               "d2h_bytes_per_step": int(len(w.particles) * bpp), "steps": k2, "ms_per_step": es / k2 * 1e3,
+               "what": "sequential: pgpu_upload_planes + pgpu_run_steps(1) + pgpu_download_planes per step"}
+    cpu = None
+    if not args.no_cpu:
+        ws = build_alt(name, {"c1": 200_000, "c1-grid": 1_000_000, "c2": 500_000, "c4": 400_000}[name]) if name != "c1-grid" else wl.c1_argon_box(1_000_000, nx=128, ny=128)
+        if name == "c2":
+            ws = wl.c2_air_box(500_000, nx=100, ny=100, T=9000.0, nrho=1e21, dt=2e-7)
+        o = capi.load_oracle(rng_mode=0)
+        wl.apply(o, ws)
+        if name == "c4":
+            o.set_field_bcs(wall_potential=[0.0, 0.0], wall_rf_potential=[200.0, 0.0], rf_frequency=[13.56e6, 0.0])
+            def ostep(t):
+                rhs = o.deposit_charge(ws.mesh.nn)
+                o.field_solve_1d(t, ws.mesh.nn, ws.mesh.nc, rhs=rhs)
+                o.advect(t)
+                o.mcc_vahedi(t)
+        else:
+            ostep = lambda t: o.run_steps(t, 1)
+        ostep(1)
+        t1 = time.perf_counter()
+        k = 0
+        while time.perf_counter() - t1 < 8.0:
+            ostep(2 + k)
+            k += 1
+        cs = time.perf_counter() - t1
+        cpu = {"value": o.num_particles() * k / cs, "unit": "particle-timesteps/s", "cores": 1, "kind": "port",
+               "sample": f"{ws.name}: {o.num_particles()} particles, {k} steps, single thread, same cell loading as the GPU arm"}
+        o.close()
+    line = {"metric": "particle-timesteps/s (move+sort+collide)", "value": value, "unit": "particle-timesteps/s", "n_gpus": 1,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt_s / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": desc, "particles": int(n_avg), "cells": int(w.mesh.nc if w.mesh is not None else w.cfg.nx * w.cfg.ny),
+                       "l2_policy": "inputs far larger than the 126 MB L2" if n_avg * 64 > 3e8 else "inputs comparable to L2: see note",
+                       "rng": "Philox4x32-10"},
+            "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu, "gpu_launches": int(launches), "clocks": clocks,
+            "collisions_per_step": ncoll / args.steps}
+    print(json.dumps(line), flush=True)
+    gpu.close()
+
+
 class StdoutGuard:
     """The driver reads ONE JSON line from rank 0's stdout.  Libraries write there too (NCCL prints its version
     banner on stdout at communicator creation), so file descriptor 1 points at stderr while the benchmark runs and
@@ -171,6 +325,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--particles", type=int, default=125_000_000, help="particles per GPU")
     ap.add_argument("--cubes", type=int, nargs=3, default=[32, 128, 128], help="cubes per GPU strip (6 tets each)")
+    ap.add_argument("--workload", default="c5", choices=["c5"] + sorted(ALT), help="c5 (default, the metric's config) or another BASELINE.json config")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="timed e2e steps (0 = same as --steps)")
@@ -184,6 +339,11 @@ def main():
         return
     if args.warmup < 3:
         args.warmup = 3
+    if args.workload != "c5":
+        if world > 1:
+            raise SystemExit("--workload other than c5 runs on one GPU")
+        run_alt(args)
+        return
     guard = StdoutGuard()
 
     import torch
@@ -280,35 +440,47 @@ def main():
                 "groups_ms_per_step": grp,
                 "groups_frac": {k: n_now * bytes_grp[k] / (grp[k] * 1e-3) / 1e9 / peak for k in bytes_grp if grp[k] > 0}}
 
-    # ---------------- e2e: host AoS in, one step, host AoS out, every step --------------------------
-    # Every step: pgpu_upload_particles from pinned host records, one hot-path step, pgpu_download_particles into
-    # pinned host records.  A step is PCIe-bound (2 x 12 GB per GPU against 16 ms of kernels), so at N = 1 two
-    # library contexts on the same GPU, each driven by its own host thread, work on alternating steps: the
-    # download of step s overlaps the upload of step s+1 (PCIe is full duplex).  Each step still makes the full
-    # host -> device -> host round trip through the C ABI.  With N > 1 one context per rank is used (two NCCL
-    # communicators driven from two threads are not ordered against each other).
+    # ---------------- e2e: host buffers in, one step, host buffers out, every step ------------------
+    # Every step: upload from pinned host memory, one hot-path step, download into pinned host memory, through the C ABI.
+    # The host keeps the particle state as record planes (pgpu_upload_planes / pgpu_download_planes: the device's own
+    # 32-byte position and velocity records, 64 B per particle; ID, DUMP_TRAJ and DTRIM stay on the host as SURVEY 8(d)
+    # counts them) -- the 96-byte AoS path of the Fortran TYPE is timed next to it.  A step is PCIe-bound (2 x 8 GB per
+    # GPU against 13 ms of kernels), so the headline number pipelines: at N = 1 two library contexts on the same GPU,
+    # each driven by its own host thread, work on alternating steps, and the download of step s overlaps the upload of
+    # step s+1 (PCIe is full duplex).  `sequential` is one context doing upload -> step -> download back to back.
     e2e = None
     if not args.no_e2e:
         import threading
         k2 = args.e2e_steps or args.steps
+        cap = int(w.cfg.capacity)
+        pos0, vel0, _ = capi.to_planes(w.particles, wl.pinned_array(len(w.particles), capi.POS_DTYPE), wl.pinned_array(len(w.particles), capi.VEL_DTYPE))
         ctxs = [gpu]
         if world == 1:
             g2 = capi.load_gpu(local_rank)
             wl.apply(g2, w, upload=False)
             ctxs.append(g2)
-        outs = [wl.pinned_particles(int(w.cfg.capacity)) for _ in ctxs]   # a strip's population changes with N > 1
+        outs = [(wl.pinned_array(cap, capi.POS_DTYPE), wl.pinned_array(cap, capi.VEL_DTYPE)) for _ in ctxs]
         moved = [0 for _ in ctxs]
         errors = []
+
+        def one_step(i, tid, aos=False):
+            if aos:
+                ctxs[i].upload_particles(w.particles)
+                ctxs[i].run_steps(tid, 1)
+                return ctxs[i].download_into(aos_out)
+            ctxs[i].upload_planes(pos0, vel0)
+            ctxs[i].run_steps(tid, 1)
+            return ctxs[i].download_planes_into(*outs[i])
 
         def drive(i, first, count, tid0, go, nxt):
             go.wait()  # staggered start: context i+1 begins its upload when context i has finished its first one,
             try:       # so uploads meet downloads, not other uploads
-                for k, s in enumerate(range(first, count, len(ctxs))):
-                    ctxs[i].upload_particles(w.particles)
+                for k, s_ in enumerate(range(first, count, len(ctxs))):
+                    ctxs[i].upload_planes(pos0, vel0)
                     if k == 0 and nxt is not None:
                         nxt.set()
-                    ctxs[i].run_steps(tid0 + s, 1)
-                    moved[i] += ctxs[i].download_into(outs[i])
+                    ctxs[i].run_steps(tid0 + s_, 1)
+                    moved[i] += ctxs[i].download_planes_into(*outs[i])
             except Exception as e:  # never leave the other ranks waiting at the barrier
                 errors.append(repr(e))
                 if world > 1:       # the peers wait for this rank inside the exchange: fail the whole job at once
@@ -328,7 +500,7 @@ def main():
             for t in th:
                 t.join()
 
-        run_all(3 * len(ctxs), 1000)  # warm-up (first-touch of both contexts' stores and staging buffers)
+        run_all(3 * len(ctxs), 1000)  # warm-up (first-touch of both contexts' stores and of the pinned buffers)
         moved = [0 for _ in ctxs]
         barrier()
         t0 = time.perf_counter()
@@ -337,11 +509,32 @@ def main():
         e2e_s = max_over_ranks(time.perf_counter() - t0)
         if errors:
             raise RuntimeError("e2e leg failed: " + "; ".join(errors))
+        # sequential: one context, upload -> step -> download back to back (what a host that needs the particles after
+        # every step would see), record planes and 96-byte AoS records
+        seq = {}
+        ks = max(2, min(4, k2))
+        for name, aos in (("planes_64B", False), ("aos_96B", True)):
+            if aos:
+                aos_out = wl.pinned_particles(cap)
+            one_step(0, 3000, aos)
+            barrier()
+            t1 = time.perf_counter()
+            m = 0
+            for s_ in range(ks):
+                m += one_step(0, 3001 + s_, aos)
+            barrier()
+            dt_s = max_over_ranks(time.perf_counter() - t1)
+            seq[name] = {"value": sum_over_ranks(float(m)) / dt_s, "ms_per_step": dt_s / ks * 1e3, "steps": ks,
+                         "bytes_per_particle_each_way": 96 if aos else 64}
+            if aos:
+                del aos_out
+                wl._PINNED_KEEPALIVE.pop()  # release the 96-byte buffer
         e2e = {"value": sum_over_ranks(float(sum(moved))) / e2e_s, "unit": "particle-timesteps/s",
-               "h2d_bytes_per_step": int(n_local * 96 * world), "d2h_bytes_per_step": int(n_local * 96 * world),
-               "steps": k2, "ms_per_step": e2e_s / k2 * 1e3, "contexts_per_gpu": len(ctxs),
-               "what": "per step: pgpu_upload_particles(pinned 96-byte AoS) + pgpu_run_steps(1) + pgpu_download_particles"
-                       "(pinned AoS); PCIe-bound" + ("; two contexts on alternating steps overlap H2D with D2H" if len(ctxs) > 1 else "")}
+               "h2d_bytes_per_step": int(n_local * 64 * world), "d2h_bytes_per_step": int(n_local * 64 * world),
+               "steps": k2, "ms_per_step": e2e_s / k2 * 1e3, "contexts_per_gpu": len(ctxs), "format": "record planes, 64 B per particle",
+               "sequential": seq,
+               "what": "per step: pgpu_upload_planes(pinned pos + vel records) + pgpu_run_steps(1) + pgpu_download_planes(pinned); "
+                       "PCIe-bound" + ("; two contexts on alternating steps overlap H2D with D2H" if len(ctxs) > 1 else "")}
         for g in ctxs[1:]:
             g.close()
 

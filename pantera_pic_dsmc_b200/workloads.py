@@ -417,6 +417,18 @@ def pinned_particles(n: int) -> np.ndarray:
     return t.numpy().view(capi.PARTICLE_DTYPE)[:n]
 
 
+def pinned_array(n: int, dtype) -> np.ndarray:
+    """n zeroed records of `dtype` in page-locked host memory."""
+    import torch
+    nbytes = max(n, 1) * np.dtype(dtype).itemsize
+    try:
+        t = torch.zeros(nbytes, dtype=torch.uint8, pin_memory=torch.cuda.is_available())
+    except RuntimeError:
+        t = torch.zeros(nbytes, dtype=torch.uint8)
+    _PINNED_KEEPALIVE.append(t)
+    return t.numpy().view(dtype)[:n]
+
+
 def c5_channel_strip(ncx: int, ncy: int, ncz: int, n: int, rank: int = 0, world: int = 1, seed: int = 2,
                      T0: float = 300.0, nrho: float = 1e20, cell_mfp: float = 0.5, dt_frac: float = 0.2,
                      u_drift: float = 100.0, wall_temp: float = 400.0, pinned: bool = False,
