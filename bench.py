@@ -39,9 +39,10 @@ B_ALG_RESTATED = B_MOVE + B_SORT_RESTATED + B_COLLIDE
 
 
 def ncu_traffic_per_particle(group):
-    """DRAM bytes per particle of the group's main kernel from the committed ncu capture (None if absent)."""
+    """DRAM bytes per particle of the group's main kernel from the COMMITTED ncu capture profiles/traffic.json (None if
+    absent) -- not measured in this run: ncu cannot run inside the timed region; the file names the capture it came from."""
     try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
         return float(t["dram_bytes_per_particle"][group])
     except Exception:
         return None
@@ -186,6 +187,10 @@ def alt_step_fn(name, lib, w):
         grp = {"deposit": 0.0, "field": 0.0, "move": 0.0, "collide": 0.0}
         for t in range(t0, t0 + k):
             a = time.perf_counter()
+            if t % 4 == 0:
+                lib.sort()   # not part of the reference's PIC loop: keeps the store cell-ordered (locality of the gather,
+                             # of the deposit and of the histogram) and compacts tombstones; counted in `move`
+            a0 = time.perf_counter()
             lib.deposit_charge(w.mesh.nn)
             b = time.perf_counter()
             lib.field_solve_1d(t, w.mesh.nn, w.mesh.nc)
@@ -194,7 +199,7 @@ def alt_step_fn(name, lib, w):
             d = time.perf_counter()
             nc += lib.mcc_vahedi(t)[0]
             e = time.perf_counter()
-            grp["deposit"] += b - a; grp["field"] += c - b; grp["move"] += d - c; grp["collide"] += e - d
+            grp["deposit"] += b - a0; grp["field"] += c - b; grp["move"] += (d - c) + (a0 - a); grp["collide"] += e - d
         return nc, grp
     return f
 
@@ -426,14 +431,19 @@ def main():
     ach_step = n_now * B_ALG_RESTATED / (total_ms / args.steps * 1e-3) / 1e9
     ach_step_survey = n_now * B_ALG / (total_ms / args.steps * 1e-3) / 1e9
     tpp = ncu_traffic_per_particle(dom)
+    try:
+        traffic_src = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["source"] + " (committed capture, not this run)"
+    except Exception:
+        traffic_src = None
     roofline = {"bound": "hbm", "achieved": ach_dom, "peak": peak, "unit": "GB/s", "frac": ach_dom / peak,
-                "traffic": (tpp * n_now if tpp is not None else None),
+                "traffic": (tpp * n_now if tpp is not None else None), "traffic_source": traffic_src,
                 "kernel": {"move": "advect_lean_kernel (+advect_full_kernel)", "sort": "scatter_kernel",
                            "collide": "cell_collide_kernel"}[dom],
                 "kernel_ms_per_launch": grp[dom], "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs, burst copy)",
                 "algorithmic_bytes_per_particle": bytes_grp[dom], "algorithmic_bytes_per_launch": bytes_grp[dom] * n_now,
-                "note": ("only the sort is HBM-bound (DRAM traffic at 85 % of the measured peak); ADVECT is bound by the L1 data pipe "
-                         "(wavefronts 76-82 %), the collisions by DRAM latency (DESIGN.md section 3, profiles/r01o_*)"),
+                "note": ("only the sort is HBM-bound (88 % of the measured peak for the bytes it must move); ADVECT is issue/latency-"
+                         "bound since the single-precision face filter took it off the L1 data pipe (wavefronts 76 % -> 43 %), the "
+                         "collisions are bound by per-lane DRAM latency (DESIGN.md section 3, profiles/r02*)"),
                 "whole_step": {"achieved": ach_step, "frac": ach_step / peak, "algorithmic_bytes_per_particle": B_ALG_RESTATED,
                                "survey_8d": {"achieved": ach_step_survey, "frac": ach_step_survey / peak,
                                              "algorithmic_bytes_per_particle": B_ALG}},

@@ -903,8 +903,8 @@ __device__ __forceinline__ void store_particle(const PgDev& d, long long slot, c
     }
     /* nranks > 1: a particle that ends in a cell of another rank is an emigrant.  It is not counted (the sort of this
      * rank will not see it); its slot and destination are recorded for EXCHANGE instead. */
+    const int lane = threadIdx.x & 31;
     if (d.emig_list) {
-        const int lane = threadIdx.x & 31;
         /* emig_trust: every particle started the step in a cell of this rank, so the ownership flag carried along the
          * face walk decides, and only the emigrants (about 1 %) read CELL_PROCS; otherwise every particle does */
         int dest = d.rank;
@@ -921,11 +921,21 @@ __device__ __forceinline__ void store_particle(const PgDev& d, long long slot, c
                 if (k < (unsigned long long)d.emig_cap) d.emig_list[k] = (unsigned int)slot;
                 else atomicAdd(&d.xrow[PG_XROW_OVF], 1ULL);
                 atomicAdd(&d.xrow[dest], 1ULL);
-                return;
             }
+            peers &= ~em;
+            if (emig) return;
         }
     }
-    atomicAdd(&d.cell_count[q.ic - 1], 1u);
+    /* The store is cell-sorted, so the lanes that finish together often share their cell, and coarse grids (the
+     * one-cell heat bath, a 512-segment line) send millions of increments to a handful of counters: when the whole
+     * group agrees on the cell, one lane adds the group's size (two warp votes); otherwise every lane adds one. */
+    const int leader = __ffs(peers) - 1;
+    const int ic0 = __shfl_sync(peers, q.ic, leader);
+    if (__all_sync(peers, q.ic == ic0)) {
+        if (lane == leader) atomicAdd(&d.cell_count[ic0 - 1], (unsigned int)__popc(peers));
+    } else {
+        atomicAdd(&d.cell_count[q.ic - 1], 1u);
+    }
 }
 
 __device__ __forceinline__ void tombstone_particle(const PgDev& d, long long slot) {

@@ -397,6 +397,33 @@ def assign_cells_to_procs(m: Mesh, nranks: int, style: int = 0) -> np.ndarray:
     return procs.astype(np.int32)
 
 
+def load_balance_cut(m: Mesh, np_cells: np.ndarray, nranks: int, style: int = 0) -> np.ndarray:
+    """The LOAD_BALANCE branch of ASSIGN_CELLS_TO_PROCS (src/grid_and_partition.f90:214-310): cell weight = particles in
+    the cell (summed over the ranks) + 10 % of the mean, cells ordered by centroid coordinate, greedy cut whenever the
+    cumulated weight exceeds the per-rank share.  Host work in the reference (it stays in Fortran); the device side is
+    pgpu_get_cell_counts -> (MPI_REDUCE on the host) -> pgpu_set_cell_procs -> EXCHANGE."""
+    cn = np.asarray(m.cell_nodes) - 1
+    coords = np.asarray(m.node_coords)
+    nv = m.dims + 1
+    cen = coords[style, cn[0]]
+    for i in range(1, nv):
+        cen = cen + coords[style, cn[i]]
+    cen = cen / float(nv)
+    weight = np.asarray(np_cells, dtype=np.float64)
+    weight = weight + float(np.float32(0.1)) * weight.sum() / float(m.nc)
+    per_proc = weight.sum() / float(nranks)
+    order = np.argsort(cen, kind="stable")      # QUICKSORT by centroid (ties: any order; the regular test meshes have none across a cut)
+    procs = np.zeros(m.nc, dtype=np.int32)
+    iproc, cum = 0, 0.0
+    for ic in order:
+        cum += weight[ic]
+        procs[ic] = min(iproc, nranks - 1)
+        if cum > per_proc:
+            iproc += 1
+            cum = 0.0
+    return procs
+
+
 def to_su2(m: Mesh, path: str):
     """Write the mesh in the SU2 subset the reference readers accept."""
     etype = {1: 3, 2: 5, 3: 10}[m.dims]

@@ -145,6 +145,64 @@ def test_one_gpu_contexts_collisions_per_rank_streams():
             lib.close()
 
 
+def test_load_balance_recut_then_exchange():
+    """LOAD_BALANCE (src/grid_and_partition.f90:214-310, called from src/timecycle.f90:185-189): per-cell counts from the
+    device, summed over the ranks on the host, the reference's greedy cut, pgpu_set_cell_procs, a full EXCHANGE.  The
+    drift of the channel has piled particles up downstream; after the re-cut the ranks are balanced again, every
+    particle sits on its new owner, and the oracle's rank model lands on the same particles bit for bit."""
+    from pantera_pic_dsmc_b200 import meshgen as mg
+    world, steps = 2, 6
+    gpus, orcs, mesh = [], [], None
+    try:
+        for r in range(world):
+            w = strip_workload(r, world, collisions=False, mesh=mesh)
+            mesh = w.mesh
+            g, o = capi.load_gpu(0), capi.load_oracle(rng_mode=0)
+            wl.apply(g, w)
+            wl.apply(o, w)
+            gpus.append(g)
+            orcs.append(o)
+        for s in range(steps):
+            for g in gpus:
+                g.advect(1 + s)
+            host_all_to_all(gpus)
+        refbench.sim_run(orcs, 1, steps)
+        before = [g.num_particles() for g in gpus]
+        assert max(before) > 1.08 * min(before), before           # the drift has unbalanced the strips
+        npc = np.zeros(mesh.nc, dtype=np.int64)
+        for g in gpus:
+            g.sort()
+            npc += g.get_cell_counts(mesh.nc)
+        npc_o = np.zeros(mesh.nc, dtype=np.int64)
+        for o in orcs:
+            p = o.download_particles()
+            npc_o += np.bincount(p["IC"] - 1, minlength=mesh.nc)
+        assert np.array_equal(npc, npc_o)
+        procs = mg.load_balance_cut(mesh, npc, world, 0)
+        assert set(np.unique(procs)) == {0, 1} and not np.array_equal(procs, np.asarray(mesh.cell_procs))
+        for lib in gpus + orcs:
+            lib.set_cell_procs(procs)
+        host_all_to_all(gpus)
+        host_all_to_all(orcs)
+        after = [g.num_particles() for g in gpus]
+        assert sum(after) == sum(before) and max(after) < 1.03 * min(after), (before, after)
+        dev = [g.download_particles() for g in gpus]
+        ref = [o.download_particles() for o in orcs]
+        compare_ranks(dev, ref, exact=True)
+        for r, p in enumerate(dev):
+            assert np.all(procs[p["IC"] - 1] == r)
+        # and the run goes on under the new ownership (hop codes rebuilt with the new flags)
+        for s in range(2):
+            for g in gpus:
+                g.advect(50 + s)
+            host_all_to_all(gpus)
+        refbench.sim_run(orcs, 50, 2)
+        compare_ranks([g.download_particles() for g in gpus], [o.download_particles() for o in orcs], exact=True)
+    finally:
+        for lib in gpus + orcs:
+            lib.close()
+
+
 # --------------------------------------------------------------------------------------------- NCCL (>= 2 GPUs)
 def _free_port() -> int:
     with socket.socket() as s:

@@ -2,7 +2,7 @@
 """Turns the ncu outputs of tools/gpu_round.sh (gpurun_out/) into the small tracked summaries under profiles/:
    launches_<tag>.csv          -> profiles/<tag>_launches.csv (copy) + <tag>_launches_summary.csv (time share per kernel)
    prof_<tag>.ncu-rep (full)   -> profiles/<tag>_ncu_full_summary.json (per kernel: duration, DRAM bytes, pipe/stall
-                                  metrics) and profiles/r01_traffic.json (DRAM bytes per particle, read by bench.py)
+                                  metrics) and profiles/traffic.json (DRAM bytes per particle, read by bench.py)
 usage: python tools/ncu_summarize.py <tag> <particles>"""
 import csv
 import io
@@ -76,5 +76,5 @@ if os.path.exists(rep):
         out.append(e)
     json.dump(out, open(os.path.join(P, f"{tag}_ncu_full_summary.json"), "w"), indent=1)
     json.dump({"source": f"ncu --set full --clock-control none, profiles/{tag}_ncu_full_summary.json, C5 strip {npart:.3g} particles",
-               "dram_bytes_per_particle": traffic}, open(os.path.join(P, "r01_traffic.json"), "w"), indent=1)
+               "dram_bytes_per_particle": traffic}, open(os.path.join(P, "traffic.json"), "w"), indent=1)
     print(json.dumps(out, indent=1))
