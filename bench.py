@@ -157,6 +157,8 @@ ALT = {
     "c1": ("C1 0-D argon heat bath: ONE cell, VSS collisions (the GLOBAL dependency-round path), periodic box", 280.0),
     "c1-grid": ("C1 argon heat bath on a 1024x1024 structured grid, VSS collisions, periodic", 280.0),
     "c2": ("C2-like air box: N2/O2/O/N/NO with TCE reactions and Borgnakke-Larsen, 1024x1024 structured grid, periodic", 312.0),
+    "c5-1e9": ("C5 3-D unstructured argon channel, the WHOLE 256x128x128-cube mesh (2.5e7 tets) and 10^9 particles on ONE GPU "
+               "(north_star's single-GPU target configuration; particles streamed in from the host in batches)", 280.0),
     "c4": ("C4 1-D argon PIC-MCC (Vahedi null collision, LXCat-format tables), 512 segments: DEPOSIT_CHARGE + Poisson + "
            "E + ADVECT (Boris) + MCC per step, all on the device", None),
 }
@@ -164,6 +166,10 @@ ALT = {
 
 def build_alt(name, n):
     from pantera_pic_dsmc_b200 import capi, workloads as wl
+    if name == "c5-1e9":
+        w = wl.c5_channel_strip(256, 128, 128, n=n, rank=0, world=1, seed=1234, u_drift=0.0, lazy=True)
+        w.cfg.capacity = int(n + n // 256) + 65536
+        return w
     if name == "c1":
         w = wl.c1_argon_box(n, nx=1, ny=1)
     elif name == "c1-grid":
@@ -211,10 +217,20 @@ def run_alt(args):
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
     name = args.workload
     desc, b_alg = ALT[name]
-    n = args.particles if args.particles != 125_000_000 else {"c1": 10_000_000, "c1-grid": 100_000_000, "c2": 50_000_000, "c4": 10_000_000}[name]
+    n = args.particles if args.particles != 125_000_000 else {"c1": 10_000_000, "c1-grid": 100_000_000, "c2": 50_000_000, "c4": 10_000_000,
+                                                              "c5-1e9": 1_000_000_000}[name]
     w = build_alt(name, n)
     gpu = capi.load_gpu(0)
-    wl.apply(gpu, w)
+    if name == "c5-1e9":
+        wl.apply(gpu, w, upload=False)
+        first = True
+        for batch in w.batches():
+            (gpu.upload_particles if first else gpu.append_particles)(batch)
+            first = False
+        args.no_e2e = True   # 96 GB of host records per direction: not part of this leg
+        args.no_cpu = True
+    else:
+        wl.apply(gpu, w)
     if name == "c4":
         gpu.set_field_bcs(wall_potential=[0.0, 0.0], wall_rf_potential=[200.0, 0.0], rf_frequency=[13.56e6, 0.0])
     step = alt_step_fn(name, gpu, w)
@@ -298,6 +314,7 @@ def run_alt(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt_s / args.steps * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": desc, "particles": int(n_avg), "cells": int(w.mesh.nc if w.mesh is not None else w.cfg.nx * w.cfg.ny),
+                       "device_memory_gb": round(torch.cuda.mem_get_info()[1] / 1e9 - torch.cuda.mem_get_info()[0] / 1e9, 1),
                        "l2_policy": "inputs far larger than the 126 MB L2" if n_avg * 64 > 3e8 else "inputs comparable to L2: see note",
                        "rng": "Philox4x32-10"},
             "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu, "gpu_launches": int(launches), "clocks": clocks,

@@ -230,6 +230,13 @@ int pgpu_exchange(pgpu_ctx* ctx);
  * (the ADD_PARTICLE_ARRAY loop of :610-612).  Needs no communicator. */
 int pgpu_exchange_pack(pgpu_ctx* ctx, void* sendbuf_aos, int64_t capacity, int64_t* sendcount);
 
+/* Deterministic mode: the counting sort becomes STABLE (radix sort of (cell, slot) pairs instead of the atomic per-cell
+ * cursor), so that the in-cell order -- which the pair selection indexes and the slot-keyed wall streams depend on --
+ * is a function of the input alone: the same particles and seed reproduce a run bit for bit, as the reference's stable
+ * counting sort does (src/collisions.f90:102-112).  Off by default (cost: DESIGN.md).  Particles created on the device
+ * within one call (reaction products, injection, immigrants) are appended in cursor order, which this mode does not fix. */
+int pgpu_set_deterministic(pgpu_ctx* ctx, int32_t on);
+
 /* counting sort by cell of DSMC_COLLISIONS (src/collisions.f90:61-112), done as a physical
  * SoA reorder.  Called implicitly by pgpu_collide when the store is not sorted. */
 int pgpu_sort(pgpu_ctx* ctx);

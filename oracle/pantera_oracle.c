@@ -2362,6 +2362,7 @@ int po_set_rng_script(po_ctx* w, const double* draws, int64_t n) {
 }
 int64_t po_rng_script_used(const po_ctx* w) { return w->script_pos; }
 int po_collision_type(const po_ctx* w) { return w->c.collision_type; }
+int po_set_deterministic(po_ctx* w, int32_t on) { (void)w; (void)on; return PGPU_OK; } /* the oracle is sequential */
 
 int po_set_config(po_ctx* w, const pgpu_config* cfg) {
     w->c = *cfg;

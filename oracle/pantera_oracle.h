@@ -45,6 +45,7 @@ int po_set_rng_mode(po_ctx* ctx, int mode);
 int po_set_rng_script(po_ctx* ctx, const double* draws, int64_t n);
 int64_t po_rng_script_used(const po_ctx* ctx);
 int po_collision_type(const po_ctx* ctx);
+int po_set_deterministic(po_ctx* ctx, int32_t on);
 /* raw generator access for the known-answer tests */
 double po_rf(po_ctx* ctx);
 int po_pick(po_ctx* ctx, int n); /* pair-selection index INT(N*rf()), one stream word in Philox mode for N <= 65536 */

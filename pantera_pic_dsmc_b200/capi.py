@@ -375,6 +375,9 @@ class Lib:
         self._call("exchange_pack", _p(buf), C.c_int64(len(buf)), _p(cnt))
         return buf[: int(cnt.sum())], cnt
 
+    def set_deterministic(self, on: bool = True):
+        self._call("set_deterministic", C.c_int32(int(on)))
+
     def sort(self):
         self._call("sort")
 

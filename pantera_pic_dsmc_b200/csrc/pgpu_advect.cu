@@ -896,11 +896,7 @@ __device__ __forceinline__ void store_particle(const PgDev& d, long long slot, c
         V.vx = q.vx; V.vy = q.vy; V.vz = q.vz; V.sid = q.sid; V.pad = 0;
         d.p.vel[slot] = V;
     }
-    if (dirty & DIRTY_E) {
-        PgIe E;
-        E.erot = q.erot; E.evib = q.evib;
-        d.p.ie[slot] = E;
-    }
+    if (dirty & DIRTY_E) pg_ie_store(d.p.ie, slot, q.erot, q.evib, d.status);
     /* nranks > 1: a particle that ends in a cell of another rank is an emigrant.  It is not counted (the sort of this
      * rank will not see it); its slot and destination are recorded for EXCHANGE instead. */
     const int lane = threadIdx.x & 31;

@@ -8,6 +8,7 @@
  * There is no CPU fallback anywhere in this library: every entry point that computes needs a CUDA
  * device and fails with PGPU_ERR_CUDA otherwise.
  */
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
 #include <algorithm>
@@ -177,6 +178,8 @@ extern "C" int pgpu_destroy(pgpu_ctx* c) {
     }
     dev_free(c->d_rhs); dev_free(c->d_bcount); dev_free(c->d_wcount); dev_free(c->d_tallies);
     dev_free(c->d_surface_charge);
+    for (int k = 0; k < 4; k++) dev_free(c->d_det[k]);
+    if (c->d_det_tmp) cudaFree(c->d_det_tmp);
     dev_free(c->d_gavg); dev_free(c->d_gavg_np); dev_free(c->d_gavg_sums); dev_free(c->d_gavg_cum);
     dev_free(c->d_sendbuf); dev_free(c->d_recvbuf); dev_free(c->d_xcount); dev_free(c->d_emig_list);
     for (int i = 0; i < 16; i++) cudaEventDestroy(c->ev[i]);
@@ -710,11 +713,13 @@ void pg_refresh_dev(pgpu_ctx* c) {
     d.id_base = c->id_counter;
     d.vel_src = c->vel_deferred ? c->planes[c->cur ^ 1].vel : nullptr;
     d.src_of = c->vel_deferred ? c->d_src_of : nullptr;
-    d.use_ie = (c->any_internal_dof || c->dev.nr > 0 || c->ie_seen) ? 1 : 0;
+    d.use_ie = ((c->any_internal_dof || c->dev.nr > 0 || c->ie_seen) && c->planes[c->cur].ie) ? 1 : 0;
     d.tile_first = c->d_tile_first;
     d.cell_order = c->sorted ? c->d_cell_order : nullptr;
     d.ntiles = c->sorted ? (int)((c->np + PG_TILE_S - 1) / PG_TILE_S) : 0;
 }
+
+static bool wants_ie(const pgpu_ctx* c) { return c->any_internal_dof || c->dev.nr > 0 || c->ie_seen; }
 
 int pg_prepare(pgpu_ctx* c) {
     cudaSetDevice(c->device);
@@ -733,6 +738,7 @@ int pg_prepare(pgpu_ctx* c) {
             PG_FAIL(c, PGPU_ERR_STATE, "non-uniform grid without matching pgpu_set_grid_coords");
     }
     if ((rc = pg_ensure_cell_arrays(c))) return rc;
+    if (wants_ie(c) && (rc = pg_need_ie(c))) return rc; /* (species / reactions may have been set after the upload) */
     pg_refresh_dev(c);
     return PGPU_OK;
 }
@@ -797,13 +803,15 @@ int pg_finish(pgpu_ctx* c, const char* what) {
 /* ------------------------------------------------------------------------------------------
  * particle store
  * ---------------------------------------------------------------------------------------- */
-static int alloc_planes(pgpu_ctx* c, PgPlanes& p, long long cap, bool with_dtrim, bool with_id) {
+static int alloc_planes(pgpu_ctx* c, PgPlanes& p, long long cap, bool with_ie, bool with_dtrim, bool with_id) {
     int rc;
     memset(&p, 0, sizeof(p));
     size_t n = (size_t)cap;
-    if ((rc = dev_alloc(c, &p.pos, n)) || (rc = dev_alloc(c, &p.vel, n)) || (rc = dev_alloc(c, &p.ie, n))) return rc;
-    /* the ie plane is not reordered while every EROT/EVIB is zero: both copies start out (and stay) zero */
-    PG_CUDA(c, cudaMemsetAsync(p.ie, 0, sizeof(PgIe) * n, c->stream));
+    if ((rc = dev_alloc(c, &p.pos, n)) || (rc = dev_alloc(c, &p.vel, n))) return rc;
+    if (with_ie) {
+        if ((rc = dev_alloc(c, &p.ie, n))) return rc;
+        PG_CUDA(c, cudaMemsetAsync(p.ie, 0, sizeof(PgIe) * n, c->stream));
+    }
     if (with_dtrim && (rc = dev_alloc(c, &p.dtrim, n))) return rc;
     if (with_id && (rc = dev_alloc(c, &p.id, n))) return rc;
     return PGPU_OK;
@@ -823,8 +831,9 @@ int pg_ensure_capacity(pgpu_ctx* c, long long n) {
     int rc;
     PgPlanes np0, np1;
     bool with_id = c->cfg.track_id != 0;
-    if ((rc = alloc_planes(c, np0, cap, true, with_id))) return rc;
-    if ((rc = alloc_planes(c, np1, cap, true, with_id))) return rc;
+    const bool with_ie = wants_ie(c) || c->planes[0].ie != nullptr, with_dtrim = c->has_dtrim || c->planes[0].dtrim != nullptr;
+    if ((rc = alloc_planes(c, np0, cap, with_ie, with_dtrim, with_id))) return rc;
+    if ((rc = alloc_planes(c, np1, cap, with_ie, with_dtrim, with_id))) return rc;
     PgPlanes& o = c->planes[c->cur];
     long long m = c->np;
     if (m > 0) {
@@ -840,10 +849,10 @@ int pg_ensure_capacity(pgpu_ctx* c, long long n) {
     dev_free(c->d_hitlist);
     dev_free(c->d_src_of);
     if ((rc = dev_alloc(c, &c->d_hitlist, (size_t)cap))) return rc;
-    if ((rc = dev_alloc(c, &c->d_src_of, (size_t)cap))) return rc;
+    if (c->defer_vel && (rc = dev_alloc(c, &c->d_src_of, (size_t)cap))) return rc; /* (only the deferred reorder uses it) */
     dev_free(c->d_emig_list);
     c->emig_cap = cap / 8 + 1024;
-    if ((rc = dev_alloc(c, &c->d_emig_list, (size_t)c->emig_cap))) return rc;
+    if (c->cfg.nranks > 1 && (rc = dev_alloc(c, &c->d_emig_list, (size_t)c->emig_cap))) return rc;
     c->emig_valid = false;
     dev_free(c->d_tile_first);
     dev_free(c->d_big_list);
@@ -887,9 +896,10 @@ __global__ void __launch_bounds__(256) aos_to_soa_kernel(const unsigned char* __
     E.erot = f[6]; E.evib = f[7];
     p.pos[o] = P;
     p.vel[o] = V;
-    p.ie[o] = E;
+    pg_ie_store(p.ie, o, E.erot, E.evib, st);
     double dtrim = f[8];
-    p.dtrim[o] = dtrim;
+    if (p.dtrim) p.dtrim[o] = dtrim;
+    else if (dtrim != dt) st->need_dtrim = 1;
     if (p.id) p.id[o] = *reinterpret_cast<const long long*>(r + OFF_ID);
     if (dtrim != dt) st->flag_dtrim = 1;
     if (E.erot != 0. || E.evib != 0.) st->flag_ie = 1;
@@ -906,11 +916,11 @@ __global__ void __launch_bounds__(256) soa_to_aos_kernel(unsigned char* __restri
     long long o = base + i;
     const PgPos P = p.pos[o];
     const PgVel V = p.vel[o];
-    const PgIe E = p.ie[o];
+    const PgIe E = pg_ie_load(p.ie, o);
     f[0] = P.x; f[1] = P.y; f[2] = P.z;
     f[3] = V.vx; f[4] = V.vy; f[5] = V.vz;
     f[6] = E.erot; f[7] = E.evib;
-    f[8] = has_dtrim ? p.dtrim[o] : dt;
+    f[8] = (has_dtrim && p.dtrim) ? p.dtrim[o] : dt;
     *reinterpret_cast<int*>(r + OFF_IC) = P.ic;
     *reinterpret_cast<int*>(r + OFF_SID) = P.sid;
     /* ID = PROC_ID + ISHFT(counter, 8), ref: src/particle.f90:75 (regenerated unless cfg.track_id) */
@@ -952,10 +962,14 @@ static int append_impl(pgpu_ctx* c, const void* aos, int64_t n, int32_t stride, 
     }
     if (n == 0) return PGPU_OK;
     if ((rc = ensure_stage(c, stride))) return rc;
-    if ((rc = pg_reset_status(c))) return rc;
+    if (wants_ie(c) && (rc = pg_need_ie(c))) return rc;
+    if (c->has_dtrim && (rc = pg_need_dtrim(c))) return rc;
     int ncells = (c->cfg.grid_type == PGPU_UNSTRUCTURED) ? (c->mesh_set ? c->nc : 0) : c->cfg.nx * c->cfg.ny;
-    PgPlanes p = c->planes[c->cur];
     cudaEvent_t evs[2] = {c->ev[14], c->ev[15]};
+  for (int pass = 0; pass < 2; pass++) { /* a second pass only when the records carry internal energy / their own DTRIM
+                                            and the plane for it did not exist yet (it does now) */
+    if ((rc = pg_reset_status(c))) return rc;
+    PgPlanes p = c->planes[c->cur];
     bool used[2] = {false, false};
     int k = 0;
     for (long long done = 0; done < n; done += STAGE_PARTICLES, k ^= 1) {
@@ -968,6 +982,15 @@ static int append_impl(pgpu_ctx* c, const void* aos, int64_t n, int32_t stride, 
         PG_CUDA(c, cudaEventRecord(evs[k], c->stream));
         used[k] = true;
     }
+    PG_CUDA(c, cudaMemcpyAsync(c->h_status, c->d_status, sizeof(PgStatus), cudaMemcpyDeviceToHost, c->stream));
+    PG_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (!c->h_status->need_ie && !c->h_status->need_dtrim) break;
+    if (pass == 1) PG_FAIL(c, PGPU_ERR_STATE, "%s: optional planes could not be provided", what);
+    if (c->h_status->need_ie && (rc = pg_need_ie(c))) return rc;
+    if (c->h_status->need_dtrim) { /* particles already in the store have DTRIM = DT */
+        if ((rc = pg_fill_dtrim(c))) return rc;
+    }
+  }
     long long np_old = c->np;
     c->np += n;
     c->sorted = false;
@@ -995,8 +1018,31 @@ extern "C" int pgpu_upload_particles(pgpu_ctx* c, const void* aos, int64_t n, in
     return append_impl(c, aos, n, stride, "pgpu_upload_particles");
 }
 
+int pg_need_ie(pgpu_ctx* c) {
+    cudaSetDevice(c->device);
+    if (c->capacity == 0 || c->planes[0].ie) return PGPU_OK;
+    for (int k = 0; k < 2; k++) {
+        int rc;
+        if ((rc = dev_alloc(c, &c->planes[k].ie, (size_t)c->capacity))) return rc;
+        PG_CUDA(c, cudaMemsetAsync(c->planes[k].ie, 0, sizeof(PgIe) * (size_t)c->capacity, c->stream));
+    }
+    pg_refresh_dev(c);
+    return PGPU_OK;
+}
+int pg_need_dtrim(pgpu_ctx* c) {
+    cudaSetDevice(c->device);
+    if (c->capacity == 0 || c->planes[0].dtrim) return PGPU_OK;
+    for (int k = 0; k < 2; k++) {
+        int rc;
+        if ((rc = dev_alloc(c, &c->planes[k].dtrim, (size_t)c->capacity))) return rc;
+    }
+    pg_refresh_dev(c);
+    return PGPU_OK;
+}
+
 int pg_fill_dtrim(pgpu_ctx* c) {
     cudaSetDevice(c->device);
+    { int rc0; if ((rc0 = pg_need_dtrim(c))) return rc0; }
     if (c->np > 0) fill_f64_kernel<<<(unsigned int)((c->np + 255) / 256), 256, 0, c->stream>>>(c->planes[c->cur].dtrim, c->np, c->cfg.dt);
     PG_CUDA(c, cudaGetLastError());
     return PGPU_OK;
@@ -1004,12 +1050,12 @@ int pg_fill_dtrim(pgpu_ctx* c) {
 
 extern "C" int pgpu_append_particles(pgpu_ctx* c, const void* aos, int64_t n, int32_t stride) {
     if (!c) return PGPU_ERR_INVALID;
-    if (n > 0 && c->np > 0 && !c->has_dtrim) {
-        /* the DTRIM plane is not maintained while every particle has DTRIM == DT: rebuild it so that the
-         * appended particles (DTRIM = rf()*DT after an injection, ref: src/timecycle.f90:463) can differ */
+    if (n > 0 && c->np > 0 && !c->has_dtrim && c->planes[c->cur].dtrim) {
+        /* the DTRIM plane is not maintained while every particle has DTRIM == DT: make it say so before particles that
+         * may differ are appended (DTRIM = rf()*DT after an injection, ref: src/timecycle.f90:463).  When the plane does
+         * not exist it is created only if the appended records need it (append_impl, second pass). */
         int rc0;
         if ((rc0 = pg_fill_dtrim(c))) return rc0;
-        c->has_dtrim = true;
     }
     return append_impl(c, aos, n, stride, "pgpu_append_particles");
 }
@@ -1055,8 +1101,12 @@ extern "C" int pgpu_upload_planes(pgpu_ctx* c, const void* pos, const void* vel,
     PgPlanes p = c->planes[c->cur];
     PG_CUDA(c, cudaMemcpyAsync(p.pos, pos, sizeof(PgPos) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
     PG_CUDA(c, cudaMemcpyAsync(p.vel, vel, sizeof(PgVel) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    if (ie || wants_ie(c)) {
+        if ((rc = pg_need_ie(c))) return rc;
+        p = c->planes[c->cur];
+    }
     if (ie) PG_CUDA(c, cudaMemcpyAsync(p.ie, ie, sizeof(PgIe) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
-    else if (c->ie_seen || c->any_internal_dof || c->dev.nr > 0) PG_CUDA(c, cudaMemsetAsync(p.ie, 0, sizeof(PgIe) * (size_t)n, c->stream));
+    else if (p.ie) PG_CUDA(c, cudaMemsetAsync(p.ie, 0, sizeof(PgIe) * (size_t)n, c->stream));
     const int ncells = (c->cfg.grid_type == PGPU_UNSTRUCTURED) ? (c->mesh_set ? c->nc : 0) : c->cfg.nx * c->cfg.ny;
     planes_check_kernel<<<(unsigned int)((n + 255) / 256), 256, 0, c->stream>>>(p.pos, ie ? p.ie : nullptr, n, ncells, c->d_status);
     c->np = n;
@@ -1087,7 +1137,10 @@ extern "C" int pgpu_download_planes(pgpu_ctx* c, void* pos, void* vel, void* ie,
     PgPlanes p = c->planes[c->cur];
     PG_CUDA(c, cudaMemcpyAsync(pos, p.pos, sizeof(PgPos) * (size_t)c->np, cudaMemcpyDeviceToHost, c->stream));
     PG_CUDA(c, cudaMemcpyAsync(vel, p.vel, sizeof(PgVel) * (size_t)c->np, cudaMemcpyDeviceToHost, c->stream));
-    if (ie) PG_CUDA(c, cudaMemcpyAsync(ie, p.ie, sizeof(PgIe) * (size_t)c->np, cudaMemcpyDeviceToHost, c->stream));
+    if (ie) {
+        if (p.ie) PG_CUDA(c, cudaMemcpyAsync(ie, p.ie, sizeof(PgIe) * (size_t)c->np, cudaMemcpyDeviceToHost, c->stream));
+        else memset(ie, 0, sizeof(PgIe) * (size_t)c->np);
+    }
     PG_CUDA(c, cudaStreamSynchronize(c->stream));
     return PGPU_OK;
 }
@@ -1197,7 +1250,7 @@ __global__ void __launch_bounds__(256) scatter_kernel(PgPlanes src, PgPlanes dst
         const PgRec32 V = pg_ld_stream(src.vel + i);
         *reinterpret_cast<PgRec32*>(dst.vel + o) = V;
     }
-    if (use_ie) dst.ie[o] = src.ie[i];
+    if (use_ie && src.ie) dst.ie[o] = src.ie[i];
     if (src.dtrim) dst.dtrim[o] = src.dtrim[i];
     if (src.id) dst.id[o] = src.id[i];
 }
@@ -1291,9 +1344,74 @@ int pg_resolve_vel(pgpu_ctx* c) {
     return PGPU_OK;
 }
 
+/* ---- deterministic mode (pgpu_set_deterministic): a STABLE counting sort -- radix sort of (cell, slot) pairs -- instead
+ * of the atomic per-cell cursor, so that the in-cell order, and with it the pair selection and the slot-keyed wall
+ * streams, do not depend on the order in which warps happen to reach the atomics: the same input and seed give the
+ * same particles bit for bit, run after run (the reference's counting sort is stable too, src/collisions.f90:102-112).
+ * Cost at the bench size: see DESIGN.md section 3. */
+__global__ void __launch_bounds__(256) det_keys_kernel(const PgPos* __restrict__ pos, long long n, unsigned int ncells,
+                                                       unsigned int* __restrict__ keys, unsigned int* __restrict__ vals) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int ic = pos[i].ic;
+    keys[i] = (ic >= 1) ? (unsigned int)(ic - 1) : ncells; /* tombstones sort behind the last cell */
+    vals[i] = (unsigned int)i;
+}
+__global__ void __launch_bounds__(256) det_gather_kernel(PgPlanes src, PgPlanes dst, const unsigned int* __restrict__ perm,
+                                                         const unsigned int* __restrict__ cell_off, int ncells, int use_ie) {
+    const long long n = (long long)cell_off[ncells];
+    long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= n) return;
+    const size_t i = perm[o];
+    *reinterpret_cast<PgRec32*>(dst.pos + o) = pg_ld_stream(src.pos + i);
+    *reinterpret_cast<PgRec32*>(dst.vel + o) = pg_ld_stream(src.vel + i);
+    if (use_ie && src.ie) dst.ie[o] = src.ie[i];
+    if (src.dtrim) dst.dtrim[o] = src.dtrim[i];
+    if (src.id) dst.id[o] = src.id[i];
+}
+
+static int sort_deterministic(pgpu_ctx* c, PgPlanes src, PgPlanes dst, int ncells) {
+    /* the item count must be on the host for the radix sort: this mode pays one more synchronisation */
+    unsigned long long* hn = reinterpret_cast<unsigned long long*>(&c->h_status->scratch[2]);
+    PG_CUDA(c, cudaMemcpyAsync(hn, &c->d_status->np_cur, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    PG_CUDA(c, cudaStreamSynchronize(c->stream));
+    const long long n = (long long)*hn;
+    if (c->det_cap < c->capacity) {
+        for (int k = 0; k < 4; k++) { cudaFree(c->d_det[k]); c->d_det[k] = nullptr; }
+        for (int k = 0; k < 4; k++) PG_CUDA(c, cudaMalloc((void**)&c->d_det[k], sizeof(unsigned int) * (size_t)c->capacity));
+        c->det_cap = c->capacity;
+    }
+    int bits = 1;
+    while ((1ULL << bits) <= (unsigned long long)ncells) bits++;
+    size_t tmp = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp, c->d_det[0], c->d_det[1], c->d_det[2], c->d_det[3], (int)n, 0, bits, c->stream);
+    if (tmp > c->det_tmp_bytes) {
+        cudaFree(c->d_det_tmp);
+        c->d_det_tmp = nullptr;
+        PG_CUDA(c, cudaMalloc(&c->d_det_tmp, tmp + 256));
+        c->det_tmp_bytes = tmp + 256;
+    }
+    const unsigned int blocks = (unsigned int)((n + 255) / 256);
+    if (n > 0) {
+        det_keys_kernel<<<blocks, 256, 0, c->stream>>>(src.pos, n, (unsigned int)ncells, c->d_det[0], c->d_det[2]);
+        tmp = c->det_tmp_bytes;
+        PG_CUDA(c, cub::DeviceRadixSort::SortPairs(c->d_det_tmp, tmp, c->d_det[0], c->d_det[1], c->d_det[2], c->d_det[3], (int)n, 0, bits, c->stream));
+        det_gather_kernel<<<blocks, 256, 0, c->stream>>>(src, dst, c->d_det[3], c->d_cell_off, ncells, c->dev.use_ie);
+        c->launches += 3;
+    }
+    return PGPU_OK;
+}
+
+extern "C" int pgpu_set_deterministic(pgpu_ctx* c, int32_t on) {
+    if (!c) return PGPU_ERR_INVALID;
+    c->deterministic = on != 0;
+    return PGPU_OK;
+}
+
 int pg_sort_impl(pgpu_ctx* c, bool defer_vel, bool sync_np) {
     int ncells = pg_ncells(c);
     { int rc0; if ((rc0 = pg_resolve_vel(c))) return rc0; }
+    if (c->deterministic) defer_vel = false;
     c->n_big = 0;
     c->dev.ntiles = 0;
     if (c->np_ub == 0) {
@@ -1319,11 +1437,16 @@ int pg_sort_impl(pgpu_ctx* c, bool defer_vel, bool sync_np) {
     size_t tmp = c->scan_tmp_bytes;
     PG_CUDA(c, cub::DeviceScan::ExclusiveSum(c->d_scan_tmp, tmp, c->d_cell_count, c->d_cell_off, ncells + 1, c->stream));
     c->launches++;
-    /* the histogram has been scanned into cell_off: its array now serves as the per-cell cursor of the scatter */
-    PG_CUDA(c, cudaMemsetAsync(c->d_cell_count, 0, sizeof(unsigned int) * ((size_t)ncells + 1), c->stream));
-    scatter_kernel<<<blocks, 256, 0, c->stream>>>(src, dst, c->d_status, c->d_cell_off, c->d_cell_count, c->dev.use_ie,
-                                                  defer_vel ? c->d_src_of : nullptr);
-    c->launches++;
+    if (c->deterministic) {
+        int rcd;
+        if ((rcd = sort_deterministic(c, src, dst, ncells))) return rcd;
+    } else {
+        /* the histogram has been scanned into cell_off: its array now serves as the per-cell cursor of the scatter */
+        PG_CUDA(c, cudaMemsetAsync(c->d_cell_count, 0, sizeof(unsigned int) * ((size_t)ncells + 1), c->stream));
+        scatter_kernel<<<blocks, 256, 0, c->stream>>>(src, dst, c->d_status, c->d_cell_off, c->d_cell_count, c->dev.use_ie,
+                                                      defer_vel ? c->d_src_of : nullptr);
+        c->launches++;
+    }
     {
         unsigned int cb = (unsigned int)((ncells + 255) / 256);
         cell_tail_kernel<<<cb, 256, 0, c->stream>>>(c->d_cell_off, ncells, c->d_big_list, c->big_alloc, c->d_status);

@@ -113,98 +113,113 @@ __device__ __forceinline__ bool pair_accept(const PgDev& d, double rfp, const do
     return rfp < collprob;
 }
 
-/* an ACCEPTED candidate: reactions, Borgnakke-Larsen, VSS deflection, ref: src/collisions.f90:327-546.
- * g continues the candidate's stream right after the acceptance draw. */
-/* gate_all: MCC_COLLISIONS skips a reaction whose activation energy is not exceeded whatever its type
- * (ref: :1383-1384); VSS_COLLIS applies that test to TCE reactions only (ref: :349-350). */
-__device__ int pair_collide(const PgDev& d, PgRng& g, PairIO& p, long long gslot2, int cell0, bool gate_all = false) {
-    const double PI2 = 2. * PG_PI;
-    double* c1 = p.c1;
-    double* c2 = p.c2;
+/* An ACCEPTED candidate, ref: src/collisions.f90:327-546, in three pieces so that the lane-per-cell kernel can keep its
+ * warp together: (1) the reaction test, (2) the redistribution after a reaction -- rare and long, batched there --,
+ * (3) Borgnakke-Larsen + VSS deflection.  g continues the candidate's stream right after the acceptance draw.
+ * gate_all: MCC_COLLISIONS skips a reaction whose activation energy is not exceeded whatever its type (ref: :1383-1384);
+ * VSS_COLLIS applies that test to TCE reactions only (ref: :349-350). */
+
+/* (1) ref: :331-352: returns the index of the reaction that fires (ecoll_out = ECOLL - EA) or -1 */
+__device__ __forceinline__ int pair_react_test(const PgDev& d, PgRng& g, const PairIO& p, bool gate_all, double& ecoll_out) {
+    if (d.nr == 0) return -1;
+    const double* c1 = p.c1;
+    const double* c2 = p.c2;
     const int s1 = p.s1, s2 = p.s2;
-    double vr2 = (c2[0] - c1[0]) * (c2[0] - c1[0]) + (c2[1] - c1[1]) * (c2[1] - c1[1]) + (c2[2] - c1[2]) * (c2[2] - c1[2]);
-    double vr = sqrt(vr2);
-    double cref = VSS2(d.grefs, s1, s2), sigma = VSS2(d.sigmas, s1, s2);
-    double omega = VSS2(d.omegas, s1, s2), alpha = VSS2(d.alphas, s1, s2);
-    double m1 = __ldg(&d.mass[s1 - 1]), m2 = __ldg(&d.mass[s2 - 1]);
-    double mred = m1 * m2 / (m1 + m2);
-    double etr = 0.5 * mred * vr2;
-    double rfp;
-    int flags = PR_ACCEPTED;
-
-    int rd1 = __ldg(&d.rotdof[s1 - 1]), rd2 = __ldg(&d.rotdof[s2 - 1]);
-    int vd1 = __ldg(&d.vibdof[s1 - 1]), vd2 = __ldg(&d.vibdof[s2 - 1]);
-    double erot1 = p.erot1, evib1 = p.evib1, erot2 = p.erot2, evib2 = p.evib2;
-
-    /* ref: :331-449 TCE / LXCat reaction test */
-    double ecoll = etr + erot1 + erot2 + evib1 + evib2;
+    const double vr2 = (c2[0] - c1[0]) * (c2[0] - c1[0]) + (c2[1] - c1[1]) * (c2[1] - c1[1]) + (c2[2] - c1[2]) * (c2[2] - c1[2]);
+    const double vr = sqrt(vr2);
+    const double m1 = __ldg(&d.mass[s1 - 1]), m2 = __ldg(&d.mass[s2 - 1]);
+    const double mred = m1 * m2 / (m1 + m2);
+    const double etr = 0.5 * mred * vr2;
+    const double ecoll = etr + p.erot1 + p.erot2 + p.evib1 + p.evib2;
     for (int jr = 0; jr < d.nr; jr++) {
-        const PgReaction r = d.reac[jr];
-        if (r.r1 != s1) {
-            if (r.r1 != s2) continue;
-            else if (r.r2 != s1) continue;
+        const PgReaction* r = &d.reac[jr];
+        const int rr1 = __ldg(&r->r1), rr2 = __ldg(&r->r2);
+        if (rr1 != s1) {
+            if (rr1 != s2) continue;
+            else if (rr2 != s1) continue;
         } else {
-            if (r.r2 != s2) continue;
+            if (rr2 != s2) continue;
         }
-        double ea = r.ea, ptce;
+        const double ea = __ldg(&r->ea);
+        const int type = __ldg(&r->type);
+        double ptce;
         if (gate_all && ecoll <= ea) continue;
-        if (r.type == PGPU_TCE) {
+        if (type == PGPU_TCE) {
             if (ecoll <= ea) continue;
-            ptce = r.c1 * pow(ecoll - ea, r.c2) * pow(1. - ea / ecoll, r.c3);
-        } else if (r.type == PGPU_LXCAT) {
-            double sigma_r = pg_interp_cs(etr, r.tab_n, d.tab_e + r.tab_off, d.tab_cs + r.tab_off);
+            ptce = __ldg(&r->c1) * pow(ecoll - ea, __ldg(&r->c2)) * pow(1. - ea / ecoll, __ldg(&r->c3));
+        } else if (type == PGPU_LXCAT) {
+            const double cref = VSS2(d.grefs, s1, s2), sigma = VSS2(d.sigmas, s1, s2), omega = VSS2(d.omegas, s1, s2);
+            double sigma_r = pg_interp_cs(etr, r->tab_n, d.tab_e + r->tab_off, d.tab_cs + r->tab_off);
             ptce = sigma_r / (sigma * pow(vr / cref, 1. - 2. * omega));
         } else {
             ptce = 0;
         }
-        rfp = g.rf();
+        const double rfp = g.rf();
         if (rfp < ptce) {
-            ecoll = ecoll - ea;
-            /* roles are NOT swapped when the pair order is opposite to the reaction */
-            const PgPos P2 = d.p.pos[gslot2];
-            pg_react_redistribute(d, g, r, ecoll, c1, c2, erot1, evib1, erot2, evib2, P2.x, P2.y, P2.z, cell0 + 1);
-            p.s1 = r.p1;
-            p.s2 = r.p2;
-            p.erot1 = erot1; p.evib1 = evib1; p.erot2 = erot2; p.evib2 = evib2;
-            return flags | PR_REACTED | PR_V | PR_E1 | PR_E2 | PR_S;
+            ecoll_out = ecoll - ea;
+            return jr;
         }
     }
+    return -1;
+}
 
-    /* ref: :454-490 Borgnakke-Larsen, at most one mode */
+/* (2) ref: :353-447.  Roles are NOT swapped when the pair order is opposite to the reaction. */
+__device__ int pair_react_apply(const PgDev& d, PgRng& g, PairIO& p, int jr, double ecoll, long long gslot2, int cell0) {
+    const PgReaction r = d.reac[jr];
+    double erot1 = p.erot1, evib1 = p.evib1, erot2 = p.erot2, evib2 = p.evib2;
+    const PgPos P2 = d.p.pos[gslot2];
+    pg_react_redistribute(d, g, r, ecoll, p.c1, p.c2, erot1, evib1, erot2, evib2, P2.x, P2.y, P2.z, cell0 + 1);
+    p.s1 = r.p1;
+    p.s2 = r.p2;
+    p.erot1 = erot1; p.evib1 = evib1; p.erot2 = erot2; p.evib2 = evib2;
+    return PR_ACCEPTED | PR_REACTED | PR_V | PR_E1 | PR_E2 | PR_S;
+}
+
+/* (3) ref: :454-546 Borgnakke-Larsen (at most one mode) + VSS deflection.  The four branches of the reference's
+ * IF / ELSE IF chain differ only in WHICH energy is redrawn: the mode is selected first and COLL_INTERNAL_ENERGY is
+ * called from one place, so that the lanes of a warp share its rejection loop instead of running it four times over. */
+__device__ int pair_inelastic_vss(const PgDev& d, PgRng& g, PairIO& p) {
+    const double PI2 = 2. * PG_PI;
+    double* c1 = p.c1;
+    double* c2 = p.c2;
+    const int s1 = p.s1, s2 = p.s2;
+    const double vr2 = (c2[0] - c1[0]) * (c2[0] - c1[0]) + (c2[1] - c1[1]) * (c2[1] - c1[1]) + (c2[2] - c1[2]) * (c2[2] - c1[2]);
+    const double omega = VSS2(d.omegas, s1, s2), alpha = VSS2(d.alphas, s1, s2);
+    const double m1 = __ldg(&d.mass[s1 - 1]), m2 = __ldg(&d.mass[s2 - 1]);
+    const double mred = m1 * m2 / (m1 + m2);
+    double etr = 0.5 * mred * vr2;
+    int flags = PR_ACCEPTED;
+    const int rd1 = __ldg(&d.rotdof[s1 - 1]), rd2 = __ldg(&d.rotdof[s2 - 1]);
+    const int vd1 = __ldg(&d.vibdof[s1 - 1]), vd2 = __ldg(&d.vibdof[s2 - 1]);
+    const double rr1 = __ldg(&d.rotrel[s1 - 1]), rr2 = __ldg(&d.rotrel[s2 - 1]);
+    const double vr1 = __ldg(&d.vibrel[s1 - 1]), vr2_ = __ldg(&d.vibrel[s2 - 1]);
     double trdof = 3.;
-    double prot1 = (trdof + rd1) / trdof * __ldg(&d.rotrel[s1 - 1]);
-    double prot2 = (trdof + rd2) / trdof * __ldg(&d.rotrel[s2 - 1]);
-    double pvib1 = (trdof + vd1) / trdof * __ldg(&d.vibrel[s1 - 1]);
-    double pvib2 = (trdof + vd2) / trdof * __ldg(&d.vibrel[s2 - 1]);
+    const double prot1 = (trdof + rd1) / trdof * rr1;
+    const double prot2 = (trdof + rd2) / trdof * rr2;
+    const double pvib1 = (trdof + vd1) / trdof * vr1;
+    const double pvib2 = (trdof + vd2) / trdof * vr2_;
     trdof = 5. - 2. * omega;
     /* when neither species can exchange internal energy the selector cannot fall in any branch and its draw is not
      * taken from the stream (stream contract shared with the oracle's rng_mode 1) */
-    if (__ldg(&d.rotrel[s1 - 1]) + __ldg(&d.rotrel[s2 - 1]) + __ldg(&d.vibrel[s1 - 1]) + __ldg(&d.vibrel[s2 - 1]) == 0.) rfp = 1.;
+    double rfp;
+    if (rr1 + rr2 + vr1 + vr2_ == 0.) rfp = 1.;
     else rfp = g.rf();
-    if (rfp < prot1) {
-        ecoll = etr + erot1;
-        erot1 = coll_internal_energy(g, ecoll, trdof, rd1);
-        etr = ecoll - erot1;
-        p.erot1 = erot1;
-        flags |= PR_E1;
-    } else if (rfp < prot1 + prot2) {
-        ecoll = etr + erot2;
-        erot2 = coll_internal_energy(g, ecoll, trdof, rd2);
-        etr = ecoll - erot2;
-        p.erot2 = erot2;
-        flags |= PR_E2;
-    } else if (rfp < prot1 + prot2 + pvib1) {
-        ecoll = etr + evib1;
-        evib1 = coll_internal_energy(g, ecoll, trdof, vd1);
-        etr = ecoll - evib1;
-        p.evib1 = evib1;
-        flags |= PR_E1;
-    } else if (rfp < prot1 + prot2 + pvib1 + pvib2) {
-        ecoll = etr + evib2;
-        evib2 = coll_internal_energy(g, ecoll, trdof, vd2);
-        etr = ecoll - evib2;
-        p.evib2 = evib2;
-        flags |= PR_E2;
+    int mode = 0; /* 1 rot of particle 1, 2 rot of 2, 3 vib of 1, 4 vib of 2 */
+    if (rfp < prot1) mode = 1;
+    else if (rfp < prot1 + prot2) mode = 2;
+    else if (rfp < prot1 + prot2 + pvib1) mode = 3;
+    else if (rfp < prot1 + prot2 + pvib1 + pvib2) mode = 4;
+    if (mode) {
+        const double eold = (mode == 1) ? p.erot1 : (mode == 2) ? p.erot2 : (mode == 3) ? p.evib1 : p.evib2;
+        const int dof = (mode == 1) ? rd1 : (mode == 2) ? rd2 : (mode == 3) ? vd1 : vd2;
+        const double ecoll = etr + eold;
+        const double enew = coll_internal_energy(g, ecoll, trdof, dof);
+        etr = ecoll - enew;
+        if (mode == 1) p.erot1 = enew;
+        else if (mode == 2) p.erot2 = enew;
+        else if (mode == 3) p.evib1 = enew;
+        else p.evib2 = enew;
+        flags |= (mode == 1 || mode == 3) ? PR_E1 : PR_E2;
     }
 
     /* ref: :495-546 VSS deflection */
@@ -238,6 +253,14 @@ __device__ int pair_collide(const PgDev& d, PgRng& g, PairIO& p, long long gslot
         c2[i] = wc[i] - m1 / (m1 + m2) * grel[i];
     }
     return flags | PR_V;
+}
+
+/* the three pieces in sequence (GLOBAL path, MCC_COLLISIONS) */
+__device__ int pair_collide(const PgDev& d, PgRng& g, PairIO& p, long long gslot2, int cell0, bool gate_all = false) {
+    double ecoll = 0.;
+    const int jr = pair_react_test(d, g, p, gate_all, ecoll);
+    if (jr >= 0) return pair_react_apply(d, g, p, jr, ecoll, gslot2, cell0);
+    return pair_inelastic_vss(d, g, p);
 }
 
 /* one candidate pair of VSS_COLLIS start to end (GLOBAL path) */
@@ -296,6 +319,26 @@ __device__ __forceinline__ void pair_collide_fast(const PgDev& d, PgRng& g, doub
     for (int i = 0; i < 3; i++) {
         c1[i] = wc[i] + m2 / (m1 + m2) * grel[i];
         c2[i] = wc[i] - m1 / (m1 + m2) * grel[i];
+    }
+}
+
+/* pair -> store, by what the collision touched */
+template <bool IE>
+__device__ __forceinline__ void write_pair(const PgDev& d, const PairIO& p, unsigned int j1, unsigned int j2, int fl) {
+    if (fl & (PR_V | PR_S)) {
+        PgVel W1, W2;
+        W1.vx = p.c1[0]; W1.vy = p.c1[1]; W1.vz = p.c1[2]; W1.sid = p.s1; W1.pad = 0;
+        W2.vx = p.c2[0]; W2.vy = p.c2[1]; W2.vz = p.c2[2]; W2.sid = p.s2; W2.pad = 0;
+        d.p.vel[j1] = W1;
+        d.p.vel[j2] = W2;
+    }
+    if (IE) {
+        if (fl & PR_E1) { PgIe E; E.erot = p.erot1; E.evib = p.evib1; d.p.ie[j1] = E; }
+        if (fl & PR_E2) { PgIe E; E.erot = p.erot2; E.evib = p.evib2; d.p.ie[j2] = E; }
+        if (fl & PR_S) { /* the species mirror in the pos records */
+            d.p.pos[j1].sid = p.s1;
+            d.p.pos[j2].sid = p.s2;
+        }
     }
 }
 
@@ -363,18 +406,22 @@ __global__ void __launch_bounds__(128, IE ? PG_CELL_MINBLOCKS_IE : PG_CELL_MINBL
 
     int nacc = 0, nreac = 0;
     int j = 0;
-    while (__any_sync(FULL, j < ncoll)) {
+    /* state that survives a loop trip only for a lane parked on a reaction (IE) */
+    int react_jr = -1;
+    double react_ecoll = 0.;
+    unsigned int j1 = 0, j2 = 0, jhit = 0, used = 4;
+    PairIO p;
+    PgRng rng;
+    rng.init(d.seed_local, 2, d.tID, (unsigned long long)c, 0ULL);
+    while (__any_sync(FULL, j < ncoll || react_jr >= 0)) {
         /* cheap part: this lane's next candidates, up to and including its next accepted one; bounded, so that
          * the lanes that already hold an accepted candidate do not idle behind the unluckiest lane */
         bool hit = false;
-        unsigned int j1 = 0, j2 = 0, jhit = 0, used = 4;
-        PairIO p;
-        for (int tries = 0; tries < PG_CELL_TRIES && j < ncoll && !hit; tries++) {
+        for (int tries = 0; tries < PG_CELL_TRIES && j < ncoll && !hit && react_jr < 0; tries++) {
             /* ref: :263-271.  The first block of the candidate's stream (PgRng contract: kind 2, cell, candidate)
              * holds everything a candidate needs: word 0 -> first index, word 1 -> second index, words 2,3 -> the
              * acceptance draw (n <= PG_TILE_BIG here, so the indices are one-word picks).  Only a repeated index
              * (probability 1/n) goes on through the general stream. */
-            PgRng rng;
             rng.init(d.seed_local, 2, d.tID, (unsigned long long)c, (unsigned long long)j);
             uint32_t o[4];
             pg_philox(0u, rng.e0, rng.e1, rng.e2, rng.k0, rng.k1, o);
@@ -400,9 +447,8 @@ __global__ void __launch_bounds__(128, IE ? PG_CELL_MINBLOCKS_IE : PG_CELL_MINBL
         /* expensive part, for all lanes that hold an accepted candidate */
         if (hit) {
             nacc++;
-            PgRng rng; /* the candidate's stream, right after its acceptance draw */
-            rng.init(d.seed_local, 2, d.tID, (unsigned long long)c, (unsigned long long)jhit);
-            rng.seek(used);
+            rng.init(d.seed_local, 2, d.tID, (unsigned long long)c, (unsigned long long)jhit); /* the candidate's stream, */
+            rng.seek(used);                                                                     /* after its acceptance draw */
             if (!IE) {
                 pair_collide_fast(d, rng, p.c1, p.c2, p.s1, p.s2);
                 PgVel W1, W2;
@@ -413,20 +459,30 @@ __global__ void __launch_bounds__(128, IE ? PG_CELL_MINBLOCKS_IE : PG_CELL_MINBL
             } else {
                 const PgIe E1 = d.p.ie[j1], E2 = d.p.ie[j2];
                 p.erot1 = E1.erot; p.evib1 = E1.evib; p.erot2 = E2.erot; p.evib2 = E2.evib;
-                const int fl = pair_collide(d, rng, p, (long long)j2, (int)c);
-                if (fl & PR_REACTED) nreac++;
-                if (fl & (PR_V | PR_S)) {
-                    PgVel W1, W2;
-                    W1.vx = p.c1[0]; W1.vy = p.c1[1]; W1.vz = p.c1[2]; W1.sid = p.s1; W1.pad = 0;
-                    W2.vx = p.c2[0]; W2.vy = p.c2[1]; W2.vz = p.c2[2]; W2.sid = p.s2; W2.pad = 0;
-                    d.p.vel[j1] = W1;
-                    d.p.vel[j2] = W2;
+                react_jr = pair_react_test(d, rng, p, false, react_ecoll);
+                if (react_jr < 0) {
+                    const int fl = pair_inelastic_vss(d, rng, p);
+                    write_pair<IE>(d, p, j1, j2, fl);
                 }
-                if (fl & PR_E1) { PgIe E; E.erot = p.erot1; E.evib = p.evib1; d.p.ie[j1] = E; }
-                if (fl & PR_E2) { PgIe E; E.erot = p.erot2; E.evib = p.evib2; d.p.ie[j2] = E; }
-                if (fl & PR_S) { /* the species mirror in the pos records */
-                    d.p.pos[j1].sid = p.s1;
-                    d.p.pos[j2].sid = p.s2;
+            }
+        }
+        if (IE) {
+            /* A reaction (energy redistribution over the products' modes, two isotropic scatterings, a third product)
+             * is rare -- about one accepted pair in a hundred in hot air -- and about ten times longer than an inelastic
+             * collision; run as it comes it would leave one or two lanes working while thirty wait (ncu r02f: 6 of 32
+             * lanes active).  A lane whose pair reacts PARKS (its cell's later candidates must see the products, so
+             * the lane does not go on) until a quarter of the warp is parked or nobody else has work; then the parked
+             * lanes run the redistribution together. */
+            const unsigned int parked = __ballot_sync(FULL, react_jr >= 0);
+            if (parked) {
+                const unsigned int working = __ballot_sync(FULL, react_jr < 0 && j < ncoll);
+                if (__popc(parked) >= 8 || !working) {
+                    if (react_jr >= 0) {
+                        nreac++;
+                        const int fl = pair_react_apply(d, rng, p, react_jr, react_ecoll, (long long)j2, (int)c);
+                        write_pair<IE>(d, p, j1, j2, fl);
+                        react_jr = -1;
+                    }
                 }
             }
         }
@@ -462,7 +518,7 @@ __global__ void __launch_bounds__(128) mcc_vss_kernel(const __grid_constant__ Pg
     const int sp1 = P1.sid; /* SP_ID1 is read once (:1291) and NOT refreshed after a reaction */
     int sid_now = sp1;
     const PgVel V1 = d.p.vel[jp1];
-    const PgIe E1 = d.p.ie[jp1];
+    const PgIe E1 = pg_ie_load(d.p.ie, jp1);
     PairIO p;
     p.c1[0] = V1.vx; p.c1[1] = V1.vy; p.c1[2] = V1.vz;
     p.erot1 = E1.erot; p.evib1 = E1.evib;
@@ -499,7 +555,7 @@ __global__ void __launch_bounds__(128) mcc_vss_kernel(const __grid_constant__ Pg
         W.vx = p.c1[0]; W.vy = p.c1[1]; W.vz = p.c1[2]; W.sid = sid_now; W.pad = 0;
         d.p.vel[jp1] = W;
     }
-    if (dirty & PR_E1) { PgIe E; E.erot = p.erot1; E.evib = p.evib1; d.p.ie[jp1] = E; }
+    if (dirty & PR_E1) pg_ie_store(d.p.ie, jp1, p.erot1, p.evib1, d.status);
     if (dirty & PR_S) d.p.pos[jp1].sid = sid_now;
     if (ncoll) atomicAdd(&d.status->ncoll, (unsigned long long)ncoll);
     if (nreac) atomicAdd(&d.status->nreac, (unsigned long long)nreac);

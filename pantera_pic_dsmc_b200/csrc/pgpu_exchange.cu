@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(256) xpack_kernel(const __grid_constant__ PgDe
     unsigned long long k = xoff[dest] + atomicAdd(&xcursor[dest], 1ULL);
     double* r = sendbuf + k * XREC_DOUBLES;
     const PgVel V = d.p.vel[i];
-    const PgIe E = d.p.ie[i];
+    const PgIe E = pg_ie_load(d.p.ie, i);
     r[0] = P.x; r[1] = P.y; r[2] = P.z;
     r[3] = V.vx; r[4] = V.vy; r[5] = V.vz;
     r[6] = E.erot; r[7] = E.evib;
@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(256) xpack_list_kernel(const __grid_constant__
     unsigned long long k = xoff[dest] + atomicAdd(&xcursor[dest], 1ULL);
     double* r = sendbuf + k * XREC_DOUBLES;
     const PgVel V = d.p.vel[i];
-    const PgIe E = d.p.ie[i];
+    const PgIe E = pg_ie_load(d.p.ie, i);
     r[0] = P.x; r[1] = P.y; r[2] = P.z;
     r[3] = V.vx; r[4] = V.vy; r[5] = V.vz;
     r[6] = E.erot; r[7] = E.evib;
@@ -165,10 +165,11 @@ __global__ void __launch_bounds__(256) xunpack_kernel(const __grid_constant__ Pg
     E.erot = r[6]; E.evib = r[7];
     p.pos[o] = P;
     p.vel[o] = V;
-    p.ie[o] = E;
+    pg_ie_store(p.ie, o, E.erot, E.evib, d.status);
     if (E.erot != 0. || E.evib != 0.) d.status->flag_ie = 1;
     double dtrim = r[8];
-    p.dtrim[o] = dtrim;
+    if (p.dtrim) p.dtrim[o] = dtrim;
+    else if (dtrim != d.dt) d.status->need_dtrim = 1;
     if (dtrim != d.dt) d.status->flag_dtrim = 1;
     t = r[10];
     if (p.id) p.id[o] = *reinterpret_cast<long long*>(&t);
@@ -224,7 +225,7 @@ __global__ void __launch_bounds__(256) xpack_fast_kernel(const __grid_constant__
         }
         double* r = sendbuf + ((size_t)plan.off[dest] + 1 + k) * XREC_DOUBLES;
         const PgVel V = d.p.vel[i];
-        const PgIe E = d.p.ie[i];
+        const PgIe E = pg_ie_load(d.p.ie, i);
         r[0] = P.x; r[1] = P.y; r[2] = P.z;
         r[3] = V.vx; r[4] = V.vy; r[5] = V.vz;
         r[6] = E.erot; r[7] = E.evib;
@@ -282,7 +283,7 @@ __global__ void __launch_bounds__(256) xunpack_fast_kernel(const __grid_constant
         E.erot = r[6]; E.evib = r[7];
         p.pos[o] = P;
         p.vel[o] = V;
-        p.ie[o] = E;
+        pg_ie_store(p.ie, o, E.erot, E.evib, d.status);
         if (E.erot != 0. || E.evib != 0.) d.status->flag_ie = 1;
         if (p.dtrim) p.dtrim[o] = r[8];
         t = r[10];

@@ -59,12 +59,11 @@ __device__ __forceinline__ void append(const PgDev& d, double x, double y, doubl
     P.x = x; P.y = y; P.z = z; P.ic = ic; P.sid = sid;
     PgVel V;
     V.vx = v[0]; V.vy = v[1]; V.vz = v[2]; V.sid = sid; V.pad = 0;
-    PgIe E;
-    E.erot = erot; E.evib = evib;
     d.p.pos[o] = P;
     d.p.vel[o] = V;
-    d.p.ie[o] = E;
+    pg_ie_store(d.p.ie, o, erot, evib, d.status);
     if (d.p.dtrim) d.p.dtrim[o] = dtrim;
+    else if (dtrim != d.dt) d.status->need_dtrim = 1;
     if (d.p.id) d.p.id[o] = (long long)d.rank + ((d.id_base + (long long)k) << 8);
     if (erot != 0. || evib != 0.) d.status->flag_ie = 1;
 }
@@ -434,6 +433,7 @@ static int begin_create(pgpu_ctx* c, double expect, bool own_dtrim) {
         return rc;
     }
     if ((rc = pg_resolve_vel(c))) return rc;
+    if (c->any_internal_dof && (rc = pg_need_ie(c))) return rc;
     if (own_dtrim && !c->has_dtrim) {
         /* emitted particles carry DTRIM = rf()*DT (src/timecycle.f90:463): the plane must hold DT for everybody else */
         if ((rc = pg_fill_dtrim(c))) return rc;

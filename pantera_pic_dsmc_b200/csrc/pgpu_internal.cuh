@@ -97,6 +97,7 @@ struct PgStatus {
     int flag_dtrim;                 /* some uploaded/received particle has DTRIM != DT   */
     int flag_ie;                    /* some uploaded/received particle has EROT/EVIB != 0 */
     unsigned int n_big;             /* cells with more particles than a collision tile holds */
+    int need_ie, need_dtrim;        /* a kernel had internal energy / a DTRIM != DT to store but the plane does not exist */
     unsigned int scratch[4];        /* host landing zone of small read-backs (pinned copy only) */
     unsigned long long x_sent[64];  /* EXCHANGE fast path: emigrants per destination ...                            */
     unsigned long long x_recv[64];  /* ... and immigrants per source (they size the next step's messages)          */
@@ -371,6 +372,13 @@ struct pgpu_ctx {
     double* d_surface_charge;
     long long nsc;
 
+    /* deterministic mode: radix-sort scratch (keys in/out, slots in/out) */
+    bool deterministic = false;
+    unsigned int* d_det[4] = {nullptr, nullptr, nullptr, nullptr};
+    long long det_cap = 0;
+    void* d_det_tmp = nullptr;
+    size_t det_tmp_bytes = 0;
+
     /* injection (pgpu_inject.cu), field step (pgpu_field.cu) */
     void* inject = nullptr;
     void* field = nullptr;
@@ -439,7 +447,9 @@ int pg_collide_impl(pgpu_ctx* c, int tID, bool big_now = true); /* CELL path (as
 int pg_collide_big(pgpu_ctx* c);             /* GLOBAL path for the oversized cells + end of a deferred vel reorder */
 int pg_exchange_impl(pgpu_ctx* c);
 void pg_refresh_dev(pgpu_ctx* c);
-int pg_fill_dtrim(pgpu_ctx* c);               /* DTRIM plane = DT for the particles in the store */
+int pg_fill_dtrim(pgpu_ctx* c);               /* DTRIM plane (allocated on first use) = DT for the particles in the store */
+int pg_need_ie(pgpu_ctx* c);                  /* allocate the internal-energy planes (zero) if they do not exist yet */
+int pg_need_dtrim(pgpu_ctx* c);               /* allocate the DTRIM planes if they do not exist yet */
 void pg_inject_destroy(pgpu_ctx* c);
 void pg_field_destroy(pgpu_ctx* c);
 int pg_adopt_efield(pgpu_ctx* c, double* d_e); /* a device array becomes E_FIELD (owned by the context from then on) */
@@ -614,5 +624,18 @@ __device__ __forceinline__ double pg_interp_cs(double e, int n, const double* __
 }
 
 __device__ __forceinline__ void pg_set_err(const PgDev& d, int code) { atomicCAS(&d.status->err, 0, code); }
+
+/* The internal-energy and DTRIM planes exist only while something can live in them (pg_need_ie / pg_need_dtrim): a
+ * missing plane reads as {0, 0} / DT and swallows stores of exactly that; a store of anything else raises the status
+ * flag the host turns into the allocation (10^9 argon particles on one B200: 48 GB that are never touched). */
+__device__ __forceinline__ PgIe pg_ie_load(const PgIe* ie, long long i) {
+    if (ie) return ie[i];
+    PgIe z; z.erot = 0.; z.evib = 0.;
+    return z;
+}
+__device__ __forceinline__ void pg_ie_store(PgIe* ie, long long i, double erot, double evib, PgStatus* st) {
+    if (ie) { PgIe E; E.erot = erot; E.evib = evib; ie[i] = E; }
+    else if (erot != 0. || evib != 0.) st->need_ie = 1;
+}
 
 #endif /* __CUDACC__ */

@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(256) dump_pack_kernel(PgPlanes p, long long ba
     const long long o = base + i;
     const PgPos P = p.pos[o];
     const PgVel V = p.vel[o];
-    const PgIe E = p.ie[o];
+    const PgIe E = pg_ie_load(p.ie, o);
     const double f[8] = {P.x, P.y, P.z, V.vx, V.vy, V.vz, E.erot, E.evib};
     unsigned int* w = out + (size_t)i * (DUMP_REC / 4);
     w[0] = bswap32(80u);
@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(256) dump_pack_kernel(PgPlanes p, long long ba
     }
     w[17] = bswap32((unsigned int)P.sid);
     w[18] = bswap32((unsigned int)P.ic);
-    const unsigned long long b = bswap64((unsigned long long)__double_as_longlong(has_dtrim ? p.dtrim[o] : dt));
+    const unsigned long long b = bswap64((unsigned long long)__double_as_longlong((has_dtrim && p.dtrim) ? p.dtrim[o] : dt));
     w[19] = (unsigned int)(b & 0xffffffffULL);
     w[20] = (unsigned int)(b >> 32);
     w[21] = bswap32(80u);
@@ -78,8 +78,8 @@ __global__ void __launch_bounds__(256) dump_unpack_kernel(const unsigned int* __
     E.erot = f[6]; E.evib = f[7];
     p.pos[o] = P;
     p.vel[o] = V;
-    p.ie[o] = E;
-    p.dtrim[o] = dt; /* INIT_PARTICLE(..., DT, ...), ref: src/tools.f90:497 */
+    pg_ie_store(p.ie, o, E.erot, E.evib, st);
+    if (p.dtrim) p.dtrim[o] = dt; /* INIT_PARTICLE(..., DT, ...), ref: src/tools.f90:497 */
     if (p.id) p.id[o] = (long long)rank + ((id_base + i) << 8);
     if (E.erot != 0. || E.evib != 0.) st->flag_ie = 1;
     if (bswap32(w[0]) != 80u || bswap32(w[21]) != 80u) atomicCAS(&st->err, 0, PG_DEVERR_CELL_RANGE);

@@ -57,11 +57,9 @@ static __device__ long long pg_append_particle(const PgDev& d, double x, double 
     P.x = x; P.y = y; P.z = z; P.ic = ic; P.sid = sid;
     PgVel V;
     V.vx = vx; V.vy = vy; V.vz = vz; V.sid = sid; V.pad = 0;
-    PgIe E;
-    E.erot = erot; E.evib = evib;
     d.p.pos[o] = P;
     d.p.vel[o] = V;
-    d.p.ie[o] = E;
+    pg_ie_store(d.p.ie, o, erot, evib, d.status);
     if (d.p.dtrim) d.p.dtrim[o] = d.dt;
     if (d.p.id) d.p.id[o] = (long long)d.rank + ((d.id_base + (long long)k) << 8);
     return o;

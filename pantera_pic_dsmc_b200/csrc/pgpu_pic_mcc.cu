@@ -157,16 +157,14 @@ __global__ void __launch_bounds__(128) mcc_vahedi_kernel(const __grid_constant__
                 double x = P1.x, y = P1.y, z = P1.z;
                 atomicAdd(&d.status->nreac, 1ULL);
                 double ecoll = etr - ea;
-                const PgIe E1 = d.p.ie[jp1];
+                const PgIe E1 = pg_ie_load(d.p.ie, jp1);
                 double erot1 = E1.erot, evib1 = E1.evib;
                 int bad = 0;
                 if (!r.is_cex) {
                     /* products past the second are appended by the redistribution itself; the oracle
                      * appends the partner first, so creation order differs but not the set of particles */
                     bad = pg_react_redistribute(d, g, r, ecoll, c1, c2, erot1, evib1, erot2, evib2, x, y, z, ic);
-                    PgIe E;
-                    E.erot = erot1; E.evib = evib1;
-                    d.p.ie[jp1] = E;
+                    pg_ie_store(d.p.ie, jp1, erot1, evib1, d.status);
                 }
                 (void)bad;
                 PgVel W;

@@ -432,7 +432,7 @@ def pinned_array(n: int, dtype) -> np.ndarray:
 def c5_channel_strip(ncx: int, ncy: int, ncz: int, n: int, rank: int = 0, world: int = 1, seed: int = 2,
                      T0: float = 300.0, nrho: float = 1e20, cell_mfp: float = 0.5, dt_frac: float = 0.2,
                      u_drift: float = 100.0, wall_temp: float = 400.0, pinned: bool = False,
-                     rng_seed_global: int = 65644, mesh: Optional[mg.Mesh] = None) -> Workload:
+                     rng_seed_global: int = 65644, mesh: Optional[mg.Mesh] = None, lazy: bool = False) -> Workload:
     """C5 at bench scale.  The whole channel is world*ncx x ncy x ncz cubes (mesh replicated on every rank,
     as the reference does, grid_and_partition.f90:123-353); rank r owns the x-strip r and seeds n particles
     uniformly in it (all Kuhn tets of the regular box have the same volume)."""
@@ -456,16 +456,15 @@ def c5_channel_strip(ncx: int, ncy: int, ncz: int, n: int, rank: int = 0, world:
                            rng_seed_global=rng_seed_global, dump_bound_avg_every=0)
     bcs = dict(particle_bc=[capi.SPECULAR, capi.SPECULAR, capi.DIFFUSE, capi.DIFFUSE, capi.SPECULAR, capi.SPECULAR],
                wall_temp=[wall_temp] * 6, acc_n=[1.0] * 6, acc_t=[1.0] * 6)
-    p = pinned_particles(n) if pinned else np.zeros(n, dtype=capi.PARTICLE_DTYPE)
     cn = np.asarray(mesh.cell_nodes)
     xyz = np.asarray(mesh.node_coords)
     sig = np.sqrt(KB * T0 / m)
     chunk = 2_000_000
 
-    def fill(a):
+    def fill_into(q, a, b):
+        """particles [a, b) of the strip (a is a multiple of the chunk size) into the record array q of length b - a"""
         # one generator per chunk (seeded by (seed, chunk index)): chunks are independent, so they are filled by a
         # few host threads -- NumPy releases the GIL in the generators, the gathers and the element-wise kernels
-        b = min(n, a + chunk)
         k = b - a
         rng = np.random.default_rng([seed, a // chunk])
         ci = rng.integers(rank * ncx, (rank + 1) * ncx, k)
@@ -475,7 +474,6 @@ def c5_channel_strip(ncx: int, ncy: int, ncz: int, n: int, rank: int = 0, world:
         lam = rng.exponential(size=(4, k))
         lam /= lam.sum(axis=0, keepdims=True)
         nodes = cn[:, cell0] - 1
-        q = p[a:b]
         for ax, name in enumerate(("X", "Y", "Z")):
             q[name] = (xyz[ax, nodes] * lam).sum(axis=0)
         q["VX"] = rng.standard_normal(k) * sig + u_drift
@@ -489,19 +487,41 @@ def c5_channel_strip(ncx: int, ncy: int, ncz: int, n: int, rank: int = 0, world:
         q["ID"] = (np.arange(a, b, dtype=np.int64) << 8) + rank
         q["DUMP_TRAJ"] = 0
 
-    starts = list(range(0, n, chunk))
     try:
         cores = len(os.sched_getaffinity(0))
     except AttributeError:
         cores = os.cpu_count() or 1
     local_world = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
-    nthreads = max(1, min(8, cores // local_world, len(starts)))
-    if nthreads > 1:
-        from concurrent.futures import ThreadPoolExecutor
-        with ThreadPoolExecutor(nthreads) as ex:
-            list(ex.map(fill, starts))
-    else:
-        for a in starts:
-            fill(a)
+
+    def fill_range(p, a0, b0):
+        """fills p[0 : b0 - a0] with the particles [a0, b0) (a0 a multiple of the chunk size), a few host threads"""
+        starts = list(range(a0, b0, chunk))
+        nthreads = max(1, min(8, cores // local_world, len(starts)))
+        job = lambda a: fill_into(p[a - a0:min(b0, a + chunk) - a0], a, min(b0, a + chunk))
+        if nthreads > 1:
+            from concurrent.futures import ThreadPoolExecutor
+            with ThreadPoolExecutor(nthreads) as ex:
+                list(ex.map(job, starts))
+        else:
+            for a in starts:
+                job(a)
+
+    if lazy:
+        # 10^9 particles do not fit a host array: the caller streams them, `batch` records at a time
+        p = np.zeros(0, dtype=capi.PARTICLE_DTYPE)
+        w = Workload("C5 3-D tet channel strip", cfg, sp, p, mesh=mesh, bcs=bcs,
+                     notes=f"h={h:.4g} nu={nu:.5g} dt={dt:.4g} nc={mesh.nc} world={world}")
+
+        def batches(batch=24_000_000):
+            batch = (batch // chunk) * chunk
+            buf = pinned_particles(batch)
+            for a0 in range(0, n, batch):
+                b0 = min(n, a0 + batch)
+                fill_range(buf, a0, b0)
+                yield buf[: b0 - a0]
+        w.batches = batches
+        return w
+    p = pinned_particles(n) if pinned else np.zeros(n, dtype=capi.PARTICLE_DTYPE)
+    fill_range(p, 0, n)
     return Workload("C5 3-D tet channel strip", cfg, sp, p, mesh=mesh, bcs=bcs,
                     notes=f"h={h:.4g} nu={nu:.5g} dt={dt:.4g} nc={mesh.nc} world={world}")
