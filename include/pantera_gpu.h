@@ -169,6 +169,11 @@ int pgpu_set_mesh(pgpu_ctx* ctx, int dims, int nn, int nc,
 
 /* CELL_PROCS re-cut (load balance, src/timecycle.f90:185-189) */
 int pgpu_set_cell_procs(pgpu_ctx* ctx, int nc, const int32_t* cell_procs);
+/* BOOL_RADIAL_WEIGHTING: CELL_FNUM(NX*NY) of a rectilinear axisymmetric grid (src/initialization.f90:2304-2310).  With
+ * it ADVECT deletes / clones a particle that changed cell with the ratio of the cells' weights
+ * (src/timecycle.f90:2110-2128), VSS_COLLIS, DEPOSIT_CHARGE and CHECKS use the cell's weight instead of FNUM
+ * (src/collisions.f90:192-196, src/fields.f90:5507-5508, src/postprocess.f90:1764-1768).  NULL switches it off. */
+int pgpu_set_cell_fnum(pgpu_ctx* ctx, int nc, const double* cell_fnum);
 
 /* GRID_BC(:) -- src/global.f90:218-253 */
 int pgpu_set_bcs(pgpu_ctx* ctx, int nbc, const int32_t* particle_bc, const int32_t* field_bc,

@@ -112,6 +112,7 @@ struct po_ctx {
     double* vinj_par; int* vinj_mix;
     double* emit_par; int* emit_int;   /* [n][7]: UX, UY, UZ, U_NORM, TTRA, TROT, TVIB; [n][6]: MIX_ID, IC, IV1, IV2, IFACE, nfs offset */
     double* emit_nfs;
+    double* cell_fnum; /* CELL_FNUM (BOOL_RADIAL_WEIGHTING) or NULL */
     /* field boundary parameters (GRID_BC%WALL_POTENTIAL, ...) */
     double *fb_pot, *fb_rfpot, *fb_freq, *fb_efield, *fb_eps;
     /* GRID_AVG running averages */
@@ -1109,12 +1110,31 @@ int po_advect(po_ctx* w, int32_t tID) {
         q->DTRIM = w->c.dt;
     }
 
-    /* ref: :2099-2132 reverse sweep: swap-remove + structured re-index (radial weighting: not on the path) */
+    /* ref: :2099-2132 reverse sweep: swap-remove + structured re-index + radial weighting (:2110-2128; Philox mode:
+     * stream kind 8 keyed by the particle's index) */
     for (int64_t ip = np - 1; ip >= 0; ip--) {
         if (remove_part[ip]) {
             remove_particle(w, ip);
         } else if (!uns) {
-            w->p[ip].IC = cell_from_position(w, w->p[ip].X, w->p[ip].Y);
+            int ic = cell_from_position(w, w->p[ip].X, w->p[ip].Y);
+            int old_ic = w->p[ip].IC;
+            w->p[ip].IC = ic;
+            if (w->cell_fnum && ic != old_ic) {
+                double weight_ratio = w->cell_fnum[old_ic - 1] / w->cell_fnum[ic - 1];
+                if (weight_ratio < 1.) {
+                    po_rng_stream(w, 8, tID, (uint64_t)ip, 0);
+                    double rfp = po_rf(w);
+                    if (weight_ratio < rfp) remove_particle(w, ip);
+                } else if (weight_ratio > 1.) {
+                    po_rng_stream(w, 8, tID, (uint64_t)ip, 0);
+                    double rfp = po_rf(w);
+                    while ((weight_ratio - 1.) > rfp) {
+                        part_t q = w->p[ip];
+                        add_particle(w, q.X, q.Y, q.Z, q.VX, q.VY, q.VZ, q.EROT, q.EVIB, q.S_ID, ic, w->c.dt);
+                        weight_ratio = weight_ratio - 1.;
+                    }
+                }
+            }
         }
     }
     free(remove_part);
@@ -1375,7 +1395,7 @@ static int accepted_pair(po_ctx* w, int64_t jp1, int64_t jp2, int s1, int s2, do
 
 /* ref: src/collisions.f90:155-558 VSS_COLLIS for cell jc (1-based); ind = INDALL slice (0-based particle ids) */
 static int64_t vss_collis(po_ctx* w, int jc, int tID, int npcj, const int32_t* ind) {
-    double cfnum = w->c.fnum; /* BOOL_RADIAL_WEIGHTING not on the path */
+    double cfnum = w->cell_fnum ? w->cell_fnum[jc - 1] : w->c.fnum; /* ref: :192-196 CFNUM = CELL_FNUM(JC) */
     double vxmax = -1.e+38, vxmin = 1.e+38, vymax = -1.e+38, vymin = 1.e+38, vzmax = -1.e+38, vzmin = 1.e+38;
     for (int j = 0; j < npcj; j++) {
         const part_t* q = &w->p[ind[j]];
@@ -1674,7 +1694,8 @@ static int deposit_impl(po_ctx* w, double* rhs, double* abs_sum, int64_t nnodes,
             compute_weights(w, q, wt, idx, indi, indj);
             double vol = (w->c.xmax - w->c.xmin) * (w->c.ymax - w->c.ymin) * (w->c.zmax - w->c.zmin) /
                          (w->c.nx * w->c.ny); /* CELL_VOL, initialization.f90:2299 */
-            double rho_q = -K * charge * w->c.fnum / vol;
+            double cfnum = w->cell_fnum ? w->cell_fnum[q->IC - 1] : w->c.fnum; /* ref: src/fields.f90:5507-5508 */
+            double rho_q = -K * charge * cfnum / vol;
             int nw = (w->c.dims == 2) ? 4 : 2;
             for (int k = 0; k < nw; k++) ADD(idx[k], rho_q * wt[k]);
         }
@@ -1873,7 +1894,7 @@ static int cell_source(po_ctx* w, int kind, int tID, int ntask, const double* pa
                 for (int ip = 0; ip < np_init; ip++) {
                     po_rng_stream(w, kind, tID, (uint64_t)(1 + ip), (uint64_t)(it * 256 + icomp));
                     double xp = w->c.xmin + (w->c.xmax - w->c.xmin) * po_rf(w), yp, zp;
-                    if (w->c.axi) {
+                    if (w->c.axi && !w->cell_fnum) { /* IF (AXI .AND. (.NOT. BOOL_RADIAL_WEIGHTING)) */
                         yp = sqrt(w->c.ymin * w->c.ymin + po_rf(w) * (w->c.ymax * w->c.ymax - w->c.ymin * w->c.ymin));
                         zp = 0;
                     } else {
@@ -2264,7 +2285,7 @@ int po_checks(po_ctx* w, int64_t* tot_num, double* tot_momentum, double* tot_ke_
     for (int64_t jp = 0; jp < w->np; jp++) {
         const part_t* q = &w->p[jp];
         int js = q->S_ID - 1;
-        double cfnum = w->c.fnum, m = w->mass[js];
+        double cfnum = w->cell_fnum ? w->cell_fnum[q->IC - 1] : w->c.fnum, m = w->mass[js]; /* ref: :1764-1768 */
         if (tot_num) tot_num[js]++;
         if (tot_momentum) {
             tot_momentum[0 + 3 * js] += m * q->VX * cfnum;
@@ -2337,7 +2358,7 @@ int po_destroy(po_ctx* w) {
     free(w->xcoord); free(w->ycoord);
     free(w->e_field); free(w->b_field); free(w->surface_charge); free(w->spwt); free(w->mix_off); free(w->mix_sp); free(w->mix_frac); free(w->seed_par); free(w->seed_mix);
     free(w->vinj_par); free(w->vinj_mix); free(w->emit_par); free(w->emit_int); free(w->emit_nfs);
-    free(w->fb_pot); free(w->fb_rfpot); free(w->fb_freq); free(w->fb_efield); free(w->fb_eps);
+    free(w->cell_fnum); free(w->fb_pot); free(w->fb_rfpot); free(w->fb_freq); free(w->fb_efield); free(w->fb_eps);
     free(w->script); free(w->gavg); free(w->gcum1); free(w->gcum2);
     free(w->p); free(w->bcount); free(w->wcount); free(w->tallies); free(w->npcall);
     free(w);
@@ -2362,6 +2383,11 @@ int po_set_rng_script(po_ctx* w, const double* draws, int64_t n) {
 }
 int64_t po_rng_script_used(const po_ctx* w) { return w->script_pos; }
 int po_collision_type(const po_ctx* w) { return w->c.collision_type; }
+int po_set_cell_fnum(po_ctx* w, int nc, const double* cell_fnum) {
+    if (!cell_fnum || nc <= 0) { free(w->cell_fnum); w->cell_fnum = NULL; return PGPU_OK; }
+    REPL(w->cell_fnum, cell_fnum, nc);
+    return PGPU_OK;
+}
 int po_set_deterministic(po_ctx* w, int32_t on) { (void)w; (void)on; return PGPU_OK; } /* the oracle is sequential */
 
 int po_set_config(po_ctx* w, const pgpu_config* cfg) {

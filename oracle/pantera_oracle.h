@@ -46,6 +46,7 @@ int po_set_rng_script(po_ctx* ctx, const double* draws, int64_t n);
 int64_t po_rng_script_used(const po_ctx* ctx);
 int po_collision_type(const po_ctx* ctx);
 int po_set_deterministic(po_ctx* ctx, int32_t on);
+int po_set_cell_fnum(po_ctx* ctx, int nc, const double* cell_fnum);
 /* raw generator access for the known-answer tests */
 double po_rf(po_ctx* ctx);
 int po_pick(po_ctx* ctx, int n); /* pair-selection index INT(N*rf()), one stream word in Philox mode for N <= 65536 */

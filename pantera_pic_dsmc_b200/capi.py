@@ -279,6 +279,13 @@ class Lib:
         a = _i32(cell_procs)
         self._call("set_cell_procs", C.c_int(len(a)), _p(a))
 
+    def set_cell_fnum(self, cell_fnum):
+        if cell_fnum is None:
+            self._call("set_cell_fnum", C.c_int(0), None)
+        else:
+            a = _f64(cell_fnum)
+            self._call("set_cell_fnum", C.c_int(len(a)), _p(a))
+
     def set_bcs(self, particle_bc, field_bc=None, volume_bc=None, wall_temp=None, acc_n=None, acc_t=None,
                 react=None, dump_fluxes=None):
         n = len(particle_bc)

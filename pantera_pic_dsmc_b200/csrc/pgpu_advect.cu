@@ -23,7 +23,9 @@
  * No FMA contraction (-fmad=false) and the reference's evaluation order are kept so that positions and
  * cell indices match the CPU oracle bit for bit away from walls.
  */
+#include <math_constants.h>
 #include "pgpu_internal.cuh"
+#include "pgpu_physics.cuh"
 
 namespace {
 
@@ -151,23 +153,31 @@ __device__ __forceinline__ void apply_b_field(const PgDev& d, const PState& q, d
     }
 }
 
+/* x / m with the zero numerators answered directly: an FP64 division whose numerator is zero leaves the inlined
+ * Newton fast path for a ~100-instruction subroutine, and in an unmagnetised or 1-D run six of the nine divisions
+ * of the Boris push are 0 / m (measured: 60 % of the C4 ADVECT instructions).  For a finite positive m, (+-0) / m is
+ * (+-0) itself, so the answer is the same bit pattern. */
+__device__ __forceinline__ double div_z(double x, double m) {
+    return (x == 0. && m > 0. && m < CUDART_INF) ? x : x / m;
+}
+
 /* ref: src/timecycle.f90:2271-2291 UPDATE_VELOCITY_BORIS */
 __device__ __forceinline__ void boris(double dtime, PState& q, double charge, double mass, const double* e,
                                       const double* b) {
     double qc = charge * PG_QE;
     double vo[3] = {q.vx, q.vy, q.vz};
     double vm[3], t[3], vp[3], s[3], vpl[3], c[3];
-    for (int k = 0; k < 3; k++) vm[k] = vo[k] + 0.5 * qc * e[k] / mass * dtime;
-    for (int k = 0; k < 3; k++) t[k] = 0.5 * qc * b[k] / mass * dtime;
+    for (int k = 0; k < 3; k++) vm[k] = vo[k] + div_z(0.5 * qc * e[k], mass) * dtime;
+    for (int k = 0; k < 3; k++) t[k] = div_z(0.5 * qc * b[k], mass) * dtime;
     cross3(vm, t, c);
     for (int k = 0; k < 3; k++) vp[k] = vm[k] + c[k];
     double t2 = 1. + (t[0] * t[0] + t[1] * t[1] + t[2] * t[2]);
-    for (int k = 0; k < 3; k++) s[k] = 2. * t[k] / t2;
+    for (int k = 0; k < 3; k++) s[k] = div_z(2. * t[k], t2);
     cross3(vp, s, c);
     for (int k = 0; k < 3; k++) vpl[k] = vm[k] + c[k];
-    q.vx = vpl[0] + 0.5 * qc * e[0] / mass * dtime;
-    q.vy = vpl[1] + 0.5 * qc * e[1] / mass * dtime;
-    q.vz = vpl[2] + 0.5 * qc * e[2] / mass * dtime;
+    q.vx = vpl[0] + div_z(0.5 * qc * e[0], mass) * dtime;
+    q.vy = vpl[1] + div_z(0.5 * qc * e[1], mass) * dtime;
+    q.vz = vpl[2] + div_z(0.5 * qc * e[2], mass) * dtime;
 }
 
 /* ref: src/fields.f90:4302-4341 WALL_REACT (no EXIT after a successful reaction) */
@@ -863,10 +873,10 @@ __device__ __forceinline__ bool load_particle(const PgDev& d, long long slot, PS
     return true;
 }
 
-/* end of ADVECT for one particle that was not removed: periodic wraps, structured re-index.
- * Returns false (and flags the error) when the particle ends outside the grid. */
+/* end of ADVECT for one particle that was not removed: periodic wraps, structured re-index, radial weighting.
+ * Returns false (and flags the error) when the particle ends outside the grid, or when the weighting deletes it. */
 template <int MODE>
-__device__ __forceinline__ bool finish_particle(const PgDev& d, PState& q) {
+__device__ __forceinline__ bool finish_particle(const PgDev& d, PState& q, long long slot) {
     /* ref: :2048-2068 */
     if (d.zper) {
         while (q.z > d.zmax) q.z = d.zmin + (q.z - d.zmax);
@@ -877,10 +887,30 @@ __device__ __forceinline__ bool finish_particle(const PgDev& d, PState& q) {
         while (q.y < d.ymin) q.y = d.ymax + (q.y - d.ymin);
     }
     /* ref: :2105-2108 structured grids are re-indexed from the final position */
+    const int old_ic = q.ic;
     if (MODE == 0) q.ic = cell_from_position(d, q.x, q.y);
     if (q.ic < 1 || q.ic > d.ncells) {
         pg_set_err(d, PG_DEVERR_CELL_RANGE);
         return false;
+    }
+    if (MODE == 0 && d.cell_fnum && q.ic != old_ic) {
+        /* ref: :2110-2128 BOOL_RADIAL_WEIGHTING: a particle that changed cell is deleted or cloned with the ratio of the
+         * cells' weights; one draw (stream kind 8, keyed by the slot) */
+        double weight_ratio = d.cell_fnum[old_ic - 1] / d.cell_fnum[q.ic - 1];
+        if (weight_ratio < 1.) {
+            PgRng g;
+            g.init(d.seed_local, 8, d.tID, (unsigned long long)slot, 0ULL);
+            if (weight_ratio < g.rf()) return false;
+        } else if (weight_ratio > 1.) {
+            PgRng g;
+            g.init(d.seed_local, 8, d.tID, (unsigned long long)slot, 0ULL);
+            const double rfp = g.rf();
+            const PgIe E = pg_ie_load(d.p.ie, slot);
+            while ((weight_ratio - 1.) > rfp) {
+                pg_append_particle(d, q.x, q.y, q.z, q.vx, q.vy, q.vz, E.erot, E.evib, q.sid, q.ic);
+                weight_ratio = weight_ratio - 1.;
+            }
+        }
     }
     return true;
 }
@@ -888,7 +918,8 @@ __device__ __forceinline__ bool finish_particle(const PgDev& d, PState& q) {
 /* registers -> slot, and the particle's cell is counted for the counting sort: one fire-and-forget reduction
  * (RED.ADD, nothing waits for it); the arrival rank inside the cell is taken by the scatter pass, where the atomic's
  * latency hides behind HBM traffic (pgpu_api.cu scatter_kernel).  Every lane of `peers` must call this. */
-__device__ __forceinline__ void store_particle(const PgDev& d, long long slot, const PState& q, int dirty, unsigned int peers) {
+__device__ __forceinline__ void store_particle(const PgDev& d, long long slot, const PState& q, int dirty, unsigned int peers,
+                                               unsigned int* __restrict__ sh_count = nullptr) {
     /* one 256-bit store (the compiler splits a struct assignment with int members into three stores) */
     pg_store_sector(d.p.pos + slot, q.x, q.y, q.z, q.ic, q.sid);
     if (dirty & (DIRTY_V | DIRTY_S)) {
@@ -925,12 +956,17 @@ __device__ __forceinline__ void store_particle(const PgDev& d, long long slot, c
     /* The store is cell-sorted, so the lanes that finish together often share their cell, and coarse grids (the
      * one-cell heat bath, a 512-segment line) send millions of increments to a handful of counters: when the whole
      * group agrees on the cell, one lane adds the group's size (two warp votes); otherwise every lane adds one. */
+    /* Coarse grids again (PG_COUNT_SMEM_CELLS or fewer cells): a 512-segment line takes ten million increments on
+     * 512 addresses in sixteen L2 lines, and the L2 atomic unit serialises them (measured: the C4 ADVECT spent 3.2 ms
+     * on 1e7 particles, 65 % of it waiting behind the reductions).  The block counts in shared memory and adds its
+     * handful of non-zero counters once, at its end. */
+    unsigned int* cnt = sh_count ? sh_count : d.cell_count;
     const int leader = __ffs(peers) - 1;
     const int ic0 = __shfl_sync(peers, q.ic, leader);
     if (__all_sync(peers, q.ic == ic0)) {
-        if (lane == leader) atomicAdd(&d.cell_count[ic0 - 1], (unsigned int)__popc(peers));
+        if (lane == leader) atomicAdd(&cnt[ic0 - 1], (unsigned int)__popc(peers));
     } else {
-        atomicAdd(&d.cell_count[q.ic - 1], 1u);
+        atomicAdd(&cnt[q.ic - 1], 1u);
     }
 }
 
@@ -944,12 +980,17 @@ __device__ __forceinline__ void tombstone_particle(const PgDev& d, long long slo
  */
 template <int MODE, bool AXI>
 __global__ void __launch_bounds__(128, PG_ADVECT_MINBLOCKS) advect_lean_kernel(const __grid_constant__ PgDev d, long long n,
-                                                                               int chunk) {
+                                                                               int chunk, int count_smem) {
+    extern __shared__ unsigned int sh_count_buf[]; /* [count_smem] the block's cell histogram (coarse grids), or empty */
+    unsigned int* const sh_count = count_smem ? sh_count_buf : nullptr;
+    if (count_smem) {
+        for (int i = threadIdx.x; i < count_smem; i += blockDim.x) sh_count_buf[i] = 0u;
+        __syncthreads();
+    }
     const unsigned int FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     long long next = warp * chunk;
-    if (next >= n) return;
     const long long end = (next + chunk < n) ? next + chunk : n;
 
     PState q;
@@ -960,7 +1001,7 @@ __global__ void __launch_bounds__(128, PG_ADVECT_MINBLOCKS) advect_lean_kernel(c
     PgRng g; /* never drawn from in the LEAN pass */
     g.init(0ULL, 0, 0, 0ULL, 0ULL);
 
-    for (;;) {
+    for (bool active = next < n; active;) { /* (a warp past the end of the store only joins the block's final flush) */
         /* refill: idle lanes take the next slots of the chunk, in order */
         unsigned int idle = __ballot_sync(FULL, !have);
         if (idle && next < end) {
@@ -1004,7 +1045,7 @@ __global__ void __launch_bounds__(128, PG_ADVECT_MINBLOCKS) advect_lean_kernel(c
         bool keep = false;
         if (st == IT_DONE) {
             have = false;
-            keep = !remove && finish_particle<MODE>(d, q);
+            keep = !remove && finish_particle<MODE>(d, q, slot);
             if (!keep) tombstone_particle(d, slot);
         }
         unsigned int fm = __ballot_sync(FULL, keep);
@@ -1013,7 +1054,14 @@ __global__ void __launch_bounds__(128, PG_ADVECT_MINBLOCKS) advect_lean_kernel(c
                 for (int b = 0; b < 4; b++)
                     if (bhits[b]) atomicAdd(&d.bcount[b + 4 * (q.sid - 1)], (unsigned long long)bhits[b]);
             }
-            store_particle(d, slot, q, dirty, fm);
+            store_particle(d, slot, q, dirty, fm, sh_count);
+        }
+    }
+    if (count_smem) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < count_smem; i += blockDim.x) {
+            const unsigned int v = sh_count_buf[i];
+            if (v) atomicAdd(&d.cell_count[i], v);
         }
     }
 }
@@ -1039,7 +1087,7 @@ __global__ void __launch_bounds__(128) advect_full_kernel(const __grid_constant_
                 if constexpr (MODE == 0) structured_iter<AXI, false>(d, g, q, remove, dirty, bhits, hops);
                 else unstructured_iter<MODE, AXI, false>(d, g, q, remove, dirty, hops);
             }
-            keep = !remove && finish_particle<MODE>(d, q);
+            keep = !remove && finish_particle<MODE>(d, q, slot);
             if (!keep) tombstone_particle(d, slot);
         }
         unsigned int fm = __ballot_sync(0xffffffffu, keep);
@@ -1061,9 +1109,10 @@ int launch_advect(pgpu_ctx* c, long long n) {
     unsigned int blocks = (unsigned int)((n + per_block - 1) / per_block);
     if (!LEAN && blocks > 148u * 16u) blocks = 148u * 16u; /* the FULL pass strides over the device-side list length */
     bool axi = d.axi != 0;
+    const int csm = (LEAN && d.ncells <= PG_COUNT_SMEM_CELLS) ? d.ncells : 0; /* block-level histogram: store_particle */
 #define PG_LAUNCH(MODE, AXI)                                                                   \
     do {                                                                                       \
-        if (LEAN) advect_lean_kernel<MODE, AXI><<<blocks, 128, 0, c->stream>>>(d, n, chunk);   \
+        if (LEAN) advect_lean_kernel<MODE, AXI><<<blocks, 128, csm * sizeof(unsigned int), c->stream>>>(d, n, chunk, csm); \
         else advect_full_kernel<MODE, AXI><<<blocks, 128, 0, c->stream>>>(d, n, chunk);        \
     } while (0)
     if (d.grid_type != PGPU_UNSTRUCTURED) {

@@ -24,7 +24,7 @@ enum {
     S_WR_R, S_WR_P1, S_WR_NPROD, S_WR_PROB,
     S_MCC_SP, S_MCC_FRAC, S_MCC_CELL_NRHO,
     S_FACE_GEO, S_FACE_FILT, S_FACE_EXACT, S_FACE_CODE, S_TANG1, S_TANG2, S_EDGE_LEN, S_FACE_BIDX, S_BOUND_AREA, S_CELL_NODES, S_BASIS,
-    S_CELL_VOL, S_CELL_PROCS,
+    S_CELL_VOL, S_CELL_PROCS, S_CELL_FNUM,
     S_BC_PARTICLE, S_BC_FIELD, S_BC_REACT, S_BC_TEMP, S_BC_ACCN, S_BC_ACCT,
     S_W_X1, S_W_Y1, S_W_X2, S_W_Y2, S_W_NX, S_W_NY, S_W_TEMP, S_W_TRANSM, S_W_SPEC, S_W_DIFF, S_W_POROUS, S_W_REACT,
     S_XCOORD, S_YCOORD, S_EFIELD, S_BFIELD,
@@ -428,6 +428,17 @@ extern "C" int pgpu_set_cell_procs(pgpu_ctx* c, int nc, const int32_t* cell_proc
     c->x_counts_valid = false;
     c->mesh_dirty = c->mesh_set; /* the hop codes carry the ownership flags */
     return put(c, S_CELL_PROCS, (const int*)cell_procs, (size_t)nc, &c->dev.cell_procs);
+}
+
+/* CELL_FNUM(NX*NY) of BOOL_RADIAL_WEIGHTING (src/initialization.f90:2304-2310); NULL switches the weighting off */
+extern "C" int pgpu_set_cell_fnum(pgpu_ctx* c, int nc, const double* cell_fnum) {
+    if (!c) return PGPU_ERR_INVALID;
+    cudaSetDevice(c->device);
+    if (!cell_fnum || nc <= 0) return put(c, S_CELL_FNUM, (const double*)nullptr, 0, &c->dev.cell_fnum);
+    if (!c->cfg_set) PG_FAIL(c, PGPU_ERR_STATE, "set_cell_fnum: set_config first");
+    if (c->cfg.grid_type == PGPU_UNSTRUCTURED) PG_FAIL(c, PGPU_ERR_UNSUPPORTED, "set_cell_fnum: radial weighting exists on rectilinear grids only (src/timecycle.f90:2105-2128)");
+    if (nc != pg_ncells(c)) PG_FAIL(c, PGPU_ERR_INVALID, "set_cell_fnum: nc (%d) != number of cells (%d)", nc, pg_ncells(c));
+    return put(c, S_CELL_FNUM, cell_fnum, (size_t)nc, &c->dev.cell_fnum);
 }
 
 extern "C" int pgpu_set_bcs(pgpu_ctx* c, int nbc, const int32_t* particle_bc, const int32_t* field_bc,

@@ -56,7 +56,8 @@ __device__ __forceinline__ int cell_majorant(const PgDev& d, int cell0, int n, d
     else vol = (d.xmax - d.xmin) * (d.ymax - d.ymin) * (d.zmax - d.zmin) / (d.nx * d.ny);
     /* ref: :232  0.5*NPC*(NPC-1) is evaluated in single precision */
     float pairs_f = (0.5f * (float)n) * (float)(n - 1);
-    double ncollmax = (double)pairs_f * d.sigmamax * vrmax * d.fnum * d.dt / vol;
+    const double cfnum = d.cell_fnum ? __ldg(&d.cell_fnum[cell0]) : d.fnum; /* ref: :192-196 CFNUM = CELL_FNUM(JC) */
+    double ncollmax = (double)pairs_f * d.sigmamax * vrmax * cfnum * d.dt / vol;
     double r = floor(ncollmax + 0.5);
     long long half = (long long)floorf(0.5f * (float)n);
     long long ncoll;

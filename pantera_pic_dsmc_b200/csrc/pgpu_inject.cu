@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(128) domain_source_kernel(const __grid_constan
     PgRng g;
     g.init(d.seed_local, kind, d.tID, (unsigned long long)(1 + ip), (unsigned long long)(it * 256 + icomp));
     double xp = d.xmin + (d.xmax - d.xmin) * g.rf(), yp, zp;
-    if (d.axi) {
+    if (d.axi && !d.cell_fnum) { /* IF (AXI .AND. (.NOT. BOOL_RADIAL_WEIGHTING)) */
         yp = sqrt(d.ymin * d.ymin + g.rf() * (d.ymax * d.ymax - d.ymin * d.ymin));
         zp = 0;
     } else {

@@ -62,6 +62,7 @@
 #ifndef PG_ADVECT_MINBLOCKS
 #define PG_ADVECT_MINBLOCKS 7 /* 72 registers; swept 6/7/8/10 at full size (r02b): 9.00/8.70/9.39/13.4 ms */
 #endif
+#define PG_COUNT_SMEM_CELLS 4096 /* grids this coarse count their cells per block in shared memory (pgpu_advect.cu) */
 #ifndef PG_ADVECT_PREFETCH
 #define PG_ADVECT_PREFETCH 0 /* next-cell filter prefetch: measured r02b, +3 % move time (more L1 traffic than latency saved) */
 #endif
@@ -231,6 +232,7 @@ struct PgDev {
     const int* cell_nodes;    /* [nc][nf] 1-based */
     const double* basis;      /* [nc][nf][nf] BASIS_COEFFS(j,i,ic) */
     const double* cell_vol;   /* [nc] */
+    const double* cell_fnum;  /* [ncells] CELL_FNUM (BOOL_RADIAL_WEIGHTING, rectilinear axisymmetric grids) or null */
     const int* cell_procs;    /* [ncells] or null */
     /* --- boundary conditions GRID_BC(:) --- */
     int nbc;

@@ -87,7 +87,8 @@ __global__ void __launch_bounds__(256) deposit_kernel(const __grid_constant__ Pg
             double fx = (x - cxmin) / hx;
             double fy = (y - cymin) / hy;
             double vol = (d.xmax - d.xmin) * (d.ymax - d.ymin) * (d.zmax - d.zmin) / (d.nx * d.ny);
-            double rho_q = -K * charge * d.fnum / vol;
+            const double cfnum = d.cell_fnum ? __ldg(&d.cell_fnum[ic - 1]) : d.fnum; /* ref: src/fields.f90:5508 */
+            double rho_q = -K * charge * cfnum / vol;
             if (d.dims == 2) {
                 int i0 = ic + j - 1;
                 atomicAdd(&acc[i0], rho_q * ((1. - fx) * (1. - fy)));

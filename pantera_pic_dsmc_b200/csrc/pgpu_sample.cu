@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(256) checks_kernel(const __grid_constant__ PgD
         if (P.ic < 1) continue;
         const PgVel V = d.p.vel[i];
         const int js = P.sid - 1;
-        const double m = d.mass[js], cf = d.fnum;
+        const double m = d.mass[js], cf = d.cell_fnum ? d.cell_fnum[P.ic - 1] : d.fnum; /* ref: :1764-1768 */
         atomicAdd(&sh[js], 1.0);
         atomicAdd(&sh[ns + 3 * js + 0], m * V.vx * cf);
         atomicAdd(&sh[ns + 3 * js + 1], m * V.vy * cf);

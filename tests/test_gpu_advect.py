@@ -279,3 +279,55 @@ def test_empty_store_and_error_paths(gpu):
     bad.particles["IC"][3] = 99
     with pytest.raises(capi.PanteraError):
         wl.apply(gpu, bad)
+
+
+def radial_case(n=40_000, nx=6, ny=8):
+    """Rectilinear axisymmetric box with BOOL_RADIAL_WEIGHTING: CELL_FNUM grows with the radius of the cell row
+    (src/initialization.f90:2304-2310)."""
+    w = wl.c1_argon_box(n, nx=nx, ny=ny, periodic=False)
+    w.cfg.axi = 1
+    w.cfg.ymin, w.cfg.ymax = 0.0, 1.0
+    w.cfg.zmin, w.cfg.zmax = 0.0, 1.0
+    w.cfg.bool_z_periodic = 0
+    w.cfg.collision_type = capi.DSMC
+    w.cfg.dt = 1.5e-4
+    w.cfg.capacity = 4 * n
+    w.particles["Z"] = 0.0
+    w.particles["DTRIM"] = w.cfg.dt
+    j = np.arange(ny)
+    ymin, ymax = w.cfg.ymin + j * (w.cfg.ymax - w.cfg.ymin) / ny, w.cfg.ymin + (j + 1) * (w.cfg.ymax - w.cfg.ymin) / ny
+    row = w.cfg.fnum * ny * (ymax ** 2 - ymin ** 2) / (w.cfg.ymax ** 2 - w.cfg.ymin ** 2)
+    cell_fnum = np.repeat(row, nx)          # index I + NX*(J-1)
+    return w, cell_fnum
+
+
+def test_radial_weighting_clone_and_delete(gpu, oracle_philox):
+    """src/timecycle.f90:2110-2128: a particle that moved to a cell row of different weight is deleted with probability
+    1 - ratio or cloned floor/rand(ratio - 1) times; one draw per particle (stream kind 8, keyed by the slot).  Same
+    survivors and clones on both sides, as a set."""
+    w, cell_fnum = radial_case()
+    for lib in (oracle_philox, gpu):
+        wl.apply(lib, w)
+        lib.set_cell_fnum(cell_fnum)
+        lib.advect(1)
+    a, b = oracle_philox.download_particles(), gpu.download_particles()
+    assert len(a) == len(b) and len(a) != len(w.particles)
+    key = lambda p: p[np.lexsort((p["VZ"], p["VY"], p["VX"], p["Y"], p["X"], p["IC"]))]
+    a, b = key(a), key(b)
+    for f in ("IC", "S_ID"):
+        assert np.array_equal(a[f], b[f]), f
+    for f in ("X", "Y", "VX", "VY", "VZ"):
+        assert np.allclose(a[f], b[f], rtol=1e-12, atol=1e-12), f
+    # clones exist (several particles with identical state) and so do deletions
+    _, counts = np.unique(np.stack([b["X"], b["Y"], b["VX"]]), axis=1, return_counts=True)
+    assert (counts > 1).sum() > 50
+    # CFNUM = CELL_FNUM(JC) in the collision majorant: same pairs on both sides
+    gpu.sort()
+    ps = gpu.download_particles()
+    oracle_philox.upload_particles(ps)      # the device's sorted order is the order the pairs index into
+    co, cg = oracle_philox.collide(2), gpu.collide(2)
+    assert co == cg and cg[0] > 0
+    util.assert_particles_match(oracle_philox.download_particles(), gpu.download_particles(), rtol=1e-12, atol=1e-9, what="radial DSMC")
+    no, mo, ko, io = oracle_philox.checks()
+    ng, mg_, kg, ig = gpu.checks()
+    assert np.array_equal(no, ng) and np.allclose(ko, kg, rtol=1e-12)

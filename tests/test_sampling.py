@@ -167,7 +167,11 @@ def test_density_and_temperature_fields_within_3_sigma_of_the_reference_stream(o
             k = np.mean(((a1 - a2)[ok] ** 2) / 2.0 / scale[ok])
             sigma = np.sqrt(k * scale)
             z = (a1 - r)[ok] / (np.sqrt(2.0) * sigma[ok])
-            assert np.mean(np.abs(z) < 3.0) >= 0.98, (key, js, float(np.mean(np.abs(z) < 3.0)), float(np.abs(z).max()))
+            # ~48 cells per field: a 98 % rule on |z| < 3 would be failed by ONE 3.1-sigma cell (12 % of runs, and the
+            # atomics make the device's particle order, hence its draws, differ run to run); allow one cell past 3.5
+            # sigma (P(two or more) ~ 3e-4 per field) and nothing past 5
+            out = int(np.sum(np.abs(z) >= 3.5))
+            assert out <= max(1, int(0.02 * z.size)) and np.abs(z).max() < 5.0, (key, js, out, float(np.abs(z).max()))
             assert 0.4 < np.mean(z * z) < 1.9, (key, js, float(np.mean(z * z)))
     # the case is not trivial: the hot wall heats the gas next to it and thins it out
     yc = np.asarray(field_case(1).mesh.node_coords)[1, np.asarray(field_case(1).mesh.cell_nodes) - 1].mean(axis=0)
