@@ -1,6 +1,6 @@
 #!/bin/bash
 tag=$1
-timeout 900 python -m pytest tests/test_sampling.py tests/test_gpu_advect.py tests/test_field_step.py -m gpu -q 2>&1 | grep -E "^E    |passed|failed" | cut -c1-300 | head -12
+timeout 900 python -m pytest tests -m gpu -q 2>&1 | grep -E "^E    |passed|failed" | cut -c1-300 | head -12
 timeout 600 python bench.py --workload c4 --steps 10 --warmup 3 --no-e2e --no-cpu > gpurun_out/bench_c4_$tag.json 2> gpurun_out/bench_c4_$tag.err
 python -c "
 import json;d=json.load(open('gpurun_out/bench_c4_$tag.json'));print('c4', d['value'], d['ms_per_step'], d['roofline']['groups_ms_per_step'])"
