@@ -93,6 +93,7 @@ struct PgStatus {
                                        on the device (immigrants appended by EXCHANGE, the compaction of the sort), so
                                        that a whole timestep needs ONE host synchronisation, at its end            */
     unsigned long long n_immigrants; /* particles received by the last EXCHANGE                                     */
+    unsigned long long n_cand;      /* MCC: particles that passed the null-collision test (their slots are in hitlist) */
     unsigned long long x_overflow;  /* emigrants that did not fit the fixed-capacity message of their destination  */
     int err;                        /* first device-side error code (0 = none)           */
     int flag_dtrim;                 /* some uploaded/received particle has DTRIM != DT   */

@@ -149,22 +149,35 @@ __global__ void add_surface_charge_kernel(double* __restrict__ rhs, const double
     if (i < n) rhs[i] = rhs[i] + sc[i];
 }
 
-/* ref: src/collisions.f90:1646-1890, one thread per particle present at entry */
-__global__ void __launch_bounds__(128) mcc_vahedi_kernel(const __grid_constant__ PgDev d, double p_null) {
-    long long jp1 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool present = jp1 < (long long)d.status->np_cur; /* the particles present at entry */
-    PgPos P1;
-    P1.ic = 0;
-    if (present) P1 = d.p.pos[jp1];
-    int ic = P1.ic;
+/* ref: src/collisions.f90:1646-1890.  Two kernels: the null-collision test of every particle present at entry (one
+ * Philox draw, 32 registers) compacts the ~1 % that collide into a list; the collision proper (background partner,
+ * cross-section tables, reaction products: 118 registers) then runs on full warps.  As one kernel a warp with a single
+ * candidate ran the whole collision path for it (measured: 8 active lanes on average, 0.53 ms per 1e7 particles). */
+__global__ void __launch_bounds__(256) mcc_select_kernel(const __grid_constant__ PgDev d, double p_null) {
+    const long long jp1 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    int ic = 0;
+    if (jp1 < (long long)d.status->np_cur) ic = d.p.pos[jp1].ic; /* the particles present at entry */
     PgRng g;
     g.init(d.seed_local, 3, d.tID, (unsigned long long)jp1, 0ULL);
     const bool cand = ic >= 1 && !(g.rf() > p_null);
-    /* one counter for the whole store: the warp adds its candidates once (per-lane increments of a single address
-     * serialise in L2; measured 0.5 ms per 1e7 particles) */
     const unsigned int cm = __ballot_sync(0xffffffffu, cand);
-    if (cm && (threadIdx.x & 31) == __ffs(cm) - 1) atomicAdd(&d.status->ncoll, (unsigned long long)__popc(cm));
-    if (!cand) return;
+    if (!cm) return;
+    const int lane = threadIdx.x & 31, leader = __ffs(cm) - 1;
+    unsigned long long base = 0;
+    if (lane == leader) {
+        base = atomicAdd(&d.status->n_cand, (unsigned long long)__popc(cm));
+        atomicAdd(&d.status->ncoll, (unsigned long long)__popc(cm));
+    }
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (cand) d.hitlist[base + __popc(cm & ((1u << lane) - 1u))] = (unsigned int)jp1;
+}
+
+__device__ void mcc_vahedi_one(const PgDev& d, const long long jp1, double p_null) {
+    const PgPos P1 = d.p.pos[jp1];
+    const int ic = P1.ic;
+    PgRng g;
+    g.init(d.seed_local, 3, d.tID, (unsigned long long)jp1, 0ULL);
+    (void)g.rf(); /* the draw of the null-collision test */
     const double dt = d.dt;
     int s1 = P1.sid;
     const PgVel V1 = d.p.vel[jp1];
@@ -216,6 +229,12 @@ __global__ void __launch_bounds__(128) mcc_vahedi_kernel(const __grid_constant__
             }
         }
     }
+}
+
+__global__ void __launch_bounds__(128) mcc_vahedi_kernel(const __grid_constant__ PgDev d, double p_null) {
+    const long long n = (long long)d.status->n_cand, stride = (long long)gridDim.x * blockDim.x;
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride)
+        mcc_vahedi_one(d, (long long)d.hitlist[k], p_null);
 }
 
 __global__ void __launch_bounds__(256) remove_species_kernel(const __grid_constant__ PgDev d, int sp) {
@@ -292,8 +311,14 @@ int pg_mcc_impl(pgpu_ctx* c, int tID) {
     double null_coll_freq = c->cfg.mcc_bg_dens * (double)1e-12f;
     double p_null = 1 - exp(-dt * null_coll_freq);
     if (p_null > 1) p_null = 1.;
-    mcc_vahedi_kernel<<<(unsigned int)((c->np_ub + 127) / 128), 128, 0, c->stream>>>(c->dev, p_null);
-    c->launches++;
+    PG_CUDA(c, cudaMemsetAsync(&c->d_status->n_cand, 0, sizeof(unsigned long long), c->stream));
+    mcc_select_kernel<<<(unsigned int)((c->np_ub + 255) / 256), 256, 0, c->stream>>>(c->dev, p_null);
+    {
+        /* the list's length stays on the device: a grid that fills the machine strides over it */
+        const long long want = (c->np_ub + 127) / 128;
+        mcc_vahedi_kernel<<<(unsigned int)std::min<long long>(want, 148LL * 8), 128, 0, c->stream>>>(c->dev, p_null);
+    }
+    c->launches += 2;
     PG_CUDA(c, cudaGetLastError());
     c->sorted = false;
     c->hist_valid = false;
