@@ -23,7 +23,6 @@
  * No FMA contraction (-fmad=false) and the reference's evaluation order are kept so that positions and
  * cell indices match the CPU oracle bit for bit away from walls.
  */
-#include <math_constants.h>
 #include "pgpu_internal.cuh"
 #include "pgpu_physics.cuh"
 
@@ -153,31 +152,26 @@ __device__ __forceinline__ void apply_b_field(const PgDev& d, const PState& q, d
     }
 }
 
-/* x / m with the zero numerators answered directly: an FP64 division whose numerator is zero leaves the inlined
- * Newton fast path for a ~100-instruction subroutine, and in an unmagnetised or 1-D run six of the nine divisions
- * of the Boris push are 0 / m (measured: 60 % of the C4 ADVECT instructions).  For a finite positive m, (+-0) / m is
- * (+-0) itself, so the answer is the same bit pattern. */
-__device__ __forceinline__ double div_z(double x, double m) {
-    return (x == 0. && m > 0. && m < CUDART_INF) ? x : x / m;
-}
-
-/* ref: src/timecycle.f90:2271-2291 UPDATE_VELOCITY_BORIS */
+/* ref: src/timecycle.f90:2271-2291 UPDATE_VELOCITY_BORIS
+ * (Tried r02: answering the 0 / m divisions of an unmagnetised or 1-D push without the ~100-instruction FP64 division
+ *  subroutine removes 60 % of the C4 ADVECT instructions and not a microsecond of its time -- the kernel waits on memory
+ *  -- while the extra branches cost the tet walk registers it does not have: +0.25 ms at full size.  Not kept.) */
 __device__ __forceinline__ void boris(double dtime, PState& q, double charge, double mass, const double* e,
                                       const double* b) {
     double qc = charge * PG_QE;
     double vo[3] = {q.vx, q.vy, q.vz};
     double vm[3], t[3], vp[3], s[3], vpl[3], c[3];
-    for (int k = 0; k < 3; k++) vm[k] = vo[k] + div_z(0.5 * qc * e[k], mass) * dtime;
-    for (int k = 0; k < 3; k++) t[k] = div_z(0.5 * qc * b[k], mass) * dtime;
+    for (int k = 0; k < 3; k++) vm[k] = vo[k] + 0.5 * qc * e[k] / mass * dtime;
+    for (int k = 0; k < 3; k++) t[k] = 0.5 * qc * b[k] / mass * dtime;
     cross3(vm, t, c);
     for (int k = 0; k < 3; k++) vp[k] = vm[k] + c[k];
     double t2 = 1. + (t[0] * t[0] + t[1] * t[1] + t[2] * t[2]);
-    for (int k = 0; k < 3; k++) s[k] = div_z(2. * t[k], t2);
+    for (int k = 0; k < 3; k++) s[k] = 2. * t[k] / t2;
     cross3(vp, s, c);
     for (int k = 0; k < 3; k++) vpl[k] = vm[k] + c[k];
-    q.vx = vpl[0] + div_z(0.5 * qc * e[0], mass) * dtime;
-    q.vy = vpl[1] + div_z(0.5 * qc * e[1], mass) * dtime;
-    q.vz = vpl[2] + div_z(0.5 * qc * e[2], mass) * dtime;
+    q.vx = vpl[0] + 0.5 * qc * e[0] / mass * dtime;
+    q.vy = vpl[1] + 0.5 * qc * e[1] / mass * dtime;
+    q.vz = vpl[2] + 0.5 * qc * e[2] / mass * dtime;
 }
 
 /* ref: src/fields.f90:4302-4341 WALL_REACT (no EXIT after a successful reaction) */
@@ -978,12 +972,14 @@ __device__ __forceinline__ void tombstone_particle(const PgDev& d, long long slo
 /*
  * LEAN pass.  One warp works through `chunk` consecutive slots (64..1024, launch_advect); see the file header.
  */
-template <int MODE, bool AXI>
+template <int MODE, bool AXI, bool CSM>
 __global__ void __launch_bounds__(128, PG_ADVECT_MINBLOCKS) advect_lean_kernel(const __grid_constant__ PgDev d, long long n,
                                                                                int chunk, int count_smem) {
-    extern __shared__ unsigned int sh_count_buf[]; /* [count_smem] the block's cell histogram (coarse grids), or empty */
-    unsigned int* const sh_count = count_smem ? sh_count_buf : nullptr;
-    if (count_smem) {
+    /* CSM (coarse grids, launch_advect): the block's cell histogram lives in shared memory, [count_smem] counters.
+     * A template parameter, not a run-time branch: the barrier and the shared-memory path cost the fine-grid kernel
+     * 0.3 ms at full size when they were merely skipped at run time. */
+    extern __shared__ unsigned int sh_count_buf[];
+    if (CSM) {
         for (int i = threadIdx.x; i < count_smem; i += blockDim.x) sh_count_buf[i] = 0u;
         __syncthreads();
     }
@@ -991,6 +987,7 @@ __global__ void __launch_bounds__(128, PG_ADVECT_MINBLOCKS) advect_lean_kernel(c
     const int lane = threadIdx.x & 31;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     long long next = warp * chunk;
+    if (!CSM && next >= n) return;
     const long long end = (next + chunk < n) ? next + chunk : n;
 
     PState q;
@@ -1054,10 +1051,10 @@ __global__ void __launch_bounds__(128, PG_ADVECT_MINBLOCKS) advect_lean_kernel(c
                 for (int b = 0; b < 4; b++)
                     if (bhits[b]) atomicAdd(&d.bcount[b + 4 * (q.sid - 1)], (unsigned long long)bhits[b]);
             }
-            store_particle(d, slot, q, dirty, fm, sh_count);
+            store_particle(d, slot, q, dirty, fm, CSM ? sh_count_buf : nullptr);
         }
     }
-    if (count_smem) {
+    if (CSM) {
         __syncthreads();
         for (int i = threadIdx.x; i < count_smem; i += blockDim.x) {
             const unsigned int v = sh_count_buf[i];
@@ -1112,7 +1109,8 @@ int launch_advect(pgpu_ctx* c, long long n) {
     const int csm = (LEAN && d.ncells <= PG_COUNT_SMEM_CELLS) ? d.ncells : 0; /* block-level histogram: store_particle */
 #define PG_LAUNCH(MODE, AXI)                                                                   \
     do {                                                                                       \
-        if (LEAN) advect_lean_kernel<MODE, AXI><<<blocks, 128, csm * sizeof(unsigned int), c->stream>>>(d, n, chunk, csm); \
+        if (LEAN && csm) advect_lean_kernel<MODE, AXI, true><<<blocks, 128, csm * sizeof(unsigned int), c->stream>>>(d, n, chunk, csm); \
+        else if (LEAN) advect_lean_kernel<MODE, AXI, false><<<blocks, 128, 0, c->stream>>>(d, n, chunk, 0); \
         else advect_full_kernel<MODE, AXI><<<blocks, 128, 0, c->stream>>>(d, n, chunk);        \
     } while (0)
     if (d.grid_type != PGPU_UNSTRUCTURED) {
