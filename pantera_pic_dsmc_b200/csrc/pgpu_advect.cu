@@ -941,7 +941,10 @@ __device__ __forceinline__ void store_particle(const PgDev& d, long long slot, c
                 const unsigned long long k = ebase + __popc(em & ((1u << lane) - 1u));
                 if (k < (unsigned long long)d.emig_cap) d.emig_list[k] = (unsigned int)slot;
                 else atomicAdd(&d.xrow[PG_XROW_OVF], 1ULL);
-                atomicAdd(&d.xrow[dest], 1ULL);
+                /* one increment per (warp, destination): a rank has a neighbour or two, and a million per-lane
+                 * increments of the same address queue up in L2 */
+                const unsigned int same = __match_any_sync(em, dest);
+                if (lane == __ffs(same) - 1) atomicAdd(&d.xrow[dest], (unsigned long long)__popc(same));
             }
             peers &= ~em;
             if (emig) return;

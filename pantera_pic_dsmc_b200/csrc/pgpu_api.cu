@@ -183,6 +183,12 @@ extern "C" int pgpu_destroy(pgpu_ctx* c) {
     dev_free(c->d_gavg); dev_free(c->d_gavg_np); dev_free(c->d_gavg_sums); dev_free(c->d_gavg_cum);
     dev_free(c->d_sendbuf); dev_free(c->d_recvbuf); dev_free(c->d_xcount); dev_free(c->d_emig_list);
     for (int i = 0; i < 16; i++) cudaEventDestroy(c->ev[i]);
+    if (c->x_trace == 1) {
+        if (c->x_traced > 0)
+            fprintf(stderr, "[pantera_gpu rank %d] EXCHANGE per step over %lld steps: pack %.3f ms, transfer %.3f ms, unpack %.3f ms\n",
+                    c->cfg.rank, c->x_traced, c->x_ms[0] / c->x_traced, c->x_ms[1] / c->x_traced, c->x_ms[2] / c->x_traced);
+        for (int i = 0; i < 4; i++) cudaEventDestroy(c->xev[i]);
+    }
     cudaStreamDestroy(c->stream);
     delete c;
     return PGPU_OK;

@@ -399,6 +399,11 @@ struct pgpu_ctx {
 
     /* timings */
     cudaEvent_t ev[16];
+    /* PANTERA_GPU_XCHG_TRACE=1: pack / transfer / unpack split of the per-step EXCHANGE, printed when the context closes */
+    cudaEvent_t xev[4] = {nullptr, nullptr, nullptr, nullptr};
+    double x_ms[3] = {0., 0., 0.};
+    long long x_traced = 0;
+    int x_trace = -1;
     double ms[8];
     long long launches;
 
