@@ -592,11 +592,19 @@ static int build_packed_mesh(pgpu_ctx* c) {
     /* the codes ride in the cell records (no dependent load in the face walk); plain specular walls are marked so
      * that the LEAN pass can reflect in line instead of deferring the particle (PG_CODE_SPEC) */
     const bool owner_flags = c->cfg.nranks > 1 && !c->h_cell_procs.empty();
+    /* ranks whose cells share a face with a cell of this rank: the peers of the per-step EXCHANGE (pgpu_exchange.cu).
+     * Face adjacency is symmetric, so both ends of a pair come to the same answer. */
+    c->x_adjacent.assign((size_t)std::max(c->cfg.nranks, 1), 0);
+    c->x_adjacent_known = owner_flags;
     auto packed_codes = [&](int ic, int* rec) {
         rec[0] = rec[1] = rec[2] = rec[3] = 0;
         for (int j = 0; j < nf; j++) {
             int cd = code[(size_t)ic * nf + j];
-            if (cd > 0 && owner_flags && c->h_cell_procs[cd - 1] != c->cfg.rank) cd |= PG_CODE_FOREIGN;
+            if (cd > 0 && owner_flags && c->h_cell_procs[cd - 1] != c->cfg.rank) {
+                const int owner = c->h_cell_procs[cd - 1];
+                if (c->h_cell_procs[ic] == c->cfg.rank && owner >= 0 && owner < c->cfg.nranks) c->x_adjacent[owner] = 1;
+                cd |= PG_CODE_FOREIGN;
+            }
             if (cd < 0) {
                 int gi = -cd - 1;
                 if (c->h_bc_particle[gi] == PGPU_SPECULAR && !c->h_bc_react[gi] && c->h_bc_field[gi] != PGPU_DIELECTRIC_BC)
@@ -782,7 +790,8 @@ static const char* deverr_text(int e) {
         case PG_DEVERR_HOPS: return "a particle exceeded the hop limit (malformed mesh or NaN state)";
         case PG_DEVERR_CELL_RANGE: return "a particle ended outside the grid (cell index out of range)";
         case PG_DEVERR_CAPACITY: return "particle capacity exhausted while creating particles (raise pgpu_config.capacity)";
-        case PG_DEVERR_XCAP: return "EXCHANGE: more emigrants than the message sized from the previous step holds (PANTERA_GPU_XCHG_HEADROOM)";
+        case PG_DEVERR_XCAP: return "EXCHANGE: more emigrants than the message sized from the previous step holds (PANTERA_GPU_XCHG_HEADROOM), or an emigrant for a rank that shares no face with this one (PANTERA_GPU_XCHG_ALLPAIRS=1)";
+        case PG_DEVERR_XWAIT: return "EXCHANGE: a peer's message did not arrive in its window within 30 s (peer stopped?)";
         default: return "unknown device error";
     }
 }

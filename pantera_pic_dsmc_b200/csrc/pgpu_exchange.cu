@@ -200,63 +200,88 @@ __global__ void __launch_bounds__(256) xrec_to_aos_kernel(const double* __restri
  * send slots with the count in the header".)
  * ---------------------------------------------------------------------------------------- */
 struct XPlan {
-    unsigned int off[64]; /* first record (the header) of the message for / from rank r, in records */
-    unsigned int cap[64]; /* particle records the message holds                                       */
+    double* msg[64];           /* first record (the header) of the message for / from rank r.  Sending: the slot of
+                                  this rank in r's window (peer memory over NVLink) or a segment of the local send
+                                  buffer (NCCL pair); receiving: the slot of r in this rank's window, or a segment of
+                                  the receive buffer */
+    unsigned long long* flag[64]; /* sending: r's arrival flag for this rank (window pairs), else null;
+                                     receiving: this rank's arrival flag for r, else null */
+    unsigned int cap[64];      /* particle records the message holds */
+    unsigned char on[64];      /* a message is exchanged with rank r this step (never with oneself) */
+    unsigned long long seq;    /* number of this exchange (arrival flags carry it) */
     int nr, rank;
 };
 
-/* emigrant list -> messages; grid-stride over the list, whose length lives on the device */
+/* Emigrant list -> messages, written where they are read: for a window pair the message slot is PEER MEMORY, so the
+ * pack IS the send (no staging copy, no transfer kernel, and only the records that exist cross NVLink, not the slot's
+ * capacity).  A warp takes 32 entries of the list, reserves their message slots with one atomic per destination, lays
+ * the 88-byte records out in shared memory and writes each destination's run as ONE contiguous, lane-coalesced range
+ * (8-byte stores of scattered records would cross the link as quarter-filled packets). */
 __global__ void __launch_bounds__(256) xpack_fast_kernel(const __grid_constant__ PgDev d, const unsigned int* __restrict__ list,
-                                                         const unsigned long long* __restrict__ xrow, double* __restrict__ sendbuf,
+                                                         const unsigned long long* __restrict__ xrow,
                                                          const __grid_constant__ XPlan plan, unsigned long long* __restrict__ xcursor) {
+    __shared__ double stage[8][32 * XREC_DOUBLES];
     unsigned long long n = xrow[PG_XROW_LEN];
     if (n > (unsigned long long)d.emig_cap) n = (unsigned long long)d.emig_cap;
-    /* (warp-uniform trip count: the lanes of a warp reserve their message slots together, one atomic per destination --
-     *  a rank has one or two neighbours, so per-lane increments all queued on the same one or two addresses:
-     *  measured 0.30 ms of a 0.49 ms EXCHANGE at 1.25e6 emigrants) */
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
     const int lane = threadIdx.x & 31;
+    double* const st = stage[threadIdx.x >> 5];
     for (unsigned long long base = (unsigned long long)blockIdx.x * blockDim.x; base < n; base += stride) {
         const unsigned long long t = base + threadIdx.x;
         const bool on = t < n;
-        long long i = 0;
-        PgPos P;
-        int ic = 0, dest = -1;
+        double rec[XREC_DOUBLES];
+        int dest = -1;
         if (on) {
-            i = (long long)list[t];
-            P = d.p.pos[i];
-            ic = P.ic;
-            dest = __ldg(&d.cell_procs[ic - 1]);
+            const long long i = (long long)list[t];
+            const PgPos P = d.p.pos[i];
+            dest = __ldg(&d.cell_procs[P.ic - 1]);
+            const PgVel V = d.p.vel[i];
+            const PgIe E = pg_ie_load(d.p.ie, i);
+            rec[0] = P.x; rec[1] = P.y; rec[2] = P.z;
+            rec[3] = V.vx; rec[4] = V.vy; rec[5] = V.vz;
+            rec[6] = E.erot; rec[7] = E.evib;
+            rec[8] = d.p.dtrim ? d.p.dtrim[i] : d.dt;
+            int2 cs = make_int2(P.ic, P.sid);
+            rec[9] = *reinterpret_cast<double*>(&cs);
+            long long id = d.p.id ? d.p.id[i] : 0;
+            rec[10] = *reinterpret_cast<double*>(&id);
+            d.p.pos[i].ic = PG_TOMBSTONE;
         }
-        const unsigned int grp = __match_any_sync(0xffffffffu, dest);
-        if (!on) continue;
-        const int leader = __ffs(grp) - 1;
-        unsigned long long k = 0;
-        if (lane == leader) k = atomicAdd(&xcursor[dest], (unsigned long long)__popc(grp));
-        k = __shfl_sync(grp, k, leader) + __popc(grp & ((1u << lane) - 1u));
-        d.p.pos[i].ic = PG_TOMBSTONE;
-        if (k >= (unsigned long long)plan.cap[dest]) { /* does not fit: the step fails loudly at its read-back */
-            atomicAdd(&d.status->x_overflow, 1ULL);
-            pg_set_err(d, PG_DEVERR_XCAP);
-            continue;
+        unsigned int rem = __ballot_sync(0xffffffffu, on);
+        while (rem) { /* one round per destination among the warp's entries (a neighbour or two) */
+            const int lead = __ffs(rem) - 1;
+            const int dg = __shfl_sync(0xffffffffu, dest, lead);
+            const unsigned int grp = __ballot_sync(0xffffffffu, on && dest == dg);
+            const int cnt = __popc(grp);
+            unsigned long long k0 = 0;
+            if (lane == lead) k0 = atomicAdd(&xcursor[dg], (unsigned long long)cnt);
+            k0 = __shfl_sync(0xffffffffu, k0, lead);
+            const unsigned long long cap = plan.on[dg] ? (unsigned long long)plan.cap[dg] : 0ULL;
+            const int fit = (k0 >= cap) ? 0 : (int)((cap - k0 < (unsigned long long)cnt) ? cap - k0 : (unsigned long long)cnt);
+            if (grp & (1u << lane)) {
+                const int rk = __popc(grp & ((1u << lane) - 1u));
+#pragma unroll
+                for (int j = 0; j < XREC_DOUBLES; j++) st[rk * XREC_DOUBLES + j] = rec[j];
+            }
+            __syncwarp();
+            if (fit < cnt && lane == lead) { /* does not fit: the step fails loudly at its read-back */
+                atomicAdd(&d.status->x_overflow, (unsigned long long)(cnt - fit));
+                pg_set_err(d, PG_DEVERR_XCAP);
+            }
+            if (fit > 0) {
+                double* out = plan.msg[dg] + (size_t)(1 + k0) * XREC_DOUBLES;
+                for (int j = lane; j < fit * XREC_DOUBLES; j += 32) out[j] = st[j];
+            }
+            __syncwarp();
+            rem &= ~grp;
         }
-        double* r = sendbuf + ((size_t)plan.off[dest] + 1 + k) * XREC_DOUBLES;
-        const PgVel V = d.p.vel[i];
-        const PgIe E = pg_ie_load(d.p.ie, i);
-        r[0] = P.x; r[1] = P.y; r[2] = P.z;
-        r[3] = V.vx; r[4] = V.vy; r[5] = V.vz;
-        r[6] = E.erot; r[7] = E.evib;
-        r[8] = d.p.dtrim ? d.p.dtrim[i] : d.dt;
-        int2 cs = make_int2(ic, P.sid);
-        r[9] = *reinterpret_cast<double*>(&cs);
-        long long id = d.p.id ? d.p.id[i] : 0;
-        r[10] = *reinterpret_cast<double*>(&id);
     }
 }
 
-/* headers of the outgoing messages; also the per-destination counts for the host's next plan */
-__global__ void xheader_kernel(const __grid_constant__ PgDev d, const unsigned long long* __restrict__ xrow, double* __restrict__ sendbuf,
-                               const __grid_constant__ XPlan plan) {
+/* headers of the outgoing messages; also the per-destination counts for the host's next plan.  Window pairs: the
+ * records were written into the peer's memory by the pack kernel, which has completed (stream order); the header
+ * follows, then -- fenced behind it -- the arrival flag the peer's xwait_kernel is polling. */
+__global__ void xheader_kernel(const __grid_constant__ PgDev d, const unsigned long long* __restrict__ xrow, const __grid_constant__ XPlan plan) {
     const int r = threadIdx.x;
     if (r == 0 && xrow[PG_XROW_OVF]) { /* the emigrant list itself overflowed: particles would be lost */
         atomicAdd(&d.status->x_overflow, xrow[PG_XROW_OVF]);
@@ -265,29 +290,52 @@ __global__ void xheader_kernel(const __grid_constant__ PgDev d, const unsigned l
     if (r >= plan.nr) return;
     unsigned long long n = (r == plan.rank) ? 0ULL : xrow[r];
     d.status->x_sent[r] = n;
-    if (r == plan.rank) return;
+    if (!plan.on[r]) return; /* (an emigrant for a rank without a message has already failed the step in the pack) */
     if (n > plan.cap[r]) n = plan.cap[r];
-    unsigned long long* h = reinterpret_cast<unsigned long long*>(sendbuf + (size_t)plan.off[r] * XREC_DOUBLES);
+    unsigned long long* h = reinterpret_cast<unsigned long long*>(plan.msg[r]);
     h[0] = n;
+    if (plan.flag[r]) {
+        __threadfence_system();
+        *reinterpret_cast<volatile unsigned long long*>(plan.flag[r]) = plan.seq;
+    }
+}
+
+/* window pairs: wait until every peer's message of this exchange has arrived (its flag carries the exchange number).
+ * The peers' packs do not depend on this rank, so the wait is bounded by the skew between ranks; a peer that stopped
+ * is reported after 30 s instead of hanging the device. */
+__global__ void xwait_kernel(const __grid_constant__ PgDev d, const __grid_constant__ XPlan plan) {
+    const int r = threadIdx.x;
+    if (r >= plan.nr || !plan.on[r] || !plan.flag[r]) return;
+    const volatile unsigned long long* f = reinterpret_cast<const volatile unsigned long long*>(plan.flag[r]);
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    while (*f < plan.seq) {
+        __nanosleep(200);
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > 30000000000ULL) {
+            pg_set_err(d, PG_DEVERR_XWAIT);
+            break;
+        }
+    }
+    __threadfence_system();
 }
 
 /* incoming messages -> append region; grid (capacity blocks, source rank).  The immigrants join the histogram of the
  * ADVECT epilogue, so the counting sort that follows needs no recount. */
-__global__ void __launch_bounds__(256) xunpack_fast_kernel(const __grid_constant__ PgDev d, const double* __restrict__ recvbuf,
-                                                           const __grid_constant__ XPlan plan, PgPlanes p) {
+__global__ void __launch_bounds__(256) xunpack_fast_kernel(const __grid_constant__ PgDev d, const __grid_constant__ XPlan plan, PgPlanes p) {
     const int src = blockIdx.y;
-    if (src == plan.rank) return;
-    const unsigned long long* hdr = reinterpret_cast<const unsigned long long*>(recvbuf + (size_t)plan.off[src] * XREC_DOUBLES);
+    if (!plan.on[src]) return;
+    const unsigned long long* hdr = reinterpret_cast<const unsigned long long*>(plan.msg[src]);
     unsigned long long n = hdr[0];
     if (n > plan.cap[src]) n = plan.cap[src];
     unsigned long long base = d.status->np_cur;
     for (int q = 0; q < src; q++) {
-        if (q == plan.rank) continue;
-        unsigned long long m = *reinterpret_cast<const unsigned long long*>(recvbuf + (size_t)plan.off[q] * XREC_DOUBLES);
+        if (!plan.on[q]) continue;
+        unsigned long long m = *reinterpret_cast<const unsigned long long*>(plan.msg[q]);
         base += (m > plan.cap[q]) ? plan.cap[q] : m;
     }
     for (unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (unsigned long long)gridDim.x * blockDim.x) {
-        const double* r = recvbuf + ((size_t)plan.off[src] + 1 + k) * XREC_DOUBLES;
+        const double* r = plan.msg[src] + (size_t)(1 + k) * XREC_DOUBLES;
         const long long o = (long long)(base + k);
         if (o >= d.capacity) { pg_set_err(d, PG_DEVERR_CAPACITY); continue; }
         double t = r[9];
@@ -310,13 +358,13 @@ __global__ void __launch_bounds__(256) xunpack_fast_kernel(const __grid_constant
 }
 
 /* after the unpack: the particle count moves on the device; per-source counts for the host's next plan */
-__global__ void xfinish_kernel(const __grid_constant__ PgDev d, const double* __restrict__ recvbuf, const __grid_constant__ XPlan plan) {
+__global__ void xfinish_kernel(const __grid_constant__ PgDev d, const __grid_constant__ XPlan plan) {
     if (threadIdx.x != 0) return;
     unsigned long long tot = 0;
     for (int q = 0; q < plan.nr; q++) {
         unsigned long long m = 0;
-        if (q != plan.rank) {
-            m = *reinterpret_cast<const unsigned long long*>(recvbuf + (size_t)plan.off[q] * XREC_DOUBLES);
+        if (plan.on[q]) {
+            m = *reinterpret_cast<const unsigned long long*>(plan.msg[q]);
             d.status->x_recv[q] = m; /* (the uncapped count: the next plan must grow with it) */
             if (m > plan.cap[q]) m = plan.cap[q];
         } else {
@@ -336,6 +384,82 @@ __global__ void fill_kernel(double* p, long long n, double v) {
 }
 
 } /* namespace */
+
+/*
+ * EXCHANGE over peer memory.  Every rank owns a WINDOW: 64 arrival flags, then two parities of one message slot per
+ * source rank.  The windows are cudaMalloc'ed once, published as CUDA IPC handles (gathered with ncclAllGather) and mapped
+ * into every other rank of the node, so that the pack kernel of a sender writes its records straight into the
+ * receiver's memory over NVLink and raises the receiver's flag; NCCL then carries only the pairs that could not be
+ * mapped (another node, IPC refused, PANTERA_GPU_XCHG_P2P=0) or whose message outgrew the slot
+ * (PANTERA_GPU_XCHG_WINDOW records per slot; default 2^21, at most 4 GiB per rank).
+ * Two parities are enough: a sender re-uses a slot two exchanges later, and it cannot get there before the receiver
+ * has unpacked it -- its own next exchange waits for the receiver's next message, which the receiver's stream sends
+ * after that unpack.
+ * Collective (every rank of the communicator calls it from pgpu_comm_init).  A pair is used only if BOTH ends mapped
+ * each other (the outcomes are gathered too), so the two ends of a pair always agree on the transport.
+ */
+static int setup_windows(pgpu_ctx* c) {
+    const int nr = c->comm_nranks, me = c->comm_rank;
+    ncclComm_t comm = (ncclComm_t)c->nccl_comm;
+    const char* e = getenv("PANTERA_GPU_XCHG_P2P");
+    const bool want = !(e && *e == '0') && nr > 1;
+    long long recs = 1LL << 21;
+    if (const char* w = getenv("PANTERA_GPU_XCHG_WINDOW")) recs = std::max(1024LL, atoll(w));
+    recs = std::min(recs, (4LL << 30) / (2LL * nr * 8 * XREC_DOUBLES) - 1);
+    struct Blob { cudaIpcMemHandle_t h; long long recs; int ok; int pad; };
+    static_assert(sizeof(Blob) <= 128, "blob");
+    std::vector<unsigned char> mine(128, 0), all((size_t)nr * 128, 0);
+    Blob* b = reinterpret_cast<Blob*>(mine.data());
+    b->recs = recs;
+    if (want) {
+        const size_t bytes = 1024 + 2 * (size_t)nr * (size_t)(recs + 1) * XREC_DOUBLES * sizeof(double);
+        if (cudaMalloc(&c->x_win, bytes) == cudaSuccess && cudaMemset(c->x_win, 0, 1024) == cudaSuccess &&
+            cudaIpcGetMemHandle(&b->h, c->x_win) == cudaSuccess) {
+            b->ok = 1;
+        } else {
+            cudaGetLastError();
+            if (c->x_win) cudaFree(c->x_win);
+            c->x_win = nullptr;
+        }
+    }
+    unsigned char* d_io = nullptr;
+    PG_CUDA(c, cudaMalloc((void**)&d_io, (size_t)(nr + 1) * 128));
+    auto gather = [&]() -> int {
+        PG_CUDA(c, cudaMemcpyAsync(d_io, mine.data(), 128, cudaMemcpyHostToDevice, c->stream));
+        PG_NCCL(c, g_nccl.AllGather(d_io, d_io + 128, 128, ncclChar, comm, c->stream));
+        PG_CUDA(c, cudaMemcpyAsync(all.data(), d_io + 128, (size_t)nr * 128, cudaMemcpyDeviceToHost, c->stream));
+        PG_CUDA(c, cudaStreamSynchronize(c->stream));
+        return PGPU_OK;
+    };
+    int rc = gather();
+    if (rc) { cudaFree(d_io); return rc; }
+    void* opened[64] = {};
+    for (int r = 0; r < nr && b->ok; r++) {
+        if (r == me) continue;
+        const Blob* pb = reinterpret_cast<const Blob*>(all.data() + (size_t)r * 128);
+        if (!pb->ok || pb->recs != recs) continue;
+        void* q = nullptr;
+        if (cudaIpcOpenMemHandle(&q, pb->h, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess) opened[r] = q;
+        else cudaGetLastError(); /* (another node, the same process, IPC not permitted: that pair stays on NCCL) */
+    }
+    /* second round: who mapped whom */
+    memset(mine.data(), 0, 128);
+    for (int r = 0; r < nr; r++) mine[(size_t)r] = opened[r] ? 1 : 0;
+    rc = gather();
+    cudaFree(d_io);
+    if (rc) return rc;
+    int npairs = 0;
+    for (int r = 0; r < nr; r++) {
+        if (r == me || !opened[r]) continue;
+        if (all[(size_t)r * 128 + (size_t)me]) { c->x_peer_win[r] = opened[r]; npairs++; }
+        else cudaIpcCloseMemHandle(opened[r]);
+    }
+    c->x_win_recs = recs;
+    c->x_seq = 0;
+    if (getenv("PANTERA_GPU_XCHG_TRACE"))
+        fprintf(stderr, "[pantera_gpu rank %d] EXCHANGE windows: %d of %d peers mapped over CUDA IPC, %lld records per slot\n", me, npairs, nr - 1, recs);
+    return PGPU_OK;
+}
 
 extern "C" int pgpu_comm_unique_id(char id128[128]) {
     const char* e = load_nccl();
@@ -362,10 +486,13 @@ extern "C" int pgpu_comm_init(pgpu_ctx* c, int nranks, int rank, const char id12
     c->comm_rank = rank;
     PG_CUDA(c, cudaMalloc((void**)&c->d_xcount, sizeof(unsigned long long) * PG_XROW * (4 + 64)));
     c->emig_valid = false;
-    return PGPU_OK;
+    return setup_windows(c);
 }
 
 extern "C" void pg_comm_destroy(pgpu_ctx* c) {
+    for (int r = 0; r < 64; r++)
+        if (c->x_peer_win[r]) { cudaIpcCloseMemHandle(c->x_peer_win[r]); c->x_peer_win[r] = nullptr; }
+    if (c->x_win) { cudaFree(c->x_win); c->x_win = nullptr; }
     if (c->nccl_comm && g_nccl.lib) g_nccl.CommDestroy((ncclComm_t)c->nccl_comm);
     c->nccl_comm = nullptr;
 }
@@ -461,22 +588,62 @@ int pg_exchange_impl(pgpu_ctx* c) {
         sp.nr = rp.nr = nr;
         sp.rank = rp.rank = c->cfg.rank;
         unsigned long long so = 0, ro = 0;
+        /* Peers: the ranks that share a face with this one, plus any rank particles went to or came from last step.
+         * (Both conditions are symmetric, so every Send has its Recv.)  A rank that is neither gets no message --
+         * at N ranks in strips that is N-3 of them, each a launch-latency-bound transfer on the critical path -- and
+         * an emigrant for it fails the step loudly (a particle crossed a whole rank's region in one step):
+         * PANTERA_GPU_XCHG_ALLPAIRS=1 brings the all-pairs messages back. */
+        if (c->x_allpairs < 0) {
+            const char* e = getenv("PANTERA_GPU_XCHG_ALLPAIRS");
+            c->x_allpairs = (e && *e == '1') ? 1 : 0;
+        }
+        bool peer[64];
+        for (int r = 0; r < nr; r++)
+            peer[r] = r != c->cfg.rank && (c->x_allpairs || !c->x_adjacent_known || (int)c->x_adjacent.size() != nr || c->x_adjacent[r] ||
+                                           c->x_prev_send[r] > 0 || c->x_prev_recv[r] > 0);
+        /* window pairs (peer memory) and NCCL pairs; both ends of a pair decide alike: the mapping was agreed on at
+         * pgpu_comm_init and the capacities derive from counts both ends know */
+        const unsigned long long seq = ++c->x_seq;
+        sp.seq = rp.seq = seq;
+        const size_t slot_d = (size_t)(c->x_win_recs + 1) * XREC_DOUBLES; /* doubles per message slot of a window */
+        bool win[64];
+        unsigned int soff[64] = {0}, roff[64] = {0};
+        unsigned long long imm = 0; /* upper bound of the immigrants */
         for (int r = 0; r < nr; r++) {
-            if (r == c->cfg.rank) continue;
-            sp.off[r] = (unsigned int)so;
-            rp.off[r] = (unsigned int)ro;
+            sp.on[r] = rp.on[r] = peer[r] ? 1 : 0;
+            win[r] = false;
+            if (!peer[r]) continue;
             sp.cap[r] = (unsigned int)std::min<double>(4.0e9, c->x_headroom * (double)c->x_prev_send[r] + 8192.0);
             rp.cap[r] = (unsigned int)std::min<double>(4.0e9, c->x_headroom * (double)c->x_prev_recv[r] + 8192.0);
+            imm += rp.cap[r];
+            win[r] = c->x_peer_win[r] && (long long)sp.cap[r] <= c->x_win_recs && (long long)rp.cap[r] <= c->x_win_recs;
+            if (win[r]) continue;
+            soff[r] = (unsigned int)so;
+            roff[r] = (unsigned int)ro;
             so += (unsigned long long)sp.cap[r] + 1;
             ro += (unsigned long long)rp.cap[r] + 1;
         }
         if ((rc = ensure_xbuf(c, (long long)std::max(so, ro)))) return rc;
         /* (pg_advect_impl has made room for the immigrants before it recorded the emigrant list: a re-allocation
          *  here would drop that list) */
-        if (c->np_ub + (long long)ro > c->capacity)
+        if (c->np_ub + (long long)imm > c->capacity)
             PG_FAIL(c, PGPU_ERR_STATE, "exchange: %lld slots in use + %llu message slots exceed the capacity %lld (raise pgpu_config.capacity)",
-                    c->np_ub, ro, c->capacity);
+                    c->np_ub, imm, c->capacity);
         pg_refresh_dev(c);
+        for (int r = 0; r < nr; r++) {
+            if (!peer[r]) continue;
+            if (win[r]) {
+                /* window layout: 128 doubles of flags, then [parity][source rank] message slots */
+                const size_t par = (size_t)(seq & 1ULL) * (size_t)nr;
+                sp.msg[r] = (double*)c->x_peer_win[r] + 128 + (par + (size_t)c->cfg.rank) * slot_d;
+                sp.flag[r] = (unsigned long long*)c->x_peer_win[r] + c->cfg.rank;
+                rp.msg[r] = (double*)c->x_win + 128 + (par + (size_t)r) * slot_d;
+                rp.flag[r] = (unsigned long long*)c->x_win + r;
+            } else {
+                sp.msg[r] = (double*)c->d_sendbuf + (size_t)soff[r] * XREC_DOUBLES;
+                rp.msg[r] = (double*)c->d_recvbuf + (size_t)roff[r] * XREC_DOUBLES;
+            }
+        }
         if (c->x_trace < 0) {
             const char* e = getenv("PANTERA_GPU_XCHG_TRACE");
             c->x_trace = (e && *e == '1') ? 1 : 0;
@@ -490,30 +657,36 @@ int pg_exchange_impl(pgpu_ctx* c) {
         if (c->x_trace) cudaEventRecord(c->xev[0], c->stream);
         c->dev.emig_list = c->d_emig_list; /* (emig_cap is read by the pack kernel) */
         PG_CUDA(c, cudaMemsetAsync(xcursor, 0, sizeof(unsigned long long) * PG_XROW, c->stream));
-        xpack_fast_kernel<<<148 * 8, 256, 0, c->stream>>>(c->dev, c->d_emig_list, xcount, (double*)c->d_sendbuf, sp, xcursor);
-        xheader_kernel<<<1, 64, 0, c->stream>>>(c->dev, xcount, (double*)c->d_sendbuf, sp);
+        xpack_fast_kernel<<<148 * 4, 256, 0, c->stream>>>(c->dev, c->d_emig_list, xcount, sp, xcursor);
+        xheader_kernel<<<1, 64, 0, c->stream>>>(c->dev, xcount, sp);
         c->dev.emig_list = nullptr;
         if (c->x_trace) cudaEventRecord(c->xev[1], c->stream);
-        PG_NCCL(c, g_nccl.GroupStart());
+        bool any_nccl = false, any_win = false;
         for (int r = 0; r < nr; r++) {
-            if (r == c->cfg.rank) continue;
-            PG_NCCL(c, g_nccl.Send((const double*)c->d_sendbuf + (size_t)sp.off[r] * XREC_DOUBLES, ((size_t)sp.cap[r] + 1) * XREC_DOUBLES,
-                                   ncclDouble, r, comm, c->stream));
-            PG_NCCL(c, g_nccl.Recv((double*)c->d_recvbuf + (size_t)rp.off[r] * XREC_DOUBLES, ((size_t)rp.cap[r] + 1) * XREC_DOUBLES,
-                                   ncclDouble, r, comm, c->stream));
+            any_nccl |= peer[r] && !win[r];
+            any_win |= peer[r] && win[r];
         }
-        PG_NCCL(c, g_nccl.GroupEnd());
+        if (any_nccl) {
+            PG_NCCL(c, g_nccl.GroupStart());
+            for (int r = 0; r < nr; r++) {
+                if (!peer[r] || win[r]) continue;
+                PG_NCCL(c, g_nccl.Send(sp.msg[r], ((size_t)sp.cap[r] + 1) * XREC_DOUBLES, ncclDouble, r, comm, c->stream));
+                PG_NCCL(c, g_nccl.Recv(rp.msg[r], ((size_t)rp.cap[r] + 1) * XREC_DOUBLES, ncclDouble, r, comm, c->stream));
+            }
+            PG_NCCL(c, g_nccl.GroupEnd());
+        }
+        if (any_win) xwait_kernel<<<1, 64, 0, c->stream>>>(c->dev, rp);
         if (c->x_trace) cudaEventRecord(c->xev[2], c->stream);
         unsigned int maxcap = 1;
         for (int r = 0; r < nr; r++) maxcap = std::max(maxcap, rp.cap[r]);
         PgPlanes p = c->planes[c->cur];
         p.dtrim = nullptr; /* every particle has DTRIM == DT right after ADVECT */
         dim3 grid(std::min<unsigned int>((maxcap + 255) / 256, 148u * 4u), (unsigned int)nr);
-        xunpack_fast_kernel<<<grid, 256, 0, c->stream>>>(c->dev, (const double*)c->d_recvbuf, rp, p);
-        xfinish_kernel<<<1, 32, 0, c->stream>>>(c->dev, (const double*)c->d_recvbuf, rp);
+        xunpack_fast_kernel<<<grid, 256, 0, c->stream>>>(c->dev, rp, p);
+        xfinish_kernel<<<1, 32, 0, c->stream>>>(c->dev, rp);
         if (c->x_trace) cudaEventRecord(c->xev[3], c->stream);
-        c->launches += 4;
-        c->np_ub += (long long)ro;
+        c->launches += 4 + (any_win ? 1 : 0);
+        c->np_ub += (long long)imm;
         c->np_dev_valid = true;
         c->x_plan_pending = true; /* pg_finish turns status->x_sent / x_recv into the next plan */
         c->maybe_tombstones = true;

@@ -104,7 +104,7 @@ struct PgStatus {
     unsigned long long x_sent[64];  /* EXCHANGE fast path: emigrants per destination ...                            */
     unsigned long long x_recv[64];  /* ... and immigrants per source (they size the next step's messages)          */
 };
-enum { PG_DEVERR_NONE = 0, PG_DEVERR_HOPS = 1, PG_DEVERR_CELL_RANGE = 2, PG_DEVERR_CAPACITY = 3, PG_DEVERR_XCAP = 4 };
+enum { PG_DEVERR_NONE = 0, PG_DEVERR_HOPS = 1, PG_DEVERR_CELL_RANGE = 2, PG_DEVERR_CAPACITY = 3, PG_DEVERR_XCAP = 4, PG_DEVERR_XWAIT = 5 };
 
 struct __align__(32) PgPos { double x, y, z; int ic, sid; };
 struct __align__(32) PgVel { double vx, vy, vz; int sid, pad; };
@@ -398,6 +398,9 @@ struct pgpu_ctx {
     int avg_cumulated = 0;
 
     /* timings */
+    std::vector<char> x_adjacent; /* [nranks] shares a face with this rank's cells (build_packed_mesh) */
+    bool x_adjacent_known = false;
+    int x_allpairs = -1;          /* PANTERA_GPU_XCHG_ALLPAIRS=1: a message for every rank, adjacent or not */
     cudaEvent_t ev[16];
     /* PANTERA_GPU_XCHG_TRACE=1: pack / transfer / unpack split of the per-step EXCHANGE, printed when the context closes */
     cudaEvent_t xev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -414,6 +417,12 @@ struct pgpu_ctx {
     void* d_sendbuf;
     void* d_recvbuf;
     long long xbuf_capacity; /* particles */
+    /* EXCHANGE over peer memory (pgpu_exchange.cu): this rank's window (flags + two parities of one message slot per
+     * source rank), the peers' windows mapped into this process (CUDA IPC; null: that pair goes through NCCL) */
+    void* x_win = nullptr;
+    long long x_win_recs = 0;
+    void* x_peer_win[64] = {};
+    unsigned long long x_seq = 0;
     unsigned long long* d_xcount; /* 4 rows of PG_XROW (counts, offsets, cursors, spare) + [nranks] gathered rows */
     unsigned int* d_emig_list;    /* [emig_cap] slots of the emigrants found by the last ADVECT */
     long long emig_cap;

@@ -37,8 +37,12 @@ EXACT = ("X", "Y", "Z", "VX", "VY", "VZ", "EROT", "EVIB")
 
 
 def strip_workload(rank, world, collisions, mesh=None):
-    n = CUBES[0] * CUBES[1] * CUBES[2] * 6 * PPC
-    w = wl.c5_channel_strip(*CUBES, n=n, rank=rank, world=world, seed=31 + rank, mesh=mesh, dt_frac=0.6)
+    # The per-step NCCL EXCHANGE only talks to ranks that share a face with this one (pgpu_exchange.cu): with four
+    # strips the x extent is doubled and the step shortened, so that no particle can cross a whole strip in one step
+    # (which would fail the step loudly, as it should).
+    cubes, dt_frac = (CUBES, 0.6) if world < 4 else ((2 * CUBES[0], CUBES[1] - 1, CUBES[2] - 1), 0.3)
+    n = cubes[0] * cubes[1] * cubes[2] * 6 * PPC
+    w = wl.c5_channel_strip(*cubes, n=n, rank=rank, world=world, seed=31 + rank, mesh=mesh, dt_frac=dt_frac)
     w.cfg.track_id = 1
     w.cfg.capacity = 3 * n
     if collisions:
