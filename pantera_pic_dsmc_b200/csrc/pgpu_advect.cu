@@ -1150,7 +1150,14 @@ int pg_advect_impl(pgpu_ctx* c, int tID) {
     if ((rc = pg_resolve_vel(c))) return rc;
 
     /* zero the per-call counters and the histogram */
-    PG_CUDA(c, cudaMemsetAsync(c->d_cell_count, 0, sizeof(unsigned int) * (size_t)pg_ncells(c), c->stream));
+    {
+        /* (several ranks, strays shipped: only the span of this rank's own cells can be counted in -- pg_cell_range) */
+        long long lo, hi;
+        pg_cell_range(c, &lo, &hi);
+        PG_CUDA(c, cudaMemsetAsync(c->d_cell_count + lo, 0, sizeof(unsigned int) * (size_t)(hi - lo), c->stream));
+        c->hist_lo = lo;
+        c->hist_hi = hi;
+    }
     PG_CUDA(c, cudaMemsetAsync(c->d_bcount, 0, sizeof(unsigned long long) * 4 * (size_t)c->ns, c->stream));
     if (c->nw) PG_CUDA(c, cudaMemsetAsync(c->d_wcount, 0, sizeof(unsigned long long) * (size_t)(c->nw * c->ns), c->stream));
 
@@ -1180,5 +1187,9 @@ int pg_advect_impl(pgpu_ctx* c, int tID) {
     c->sorted = false;
     c->hist_valid = true;
     c->maybe_tombstones = true;
+    /* several ranks: particles may now sit in cells of other ranks until EXCHANGE ships them (it sets the flag again).
+     * Until then neither the next ADVECT may trust the ownership flags of the hop codes nor a sort restrict itself to
+     * this rank's own cell range (the histogram above, which leaves the emigrants out, was counted over that range). */
+    if (c->cfg.nranks > 1) c->owned_clean = false;
     return PGPU_OK;
 }

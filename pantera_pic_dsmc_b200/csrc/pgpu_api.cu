@@ -596,6 +596,16 @@ static int build_packed_mesh(pgpu_ctx* c) {
      * Face adjacency is symmetric, so both ends of a pair come to the same answer. */
     c->x_adjacent.assign((size_t)std::max(c->cfg.nranks, 1), 0);
     c->x_adjacent_known = owner_flags;
+    c->own_lo = c->own_hi = 0; /* the span of this rank's own cells (pg_cell_range) */
+    if (owner_flags) {
+        long long first = -1, last = -1;
+        for (long long i = 0; i < (long long)c->h_cell_procs.size(); i++)
+            if (c->h_cell_procs[(size_t)i] == c->cfg.rank) {
+                if (first < 0) first = i;
+                last = i;
+            }
+        if (first >= 0) { c->own_lo = first; c->own_hi = last + 1; }
+    }
     auto packed_codes = [&](int ic, int* rec) {
         rec[0] = rec[1] = rec[2] = rec[3] = 0;
         for (int j = 0; j < nf; j++) {
@@ -741,6 +751,8 @@ void pg_refresh_dev(pgpu_ctx* c) {
     d.use_ie = ((c->any_internal_dof || c->dev.nr > 0 || c->ie_seen) && c->planes[c->cur].ie) ? 1 : 0;
     d.tile_first = c->d_tile_first;
     d.cell_order = c->sorted ? c->d_cell_order : nullptr;
+    d.cells_lo = (int)c->cells_lo;
+    d.order_n = (int)(c->cells_hi - c->cells_lo);
     d.ntiles = c->sorted ? (int)((c->np + PG_TILE_S - 1) / PG_TILE_S) : 0;
 }
 
@@ -1369,14 +1381,14 @@ __global__ void __launch_bounds__(256) scatter_small_kernel(PgPlanes src, PgPlan
 
 /* after the scan: the list of cells too large for one lane of the collision kernel (GLOBAL path), and the new particle
  * count -- the total of the histogram, tombstones left out -- which stays on the device until the call's final read-back */
-__global__ void __launch_bounds__(256) cell_tail_kernel(const unsigned int* __restrict__ cell_off, int ncells,
+__global__ void __launch_bounds__(256) cell_tail_kernel(const unsigned int* __restrict__ cell_off, int ncells, unsigned int first_cell,
                                                         unsigned int* __restrict__ big_list, long long big_cap, PgStatus* st) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= ncells) return;
     unsigned int o = cell_off[c], o1 = cell_off[c + 1];
     if (o1 - o > PG_TILE_BIG) {
         unsigned int k = atomicAdd(&st->n_big, 1u);
-        if ((long long)k < big_cap) big_list[k] = (unsigned int)c;
+        if ((long long)k < big_cap) big_list[k] = first_cell + (unsigned int)c;
     }
     if (c == ncells - 1) st->np_cur = (unsigned long long)o1;
 }
@@ -1414,7 +1426,7 @@ __global__ void __launch_bounds__(288) cell_bucket_scan_kernel(unsigned int* __r
     __syncthreads();
     for (int i = threadIdx.x; i < PG_NBUCKET; i += blockDim.x) bucket[PG_NBUCKET + i] = o[i];
 }
-__global__ void __launch_bounds__(256) cell_bucket_fill_kernel(const unsigned int* __restrict__ cell_off, int ncells,
+__global__ void __launch_bounds__(256) cell_bucket_fill_kernel(const unsigned int* __restrict__ cell_off, int ncells, unsigned int first_cell,
                                                                unsigned int* __restrict__ bucket,
                                                                unsigned int* __restrict__ order) {
     __shared__ unsigned int h[PG_NBUCKET], base[PG_NBUCKET];
@@ -1431,7 +1443,7 @@ __global__ void __launch_bounds__(256) cell_bucket_fill_kernel(const unsigned in
     for (int i = threadIdx.x; i < PG_NBUCKET; i += blockDim.x)
         if (h[i]) base[i] = atomicAdd(&bucket[PG_NBUCKET + i], h[i]);
     __syncthreads();
-    if (c < ncells) order[base[b] + r] = (unsigned int)c;
+    if (c < ncells) order[base[b] + r] = first_cell + (unsigned int)c;
 }
 
 __global__ void __launch_bounds__(256) resolve_vel_kernel(const PgVel* __restrict__ vel_src, const unsigned int* __restrict__ src_of,
@@ -1520,8 +1532,21 @@ extern "C" int pgpu_set_deterministic(pgpu_ctx* c, int32_t on) {
     return PGPU_OK;
 }
 
+void pg_cell_range(pgpu_ctx* c, long long* lo, long long* hi) {
+    *lo = 0;
+    *hi = pg_ncells(c);
+    if (c->cfg.nranks > 1 && c->owned_clean && !c->deterministic && !c->h_cell_procs.empty() && c->own_hi > c->own_lo &&
+        (long long)c->h_cell_procs.size() == *hi && *hi > PG_COUNT_SMEM_CELLS) {
+        *lo = c->own_lo;
+        *hi = c->own_hi;
+    }
+}
+
 int pg_sort_impl(pgpu_ctx* c, bool defer_vel, bool sync_np) {
     int ncells = pg_ncells(c);
+    long long lo, hi;
+    pg_cell_range(c, &lo, &hi);
+    const int nrc = (int)(hi - lo); /* cells in the range */
     { int rc0; if ((rc0 = pg_resolve_vel(c))) return rc0; }
     if (c->deterministic) defer_vel = false;
     c->n_big = 0;
@@ -1530,8 +1555,11 @@ int pg_sort_impl(pgpu_ctx* c, bool defer_vel, bool sync_np) {
         PG_CUDA(c, cudaMemsetAsync(c->d_cell_off, 0, sizeof(unsigned int) * ((size_t)ncells + 1), c->stream));
         c->sorted = true;
         c->maybe_tombstones = false;
+        c->cells_lo = 0;
+        c->cells_hi = ncells;
         return PGPU_OK;
     }
+    if (c->hist_valid && (c->hist_lo != lo || c->hist_hi != hi)) c->hist_valid = false; /* counted over another range */
     PgPlanes src = c->planes[c->cur], dst = c->planes[c->cur ^ 1];
     if (!c->has_dtrim) src.dtrim = nullptr;
     /* the particle count may have moved on the device since the call began (immigrants): the grids cover the host's
@@ -1542,7 +1570,7 @@ int pg_sort_impl(pgpu_ctx* c, bool defer_vel, bool sync_np) {
         c->emig_valid = false;
     }
     if (!c->hist_valid) {
-        PG_CUDA(c, cudaMemsetAsync(c->d_cell_count, 0, sizeof(unsigned int) * ((size_t)ncells + 1), c->stream));
+        PG_CUDA(c, cudaMemsetAsync(c->d_cell_count + lo, 0, sizeof(unsigned int) * ((size_t)nrc + 1), c->stream));
         if (ncells <= PG_COUNT_SMEM_CELLS) {
             const unsigned int hb = blocks < 148u * 8u ? blocks : 148u * 8u;
             hist_small_kernel<<<hb, 256, sizeof(unsigned int) * (size_t)ncells, c->stream>>>(src.pos, c->d_status, c->d_cell_count, ncells);
@@ -1552,14 +1580,14 @@ int pg_sort_impl(pgpu_ctx* c, bool defer_vel, bool sync_np) {
         c->launches++;
     }
     size_t tmp = c->scan_tmp_bytes;
-    PG_CUDA(c, cub::DeviceScan::ExclusiveSum(c->d_scan_tmp, tmp, c->d_cell_count, c->d_cell_off, ncells + 1, c->stream));
+    PG_CUDA(c, cub::DeviceScan::ExclusiveSum(c->d_scan_tmp, tmp, c->d_cell_count + lo, c->d_cell_off + lo, nrc + 1, c->stream));
     c->launches++;
     if (c->deterministic) {
         int rcd;
         if ((rcd = sort_deterministic(c, src, dst, ncells))) return rcd;
     } else {
         /* the histogram has been scanned into cell_off: its array now serves as the per-cell cursor of the scatter */
-        PG_CUDA(c, cudaMemsetAsync(c->d_cell_count, 0, sizeof(unsigned int) * ((size_t)ncells + 1), c->stream));
+        PG_CUDA(c, cudaMemsetAsync(c->d_cell_count + lo, 0, sizeof(unsigned int) * ((size_t)nrc + 1), c->stream));
         if (ncells <= PG_COUNT_SMEM_CELLS && !defer_vel) {
             const unsigned int sb = (unsigned int)((c->np_ub + 256 * PG_SCATTER_TILE - 1) / (256 * PG_SCATTER_TILE));
             scatter_small_kernel<<<sb, 256, 2 * sizeof(unsigned int) * (size_t)ncells, c->stream>>>(
@@ -1571,13 +1599,16 @@ int pg_sort_impl(pgpu_ctx* c, bool defer_vel, bool sync_np) {
         c->launches++;
     }
     {
-        unsigned int cb = (unsigned int)((ncells + 255) / 256);
-        cell_tail_kernel<<<cb, 256, 0, c->stream>>>(c->d_cell_off, ncells, c->d_big_list, c->big_alloc, c->d_status);
+        /* (the kernels see the range as cells 0..nrc-1 of a shifted cell_off and add `lo` to the ids they store) */
+        unsigned int cb = (unsigned int)((nrc + 255) / 256);
+        cell_tail_kernel<<<cb, 256, 0, c->stream>>>(c->d_cell_off + lo, nrc, (unsigned int)lo, c->d_big_list, c->big_alloc, c->d_status);
         PG_CUDA(c, cudaMemsetAsync(c->d_cell_bucket, 0, sizeof(unsigned int) * 2 * PG_NBUCKET, c->stream));
-        cell_bucket_count_kernel<<<cb, 256, 0, c->stream>>>(c->d_cell_off, ncells, c->d_cell_bucket);
+        cell_bucket_count_kernel<<<cb, 256, 0, c->stream>>>(c->d_cell_off + lo, nrc, c->d_cell_bucket);
         cell_bucket_scan_kernel<<<1, 288, 0, c->stream>>>(c->d_cell_bucket);
-        cell_bucket_fill_kernel<<<cb, 256, 0, c->stream>>>(c->d_cell_off, ncells, c->d_cell_bucket, c->d_cell_order);
+        cell_bucket_fill_kernel<<<cb, 256, 0, c->stream>>>(c->d_cell_off + lo, nrc, (unsigned int)lo, c->d_cell_bucket, c->d_cell_order);
         c->launches += 4;
+        c->cells_lo = lo;
+        c->cells_hi = hi;
     }
     PG_CUDA(c, cudaGetLastError());
     c->cur ^= 1;
@@ -1792,9 +1823,11 @@ extern "C" int pgpu_get_cell_counts(pgpu_ctx* c, int32_t* npc, int64_t nc) {
     cudaSetDevice(c->device);
     if (!c->sorted) PG_FAIL(c, PGPU_ERR_STATE, "get_cell_counts: the store is not sorted (call pgpu_sort or pgpu_collide first)");
     int64_t m = std::min<int64_t>(nc, pg_ncells(c));
-    std::vector<unsigned int> off((size_t)m + 1);
+    /* cell_off describes the cells [cells_lo, cells_hi) (the rank's own range once an EXCHANGE has run); the rest are empty */
+    const int64_t lo = std::min<int64_t>(c->cells_lo, m), hi = std::min<int64_t>(c->cells_hi, m);
+    std::vector<unsigned int> off((size_t)(hi - lo) + 1);
     PG_CUDA(c, cudaStreamSynchronize(c->stream));
-    PG_CUDA(c, cudaMemcpy(off.data(), c->d_cell_off, sizeof(unsigned int) * ((size_t)m + 1), cudaMemcpyDeviceToHost));
-    for (int64_t i = 0; i < m; i++) npc[i] = (int32_t)(off[i + 1] - off[i]);
+    if (hi > lo) PG_CUDA(c, cudaMemcpy(off.data(), c->d_cell_off + lo, sizeof(unsigned int) * ((size_t)(hi - lo) + 1), cudaMemcpyDeviceToHost));
+    for (int64_t i = 0; i < m; i++) npc[i] = (i >= lo && i < hi) ? (int32_t)(off[i - lo + 1] - off[i - lo]) : 0;
     return PGPU_OK;
 }

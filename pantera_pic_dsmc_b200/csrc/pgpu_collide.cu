@@ -357,7 +357,7 @@ __global__ void __launch_bounds__(128, IE ? PG_CELL_MINBLOCKS_IE : PG_CELL_MINBL
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     /* cells are handed out grouped by particle count (pg_sort_impl): the lanes of a warp then walk similar numbers
      * of candidates instead of idling behind the fullest cell */
-    const long long c = (tid < d.ncells) ? (d.cell_order ? (long long)__ldg(&d.cell_order[tid]) : tid) : (long long)d.ncells;
+    const long long c = (tid < d.order_n) ? (d.cell_order ? (long long)__ldg(&d.cell_order[tid]) : tid + d.cells_lo) : (long long)d.ncells;
     unsigned int o0 = 0;
     int n = 0;
     if (c < d.ncells) {
@@ -837,7 +837,7 @@ int pg_collide_impl(pgpu_ctx* c, int tID, bool big_now) {
     const PgDev& d = c->dev;
 
     {
-        unsigned int blocks = (unsigned int)((d.ncells + 127) / 128);
+        unsigned int blocks = (unsigned int)((d.order_n + 127) / 128); /* (the cells the sort covered: pg_cell_range) */
         const bool gather = c->vel_deferred;
         if (d.use_ie) {
             if (gather) cell_collide_kernel<true, true><<<blocks, 128, 0, c->stream>>>(d);

@@ -271,7 +271,8 @@ struct PgDev {
     long long id_base;        /* ID counter for particles created on the device */
     int use_ie;               /* 1: the ie plane is live (some particle can hold internal energy) */
     const unsigned int* tile_first; /* [ntiles+1] first cell of every collision tile (valid while sorted) */
-    const unsigned int* cell_order; /* [ncells] the cells grouped by particle count, fullest first (valid while sorted) */
+    const unsigned int* cell_order; /* [order_n] the cells grouped by particle count, fullest first (valid while sorted) */
+    int order_n, cells_lo;          /* cell_order / cell_off describe the cells [cells_lo, cells_lo + order_n) (pgpu_ctx::own_lo) */
     int ntiles;
     /* emigrant bookkeeping in the ADVECT epilogue (nranks > 1): a particle whose final cell belongs to another
      * rank is not histogrammed; its slot goes to emig_list and its destination is counted in xrow, so that
@@ -398,6 +399,13 @@ struct pgpu_ctx {
     int avg_cumulated = 0;
 
     /* timings */
+    /* Cells this rank can hold particles in.  Every rank carries the whole mesh (hop codes and geometry of all cells:
+     * a particle may finish its step anywhere), but once an EXCHANGE has shipped the strays (owned_clean) only the
+     * cells [own_lo, own_hi) spanned by this rank's own cells are populated: the histogram, its scan, the cursor, the
+     * cell lists and the collision launch then cover that range instead of the global mesh (at N ranks in strips, 1/N
+     * of it).  hist_lo/hi: the range a valid histogram was counted over; cells_lo/hi: the range cell_off and
+     * cell_order describe. */
+    long long own_lo = 0, own_hi = 0, hist_lo = 0, hist_hi = 0, cells_lo = 0, cells_hi = 0;
     std::vector<char> x_adjacent; /* [nranks] shares a face with this rank's cells (build_packed_mesh) */
     bool x_adjacent_known = false;
     int x_allpairs = -1;          /* PANTERA_GPU_XCHG_ALLPAIRS=1: a message for every rank, adjacent or not */
@@ -465,6 +473,7 @@ int pg_collide_big(pgpu_ctx* c);             /* GLOBAL path for the oversized ce
 int pg_exchange_impl(pgpu_ctx* c);
 void pg_refresh_dev(pgpu_ctx* c);
 int pg_fill_dtrim(pgpu_ctx* c);               /* DTRIM plane (allocated on first use) = DT for the particles in the store */
+void pg_cell_range(pgpu_ctx* c, long long* lo, long long* hi); /* the cells the per-cell passes have to cover now */
 int pg_need_ie(pgpu_ctx* c);                  /* allocate the internal-energy planes (zero) if they do not exist yet */
 int pg_need_dtrim(pgpu_ctx* c);               /* allocate the DTRIM planes if they do not exist yet */
 void pg_inject_destroy(pgpu_ctx* c);
