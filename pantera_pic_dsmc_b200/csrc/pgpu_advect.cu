@@ -474,6 +474,56 @@ __device__ __forceinline__ void select_face(const PgDev& d, const PState& q, int
     float t_lo[NF];
     float T = INF;
     unsigned int open = 0u;
+    if constexpr (DIMS == 3) {
+        /* Tetrahedra: the kernel issues on 65 % of its cycles (ncu r02t) and the brackets are a third of its
+         * instructions, so the four faces are evaluated two at a time in packed single precision (FFMA2 / FADD2 /
+         * FMUL2 of sm_100: the same roundings as the scalar code below, half the instructions), the accurate-range
+         * tests of the reciprocals are one integer compare each, and the products VN*DT of the scalar form are replaced
+         * by comparisons of the crossing-time brackets that are needed anyway:
+         *     t_lo = dx_lo / vn_hi (a lower bound of the crossing time, if dx_lo > 0 and vn_hi is in range, else -inf)
+         *     t_hi = max(dx_hi, 0) / vn_lo * (1 + 4e-6)   (an upper bound, if vn_lo is in range)
+         *     fail  <=  vn_hi < 0  or  t_lo > dt_hi ;   pass  <=  vn_lo in range  and  t_hi < dt_lo .
+         * The approximate reciprocal is good to 1 ulp and the product to half an ulp; t_lo carries no margin of its own,
+         * t_hi carries both (4e-6 >> 2 x 2^-22), so that t_lo > T still means "certainly later than the face of T". */
+        const float2 vx2 = make_float2(vxf, vxf), vy2 = make_float2(vyf, vyf), vz2 = make_float2(vzf, vzf);
+        const float2 x2 = make_float2(xf, xf), y2 = make_float2(yf, yf), z2 = make_float2(zf, zf);
+        const float2 pEV = make_float2(EV, EV), nEV = make_float2(-EV, -EV), X12 = make_float2(X1, X1);
+        const float2 cp = make_float2(1.e-6f, 1.e-6f), cn = make_float2(-1.e-6f, -1.e-6f), m1 = make_float2(-1.f, -1.f);
+        const float2 c4 = make_float2(1.f + 4.e-6f, 1.f + 4.e-6f);
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const float4 A = F[2 * h], B = F[2 * h + 1];
+            const float2 nx = make_float2(A.x, B.x), ny = make_float2(A.y, B.y), nz = make_float2(A.z, B.z), w = make_float2(A.w, B.w);
+            float2 vn = __fmul2_rn(vx2, nx), xn = __fmul2_rn(x2, nx);
+            vn = __ffma2_rn(vy2, ny, vn); xn = __ffma2_rn(y2, ny, xn);
+            vn = __ffma2_rn(vz2, nz, vn); xn = __ffma2_rn(z2, nz, xn);
+            const float2 dx = __ffma2_rn(xn, m1, w); /* w - xn, one rounding */
+            const float2 Ea = __fadd2_rn(X12, make_float2(fabsf(A.w), fabsf(B.w)));
+            const float2 vhi = __fadd2_rn(vn, pEV), vlo = __fadd2_rn(vn, nEV);
+            const float2 dhi = __ffma2_rn(Ea, cp, dx), dlo = __ffma2_rn(Ea, cn, dx);
+            float2 rhi, rlo;
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rhi.x) : "f"(vhi.x));
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rhi.y) : "f"(vhi.y));
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rlo.x) : "f"(vlo.x));
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rlo.y) : "f"(vlo.y));
+            const float2 tl = __fmul2_rn(dlo, rhi);
+            const float2 th = __fmul2_rn(__fmul2_rn(make_float2(fmaxf(dhi.x, 0.f), fmaxf(dhi.y, 0.f)), rlo), c4);
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const int i = 2 * h + e;
+                const float vhi_e = e ? vhi.y : vhi.x, vlo_e = e ? vlo.y : vlo.x, dlo_e = e ? dlo.y : dlo.x;
+                const float tl_e = e ? tl.y : tl.x, th_e = e ? th.y : th.x;
+                /* x in (1e-30, 1e30) as one unsigned compare of the bit patterns (negative, zero, NaN: false) */
+                const bool hi_ok = (__float_as_uint(vhi_e) - 0x0DA24261u) < (0x7149F2CAu - 0x0DA24261u);
+                const bool lo_ok = (__float_as_uint(vlo_e) - 0x0DA24261u) < (0x7149F2CAu - 0x0DA24261u);
+                t_lo[i] = (dlo_e > 0.f && hi_ok) ? tl_e : -INF;
+                const bool fail = (vhi_e < 0.f) || (t_lo[i] > dt_hi);
+                const bool pass = lo_ok && (th_e < dt_lo);
+                T = fminf(T, pass ? th_e : INF);
+                if (!fail) open |= 1u << i; /* (a NaN anywhere compares false: the face stays open) */
+            }
+        }
+    } else {
 #pragma unroll
     for (int i = 0; i < NF; i++) {
         /* (explicit fused multiply-adds: the bounds hold for any single-precision evaluation order) */
@@ -492,6 +542,7 @@ __device__ __forceinline__ void select_face(const PgDev& d, const PState& q, int
         const float th = __fdividef(fmaxf(dx_hi, 0.f), vn_lo) * (1.f + 2.e-6f);
         T = pass ? fminf(T, th) : T;
         if (!fail) open |= 1u << i; /* (a NaN anywhere compares false: the face stays open) */
+    }
     }
     unsigned int rel = 0u;
 #pragma unroll
