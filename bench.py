@@ -458,9 +458,10 @@ def main():
                            "collide": "cell_collide_kernel"}[dom],
                 "kernel_ms_per_launch": grp[dom], "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs, burst copy)",
                 "algorithmic_bytes_per_particle": bytes_grp[dom], "algorithmic_bytes_per_launch": bytes_grp[dom] * n_now,
-                "note": ("only the sort is HBM-bound (88 % of the measured peak for the bytes it must move); ADVECT is issue/latency-"
-                         "bound since the single-precision face filter took it off the L1 data pipe (wavefronts 76 % -> 43 %), the "
-                         "collisions are bound by per-lane DRAM latency (DESIGN.md section 3, profiles/r02*)"),
+                "note": ("only the sort is HBM-bound (88 % of the measured peak for the bytes it must move); ADVECT has three "
+                         "co-limiters at 60-65 % each (issue slots, L1 data pipe, the dependent record -> filter -> exact-face "
+                         "chain; ncu r02v), the collisions are bound by the latency of the draw -> loads -> test chain per "
+                         "candidate (t = 2.1 ms + 5.5 ms / resident blocks per SM; DESIGN.md section 3, profiles/r02*)"),
                 "whole_step": {"achieved": ach_step, "frac": ach_step / peak, "algorithmic_bytes_per_particle": B_ALG_RESTATED,
                                "survey_8d": {"achieved": ach_step_survey, "frac": ach_step_survey / peak,
                                              "algorithmic_bytes_per_particle": B_ALG}},
