@@ -471,12 +471,19 @@ extern "C" int pgpu_comm_unique_id(char id128[128]) {
     return PGPU_OK;
 }
 
+extern "C" void pg_comm_destroy(pgpu_ctx* c);
+
 extern "C" int pgpu_comm_init(pgpu_ctx* c, int nranks, int rank, const char id128[128]) {
     if (!c) return PGPU_ERR_INVALID;
     cudaSetDevice(c->device);
     if (nranks < 1 || nranks > 64 || rank < 0 || rank >= nranks) PG_FAIL(c, PGPU_ERR_INVALID, "comm_init: bad rank %d of %d (max 64 ranks)", rank, nranks);
     const char* e = load_nccl();
     if (e) PG_FAIL(c, PGPU_ERR_NCCL, "comm_init: %s", e);
+    if (c->nccl_comm) { /* a second initialisation replaces the first (communicator, windows, counters) */
+        pg_comm_destroy(c);
+        if (c->d_xcount) { cudaFree(c->d_xcount); c->d_xcount = nullptr; }
+        c->x_counts_valid = false;
+    }
     ncclUniqueId id;
     memcpy(&id, id128, 128);
     ncclComm_t comm;

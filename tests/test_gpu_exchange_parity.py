@@ -214,10 +214,13 @@ def _free_port() -> int:
         return s.getsockname()[1]
 
 
-def _nccl_worker(rank, world, port, out_dir):
+def _nccl_worker(rank, world, port, out_dir, p2p):
     import torch
     import torch.distributed as dist
 
+    # "1": EXCHANGE over peer-memory windows (CUDA IPC, the default); "0": every message through ncclSend/ncclRecv
+    # (the path a pair takes when its windows cannot be mapped)
+    os.environ["PANTERA_GPU_XCHG_P2P"] = p2p
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
@@ -257,14 +260,14 @@ def _nccl_worker(rank, world, port, out_dir):
 
 
 @pytest.mark.timeout(600)
-@pytest.mark.parametrize("world", [2, 4])
-def test_nccl_ranks_match_rank_per_strip_oracle(tmp_path, world):
+@pytest.mark.parametrize("world,p2p", [(2, "1"), (2, "0"), (4, "1")])
+def test_nccl_ranks_match_rank_per_strip_oracle(tmp_path, world, p2p):
     import torch
     import torch.multiprocessing as mp
 
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
-    mp.spawn(_nccl_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_nccl_worker, args=(world, _free_port(), str(tmp_path), p2p), nprocs=world, join=True)
     orcs, mesh = [], None
     for r in range(world):
         w = strip_workload(r, world, collisions=False, mesh=mesh)
