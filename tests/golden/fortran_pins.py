@@ -18,6 +18,8 @@ Covered reference lines:
                 :1433-1443 (specular), :1648-1657; face geometry src/grid_and_partition.f90:1932-1957
   axi_move      src/timecycle.f90:2297-2332 (MOVE_PARTICLE, axisymmetric branch)
   cll_reflect   src/timecycle.f90:1485-1550 (CLL), src/tools.f90:245-285 (INTERNAL_ENERGY)
+  mcc_vahedi    src/collisions.f90:1606-1892 (MCC_COLLISIONS_VAHEDI), src/tools.f90:1544-1593 (INTERP_CS), :130-187 (MAXWELL)
+  diffuse_reflect  src/timecycle.f90:1445-1476 (DIFFUSE), src/tools.f90:130-187 (MAXWELL), :1150-1186 (FLX), :245-285
   vss_pair_bl   src/collisions.f90:202-253 (majorant), :259-325 (selection, acceptance), :454-546 (Borgnakke-Larsen + VSS
                 deflection), :892-937 (FUNCTION_I, COLL_INTERNAL_ENERGY)
   tce_3prod     src/collisions.f90:331-449 (TCE test, 3-product redistribution), :956-992 (HS_SCATTER)
@@ -147,6 +149,39 @@ def internal_energy(rf, dof, temp):
     return x * KB * temp
 
 
+def maxwell(rf, ux, uy, uz, tx, ty, tz, m):
+    """src/tools.f90:130-187."""
+    pi2 = 2.0 * PI
+    vel = []
+    for tt in (tx, ty, tz):
+        if tt == 0.0:
+            vel.append(0.0)
+            continue
+        r = rf()
+        teta = pi2 * r
+        beta = 1.0 / math.sqrt(2.0 * KB / m * tt)
+        r1 = rf()
+        while r1 < 1.0e-13:
+            r1 = rf()
+        ro = math.sqrt(-math.log(r1)) / beta
+        vel.append(ro * math.sin(teta))
+    return ux + vel[0], uy + vel[1], uz + vel[2]
+
+
+def flx(rf, sn, tinf, m):
+    """src/tools.f90:1150-1186."""
+    beta = 1.0 / math.sqrt(2.0 * KB / m * tinf)
+    acca = math.sqrt(sn ** 2 + 2.0)
+    kappa = 2.0 / (sn + acca) * math.exp(0.5 + 0.5 * sn * (sn - acca))
+    while True:
+        r1 = rf()
+        y = -3.0 + 6.0 * r1
+        r2 = rf()
+        fm = kappa * (y + sn) * math.exp(-y ** 2)
+        if r2 <= fm:
+            return y / beta
+
+
 def advect_tet(mesh, bc, species, p, dt, rf):
     """One particle through ADVECT on the 3-D unstructured grid (no PIC, no axisymmetry, no tallies).
     src/timecycle.f90:1166-1170, 1257-1305, 1309-1360, 1433-1443 (specular), 1485-1550 (CLL), 1644-1657.
@@ -211,6 +246,20 @@ def advect_tet(mesh, bc, species, p, dt, rf):
                     vx = v_perp * fn[0] + v_tang1 * t1[0] + v_tang2 * t2[0]
                     vy = v_perp * fn[1] + v_tang1 * t1[1] + v_tang2 * t2[1]
                     vz = v_perp * fn[2] + v_tang1 * t1[2] + v_tang2 * t2[2]
+                elif kind[0] == "diffuse":
+                    # src/timecycle.f90:1445-1476: MAXWELL(0,0,0,Tw,Tw,Tw, VDUMMY, V_TANG1, V_TANG2) -- three components are
+                    # drawn, the first is discarded --, INTERNAL_ENERGY (rot, vib), then FLX for the normal component
+                    wall_temp = kind[1]
+                    m = species[p["sid"]]["mass"]
+                    _, v_tang1, v_tang2 = maxwell(rf, 0.0, 0.0, 0.0, wall_temp, wall_temp, wall_temp, m)
+                    erot = internal_energy(rf, species[p["sid"]]["rotdof"], wall_temp)
+                    evib = internal_energy(rf, species[p["sid"]]["vibdof"], wall_temp)
+                    v_perp = flx(rf, 0.0, wall_temp, m)
+                    t1 = mesh["tang1"][ic - 1][boundcoll - 1]
+                    t2 = mesh["tang2"][ic - 1][boundcoll - 1]
+                    vx = v_perp * fn[0] + v_tang1 * t1[0] + v_tang2 * t2[0]
+                    vy = v_perp * fn[1] + v_tang1 * t1[1] + v_tang2 * t2[1]
+                    vz = v_perp * fn[2] + v_tang1 * t1[2] + v_tang2 * t2[2]
                 else:
                     raise ValueError(kind)
             else:
@@ -265,6 +314,119 @@ def hs_scatter(rf, ecoll, m1, m2, c1, c2):
     grel = [g * sinphi * math.cos(theta), g * sinphi * math.sin(theta), g * cosphi]
     w = [m1 / (m1 + m2) * c1[i] + m2 / (m1 + m2) * c2[i] for i in range(3)]
     return ([w[i] + m2 / (m1 + m2) * grel[i] for i in range(3)], [w[i] - m1 / (m1 + m2) * grel[i] for i in range(3)])
+
+
+def interp_cs(e, te, tcs):
+    """src/tools.f90:1544-1593 (1-based L, R, INDEX kept as in the source)."""
+    L, R = 1, len(te)
+    if e < te[L - 1] or e > te[R - 1]:
+        return 0.0
+    if R != L + 1:
+        while True:
+            idx = (L + R) // 2
+            if te[idx - 1] <= e:
+                if te[idx] > e:
+                    break
+                L = idx
+            else:
+                if te[idx - 2] <= e:
+                    idx = idx - 1
+                    break
+                R = idx
+        L, R = idx, idx + 1
+    return tcs[L - 1] + (tcs[R - 1] - tcs[L - 1]) * (e - te[L - 1]) / (te[R - 1] - te[L - 1])
+
+
+def mcc_collisions_vahedi(species, parts, reactions, bg, bg_dens, bg_ttra, dt, rf):
+    """src/collisions.f90:1606-1892 for N_PROD <= 3.  parts: list of dicts v, erot, evib, sid (name), pos; modified in place,
+    created particles appended (the materialised partner first, then a third product).  bg: [(name, molfrac)].
+    reactions: dicts r1, r2, p1, p2, p3 (names), nprod, is_cex, ea, te, tcs.  Returns (TIMESTEP_COLL, TIMESTEP_REAC)."""
+    null_coll_freq = bg_dens * float(F32(1e-12))            # :1637  (1e-12 is a default-REAL literal)
+    p_null = 1 - math.exp(-dt * null_coll_freq)
+    assert p_null <= 1
+    ncoll = nreac = 0
+    for jp1 in range(len(parts)):                            # DO JP1 = 1, NP_PROC_INITIAL
+        q1 = parts[jp1]
+        if rf() > p_null:
+            continue
+        ncoll += 1
+        s1 = q1["sid"]
+        reacted = False
+        for s2, frac in bg:
+            bg_nrho = frac * bg_dens
+            if bg_nrho == 0:
+                continue
+            c2 = list(maxwell(rf, 0.0, 0.0, 0.0, bg_ttra, bg_ttra, bg_ttra, species[s2]["mass"]))
+            vr2 = (c2[0] - q1["v"][0]) ** 2 + (c2[1] - q1["v"][1]) ** 2 + (c2[2] - q1["v"][2]) ** 2
+            vr = math.sqrt(vr2)
+            r_select = rf()
+            c1 = list(q1["v"])
+            m1, m2 = species[s1]["mass"], species[s2]["mass"]
+            mred = m1 * m2 / (m1 + m2)
+            etr = 0.5 * mred * vr2
+            p_cum = 0.0
+            for r in reactions:
+                if r["r1"] != s1 or r["r2"] != s2:
+                    continue
+                ea = r["ea"]
+                if etr <= ea:
+                    continue
+                sigma_r = interp_cs(etr, r["te"], r["tcs"])
+                p_cum = p_cum + (1.0 - math.exp(-bg_nrho * sigma_r * vr * dt)) / p_null
+                if r_select < p_cum:
+                    erot = internal_energy(rf, species[s2]["rotdof"], bg_ttra)
+                    evib = internal_energy(rf, species[s2]["vibdof"], bg_ttra)
+                    q2 = dict(v=list(c2), erot=erot, evib=evib, sid=s2, pos=list(q1["pos"]))
+                    parts.append(q2)
+                    nreac += 1
+                    ecoll = etr - ea
+                    p1, p2 = r["p1"], r["p2"]
+                    q1["sid"], q2["sid"] = p1, p2
+                    if not r["is_cex"]:
+                        totdof = 3.0 + species[p2]["rotdof"] + species[p2]["vibdof"] + species[p1]["rotdof"]
+                        if r["nprod"] >= 3:
+                            p3 = r["p3"]
+                            totdof = totdof + 3.0 + species[p3]["rotdof"] + species[p3]["vibdof"]
+                        ei = coll_internal_energy(rf, ecoll, totdof, species[p1]["vibdof"])
+                        q1["evib"] = ei
+                        ecoll = ecoll - ei
+                        totdof = totdof - species[p1]["rotdof"]
+                        ei = coll_internal_energy(rf, ecoll, totdof, species[p1]["rotdof"])
+                        q1["erot"] = ei
+                        ecoll = ecoll - ei
+                        totdof = totdof - species[p2]["vibdof"]
+                        ei = coll_internal_energy(rf, ecoll, totdof, species[p2]["vibdof"])
+                        q2["evib"] = ei
+                        ecoll = ecoll - ei
+                        totdof = totdof - species[p2]["rotdof"]
+                        ei = coll_internal_energy(rf, ecoll, totdof, species[p2]["rotdof"])
+                        q2["erot"] = ei
+                        ecoll = ecoll - ei
+                        m1 = species[p1]["mass"]
+                        m2 = species[p2]["mass"] if r["nprod"] == 2 else species[p2]["mass"] + species[p3]["mass"]
+                        totdof = totdof - 3.0
+                        ei = coll_internal_energy(rf, ecoll, totdof, 3)
+                        c1, c2 = hs_scatter(rf, ei, m1, m2, c1, c2)
+                        ecoll = ecoll - ei
+                        q1["v"] = list(c1)
+                        if r["nprod"] == 2:
+                            q2["v"] = list(c2)
+                        else:
+                            totdof = totdof - species[p3]["vibdof"]
+                            evib3 = coll_internal_energy(rf, ecoll, totdof, species[p3]["vibdof"])
+                            ecoll = ecoll - evib3
+                            totdof = totdof - species[p3]["rotdof"]
+                            erot3 = coll_internal_energy(rf, ecoll, totdof, species[p3]["rotdof"])
+                            ecoll = ecoll - erot3
+                            c1 = list(c2)
+                            c1, c2 = hs_scatter(rf, ecoll, species[p2]["mass"], species[p3]["mass"], c1, c2)
+                            q2["v"] = list(c1)
+                            parts.append(dict(v=list(c2), erot=erot3, evib=evib3, sid=p3, pos=list(q2["pos"])))
+                    reacted = True
+                    break
+            if reacted:
+                break
+    return ncoll, nreac
 
 
 def vss_collis_cell(species, names, parts, reactions, sigmamax, fnum, dt, vol, rf):
@@ -503,6 +665,18 @@ def main():
     out["cll_reflect"] = dict(dt=hx(1.0e-3), wall=dict(temp=500.0, acc_n=0.8, acc_t=0.6), draws=draws, inp=pdict(p), out=pdict(q),
                               trace=trace)
 
+    # ---- diffuse_reflect: O2 against a fully diffuse (Maxwell) wall on z = 0.  Draws: MAXWELL 3 x (R, R1) -- the first R1
+    # below 1e-13 and redrawn --, EROT (dof 2), EVIB (dof 2), FLX: one rejected (R1, R2) pair, then an accepted one
+    bc_dif = dict(bc_spec)
+    bc_dif[1] = ("diffuse", 650.0)
+    draws = [0.11, 1.0e-14, 0.52, 0.73, 0.29, 0.91, 0.64, 0.35, 0.48, 0.95, 0.99, 0.62, 0.17]
+    p = dict(x=0.25, y=0.3, z=0.15, vx=-130.0, vy=240.0, vz=-520.0, erot=1.5e-21, evib=0.5e-21, ic=1, sid="O2")
+    s = Script(draws)
+    q, trace = advect_tet(mesh, bc_dif, air, p, 1.0e-3, s)
+    assert s.k == len(draws) and trace[0] == [1, 1], (s.k, trace)
+    out["diffuse_reflect"] = dict(dt=hx(1.0e-3), wall=dict(temp=650.0, acc_n=1.0, acc_t=1.0), draws=draws, inp=pdict(p),
+                                  out=pdict(q), trace=trace)
+
     # ---- collisions in one structured cell (Dimensions 2, NX = NY = 1, VOL = CELL_VOL)
     names = ["O2", "N2", "O", "N", "NO"]
     sigmamax = max(vss_pair(air[a], air[b])["sigma"] for a in names for b in names)
@@ -551,6 +725,60 @@ def main():
                             inp=[dict(v=[hx(c) for c in q["v"]], erot=hx(q["erot"]), evib=hx(q["evib"]), sid=q["sid"], pos=q["pos"]) for q in hot_in],
                             out=[dict(v=[hx(c) for c in q["v"]], erot=hx(q["erot"]), evib=hx(q["evib"]), sid=q["sid"]) for q in hot],
                             created=[dict(v=[hx(c) for c in q["v"]], erot=hx(q["erot"]), evib=hx(q["evib"]), sid=q["sid"], pos=q["pos"]) for q in created])
+    # ---- mcc_vahedi: e + Ar -> e + Ar+ + e (LXCat ionisation, three products), Ar+ + Ar charge exchange, one particle that
+    # fails the null-collision test.  Tables: a few points, so that INTERP_CS's bisection takes both branches.
+    ar = read_species("ar")
+    QE = 1.602176634e-19
+    te = [v * QE for v in (0.0, 0.5, 2.0, 8.0, 15.0, 30.0, 100.0, 1000.0)]
+    reac = [dict(r1="e", r2="Ar", p1="e", p2="Ar", p3=None, nprod=2, is_cex=0, ea=0.0, te=te,
+                 tcs=[1.0e-20, 0.6e-20, 1.5e-20, 9.0e-20, 14.0e-20, 9.0e-20, 3.0e-20, 0.5e-20]),
+            dict(r1="e", r2="Ar", p1="e", p2="Ar", p3=None, nprod=2, is_cex=0, ea=11.5 * QE, te=te,
+                 tcs=[0.0, 0.0, 0.0, 0.0, 0.4e-20, 1.6e-20, 1.1e-20, 0.2e-20]),
+            dict(r1="e", r2="Ar", p1="e", p2="Ar+", p3="e", nprod=3, is_cex=0, ea=15.76 * QE, te=te,
+                 tcs=[0.0, 0.0, 0.0, 0.0, 0.0, 20.0e-20, 28.0e-20, 8.0e-20]),
+            dict(r1="Ar+", r2="Ar", p1="Ar+", p2="Ar", p3=None, nprod=2, is_cex=0, ea=0.0, te=te,
+                 tcs=[40.0e-20, 38.0e-20, 35.0e-20, 30.0e-20, 28.0e-20, 25.0e-20, 20.0e-20, 10.0e-20]),
+            dict(r1="Ar+", r2="Ar", p1="Ar", p2="Ar+", p3=None, nprod=2, is_cex=1, ea=0.0, te=te,
+                 tcs=[60.0e-20, 58.0e-20, 55.0e-20, 50.0e-20, 47.0e-20, 43.0e-20, 35.0e-20, 20.0e-20])]
+    bg_dens, bg_ttra, dtm = 1.0e21, 350.0, 1.0e-10
+    parts = [dict(v=[2.2e6, 1.5e6, -1.2e6], erot=0.0, evib=0.0, sid="e", pos=[0.2, 0.3, 0.1]),
+             dict(v=[3000.0, -1500.0, 800.0], erot=0.0, evib=0.0, sid="Ar+", pos=[0.6, 0.7, -0.2]),
+             dict(v=[-9.0e5, 4.0e5, 2.0e5], erot=0.0, evib=0.0, sid="e", pos=[0.4, 0.1, 0.3])]
+    parts_in = [dict(q, v=list(q["v"]), pos=list(q["pos"])) for q in parts]
+
+    def interval(q, mx, which):
+        """[lo, hi) of R_SELECT that picks reaction `which` for particle q and the partner drawn from `mx`"""
+        c2 = maxwell(Script(mx), 0.0, 0.0, 0.0, bg_ttra, bg_ttra, bg_ttra, ar["Ar"]["mass"])
+        vr2 = sum((c2[k] - q["v"][k]) ** 2 for k in range(3))
+        m1, m2 = ar[q["sid"]]["mass"], ar["Ar"]["mass"]
+        etr = 0.5 * (m1 * m2 / (m1 + m2)) * vr2
+        pn = 1 - math.exp(-dtm * bg_dens * float(F32(1e-12)))
+        pc, lo = 0.0, 0.0
+        for k, r in enumerate(reac):
+            if r["r1"] != q["sid"] or etr <= r["ea"]:
+                continue
+            lo = pc
+            pc = pc + (1.0 - math.exp(-bg_dens * interp_cs(etr, r["te"], r["tcs"]) * math.sqrt(vr2) * dtm)) / pn
+            if k == which:
+                return lo, pc
+        raise AssertionError("reaction not reachable")
+
+    mx1 = [0.13, 0.41, 0.77, 0.58, 0.36, 0.89]
+    mx2 = [0.62, 0.27, 0.08, 0.71, 0.93, 0.44]
+    lo1, hi1 = interval(parts[0], mx1, 2)
+    lo2, hi2 = interval(parts[1], mx2, 4)
+    assert 0 < lo1 < hi1 < 1 and 0 < lo2 < hi2 < 1, (lo1, hi1, lo2, hi2)
+    draws = ([0.01] + mx1 + [0.5 * (lo1 + hi1)] + [0.02, 0.9, 0.45, 0.6] + [0.31, 0.84] + [0.67, 0.22]
+             + [0.05] + mx2 + [0.5 * (lo2 + hi2)]
+             + [0.5])
+    s = Script(draws)
+    nc, nr = mcc_collisions_vahedi(ar, parts, reac, [("Ar", 1.0)], bg_dens, bg_ttra, dtm, s)
+    assert (nc, nr) == (2, 2) and s.k == len(draws) and [q["sid"] for q in parts] == ["e", "Ar", "e", "Ar+", "e", "Ar+"], \
+        (nc, nr, s.k, len(draws), [q["sid"] for q in parts])
+    pd = lambda q: dict(v=[hx(c) for c in q["v"]], erot=hx(q["erot"]), evib=hx(q["evib"]), sid=q["sid"], pos=q["pos"])
+    out["mcc_vahedi"] = dict(bg_dens=hx(bg_dens), bg_ttra=hx(bg_ttra), dt=hx(dtm), draws=[hx(v) for v in draws], ncoll=nc, nreac=nr,
+                             reactions=[dict(r, te=[hx(v) for v in r["te"]], tcs=[hx(v) for v in r["tcs"]], ea=hx(r["ea"])) for r in reac],
+                             inp=[pd(q) for q in parts_in], out=[pd(q) for q in parts])
     json.dump(out, open(os.path.join(HERE, "fortran_pins.json"), "w"), indent=1)
     print("wrote fortran_pins.json:", {k: (len(v) if isinstance(v, (list, dict)) else v) for k, v in out.items()})
 

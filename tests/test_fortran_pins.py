@@ -166,6 +166,22 @@ def test_cll_reflection_oracle_matches_fortran_reading(oracle):
         assert float(out[f.upper()][0]) == pytest.approx(fh(e[f]), rel=1e-13, abs=1e-300), f
 
 
+def test_diffuse_reflection_oracle_matches_fortran_reading(oracle):
+    """Maxwell wall (src/timecycle.f90:1445-1476) on scripted draws: MAXWELL with a redrawn R1 (src/tools.f90:130-187),
+    INTERNAL_ENERGY twice, FLX with one rejected pair (src/tools.f90:1150-1186); FACE_TANG1/2 of the pin mesh."""
+    t = PINS["diffuse_reflect"]
+    w = tet_workload([t], fh(t["dt"]), bc_kind=capi.DIFFUSE, wall=t["wall"])
+    wl.apply(oracle, w)
+    script(oracle, t["draws"])
+    oracle.advect(1)
+    assert script_used(oracle) == len(t["draws"])
+    out = oracle.download_particles()
+    e = t["out"]
+    assert out["IC"][0] == e["ic"]
+    for f in ("x", "y", "z", "vx", "vy", "vz", "erot", "evib"):
+        assert float(out[f.upper()][0]) == pytest.approx(fh(e[f]), rel=1e-14, abs=1e-300), f
+
+
 def collision_setup(orc, t, with_reactions):
     names = t["species"]
     sp = wl.load_species("air", names)
@@ -239,3 +255,262 @@ def test_tce_coefficients_match_fortran_reading():
         assert [r["c1"], r["c2"], r["c3"], r["ea"]] == pytest.approx([c1, c2, c3, ea], rel=1e-13)
         seen += 1
     assert seen == len(PINS["tce_coeffs"]) and seen >= 10
+
+
+# ------------------------------------------------------------------------------------------ radial weighting
+def radial_reading(p0, cell_fnum, cfg, draws):
+    """src/timecycle.f90:2100-2131 read in plain Python: the reverse sweep IP = NP..1 over the moved particles,
+    CELL_FROM_POSITION (src/grid_and_partition.f90:34-60, uniform grid), one draw per particle that changed to a cell
+    of different weight, REMOVE_PARTICLE_ARRAY = overwrite with the last element, clones appended at the end.
+    Returns the IDs in final array order and the number of draws consumed."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("fortran_pins_gen", os.path.join(GOLD, "fortran_pins.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    dx = (cfg.xmax - cfg.xmin) / cfg.nx
+    dy = (cfg.ymax - cfg.ymin) / cfg.ny
+    arr = []  # the particle array after the move: (id, old_ic, x, y)
+    for q in p0:
+        m = gen.move_particle_axi(dict(x=float(q["X"]), y=float(q["Y"]), z=float(q["Z"]), vx=float(q["VX"]), vy=float(q["VY"]),
+                                       vz=float(q["VZ"])), cfg.dt)
+        arr.append([int(q["ID"]), int(q["IC"]), m["x"], m["y"]])
+    it = iter(draws)
+    used = 0
+    ip = len(arr)
+    while ip >= 1:
+        pid, old_ic, x, y = arr[ip - 1]
+        ic = int((x - cfg.xmin) / dx) + cfg.nx * int((y - cfg.ymin) / dy) + 1
+        arr[ip - 1][1] = ic
+        if ic != old_ic:
+            ratio = cell_fnum[old_ic - 1] / cell_fnum[ic - 1]
+            if ratio < 1.0:
+                rfp = next(it); used += 1
+                if ratio < rfp:
+                    arr[ip - 1] = arr[-1]   # REMOVE_PARTICLE_ARRAY (src/particle.f90:139-179): the last one takes its place
+                    arr.pop()
+            elif ratio > 1.0:
+                rfp = next(it); used += 1
+                while (ratio - 1.0) > rfp:
+                    arr.append([pid, ic, x, y])
+                    ratio = ratio - 1.0
+        ip -= 1
+    return [a[0] for a in arr], [a[1] for a in arr], used
+
+
+def test_radial_weighting_oracle_matches_fortran_reading(oracle):
+    """BOOL_RADIAL_WEIGHTING, src/timecycle.f90:2110-2128, on scripted draws: same survivors, same clones, same array
+    order (the reverse sweep and the swap-with-last removal), same number of draws."""
+    rng = np.random.default_rng(12)
+    nx, ny, n = 3, 4, 400
+    w = wl.c1_argon_box(n, nx=nx, ny=ny, periodic=False)
+    w.cfg.axi = 1
+    w.cfg.ymin, w.cfg.ymax, w.cfg.zmin, w.cfg.zmax = 0.0, 1.0, 0.0, 1.0
+    w.cfg.xmin, w.cfg.xmax = 0.0, 1.0
+    w.cfg.bool_z_periodic = 0
+    w.cfg.collision_type = capi.NO_COLL
+    w.cfg.dt = 2.0e-4
+    w.cfg.track_id = 1
+    w.cfg.capacity = 8 * n
+    p = w.particles
+    p["X"] = rng.uniform(0.3, 0.7, n)           # (stay clear of the walls: the pin is about the weighting)
+    p["Y"] = rng.uniform(0.3, 0.7, n)
+    p["Z"] = 0.0
+    p["VX"] = rng.normal(0.0, 300.0, n)
+    p["VY"] = rng.normal(0.0, 300.0, n)
+    p["VZ"] = rng.normal(0.0, 300.0, n)
+    p["DTRIM"] = w.cfg.dt
+    p["ID"] = np.arange(1, n + 1)
+    dx, dy = 1.0 / nx, 1.0 / ny
+    p["IC"] = (p["X"] / dx).astype(int) + nx * (p["Y"] / dy).astype(int) + 1
+    row = np.array([0.5, 1.0, 3.7, 9.0])        # CELL_FNUM per cell row: ratios below 1, and above 2 (several clones)
+    cell_fnum = np.repeat(row, nx)
+    draws = rng.uniform(0.0, 1.0, 2 * n)
+    ids, ics, used = radial_reading(p, cell_fnum, w.cfg, draws)
+    wl.apply(oracle, w)
+    oracle.set_cell_fnum(cell_fnum)
+    script(oracle, draws)
+    oracle.advect(1)
+    out = oracle.download_particles()
+    assert used > 50 and len(ids) != n
+    assert script_used(oracle) == used
+    # a clone is a new particle (INIT_PARTICLE draws a fresh ID, src/particle.f90:75-76) with its parent's state: VX is
+    # untouched by the axisymmetric move and identifies the parent
+    parent_of = {float(v): int(i) for v, i in zip(p["VX"], p["ID"])}
+    parents = [parent_of[float(v)] for v in out["VX"]]
+    assert parents == ids
+    assert list(out["IC"]) == ics
+    assert np.array_equal(out["ID"][out["ID"] <= n], np.array([i for k, i in enumerate(ids) if out["ID"][k] <= n]))
+    assert max(np.bincount(parents)) >= 3       # some particle was cloned at least twice
+
+
+# ------------------------------------------------------------------------------------------ Boris push
+def boris_reading(v_old, charge, mass, e, b, dtime):
+    """src/timecycle.f90:2271-2291 UPDATE_VELOCITY_BORIS, element by element in Fortran's evaluation order
+    (left to right, no contraction); CROSS is src/tools.f90:1284-1292; QE from src/global.f90:35."""
+    QE = 1.602176634e-19
+    qc = charge * QE
+    cross = lambda a, c: [a[1] * c[2] - a[2] * c[1], a[2] * c[0] - a[0] * c[2], a[0] * c[1] - a[1] * c[0]]
+    v_minus = [v_old[k] + 0.5 * qc * e[k] / mass * dtime for k in range(3)]
+    t = [0.5 * qc * b[k] / mass * dtime for k in range(3)]
+    c = cross(v_minus, t)
+    v_prime = [v_minus[k] + c[k] for k in range(3)]
+    den = 1.0 + (t[0] * t[0] + t[1] * t[1] + t[2] * t[2])
+    s = [2.0 * t[k] / den for k in range(3)]
+    c = cross(v_prime, s)
+    v_plus = [v_minus[k] + c[k] for k in range(3)]
+    return [v_plus[k] + 0.5 * qc * e[k] / mass * dtime for k in range(3)]
+
+
+def check_boris(lib):
+    """One electron and one ion in the middle of a segment of a 1-D mesh, cell-constant E with three components
+    (APPLY_E_FIELD, unstructured branch, src/fields.f90:4194-4201), uniform external B, a step short enough that no face
+    is reached: V_NEW from the push, then X = X + V_NEW * DT (src/timecycle.f90:1229-1250, 2297-2310), bit for bit."""
+    w = wl.c4_ccp_1d(ncells=4, n_per_species=1)
+    w.cfg.collision_type = capi.NO_COLL
+    w.cfg.dt = 3.0e-11
+    bext = [0.013, -0.021, 0.034]
+    for i, v in enumerate(bext):
+        w.cfg.external_b[i] = v
+    p = w.particles
+    h = 0.0254 / 4
+    p["X"] = [1.5 * h, 2.5 * h]
+    p["Y"], p["Z"] = [0.41, 0.52], [0.63, 0.37]
+    p["VX"], p["VY"], p["VZ"] = [8.1e5, -3.3e2], [-4.7e5, 2.9e2], [2.2e5, 1.7e2]
+    p["S_ID"] = [w.species.id("e"), w.species.id("Ar+")]
+    p["IC"] = [2, 3]
+    p["DTRIM"] = w.cfg.dt
+    ef = np.zeros((3, 4), order="F")
+    ef[:, 1] = [1234.5, -987.6, 432.1]
+    ef[:, 2] = [-2222.2, 333.3, 4444.4]
+    w.efield = ef
+    wl.apply(lib, w)
+    lib.advect(1)
+    out = lib.download_particles()
+    assert len(out) == 2
+    for k in range(2):
+        s = int(p["S_ID"][k]) - 1
+        vn = boris_reading([float(p["VX"][k]), float(p["VY"][k]), float(p["VZ"][k])], float(w.species.charge[s]),
+                           float(w.species.mass[s]), [float(x) for x in ef[:, int(p["IC"][k]) - 1]], bext, w.cfg.dt)
+        assert [float(out["VX"][k]), float(out["VY"][k]), float(out["VZ"][k])] == vn, (k, vn)
+        assert float(out["X"][k]) == float(p["X"][k]) + vn[0] * w.cfg.dt
+        assert float(out["Y"][k]) == float(p["Y"][k]) + vn[1] * w.cfg.dt
+        assert float(out["Z"][k]) == float(p["Z"][k]) + vn[2] * w.cfg.dt
+        assert out["IC"][k] == p["IC"][k]
+
+
+def test_boris_push_oracle_matches_fortran_reading(oracle):
+    check_boris(oracle)
+
+
+@pytest.mark.gpu
+def test_boris_push_device_matches_fortran_reading(gpu):
+    check_boris(gpu)
+
+
+# ------------------------------------------------------------------------------------------ DEPOSIT_CHARGE
+def check_deposit_single_particle(lib):
+    """src/fields.f90:5440-5520 for ONE charged particle (no summation order involved), in plain Python:
+    triangle mesh (DIMS == 2): RHS(VP) = K*CHARGE*FNUM/(ZMAX-ZMIN) * (B1*X + B2*Y + B3) on the three nodes of its cell;
+    uniform rectilinear grid: COMPUTE_WEIGHTS (:5341-5431) and RHS(INDICES(k)) = -K*CHARGE*FNUM/CELL_VOL * WEIGHTS(k).
+    K = QE/(EPS0*EPS_SCALING**2), constants from src/global.f90:32-35."""
+    QE, EPS0 = 1.602176634e-19, 8.8541878128e-12
+    sp = wl.load_species("ar", ["Ar+", "e", "Ar"])
+    # --- triangles
+    w = wl.c3_tri_box(nx=4, ny=3, n=3, lo=(0.0, 0.0), hi=(0.1, 0.06), dt=1e-10, wall_bc=("specular",) * 4)
+    w.species = sp
+    w.cfg.pic_type = capi.PIC_EXPLICIT
+    w.cfg.fnum = 3.5e4
+    w.cfg.eps_scaling = 1.7
+    m = w.mesh
+    ic = 7
+    nodes = np.asarray(m.cell_nodes)[:, ic - 1]
+    xy = np.asarray(m.node_coords)[:2, nodes - 1]
+    x, y = (float(v) for v in xy.mean(axis=1) + np.array([1.3e-3, -0.7e-3]))
+    p = w.particles
+    p["X"], p["Y"], p["Z"] = [x, x, x], [y, y, y], 0.0
+    p["S_ID"] = [sp.id("Ar"), sp.id("e"), sp.id("Ar")]     # the neutrals are skipped (ABS(CHARGE) < 1e-6)
+    p["IC"] = ic
+    wl.apply(lib, w)
+    rhs = lib.deposit_charge(m.nn)
+    K = QE / (EPS0 * w.cfg.eps_scaling ** 2)
+    rho_q = K * float(sp.charge[sp.id("e") - 1]) * w.cfg.fnum / (w.cfg.zmax - w.cfg.zmin)
+    want = np.zeros(m.nn)
+    B = np.asarray(m.basis_coeffs)
+    for pp in range(3):
+        psip = float(B[0, pp, ic - 1]) * x + float(B[1, pp, ic - 1]) * y + float(B[2, pp, ic - 1])
+        want[nodes[pp] - 1] = 0.0 + rho_q * psip
+    assert np.array_equal(rhs, want) and np.count_nonzero(rhs) == 3
+    assert abs(rhs.sum() - rho_q) < 1e-12 * abs(rho_q)      # the P1 basis is a partition of unity
+    # --- uniform rectilinear grid, DIMS == 2
+    nx, ny = 5, 4
+    cfg = capi.make_config(dims=2, nx=nx, ny=ny, xmin=-0.2, xmax=0.8, ymin=0.1, ymax=0.5, zmin=0.0, zmax=0.3, dt=1e-10,
+                           fnum=7.7e3, pic_type=capi.PIC_EXPLICIT, bool_periodic=[1] * 4, bool_z_periodic=1)
+    q = wl.new_particles(1)
+    xp, yp = 0.3137, 0.2719
+    hx, hy = (cfg.xmax - cfg.xmin) / float(nx), (cfg.ymax - cfg.ymin) / float(ny)
+    ic = int((xp - cfg.xmin) / hx) + nx * int((yp - cfg.ymin) / hy) + 1
+    q["X"], q["Y"], q["Z"], q["S_ID"], q["IC"], q["DTRIM"] = xp, yp, 0.1, sp.id("Ar+"), ic, cfg.dt
+    w2 = wl.Workload("deposit-pin", cfg, sp, q)
+    wl.apply(lib, w2)
+    nn = (nx + 1) * (ny + 1)
+    rhs = lib.deposit_charge(nn)
+    i, j = (ic - 1) % nx, (ic - 1) // nx
+    fx = (xp - (i * hx + cfg.xmin)) / hx
+    fy = (yp - (j * hy + cfg.ymin)) / hy
+    cell_vol = (cfg.xmax - cfg.xmin) * (cfg.ymax - cfg.ymin) * (cfg.zmax - cfg.zmin) / (nx * ny)
+    rho_q = -(QE / (EPS0 * 1.0 ** 2)) * float(sp.charge[sp.id("Ar+") - 1]) * cfg.fnum / cell_vol
+    i1 = ic + j - 1                                         # INDICES are 0-based node numbers (RHS(0:NNODES-1))
+    want = np.zeros(nn)
+    want[i1] = rho_q * ((1. - fx) * (1. - fy))
+    want[i1 + 1] = rho_q * (fx * (1. - fy))
+    want[i1 + nx + 1] = rho_q * ((1. - fx) * fy)
+    want[i1 + nx + 2] = rho_q * (fx * fy)
+    assert np.array_equal(rhs, want)
+
+
+def test_deposit_single_particle_oracle_matches_fortran_reading(oracle):
+    check_deposit_single_particle(oracle)
+
+
+@pytest.mark.gpu
+def test_deposit_single_particle_device_matches_fortran_reading(gpu):
+    check_deposit_single_particle(gpu)
+
+
+# ------------------------------------------------------------------------------------------ MCC_COLLISIONS_VAHEDI
+def test_mcc_vahedi_oracle_matches_fortran_reading(oracle):
+    """src/collisions.f90:1606-1892 on scripted draws: a three-product LXCat ionisation (partner materialised, energy
+    redistribution with TOTDOF as the source counts it, two HS_SCATTERs, third product appended), a charge exchange, and
+    a particle that fails the null-collision test; INTERP_CS (src/tools.f90:1544-1593) on an 8-point table."""
+    t = PINS["mcc_vahedi"]
+    sp = wl.load_species("ar", ["Ar", "Ar+", "e"])
+    cfg = capi.make_config(dims=2, grid_type=capi.RECTILINEAR_UNIFORM, nx=1, ny=1, xmin=0.0, xmax=1.0, ymin=0.0, ymax=1.0,
+                           zmin=-0.5, zmax=0.5, dt=fh(t["dt"]), fnum=1.0, collision_type=capi.MCC_VAHEDI,
+                           mcc_bg_dens=fh(t["bg_dens"]), mcc_bg_ttra=fh(t["bg_ttra"]), bool_periodic=[1] * 4,
+                           bool_z_periodic=1, capacity=64)
+    p = wl.new_particles(len(t["inp"]))
+    for k, q in enumerate(t["inp"]):
+        p["X"][k], p["Y"][k], p["Z"][k] = q["pos"]
+        p["VX"][k], p["VY"][k], p["VZ"][k] = (fh(c) for c in q["v"])
+        p["EROT"][k], p["EVIB"][k] = fh(q["erot"]), fh(q["evib"])
+        p["S_ID"][k] = sp.id(q["sid"])
+    p["IC"] = 1
+    p["DTRIM"] = cfg.dt
+    reactions = [dict(type=capi.LXCAT, r1=sp.id(r["r1"]), r2=sp.id(r["r2"]), p1=sp.id(r["p1"]), p2=sp.id(r["p2"]),
+                      p3=sp.id(r["p3"]) if r["p3"] else -1, p4=-1, nprod=r["nprod"], is_cex=r["is_cex"], ea=fh(r["ea"]),
+                      table_energy=np.array([fh(v) for v in r["te"]]), table_cs=np.array([fh(v) for v in r["tcs"]]))
+                 for r in t["reactions"]]
+    w = wl.Workload("pin mcc", cfg, sp, p, reactions=reactions, mcc_background=([sp.id("Ar")], [1.0]))
+    wl.apply(oracle, w)
+    script(oracle, [fh(v) for v in t["draws"]])
+    nc, nr = oracle.mcc_vahedi(1)
+    assert (nc, nr) == (t["ncoll"], t["nreac"])
+    assert script_used(oracle) == len(t["draws"])
+    out = oracle.download_particles()
+    assert len(out) == len(t["out"])
+    for k, e in enumerate(t["out"]):
+        assert out["S_ID"][k] == sp.id(e["sid"]), (k, out["S_ID"][k], e["sid"])
+        got = [out["VX"][k], out["VY"][k], out["VZ"][k], out["EROT"][k], out["EVIB"][k]]
+        want = [fh(c) for c in e["v"]] + [fh(e["erot"]), fh(e["evib"])]
+        assert got == pytest.approx(want, rel=1e-13, abs=1e-300), (k, got, want)
+        assert [out["X"][k], out["Y"][k], out["Z"][k]] == e["pos"] and out["IC"][k] == 1
