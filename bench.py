@@ -348,6 +348,7 @@ def main():
     ap.add_argument("--particles", type=int, default=125_000_000, help="particles per GPU")
     ap.add_argument("--cubes", type=int, nargs=3, default=[32, 128, 128], help="cubes per GPU strip (6 tets each)")
     ap.add_argument("--workload", default="c5", choices=["c5"] + sorted(ALT), help="c5 (default, the metric's config) or another BASELINE.json config")
+    ap.add_argument("--deterministic", action="store_true", help="pgpu_set_deterministic(1): stable sort (reproducible runs); off by default")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="timed e2e steps (0 = same as --steps)")
@@ -388,6 +389,8 @@ def main():
     #  size, and a store that outgrows its capacity is re-allocated in the middle of a timed step)
     w.cfg.capacity = int(n_local * (1.02 if world == 1 else 1.25)) + 1024
     wl.apply(gpu, w)
+    if args.deterministic:
+        gpu.set_deterministic(True)
     if world > 1:
         uid = [gpu.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
@@ -581,7 +584,8 @@ def main():
                        "particles_per_gpu": n_local, "cells_per_gpu": int(w.mesh.nc // max(world, 1)), "mesh_cells": int(w.mesh.nc),
                        "ppc": n_local / (w.mesh.nc / max(world, 1)), "partition": f"stripsx x{world}",
                        "l2_policy": "inputs (8 GB of pos+vel records per GPU, streamed every step) are far larger than the 126 MB L2",
-                       "rng": "Philox4x32-10 per particle/candidate", "ids": "regenerated on download (track_id=0)"},
+                       "rng": "Philox4x32-10 per particle/candidate", "ids": "regenerated on download (track_id=0)",
+                       "sort": "stable radix sort (pgpu_set_deterministic)" if args.deterministic else "atomic arrival order (default)"},
             "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu, "gpu_launches": int(launches),
             "per_rank": [{"rank": r, "particles": int(v[0]), "move": v[1], "sort": v[2], "collide": v[3], "exchange": v[4],
                           "step": v[5]} for r, v in enumerate(per_rank)],
