@@ -60,7 +60,7 @@
 #define PG_CELL_TRIES 2 /* acceptance tests a lane runs before the warp re-converges for the deflections */
 #endif
 #ifndef PG_ADVECT_MINBLOCKS
-#define PG_ADVECT_MINBLOCKS 7 /* 72 registers; swept 6/7/8/10 at full size (r02b): 9.00/8.70/9.39/13.4 ms */
+#define PG_ADVECT_MINBLOCKS 7 /* 72 registers; swept 6/7/8 at full size: r02b 9.00/8.70/9.39 ms, r02v (packed brackets) 7.76/7.28/7.79 ms */
 #endif
 #define PG_COUNT_SMEM_CELLS 4096 /* grids this coarse count their cells per block in shared memory (pgpu_advect.cu) */
 #ifndef PG_ADVECT_PREFETCH
