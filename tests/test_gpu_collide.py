@@ -260,3 +260,33 @@ def test_deposit_charge_within_1e12(gpu, oracle, kind):
     got = gpu.deposit_charge(nn)
     assert np.abs(ref).max() > 0
     assert np.all(np.abs(got - ref) <= 1e-12 * ab + 1e-300), np.max(np.abs(got - ref) / (ab + 1e-300))
+
+
+def test_borgnakke_larsen_equipartition_on_device(gpu):
+    """N2/O2 heat bath started with cold internal modes: T_rot -> T_tr, total energy conserved (the oracle's version of this
+    test runs on the reference's MT stream: tests/test_oracle_physics.py)."""
+    w = wl.c2_air_box(40_000, nx=4, ny=4, T=2000.0, with_reactions=False, species=("O2", "N2"), frac=(0.5, 0.5), dt=4e-7)
+    w.particles["EROT"] = 0.0
+    w.particles["EVIB"] = 0.0
+    wl.apply(gpu, w)
+    m = w.species.mass
+    etot0 = util.kinetic_energy(w.particles, m)
+    gpu.run_steps(1, 150)
+    q = gpu.download_particles()
+    etot1 = util.kinetic_energy(q, m) + q["EROT"].sum() + q["EVIB"].sum()
+    assert etot1 == pytest.approx(etot0, rel=1e-10)
+    ttr = 2.0 / 3.0 * util.kinetic_energy(q, m) / len(q) / KB
+    trot = q["EROT"].mean() / KB
+    assert abs(trot - ttr) < 0.04 * ttr
+
+
+@pytest.mark.parametrize("T", [8000.0, 12000.0])
+def test_tce_recovers_the_arrhenius_rate_on_device(gpu, T):
+    """Dissociations of N2 + O2 -> N2 + O + O in an equilibrium gas against k(T) = A T^n exp(-Ea/kT) (data/air.tce)."""
+    from test_oracle_physics import arrhenius_case
+    w, per_step = arrhenius_case(T)
+    wl.apply(gpu, w)
+    steps = 6
+    _, nreac = gpu.run_steps(1, steps)
+    ratio = nreac / (per_step * steps)
+    assert 0.85 < ratio < 1.0 + 4.0 / np.sqrt(per_step * steps) + 0.03, (T, nreac, per_step * steps, ratio)

@@ -408,3 +408,30 @@ def test_mcc_collisions_air_reactions_conserve_mass(oracle):
     # mass: originals + one O2/N2 partner per collision, reshuffled by the reactions
     assert np.all(q["EROT"] >= 0) and np.all(q["EVIB"] >= 0)
     assert np.isfinite(q["VX"]).all()
+
+
+def arrhenius_case(T, n=400_000):
+    """O2/N2 50/50 at equilibrium (translation, rotation, vibration at T), ONE reaction of data/air.tce switched on:
+    N2 + O2 -> N2 + O + O.  Returns (workload, expected simulated reactions per step from k(T) = A T^n exp(-Ea/kT))."""
+    w = wl.c2_air_box(n, nx=4, ny=4, T=T, species=("O2", "N2", "O", "N", "NO"), frac=(0.5, 0.5, 0.0, 0.0, 0.0), dt=2e-7)
+    sp = w.species
+    r = [x for x in w.reactions if x["r1"] == sp.id("N2") and x["r2"] == sp.id("O2")]
+    assert len(r) == 1
+    w.reactions = r
+    k = r[0]["A"] * T ** r[0]["n"] * np.exp(-r[0]["ea"] / (KB * T))
+    n_o2 = n_n2 = 0.5e21                                    # c2_air_box: nrho = 1e21 in a unit volume
+    return w, n_o2 * n_n2 * k * 1.0 * w.cfg.dt / w.cfg.fnum
+
+
+@pytest.mark.parametrize("T", [8000.0, 12000.0])
+def test_tce_recovers_the_arrhenius_rate(oracle, T):
+    """The TCE reaction probability (src/collisions.f90:331-378, coefficients src/initialization.f90:2681-2724) is built so
+    that an equilibrium gas reacts at the Arrhenius rate it was fitted to: count the dissociations of a few steps on the
+    reference's MT19937-64 stream.  (The gas cools and O2 is depleted by about a percent meanwhile: the recovered rate
+    sits a few percent below 1.)"""
+    w, per_step = arrhenius_case(T)
+    wl.apply(oracle, w)
+    steps = 6
+    _, nreac = oracle.run_steps(1, steps)
+    ratio = nreac / (per_step * steps)
+    assert 0.85 < ratio < 1.0 + 4.0 / np.sqrt(per_step * steps) + 0.03, (T, nreac, per_step * steps, ratio)
