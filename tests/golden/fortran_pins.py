@@ -18,6 +18,8 @@ Covered reference lines:
                 :1433-1443 (specular), :1648-1657; face geometry src/grid_and_partition.f90:1932-1957
   axi_move      src/timecycle.f90:2297-2332 (MOVE_PARTICLE, axisymmetric branch)
   cll_reflect   src/timecycle.f90:1485-1550 (CLL), src/tools.f90:245-285 (INTERNAL_ENERGY)
+  initial_seed  src/initialization.f90:2017-2233 (INITIAL_SEED, unstructured 3-D), src/tools.f90:1304-1311 (RANDINT)
+  boundaries_emit  src/timecycle.f90:368-547 (BOUNDARIES_EMIT, DIMS == 3), src/tools.f90:130-187, 245-285, 1150-1186
   mcc_vahedi    src/collisions.f90:1606-1892 (MCC_COLLISIONS_VAHEDI), src/tools.f90:1544-1593 (INTERP_CS), :130-187 (MAXWELL)
   diffuse_reflect  src/timecycle.f90:1445-1476 (DIFFUSE), src/tools.f90:130-187 (MAXWELL), :1150-1186 (FLX), :245-285
   vss_pair_bl   src/collisions.f90:202-253 (majorant), :259-325 (selection, acceptance), :454-546 (Borgnakke-Larsen + VSS
@@ -314,6 +316,82 @@ def hs_scatter(rf, ecoll, m1, m2, c1, c2):
     grel = [g * sinphi * math.cos(theta), g * sinphi * math.sin(theta), g * cosphi]
     w = [m1 / (m1 + m2) * c1[i] + m2 / (m1 + m2) * c2[i] for i in range(3)]
     return ([w[i] + m2 / (m1 + m2) * grel[i] for i in range(3)], [w[i] - m1 / (m1 + m2) * grel[i] for i in range(3)])
+
+
+def boundaries_emit_3d(mesh, species, mix, task, dt, rf):
+    """src/timecycle.f90:368-547, DIMS == 3, no colocated electrons.  mix: [(name, molfrac)], task: dict ic, iface, nfs[],
+    ux, uy, uz, u_norm, ttra, trot, tvib.  Returns the particles in creation order."""
+    ic, iface = task["ic"], task["iface"]
+    fn = mesh["normal"][ic - 1][iface - 1]
+    t1 = mesh["tang1"][ic - 1][iface - 1]
+    t2 = mesh["tang2"][ic - 1][iface - 1]
+    v1, v2, v3 = (mesh["nodes"][mesh["cells"][ic - 1][IND[iface - 1][k] - 1] - 1] for k in range(3))   # FACE_NODES
+    made = []
+    for k, (name, _) in enumerate(mix):
+        m = species[name]["mass"]
+        nfs = math.floor(task["nfs"][k])
+        if task["nfs"][k] - float(nfs) >= rf():
+            nfs = nfs + 1
+        beta = 0.0 if task["ttra"] == 0 else 1.0 / math.sqrt(2.0 * KB / m * task["ttra"])
+        for _ip in range(nfs):
+            _, v_tang1, v_tang2 = maxwell(rf, 0.0, 0.0, 0.0, task["ttra"], task["ttra"], task["ttra"], m)
+            erot = internal_energy(rf, species[name]["rotdof"], task["trot"])
+            evib = internal_energy(rf, species[name]["vibdof"], task["tvib"])
+            v_norm = 0.0 if task["ttra"] == 0 else flx(rf, task["u_norm"] * beta, task["ttra"], m)
+            vx = task["ux"] - v_norm * fn[0] - v_tang1 * t1[0] - v_tang2 * t2[0]
+            vy = task["uy"] - v_norm * fn[1] - v_tang1 * t1[1] - v_tang2 * t2[1]
+            vz = task["uz"] - v_norm * fn[2] - v_tang1 * t1[2] - v_tang2 * t2[2]
+            dtfrac = rf() * dt
+            sdraw = rf()
+            tdraw = rf()
+            if sdraw > 1 - tdraw:
+                q, pp = 1 - tdraw, 1 - sdraw
+            else:
+                q, pp = tdraw, sdraw
+            x = v1[0] + (v2[0] - v1[0]) * pp + (v3[0] - v1[0]) * q
+            y = v1[1] + (v2[1] - v1[1]) * pp + (v3[1] - v1[1]) * q
+            z = v1[2] + (v2[2] - v1[2]) * pp + (v3[2] - v1[2]) * q
+            made.append(dict(x=x, y=y, z=z, vx=vx, vy=vy, vz=vz, erot=erot, evib=evib, sid=name, ic=ic, dtrim=dtfrac))
+    return made
+
+
+def randint(rf, x):
+    """src/tools.f90:1304-1311."""
+    r = int(x)
+    if x - r > rf():
+        r = r + 1
+    return r
+
+
+def initial_seed_3d(mesh, species, mixtures, spwt, tasks, fnum, rf):
+    """src/initialization.f90:2017-2233, GRID_TYPE == UNSTRUCTURED, DIMS == 3, one rank, no solid cells, no colocated
+    electrons.  mixtures: list of [(name, molfrac)], tasks: dicts mix_id, nrho, ux, uy, uz, ttrax, ttray, ttraz, trot, tvib."""
+    made = []
+    for task in tasks:
+        for name, molfrac in mixtures[task["mix_id"]]:
+            for ic in range(1, len(mesh["cells"]) + 1):
+                vol = mesh["vol"][ic - 1]
+                np_init = randint(rf, task["nrho"] / (fnum * spwt[name]) * vol * molfrac)
+                if np_init == 0:
+                    continue
+                v1, v2, v3, v4 = (mesh["nodes"][mesh["cells"][ic - 1][k] - 1] for k in range(4))
+                for _ip in range(np_init):
+                    sd, td, ud = rf(), rf(), rf()
+                    if sd + td > 1:
+                        sd, td = 1 - sd, 1 - td
+                    if sd + td + ud <= 1:
+                        pp, q, r = sd, td, ud
+                    elif td + ud > 1:
+                        pp, q, r = sd, 1 - ud, 1 - sd - td
+                    else:
+                        pp, q, r = 1 - td - ud, td, sd + td + ud - 1
+                    xyz = [v1[k] + (v2[k] - v1[k]) * pp + (v3[k] - v1[k]) * q + (v4[k] - v1[k]) * r for k in range(3)]
+                    m = species[name]["mass"]
+                    vx, vy, vz = maxwell(rf, task["ux"], task["uy"], task["uz"], task["ttrax"], task["ttray"], task["ttraz"], m)
+                    erot = internal_energy(rf, species[name]["rotdof"], task["trot"])
+                    evib = internal_energy(rf, species[name]["vibdof"], task["tvib"])
+                    made.append(dict(x=xyz[0], y=xyz[1], z=xyz[2], vx=vx, vy=vy, vz=vz, erot=erot, evib=evib, sid=name, ic=ic))
+    return made
 
 
 def interp_cs(e, te, tcs):
@@ -725,6 +803,34 @@ def main():
                             inp=[dict(v=[hx(c) for c in q["v"]], erot=hx(q["erot"]), evib=hx(q["evib"]), sid=q["sid"], pos=q["pos"]) for q in hot_in],
                             out=[dict(v=[hx(c) for c in q["v"]], erot=hx(q["erot"]), evib=hx(q["evib"]), sid=q["sid"]) for q in hot],
                             created=[dict(v=[hx(c) for c in q["v"]], erot=hx(q["erot"]), evib=hx(q["evib"]), sid=q["sid"], pos=q["pos"]) for q in created])
+    # ---- boundaries_emit: one task on the boundary face (cell 1, face 1) of the pin mesh, N2/O2 mixture, fractional NFS
+    import random
+    rr = random.Random(20261017)
+    draws = [rr.random() for _ in range(120)]
+    draws[0], draws[2] = 0.3, 1.0e-14       # NFS(N2) = 2.4 -> 3 particles; the first R1 of MAXWELL is redrawn
+    task = dict(ic=1, iface=1, nfs=[2.4, 0.7], ux=12.0, uy=-7.0, uz=45.0, u_norm=0.35, ttra=900.0, trot=700.0, tvib=500.0)
+    mixe = [("N2", 0.79), ("O2", 0.21)]
+    s = Script(draws)
+    made = boundaries_emit_3d(mesh, air, mixe, task, 2.0e-6, s)
+    assert len(made) >= 3 and s.k < len(draws)
+    out["boundaries_emit"] = dict(task=task, mix=mixe, dt=hx(2.0e-6), draws=[hx(v) for v in draws[:s.k]], used=s.k,
+                                  out=[dict(pdict(q), dtrim=hx(q["dtrim"])) for q in made])
+
+    # ---- initial_seed: two tasks on the pin mesh (N2/O2 mixture with anisotropic temperatures, a zero TTRAY; pure O with
+    # SPWT = 2), a handful of particles per cell
+    rr = random.Random(777)
+    draws = [rr.random() for _ in range(600)]
+    mixs = [[("N2", 0.79), ("O2", 0.21)], [("O", 1.0)]]
+    spwt = {"N2": 1.0, "O2": 1.0, "O": 2.0, "N": 1.0, "NO": 1.0}
+    tasks = [dict(mix_id=0, nrho=9.0e3, ux=120.0, uy=-30.0, uz=10.0, ttrax=300.0, ttray=0.0, ttraz=600.0, trot=350.0, tvib=0.0),
+             dict(mix_id=1, nrho=6.0e3, ux=0.0, uy=0.0, uz=0.0, ttrax=900.0, ttray=900.0, ttraz=900.0, trot=900.0, tvib=1200.0)]
+    fnum_seed = 250.0
+    s = Script(draws)
+    made = initial_seed_3d(mesh, air, mixs, spwt, tasks, fnum_seed, s)
+    assert 10 <= len(made) <= 60 and s.k < len(draws), (len(made), s.k)
+    out["initial_seed"] = dict(tasks=tasks, mixtures=mixs, spwt=spwt, fnum=hx(fnum_seed), draws=[hx(v) for v in draws[:s.k]], used=s.k,
+                               out=[pdict(q) for q in made])
+
     # ---- mcc_vahedi: e + Ar -> e + Ar+ + e (LXCat ionisation, three products), Ar+ + Ar charge exchange, one particle that
     # fails the null-collision test.  Tables: a few points, so that INTERP_CS's bisection takes both branches.
     ar = read_species("ar")

@@ -514,3 +514,54 @@ def test_mcc_vahedi_oracle_matches_fortran_reading(oracle):
         want = [fh(c) for c in e["v"]] + [fh(e["erot"]), fh(e["evib"])]
         assert got == pytest.approx(want, rel=1e-13, abs=1e-300), (k, got, want)
         assert [out["X"][k], out["Y"][k], out["Z"][k]] == e["pos"] and out["IC"][k] == 1
+
+
+# ------------------------------------------------------------------------------------------ BOUNDARIES_EMIT
+def test_boundaries_emit_oracle_matches_fortran_reading(oracle):
+    """src/timecycle.f90:368-547 (DIMS == 3) on scripted draws: fractional NFS per mixture component, MAXWELL tangentials
+    (first component discarded), INTERNAL_ENERGY at TROT / TVIB, FLX with the drift ratio U_NORM*BETA, DTFRAC, the
+    folded (S, T) point on the face; particles in creation order."""
+    t = PINS["boundaries_emit"]
+    w = tet_workload([], fh(t["dt"]))
+    w.cfg.capacity = 64
+    wl.apply(oracle, w)
+    sp = w.species
+    oracle.set_mixtures([[(sp.id(name), frac) for name, frac in t["mix"]]])
+    oracle.set_species_weights([1.0] * len(sp.mass))
+    oracle.set_emit_tasks([dict(t["task"], mix_id=0, iv1=1, iv2=1)])
+    script(oracle, [fh(v) for v in t["draws"]])
+    oracle.boundaries_emit(1)
+    assert script_used(oracle) == t["used"]
+    out = oracle.download_particles()
+    assert len(out) == len(t["out"]) >= 3
+    for k, e in enumerate(t["out"]):
+        assert out["S_ID"][k] == sp.id(e["sid"]) and out["IC"][k] == e["ic"]
+        for f in ("x", "y", "z", "vx", "vy", "vz", "erot", "evib", "dtrim"):
+            assert float(out[f.upper()][k]) == pytest.approx(fh(e[f]), rel=1e-13, abs=1e-300), (k, f)
+
+
+# ------------------------------------------------------------------------------------------ INITIAL_SEED
+def test_initial_seed_oracle_matches_fortran_reading(oracle):
+    """src/initialization.f90:2017-2233 (unstructured, DIMS == 3) on scripted draws: RANDINT per (task, component, cell),
+    the folded (S, T, U) point in the tetrahedron, MAXWELL with a drift and a zero temperature component (no draw for it),
+    INTERNAL_ENERGY, SPWT; particles in creation order."""
+    t = PINS["initial_seed"]
+    w = tet_workload([], 1.0e-6)
+    w.species = wl.load_species("air", ["N2", "O2", "O"])
+    w.cfg.fnum = fh(t["fnum"])
+    w.cfg.capacity = 256
+    wl.apply(oracle, w)
+    sp = w.species
+    oracle.set_mixtures([[(sp.id(name), frac) for name, frac in m] for m in t["mixtures"]])
+    oracle.set_species_weights([t["spwt"][n] for n in ("N2", "O2", "O")])
+    oracle.set_initial_particles_tasks([dict(q, rate=q["nrho"]) for q in t["tasks"]])
+    script(oracle, [fh(v) for v in t["draws"]])
+    oracle.initial_seed()
+    assert script_used(oracle) == t["used"]
+    out = oracle.download_particles()
+    assert len(out) == len(t["out"])
+    for k, e in enumerate(t["out"]):
+        assert out["S_ID"][k] == sp.id(e["sid"]) and out["IC"][k] == e["ic"], k
+        for f in ("x", "y", "z", "vx", "vy", "vz", "erot", "evib"):
+            assert float(out[f.upper()][k]) == pytest.approx(fh(e[f]), rel=1e-13, abs=1e-300), (k, f)
+        assert float(out["DTRIM"][k]) == 1.0e-6
