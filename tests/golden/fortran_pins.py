@@ -18,6 +18,7 @@ Covered reference lines:
                 :1433-1443 (specular), :1648-1657; face geometry src/grid_and_partition.f90:1932-1957
   axi_move      src/timecycle.f90:2297-2332 (MOVE_PARTICLE, axisymmetric branch)
   cll_reflect   src/timecycle.f90:1485-1550 (CLL), src/tools.f90:245-285 (INTERNAL_ENERGY)
+  volume_inject  src/timecycle.f90:553-737 (VOLUME_INJECT, structured branch, plane and axisymmetric)
   initial_seed  src/initialization.f90:2017-2233 (INITIAL_SEED, unstructured 3-D), src/tools.f90:1304-1311 (RANDINT)
   boundaries_emit  src/timecycle.f90:368-547 (BOUNDARIES_EMIT, DIMS == 3), src/tools.f90:130-187, 245-285, 1150-1186
   mcc_vahedi    src/collisions.f90:1606-1892 (MCC_COLLISIONS_VAHEDI), src/tools.f90:1544-1593 (INTERP_CS), :130-187 (MAXWELL)
@@ -391,6 +392,36 @@ def initial_seed_3d(mesh, species, mixtures, spwt, tasks, fnum, rf):
                     erot = internal_energy(rf, species[name]["rotdof"], task["trot"])
                     evib = internal_energy(rf, species[name]["vibdof"], task["tvib"])
                     made.append(dict(x=xyz[0], y=xyz[1], z=xyz[2], vx=vx, vy=vy, vz=vz, erot=erot, evib=evib, sid=name, ic=ic))
+    return made
+
+
+def volume_inject_structured(species, mixtures, spwt, tasks, g, rf):
+    """src/timecycle.f90:553-737, structured branch (uniform grid; AXI without radial weighting draws Y from the
+    area-weighted law and sets Z = 0), one rank.  g: dict xmin, xmax, ymin, ymax, zmin, zmax, nx, ny, axi, dt, fnum.
+    CELL_FROM_POSITION: src/grid_and_partition.f90:34-60."""
+    made = []
+    for task in tasks:
+        for name, molfrac in mixtures[task["mix_id"]]:
+            if g["axi"]:
+                domain_volume = 0.5 * (g["xmax"] - g["xmin"]) * (g["ymax"] ** 2 - g["ymin"] ** 2) * (g["zmax"] - g["zmin"])
+            else:
+                domain_volume = (g["xmax"] - g["xmin"]) * (g["ymax"] - g["ymin"]) * (g["zmax"] - g["zmin"])
+            np_init = randint(rf, g["dt"] * task["nrhodot"] / (g["fnum"] * spwt[name]) * domain_volume * molfrac / 1)
+            for _ip in range(np_init):
+                xp = g["xmin"] + (g["xmax"] - g["xmin"]) * rf()
+                if g["axi"]:
+                    yp = math.sqrt(g["ymin"] * g["ymin"] + rf() * (g["ymax"] * g["ymax"] - g["ymin"] * g["ymin"]))
+                    zp = 0.0
+                else:
+                    yp = g["ymin"] + (g["ymax"] - g["ymin"]) * rf()
+                    zp = g["zmin"] + (g["zmax"] - g["zmin"]) * rf()
+                m = species[name]["mass"]
+                vx, vy, vz = maxwell(rf, task["ux"], task["uy"], task["uz"], task["ttrax"], task["ttray"], task["ttraz"], m)
+                erot = internal_energy(rf, species[name]["rotdof"], task["trot"])
+                evib = internal_energy(rf, species[name]["vibdof"], task["tvib"])
+                dx, dy = (g["xmax"] - g["xmin"]) / g["nx"], (g["ymax"] - g["ymin"]) / g["ny"]
+                cid = int((xp - g["xmin"]) / dx) + g["nx"] * int((yp - g["ymin"]) / dy) + 1
+                made.append(dict(x=xp, y=yp, z=zp, vx=vx, vy=vy, vz=vz, erot=erot, evib=evib, sid=name, ic=cid))
     return made
 
 
@@ -830,6 +861,19 @@ def main():
     assert 10 <= len(made) <= 60 and s.k < len(draws), (len(made), s.k)
     out["initial_seed"] = dict(tasks=tasks, mixtures=mixs, spwt=spwt, fnum=hx(fnum_seed), draws=[hx(v) for v in draws[:s.k]], used=s.k,
                                out=[pdict(q) for q in made])
+
+    # ---- volume_inject: uniform grid, plane and axisymmetric
+    vi = []
+    for axi in (0, 1):
+        rr = random.Random(4242 + axi)
+        draws = [rr.random() for _ in range(400)]
+        g = dict(xmin=-0.2, xmax=0.8, ymin=0.1, ymax=0.5, zmin=0.0, zmax=0.3, nx=5, ny=4, axi=axi, dt=2.0e-6, fnum=40.0)
+        tasks = [dict(mix_id=0, nrhodot=1.0e10 if axi else 2.5e9, ux=0.0, uy=50.0, uz=0.0, ttrax=500.0, ttray=500.0, ttraz=500.0, trot=500.0, tvib=500.0)]
+        s = Script(draws)
+        made = volume_inject_structured(air, mixs, spwt, tasks, g, s)
+        assert 8 <= len(made) <= 40 and s.k < len(draws), (len(made), s.k)
+        vi.append(dict(grid=g, tasks=tasks, mixtures=mixs, spwt=spwt, draws=[hx(v) for v in draws[:s.k]], used=s.k, out=[pdict(q) for q in made]))
+    out["volume_inject"] = vi
 
     # ---- mcc_vahedi: e + Ar -> e + Ar+ + e (LXCat ionisation, three products), Ar+ + Ar charge exchange, one particle that
     # fails the null-collision test.  Tables: a few points, so that INTERP_CS's bisection takes both branches.

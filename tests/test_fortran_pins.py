@@ -565,3 +565,30 @@ def test_initial_seed_oracle_matches_fortran_reading(oracle):
         for f in ("x", "y", "z", "vx", "vy", "vz", "erot", "evib"):
             assert float(out[f.upper()][k]) == pytest.approx(fh(e[f]), rel=1e-13, abs=1e-300), (k, f)
         assert float(out["DTRIM"][k]) == 1.0e-6
+
+
+# ------------------------------------------------------------------------------------------ VOLUME_INJECT
+@pytest.mark.parametrize("case", [0, 1])
+def test_volume_inject_structured_oracle_matches_fortran_reading(oracle, case):
+    """src/timecycle.f90:553-737, structured branch on scripted draws; case 1 is axisymmetric (Y from the area-weighted
+    law, Z = 0, DOMAIN_VOLUME with the 0.5*(YMAX**2-YMIN**2) factor)."""
+    t = PINS["volume_inject"][case]
+    g = t["grid"]
+    sp = wl.load_species("air", ["N2", "O2", "O"])
+    cfg = capi.make_config(dims=2, grid_type=capi.RECTILINEAR_UNIFORM, nx=g["nx"], ny=g["ny"], xmin=g["xmin"], xmax=g["xmax"],
+                           ymin=g["ymin"], ymax=g["ymax"], zmin=g["zmin"], zmax=g["zmax"], dt=g["dt"], fnum=g["fnum"], axi=g["axi"],
+                           collision_type=capi.NO_COLL, capacity=256)
+    w = wl.Workload("pin vinj", cfg, sp, wl.new_particles(0))
+    wl.apply(oracle, w)
+    oracle.set_mixtures([[(sp.id(name), frac) for name, frac in m] for m in t["mixtures"]])
+    oracle.set_species_weights([t["spwt"][n] for n in ("N2", "O2", "O")])
+    oracle.set_volume_inject_tasks([dict(q, rate=q["nrhodot"]) for q in t["tasks"]])
+    script(oracle, [fh(v) for v in t["draws"]])
+    oracle.volume_inject(1)
+    assert script_used(oracle) == t["used"]
+    out = oracle.download_particles()
+    assert len(out) == len(t["out"])
+    for k, e in enumerate(t["out"]):
+        assert out["S_ID"][k] == sp.id(e["sid"]) and out["IC"][k] == e["ic"], k
+        for f in ("x", "y", "z", "vx", "vy", "vz", "erot", "evib"):
+            assert float(out[f.upper()][k]) == pytest.approx(fh(e[f]), rel=1e-13, abs=1e-300), (k, f)
