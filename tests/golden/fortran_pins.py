@@ -22,6 +22,7 @@ Covered reference lines:
   initial_seed  src/initialization.f90:2017-2233 (INITIAL_SEED, unstructured 3-D), src/tools.f90:1304-1311 (RANDINT)
   boundaries_emit  src/timecycle.f90:368-547 (BOUNDARIES_EMIT, DIMS == 3), src/tools.f90:130-187, 245-285, 1150-1186
   mcc_vahedi    src/collisions.f90:1606-1892 (MCC_COLLISIONS_VAHEDI), src/tools.f90:1544-1593 (INTERP_CS), :130-187 (MAXWELL)
+  wall_react    src/fields.f90:4302-4341 (WALL_REACT), src/timecycle.f90:1433-1443
   diffuse_reflect  src/timecycle.f90:1445-1476 (DIFFUSE), src/tools.f90:130-187 (MAXWELL), :1150-1186 (FLX), :245-285
   vss_pair_bl   src/collisions.f90:202-253 (majorant), :259-325 (selection, acceptance), :454-546 (Borgnakke-Larsen + VSS
                 deflection), :892-937 (FUNCTION_I, COLL_INTERNAL_ENERGY)
@@ -185,7 +186,28 @@ def flx(rf, sn, tinf, m):
             return y / beta
 
 
-def advect_tet(mesh, bc, species, p, dt, rf):
+def wall_react(species, wall_reactions, q, rf):
+    """src/fields.f90:4302-4341 (no EXIT after a reaction: JS keeps the species the particle arrived with).
+    q: dict sid, v (list); returns True when the particle is removed."""
+    js = q["sid"]
+    prob_scale = 1.0
+    remove = False
+    for r in wall_reactions:
+        if r["r"] == js:
+            if rf() <= r["prob"] / prob_scale:
+                if r["nprod"] == 0:
+                    remove = True
+                else:
+                    jp = r["p1"]
+                    q["sid"] = jp
+                    vel_scale = species[js]["mass"] / species[jp]["mass"]
+                    q["v"] = [c * vel_scale for c in q["v"]]
+            else:
+                prob_scale = prob_scale - r["prob"]
+    return remove
+
+
+def advect_tet(mesh, bc, species, p, dt, rf, wall_reactions=None):
     """One particle through ADVECT on the 3-D unstructured grid (no PIC, no axisymmetry, no tallies).
     src/timecycle.f90:1166-1170, 1257-1305, 1309-1360, 1433-1443 (specular), 1485-1550 (CLL), 1644-1657.
     p = dict(x, y, z, vx, vy, vz, erot, evib, ic (1-based), sid (name)); bc[pg] = ('specular',) or ('cll', Tw, acc_n, acc_t).
@@ -214,6 +236,13 @@ def advect_tet(mesh, bc, species, p, dt, rf):
                 pg = mesh["faces_pg"][ic - 1][boundcoll - 1]
                 fn = [-c for c in mesh["normal"][ic - 1][boundcoll - 1]]        # FACE_NORMAL = -U3D_GRID%FACE_NORMAL, :1357
                 kind = bc[pg]
+                if kind[-1] == "react":                      # GRID_BC(FACE_PG)%REACT, :1434-1436 / :1446-1448
+                    qq = dict(sid=p["sid"], v=[vx, vy, vz])
+                    if wall_react(species, wall_reactions, qq, rf):
+                        p["removed"] = True
+                        dtrim = 0.0                         # part_adv(IP)%DTRIM = 0.
+                    p["sid"] = qq["sid"]
+                    vx, vy, vz = qq["v"]
                 if kind[0] == "specular":
                     vdotn = vx * fn[0] + vy * fn[1] + vz * fn[2]
                     vx = vx - 2.0 * vdotn * fn[0]
@@ -773,6 +802,23 @@ def main():
     assert s.k == len(draws) and trace[0] == [1, 1]
     out["cll_reflect"] = dict(dt=hx(1.0e-3), wall=dict(temp=500.0, acc_n=0.8, acc_t=0.6), draws=draws, inp=pdict(p), out=pdict(q),
                               trace=trace)
+
+    # ---- wall_react: O2 on a reacting specular wall with two reactions for O2 (O2 -> N2 with the mass-ratio velocity scaling,
+    # O2 -> none); three draw scripts: first fires only / second fires after the first failed (renormalised probability) /
+    # both fire (no EXIT: the particle is converted AND removed)
+    wr = [dict(r="O2", p1="N2", nprod=1, prob=0.4), dict(r="O2", p1=None, nprod=0, prob=0.5)]
+    bc_wr = dict(bc_spec)
+    bc_wr[1] = ("specular", "react")
+    cases_wr = []
+    for draws in ([0.3, 0.7], [0.9, 0.8], [0.1, 0.2]):
+        p = dict(x=0.3, y=0.2, z=0.2, vx=210.0, vy=-95.0, vz=-480.0, erot=1.0e-21, evib=2.0e-21, ic=1, sid="O2")
+        pin = dict(p)
+        s = Script(draws)
+        q, trace = advect_tet(mesh, bc_wr, air, p, 1.0e-3, s, wr)
+        assert s.k == len(draws) and trace[0] == [1, 1]
+        cases_wr.append(dict(draws=draws, inp=pdict(pin), out=pdict(q), removed=bool(p.get("removed", False))))
+    assert [c["removed"] for c in cases_wr] == [False, True, True] and cases_wr[0]["out"]["sid"] == "N2"
+    out["wall_react"] = dict(dt=hx(1.0e-3), reactions=wr, cases=cases_wr)
 
     # ---- diffuse_reflect: O2 against a fully diffuse (Maxwell) wall on z = 0.  Draws: MAXWELL 3 x (R, R1) -- the first R1
     # below 1e-13 and redrawn --, EROT (dof 2), EVIB (dof 2), FLX: one rejected (R1, R2) pair, then an accepted one

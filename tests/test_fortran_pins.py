@@ -166,6 +166,35 @@ def test_cll_reflection_oracle_matches_fortran_reading(oracle):
         assert float(out[f.upper()][0]) == pytest.approx(fh(e[f]), rel=1e-13, abs=1e-300), f
 
 
+def check_wall_react(lib, scripted):
+    """WALL_REACT (src/fields.f90:4302-4341) on a reacting specular wall: conversion with the mass-ratio velocity
+    scaling, removal with the renormalised probability, and the missing EXIT (a converted particle can still be removed
+    by a later reaction of its ORIGINAL species)."""
+    t = PINS["wall_react"]
+    for c in t["cases"]:
+        w = tet_workload([c], fh(t["dt"]))
+        w.bcs["react"] = [1, 0, 0, 0]
+        sp = w.species
+        w.wall_reactions = dict(r_sp=[sp.id(r["r"]) for r in t["reactions"]], p1_sp=[sp.id(r["p1"]) if r["p1"] else -1 for r in t["reactions"]],
+                                nprod=[r["nprod"] for r in t["reactions"]], prob=[r["prob"] for r in t["reactions"]])
+        wl.apply(lib, w)
+        script(lib, c["draws"])
+        lib.advect(1)
+        assert script_used(lib) == len(c["draws"])
+        out = lib.download_particles()
+        if c["removed"]:
+            assert len(out) == 0
+            continue
+        e = c["out"]
+        assert len(out) == 1 and out["S_ID"][0] == sp.id(e["sid"]) and out["IC"][0] == e["ic"]
+        for f in ("x", "y", "z", "vx", "vy", "vz", "erot", "evib"):
+            assert float(out[f.upper()][0]) == fh(e[f]), (f, float(out[f.upper()][0]).hex(), e[f])
+
+
+def test_wall_react_oracle_matches_fortran_reading(oracle):
+    check_wall_react(oracle, True)
+
+
 def test_diffuse_reflection_oracle_matches_fortran_reading(oracle):
     """Maxwell wall (src/timecycle.f90:1445-1476) on scripted draws: MAXWELL with a redrawn R1 (src/tools.f90:130-187),
     INTERNAL_ENERGY twice, FLX with one rejected pair (src/tools.f90:1150-1186); FACE_TANG1/2 of the pin mesh."""
