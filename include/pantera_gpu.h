@@ -313,6 +313,19 @@ int pgpu_field_solve_1d(pgpu_ctx* ctx, int32_t tID, const double* rhs_host, doub
  * reference, gives every restarted particle DTRIM = DT. */
 int pgpu_dump_particles_file(pgpu_ctx* ctx, const char* path_prefix, int32_t timestep, int32_t binary);
 int pgpu_read_particles_file(pgpu_ctx* ctx, const char* path_prefix, int32_t timestep, int32_t binary);
+/* binary = 1: the IC of every record must be a cell of the current grid (a dump of the same mesh; the run can go on at
+ * once).  binary = 3 (1 + PGPU_RESTART_UNASSIGNED): the reference's restart semantics -- IC is not trusted (records whose
+ * IC is no cell of this grid are kept with IC = 0) and every hot-path entry point refuses to run until
+ * pgpu_reassign_particles_to_cells has located the particles again, as PROGRAM PANTERA does (src/pantera.f90:58-70). */
+#define PGPU_RESTART_UNASSIGNED 2
+/* REASSIGN_PARTICLES_TO_CELLS_1D / _2D / _3D (src/tools.f90:925-1039, 782-922, 577-778): every particle is located again
+ * from its position -- the domain box (pgpu_config xmin..zmax = Domain_limits:) cut into 100 bins per direction, the
+ * cells entered in the bins their bounding boxes overlap, the lowest-numbered cell of the particle's bin whose P1
+ * basis functions are all >= 0 at the particle (`IF (PSIP < 0) INSIDE = .FALSE.`) becomes its IC; particles outside the
+ * box or inside no cell are removed.  n_removed (optional) receives their number.  Unstructured grids only (the
+ * reference: 'Not implemented!' otherwise).  Bin indices are clamped to 1..100 where the reference would leave its
+ * arrays (a cell or particle exactly at XMAX). */
+int pgpu_reassign_particles_to_cells(pgpu_ctx* ctx, int64_t* n_removed);
 
 /* ---- sampling and conservation checks ------------------------------- */
 /* GRID_AVG (src/postprocess.f90:34-416, BOOL_DUMP_MOMENTS = .FALSE.): one more sample of the per (cell, species)

@@ -1812,6 +1812,98 @@ int po_read_particles_file(po_ctx* w, const char* path_prefix, int32_t timestep,
 }
 
 /* ------------------------------------------------------------------------------------------
+ * REASSIGN_PARTICLES_TO_CELLS_1D / _2D / _3D, ref: src/tools.f90:925-1039, 782-922, 577-778 (called after
+ * READ_PARTICLES_FILE on a restart, src/pantera.f90:58-70).  One body for the three copies: the domain box cut into
+ * N_PARTITIONS = 100 bins per direction, every cell entered (ascending IC) in the bins its bounding box overlaps, the
+ * first cell of a particle's bin with all PSIP >= 0 wins; removal by the reverse swap-with-last sweep.
+ * Bin indices are clamped to 1..100 where the Fortran would index past its arrays (see pgpu_restart.cu).
+ * ---------------------------------------------------------------------------------------- */
+static int rb_index(double c, double lo, double h, int n) {
+    /* INT((C - XMIN)/DX) + 1 with INT() truncating toward zero, clamped to 1..n */
+    const double q = (c - lo) / h;
+    if (!(q < (double)n)) return n;
+    if (q < 1.0) return 1;
+    return (int)q + 1;
+}
+int po_reassign_particles_to_cells(po_ctx* w, int64_t* n_removed) {
+    if (n_removed) *n_removed = 0;
+    if (w->c.grid_type != PGPU_UNSTRUCTURED || !w->basis_coeffs) FAIL(w, PGPU_ERR_UNSUPPORTED, "po_reassign_particles_to_cells: Not implemented!");
+    const int dims = w->dims_mesh, nf = dims + 1, NPART = 100;
+    const double lo[3] = {w->c.xmin, w->c.ymin, w->c.zmin}, hi[3] = {w->c.xmax, w->c.ymax, w->c.zmax};
+    int n[3] = {1, 1, 1};
+    double h[3] = {1, 1, 1};
+    for (int k = 0; k < dims; k++) {
+        n[k] = NPART;
+        h[k] = (hi[k] - lo[k]) / NPART;
+        if (!(h[k] > 0.)) FAIL(w, PGPU_ERR_INVALID, "po_reassign_particles_to_cells: empty Domain_limits");
+    }
+    const size_t nbins = (size_t)n[0] * n[1] * n[2];
+    int* ningrid = (int*)calloc(nbins, sizeof(int));
+    int* iof = (int*)calloc(nbins + 1, sizeof(int));
+    int* ind = NULL;
+    for (int pass = 0; pass < 2; pass++) {
+        if (pass == 1) {
+            int idx = 0; /* I outermost, K innermost, :655-666 */
+            for (size_t b = 0; b < nbins; b++) { iof[b] = idx; idx += ningrid[b]; }
+            iof[nbins] = idx;
+            ind = (int*)calloc((size_t)(idx > 0 ? idx : 1), sizeof(int));
+            memset(ningrid, 0, nbins * sizeof(int));
+        }
+        for (int ic = 1; ic <= w->nc; ic++) {
+            int imin[3] = {1, 1, 1}, imax[3] = {1, 1, 1};
+            for (int k = 0; k < dims; k++) {
+                double cmin = 0, cmax = 0;
+                for (int p = 1; p <= nf; p++) {
+                    double x = NODE_X(w, k + 1, CELL_NODE(w, p, ic));
+                    if (p == 1 || x < cmin) cmin = x;
+                    if (p == 1 || x > cmax) cmax = x;
+                }
+                imin[k] = rb_index(cmin, lo[k], h[k], n[k]);
+                imax[k] = rb_index(cmax, lo[k], h[k], n[k]);
+            }
+            for (int i = imin[0]; i <= imax[0]; i++)
+                for (int j = imin[1]; j <= imax[1]; j++)
+                    for (int k = imin[2]; k <= imax[2]; k++) {
+                        size_t b = ((size_t)(i - 1) * n[1] + (j - 1)) * n[2] + (k - 1);
+                        if (pass == 1) ind[iof[b] + ningrid[b]] = ic;
+                        ningrid[b]++;
+                    }
+        }
+    }
+    char* remove_part = (char*)calloc((size_t)(w->np > 0 ? w->np : 1), 1);
+    for (int64_t ip = 0; ip < w->np; ip++) {
+        part_t* q = &w->p[ip];
+        const double xp[3] = {q->X, q->Y, q->Z};
+        int outside = 0;
+        for (int k = 0; k < dims; k++)
+            if (xp[k] < lo[k] || xp[k] > hi[k]) outside = 1;
+        if (outside) { remove_part[ip] = 1; continue; }
+        int idx[3] = {1, 1, 1};
+        for (int k = 0; k < dims; k++) idx[k] = rb_index(xp[k], lo[k], h[k], n[k]);
+        size_t b = ((size_t)(idx[0] - 1) * n[1] + (idx[1] - 1)) * n[2] + (idx[2] - 1);
+        int cellfound = 0;
+        for (int e = iof[b]; e < iof[b] + ningrid[b]; e++) {
+            int ic = ind[e], inside = 1;
+            for (int vp = 1; vp <= nf; vp++) {
+                double psip;
+                if (dims == 3) psip = xp[0] * BASIS(w, 1, vp, ic) + xp[1] * BASIS(w, 2, vp, ic) + xp[2] * BASIS(w, 3, vp, ic) + BASIS(w, 4, vp, ic);
+                else if (dims == 2) psip = xp[0] * BASIS(w, 1, vp, ic) + xp[1] * BASIS(w, 2, vp, ic) + BASIS(w, 3, vp, ic);
+                else psip = xp[0] * BASIS(w, 1, vp, ic) + BASIS(w, 2, vp, ic);
+                if (psip < 0) inside = 0;
+            }
+            if (inside) { q->IC = ic; cellfound = 1; break; }
+        }
+        if (!cellfound) remove_part[ip] = 1;
+    }
+    int64_t removed = 0;
+    for (int64_t ip = w->np - 1; ip >= 0; ip--)
+        if (remove_part[ip]) { remove_particle(w, ip); removed++; }
+    free(remove_part); free(ningrid); free(iof); free(ind);
+    if (n_removed) *n_removed = removed;
+    return PGPU_OK;
+}
+
+/* ------------------------------------------------------------------------------------------
  * INITIAL_SEED (src/initialization.f90:2017-2233), VOLUME_INJECT (src/timecycle.f90:553-737), BOUNDARIES_EMIT
  * (src/timecycle.f90:368-547); RANDINT src/tools.f90:1304-1311.  COLOCATED_ELECTRONS, BOOL_INJECT_FROM_FILE and the
  * kappa distribution are outside the scope.

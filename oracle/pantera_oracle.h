@@ -133,6 +133,7 @@ int po_boundaries_emit(po_ctx* ctx, int32_t tID);
 int po_set_field_bcs(po_ctx* ctx, int nbc, const double* wall_potential, const double* wall_rf_potential, const double* rf_frequency,
                      const double* wall_efield, const double* eps_rel);
 int po_compute_e_field(po_ctx* ctx, const double* phi, int64_t nnodes, double* e_out);
+int po_reassign_particles_to_cells(po_ctx* ctx, int64_t* n_removed);
 int po_field_solve_1d(po_ctx* ctx, int32_t tID, const double* rhs, double* phi_out, double* e_out);
 int po_grid_avg(po_ctx* ctx);
 int po_grid_reset(po_ctx* ctx);

@@ -34,6 +34,7 @@ FLUID, SOLID = 0, 1
 PIC_NONE, PIC_EXPLICIT = 0, 1
 NO_COLL, DSMC, BGK, MCC, MCC_VAHEDI, DSMC_VAHEDI = range(6)
 FIXED_RATE, TCE, LXCAT = 0, 1, 2
+RESTART_UNASSIGNED = 2  # PGPU_RESTART_UNASSIGNED
 
 # host particle record: TYPE PARTICLE_DATA_STRUCTURE, src/particle.f90:28-37 (96-byte stride)
 PARTICLE_DTYPE = np.dtype(
@@ -502,8 +503,16 @@ class Lib:
     def dump_particles_file(self, path_prefix: str, timestep: int, binary: bool = True):
         self._call("dump_particles_file", C.c_char_p(path_prefix.encode()), C.c_int32(timestep), C.c_int32(int(binary)))
 
-    def read_particles_file(self, path_prefix: str, timestep: int, binary: bool = True):
-        self._call("read_particles_file", C.c_char_p(path_prefix.encode()), C.c_int32(timestep), C.c_int32(int(binary)))
+    def read_particles_file(self, path_prefix: str, timestep: int, binary: bool = True, unassigned: bool = False):
+        """unassigned=True: the reference's restart semantics (IC of the dump not trusted; reassign_particles_to_cells next)."""
+        self._call("read_particles_file", C.c_char_p(path_prefix.encode()), C.c_int32(timestep),
+                   C.c_int32(int(binary) | (RESTART_UNASSIGNED if unassigned else 0)))
+
+    def reassign_particles_to_cells(self) -> int:
+        """REASSIGN_PARTICLES_TO_CELLS_1D/2D/3D: returns the number of particles removed (outside the domain / every cell)."""
+        n = C.c_int64()
+        self._call("reassign_particles_to_cells", C.byref(n))
+        return n.value
 
     def run_steps(self, tID0: int, nsteps: int):
         a, b = C.c_int64(), C.c_int64()

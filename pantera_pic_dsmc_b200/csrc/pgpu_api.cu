@@ -762,6 +762,8 @@ int pg_prepare(pgpu_ctx* c) {
     cudaSetDevice(c->device);
     if (!c->cfg_set) PG_FAIL(c, PGPU_ERR_STATE, "pgpu_set_config has not been called");
     if (c->ns < 1) PG_FAIL(c, PGPU_ERR_STATE, "pgpu_set_species has not been called");
+    if (c->cells_unassigned && !c->reassigning)
+        PG_FAIL(c, PGPU_ERR_STATE, "the restart file was read without trusting its cell indices: call pgpu_reassign_particles_to_cells first");
     int rc;
     if (c->cfg.grid_type == PGPU_UNSTRUCTURED) {
         if (!c->mesh_set) PG_FAIL(c, PGPU_ERR_STATE, "unstructured grid without pgpu_set_mesh");
@@ -1050,6 +1052,7 @@ extern "C" int pgpu_upload_particles(pgpu_ctx* c, const void* aos, int64_t n, in
     c->has_dtrim = false;
     c->maybe_tombstones = false;
     c->id_counter = 0;
+    c->cells_unassigned = false; /* (the store is replaced) */
     c->sorted = false; /* (also for n == 0: the offsets of the previous population must not stay marked valid) */
     c->hist_valid = false;
     c->emig_valid = false;
@@ -1127,6 +1130,7 @@ extern "C" int pgpu_upload_planes(pgpu_ctx* c, const void* pos, const void* vel,
     c->has_dtrim = false;
     c->maybe_tombstones = false;
     c->id_counter = 0;
+    c->cells_unassigned = false; /* (the store is replaced) */
     c->sorted = false; c->hist_valid = false; c->emig_valid = false; c->vel_deferred = false; c->owned_clean = false;
     if (c->capacity == 0) {
         long long cap = c->cfg.capacity > 0 ? (long long)c->cfg.capacity : (long long)(1.5 * (double)n);

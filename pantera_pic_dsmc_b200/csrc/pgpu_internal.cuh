@@ -383,6 +383,10 @@ struct pgpu_ctx {
     void* d_det_tmp = nullptr;
     size_t det_tmp_bytes = 0;
 
+    /* restart (pgpu_io.cu, pgpu_restart.cu): a dump was read with its cell indices unchecked (another mesh); every hot-path
+     * entry point refuses to run until pgpu_reassign_particles_to_cells has located the particles again */
+    bool cells_unassigned = false, reassigning = false;
+
     /* injection (pgpu_inject.cu), field step (pgpu_field.cu) */
     void* inject = nullptr;
     void* field = nullptr;

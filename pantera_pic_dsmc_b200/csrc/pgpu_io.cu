@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(256) dump_pack_kernel(PgPlanes p, long long ba
 }
 
 __global__ void __launch_bounds__(256) dump_unpack_kernel(const unsigned int* __restrict__ in, long long n, PgPlanes p, long long base,
-                                                          double dt, int rank, long long id_base, int ncells, PgStatus* st) {
+                                                          double dt, int rank, long long id_base, int ncells, int relax, PgStatus* st) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const unsigned int* w = in + (size_t)i * (DUMP_REC / 4);
@@ -68,7 +68,10 @@ __global__ void __launch_bounds__(256) dump_unpack_kernel(const unsigned int* __
         const unsigned long long b = ((unsigned long long)w[2 + 2 * k] << 32) | (unsigned long long)w[1 + 2 * k];
         f[k] = __longlong_as_double((long long)bswap64(b));
     }
-    const int sid = (int)bswap32(w[17]), ic = (int)bswap32(w[18]);
+    const int sid = (int)bswap32(w[17]);
+    int ic = (int)bswap32(w[18]);
+    /* PGPU_RESTART_UNASSIGNED: the dump's IC is not trusted; what is no cell of this grid waits as IC = 0 for the re-binning */
+    if (relax && ncells > 0 && (ic < 1 || ic > ncells)) ic = 0;
     const long long o = base + i;
     PgPos P;
     P.x = f[0]; P.y = f[1]; P.z = f[2]; P.ic = ic; P.sid = sid;
@@ -83,7 +86,7 @@ __global__ void __launch_bounds__(256) dump_unpack_kernel(const unsigned int* __
     if (p.id) p.id[o] = (long long)rank + ((id_base + i) << 8);
     if (E.erot != 0. || E.evib != 0.) st->flag_ie = 1;
     if (bswap32(w[0]) != 80u || bswap32(w[21]) != 80u) atomicCAS(&st->err, 0, PG_DEVERR_CELL_RANGE);
-    if (ncells > 0 && (ic < 1 || ic > ncells)) atomicCAS(&st->err, 0, PG_DEVERR_CELL_RANGE);
+    if (!relax && ncells > 0 && (ic < 1 || ic > ncells)) atomicCAS(&st->err, 0, PG_DEVERR_CELL_RANGE);
 }
 
 const long long IO_CHUNK = 1 << 20; /* particles per staging chunk (88 MiB) */
@@ -157,9 +160,13 @@ extern "C" int pgpu_dump_particles_file(pgpu_ctx* c, const char* path_prefix, in
 
 extern "C" int pgpu_read_particles_file(pgpu_ctx* c, const char* path_prefix, int32_t timestep, int32_t binary) {
     if (!c) return PGPU_ERR_INVALID;
-    if (!binary) PG_FAIL(c, PGPU_ERR_UNSUPPORTED, "read_particles_file: only the binary flavour is read on the device");
+    if (!(binary & 1)) PG_FAIL(c, PGPU_ERR_UNSUPPORTED, "read_particles_file: only the binary flavour is read on the device");
+    const int relax = (binary & PGPU_RESTART_UNASSIGNED) ? 1 : 0;
     int rc;
-    if ((rc = pg_prepare(c))) return rc;
+    c->reassigning = true; /* (a second file may follow a first one read with PGPU_RESTART_UNASSIGNED) */
+    rc = pg_prepare(c);
+    c->reassigning = false;
+    if (rc) return rc;
     char name[1024];
     dump_name(name, sizeof(name), path_prefix, c->cfg.rank, timestep);
     FILE* fp = fopen(name, "rb");
@@ -195,7 +202,7 @@ extern "C" int pgpu_read_particles_file(pgpu_ctx* c, const char* path_prefix, in
         if (fread(h_buf, DUMP_REC, (size_t)m, fp) != (size_t)m) { rc = PGPU_ERR_INVALID; break; }
         cudaMemcpyAsync(d_buf, h_buf, (size_t)m * DUMP_REC, cudaMemcpyHostToDevice, c->stream);
         dump_unpack_kernel<<<(unsigned int)((m + 255) / 256), 256, 0, c->stream>>>((const unsigned int*)d_buf, m, p, c->np + done, c->cfg.dt,
-                                                                                  c->cfg.rank, c->id_counter + done, ncells, c->d_status);
+                                                                                  c->cfg.rank, c->id_counter + done, ncells, relax, c->d_status);
         cudaStreamSynchronize(c->stream); /* one staging buffer: the host refills it next */
         c->launches++;
     }
@@ -214,5 +221,6 @@ extern "C" int pgpu_read_particles_file(pgpu_ctx* c, const char* path_prefix, in
     }
     if (c->h_status->flag_ie) c->ie_seen = true;
     c->id_counter = std::max(c->id_counter, c->np);
+    if (relax && n > 0) c->cells_unassigned = true;
     return PGPU_OK;
 }
