@@ -303,6 +303,18 @@ int pgpu_compute_e_field(pgpu_ctx* ctx, const double* phi_host, int64_t nnodes, 
  * (:137-253, 758-760) with the right-hand side rows of DEPOSIT_CHARGE (:5538-5561) + COMPUTE_E_FIELD, all on the
  * device.  rhs_host == NULL uses the RHS of the last pgpu_deposit_charge.  phi_host, e_host optional outputs. */
 int pgpu_field_solve_1d(pgpu_ctx* ctx, int32_t tID, const double* rhs_host, double* phi_host, double* e_host);
+/* Any unstructured mesh.  1-D: as above.  2-D (plane / axisymmetric triangles) and 3-D (tetrahedra): the P1 stiffness
+ * matrix of ASSEMBLE_POISSON (src/fields.f90:256-424, 425-637; Dirichlet, RF-voltage and unused nodes as identity rows,
+ * :639-646, :758-760; NEUMANN(:) from the boundary faces, :391-421, :579-633; EPS_REL of the cell's volume group),
+ * SET_WALL_POTENTIAL at timestep tID (:5609-5711), the right-hand side rows of DEPOSIT_CHARGE (:5538-5547) and
+ * COMPUTE_E_FIELD, with the linear solve (KSPSolve in the reference, src/fields.f90:5205-5234) done on the device by a
+ * Jacobi-preconditioned conjugate gradient: it stops when |r| <= max(rtol |b|, 1e-50) or after max_iter iterations
+ * (rtol <= 0: 1e-5 and max_iter <= 0: 10000, PETSc's KSP defaults), starting from the previous potential.
+ * iters_out / relres_out (optional): iterations used and the relative residual reached; running out of iterations is
+ * not an error (the reference prints KSPConvergedReason and goes on) -- compare relres with the tolerance.
+ * PIC_TYPE explicit only (EXPLICITLIMITED's DXLDRATIO factors are not assembled). */
+int pgpu_field_solve(pgpu_ctx* ctx, int32_t tID, const double* rhs_host, double* phi_host, double* e_host, double rtol,
+                     int32_t max_iter, int32_t* iters_out, double* relres_out);
 
 /* ---- dump / restart -------------------------------------------------- */
 /* DUMP_PARTICLES_FILE (src/tools.f90:327-365) / READ_PARTICLES_FILE (src/tools.f90:465-517): the file

@@ -2182,57 +2182,121 @@ int po_compute_e_field(po_ctx* w, const double* phi, int64_t nnodes, double* e_o
     free(e);
     return PGPU_OK;
 }
-int po_field_solve_1d(po_ctx* w, int32_t tID, const double* rhs, double* phi_out, double* e_out) {
-    if (w->c.grid_type != PGPU_UNSTRUCTURED || w->dims_mesh != 1) FAIL(w, PGPU_ERR_UNSUPPORTED, "po_field_solve_1d: 1-D meshes only");
-    if (!rhs) FAIL(w, PGPU_ERR_INVALID, "po_field_solve_1d: the oracle needs the RHS passed in");
-    const int nn = w->nn, nc = w->nc;
+/* The whole field step on any unstructured mesh.  One body for the three branches of ASSEMBLE_POISSON
+ * (src/fields.f90:137-253 segments, :256-424 triangles, :425-637 tetrahedra; unused nodes :639-646; identity rows
+ * :758-760), SET_WALL_POTENTIAL (:5566-5717) and the right-hand side rows of DEPOSIT_CHARGE (:5538-5547).  The matrix
+ * is dense with MatSetValue(ADD_VALUES) semantics -- cells in ascending order -- and solved by Gaussian elimination with
+ * partial pivoting: deliberately neither the device's tridiagonal sweep nor its conjugate gradient. */
+static const int FACE_LOCAL_1D[2][3] = {{1, 0, 0}, {2, 0, 0}};
+static const int FACE_LOCAL_2D[3][3] = {{1, 2, 0}, {2, 3, 0}, {3, 1, 0}};
+static const int FACE_LOCAL_3D[4][3] = {{1, 3, 2}, {1, 2, 4}, {2, 3, 4}, {1, 4, 3}};
+static int face_local(int d, int j, int t) { /* local node t (0-based) of face j (1-based), 1-based local number */
+    return d == 1 ? FACE_LOCAL_1D[j - 1][t] : d == 2 ? FACE_LOCAL_2D[j - 1][t] : FACE_LOCAL_3D[j - 1][t];
+}
+static int field_solve(po_ctx* w, int32_t tID, const double* rhs, double* phi_out, double* e_out) {
+    if (w->c.grid_type != PGPU_UNSTRUCTURED) FAIL(w, PGPU_ERR_UNSUPPORTED, "po_field_solve: unstructured meshes only");
+    if (!rhs) FAIL(w, PGPU_ERR_INVALID, "po_field_solve: the oracle needs the RHS passed in");
+    const int nn = w->nn, nc = w->nc, d = w->dims_mesh, nf = d + 1;
     double* A = (double*)calloc((size_t)nn * nn, sizeof(double));
     double* b = (double*)calloc((size_t)nn, sizeof(double));
     double* dir = (double*)calloc((size_t)nn, sizeof(double));
     double* neu = (double*)calloc((size_t)nn, sizeof(double));
     char* isd = (char*)calloc((size_t)nn, 1);
     char* isn = (char*)calloc((size_t)nn, 1);
-    for (int i = 0; i < nc; i++) /* :143-176 with SET_WALL_POTENTIAL's time-dependent value */
-        for (int j = 0; j < 2; j++) {
-            int pg = w->cell_faces_pg[2 * i + j];
+    char* unused = (char*)malloc((size_t)nn);
+    memset(unused, 1, (size_t)nn);
+#define FB(arr, pg) ((arr) ? (arr)[(pg)-1] : 0.0)
+    for (int i = 1; i <= nc; i++) { /* flags, with SET_WALL_POTENTIAL's time-dependent value */
+        for (int p = 1; p <= nf; p++) unused[CELL_NODE(w, p, i) - 1] = 0;
+        for (int j = 1; j <= nf; j++) {
+            int pg = FACE_PG(w, j, i);
             if (pg == -1) continue;
-            int fbc = w->bc_field[pg - 1], v = w->cell_nodes[2 * i + j] - 1;
-            if (fbc == PGPU_DIRICHLET_BC || fbc == PGPU_RF_VOLTAGE_BC || fbc == PGPU_DECOUPLED_RF_VOLTAGE_BC) {
-                double pot = w->fb_pot ? w->fb_pot[pg - 1] : 0.0;
-                if (fbc != PGPU_DIRICHLET_BC)
-                    pot = (w->fb_pot ? w->fb_pot[pg - 1] : 0.0) + 0.5 * (w->fb_rfpot ? w->fb_rfpot[pg - 1] : 0.0) * cos(2 * PI * (w->fb_freq ? w->fb_freq[pg - 1] : 0.0) * tID * w->c.dt);
-                dir[v] = pot;
-                isd[v] = 1;
-            }
-            if (fbc == PGPU_NEUMANN_BC) isn[v] = 1;
-        }
-    for (int i = 0; i < nc; i++) { /* :198-251 */
-        double eps_rel = 1.0;
-        if (w->cell_pg && w->cell_pg[i] != -1 && w->fb_eps) eps_rel = w->fb_eps[w->cell_pg[i] - 1];
-        int v1 = w->cell_nodes[2 * i] - 1, v2 = w->cell_nodes[2 * i + 1] - 1;
-        double length = fabs(w->node_coords[3 * v2] - w->node_coords[3 * v1]);
-        double k11 = 1.0 / length * eps_rel, k22 = 1.0 / length * eps_rel, k12 = -1.0 / length * eps_rel;
-        if (!isd[v1]) { A[(size_t)v1 * nn + v1] += k11; A[(size_t)v1 * nn + v2] += k12; }
-        if (!isd[v2]) { A[(size_t)v2 * nn + v1] += k12; A[(size_t)v2 * nn + v2] += k22; }
-        for (int j = 0; j < 2; j++) {
-            int pg = w->cell_faces_pg[2 * i + j];
-            if (pg == -1) continue;
-            if (w->bc_field[pg - 1] == PGPU_NEUMANN_BC) {
-                int v = j == 0 ? v1 : v2;
-                if (!isd[v]) neu[v] = neu[v] + (w->fb_efield ? w->fb_efield[pg - 1] : 0.0);
+            int fbc = w->bc_field[pg - 1];
+            for (int t = 0; t < d; t++) {
+                int v = CELL_NODE(w, face_local(d, j, t), i) - 1;
+                if (fbc == PGPU_DIRICHLET_BC || fbc == PGPU_RF_VOLTAGE_BC || fbc == PGPU_DECOUPLED_RF_VOLTAGE_BC) {
+                    double pot = FB(w->fb_pot, pg);
+                    if (fbc != PGPU_DIRICHLET_BC) pot = FB(w->fb_pot, pg) + 0.5 * FB(w->fb_rfpot, pg) * cos(2 * PI * FB(w->fb_freq, pg) * tID * w->c.dt);
+                    dir[v] = pot;
+                    isd[v] = 1;
+                }
+                if (fbc == PGPU_NEUMANN_BC) isn[v] = 1;
             }
         }
     }
+    for (int i = 1; i <= nc; i++) {
+        double eps_rel = 1.0;
+        if (w->cell_pg && w->cell_pg[i - 1] != -1 && w->fb_eps) eps_rel = w->fb_eps[w->cell_pg[i - 1] - 1];
+        double K[4][4];
+        if (d == 1) { /* :204-212 */
+            double length = fabs(NODE_X(w, 1, CELL_NODE(w, 2, i)) - NODE_X(w, 1, CELL_NODE(w, 1, i))); /* SEGMENT_LENGTHS */
+            K[0][0] = 1.0 / length * eps_rel; K[1][1] = 1.0 / length * eps_rel; K[0][1] = K[1][0] = -1.0 / length * eps_rel;
+        } else if (d == 2) { /* :332-361 */
+            int v1 = CELL_NODE(w, 1, i), v2 = CELL_NODE(w, 2, i), v3 = CELL_NODE(w, 3, i);
+            double x1 = NODE_X(w, 1, v1), x2 = NODE_X(w, 1, v2), x3 = NODE_X(w, 1, v3);
+            double y1 = NODE_X(w, 2, v1), y2 = NODE_X(w, 2, v2), y3 = NODE_X(w, 2, v3);
+            double area = 0.5 * fabs(x1 * (y2 - y3) + x2 * (y3 - y1) + x3 * (y1 - y2)); /* CELL_AREAS, grid_and_partition.f90:1315 */
+            double k11 = 0.25 * ((y2 - y3) * (y2 - y3) + (x2 - x3) * (x2 - x3)) / area * eps_rel;
+            double k22 = 0.25 * ((y1 - y3) * (y1 - y3) + (x1 - x3) * (x1 - x3)) / area * eps_rel;
+            double k33 = 0.25 * ((y2 - y1) * (y2 - y1) + (x2 - x1) * (x2 - x1)) / area * eps_rel;
+            double k12 = -(0.25 * ((y2 - y3) * (y1 - y3) + (x2 - x3) * (x1 - x3)) / area * eps_rel);
+            double k23 = 0.25 * ((y1 - y3) * (y2 - y1) + (x1 - x3) * (x2 - x1)) / area * eps_rel;
+            double k13 = -(0.25 * ((y2 - y3) * (y2 - y1) + (x2 - x3) * (x2 - x1)) / area * eps_rel);
+            if (w->c.axi) {
+                k11 = k11 * (y1 + y2 + y3) / 3.; k22 = k22 * (y1 + y2 + y3) / 3.; k33 = k33 * (y1 + y2 + y3) / 3.;
+                k12 = k12 * (y1 + y2 + y3) / 3.; k23 = k23 * (y1 + y2 + y3) / 3.; k13 = k13 * (y1 + y2 + y3) / 3.;
+            }
+            K[0][0] = k11; K[1][1] = k22; K[2][2] = k33;
+            K[0][1] = K[1][0] = k12; K[1][2] = K[2][1] = k23; K[0][2] = K[2][0] = k13;
+        } else { /* :560-577 */
+            double volume = w->cell_volumes[i - 1];
+            for (int p = 1; p <= 4; p++)
+                for (int q = 1; q <= 4; q++)
+                    K[p - 1][q - 1] = volume * (BASIS(w, 1, p, i) * BASIS(w, 1, q, i) + BASIS(w, 2, p, i) * BASIS(w, 2, q, i) + BASIS(w, 3, p, i) * BASIS(w, 3, q, i)) * eps_rel;
+        }
+        for (int p = 1; p <= nf; p++) {
+            int vp = CELL_NODE(w, p, i) - 1;
+            if (isd[vp]) continue;
+            for (int q = 1; q <= nf; q++) A[(size_t)vp * nn + (CELL_NODE(w, q, i) - 1)] += K[p - 1][q - 1];
+        }
+        for (int j = 1; j <= nf; j++) { /* Neumann faces: :236-251, :391-421, :579-633 */
+            int pg = FACE_PG(w, j, i);
+            if (pg == -1 || w->bc_field[pg - 1] != PGPU_NEUMANN_BC) continue;
+            double add;
+            if (d == 1) add = FB(w->fb_efield, pg);
+            else if (d == 2) {
+                int va = CELL_NODE(w, face_local(2, j, 0), i), vb = CELL_NODE(w, face_local(2, j, 1), i);
+                double dx = NODE_X(w, 1, vb) - NODE_X(w, 1, va), dy = NODE_X(w, 2, vb) - NODE_X(w, 2, va);
+                double edgelength = sqrt(dx * dx + dy * dy);
+                add = FB(w->fb_efield, pg) * 0.5 * edgelength;
+            } else {
+                int va = CELL_NODE(w, face_local(3, j, 0), i), vb = CELL_NODE(w, face_local(3, j, 1), i), vc = CELL_NODE(w, face_local(3, j, 2), i);
+                double u[3], t[3], cr[3];
+                for (int k = 1; k <= 3; k++) { u[k - 1] = NODE_X(w, k, vb) - NODE_X(w, k, va); t[k - 1] = NODE_X(w, k, vc) - NODE_X(w, k, va); }
+                cross3(u, t, cr);
+                double facearea = 0.5 * norm2_3(cr); /* FACE_AREA, grid_and_partition.f90:1957 */
+                add = FB(w->fb_efield, pg) * facearea / 3.;
+            }
+            for (int t = 0; t < d; t++) {
+                int v = CELL_NODE(w, face_local(d, j, t), i) - 1;
+                if (!isd[v]) neu[v] = neu[v] + add;
+            }
+        }
+    }
+#undef FB
+    for (int v = 0; v < nn; v++)
+        if (unused[v]) { isd[v] = 1; dir[v] = 0.0; } /* :639-646 */
     for (int v = 0; v < nn; v++) { /* :758-760 and :5538-5547 */
         if (isd[v]) { for (int k = 0; k < nn; k++) A[(size_t)v * nn + k] = 0; A[(size_t)v * nn + v] = 1.0; b[v] = dir[v]; }
         else if (isn[v]) b[v] = rhs[v] + neu[v];
         else b[v] = rhs[v];
     }
-    for (int k = 0; k < nn; k++) { /* Gaussian elimination, partial pivoting */
+    int singular = 0;
+    for (int k = 0; k < nn && !singular; k++) { /* Gaussian elimination, partial pivoting */
         int piv = k;
         for (int r = k + 1; r < nn; r++)
             if (fabs(A[(size_t)r * nn + k]) > fabs(A[(size_t)piv * nn + k])) piv = r;
-        if (A[(size_t)piv * nn + k] == 0.0) { free(A); free(b); free(dir); free(neu); free(isd); free(isn); FAIL(w, PGPU_ERR_INVALID, "po_field_solve_1d: singular system"); }
+        if (A[(size_t)piv * nn + k] == 0.0) { singular = 1; break; }
         if (piv != k) {
             for (int cidx = 0; cidx < nn; cidx++) { double t = A[(size_t)k * nn + cidx]; A[(size_t)k * nn + cidx] = A[(size_t)piv * nn + cidx]; A[(size_t)piv * nn + cidx] = t; }
             double t = b[k]; b[k] = b[piv]; b[piv] = t;
@@ -2244,15 +2308,31 @@ int po_field_solve_1d(po_ctx* w, int32_t tID, const double* rhs, double* phi_out
             b[r] -= m * b[k];
         }
     }
-    for (int k = nn - 1; k >= 0; k--) {
-        double sum = b[k];
-        for (int cidx = k + 1; cidx < nn; cidx++) sum -= A[(size_t)k * nn + cidx] * b[cidx];
-        b[k] = sum / A[(size_t)k * nn + k];
+    int rc = PGPU_OK;
+    if (!singular) {
+        for (int k = nn - 1; k >= 0; k--) {
+            double sum = b[k];
+            for (int cidx = k + 1; cidx < nn; cidx++) sum -= A[(size_t)k * nn + cidx] * b[cidx];
+            b[k] = sum / A[(size_t)k * nn + k];
+        }
+        if (phi_out) memcpy(phi_out, b, sizeof(double) * (size_t)nn);
+        rc = po_compute_e_field(w, b, nn, e_out);
     }
-    if (phi_out) memcpy(phi_out, b, sizeof(double) * (size_t)nn);
-    int rc = po_compute_e_field(w, b, nn, e_out);
-    free(A); free(b); free(dir); free(neu); free(isd); free(isn);
+    free(A); free(b); free(dir); free(neu); free(isd); free(isn); free(unused);
+    if (singular) FAIL(w, PGPU_ERR_INVALID, "po_field_solve: singular system");
     return rc;
+}
+int po_field_solve_1d(po_ctx* w, int32_t tID, const double* rhs, double* phi_out, double* e_out) {
+    if (w->c.grid_type != PGPU_UNSTRUCTURED || w->dims_mesh != 1) FAIL(w, PGPU_ERR_UNSUPPORTED, "po_field_solve_1d: 1-D meshes only");
+    return field_solve(w, tID, rhs, phi_out, e_out);
+}
+/* (rtol, max_iter: the oracle's solve is direct) */
+int po_field_solve(po_ctx* w, int32_t tID, const double* rhs, double* phi_out, double* e_out, double rtol, int32_t max_iter,
+                   int32_t* iters_out, double* relres_out) {
+    (void)rtol; (void)max_iter;
+    if (iters_out) *iters_out = 0;
+    if (relres_out) *relres_out = 0.0;
+    return field_solve(w, tID, rhs, phi_out, e_out);
 }
 
 /* ------------------------------------------------------------------------------------------

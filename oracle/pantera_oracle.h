@@ -135,6 +135,8 @@ int po_set_field_bcs(po_ctx* ctx, int nbc, const double* wall_potential, const d
 int po_compute_e_field(po_ctx* ctx, const double* phi, int64_t nnodes, double* e_out);
 int po_reassign_particles_to_cells(po_ctx* ctx, int64_t* n_removed);
 int po_field_solve_1d(po_ctx* ctx, int32_t tID, const double* rhs, double* phi_out, double* e_out);
+int po_field_solve(po_ctx* ctx, int32_t tID, const double* rhs, double* phi_out, double* e_out, double rtol, int32_t max_iter,
+                   int32_t* iters_out, double* relres_out);
 int po_grid_avg(po_ctx* ctx);
 int po_grid_reset(po_ctx* ctx);
 int po_get_grid_avg(po_ctx* ctx, int64_t n, double* avg_np, double* avg_vx, double* avg_vy, double* avg_vz, double* avg_ttrx,

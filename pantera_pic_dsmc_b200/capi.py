@@ -474,6 +474,14 @@ class Lib:
         self._call("field_solve_1d", C.c_int32(tID), _p(r), _p(phi), _p(e))
         return phi, e.reshape(ncells, 3).T
 
+    def field_solve(self, tID, nnodes, ncells, rhs=None, rtol=0.0, max_iter=0):
+        """Any unstructured mesh; returns (phi, E(3, ncells), iterations, relative residual)."""
+        phi, e = np.zeros(nnodes), np.zeros(3 * ncells)
+        r = _f64(rhs) if rhs is not None else None
+        it, rel = C.c_int32(), C.c_double()
+        self._call("field_solve", C.c_int32(tID), _p(r), _p(phi), _p(e), C.c_double(rtol), C.c_int32(max_iter), C.byref(it), C.byref(rel))
+        return phi, e.reshape(ncells, 3).T, it.value, rel.value
+
     def grid_avg(self):
         self._call("grid_avg")
 

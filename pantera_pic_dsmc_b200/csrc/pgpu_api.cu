@@ -411,6 +411,7 @@ extern "C" int pgpu_set_mesh(pgpu_ctx* c, int dims, int nn, int nc, const double
     c->nsc = nn;
     c->mesh_set = true;
     c->mesh_dirty = true;
+    pg_field_invalidate(c);
     return alloc_counters(c);
 }
 
@@ -472,6 +473,7 @@ extern "C" int pgpu_set_bcs(pgpu_ctx* c, int nbc, const int32_t* particle_bc, co
     c->h_bc_field.assign(field_bc, field_bc + nbc);
     c->h_bc_react.assign(react, react + nbc);
     c->mesh_dirty = c->mesh_set;
+    pg_field_invalidate(c);
     return PGPU_OK;
 }
 

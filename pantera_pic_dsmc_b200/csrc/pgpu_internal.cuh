@@ -482,6 +482,7 @@ int pg_need_ie(pgpu_ctx* c);                  /* allocate the internal-energy pl
 int pg_need_dtrim(pgpu_ctx* c);               /* allocate the DTRIM planes if they do not exist yet */
 void pg_inject_destroy(pgpu_ctx* c);
 void pg_field_destroy(pgpu_ctx* c);
+void pg_field_invalidate(pgpu_ctx* c); /* mesh or boundary types changed: chains, matrices and warm starts are stale */
 int pg_adopt_efield(pgpu_ctx* c, double* d_e); /* a device array becomes E_FIELD (owned by the context from then on) */
 
 static inline int pg_ncells(const pgpu_ctx* c) {
