@@ -159,13 +159,29 @@ ALT = {
     "c2": ("C2-like air box: N2/O2/O/N/NO with TCE reactions and Borgnakke-Larsen, 1024x1024 structured grid, periodic", 312.0),
     "c5-1e9": ("C5 3-D unstructured argon channel, the WHOLE 256x128x128-cube mesh (2.5e7 tets) and 10^9 particles on ONE GPU "
                "(north_star's single-GPU target configuration; particles streamed in from the host in batches)", 280.0),
+    "c2-cyl": ("C2 air flow around a cylinder: 2-D half annulus of 2e5 triangles, N2/O2 free stream at 7 km/s emitted from the outer "
+               "boundary on the device every step (BOUNDARIES_EMIT), diffuse cylinder at 1000 K, TCE reactions + Borgnakke-Larsen", 312.0),
+    "c5-open": ("C5 3-D unstructured argon channel, open variant: vacuum end caps, inflow emitted at x = 0 on the device every step "
+                "(BOUNDARIES_EMIT), diffuse y-walls, specular z", 280.0),
     "c4": ("C4 1-D argon PIC-MCC (Vahedi null collision, LXCat-format tables), 512 segments: DEPOSIT_CHARGE + Poisson + "
            "E + ADVECT (Boris) + MCC per step, all on the device", None),
 }
 
 
-def build_alt(name, n):
+EMITTING = ("c2-cyl", "c5-open")   # workloads whose timed step starts with BOUNDARIES_EMIT on the device
+
+
+def build_alt(name, n, small=False):
     from pantera_pic_dsmc_b200 import capi, workloads as wl
+    if name == "c2-cyl":
+        w = wl.c2_cylinder(n, ni=50, nj=80) if small else wl.c2_cylinder(n, ni=250, nj=400)
+        w.cfg.capacity = int(1.5 * n) + 65536
+        return w
+    if name == "c5-open":
+        w = wl.c5_channel_strip(8, 16, 16, n=n, u_drift=300.0) if small else wl.c5_channel_strip(32, 128, 128, n=n, seed=1234, u_drift=300.0)
+        wl.open_channel(w, u=300.0)
+        w.cfg.capacity = int(1.5 * n) + 65536
+        return w
     if name == "c5-1e9":
         w = wl.c5_channel_strip(256, 128, 128, n=n, rank=0, world=1, seed=1234, u_drift=0.0, lazy=True)
         w.cfg.capacity = int(n + n // 256) + 65536
@@ -185,6 +201,20 @@ def build_alt(name, n):
 
 def alt_step_fn(name, lib, w):
     """returns f(tid0, nsteps) -> (collisions, per-group seconds dict or None)"""
+    if name in EMITTING:
+        def g(t0, k):
+            nc = 0
+            grp = {"emit": 0.0, "move": 0.0, "sort": 0.0, "collide": 0.0}
+            for t in range(t0, t0 + k):
+                a = time.perf_counter()
+                lib.boundaries_emit(t)
+                grp["emit"] += time.perf_counter() - a
+                nc += lib.run_steps(t, 1)[0]
+                if hasattr(lib, "get_timings") and lib.prefix == "pgpu_":
+                    ms = lib.get_timings()[0]
+                    grp["move"] += ms[0] * 1e-3; grp["sort"] += ms[1] * 1e-3; grp["collide"] += ms[2] * 1e-3
+            return nc, grp
+        return g
     if name != "c4":
         return lambda t0, k: (lib.run_steps(t0, k)[0], None)
 
@@ -218,7 +248,7 @@ def run_alt(args):
     name = args.workload
     desc, b_alg = ALT[name]
     n = args.particles if args.particles != 125_000_000 else {"c1": 10_000_000, "c1-grid": 100_000_000, "c2": 50_000_000, "c4": 10_000_000,
-                                                              "c5-1e9": 1_000_000_000}[name]
+                                                              "c5-1e9": 1_000_000_000, "c2-cyl": 20_000_000, "c5-open": 125_000_000}[name]
     w = build_alt(name, n)
     gpu = capi.load_gpu(0)
     if name == "c5-1e9":
@@ -231,6 +261,8 @@ def run_alt(args):
         args.no_cpu = True
     else:
         wl.apply(gpu, w)
+    if name in EMITTING:
+        wl.apply_sources(gpu, w)
     if name == "c4":
         gpu.set_field_bcs(wall_potential=[0.0, 0.0], wall_rf_potential=[200.0, 0.0], rf_frequency=[13.56e6, 0.0])
     step = alt_step_fn(name, gpu, w)
@@ -250,6 +282,8 @@ def run_alt(args):
     if name == "c4":
         p_mcc = ncoll / max(n_avg * args.steps, 1)
         b_alg = 108.0 + 32.0 + 52.0 * p_mcc   # move with the Boris kick + deposit (not fused) + MCC; no sort on this path
+        groups = {k: v / args.steps * 1e3 for k, v in grp.items()}
+    elif grp is not None:
         groups = {k: v / args.steps * 1e3 for k, v in grp.items()}
     else:
         groups = {"move": float(ms[0]) / args.steps, "sort": float(ms[1]) / args.steps, "collide": float(ms[2]) / args.steps}
@@ -274,7 +308,7 @@ def run_alt(args):
         k2 = max(2, min(args.e2e_steps or args.steps, 5))
         def one(t):
             gpu.upload_planes(pos0, vel0, ie_in)
-            gpu.run_steps(t, 1)
+            step(t, 1)
             return gpu.download_planes_into(op, ov, oe)
         one(900)
         t1 = time.perf_counter()
@@ -283,14 +317,20 @@ def run_alt(args):
         bpp = 80 if use_ie else 64
         e2e = {"value": m / es, "unit": "particle-timesteps/s", "h2d_bytes_per_step": int(len(w.particles) * bpp),
                "d2h_bytes_per_step": int(len(w.particles) * bpp), "steps": k2, "ms_per_step": es / k2 * 1e3,
-               "what": "sequential: pgpu_upload_planes + pgpu_run_steps(1) + pgpu_download_planes per step"}
+               "what": "sequential: pgpu_upload_planes + " + ("pgpu_boundaries_emit + " if name in EMITTING else "") +
+                       "pgpu_run_steps(1) + pgpu_download_planes per step"}
     cpu = None
     if not args.no_cpu:
-        ws = build_alt(name, {"c1": 200_000, "c1-grid": 1_000_000, "c2": 500_000, "c4": 400_000}[name]) if name != "c1-grid" else wl.c1_argon_box(1_000_000, nx=128, ny=128)
+        if name in EMITTING:
+            ws = build_alt(name, 500_000 if name == "c2-cyl" else 491_520, small=True)
+        else:
+            ws = build_alt(name, {"c1": 200_000, "c1-grid": 1_000_000, "c2": 500_000, "c4": 400_000}[name]) if name != "c1-grid" else wl.c1_argon_box(1_000_000, nx=128, ny=128)
         if name == "c2":
             ws = wl.c2_air_box(500_000, nx=100, ny=100, T=9000.0, nrho=1e21, dt=2e-7)
         o = capi.load_oracle(rng_mode=0)
         wl.apply(o, ws)
+        if name in EMITTING:
+            wl.apply_sources(o, ws)
         if name == "c4":
             o.set_field_bcs(wall_potential=[0.0, 0.0], wall_rf_potential=[200.0, 0.0], rf_frequency=[13.56e6, 0.0])
             def ostep(t):
@@ -298,6 +338,8 @@ def run_alt(args):
                 o.field_solve_1d(t, ws.mesh.nn, ws.mesh.nc, rhs=rhs)
                 o.advect(t)
                 o.mcc_vahedi(t)
+        elif name in EMITTING:
+            ostep = lambda t: (o.boundaries_emit(t), o.run_steps(t, 1))
         else:
             ostep = lambda t: o.run_steps(t, 1)
         ostep(1)

@@ -21,7 +21,10 @@
  * test on the device; the host reads one status word per batch of iterations.
  */
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
+
+#include <cooperative_groups.h>
 
 #include "pgpu_internal.cuh"
 
@@ -420,7 +423,7 @@ __device__ double cg_block_sum(double v, double* sm) {
     for (int w = 0; w < CG_THREADS / 32; w++) t += sm[w];
     return t;
 }
-__device__ double cg_total(const double* __restrict__ part, int nb, double* sm) {
+__device__ double cg_total(const double* part, int nb, double* sm) {
     double v = 0.0;
     for (int k = threadIdx.x; k < nb; k += CG_THREADS) v += part[k];
     return cg_block_sum(v, sm);
@@ -570,6 +573,100 @@ __global__ void __launch_bounds__(CG_THREADS) cg_check_kernel(int k, int nb, con
         sc->rr = rr;
         sc->iters = k;
         if (rr <= sc->thresh) sc->done = 1;
+    }
+}
+
+/* two totals in one pass (same fixed order as cg_total) */
+__device__ void cg_total2(const double* pa, const double* pb, int nb, double* sm, double& ta, double& tb) {
+    double a = 0.0, b = 0.0;
+    for (int k = threadIdx.x; k < nb; k += CG_THREADS) {
+        a += pa[k];
+        b += pb[k];
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncthreads();
+    if (lane == 0) {
+        sm[warp] = a;
+        sm[CG_THREADS / 32 + warp] = b;
+    }
+    __syncthreads();
+    ta = 0.0;
+    tb = 0.0;
+    for (int w = 0; w < CG_THREADS / 32; w++) {
+        ta += sm[w];
+        tb += sm[CG_THREADS / 32 + w];
+    }
+}
+
+/* The whole iteration in ONE cooperative launch: the two halves of an iteration are separated by grid-wide barriers
+ * instead of kernel boundaries (a solve of ~600 iterations was ~1200 launches), the stop test is taken by every block
+ * from the same sums, so all blocks leave the loop together.  Same arithmetic as cg_direction_kernel / cg_update_kernel. */
+__global__ void __launch_bounds__(CG_THREADS) cg_coop_kernel(int nn, int max_iter, const int* __restrict__ row_ptr, const int* __restrict__ col,
+                                                             const double* __restrict__ val, const double* __restrict__ dinv, double* r, double* p0,
+                                                             double* p1, double* q, double* x, double* part, CgScalars* sc) {
+    /* (r, p, q, x and the partial sums are written by other blocks between the barriers: plain pointers, coherent loads) */
+    namespace cgr = cooperative_groups;
+    cgr::grid_group grid = cgr::this_grid();
+    __shared__ double sm[2 * (CG_THREADS / 32)];
+    const int nb = gridDim.x, stride = gridDim.x * blockDim.x, first = blockIdx.x * blockDim.x + threadIdx.x;
+    const double thresh = sc->thresh;
+    double rz_old = 0.0;
+    int k = 0;
+    for (;; k++) {
+        const int par = k & 1;
+        double rr, rz;
+        cg_total2(part + (CGP_RR0 + par) * CG_MAX_BLOCKS, part + (CGP_RZ0 + par) * CG_MAX_BLOCKS, nb, sm, rr, rz);
+        if (rr <= thresh || k >= max_iter) {
+            if (blockIdx.x == 0 && threadIdx.x == 0) {
+                sc->done = rr <= thresh ? 1 : 0;
+                sc->iters = k;
+                sc->rr = rr;
+            }
+            return;
+        }
+        const double beta = k > 0 ? rz / rz_old : 0.0;
+        const double* p_old = par ? p1 : p0;
+        double* p_new = par ? p0 : p1;
+        double pq = 0.0;
+        for (int i = first; i < nn; i += stride) {
+            double pi = 0.0, qi = 0.0;
+            if (dinv[i] != 0.0) {
+                pi = dinv[i] * r[i] + beta * p_old[i];
+                for (int e = row_ptr[i]; e < row_ptr[i + 1]; e++) {
+                    const int j = col[e];
+                    qi += val[e] * (dinv[j] * r[j] + beta * p_old[j]);
+                }
+                pq += pi * qi;
+            }
+            p_new[i] = pi;
+            q[i] = qi;
+        }
+        pq = cg_block_sum(pq, sm);
+        if (threadIdx.x == 0) part[CGP_PQ * CG_MAX_BLOCKS + blockIdx.x] = pq;
+        grid.sync();
+        const double alpha = rz / cg_total(part + CGP_PQ * CG_MAX_BLOCKS, nb, sm);
+        double rz2 = 0.0, rr2 = 0.0;
+        for (int i = first; i < nn; i += stride) {
+            if (dinv[i] != 0.0) {
+                x[i] = x[i] + alpha * p_new[i];
+                const double ri = r[i] - alpha * q[i];
+                r[i] = ri;
+                rz2 += ri * (dinv[i] * ri);
+                rr2 += ri * ri;
+            }
+        }
+        rz2 = cg_block_sum(rz2, sm);
+        rr2 = cg_block_sum(rr2, sm);
+        if (threadIdx.x == 0) {
+            part[(CGP_RZ0 + (par ^ 1)) * CG_MAX_BLOCKS + blockIdx.x] = rz2;
+            part[(CGP_RR0 + (par ^ 1)) * CG_MAX_BLOCKS + blockIdx.x] = rr2;
+        }
+        grid.sync();
+        rz_old = rz;
     }
 }
 
@@ -792,7 +889,20 @@ extern "C" int pgpu_field_solve(pgpu_ctx* c, int32_t tID, const double* rhs_host
         PG_CUDA(c, cudaMemcpyAsync(c->d_rhs, rhs_host, sizeof(double) * (size_t)nn, cudaMemcpyHostToDevice, c->stream));
         d_rhs = c->d_rhs;
     }
-    const int nb = s->cg_blocks;
+    /* One cooperative launch when the device can hold the whole grid at once (PANTERA_GPU_CG_COOP=0: the
+     * kernel-per-half-iteration path below, also the fall-back).  Fewer, fuller blocks make the grid barriers cheaper. */
+    int nb = s->cg_blocks, coop = 0;
+    {
+        const char* e = getenv("PANTERA_GPU_CG_COOP");
+        int supported = 0, per_sm = 0, sms = 0;
+        cudaDeviceGetAttribute(&supported, cudaDevAttrCooperativeLaunch, c->device);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+        if (supported && !(e && e[0] == '0') &&
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cg_coop_kernel, CG_THREADS, 0) == cudaSuccess && per_sm > 0) {
+            coop = 1;
+            nb = std::min(nb, std::min(2, per_sm) * sms);
+        }
+    }
     CgScalars* sc = (CgScalars*)s->d_cgs;
     double* x = s->d_phi;
     cg_setup_kernel<<<nb, CG_THREADS, 0, c->stream>>>(nn, s->d_is_dir, s->d_dir, s->d_neumann, d_rhs, s->phi_valid ? 1 : 0, s->d_b, x, s->d_p[0], s->d_p[1]);
@@ -803,6 +913,16 @@ extern "C" int pgpu_field_solve(pgpu_ctx* c, int32_t tID, const double* rhs_host
     memset(&h, 0, sizeof(h));
     const int BATCH = 64;
     int k = 0;
+    if (coop) {
+        int nn_ = nn, maxit_ = max_iter;
+        double *p0 = s->d_p[0], *p1 = s->d_p[1];
+        void* args[] = {&nn_, &maxit_, &s->d_row_ptr, &s->d_col, &s->d_val, &s->d_dinv, &s->d_r, &p0, &p1, &s->d_q, &x, &s->d_part, &sc};
+        PG_CUDA(c, cudaLaunchCooperativeKernel((const void*)cg_coop_kernel, dim3((unsigned int)nb), dim3(CG_THREADS), args, 0, c->stream));
+        c->launches++;
+        PG_CUDA(c, cudaMemcpyAsync(&h, sc, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+        PG_CUDA(c, cudaStreamSynchronize(c->stream));
+        k = max_iter; /* (skips the loop below) */
+    }
     while (k < max_iter) {
         const int kend = std::min(k + BATCH, (int)max_iter);
         c->launches += 2 * (kend - k) + 1;

@@ -400,6 +400,74 @@ def emit_tasks_for_group(mesh: mg.Mesh, cfg, species: df.SpeciesTable, mixture, 
 
 
 # ------------------------------------------------------------------------------------------------
+# C2: hypersonic air flow around a cylinder: 2-D triangulated half annulus, free stream emitted from the
+# outer boundary every step (BOUNDARIES_EMIT on the device), diffuse cylinder wall, TCE chemistry + Borgnakke-Larsen
+# ------------------------------------------------------------------------------------------------
+def c2_cylinder(n: int = 10_000_000, ni: int = 250, nj: int = 400, r_in: float = 0.1524, r_out: float = 0.4572,
+                u_inf: float = 7000.0, T_inf: float = 200.0, nrho: float = 1e20, T_wall: float = 1000.0, dt: float = 1e-7,
+                seed: int = 6, with_reactions: bool = True, rng_seed_global: int = 65644) -> Workload:
+    """Polar grid ni (radial) x nj (angle 0..pi) cut into 2 ni nj triangles.  Physical groups: 1 cylinder (diffuse,
+    T_wall), 2 outer boundary (vacuum + one EMIT task per face carrying the free stream N2 0.79 / O2 0.21 at u_inf along
+    +x), 3 and 4 the symmetry line y = 0 behind and ahead of the cylinder (specular).  The domain starts filled with
+    the free stream.  `w.mixtures` / `w.emit_tasks` hold what READINPUT + INITINJECTION would leave in MIXTURES and
+    EMIT_TASKS (apply_sources forwards them)."""
+    sp = load_species("air", ["O2", "N2", "O", "N", "NO"])
+    reactions = df.read_reactions(os.path.join(DATA_DIR, "air.tce"), sp) if with_reactions else []
+    r = np.linspace(r_in, r_out, ni + 1)
+    th = np.linspace(0.0, np.pi, nj + 1)
+    R, TH = np.meshgrid(r, th, indexing="ij")
+    X, Y = R * np.cos(TH), R * np.sin(TH)
+    Y[:, 0] = 0.0
+    Y[:, -1] = 0.0
+    mesh = mg.mapped_quads_to_tris(X, Y, zmin=-0.5, zmax=0.5)
+    mesh.pg_names = {"cylinder": 1, "outer": 2, "wake_axis": 3, "stagnation_axis": 4}
+    vol = float(np.sum(mesh.cell_volumes))
+    fnum = nrho * vol / n
+    cfg = capi.make_config(dims=2, grid_type=capi.UNSTRUCTURED, nx=1, ny=1, xmin=-r_out, xmax=r_out, ymin=0.0, ymax=r_out,
+                           zmin=-0.5, zmax=0.5, dt=dt, fnum=fnum, collision_type=capi.DSMC, bool_z_periodic=1,
+                           rng_seed_global=rng_seed_global, dump_bound_avg_every=0)
+    bcs = dict(particle_bc=[capi.DIFFUSE, capi.VACUUM, capi.SPECULAR, capi.SPECULAR], wall_temp=[T_wall] * 4,
+               acc_n=[1.0] * 4, acc_t=[1.0] * 4)
+    rng = np.random.default_rng(seed)
+    cum = np.cumsum(mesh.cell_volumes)
+    cells0 = np.minimum(np.searchsorted(cum, rng.random(n) * cum[-1]), mesh.nc - 1).astype(np.int64)
+    xyz = sample_in_tets(rng, mesh, cells0)
+    p = new_particles(n)
+    p["X"], p["Y"] = xyz[:, 0], xyz[:, 1]
+    p["Z"] = rng.random(n) - 0.5
+    sid = np.where(rng.random(n) < 0.79, sp.id("N2"), sp.id("O2")).astype(np.int32)
+    v = maxwellian(rng, n, sp.mass[sid - 1], T_inf, u=(u_inf, 0.0, 0.0))
+    p["VX"], p["VY"], p["VZ"] = v[:, 0], v[:, 1], v[:, 2]
+    p["S_ID"] = sid
+    for name, dofs in (("EROT", sp.rotdof), ("EVIB", sp.vibdof)):
+        has = dofs[sid - 1] == 2
+        p[name][has] = rng.exponential(KB * T_inf, size=int(has.sum()))
+    p["DTRIM"] = dt
+    p["IC"] = cells0 + 1
+    w = Workload("C2 air flow around a cylinder (2-D triangles, TCE + Borgnakke-Larsen, free stream emitted at the outer boundary)",
+                 cfg, sp, p, mesh=mesh, bcs=bcs, reactions=reactions)
+    w.mixtures = [[(sp.id("N2"), 0.79), (sp.id("O2"), 0.21)]]
+    w.emit_tasks = emit_tasks_for_group(mesh, cfg, sp, w.mixtures[0], pg=2, nrho=nrho, u=(u_inf, 0.0, 0.0), ttra=T_inf, trot=T_inf, tvib=T_inf)
+    return w
+
+
+def open_channel(w: Workload, nrho: float = 1e20, u: float = 300.0, T0: float = 300.0) -> Workload:
+    """The open variant of a C5 channel workload: vacuum end caps in x, Boundary_emit at x = 0."""
+    w.bcs["particle_bc"][0] = capi.VACUUM
+    w.bcs["particle_bc"][1] = capi.VACUUM
+    w.mixtures = [[(1, 1.0)]]
+    w.emit_tasks = emit_tasks_for_group(w.mesh, w.cfg, w.species, w.mixtures[0], pg=1, nrho=nrho, u=(u, 0.0, 0.0), ttra=T0, trot=T0, tvib=T0)
+    w.name += " (open: vacuum end caps, inflow emitted at x = 0)"
+    return w
+
+
+def apply_sources(lib: capi.Lib, w: Workload):
+    """MIXTURES and EMIT_TASKS of a workload with boundary injection (after `apply`)."""
+    lib.set_mixtures(w.mixtures)
+    lib.set_emit_tasks(w.emit_tasks)
+
+
+# ------------------------------------------------------------------------------------------------
 # bench-scale C5: one x-strip per rank, particles generated in chunks straight into (pinned) AoS records
 # ------------------------------------------------------------------------------------------------
 _PINNED_KEEPALIVE = []

@@ -253,8 +253,10 @@ def test_device_reproduces_a_linear_potential_on_jittered_meshes(gpu, kind, neum
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("coop", ["1", "0"])          # one cooperative launch / one kernel per half iteration
 @pytest.mark.parametrize("case", list(CASES))
-def test_device_field_solve_matches_the_oracle(gpu, oracle, case):
+def test_device_field_solve_matches_the_oracle(gpu, oracle, case, coop, monkeypatch):
+    monkeypatch.setenv("PANTERA_GPU_CG_COOP", coop)
     w, field_bc, fb = CASES[case]()
     rhs = rhs_for(w.mesh)
     for lib in (oracle, gpu):

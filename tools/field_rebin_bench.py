@@ -29,7 +29,9 @@ def main():
                       wall_efield=[0.0, 0.0, 100.0, 0.0])
     rhs = np.random.default_rng(1).standard_normal(w.mesh.nn)
     out = {"what": "pgpu_field_solve", "triangles": w.mesh.nc, "nodes": w.mesh.nn}
-    for label, tol in (("rtol_1e-5", 1e-5), ("rtol_1e-10", 1e-10)):
+    import os
+    for label, tol, coop in (("rtol_1e-5", 1e-5, "1"), ("rtol_1e-10", 1e-10, "1"), ("rtol_1e-5_kernel_per_half_iteration", 1e-5, "0")):
+        os.environ["PANTERA_GPU_CG_COOP"] = coop
         gpu.set_field_bcs(wall_potential=[0.0] * 4, wall_rf_potential=[200.0, 0.0, 0.0, 0.0], rf_frequency=[13.56e6, 0.0, 0.0, 0.0],
                           wall_efield=[0.0, 0.0, 100.0, 0.0])          # (drops the warm start, rebuilds the matrix)
         t0 = time.perf_counter()
