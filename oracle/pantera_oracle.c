@@ -1909,7 +1909,8 @@ int po_reassign_particles_to_cells(po_ctx* w, int64_t* n_removed) {
  * kappa distribution are outside the scope.
  * MT mode: the draws come from the rank's sequential stream in the reference's loop order.  Philox mode (device
  * contract): one stream per (cell | emit task, task, component) -- kind 5 INITIAL_SEED, 6 VOLUME_INJECT, 7
- * BOUNDARIES_EMIT; e0 = cell (0-based) or emit task; e1 = task * 256 + component -- whose draws are consumed in the
+ * BOUNDARIES_EMIT; e0 = cell (0-based) or emit task; e1 = task * 256 + component (kinds 5, 6), component for the count of
+ * an emit task and component + 256 (1 + ip) for its particle ip (kind 7) -- whose draws are consumed in the
  * reference's order for that loop body: the RANDINT draw, then per particle position, MAXWELL, INTERNAL_ENERGY (x2).
  * On rectilinear grids the whole domain is one loop; there the count comes from stream (e0 = 0) and particle ip draws
  * from stream (e0 = 1 + ip).
@@ -2051,6 +2052,7 @@ int po_boundaries_emit(po_ctx* w, int32_t tID) {
             double beta = 0;
             if (tp[4] != 0) beta = 1. / sqrt(2. * KB / m * tp[4]);
             for (int ip = 0; ip < nfs; ip++) {
+                po_rng_stream(w, 7, tID, (uint64_t)it, (uint64_t)(icomp + ((ip + 1) << 8))); /* (device contract: a stream per particle) */
                 double v3[3];
                 po_maxwell(w, 0., 0., 0., tp[4], tp[4], tp[4], m, v3);
                 double erot = po_internal_energy(w, w->rotdof[s_id - 1], tp[5]);

@@ -126,7 +126,7 @@ struct PgFieldState {
     std::vector<double> h_neumann;
     int *d_row_ptr = nullptr, *d_col = nullptr, *d_diag_pos = nullptr, *d_contrib_off = nullptr, *d_contrib = nullptr;
     double *d_val = nullptr, *d_dinv = nullptr, *d_b = nullptr, *d_r = nullptr, *d_q = nullptr, *d_p[2] = {nullptr, nullptr},
-           *d_part = nullptr;
+           *d_part = nullptr, *d_extra = nullptr; /* d_extra: s (two buffers) and p of the cooperative solver */
     void* d_cgs = nullptr;
 };
 static PgFieldState* fld(pgpu_ctx* c) {
@@ -140,7 +140,7 @@ void pg_field_destroy(pgpu_ctx* c) {
     cudaFree(s->d_diag); cudaFree(s->d_lower); cudaFree(s->d_upper); cudaFree(s->d_work); cudaFree(s->d_phi); cudaFree(s->d_cell_eps);
     cudaFree(s->d_row_ptr); cudaFree(s->d_col); cudaFree(s->d_diag_pos); cudaFree(s->d_contrib_off); cudaFree(s->d_contrib);
     cudaFree(s->d_val); cudaFree(s->d_dinv); cudaFree(s->d_b); cudaFree(s->d_r); cudaFree(s->d_q); cudaFree(s->d_p[0]); cudaFree(s->d_p[1]);
-    cudaFree(s->d_part); cudaFree(s->d_cgs);
+    cudaFree(s->d_part); cudaFree(s->d_cgs); cudaFree(s->d_extra);
     /* (d_e is owned by the context's e_field slot once handed over) */
     delete s;
     c->field = nullptr;
@@ -355,6 +355,7 @@ struct CgScalars {
     double bb;     /* |b~|^2, b~ = right-hand side of the free rows with the Dirichlet columns moved over */
     double rr;     /* |r|^2 when the iteration stopped / at the last look */
     int done, iters;
+    int par, pad;
 };
 
 /* element (P, Q) of the stiffness matrix of triangle I, ref: src/fields.f90:332-372 (AREA = CELL_AREAS(I),
@@ -602,71 +603,131 @@ __device__ void cg_total2(const double* pa, const double* pb, int nb, double* sm
     }
 }
 
-/* The whole iteration in ONE cooperative launch: the two halves of an iteration are separated by grid-wide barriers
- * instead of kernel boundaries (a solve of ~600 iterations was ~1200 launches), the stop test is taken by every block
- * from the same sums, so all blocks leave the loop together.  Same arithmetic as cg_direction_kernel / cg_update_kernel. */
+/* The whole solve in ONE cooperative launch with ONE grid-wide barrier per iteration: the conjugate gradient in the
+ * form of Chronopoulos and Gear (both inner products of an iteration are taken together, alpha follows from a
+ * recurrence), with the vector updates folded into the row loop of the next matrix product.  Given alpha, beta:
+ *     s' = w + beta s      r' = r - alpha s'      p = u + beta p      x = x + alpha p        (u = r / diag)
+ *     w' = A u'  with  u'_j = (r_j - alpha (w_j + beta s_j)) / diag_j  recomputed for the neighbours j of the row
+ *     gamma' = r'.u'   delta = w'.u'   |r'|^2  ->  barrier  ->  beta' = gamma'/gamma,  alpha' = gamma'/(delta - beta' gamma'/alpha)
+ * r, w, s are double-buffered (a row reads its neighbours' old values while their owners write the new ones), and so
+ * are the per-block partial sums (a fast block may start the next iteration while a slow one still adds up this
+ * one's).  The first pass runs with alpha = beta = 0: it leaves x and r alone and produces w0 = A u0, gamma0, delta0.
+ * Every block takes the stop decision from the same sums, so all blocks leave the loop together.
+ * (The kernel-per-half-iteration path below keeps the textbook recurrences: 2 launches per iteration.) */
+enum { CGQ_G = 0, CGQ_D = 1, CGQ_R = 2 }; /* partial rows: 2 parities x {gamma, delta, |r|^2} */
 __global__ void __launch_bounds__(CG_THREADS) cg_coop_kernel(int nn, int max_iter, const int* __restrict__ row_ptr, const int* __restrict__ col,
-                                                             const double* __restrict__ val, const double* __restrict__ dinv, double* r, double* p0,
-                                                             double* p1, double* q, double* x, double* part, CgScalars* sc) {
-    /* (r, p, q, x and the partial sums are written by other blocks between the barriers: plain pointers, coherent loads) */
+                                                             const double* __restrict__ val, const double* __restrict__ dinv, double* r0,
+                                                             double* r1, double* w0, double* w1, double* s0, double* s1, double* p, double* x,
+                                                             double* part, CgScalars* sc) {
+    /* (r, w, s, p, x and the partial sums are written by other blocks between the barriers: plain pointers, coherent loads) */
     namespace cgr = cooperative_groups;
     cgr::grid_group grid = cgr::this_grid();
-    __shared__ double sm[2 * (CG_THREADS / 32)];
+    __shared__ double sm[3 * (CG_THREADS / 32)];
     const int nb = gridDim.x, stride = gridDim.x * blockDim.x, first = blockIdx.x * blockDim.x + threadIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const double thresh = sc->thresh;
-    double rz_old = 0.0;
-    int k = 0;
-    for (;; k++) {
-        const int par = k & 1;
-        double rr, rz;
-        cg_total2(part + (CGP_RR0 + par) * CG_MAX_BLOCKS, part + (CGP_RZ0 + par) * CG_MAX_BLOCKS, nb, sm, rr, rz);
-        if (rr <= thresh || k >= max_iter) {
+    double alpha = 0.0, beta = 0.0, gamma_old = 0.0;
+    for (int pass = 0;; pass++) { /* pass 0 is the set-up pass; pass k >= 1 applies the k-th update of x */
+        const int par = pass & 1;
+        const double* r_old = par ? r1 : r0;
+        const double* w_old = par ? w1 : w0;
+        const double* s_old = par ? s1 : s0;
+        double* r_new = par ? r0 : r1;
+        double* w_new = par ? w0 : w1;
+        double* s_new = par ? s0 : s1;
+        double g = 0.0, dl = 0.0, rr = 0.0;
+        for (int i = first; i < nn; i += stride) {
+            double ri = 0.0, wi = 0.0, si = 0.0;
+            const double di = dinv[i];
+            if (di != 0.0) {
+                si = w_old[i] + beta * s_old[i];
+                const double pi = di * r_old[i] + beta * p[i];
+                p[i] = pi;
+                x[i] = x[i] + alpha * pi;
+                ri = r_old[i] - alpha * si;
+                for (int e = row_ptr[i]; e < row_ptr[i + 1]; e++) {
+                    const int j = col[e];
+                    wi += val[e] * (dinv[j] * (r_old[j] - alpha * (w_old[j] + beta * s_old[j])));
+                }
+                const double ui = di * ri;
+                g += ri * ui;
+                dl += wi * ui;
+                rr += ri * ri;
+            }
+            r_new[i] = ri;
+            w_new[i] = wi;
+            s_new[i] = si;
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            g += __shfl_xor_sync(0xffffffffu, g, o);
+            dl += __shfl_xor_sync(0xffffffffu, dl, o);
+            rr += __shfl_xor_sync(0xffffffffu, rr, o);
+        }
+        if (lane == 0) {
+            sm[warp] = g;
+            sm[CG_THREADS / 32 + warp] = dl;
+            sm[2 * (CG_THREADS / 32) + warp] = rr;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double a = 0.0, b = 0.0, c3 = 0.0;
+            for (int w = 0; w < CG_THREADS / 32; w++) {
+                a += sm[w];
+                b += sm[CG_THREADS / 32 + w];
+                c3 += sm[2 * (CG_THREADS / 32) + w];
+            }
+            double* row = part + (size_t)(3 * par) * CG_MAX_BLOCKS;
+            row[CGQ_G * CG_MAX_BLOCKS + blockIdx.x] = a;
+            row[CGQ_D * CG_MAX_BLOCKS + blockIdx.x] = b;
+            row[CGQ_R * CG_MAX_BLOCKS + blockIdx.x] = c3;
+        }
+        grid.sync();
+        /* totals: every block adds the same partial sums in the same order */
+        {
+            const double* row = part + (size_t)(3 * par) * CG_MAX_BLOCKS;
+            double a = 0.0, b = 0.0, c3 = 0.0;
+            for (int k = threadIdx.x; k < nb; k += CG_THREADS) {
+                a += row[CGQ_G * CG_MAX_BLOCKS + k];
+                b += row[CGQ_D * CG_MAX_BLOCKS + k];
+                c3 += row[CGQ_R * CG_MAX_BLOCKS + k];
+            }
+            for (int o = 16; o > 0; o >>= 1) {
+                a += __shfl_xor_sync(0xffffffffu, a, o);
+                b += __shfl_xor_sync(0xffffffffu, b, o);
+                c3 += __shfl_xor_sync(0xffffffffu, c3, o);
+            }
+            __syncthreads(); /* (sm of the block sums above has been read by thread 0) */
+            if (lane == 0) {
+                sm[warp] = a;
+                sm[CG_THREADS / 32 + warp] = b;
+                sm[2 * (CG_THREADS / 32) + warp] = c3;
+            }
+            __syncthreads();
+            g = 0.0; dl = 0.0; rr = 0.0;
+            for (int w = 0; w < CG_THREADS / 32; w++) {
+                g += sm[w];
+                dl += sm[CG_THREADS / 32 + w];
+                rr += sm[2 * (CG_THREADS / 32) + w];
+            }
+            __syncthreads(); /* (before the next pass overwrites sm) */
+        }
+        if (rr <= thresh || pass >= max_iter) {
             if (blockIdx.x == 0 && threadIdx.x == 0) {
                 sc->done = rr <= thresh ? 1 : 0;
-                sc->iters = k;
+                sc->iters = pass;
                 sc->rr = rr;
+                sc->par = par ^ 1; /* the buffer that holds the final r */
             }
             return;
         }
-        const double beta = k > 0 ? rz / rz_old : 0.0;
-        const double* p_old = par ? p1 : p0;
-        double* p_new = par ? p0 : p1;
-        double pq = 0.0;
-        for (int i = first; i < nn; i += stride) {
-            double pi = 0.0, qi = 0.0;
-            if (dinv[i] != 0.0) {
-                pi = dinv[i] * r[i] + beta * p_old[i];
-                for (int e = row_ptr[i]; e < row_ptr[i + 1]; e++) {
-                    const int j = col[e];
-                    qi += val[e] * (dinv[j] * r[j] + beta * p_old[j]);
-                }
-                pq += pi * qi;
-            }
-            p_new[i] = pi;
-            q[i] = qi;
+        if (pass == 0) {
+            beta = 0.0;
+            alpha = g / dl;
+        } else {
+            beta = g / gamma_old;
+            alpha = g / (dl - beta * g / alpha);
         }
-        pq = cg_block_sum(pq, sm);
-        if (threadIdx.x == 0) part[CGP_PQ * CG_MAX_BLOCKS + blockIdx.x] = pq;
-        grid.sync();
-        const double alpha = rz / cg_total(part + CGP_PQ * CG_MAX_BLOCKS, nb, sm);
-        double rz2 = 0.0, rr2 = 0.0;
-        for (int i = first; i < nn; i += stride) {
-            if (dinv[i] != 0.0) {
-                x[i] = x[i] + alpha * p_new[i];
-                const double ri = r[i] - alpha * q[i];
-                r[i] = ri;
-                rz2 += ri * (dinv[i] * ri);
-                rr2 += ri * ri;
-            }
-        }
-        rz2 = cg_block_sum(rz2, sm);
-        rr2 = cg_block_sum(rr2, sm);
-        if (threadIdx.x == 0) {
-            part[(CGP_RZ0 + (par ^ 1)) * CG_MAX_BLOCKS + blockIdx.x] = rz2;
-            part[(CGP_RR0 + (par ^ 1)) * CG_MAX_BLOCKS + blockIdx.x] = rr2;
-        }
-        grid.sync();
-        rz_old = rz;
+        gamma_old = g;
     }
 }
 
@@ -811,6 +872,7 @@ static int build_cg(pgpu_ctx* c, PgFieldState* s) {
     PG_CUDA(c, dalloc(&s->d_val, (size_t)nnz));
     for (double** p : {&s->d_dinv, &s->d_b, &s->d_r, &s->d_q, &s->d_p[0], &s->d_p[1], &s->d_dir, &s->d_phi}) PG_CUDA(c, dalloc(p, (size_t)nn + 1));
     PG_CUDA(c, dalloc(&s->d_part, (size_t)CGP_ROWS * CG_MAX_BLOCKS));
+    PG_CUDA(c, dalloc(&s->d_extra, 3 * ((size_t)nn + 1)));
     cudaFree(s->d_cgs);
     s->d_cgs = nullptr;
     PG_CUDA(c, cudaMalloc(&s->d_cgs, sizeof(CgScalars)));
@@ -914,9 +976,12 @@ extern "C" int pgpu_field_solve(pgpu_ctx* c, int32_t tID, const double* rhs_host
     const int BATCH = 64;
     int k = 0;
     if (coop) {
+        /* r: {d_r (filled by cg_residual_kernel), d_q}; w: {d_p[0] (zero), d_p[1]}; s: d_extra[0] (zero), d_extra[1]; p: d_extra[2] (zero) */
         int nn_ = nn, maxit_ = max_iter;
-        double *p0 = s->d_p[0], *p1 = s->d_p[1];
-        void* args[] = {&nn_, &maxit_, &s->d_row_ptr, &s->d_col, &s->d_val, &s->d_dinv, &s->d_r, &p0, &p1, &s->d_q, &x, &s->d_part, &sc};
+        double *r0 = s->d_r, *r1 = s->d_q, *w0 = s->d_p[0], *w1 = s->d_p[1], *s0 = s->d_extra, *s1 = s->d_extra + ((size_t)nn + 1),
+               *pp = s->d_extra + 2 * ((size_t)nn + 1);
+        PG_CUDA(c, cudaMemsetAsync(s->d_extra, 0, sizeof(double) * 3 * ((size_t)nn + 1), c->stream));
+        void* args[] = {&nn_, &maxit_, &s->d_row_ptr, &s->d_col, &s->d_val, &s->d_dinv, &r0, &r1, &w0, &w1, &s0, &s1, &pp, &x, &s->d_part, &sc};
         PG_CUDA(c, cudaLaunchCooperativeKernel((const void*)cg_coop_kernel, dim3((unsigned int)nb), dim3(CG_THREADS), args, 0, c->stream));
         c->launches++;
         PG_CUDA(c, cudaMemcpyAsync(&h, sc, sizeof(h), cudaMemcpyDeviceToHost, c->stream));

@@ -4,10 +4,11 @@
  *
  * On the host these are the step right before the hot path: with open boundaries every timestep ends in a
  * host-side RNG loop and an H2D append.  Here one thread owns one loop body of the reference -- a (cell, task,
- * mixture component) for the volume sources, an (emit task, component) for the boundary source -- draws its number of
- * particles (RANDINT / the fractional-part rule) and creates them straight in the append region of the store.
- * Random numbers: Philox streams of kind 5 (seed), 6 (volume inject), 7 (emit), keyed e0 = cell | emit task,
- * e1 = task*256 + component, consumed in the order of the reference's loop body; the oracle's rng_mode 1 follows the
+ * mixture component) for the volume sources -- and one warp an (emit task, component) of the boundary source; it draws
+ * the number of particles (RANDINT / the fractional-part rule) and creates them straight in the append region of the store.
+ * Random numbers: Philox streams of kind 5 (seed), 6 (volume inject), keyed e0 = cell, e1 = task*256 + component, and 7
+ * (emit), keyed e0 = emit task, e1 = component for the count and e1 = component + 256 (1 + ip) for particle ip;
+ * consumed in the order of the reference's loop body; the oracle's rng_mode 1 follows the
  * same contract, so the created particles can be compared value for value (as a set: creation order is the order of
  * the append cursor).  COLOCATED_ELECTRONS, BOOL_INJECT_FROM_FILE and the kappa distribution are not implemented.
  */
@@ -178,12 +179,15 @@ __global__ void __launch_bounds__(128) domain_source_kernel(const __grid_constan
     append(d, xp, yp, zp, v3, erot, evib, sid, cid, d.dt);
 }
 
-/* BOUNDARIES_EMIT: one thread per (emit task, component) */
+/* BOUNDARIES_EMIT: one WARP per (emit task, component).  The count NFS (with its rounding draw) comes from the stream
+ * (task, component); particle ip then has its own stream (task, component + 256 (1 + ip)), so the lanes of the warp
+ * create the particles of the task side by side (a face of the C2 free-stream boundary emits ~55 particles per step and
+ * component: one thread per task walked them one after the other, 0.93 ms per step for 800 tasks) */
 template <int DIMS>
 __global__ void __launch_bounds__(128) emit_kernel(const __grid_constant__ PgDev d, const __grid_constant__ PgInject q,
                                                    const PgEmitTask* __restrict__ tasks, const double* __restrict__ nfs_all, int nslot,
                                                    const int* __restrict__ slot_task, const int* __restrict__ slot_comp) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (t >= nslot) return;
     const int it = slot_task[t], icomp = slot_comp[t];
     const PgEmitTask tk = tasks[it];
@@ -218,7 +222,8 @@ __global__ void __launch_bounds__(128) emit_kernel(const __grid_constant__ PgDev
     if (nfs_x - (double)nfs >= g.rf()) nfs = nfs + 1;
     double beta = 0;
     if (tk.ttra != 0) beta = 1. / sqrt(2. * PG_KB / m * tk.ttra);
-    for (int ip = 0; ip < nfs; ip++) {
+    for (int ip = lane; ip < nfs; ip += 32) {
+        g.init(d.seed_local, 7, d.tID, (unsigned long long)it, (unsigned long long)(icomp + ((ip + 1) << 8)));
         double v3[3];
         pg_maxwell(g, 0., 0., 0., tk.ttra, tk.ttra, tk.ttra, m, v3);
         const double erot = pg_internal_energy(g, d.rotdof[sid - 1], tk.trot);
@@ -529,7 +534,7 @@ extern "C" int pgpu_boundaries_emit(pgpu_ctx* c, int32_t tID) {
     if ((rc = begin_create(c, s->expected[2], true))) return rc;
     c->dev.tID = tID;
     PgInject q = make_inject(c, s);
-    const unsigned int blocks = (unsigned int)((s->nslot[2] + 127) / 128);
+    const unsigned int blocks = (unsigned int)(((long long)s->nslot[2] * 32 + 127) / 128);
     if (c->mesh_dims == 1) emit_kernel<1><<<blocks, 128, 0, c->stream>>>(c->dev, q, s->d_emit, s->d_emit_nfs, s->nslot[2], s->d_slot_task[2], s->d_slot_comp[2]);
     else if (c->mesh_dims == 2) emit_kernel<2><<<blocks, 128, 0, c->stream>>>(c->dev, q, s->d_emit, s->d_emit_nfs, s->nslot[2], s->d_slot_task[2], s->d_slot_comp[2]);
     else emit_kernel<3><<<blocks, 128, 0, c->stream>>>(c->dev, q, s->d_emit, s->d_emit_nfs, s->nslot[2], s->d_slot_task[2], s->d_slot_comp[2]);
