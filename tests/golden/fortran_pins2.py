@@ -1,0 +1,465 @@
+#!/usr/bin/env python
+"""Independent pins, second set (round 2, after VERDICT r01 asked for more of them): single events of the hot path
+evaluated in PLAIN PYTHON from the Fortran source of the reference (file:line at every routine), NOT from
+oracle/pantera_oracle.c.  Same conventions as tests/golden/fortran_pins.py: IEEE doubles, no FMA, left-to-right like
+gfortran without -ffast-math, `x*x` for `X**2`; random draws supplied as a script.
+
+    python tests/golden/fortran_pins2.py        # regenerates tests/golden/fortran_pins2.json
+
+Covered reference lines:
+  axi_walk       src/timecycle.f90:1173-1253 (the axisymmetric edge test of unstructured grids: vertical edges, the
+                 hyperboloid quadratic with its root filters, the trial MOVE_PARTICLE forth and back -- which is not an
+                 exact inverse and leaves its rounding in the particle --, the missing ordering check between the two
+                 roots), :1308-1343 (move, neighbour), :1433-1443 (specular), :1648-1657 (hop / final flight), :2297-2324
+                 (MOVE_PARTICLE, axisymmetric); edge geometry src/grid_and_partition.f90:1401-1418
+  structured_walk  src/timecycle.f90:1072-1081 (NORMX, NORMY, XW, YW), :1659-1661, :1735-1752 (box sides, non-axisymmetric: a
+                 strict '>' here, unlike the '>=' of the unstructured faces), :1841-1863 (interior walls: one-sided, hit
+                 point inside the segment), :1868-1935 (periodic shift, specular flip, diffuse re-emission with BOUNDTEMP),
+                 :1937-1965 (specular wall: rf() is drawn even when the wall is not porous; porous removal), :2015-2019,
+                 :2044-2054 (Z wrap), :2104-2106 + src/grid_and_partition.f90:46-72 (re-index on the uniform grid)
+  dsmc_order     src/collisions.f90:37-149 (DSMC_COLLISIONS: INDALL is a stable counting sort by cell, cells are visited in
+                 ascending order), :259-271 (INT(NPC*rf()) picks into that order)
+  cell_nonuniform  src/grid_and_partition.f90:34-96 (CELL_FROM_POSITION on RECTILINEAR_NONUNIFORM grids), src/tools.f90:1499-1535
+                 (BINARY_SEARCH; a value equal to the last array element never leaves the reference's loop: not pinned)
+"""
+import json
+import math
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import fortran_pins as fp1  # noqa: E402  (species tables, VSS pair tables, vss_collis_cell of the first set)
+
+hx = fp1.hx
+Script = fp1.Script
+TOL = 1.0e-15  # src/timecycle.f90:1068
+
+
+# ------------------------------------------------------------------------------------------ axisymmetric triangles
+def tri_mesh():
+    """3 x 2 quads cut into 12 triangles over [0, 0.09] x [0.01, 0.05] (y is the radius; no cell touches the axis),
+    interior nodes displaced so that no edge is vertical or horizontal except on the boundary.  EDGE_NORMAL and
+    CELL_EDGES_LEN as src/grid_and_partition.f90:1401-1418 (edge J joins local nodes J and J mod 3 + 1).
+    Physical groups: 1 x = 0, 2 x = 0.09, 3 y = 0.01, 4 y = 0.05."""
+    nx, ny = 3, 2
+    xs, ys = [0.0, 0.03, 0.06, 0.09], [0.01, 0.03, 0.05]
+    nodes = []
+    for i in range(nx + 1):
+        for j in range(ny + 1):
+            x, y = xs[i], ys[j]
+            if 0 < i < nx and 0 < j < ny:
+                x += 0.004 * (1 if i % 2 else -1)
+                y += 0.003
+            nodes.append([x, y])
+    nid = lambda i, j: i * (ny + 1) + j + 1
+    cells = []
+    for i in range(nx):
+        for j in range(ny):
+            a, b, c, d = nid(i, j), nid(i + 1, j), nid(i + 1, j + 1), nid(i, j + 1)
+            cells.append([a, b, c])
+            cells.append([a, c, d])
+    normal, length = [], []
+    for cn in cells:
+        nrm, ln = [], []
+        for j in range(3):
+            x1, y1 = nodes[cn[j] - 1]
+            x2, y2 = nodes[cn[(j + 1) % 3] - 1]
+            le = math.sqrt((y2 - y1) * (y2 - y1) + (x2 - x1) * (x2 - x1))
+            ln.append(le)
+            nrm.append([(y2 - y1) / le, (x1 - x2) / le])
+        normal.append(nrm)
+        length.append(ln)
+    edge_owner = {}
+    for c, cn in enumerate(cells):
+        for j in range(3):
+            key = tuple(sorted((cn[j], cn[(j + 1) % 3])))
+            edge_owner.setdefault(key, []).append((c, j))
+    neighbors = [[-1] * 3 for _ in cells]
+    faces_pg = [[-1] * 3 for _ in cells]
+    for key, own in edge_owner.items():
+        if len(own) == 2:
+            (c1, j1), (c2, j2) = own
+            neighbors[c1][j1] = c2 + 1
+            neighbors[c2][j2] = c1 + 1
+        else:
+            (c1, j1), = own
+            (xa, ya), (xb, yb) = nodes[key[0] - 1], nodes[key[1] - 1]
+            if xa == 0.0 and xb == 0.0:
+                pg = 1
+            elif xa == 0.09 and xb == 0.09:
+                pg = 2
+            elif ya == 0.01 and yb == 0.01:
+                pg = 3
+            else:
+                pg = 4
+            faces_pg[c1][j1] = pg
+    return dict(nodes=nodes, cells=cells, normal=normal, edges_len=length, neighbors=neighbors, faces_pg=faces_pg)
+
+
+def move_axi(q, time):
+    """MOVE_PARTICLE, axisymmetric branch, src/timecycle.f90:2311-2324 (in place)."""
+    q["x"] = q["x"] + q["vx"] * time
+    q["z"] = 0.0
+    r = math.sqrt((q["y"] + q["vy"] * time) * (q["y"] + q["vy"] * time) + (q["vz"] * time) * (q["vz"] * time))
+    sintheta = q["vz"] * time / r
+    costheta = math.copysign(math.sqrt(1.0 - sintheta * sintheta), q["y"] + q["vy"] * time)
+    q["y"] = r
+    vz, vy = q["vz"], q["vy"]
+    q["vz"] = costheta * vz - sintheta * vy
+    q["vy"] = sintheta * vz + costheta * vy
+
+
+def advect_axi(mesh, p, dt):
+    """One particle through ADVECT on the axisymmetric triangle mesh, every boundary specular.
+    src/timecycle.f90:1166-1253, 1308-1343, 1433-1443, 1648-1657."""
+    q = dict(x=p["x"], y=p["y"], z=p["z"], vx=p["vx"], vy=p["vy"], vz=p["vz"])
+    ic = p["ic"]
+    dtrim = dt
+    trace = []
+    ntrial = 0
+    while dtrim > 0.0:
+        dtcoll = dtrim
+        boundcoll = -1
+        for i in range(1, 4):
+            edge_x1, edge_y1 = mesh["nodes"][mesh["cells"][ic - 1][i - 1] - 1]
+            n1, n2 = mesh["normal"][ic - 1][i - 1]
+            test = []
+            if abs(n2) < 1.0e-10:                                   # vertical wall, :1181-1189
+                sol1 = (edge_x1 - q["x"]) / q["vx"]
+                if sol1 >= 0 and sol1 < dtcoll:
+                    test = [sol1]
+            else:                                                   # :1191-1227
+                alpha = -n1 / n2
+                beta = (q["x"] - edge_x1) * alpha
+                coefa = q["vy"] * q["vy"] + q["vz"] * q["vz"] - alpha * alpha * (q["vx"] * q["vx"])
+                coefb = q["y"] * q["vy"] - (beta + edge_y1) * alpha * q["vx"]
+                coefc = q["y"] * q["y"] - (beta + edge_y1) * (beta + edge_y1)
+                delta = coefb * coefb - coefa * coefc
+                if delta >= 0:
+                    sol1 = (-coefb - math.sqrt(delta)) / coefa
+                    sol2 = (-coefb + math.sqrt(delta)) / coefa
+                    ok1 = sol1 >= -TOL and sol1 < dtcoll and beta + alpha * q["vx"] * sol1 + edge_y1 >= 0
+                    ok2 = sol2 >= -TOL and sol2 < dtcoll and beta + alpha * q["vx"] * sol2 + edge_y1 >= 0
+                    if ok1:
+                        if ok2:
+                            test = [sol1, sol2] if sol1 <= sol2 else [sol2, sol1]
+                        else:
+                            test = [sol1]
+                    elif ok2:
+                        test = [sol2]
+            for t in test:                                          # :1233-1251 (no comparison of TEST(SOL) with DTCOLL here)
+                move_axi(q, t)
+                ntrial += 1
+                if (q["vx"] * n1 + q["vy"] * n2) > 0:
+                    le = mesh["edges_len"][ic - 1][i - 1]
+                    colldist = -n2 * (q["x"] - edge_x1) / le + n1 * (q["y"] - edge_y1) / le
+                    if colldist >= 0 and colldist <= 1:
+                        dtcoll = t
+                        boundcoll = i
+                move_axi(q, -t)
+        if boundcoll != -1:
+            move_axi(q, dtcoll)
+            dtrim = dtrim - dtcoll
+            trace.append([ic, boundcoll])
+            neighbor = mesh["neighbors"][ic - 1][boundcoll - 1]
+            if neighbor == -1:
+                fn = [-mesh["normal"][ic - 1][boundcoll - 1][0], -mesh["normal"][ic - 1][boundcoll - 1][1], -0.0]
+                vdotn = q["vx"] * fn[0] + q["vy"] * fn[1] + q["vz"] * fn[2]
+                q["vx"] = q["vx"] - 2.0 * vdotn * fn[0]
+                q["vy"] = q["vy"] - 2.0 * vdotn * fn[1]
+                q["vz"] = q["vz"] - 2.0 * vdotn * fn[2]
+            else:
+                ic = neighbor
+        else:
+            move_axi(q, dtrim)
+            dtrim = 0.0
+    q["ic"] = ic
+    return q, trace, ntrial
+
+
+# ------------------------------------------------------------------------------------------ rectilinear grids
+def advect_structured(g, walls, species, parts, dt, rf):
+    """ADVECT on a uniform rectilinear 2-D grid, not axisymmetric, particles in store order sharing ONE rf() stream.
+    g: xmin, xmax, ymin, ymax, zmin, zmax, nx, ny, periodic[4], specular[4], diffuse[4], boundtemp, z_periodic.
+    walls: dicts x1, y1, x2, y2, normx, normy, specular, diffuse, porous, transm, temp.  Returns per particle the final
+    state (or None when it was removed) and its events."""
+    normx, normy = [1.0, -1.0, 0.0, 0.0], [0.0, 0.0, 1.0, -1.0]
+    xw = [g["xmin"], g["xmax"], g["xmin"], g["xmax"]]
+    yw = [g["ymax"], g["ymin"], g["ymin"], g["ymax"]]
+    out = []
+    for p in parts:
+        q = dict(p)
+        dtrim = dt
+        removed = False
+        events = []
+        while dtrim > 0.0:
+            dtcoll = dtrim
+            boundcoll = -1
+            for i in range(4):
+                vn = -(q["vx"] * normx[i] + q["vy"] * normy[i])
+                dx = (q["x"] - xw[i]) * normx[i] + (q["y"] - yw[i]) * normy[i]
+                if vn >= 0.0 and vn * dtcoll > dx:
+                    dtcoll = dx / vn
+                    boundcoll = i + 1
+            wallcoll = -1
+            for k, w in enumerate(walls):
+                vn = -(q["vx"] * w["normx"] + q["vy"] * w["normy"])
+                dx = (q["x"] - w["x1"]) * w["normx"] + (q["y"] - w["y1"]) * w["normy"]
+                if dx >= 0.0 and vn * dtcoll >= dx:
+                    cand = dx / vn
+                    xcoll = q["x"] + q["vx"] * cand
+                    ycoll = q["y"] + q["vy"] * cand
+                    colldist = ((xcoll - w["x1"]) * (w["x2"] - w["x1"]) + (ycoll - w["y1"]) * (w["y2"] - w["y1"])) / \
+                               ((w["x2"] - w["x1"]) * (w["x2"] - w["x1"]) + (w["y2"] - w["y1"]) * (w["y2"] - w["y1"]))
+                    if colldist >= 0 and colldist <= 1:
+                        boundcoll = -1
+                        wallcoll = k + 1
+                        dtcoll = cand
+
+            def move(t):
+                q["x"] = q["x"] + q["vx"] * t
+                q["y"] = q["y"] + q["vy"] * t
+                q["z"] = q["z"] + q["vz"] * t
+
+            if boundcoll != -1:
+                events.append(["side", boundcoll])
+                if g["periodic"][boundcoll - 1]:
+                    move(dtcoll)
+                    if boundcoll == 1:
+                        q["x"] = q["x"] + g["xmax"] - g["xmin"]
+                    elif boundcoll == 2:
+                        q["x"] = q["x"] - g["xmax"] + g["xmin"]
+                    elif boundcoll == 3:
+                        q["y"] = q["y"] + g["ymax"] - g["ymin"]
+                    else:
+                        q["y"] = q["y"] - g["ymax"] + g["ymin"]
+                    dtrim = dtrim - dtcoll
+                elif g["specular"][boundcoll - 1]:
+                    move(dtcoll)
+                    if boundcoll <= 2:
+                        q["vx"] = -q["vx"]
+                    else:
+                        q["vy"] = -q["vy"]
+                    dtrim = dtrim - dtcoll
+                elif g["diffuse"][boundcoll - 1]:
+                    move(dtcoll)
+                    dtrim = dtrim - dtcoll
+                    sp = species[q["sid"]]
+                    _, v_perp, vz = fp1.maxwell(rf, 0.0, 0.0, 0.0, g["boundtemp"], g["boundtemp"], g["boundtemp"], sp["mass"])
+                    erot = fp1.internal_energy(rf, sp["rotdof"], g["boundtemp"])
+                    evib = fp1.internal_energy(rf, sp["vibdof"], g["boundtemp"])
+                    v_norm = fp1.flx(rf, 0.0, g["boundtemp"], sp["mass"])
+                    q["vx"] = v_norm * normx[boundcoll - 1] - v_perp * normy[boundcoll - 1]
+                    q["vy"] = v_perp * normx[boundcoll - 1] + v_norm * normy[boundcoll - 1]
+                    q["vz"] = vz
+                    q["erot"], q["evib"] = erot, evib
+                else:
+                    removed = True
+                    dtrim = 0.0
+            elif wallcoll != -1:
+                w = walls[wallcoll - 1]
+                events.append(["wall", wallcoll])
+                if w["specular"]:
+                    rfp = rf()
+                    if w["porous"] and rfp <= w["transm"]:
+                        removed = True
+                        dtrim = 0.0
+                    else:
+                        move(dtcoll)
+                        vdotn = q["vx"] * w["normx"] + q["vy"] * w["normy"]
+                        q["vx"] = q["vx"] - 2.0 * vdotn * w["normx"]
+                        q["vy"] = q["vy"] - 2.0 * vdotn * w["normy"]
+                        dtrim = dtrim - dtcoll
+                elif w["diffuse"]:
+                    rfp = rf()
+                    if w["porous"] and rfp <= w["transm"]:
+                        removed = True
+                        dtrim = 0.0
+                    else:
+                        move(dtcoll)
+                        dtrim = dtrim - dtcoll
+                        sp = species[q["sid"]]
+                        _, v_perp, vz = fp1.maxwell(rf, 0.0, 0.0, 0.0, w["temp"], w["temp"], w["temp"], sp["mass"])
+                        erot = fp1.internal_energy(rf, sp["rotdof"], w["temp"])
+                        evib = fp1.internal_energy(rf, sp["vibdof"], w["temp"])
+                        v_norm = fp1.flx(rf, 0.0, w["temp"], sp["mass"])
+                        q["vx"] = v_norm * w["normx"] - v_perp * w["normy"]
+                        q["vy"] = v_perp * w["normx"] + v_norm * w["normy"]
+                        q["vz"] = vz
+                        q["erot"], q["evib"] = erot, evib
+                else:
+                    removed = True
+                    dtrim = 0.0
+            else:
+                move(dtrim)
+                dtrim = 0.0
+        if g["z_periodic"]:
+            while q["z"] > g["zmax"]:
+                q["z"] = g["zmin"] + (q["z"] - g["zmax"])
+            while q["z"] < g["zmin"]:
+                q["z"] = g["zmax"] + (q["z"] - g["zmin"])
+        if removed:
+            out.append((None, events))
+        else:
+            ddx = (g["xmax"] - g["xmin"]) / g["nx"]
+            ddy = (g["ymax"] - g["ymin"]) / g["ny"]
+            q["ic"] = int((q["x"] - g["xmin"]) / ddx) + g["nx"] * int((q["y"] - g["ymin"]) / ddy) + 1
+            out.append((q, events))
+    return out
+
+
+# ------------------------------------------------------------------------------------------ DSMC_COLLISIONS order
+def dsmc_collisions(species, names, parts, cells, ncells, sigmamax, fnum, dt, vol, rf):
+    """src/collisions.f90:37-149: INDALL(IOFALL(JC) + NPCALL(JC)) = JP for JP = 1..NP_PROC (stable in store order), then
+    VSS_COLLIS cell by cell in ascending JC for the cells holding more than one particle.  `parts` in store order,
+    cells[k] = IC of particle k.  Returns TIMESTEP_COLL."""
+    indall = {jc: [] for jc in range(1, ncells + 1)}
+    for jp, jc in enumerate(cells):
+        indall[jc].append(jp)
+    total = 0
+    for jc in range(1, ncells + 1):
+        if len(indall[jc]) > 1:
+            local = [parts[jp] for jp in indall[jc]]          # VSS_COLLIS indexes INDALL(IOFALL(JC) + INT(NPC*rf()))
+            nc, nr, created = fp1.vss_collis_cell(species, names, local, [], sigmamax, fnum, dt, vol, rf)
+            assert not created
+            total += nc
+    return total
+
+
+# ------------------------------------------------------------------------------------------ CELL_FROM_POSITION
+def binary_search(value, array):
+    """BINARY_SEARCH, src/tools.f90:1499-1535 (1-based INDEX; -1 outside the array)."""
+    lo, hi = 1, len(array)
+    if value < array[lo - 1] or value > array[hi - 1]:
+        return -1
+    if hi == lo + 1:
+        return lo
+    while True:
+        index = (lo + hi) // 2
+        if array[index - 1] <= value:
+            if array[index] > value:
+                return index
+            lo = index
+        else:
+            if array[index - 2] <= value:
+                return index - 1
+            hi = index
+
+
+def cell_from_position_nonuniform(xp, yp, xcoord, ycoord, nx):
+    """src/grid_and_partition.f90:62-90 (RECTILINEAR_NONUNIFORM): XCELL = BINARY_SEARCH(XP, XCOORD), likewise Y;
+    IDCELL = XCELL + NX*(YCELL-1)."""
+    return binary_search(xp, xcoord) + nx * (binary_search(yp, ycoord) - 1)
+
+
+def pdict(q):
+    return {k: (hx(v) if isinstance(v, float) else v) for k, v in q.items()}
+
+
+def main():
+    out = {}
+    # ---- axi_walk
+    mesh = tri_mesh()
+    out["tri_mesh"] = mesh
+    dt = 6.0e-5
+
+    def locate(x, y):
+        for c, cn in enumerate(mesh["cells"]):
+            ok = True
+            for j in range(3):
+                x1, y1 = mesh["nodes"][cn[j] - 1]
+                n1, n2 = mesh["normal"][c][j]
+                if (x - x1) * n1 + (y - y1) * n2 > 0:
+                    ok = False
+            if ok:
+                return c + 1
+        raise AssertionError((x, y))
+
+    starts = [
+        dict(x=0.012, y=0.018, z=0.0, vx=900.0, vy=350.0, vz=-420.0),      # several hops, azimuthal velocity folds into the radius
+        dict(x=0.071, y=0.041, z=0.0, vx=1400.0, vy=600.0, vz=150.0),      # reflects at x = 0.09 (vertical edge) and y = 0.05
+        dict(x=0.044, y=0.016, z=0.0, vx=-300.0, vy=-900.0, vz=260.0),     # reflects at the inner radius y = 0.01
+        dict(x=0.008, y=0.046, z=0.0, vx=-1100.0, vy=-200.0, vz=-800.0),   # reflects at x = 0, large swirl
+        dict(x=0.05, y=0.03, z=0.0, vx=12.0, vy=-7.0, vz=5.0),             # slow: stays in its cell, trial moves only
+    ]
+    walk = []
+    for p in starts:
+        p["ic"] = locate(p["x"], p["y"])
+        q, trace, ntrial = advect_axi(mesh, p, dt)
+        walk.append(dict(inp=pdict(p), out=pdict(q), trace=trace, trial_moves=ntrial))
+    assert any(len(w["trace"]) >= 3 for w in walk) and walk[-1]["trace"] == []
+    pgs = {mesh["faces_pg"][c - 1][f - 1] for w in walk for c, f in w["trace"] if mesh["neighbors"][c - 1][f - 1] == -1}
+    assert {1, 2, 3, 4} <= pgs, pgs                                          # every wall of the box was hit by some case
+    out["axi_walk"] = dict(dt=hx(dt), cases=walk)
+
+    # ---- structured_walk: 4 x 3 cells on [0, 0.4] x [0, 0.3]; x periodic, ymin specular, ymax diffuse at 450 K; wall 1 a plain
+    # specular segment at x = 0.2 facing -x, wall 2 a porous specular segment at y = 0.15 facing +y, wall 3 diffuse at x = 0.3
+    air = fp1.read_species("air")
+    g = dict(xmin=0.0, xmax=0.4, ymin=0.0, ymax=0.3, zmin=-0.5, zmax=0.5, nx=4, ny=3, periodic=[1, 1, 0, 0], specular=[0, 0, 1, 0],
+             diffuse=[0, 0, 0, 1], boundtemp=450.0, z_periodic=1)
+    walls = [dict(x1=0.2, y1=0.05, x2=0.2, y2=0.2, normx=-1.0, normy=0.0, specular=1, diffuse=0, porous=0, transm=0.0, temp=300.0),
+             dict(x1=0.22, y1=0.15, x2=0.38, y2=0.15, normx=0.0, normy=1.0, specular=1, diffuse=0, porous=1, transm=0.5, temp=300.0),
+             dict(x1=0.3, y1=0.2, x2=0.3, y2=0.29, normx=1.0, normy=0.0, specular=0, diffuse=1, porous=0, transm=0.0, temp=700.0)]
+    dts = 1.0e-4
+    base = dict(z=0.1, erot=1.0e-21, evib=2.0e-21, sid="N2")
+    det = [dict(base, x=0.35, y=0.04, vx=900.0, vy=-700.0, vz=3000.0),       # xmax periodic wrap, ymin specular, z wraps
+           dict(base, x=0.12, y=0.1, vx=1500.0, vy=300.0, vz=-200.0),         # wall 1 (draw consumed, not porous), then xmin wrap
+           dict(base, x=0.15, y=0.21, vx=1000.0, vy=400.0, vz=-9000.0),       # passes above wall 1 (COLLDIST > 1): free flight, z wraps
+           dict(base, x=0.05, y=0.02, vx=-2600.0, vy=-900.0, vz=50.0),        # ymin specular, xmin wrap, far end
+           dict(base, x=0.25, y=0.1, vx=-800.0, vy=100.0, vz=0.0)]            # behind wall 1 (DX < 0): one-sided, flies through
+    s = Script([0.6, 0.6, 0.6, 0.6, 0.6, 0.6])
+    res = advect_structured(g, walls, air, det, dts, s)
+    assert [e for q, ev in res for e in ev if e[0] == "wall"] == [["wall", 1]] and s.k == 1 and all(q is not None for q, _ in res)
+    out["structured_walk"] = dict(grid=g, walls=walls, dt=hx(dts),
+                                  det=[dict(inp=pdict(p), out=pdict(q), events=ev) for p, (q, ev) in zip(det, res)])
+    sto = [dict(base, x=0.3, y=0.2, vx=100.0, vy=-1200.0, vz=10.0, sid="O2"),     # wall 2, draw 0.3 <= 0.5: removed
+           dict(base, x=0.3, y=0.2, vx=100.0, vy=-1200.0, vz=10.0, sid="O2"),     # wall 2, draw 0.8: reflected
+           dict(base, x=0.1, y=0.25, vx=300.0, vy=1400.0, vz=-20.0),              # ymax diffuse with BOUNDTEMP
+           dict(base, x=0.36, y=0.25, vx=-1300.0, vy=20.0, vz=5.0, sid="O2")]     # wall 3 diffuse at 700 K (draw for the porous test first)
+    draws = [0.3, 0.8,
+             0.11, 0.52, 0.73, 0.29, 0.91, 0.64, 0.35, 0.48, 0.95, 0.99, 0.62, 0.17,
+             0.44, 0.21, 0.77, 0.58, 0.39, 0.83, 0.26, 0.67, 0.09, 0.5, 0.4, 0.55, 0.3, 0.61, 0.2, 0.72, 0.1, 0.5, 0.05]
+    s = Script(draws)
+    res = advect_structured(g, walls, air, sto, dts, s)
+    assert res[0][0] is None and res[1][0] is not None and res[2][1][0] == ["side", 4] and res[3][1][0] == ["wall", 3], [ev for _, ev in res]
+    out["structured_walk"]["sto"] = dict(draws=draws[:s.k], used=s.k,
+                                          cases=[dict(inp=pdict(p), out=(pdict(q) if q else None), events=ev) for p, (q, ev) in zip(sto, res)])
+
+    # ---- dsmc_order: 7 argon particles in a 2 x 1 structured grid, store order interleaved between the cells; one candidate
+    # per cell (NCOLLMAX < 1 -> NCOLL = 1); draws per cell: JP1, JP2, acceptance, the Borgnakke-Larsen selector (no internal
+    # mode for argon: nothing exchanged), then COSCHI and THETA of the VSS deflection
+    ar = fp1.read_species("ar")
+    names = ["Ar"]
+    sigmamax = fp1.vss_pair(ar["Ar"], ar["Ar"])["sigma"]
+    fnum, dtc, vol = 1.0e10, 1.0e-7, 0.5
+    cells = [2, 1, 2, 1, 1, 2, 1]
+    vel = [[310.0, -120.0, 45.0], [-250.0, 90.0, 400.0], [120.0, 330.0, -210.0], [-80.0, -410.0, 150.0],
+           [505.0, 60.0, -95.0], [-330.0, 270.0, 15.0], [40.0, -75.0, -380.0]]
+    parts = [dict(v=list(v), erot=0.0, evib=0.0, sid="Ar", pos=None) for v in vel]
+    # cell 1 holds store indices (0-based) 1, 3, 4, 6: INT(4*0.55) = 2 -> particle 4, INT(4*0.05) = 0 -> particle 1
+    # cell 2 holds 0, 2, 5: INT(3*0.7) = 2 -> particle 5, INT(3*0.7) = 2 again -> redraw, INT(3*0.34) = 1 -> particle 2
+    draws = [0.55, 0.05, 1.0e-12, 0.9, 0.31, 0.77,
+             0.7, 0.7, 0.34, 1.0e-12, 0.5, 0.64, 0.12]
+    s = Script(draws)
+    before = [list(q["v"]) for q in parts]
+    total = dsmc_collisions(ar, names, parts, cells, 2, sigmamax, fnum, dtc, vol, s)
+    changed = [k for k in range(7) if parts[k]["v"] != before[k]]
+    assert total == 2 and s.k == len(draws) and changed == [1, 2, 4, 5], (total, s.k, changed)
+    out["dsmc_order"] = dict(cells=cells, sigmamax=hx(sigmamax), fnum=hx(fnum), dt=hx(dtc), draws=draws,
+                             inp=[[hx(c) for c in v] for v in before], out=[[hx(c) for c in q["v"]] for q in parts], changed=changed)
+
+    # ---- cell_nonuniform
+    xcoord = [0.0, 0.1, 0.15, 0.4, 0.45, 1.0]
+    ycoord = [-0.5, -0.2, 0.3, 0.35, 2.0]
+    pts = [(0.0, -0.5), (0.05, -0.3), (0.1, -0.2), (0.149999999, 0.29), (0.15, 0.3), (0.42, 0.34), (0.45, 0.35), (0.999, 1.99),
+           (0.3, 0.0), (0.0999999999999, 0.3499999999)]
+    out["cell_nonuniform"] = dict(xcoord=xcoord, ycoord=ycoord,
+                                  cases=[dict(x=hx(x), y=hx(y), ic=cell_from_position_nonuniform(x, y, xcoord, ycoord, len(xcoord) - 1)) for x, y in pts])
+    with open(os.path.join(HERE, "fortran_pins2.json"), "w") as f:
+        json.dump(out, f, indent=1)
+    print("wrote fortran_pins2.json:", {k: (len(v["cases"]) if isinstance(v, dict) and "cases" in v else "-") for k, v in out.items()})
+
+
+if __name__ == "__main__":
+    main()

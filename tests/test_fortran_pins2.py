@@ -1,0 +1,247 @@
+"""Independent pins, second set: vectors evaluated in plain Python from the FORTRAN source (tests/golden/fortran_pins2.py
+-> tests/golden/fortran_pins2.json), replayed through the oracle and, for the deterministic events, through the CUDA
+library.  Reference lines covered: the header of tests/golden/fortran_pins2.py and DESIGN.md section 5.
+"""
+import json
+import os
+import types
+
+import numpy as np
+import pytest
+
+from pantera_pic_dsmc_b200 import capi, workloads as wl
+
+import util
+from test_fortran_pins import script, script_used
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+PINS = json.load(open(os.path.join(GOLD, "fortran_pins2.json")))
+fh = float.fromhex
+
+
+def pin_tri_mesh():
+    """The pin's own geometry (EDGE_NORMAL, CELL_EDGES_LEN evaluated by the pin from the Fortran formulas), not meshgen's."""
+    m = PINS["tri_mesh"]
+    nn, nc = len(m["nodes"]), len(m["cells"])
+    o = types.SimpleNamespace(dims=2, nn=nn, nc=nc)
+    xyz = np.zeros((3, nn))
+    xyz[:2] = np.array(m["nodes"], dtype=np.float64).T
+    o.node_coords = np.asfortranarray(xyz)
+    o.cell_nodes = np.asfortranarray(np.array(m["cells"], dtype=np.int32).T)
+    o.cell_neighbors = np.asfortranarray(np.array(m["neighbors"], dtype=np.int32).T)
+    o.cell_faces_pg = np.asfortranarray(np.array(m["faces_pg"], dtype=np.int32).T)
+    fnorm = np.zeros((3, 3, nc))
+    fnorm[:2] = np.array(m["normal"], dtype=np.float64).transpose(2, 1, 0)
+    o.face_normal = np.asfortranarray(fnorm)
+    o.cell_edges_len = np.asfortranarray(np.array(m["edges_len"], dtype=np.float64).T)
+    xy = np.array(m["nodes"])
+    tri = np.array(m["cells"]) - 1
+    a, b, c = xy[tri[:, 0]], xy[tri[:, 1]], xy[tri[:, 2]]
+    area = 0.5 * np.abs(a[:, 0] * (b[:, 1] - c[:, 1]) + b[:, 0] * (c[:, 1] - a[:, 1]) + c[:, 0] * (a[:, 1] - b[:, 1]))
+    o.cell_volumes = area * (a[:, 1] + b[:, 1] + c[:, 1]) / 3.0
+    o.face_tang1 = o.face_tang2 = None
+    o.cell_pg = None
+    o.basis_coeffs = None
+    o.cell_procs = None
+    o.face_boundary_index = None
+    o.nboundcells = 0
+    o.boundary_area = None
+    return o
+
+
+def axi_workload():
+    t = PINS["axi_walk"]
+    sp = wl.load_species("air", ["N2", "O2"])
+    dt = fh(t["dt"])
+    cfg = capi.make_config(dims=2, axi=1, grid_type=capi.UNSTRUCTURED, nx=1, ny=1, xmin=0.0, xmax=0.09, ymin=0.01, ymax=0.05,
+                           zmin=0.0, zmax=1.0, dt=dt, fnum=1.0, collision_type=capi.NO_COLL, dump_bound_avg_every=0)
+    p = wl.new_particles(len(t["cases"]))
+    for k, c in enumerate(t["cases"]):
+        q = c["inp"]
+        for f in ("x", "y", "z", "vx", "vy", "vz"):
+            p[f.upper()][k] = fh(q[f])
+        p["IC"][k] = q["ic"]
+    p["S_ID"] = 1
+    p["DTRIM"] = dt
+    bcs = dict(particle_bc=[capi.SPECULAR] * 4, wall_temp=[300.0] * 4, acc_n=[1.0] * 4, acc_t=[1.0] * 4)
+    w = wl.Workload("pin axisymmetric triangles", cfg, sp, p, mesh=pin_tri_mesh(), bcs=bcs)
+    w.cfg.track_id = 1
+    return w, t
+
+
+def check_axi_walk(lib, exact):
+    w, t = axi_workload()
+    wl.apply(lib, w)
+    lib.advect(1)
+    out = util.by_id(lib.download_particles())
+    assert len(out) == len(t["cases"])
+    for k, c in enumerate(t["cases"]):
+        e = c["out"]
+        assert out["IC"][k] == e["ic"], (k, out["IC"][k], e["ic"], c["trace"])
+        for f in ("x", "y", "z", "vx", "vy", "vz"):
+            got, want = float(out[f.upper()][k]), fh(e[f])
+            if exact:
+                assert got == want, (k, f, got.hex(), e[f], c["trace"])
+            else:
+                assert got == pytest.approx(want, rel=1e-11, abs=1e-13), (k, f, got, want)
+
+
+def test_axisymmetric_edge_walk_oracle_matches_fortran_reading(oracle):
+    """Quadratic edge test, trial moves forth and back (their rounding stays in the particle), vertical edges, hops and
+    specular reflections on all four walls: bit-identical with the plain-Python reading of src/timecycle.f90:1173-1253."""
+    cases = PINS["axi_walk"]["cases"]
+    assert max(len(c["trace"]) for c in cases) >= 7 and sum(c["trial_moves"] for c in cases) > 40
+    check_axi_walk(oracle, exact=True)
+
+
+@pytest.mark.gpu
+def test_axisymmetric_edge_walk_device_matches_fortran_reading(gpu):
+    """(the device evaluates the same expressions; the tolerance covers its fused trial move, see pgpu_advect.cu)"""
+    check_axi_walk(gpu, exact=False)
+
+
+def test_dsmc_collisions_visit_cells_and_particles_in_the_reference_order(oracle):
+    """Two cells, store order interleaved: the scripted INT(NPC*rf()) picks must land on the particles the stable
+    counting sort of DSMC_COLLISIONS puts at those places (src/collisions.f90:37-149, 259-271)."""
+    t = PINS["dsmc_order"]
+    w = wl.c1_argon_box(7, nx=2, ny=1)
+    w.cfg.fnum, w.cfg.dt = fh(t["fnum"]), fh(t["dt"])
+    assert fh(t["sigmamax"]) == pytest.approx(w.species.sigmamax, rel=1e-14)
+    p = wl.new_particles(7)
+    for k, (cell, v) in enumerate(zip(t["cells"], t["inp"])):
+        p["X"][k] = 0.25 + 0.5 * (cell - 1)
+        p["Y"][k] = 0.1 + 0.1 * k
+        p["VX"][k], p["VY"][k], p["VZ"][k] = (fh(c) for c in v)
+        p["IC"][k] = cell
+    p["S_ID"] = 1
+    p["DTRIM"] = w.cfg.dt
+    w.particles = p
+    w.cfg.track_id = 1
+    wl.apply(oracle, w)
+    script(oracle, t["draws"])
+    ncoll, nreac = oracle.collide(1)
+    assert (ncoll, nreac) == (2, 0) and script_used(oracle) == len(t["draws"])
+    out = util.by_id(oracle.download_particles())
+    for k in range(7):
+        for f, want in zip(("VX", "VY", "VZ"), t["out"][k]):
+            got = float(out[f][k])
+            if k in t["changed"]:
+                assert got == pytest.approx(fh(want), rel=1e-13), (k, f)
+            else:
+                assert got == fh(want), (k, f)
+
+
+def check_cell_nonuniform(lib):
+    """CELL_FROM_POSITION on a non-uniform rectilinear grid is what re-indexes a particle after its flight
+    (src/timecycle.f90:2104-2106): particles at rest are given a wrong IC and one ADVECT must bring the pinned one back."""
+    t = PINS["cell_nonuniform"]
+    xc, yc = t["xcoord"], t["ycoord"]
+    nx, ny = len(xc) - 1, len(yc) - 1
+    w = wl.c1_argon_box(len(t["cases"]), nx=nx, ny=ny)
+    w.cfg.grid_type = capi.RECTILINEAR_NONUNIFORM
+    w.cfg.xmin, w.cfg.xmax, w.cfg.ymin, w.cfg.ymax = xc[0], xc[-1], yc[0], yc[-1]
+    w.cfg.collision_type = capi.NO_COLL
+    w.cfg.track_id = 1
+    p = wl.new_particles(len(t["cases"]))
+    for k, c in enumerate(t["cases"]):
+        p["X"][k], p["Y"][k] = fh(c["x"]), fh(c["y"])
+        p["IC"][k] = 1 + (k * 7) % (nx * ny)
+    p["S_ID"] = 1
+    p["DTRIM"] = w.cfg.dt
+    w.particles = p
+    wl.apply(lib, w, upload=False)
+    lib.set_grid_coords(xc, yc)
+    lib.upload_particles(p)
+    lib.advect(1)
+    out = util.by_id(lib.download_particles())
+    assert [int(i) for i in out["IC"]] == [c["ic"] for c in t["cases"]]
+    assert np.array_equal(out["X"], p["X"]) and np.array_equal(out["Y"], p["Y"])
+
+
+def test_cell_from_position_nonuniform_oracle_matches_fortran_reading(oracle):
+    check_cell_nonuniform(oracle)
+
+
+@pytest.mark.gpu
+def test_cell_from_position_nonuniform_device_matches_fortran_reading(gpu):
+    check_cell_nonuniform(gpu)
+
+
+# ---- rectilinear grid: box sides, interior walls, Z wrap, re-index -------------------------------------------------
+def structured_workload(cases):
+    t = PINS["structured_walk"]
+    g = t["grid"]
+    sp = wl.load_species("air", ["N2", "O2"])
+    dt = fh(t["dt"])
+    cfg = capi.make_config(dims=2, grid_type=capi.RECTILINEAR_UNIFORM, nx=g["nx"], ny=g["ny"], xmin=g["xmin"], xmax=g["xmax"],
+                           ymin=g["ymin"], ymax=g["ymax"], zmin=g["zmin"], zmax=g["zmax"], dt=dt, fnum=1.0, collision_type=capi.NO_COLL,
+                           bool_periodic=g["periodic"], bool_specular=g["specular"], bool_diffuse=g["diffuse"], boundtemp=g["boundtemp"],
+                           bool_z_periodic=g["z_periodic"])
+    p = wl.new_particles(len(cases))
+    for k, c in enumerate(cases):
+        q = c["inp"]
+        for f in ("x", "y", "z", "vx", "vy", "vz", "erot", "evib"):
+            p[f.upper()][k] = fh(q[f])
+        p["S_ID"][k] = sp.id(q["sid"])
+        ddx, ddy = (g["xmax"] - g["xmin"]) / g["nx"], (g["ymax"] - g["ymin"]) / g["ny"]
+        p["IC"][k] = int((fh(q["x"]) - g["xmin"]) / ddx) + g["nx"] * int((fh(q["y"]) - g["ymin"]) / ddy) + 1
+    p["DTRIM"] = dt
+    ws = t["walls"]
+    col = lambda k: [w[k] for w in ws]
+    walls = dict(x1=col("x1"), y1=col("y1"), x2=col("x2"), y2=col("y2"), normx=col("normx"), normy=col("normy"), temp=col("temp"),
+                 specular=col("specular"), diffuse=col("diffuse"), porous=col("porous"), transmissivity=col("transm"), react=[0] * len(ws))
+    w = wl.Workload("pin rectilinear grid", cfg, sp, p, walls=walls)
+    w.cfg.track_id = 1
+    return w
+
+
+def check_structured(lib, cases, exact, rel=1e-13):
+    out = util.by_id(lib.download_particles())
+    alive = [c for c in cases if c["out"] is not None]
+    assert len(out) == len(alive)
+    for k, c in enumerate(alive):
+        e = c["out"]
+        assert out["IC"][k] == e["ic"], (k, out["IC"][k], e["ic"], c["events"])
+        for f in ("x", "y", "z", "vx", "vy", "vz", "erot", "evib"):
+            got, want = float(out[f.upper()][k]), fh(e[f])
+            if exact:
+                assert got == want, (k, f, got.hex(), e[f], c["events"])
+            else:
+                assert got == pytest.approx(want, rel=rel, abs=1e-300), (k, f, got, want, c["events"])
+
+
+def check_structured_det(lib):
+    cases = PINS["structured_walk"]["det"]
+    w = structured_workload(cases)
+    wl.apply(lib, w)
+    lib.advect(1)
+    check_structured(lib, cases, exact=True)
+    b, wc = lib.get_boundary_counts(2, nw=3)
+    assert list(b[:4]) == [1, 1, 2, 0] and list(wc[:3]) == [1, 0, 0]      # LOCAL_BOUNDARY_COLL_COUNT / LOCAL_WALL_COLL_COUNT of N2
+
+
+def test_structured_walk_oracle_matches_fortran_reading(oracle):
+    """Periodic and specular box sides (strict '>'), a one-sided interior wall with the hit point inside / outside the
+    segment, the Z wrap and the final CELL_FROM_POSITION: bit-identical."""
+    check_structured_det(oracle)
+
+
+@pytest.mark.gpu
+def test_structured_walk_device_matches_fortran_reading(gpu):
+    check_structured_det(gpu)
+
+
+def test_structured_walls_with_draws_oracle_matches_fortran_reading(oracle):
+    """Porous specular wall (removed / reflected by the scripted draw), diffuse box side at BOUNDTEMP, diffuse interior wall."""
+    t = PINS["structured_walk"]["sto"]
+    w = structured_workload(t["cases"])
+    wl.apply(oracle, w)
+    script(oracle, t["draws"])
+    oracle.advect(1)
+    assert script_used(oracle) == t["used"] == len(t["draws"])
+    # the removed particle is the first of the store: the swap-with-last removal moves the last one into its place;
+    # the IDs keep the match
+    out = util.by_id(oracle.download_particles())
+    alive = [c for c in t["cases"] if c["out"] is not None]
+    assert len(out) == 3 and len(alive) == 3
+    check_structured(oracle, t["cases"], exact=False, rel=1e-13)
