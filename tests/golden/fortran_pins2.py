@@ -17,6 +17,10 @@ Covered reference lines:
                  point inside the segment), :1868-1935 (periodic shift, specular flip, diffuse re-emission with BOUNDTEMP),
                  :1937-1965 (specular wall: rf() is drawn even when the wall is not porous; porous removal), :2015-2019,
                  :2044-2054 (Z wrap), :2104-2106 + src/grid_and_partition.f90:46-72 (re-index on the uniform grid)
+  mcc_collisions  src/collisions.f90:1261-1595 (MCC_COLLISIONS: partner drawn from the background Maxwellian BEFORE the test,
+                 P = 1 - exp(-DT n VR sigma (VR/CREF)^(1-2 omega)), partner created in the store, TCE test over the reaction list
+                 with the ORIGINAL species ids, 3-product redistribution, Borgnakke-Larsen selector, VSS deflection; loop
+                 over the NP_PROC present at entry and over the components of the background mixture)
   dsmc_order     src/collisions.f90:37-149 (DSMC_COLLISIONS: INDALL is a stable counting sort by cell, cells are visited in
                  ascending order), :259-271 (INT(NPC*rf()) picks into that order)
   cell_nonuniform  src/grid_and_partition.f90:34-96 (CELL_FROM_POSITION on RECTILINEAR_NONUNIFORM grids), src/tools.f90:1499-1535
@@ -309,6 +313,147 @@ def advect_structured(g, walls, species, parts, dt, rf):
     return out
 
 
+# ------------------------------------------------------------------------------------------ MCC_COLLISIONS
+def mcc_collisions(species, parts, reactions, bg_mix, bg_dens, bg_ttra, dt, rf):
+    """src/collisions.f90:1261-1595 with BOOL_BG_DENSITY_FILE = .FALSE.  parts: dicts pos, v, erot, evib, sid (name), in store
+    order; new particles are appended to `parts` (ADD_PARTICLE_ARRAY).  bg_mix: [(name, molfrac)].  reactions: dicts r1, r2,
+    p1, p2, p3, nprod, ea, c1, c2, c3 (TCE).  Returns (TIMESTEP_COLL, TIMESTEP_REAC)."""
+    pi2 = 2 * fp1.PI
+    ncoll = nreac = 0
+    np_initial = len(parts)
+    for jp1 in range(np_initial):
+        a = parts[jp1]
+        sp_id1 = a["sid"]                                     # read once per particle, :1292
+        for sp_id2, frac in bg_mix:
+            bg_nrho = frac * bg_dens
+            if bg_nrho == 0:
+                continue
+            s1, s2 = species[sp_id1], species[sp_id2]
+            pr = fp1.vss_pair(s1, s2)
+            cref, sigma, omega, alpha = pr["cref"], pr["sigma"], pr["omega"], pr["alpha"]
+            c2 = list(fp1.maxwell(rf, 0.0, 0.0, 0.0, bg_ttra, bg_ttra, bg_ttra, s2["mass"]))
+            vr2 = (c2[0] - a["v"][0]) * (c2[0] - a["v"][0]) + (c2[1] - a["v"][1]) * (c2[1] - a["v"][1]) + (c2[2] - a["v"][2]) * (c2[2] - a["v"][2])
+            vr = math.sqrt(vr2)
+            p_coll = 1 - math.exp(-dt * bg_nrho * vr * sigma * (vr / cref) ** (1.0 - 2.0 * omega))
+            if not (rf() < p_coll):
+                continue
+            ncoll += 1
+            c1 = list(a["v"])
+            erot = fp1.internal_energy(rf, s2["rotdof"], bg_ttra)
+            evib = fp1.internal_energy(rf, s2["vibdof"], bg_ttra)
+            b = dict(pos=list(a["pos"]), v=list(c2), erot=erot, evib=evib, sid=sp_id2, ic=a["ic"])
+            parts.append(b)
+            m1, m2 = s1["mass"], s2["mass"]
+            mred = m1 * m2 / (m1 + m2)
+            etr = 0.5 * mred * vr2
+            ecoll = etr + a["erot"] + b["erot"] + a["evib"] + b["evib"]
+            skip = False
+            for r in reactions:
+                if r["r1"] != sp_id1:
+                    if r["r1"] != sp_id2:
+                        continue
+                    elif r["r2"] != sp_id1:
+                        continue
+                elif r["r2"] != sp_id2:
+                    continue
+                ea = r["ea"]
+                if ecoll <= ea:
+                    continue
+                ptce = r["c1"] * (ecoll - ea) ** r["c2"] * (1.0 - ea / ecoll) ** r["c3"]
+                rfp = rf()
+                if rfp < ptce:
+                    skip = True
+                    nreac += 1
+                    ecoll = ecoll - ea
+                    p1, p2 = species[r["p1"]], species[r["p2"]]
+                    a["sid"], b["sid"] = r["p1"], r["p2"]
+                    totdof = 3.0 + p2["rotdof"] + p2["vibdof"] + p1["rotdof"]
+                    if r["nprod"] == 3:
+                        p3 = species[r["p3"]]
+                        totdof = totdof + 3.0 + p3["rotdof"] + p3["vibdof"]
+                    ei = fp1.coll_internal_energy(rf, ecoll, totdof, p1["vibdof"])
+                    a["evib"] = ei
+                    ecoll = ecoll - ei
+                    totdof = totdof - p1["rotdof"]
+                    ei = fp1.coll_internal_energy(rf, ecoll, totdof, p1["rotdof"])
+                    a["erot"] = ei
+                    ecoll = ecoll - ei
+                    totdof = totdof - p2["vibdof"]
+                    ei = fp1.coll_internal_energy(rf, ecoll, totdof, p2["vibdof"])
+                    b["evib"] = ei
+                    ecoll = ecoll - ei
+                    totdof = totdof - p2["rotdof"]
+                    ei = fp1.coll_internal_energy(rf, ecoll, totdof, p2["rotdof"])
+                    b["erot"] = ei
+                    ecoll = ecoll - ei
+                    mm1 = p1["mass"]
+                    mm2 = p2["mass"] if r["nprod"] == 2 else p2["mass"] + p3["mass"]
+                    totdof = totdof - 3.0
+                    ei = fp1.coll_internal_energy(rf, ecoll, totdof, 3)
+                    c1, c2 = fp1.hs_scatter(rf, ei, mm1, mm2, c1, c2)
+                    ecoll = ecoll - ei
+                    a["v"] = list(c1)
+                    if r["nprod"] == 2:
+                        b["v"] = list(c2)
+                    else:
+                        totdof = totdof - p3["vibdof"]
+                        evib3 = fp1.coll_internal_energy(rf, ecoll, totdof, p3["vibdof"])
+                        ecoll = ecoll - evib3
+                        totdof = totdof - p3["rotdof"]
+                        erot3 = fp1.coll_internal_energy(rf, ecoll, totdof, p3["rotdof"])
+                        ecoll = ecoll - erot3
+                        c1 = list(c2)
+                        c1, c2 = fp1.hs_scatter(rf, ecoll, p2["mass"], p3["mass"], c1, c2)
+                        b["v"] = list(c1)
+                        parts.append(dict(pos=list(b["pos"]), v=list(c2), erot=erot3, evib=evib3, sid=r["p3"], ic=b["ic"]))
+                    break
+            if skip:
+                continue
+            trdof = 3.0
+            prot1 = (trdof + s1["rotdof"]) / trdof * s1["rotrel"]
+            prot2 = (trdof + s2["rotdof"]) / trdof * s2["rotrel"]
+            pvib1 = (trdof + s1["vibdof"]) / trdof * s1["vibrel"]
+            pvib2 = (trdof + s2["vibdof"]) / trdof * s2["vibrel"]
+            trdof = 5.0 - 2.0 * omega
+            rfp = rf()
+            if rfp < prot1:
+                ecoll = etr + a["erot"]
+                a["erot"] = fp1.coll_internal_energy(rf, ecoll, trdof, s1["rotdof"])
+                etr = ecoll - a["erot"]
+            elif rfp < prot1 + prot2:
+                ecoll = etr + b["erot"]
+                b["erot"] = fp1.coll_internal_energy(rf, ecoll, trdof, s2["rotdof"])
+                etr = ecoll - b["erot"]
+            elif rfp < prot1 + prot2 + pvib1:
+                ecoll = etr + a["evib"]
+                a["evib"] = fp1.coll_internal_energy(rf, ecoll, trdof, s1["vibdof"])
+                etr = ecoll - a["evib"]
+            elif rfp < prot1 + prot2 + pvib1 + pvib2:
+                ecoll = etr + b["evib"]
+                b["evib"] = fp1.coll_internal_energy(rf, ecoll, trdof, s2["vibdof"])
+                etr = ecoll - b["evib"]
+            coschi = 2.0 * rf() ** (1.0 / alpha) - 1.0
+            sinchi = math.sqrt(1.0 - coschi * coschi)
+            theta = pi2 * rf()
+            costheta, sintheta = math.cos(theta), math.sin(theta)
+            if rfp < prot1 + prot2 + pvib1 + pvib2:
+                g = math.sqrt(2.0 * etr / mred)
+                cosa = 2.0 * rf() - 1.0
+                sina = math.sqrt(1 - cosa * cosa)
+                bb = pi2 * rf()
+                gx, gy, gz = g * sina * math.cos(bb), g * sina * math.sin(bb), g * cosa
+            else:
+                gx, gy, gz = c1[0] - c2[0], c1[1] - c2[1], c1[2] - c2[2]
+                g = math.sqrt(gx * gx + gy * gy + gz * gz)
+            grel = [gx * coschi + math.sqrt(gy * gy + gz * gz) * sintheta * sinchi,
+                    gy * coschi + (g * gz * costheta - gx * gy * sintheta) / math.sqrt(gy * gy + gz * gz) * sinchi,
+                    gz * coschi - (g * gy * costheta + gx * gz * sintheta) / math.sqrt(gy * gy + gz * gz) * sinchi]
+            w = [m1 / (m1 + m2) * c1[i] + m2 / (m1 + m2) * c2[i] for i in range(3)]
+            a["v"] = [w[i] + m2 / (m1 + m2) * grel[i] for i in range(3)]
+            b["v"] = [w[i] - m1 / (m1 + m2) * grel[i] for i in range(3)]
+    return ncoll, nreac
+
+
 # ------------------------------------------------------------------------------------------ DSMC_COLLISIONS order
 def dsmc_collisions(species, names, parts, cells, ncells, sigmamax, fnum, dt, vol, rf):
     """src/collisions.f90:37-149: INDALL(IOFALL(JC) + NPCALL(JC)) = JP for JP = 1..NP_PROC (stable in store order), then
@@ -426,6 +571,37 @@ def main():
     out["structured_walk"]["sto"] = dict(draws=draws[:s.k], used=s.k,
                                           cases=[dict(inp=pdict(p), out=(pdict(q) if q else None), events=ev) for p, (q, ev) in zip(sto, res)])
 
+    # ---- mcc_collisions: three test particles (a slow O2, a slow N2, a 14 km/s N2) in an O2 0.21 / N2 0.79 background at 800 K;
+    # random script; the fast particle's collision energy is above the O2 dissociation threshold: N2 + O2 --> N2 + O + O can fire
+    import random
+    names5 = ["O2", "N2", "O", "N", "NO"]
+    tce = fp1.read_tce(air)
+    reactions = []
+    for r in tce:
+        if all(x in names5 for x in r["react"] + r["prod"]):
+            c1, c2, c3 = fp1.tce_coeffs(air, r["react"][0], r["react"][1], r["A"], r["n"], r["ea"])
+            reactions.append(dict(r1=r["react"][0], r2=r["react"][1], p1=r["prod"][0], p2=r["prod"][1],
+                                  p3=r["prod"][2] if len(r["prod"]) > 2 else None, nprod=len(r["prod"]), ea=r["ea"], c1=c1, c2=c2, c3=c3))
+    bg_mix, bg_dens, bg_ttra, dtm = [("O2", 0.21), ("N2", 0.79)], 4.0e21, 800.0, 1.0e-6
+    best = None
+    for seed in range(400):
+        rr = random.Random(seed)
+        draws = [rr.random() for _ in range(400)]
+        mparts = [dict(pos=[0.1, 0.2, 0.0], v=[900.0, -300.0, 150.0], erot=2.0e-21, evib=1.0e-21, sid="O2", ic=1),
+                  dict(pos=[0.6, 0.3, 0.1], v=[-400.0, 700.0, 250.0], erot=3.0e-21, evib=0.5e-21, sid="N2", ic=1),
+                  dict(pos=[0.4, 0.8, -0.2], v=[14000.0, -2000.0, 1000.0], erot=4.0e-21, evib=6.0e-21, sid="N2", ic=1)]
+        m_in = json.loads(json.dumps(mparts))
+        s = Script(draws)
+        nc, nr = mcc_collisions(air, mparts, reactions, bg_mix, bg_dens, bg_ttra, dtm, s)
+        if nr >= 1 and nc >= 3 and any(q["sid"] == "O" for q in mparts[3:]):
+            best = (seed, draws[:s.k], m_in, mparts, nc, nr)
+            break
+    assert best, "no script with a reaction found"
+    seed, draws, m_in, mparts, nc, nr = best
+    pm = lambda q: dict(pos=q["pos"], v=[hx(c) for c in q["v"]], erot=hx(q["erot"]), evib=hx(q["evib"]), sid=q["sid"])
+    out["mcc_collisions"] = dict(species=names5, bg_mix=bg_mix, bg_dens=hx(bg_dens), bg_ttra=hx(bg_ttra), dt=hx(dtm), draws=[hx(v) for v in draws],
+                                 used=len(draws), ncoll=nc, nreac=nr, inp=[pm(q) for q in m_in], out=[pm(q) for q in mparts])
+
     # ---- dsmc_order: 7 argon particles in a 2 x 1 structured grid, store order interleaved between the cells; one candidate
     # per cell (NCOLLMAX < 1 -> NCOLL = 1); draws per cell: JP1, JP2, acceptance, the Borgnakke-Larsen selector (no internal
     # mode for argon: nothing exchanged), then COSCHI and THETA of the VSS deflection
@@ -458,6 +634,7 @@ def main():
                                   cases=[dict(x=hx(x), y=hx(y), ic=cell_from_position_nonuniform(x, y, xcoord, ycoord, len(xcoord) - 1)) for x, y in pts])
     with open(os.path.join(HERE, "fortran_pins2.json"), "w") as f:
         json.dump(out, f, indent=1)
+    print("mcc_collisions: script seed", seed, "->", nc, "collisions,", nr, "reactions,", len(mparts), "particles,", len(draws), "draws")
     print("wrote fortran_pins2.json:", {k: (len(v["cases"]) if isinstance(v, dict) and "cases" in v else "-") for k, v in out.items()})
 
 

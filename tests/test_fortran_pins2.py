@@ -245,3 +245,37 @@ def test_structured_walls_with_draws_oracle_matches_fortran_reading(oracle):
     alive = [c for c in t["cases"] if c["out"] is not None]
     assert len(out) == 3 and len(alive) == 3
     check_structured(oracle, t["cases"], exact=False, rel=1e-13)
+
+
+# ---- MCC_COLLISIONS ------------------------------------------------------------------------------------------------
+def test_mcc_collisions_oracle_matches_fortran_reading(oracle):
+    """Three test particles against an O2/N2 background on a scripted stream: partner sampling before the test, partner and
+    product creation order, the TCE dissociation N2 + O2 --> N2 + O + O of the fast particle, Borgnakke-Larsen and VSS
+    deflection of the others (src/collisions.f90:1261-1595)."""
+    t = PINS["mcc_collisions"]
+    w = wl.mcc_box("air", n=3, nx=1, ny=1, bg_T=fh(t["bg_ttra"]), bg_dens=fh(t["bg_dens"]), dt=fh(t["dt"]))
+    sp = w.species
+    assert [sp.names[k] for k in range(5)] == t["species"]
+    w.mcc_background = ([sp.id(n) for n, _ in t["bg_mix"]], [f for _, f in t["bg_mix"]])
+    p = wl.new_particles(3)
+    for k, q in enumerate(t["inp"]):
+        p["X"][k], p["Y"][k], p["Z"][k] = q["pos"]
+        p["VX"][k], p["VY"][k], p["VZ"][k] = (fh(c) for c in q["v"])
+        p["EROT"][k], p["EVIB"][k] = fh(q["erot"]), fh(q["evib"])
+        p["S_ID"][k] = sp.id(q["sid"])
+    p["IC"] = 1
+    p["DTRIM"] = w.cfg.dt
+    w.particles = p
+    wl.apply(oracle, w)
+    script(oracle, [fh(v) for v in t["draws"]])
+    ncoll, nreac = oracle.mcc_collisions(1)
+    assert (ncoll, nreac) == (t["ncoll"], t["nreac"]) and script_used(oracle) == t["used"]
+    out = oracle.download_particles()                       # store order: the 3 test particles, then partners / products as created
+    assert len(out) == len(t["out"])
+    for k, e in enumerate(t["out"]):
+        assert out["S_ID"][k] == sp.id(e["sid"]), (k, e["sid"])
+        for f, want in zip(("VX", "VY", "VZ"), e["v"]):
+            assert float(out[f][k]) == pytest.approx(fh(want), rel=1e-12, abs=1e-9), (k, f)
+        assert float(out["EROT"][k]) == pytest.approx(fh(e["erot"]), rel=1e-11, abs=1e-33), k
+        assert float(out["EVIB"][k]) == pytest.approx(fh(e["evib"]), rel=1e-11, abs=1e-33), k
+        assert (out["X"][k], out["Y"][k], out["Z"][k]) == tuple(e["pos"])
