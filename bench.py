@@ -116,7 +116,8 @@ def cpu_baseline(args, seconds=12.0):
     same particles per cell, same dt.  Reported, not the target."""
     from pantera_pic_dsmc_b200 import capi, workloads as wl
     w = wl.c5_channel_strip(24, 24, 24, n=24 * 24 * 24 * 6 * 40, rank=0, world=1, seed=99, u_drift=0.0)  # 3.3e6 particles, 318 MB: out of cache
-    o = capi.load_oracle(rng_mode=0)
+    from oracle.binding import load_oracle   # the CPU leg: test infrastructure, outside the product package
+    o = load_oracle(rng_mode=0)
     wl.apply(o, w)
     o.run_steps(1, 1)  # warm-up: first touch
     n = o.num_particles()
@@ -137,7 +138,7 @@ def run_reference(args, rank, world):
     """--impl reference: the reference's CPU algorithm (oracle port; see module docstring) on host cores."""
     if rank != 0:
         return
-    from pantera_pic_dsmc_b200 import refbench
+    from oracle import refbench
     res = refbench.run(steps=args.steps, warmup=args.warmup, world=world)
     line = {"metric": "particle-timesteps/s (move+sort+collide)", "value": res["value"], "unit": "particle-timesteps/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"],
@@ -327,7 +328,8 @@ def run_alt(args):
             ws = build_alt(name, {"c1": 200_000, "c1-grid": 1_000_000, "c2": 500_000, "c4": 400_000}[name]) if name != "c1-grid" else wl.c1_argon_box(1_000_000, nx=128, ny=128)
         if name == "c2":
             ws = wl.c2_air_box(500_000, nx=100, ny=100, T=9000.0, nrho=1e21, dt=2e-7)
-        o = capi.load_oracle(rng_mode=0)
+        from oracle.binding import load_oracle
+        o = load_oracle(rng_mode=0)
         wl.apply(o, ws)
         if name in EMITTING:
             wl.apply_sources(o, ws)

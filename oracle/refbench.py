@@ -4,7 +4,7 @@ The PANTERA binary (Fortran + MPI + PETSc) cannot be built in this image (no For
 what is timed is the oracle -- the C restatement of the reference algorithm -- in the reference's own
 parallel model: one rank per x-strip (ASSIGN_CELLS_TO_PROCS "stripsx"), per step ADVECT -> EXCHANGE ->
 DSMC_COLLISIONS, one host thread per rank (oracle/po_mpi_sim.c), MT19937-64 stream per rank seeded as
-src/initialization.f90:2294-2296.  This is the only module besides tests/ that executes oracle/ code.
+src/initialization.f90:2294-2296.  Test / benchmark infrastructure: lives under oracle/, outside the product package.
 """
 from __future__ import annotations
 
@@ -13,7 +13,8 @@ import os
 
 import numpy as np
 
-from . import capi, workloads as wl
+from pantera_pic_dsmc_b200 import capi, workloads as wl
+from oracle.binding import load_oracle
 
 
 def usable_cores() -> int:
@@ -32,7 +33,7 @@ def make_ranks(nranks: int, cubes=(8, 32, 32), ppc: int = 40, seed: int = 7, u_d
     for r in range(nranks):
         w = wl.c5_channel_strip(ncx, ncy, ncz, n=n, rank=r, world=nranks, seed=seed + r, mesh=mesh, u_drift=u_drift)
         mesh = w.mesh
-        o = capi.load_oracle(rng_mode=0)
+        o = load_oracle(rng_mode=0)
         wl.apply(o, w)
         libs.append(o)
     return libs, n, mesh

@@ -1,14 +1,10 @@
 """ctypes binding of the C ABI declared in ``include/pantera_gpu.h``.
 
-The same binding class drives two shared libraries that export the same entry points under
-different prefixes:
+``libpantera_gpu.so`` (prefix ``pgpu_``) is the product: hand-written CUDA for sm_100a.  The class :class:`Lib` is
+generic in the symbol prefix so that the test infrastructure can drive the CPU oracle (``oracle/binding.py``, prefix
+``po_``, the same entry points) with the same methods; nothing in this package loads, imports or names the oracle.
 
-* ``libpantera_gpu.so``  (prefix ``pgpu_``) -- the product: hand-written CUDA for sm_100a.
-* ``oracle/_build/liboracle.so`` (prefix ``po_``) -- the CPU oracle, test infrastructure only.
-  It is never loaded from this module unless a test / bench baseline asks for it explicitly
-  through :func:`load_oracle`.
-
-There is no fallback between the two: :func:`load_gpu` raises if the CUDA library is missing.
+There is no fallback: :func:`load_gpu` raises if the CUDA library is missing or no GPU is usable.
 """
 from __future__ import annotations
 
@@ -22,7 +18,6 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 REPO_ROOT = os.path.dirname(_HERE)
 # PANTERA_GPU_LIB: developer override to A/B-test differently tuned builds of the SAME library (never a fallback)
 GPU_LIB_PATH = os.environ.get("PANTERA_GPU_LIB") or os.path.join(_HERE, "csrc", "libpantera_gpu.so")
-ORACLE_LIB_PATH = os.path.join(REPO_ROOT, "oracle", "_build", "liboracle.so")
 
 # ---- enumerations (values of the reference's ENUM, BIND(C) blocks; see pantera_gpu.h) ----------
 RECTILINEAR_UNIFORM, RECTILINEAR_NONUNIFORM, QUADTREE, UNSTRUCTURED = 0, 1, 2, 3
@@ -569,77 +564,6 @@ class GpuLib(Lib):
         self._call("comm_init", C.c_int(nranks), C.c_int(rank), buf)
 
 
-class OracleLib(Lib):
-    """CPU oracle (test infrastructure). rng_mode 0 = MT19937-64 (reference), 1 = Philox (device)."""
-
-    def __init__(self, rng_mode: int = 0, path: str = ORACLE_LIB_PATH):
-        super().__init__(path, "po_", 0)
-        self._call("set_rng_mode", C.c_int(rng_mode))
-
-    def set_rng_mode(self, mode):
-        self._call("set_rng_mode", C.c_int(mode))
-
-    def rf(self) -> float:
-        f = self.lib.po_rf
-        f.restype = C.c_double
-        return f(self.ctx)
-
-    def pick(self, n: int) -> int:
-        f = self.lib.po_pick
-        f.restype = C.c_int
-        return f(self.ctx, C.c_int(n))
-
-    def rng_stream(self, kind, tID, e0, e1=0):
-        self.lib.po_rng_stream(self.ctx, C.c_int(kind), C.c_int(tID), C.c_uint64(e0), C.c_uint64(e1))
-
-    def mt_next_u64(self) -> int:
-        f = self.lib.po_mt_next_u64
-        f.restype = C.c_uint64
-        return f(self.ctx)
-
-    def philox(self, ctr, key):
-        c = (C.c_uint32 * 4)(*ctr)
-        k = (C.c_uint32 * 2)(*key)
-        o = (C.c_uint32 * 4)()
-        self.lib.po_philox4x32_10(c, k, o)
-        return list(o)
-
-    def maxwell(self, u, t, m):
-        v = (C.c_double * 3)()
-        self.lib.po_maxwell(self.ctx, *[C.c_double(x) for x in u], *[C.c_double(x) for x in t], C.c_double(m), v)
-        return list(v)
-
-    def internal_energy(self, dof, temp):
-        f = self.lib.po_internal_energy
-        f.restype = C.c_double
-        return f(self.ctx, C.c_int(dof), C.c_double(temp))
-
-    def flx(self, sn, tinf, m):
-        f = self.lib.po_flx
-        f.restype = C.c_double
-        return f(self.ctx, C.c_double(sn), C.c_double(tinf), C.c_double(m))
-
-    def interp_cs(self, e, te, tcs):
-        f = self.lib.po_interp_cs
-        f.restype = C.c_double
-        te, tcs = _f64(te), _f64(tcs)
-        return f(C.c_double(e), C.c_int(len(te)), _p(te), _p(tcs))
-
-    def deposit_charge_compensated(self, nnodes):
-        rhs, ab = np.zeros(nnodes), np.zeros(nnodes)
-        self._call("deposit_charge_compensated", _p(rhs), _p(ab), C.c_int64(nnodes))
-        return rhs, ab
-
-    def get_timings(self):
-        s = np.zeros(3)
-        self._call("get_timings", _p(s), C.c_int32(3))
-        return s
-
-
 def load_gpu(device: int = 0) -> GpuLib:
     """Load the CUDA library. Raises (never falls back) if it is missing or no GPU is usable."""
     return GpuLib(device)
-
-
-def load_oracle(rng_mode: int = 0) -> OracleLib:
-    return OracleLib(rng_mode)

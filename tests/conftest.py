@@ -31,7 +31,8 @@ def _build_oracle():
 @pytest.fixture
 def oracle():
     from pantera_pic_dsmc_b200 import capi
-    lib = capi.load_oracle(rng_mode=0)
+    from oracle.binding import load_oracle
+    lib = load_oracle(rng_mode=0)
     yield lib
     lib.close()
 
@@ -39,7 +40,8 @@ def oracle():
 @pytest.fixture
 def oracle_philox():
     from pantera_pic_dsmc_b200 import capi
-    lib = capi.load_oracle(rng_mode=1)
+    from oracle.binding import load_oracle
+    lib = load_oracle(rng_mode=1)
     yield lib
     lib.close()
 

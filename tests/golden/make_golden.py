@@ -29,6 +29,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 from pantera_pic_dsmc_b200 import capi, datafiles as df, workloads as wl  # noqa: E402
+from oracle.binding import load_oracle  # noqa: E402
 
 CXX = r"""
 #include <cstdint>
@@ -151,7 +152,7 @@ def run_case(lib, w, call):
 def make_snapshots():
     for name in CASES:
         w, call, mode = build_case(name)
-        lib = capi.load_oracle(rng_mode=mode)
+        lib = load_oracle(rng_mode=mode)
         out, extra = run_case(lib, w, call)
         lib.close()
         np.savez_compressed(os.path.join(HERE, name + ".npz"), inp=w.particles, out=out, **extra)

@@ -20,7 +20,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-from pantera_pic_dsmc_b200 import capi, refbench, workloads as wl  # noqa: E402
+from pantera_pic_dsmc_b200 import capi, workloads as wl  # noqa: E402
+from oracle import refbench  # noqa: E402
+from oracle.binding import load_oracle  # noqa: E402
 
 CUBES, PPC, STEPS = (3, 4, 4), 12, 4
 
@@ -65,7 +67,7 @@ def _worker(rank, world, port, out_dir):
     n = CUBES[0] * CUBES[1] * CUBES[2] * 6 * PPC
     w = wl.c5_channel_strip(*CUBES, n=n, rank=rank, world=world, seed=7 + rank)
     w.cfg.track_id = 1
-    o = capi.load_oracle(rng_mode=0)
+    o = load_oracle(rng_mode=0)
     wl.apply(o, w)
     moved = 0
     for s in range(STEPS):

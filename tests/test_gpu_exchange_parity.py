@@ -26,7 +26,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-from pantera_pic_dsmc_b200 import capi, refbench, workloads as wl  # noqa: E402
+from pantera_pic_dsmc_b200 import capi, workloads as wl  # noqa: E402
+from oracle import refbench  # noqa: E402
+from oracle.binding import load_oracle  # noqa: E402
 
 import util  # noqa: E402
 
@@ -89,7 +91,7 @@ def test_one_gpu_contexts_match_rank_per_strip_oracle_bit_exact(world):
         for r in range(world):
             w = strip_workload(r, world, collisions=False, mesh=mesh)
             mesh = w.mesh
-            g, o = capi.load_gpu(0), capi.load_oracle(rng_mode=0)
+            g, o = capi.load_gpu(0), load_oracle(rng_mode=0)
             wl.apply(g, w)
             wl.apply(o, w)
             gpus.append(g)
@@ -122,7 +124,7 @@ def test_one_gpu_contexts_collisions_per_rank_streams():
         for r in range(world):
             w = strip_workload(r, world, collisions=True, mesh=mesh)
             mesh = w.mesh
-            g, o = capi.load_gpu(0), capi.load_oracle(rng_mode=1)
+            g, o = capi.load_gpu(0), load_oracle(rng_mode=1)
             wl.apply(g, w)
             wl.apply(o, w, upload=False)
             gpus.append(g)
@@ -161,7 +163,7 @@ def test_load_balance_recut_then_exchange():
         for r in range(world):
             w = strip_workload(r, world, collisions=False, mesh=mesh)
             mesh = w.mesh
-            g, o = capi.load_gpu(0), capi.load_oracle(rng_mode=0)
+            g, o = capi.load_gpu(0), load_oracle(rng_mode=0)
             wl.apply(g, w)
             wl.apply(o, w)
             gpus.append(g)
@@ -238,7 +240,7 @@ def _nccl_worker(rank, world, port, out_dir, p2p):
     # (b) collisions, step by step: advect -> exchange (NCCL) -> sort -> collide, against this rank's oracle
     w2 = strip_workload(rank, world, collisions=True, mesh=w.mesh)
     wl.apply(g, w2)
-    o = capi.load_oracle(rng_mode=1)
+    o = load_oracle(rng_mode=1)
     wl.apply(o, w2, upload=False)
     ok = True
     for s in range(3):
@@ -272,7 +274,7 @@ def test_nccl_ranks_match_rank_per_strip_oracle(tmp_path, world, p2p):
     for r in range(world):
         w = strip_workload(r, world, collisions=False, mesh=mesh)
         mesh = w.mesh
-        o = capi.load_oracle(rng_mode=0)
+        o = load_oracle(rng_mode=0)
         wl.apply(o, w)
         orcs.append(o)
     refbench.sim_run(orcs, 1, 4)

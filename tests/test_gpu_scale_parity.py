@@ -12,6 +12,7 @@ import numpy as np
 import pytest
 
 from pantera_pic_dsmc_b200 import capi, workloads as wl
+from oracle.binding import load_oracle
 
 import util
 
@@ -44,7 +45,7 @@ def test_advect_bench_mesh_one_step(bench_strip, walls, monkeypatch):
     else:
         w.bcs["particle_bc"] = [capi.SPECULAR, capi.SPECULAR, capi.DIFFUSE, capi.DIFFUSE, capi.SPECULAR, capi.SPECULAR]
     gpu = capi.load_gpu(0)
-    orc = capi.load_oracle(rng_mode=1)
+    orc = load_oracle(rng_mode=1)
     try:
         wl.apply(gpu, w)
         wl.apply(orc, w)
