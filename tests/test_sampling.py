@@ -134,6 +134,7 @@ def field_case(seed_global):
 
 def run_fields(lib, w, spinup=60, nsamples=40, every=2):
     wl.apply(lib, w)
+    lib.set_deterministic(True)    # stable in-cell order: the device run is reproducible for its seed, and so is this test
     lib.run_steps(1, spinup)
     t = 1 + spinup
     for k in range(nsamples):
@@ -167,11 +168,12 @@ def test_density_and_temperature_fields_within_3_sigma_of_the_reference_stream(o
             k = np.mean(((a1 - a2)[ok] ** 2) / 2.0 / scale[ok])
             sigma = np.sqrt(k * scale)
             z = (a1 - r)[ok] / (np.sqrt(2.0) * sigma[ok])
-            # ~48 cells per field: a 98 % rule on |z| < 3 would be failed by ONE 3.1-sigma cell (12 % of runs, and the
-            # atomics make the device's particle order, hence its draws, differ run to run); allow one cell past 3.5
-            # sigma (P(two or more) ~ 3e-4 per field) and nothing past 5
+            # 96 cells per field, neighbouring cells and the 40 samples correlated: a 98 % rule on |z| < 3 would be failed by
+            # ONE 3.1-sigma cell (12 % of runs).  Allow two cells past 3.5 sigma (r02ab saw two ADJACENT cells at 3.6 in one of
+            # four runs with the default, run-to-run varying particle order) and nothing past 5; a bias of the sampling or of
+            # the collisions would move mean(z^2) below, which stays tight
             out = int(np.sum(np.abs(z) >= 3.5))
-            assert out <= max(1, int(0.02 * z.size)) and np.abs(z).max() < 5.0, (key, js, out, float(np.abs(z).max()))
+            assert out <= max(2, int(0.03 * z.size)) and np.abs(z).max() < 5.0, (key, js, out, float(np.abs(z).max()))
             assert 0.4 < np.mean(z * z) < 1.9, (key, js, float(np.mean(z * z)))
     # the case is not trivial: the hot wall heats the gas next to it and thins it out
     yc = np.asarray(field_case(1).mesh.node_coords)[1, np.asarray(field_case(1).mesh.cell_nodes) - 1].mean(axis=0)
