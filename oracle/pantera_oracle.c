@@ -1462,9 +1462,10 @@ static int ncells(const po_ctx* w) {
     return (w->c.grid_type == PGPU_UNSTRUCTURED) ? w->nc : w->c.nx * w->c.ny;
 }
 
-/* ref: src/collisions.f90:37-149 DSMC_COLLISIONS (index counting sort by cell, then per-cell VSS_COLLIS).
- * Only the per-cell arrays NPCALL/IOFALL/INDALL are used by VSS_COLLIS; the per-(species,cell)
- * arrays NPC/IOF/IND feed VAHEDI_COLLIS, which is out of scope. */
+/* ref: src/collisions.f90:37-149 DSMC_COLLISIONS (index counting sorts, then per-cell VSS_COLLIS).
+ * Only the per-cell arrays NPCALL/IOFALL/INDALL are used by VSS_COLLIS; the per-(species,cell) arrays NPC/IOF/IND feed
+ * VAHEDI_COLLIS, which is out of scope -- but the reference allocates, counts and fills BOTH sets every step (:55-112,
+ * :141-147), so this restatement does too: it is also the CPU arm of the benchmark and must not be flattered. */
 int po_collide(po_ctx* w, int32_t tID, int64_t* timestep_coll, int64_t* timestep_reac) {
     if (!w->sigmas) FAIL(w, PGPU_ERR_STATE, "po_collide: VSS parameters not set");
     clock_t t0 = clock();
@@ -1472,21 +1473,36 @@ int po_collide(po_ctx* w, int32_t tID, int64_t* timestep_coll, int64_t* timestep
     int64_t np = w->np;
     free(w->npcall);
     w->npcall = (int32_t*)calloc((size_t)nc, sizeof(int32_t));
+    const int ns = w->ns;
     int64_t* iofall = (int64_t*)malloc(sizeof(int64_t) * (size_t)nc);
     int32_t* indall = (int32_t*)malloc(sizeof(int32_t) * (size_t)(np > 0 ? np : 1));
+    int32_t* npc = (int32_t*)calloc((size_t)nc * ns, sizeof(int32_t));      /* NPC(N_SPECIES, NCELLS) */
+    int64_t* iof = (int64_t*)malloc(sizeof(int64_t) * (size_t)nc * ns);     /* IOF(N_SPECIES, NCELLS) */
+    int32_t* ind = (int32_t*)malloc(sizeof(int32_t) * (size_t)(np > 0 ? np : 1));
     for (int64_t jp = 0; jp < np; jp++) {
-        int jc = w->p[jp].IC;
-        if (jc < 1 || jc > nc) { free(iofall); free(indall); FAIL(w, PGPU_ERR_INVALID, "po_collide: particle %lld has IC=%d outside 1..%d", (long long)jp, jc, nc); }
+        int jc = w->p[jp].IC, js = w->p[jp].S_ID;
+        if (jc < 1 || jc > nc || js < 1 || js > ns) {
+            free(iofall); free(indall); free(npc); free(iof); free(ind);
+            FAIL(w, PGPU_ERR_INVALID, "po_collide: particle %lld has IC=%d outside 1..%d or S_ID=%d outside 1..%d", (long long)jp, jc, nc, js, ns);
+        }
+        npc[(size_t)(jc - 1) * ns + (js - 1)]++;
         w->npcall[jc - 1]++;
     }
-    int64_t idx = 0;
+    int64_t idx = 0, idxall = 0;
     for (int jc = 0; jc < nc; jc++) {
-        iofall[jc] = idx;
-        idx += w->npcall[jc];
+        iofall[jc] = idxall;
+        idxall += w->npcall[jc];
+        for (int js = 0; js < ns; js++) {
+            iof[(size_t)jc * ns + js] = idx;
+            idx += npc[(size_t)jc * ns + js];
+        }
     }
     int32_t* fill = (int32_t*)calloc((size_t)nc, sizeof(int32_t));
+    memset(npc, 0, sizeof(int32_t) * (size_t)nc * ns);
     for (int64_t jp = 0; jp < np; jp++) {
-        int jc = w->p[jp].IC - 1;
+        int jc = w->p[jp].IC - 1, js = w->p[jp].S_ID - 1;
+        ind[iof[(size_t)jc * ns + js] + npc[(size_t)jc * ns + js]] = (int32_t)jp;
+        npc[(size_t)jc * ns + js]++;
         indall[iofall[jc] + fill[jc]] = (int32_t)jp;
         fill[jc]++;
     }
@@ -1502,6 +1518,9 @@ int po_collide(po_ctx* w, int32_t tID, int64_t* timestep_coll, int64_t* timestep
     }
     free(iofall);
     free(indall);
+    free(npc);
+    free(iof);
+    free(ind);
     if (timestep_coll) *timestep_coll = w->timestep_coll;
     if (timestep_reac) *timestep_reac = w->timestep_reac;
     w->tsec[2] += (double)(clock() - t0) / CLOCKS_PER_SEC;
