@@ -279,3 +279,87 @@ def test_mcc_collisions_oracle_matches_fortran_reading(oracle):
         assert float(out["EROT"][k]) == pytest.approx(fh(e["erot"]), rel=1e-11, abs=1e-33), k
         assert float(out["EVIB"][k]) == pytest.approx(fh(e["evib"]), rel=1e-11, abs=1e-33), k
         assert (out["X"][k], out["Y"][k], out["Z"][k]) == tuple(e["pos"])
+
+
+# ---- EXCHANGE --------------------------------------------------------------------------------------------------------
+def fortran_exchange(stores, owner_of):
+    """Plain-Python reading of EXCHANGE + COUNTING_SORT (src/grid_and_partition.f90:482-518, 525-622) for all ranks at once.
+    stores[r]: list of (id, ic) in store order; owner_of(ic) = PROC_FROM_CELL.  Returns the stores after the exchange."""
+    nr = len(stores)
+    sendbufs, sendcounts = [], []
+    for r in range(nr):
+        p = list(stores[r])
+        np_proc = len(p)
+        sendbuf, sendcount = [], [0] * nr
+        ip = np_proc
+        while ip >= 1:                                   # from the last particle to the first
+            jproc = owner_of(p[ip - 1][1])
+            if jproc != r:
+                sendcount[jproc] += 1
+                sendbuf.append(p[ip - 1])
+                p[ip - 1] = p[np_proc - 1]               # REMOVE_PARTICLE_ARRAY: the last one takes the place
+                np_proc -= 1
+            ip -= 1
+        stores[r] = p[:np_proc]
+        disp = list(sendcount)                           # COUNTING_SORT: inclusive displacements, filled from the back
+        for i in range(1, nr):
+            disp[i] = disp[i] + disp[i - 1]
+        srt = [None] * len(sendbuf)
+        for i in range(len(sendbuf), 0, -1):
+            iproc = owner_of(sendbuf[i - 1][1])
+            srt[disp[iproc] - 1] = sendbuf[i - 1]
+            disp[iproc] -= 1
+        sendbufs.append(srt)
+        sendcounts.append(sendcount)
+    for r in range(nr):                                  # MPI_ALLTOALLV: blocks in source-rank order, then ADD_PARTICLE_ARRAY
+        for s in range(nr):
+            off = sum(sendcounts[s][:r])
+            stores[r] = stores[r] + sendbufs[s][off:off + sendcounts[s][r]]
+    return stores
+
+
+def test_exchange_store_order_oracle_matches_fortran_reading():
+    """The ORDER of a rank's particle array after EXCHANGE decides which pairs its sequential MT stream selects afterwards:
+    reverse sweep with swap-with-last removal, stable counting sort of the send buffer, blocks appended in source-rank order."""
+    from oracle.binding import load_oracle
+    nr = 3
+    rng = np.random.default_rng(31)
+    libs, stores = [], []
+    w0 = wl.c5_channel(6, 2, 2, ppc=1)
+    mesh = w0.mesh
+    from pantera_pic_dsmc_b200 import meshgen as mg
+    cell_procs = mg.assign_cells_to_procs(mesh, nr, 0)
+    assert set(np.unique(cell_procs)) == {0, 1, 2}
+    for r in range(nr):
+        w = wl.c5_channel(6, 2, 2, ppc=1)
+        w.mesh.cell_procs = cell_procs
+        w.cfg.rank, w.cfg.nranks, w.cfg.track_id = r, nr, 1
+        n = 40 + 7 * r
+        p = wl.new_particles(n)
+        p["IC"] = rng.integers(1, mesh.nc + 1, n)         # anywhere in the mesh: about two thirds must be shipped
+        p["S_ID"] = 1
+        p["ID"] = 1000 * (r + 1) + np.arange(n)
+        p["X"] = rng.random(n)
+        w.particles = p
+        o = load_oracle(rng_mode=0)
+        wl.apply(o, w)
+        libs.append(o)
+        stores.append([(int(i), int(c)) for i, c in zip(p["ID"], p["IC"])])
+    packed = [o.exchange_pack(nr) for o in libs]          # local half on every rank, then the all-to-all by hand
+    for r in range(nr):
+        for s in range(nr):
+            if s == r:
+                continue
+            buf, cnt = packed[s]
+            off = int(cnt[:r].sum())
+            if cnt[r]:
+                libs[r].append_particles(buf[off:off + int(cnt[r])])
+    expect = fortran_exchange(stores, lambda ic: int(cell_procs[ic - 1]))
+    moved = 0
+    for r in range(nr):
+        got = libs[r].download_particles()
+        assert [int(i) for i in got["ID"]] == [i for i, _ in expect[r]], r
+        assert all(cell_procs[ic - 1] == r for ic in got["IC"])
+        moved += sum(1 for i, _ in expect[r] if i // 1000 != r + 1)
+        libs[r].close()
+    assert moved > 50
