@@ -363,3 +363,140 @@ def test_exchange_store_order_oracle_matches_fortran_reading():
         moved += sum(1 for i, _ in expect[r] if i // 1000 != r + 1)
         libs[r].close()
     assert moved > 50
+
+
+# ---- field gather + Boris kick -----------------------------------------------------------------------------------------
+def cic_e_reading(cfg, ef, x, y, ic):
+    """APPLY_E_FIELD on a uniform rectilinear 2-D grid (src/fields.f90:4209-4216) with COMPUTE_WEIGHTS (:5341-5404):
+    E_FIELD(3, 0:NPY-1, 0:NPX-1) indexed (:, INDJ, INDI); ef is that array, shape (3, NPY, NPX)."""
+    nx, ny = cfg.nx, cfg.ny
+    hx = (cfg.xmax - cfg.xmin) / float(nx)
+    hy = (cfg.ymax - cfg.ymin) / float(ny)
+    i = (ic - 1) % nx
+    j = (ic - 1) // nx
+    cell_xmin = i * hx + cfg.xmin
+    cell_ymin = j * hy + cfg.ymin
+    fx = (x - cell_xmin) / hx
+    fy = (y - cell_ymin) / hy
+    wts = [(1.0 - fx) * (1.0 - fy), fx * (1.0 - fy), (1.0 - fx) * fy, fx * fy]
+    indi = [i, i + 1, i, i + 1]
+    indj = [j, j, j + 1, j + 1]
+    e = []
+    for c in range(3):
+        e.append(wts[0] * ef[c, indj[0], indi[0]] + wts[1] * ef[c, indj[1], indi[1]] + wts[2] * ef[c, indj[2], indi[2]]
+                 + wts[3] * ef[c, indj[3], indi[3]])
+    return [float(v) for v in e]
+
+
+def check_cic_gather(lib):
+    """Ions and electrons on a 5 x 4 periodic grid, a nodal E with a different value in every node and component, a uniform
+    external B, a step short enough that no side is reached: V_NEW = Boris(E gathered at the OLD position), X = X + V_NEW DT."""
+    from test_fortran_pins import boris_reading
+    sp = wl.load_species("ar", ["Ar+", "e"])
+    nx, ny = 5, 4
+    bext = [0.011, -0.007, 0.023]
+    cfg = capi.make_config(dims=2, nx=nx, ny=ny, xmin=-0.2, xmax=0.8, ymin=0.1, ymax=0.5, dt=4e-11, pic_type=capi.PIC_EXPLICIT,
+                           bool_periodic=[1] * 4, bool_z_periodic=1, external_b=bext, collision_type=capi.NO_COLL)
+    rng = np.random.default_rng(77)
+    n = 24
+    p = wl.new_particles(n)
+    p["X"] = cfg.xmin + (cfg.xmax - cfg.xmin) * (0.02 + 0.96 * rng.random(n))
+    p["Y"] = cfg.ymin + (cfg.ymax - cfg.ymin) * (0.02 + 0.96 * rng.random(n))
+    p["Z"] = 0.3 * (rng.random(n) - 0.5)
+    p["S_ID"] = rng.integers(1, 3, n)
+    p["VX"], p["VY"], p["VZ"] = (rng.standard_normal(n) * 3e4 for _ in range(3))
+    p["DTRIM"] = cfg.dt
+    hx, hy = (cfg.xmax - cfg.xmin) / nx, (cfg.ymax - cfg.ymin) / ny
+    p["IC"] = ((p["X"] - cfg.xmin) / hx).astype(np.int32) + nx * ((p["Y"] - cfg.ymin) / hy).astype(np.int32) + 1
+    ef = np.asfortranarray(rng.standard_normal((3, ny + 1, nx + 1)) * 2e4)
+    w = wl.Workload("pin CIC gather", cfg, sp, p, efield=ef)
+    w.cfg.track_id = 1
+    wl.apply(lib, w)
+    lib.advect(1)
+    out = util.by_id(lib.download_particles())
+    assert len(out) == n
+    for k in range(n):
+        s = int(p["S_ID"][k]) - 1
+        e = cic_e_reading(cfg, ef, float(p["X"][k]), float(p["Y"][k]), int(p["IC"][k]))
+        vn = boris_reading([float(p["VX"][k]), float(p["VY"][k]), float(p["VZ"][k])], float(sp.charge[s]), float(sp.mass[s]), e, bext, cfg.dt)
+        assert [float(out["VX"][k]), float(out["VY"][k]), float(out["VZ"][k])] == vn, (k, vn)
+        assert float(out["X"][k]) == float(p["X"][k]) + vn[0] * cfg.dt and float(out["Y"][k]) == float(p["Y"][k]) + vn[1] * cfg.dt
+
+
+def test_cic_field_gather_oracle_matches_fortran_reading(oracle):
+    check_cic_gather(oracle)
+
+
+@pytest.mark.gpu
+def test_cic_field_gather_device_matches_fortran_reading(gpu):
+    check_cic_gather(gpu)
+
+
+def check_nodal_b_gather(lib):
+    """APPLY_B_FIELD (src/fields.f90:4227-4249): B = sum_j B_FIELD(:, 1, V_j) PSI_j(x, y) on the pin's triangles (not
+    axisymmetric here), + EXTERNAL_B_FIELD, with the cell-constant E of the unstructured branch of APPLY_E_FIELD."""
+    from test_fortran_pins import boris_reading
+    m = pin_tri_mesh()
+    mm = PINS["tri_mesh"]
+    xy = np.array(mm["nodes"])
+    tri = np.array(mm["cells"]) - 1
+    # BASIS_COEFFS of the triangles, src/grid_and_partition.f90:1455-1476
+    bc = np.zeros((3, 3, m.nc))
+    for c in range(m.nc):
+        (x1, y1), (x2, y2), (x3, y3) = xy[tri[c, 0]], xy[tri[c, 1]], xy[tri[c, 2]]
+        area = 0.5 * abs(x1 * (y2 - y3) + x2 * (y3 - y1) + x3 * (y1 - y2))
+        raw = [[y2 - y3, -(x2 - x3), x2 * y3 - x3 * y2], [-(y1 - y3), x1 - x3, x3 * y1 - x1 * y3], [-(y2 - y1), x2 - x1, x1 * y2 - x2 * y1]]
+        for i in range(3):
+            for j in range(3):
+                bc[j, i, c] = 0.5 * raw[i][j] / area
+    m.basis_coeffs = np.asfortranarray(bc)
+    m.cell_volumes = np.array([0.5 * abs(xy[t[0], 0] * (xy[t[1], 1] - xy[t[2], 1]) + xy[t[1], 0] * (xy[t[2], 1] - xy[t[0], 1])
+                                         + xy[t[2], 0] * (xy[t[0], 1] - xy[t[1], 1])) for t in tri])
+    sp = wl.load_species("ar", ["Ar+", "e"])
+    bext = [0.002, 0.004, -0.003]
+    cfg = capi.make_config(dims=2, grid_type=capi.UNSTRUCTURED, nx=1, ny=1, xmin=0.0, xmax=0.09, ymin=0.01, ymax=0.05, zmin=-0.5, zmax=0.5,
+                           dt=2e-11, fnum=1.0, collision_type=capi.NO_COLL, pic_type=capi.PIC_EXPLICIT, bool_z_periodic=1, external_b=bext,
+                           dump_bound_avg_every=0)
+    rng = np.random.default_rng(5)
+    n = m.nc
+    p = wl.new_particles(n)
+    lam = rng.dirichlet([2.0, 2.0, 2.0], n)                    # one particle well inside every triangle
+    p["X"] = (lam * xy[tri, 0]).sum(axis=1)
+    p["Y"] = (lam * xy[tri, 1]).sum(axis=1)
+    p["IC"] = np.arange(1, n + 1)
+    p["S_ID"] = rng.integers(1, 3, n)
+    p["VX"], p["VY"], p["VZ"] = (rng.standard_normal(n) * 2e4 for _ in range(3))
+    p["DTRIM"] = cfg.dt
+    bcs = dict(particle_bc=[capi.SPECULAR] * 4, wall_temp=[300.0] * 4, acc_n=[1.0] * 4, acc_t=[1.0] * 4)
+    ef = np.asfortranarray(rng.standard_normal((3, m.nc)) * 1e4)
+    bf = np.asfortranarray(rng.standard_normal((3, m.nn)) * 0.02)
+    w = wl.Workload("pin nodal B", cfg, sp, p, mesh=m, bcs=bcs, efield=ef)
+    w.cfg.track_id = 1
+    wl.apply(lib, w)
+    lib.set_bfield(bf)
+    lib.advect(1)
+    out = util.by_id(lib.download_particles())
+    assert len(out) == n
+    for k in range(n):
+        c = k
+        x, y = float(p["X"][k]), float(p["Y"][k])
+        b = [0.0, 0.0, 0.0]
+        for j in range(3):
+            psij = x * bc[0, j, c] + y * bc[1, j, c] + bc[2, j, c]
+            for a in range(3):
+                b[a] = b[a] + bf[a, tri[c, j]] * psij
+        b = [float(b[a] + bext[a]) for a in range(3)]
+        s = int(p["S_ID"][k]) - 1
+        vn = boris_reading([float(p["VX"][k]), float(p["VY"][k]), float(p["VZ"][k])], float(sp.charge[s]), float(sp.mass[s]),
+                           [float(v) for v in ef[:, c]], b, cfg.dt)
+        assert [float(out["VX"][k]), float(out["VY"][k]), float(out["VZ"][k])] == vn, (k, vn)
+        assert out["IC"][k] == k + 1
+
+
+def test_nodal_b_gather_oracle_matches_fortran_reading(oracle):
+    check_nodal_b_gather(oracle)
+
+
+@pytest.mark.gpu
+def test_nodal_b_gather_device_matches_fortran_reading(gpu):
+    check_nodal_b_gather(gpu)
