@@ -500,3 +500,184 @@ def test_nodal_b_gather_oracle_matches_fortran_reading(oracle):
 @pytest.mark.gpu
 def test_nodal_b_gather_device_matches_fortran_reading(gpu):
     check_nodal_b_gather(gpu)
+
+
+# ---- TALLY_PARTICLE_TO_BOUNDARY ------------------------------------------------------------------------------------------
+def test_boundary_tallies_oracle_match_fortran_reading(oracle):
+    """The tet walk of the first pin set once more, this time accumulating TIMESTEP_NIN/NOUT/P*IN/P*OUT/EIN/EOUT as
+    TALLY_PARTICLE_TO_BOUNDARY does (src/postprocess.f90:1098-1147): the incident tally with the velocity before the wall
+    model, the reflected one after it (src/timecycle.f90:1373-1376, 1616-1621); K = FNUM*MOLMASS/AREA/DT, signs, the
+    (boundary element, species) index.  The walk below is a plain-Python reading of src/timecycle.f90:1257-1312, 1433-1443."""
+    import test_fortran_pins as t1
+    pins1 = t1.PINS
+    mesh = pins1["tet_mesh"]
+    cases = pins1["tet_walk"]["cases"]
+    dt = fh(pins1["tet_walk"]["dt"])
+    w = t1.tet_workload(cases, dt)
+    w.cfg.fnum = 3.0e12
+    w.cfg.dump_bound_start, w.cfg.dump_bound_avg_every = 0, 1
+    w.cfg.track_id = 1
+    nodes, cells = np.array(mesh["nodes"]), np.array(mesh["cells"])
+    ind = [[1, 3, 2], [1, 2, 4], [2, 3, 4], [1, 4, 3]]
+    bidx = np.full((4, len(cells)), -1, dtype=np.int32)
+    areas = []
+    for c in range(len(cells)):
+        for j in range(4):
+            if mesh["neighbors"][c][j] == -1:
+                a, b, cc = (nodes[cells[c][ind[j][m] - 1] - 1] for m in range(3))
+                cr = np.cross(b - a, cc - a)
+                areas.append(0.5 * float(np.sqrt(cr[0] * cr[0] + cr[1] * cr[1] + cr[2] * cr[2])))
+                bidx[j, c] = len(areas)
+    nb = len(areas)
+    w.mesh.face_boundary_index = np.asfortranarray(bidx)
+    w.mesh.nboundcells = nb
+    w.mesh.boundary_area = np.array(areas)
+    wl.apply(oracle, w)
+    oracle.advect(1)
+    got = oracle.get_boundary_tallies(nb, 2)          # (10, ns, nboundcells): NIN, NOUT, PXIN, PYIN, PZIN, PXOUT, PYOUT, PZOUT, EIN, EOUT
+    sp = w.species
+    exp = np.zeros((10, 2, nb))
+    hits = 0
+    for c in cases:                                   # particles in store order
+        q = {k: fh(v) if isinstance(v, str) and k != "sid" else v for k, v in c["inp"].items()}
+        x, y, z, vx, vy, vz, ic = q["x"], q["y"], q["z"], q["vx"], q["vy"], q["vz"], q["ic"]
+        js = sp.id(q["sid"]) - 1
+        molmass = float(sp.mass[js])
+        dtrim = dt
+        while dtrim > 0.0:
+            dtcoll, boundcoll = dtrim, -1
+            for i in range(1, 5):
+                n = mesh["normal"][ic - 1][i - 1]
+                P = mesh["nodes"][mesh["cells"][ic - 1][i - 1] - 1]
+                vn = vx * n[0] + vy * n[1] + vz * n[2]
+                dx = (P[0] - x) * n[0] + (P[1] - y) * n[1] + (P[2] - z) * n[2]
+                if vn >= 0.0 and vn * dtcoll >= dx:
+                    dtcoll, boundcoll = dx / vn, i
+            if boundcoll == -1:
+                x, y, z = x + vx * dtrim, y + vy * dtrim, z + vz * dtrim
+                dtrim = 0.0
+                continue
+            x, y, z = x + vx * dtcoll, y + vy * dtcoll, z + vz * dtcoll
+            dtrim = dtrim - dtcoll
+            nbr = mesh["neighbors"][ic - 1][boundcoll - 1]
+            if nbr != -1:
+                ic = nbr
+                continue
+            hits += 1
+            b = bidx[boundcoll - 1, ic - 1] - 1
+            area = areas[b]
+            k = w.cfg.fnum * molmass / area / dt
+            exp[0, js, b] = exp[0, js, b] + w.cfg.fnum / area / dt
+            exp[2, js, b] = exp[2, js, b] + k * vx
+            exp[3, js, b] = exp[3, js, b] + k * vy
+            exp[4, js, b] = exp[4, js, b] + k * vz
+            exp[8, js, b] = exp[8, js, b] + k * (vx * vx + vy * vy + vz * vz)
+            fn = [-v for v in mesh["normal"][ic - 1][boundcoll - 1]]
+            vdotn = vx * fn[0] + vy * fn[1] + vz * fn[2]
+            vx, vy, vz = vx - 2.0 * vdotn * fn[0], vy - 2.0 * vdotn * fn[1], vz - 2.0 * vdotn * fn[2]
+            exp[1, js, b] = exp[1, js, b] - w.cfg.fnum / area / dt
+            exp[5, js, b] = exp[5, js, b] - k * vx
+            exp[6, js, b] = exp[6, js, b] - k * vy
+            exp[7, js, b] = exp[7, js, b] - k * vz
+            exp[9, js, b] = exp[9, js, b] - k * (vx * vx + vy * vy + vz * vz)
+    assert hits >= 5 and np.count_nonzero(exp[0]) >= 3
+    assert np.array_equal(got, exp), np.abs(got - exp).max()
+
+
+# ---- BASIS_COEFFS and DEPOSIT_CHARGE on tetrahedra and segments --------------------------------------------------------------
+def basis_tet_reading(P, volume):
+    """BASIS_COEFFS(4, 4) of one tetrahedron, src/grid_and_partition.f90:2013-2036 (P: 4 nodes x 3 coordinates)."""
+    (X1, Y1, Z1), (X2, Y2, Z2), (X3, Y3, Z3), (X4, Y4, Z4) = ([float(v) for v in row] for row in P)
+    B = [[0.0] * 4 for _ in range(4)]                      # B[j][i] = BASIS_COEFFS(j+1, i+1)
+    B[0][0] = Y2*Z3-Y3*Z2 -Y2*Z4+Y4*Z2 +Y3*Z4-Y4*Z3
+    B[1][0] = -X2*Z3+X3*Z2 +X2*Z4-X4*Z2 -X3*Z4+X4*Z3
+    B[2][0] = X2*Y3-X3*Y2 -X2*Y4+X4*Y2 +X3*Y4-X4*Y3
+    B[3][0] = -X2*Y3*Z4 +X3*Y2*Z4 +X2*Y4*Z3 -X4*Y2*Z3 -X3*Y4*Z2 +X4*Y3*Z2
+    B[0][1] = -Y1*Z3+Y3*Z1 +Y1*Z4-Y4*Z1 -Y3*Z4+Y4*Z3
+    B[1][1] = X1*Z3-X3*Z1 -X1*Z4+X4*Z1 +X3*Z4-X4*Z3
+    B[2][1] = -X1*Y3+X3*Y1 +X1*Y4-X4*Y1 -X3*Y4+X4*Y3
+    B[3][1] = X1*Y3*Z4 -X3*Y1*Z4 -X1*Y4*Z3 +X4*Y1*Z3 +X3*Y4*Z1 -X4*Y3*Z1
+    B[0][2] = Y1*Z2-Y2*Z1 -Y1*Z4+Y4*Z1 +Y2*Z4-Y4*Z2
+    B[1][2] = -X1*Z2+X2*Z1 +X1*Z4-X4*Z1 -X2*Z4+X4*Z2
+    B[2][2] = X1*Y2-X2*Y1 -X1*Y4+X4*Y1 +X2*Y4-X4*Y2
+    B[3][2] = -X1*Y2*Z4 +X2*Y1*Z4 +X1*Y4*Z2 -X4*Y1*Z2 -X2*Y4*Z1 +X4*Y2*Z1
+    B[0][3] = -Y1*Z2+Y2*Z1 +Y1*Z3-Y3*Z1 -Y2*Z3+Y3*Z2
+    B[1][3] = X1*Z2-X2*Z1 -X1*Z3+X3*Z1 +X2*Z3-X3*Z2
+    B[2][3] = -X1*Y2+X2*Y1 +X1*Y3-X3*Y1 -X2*Y3+X3*Y2
+    B[3][3] = X1*Y2*Z3 -X2*Y1*Z3 -X1*Y3*Z2 +X3*Y1*Z2 +X2*Y3*Z1 -X3*Y2*Z1
+    return [[-B[j][i] / 6.0 / volume for i in range(4)] for j in range(4)]
+
+
+def test_basis_coeffs_and_deposit_on_tets_and_segments_match_fortran_reading(oracle):
+    """(1) meshgen's BASIS_COEFFS / CELL_VOLUMES (what READ_3D/1D_UNSTRUCTURED_GRID_SU2 would hand over) against the
+    Fortran expressions evaluated here, on a jittered tet box and a line; the basis is the barycentric one (PSI_i(x_j) =
+    delta_ij).  (2) DEPOSIT_CHARGE (src/fields.f90:5459-5487) of single charged particles on tetrahedra (RHO_Q =
+    K*CHARGE*FNUM) and on segments (RHO_Q = K*CHARGE*FNUM/(YMAX-YMIN)/(ZMAX-ZMIN)), bit for bit."""
+    QE, EPS0 = 1.602176634e-19, 8.8541878128e-12
+    sp = wl.load_species("ar", ["Ar+", "e", "Ar"])
+    # ---- tetrahedra
+    w = wl.c5_channel(3, 2, 2, ppc=1, jitter=0.2)
+    m = w.mesh
+    xyz = np.asarray(m.node_coords)
+    cn = np.asarray(m.cell_nodes) - 1
+    B = np.asarray(m.basis_coeffs)
+    for c in (0, 5, 17, m.nc - 1):
+        P = xyz[:, cn[:, c]].T
+        a, b, cc = P[1] - P[0], P[2] - P[0], P[3] - P[0]
+        vol = abs(cc[0] * (a[1] * b[2] - a[2] * b[1]) + cc[1] * (a[2] * b[0] - a[0] * b[2]) + cc[2] * (a[0] * b[1] - a[1] * b[0])) / 6.0
+        assert float(m.cell_volumes[c]) == vol
+        R = basis_tet_reading(P, vol)
+        assert np.array_equal(B[:, :, c], np.array(R)), c
+        psi = P @ B[:3, :, c] + B[3, :, c]                 # psi[node j, function i]
+        assert np.allclose(psi, np.eye(4), atol=1e-9)
+    w.species = sp
+    w.cfg.pic_type = capi.PIC_EXPLICIT
+    w.cfg.collision_type = capi.NO_COLL
+    w.cfg.fnum, w.cfg.eps_scaling = 2.5e6, 1.3
+    ic = 18
+    lam = np.array([0.1, 0.2, 0.3, 0.4])
+    xp = [float(v) for v in xyz[:, cn[:, ic - 1]] @ lam]
+    p = wl.new_particles(2)
+    p["X"], p["Y"], p["Z"] = xp[0], xp[1], xp[2]
+    p["S_ID"] = [sp.id("Ar"), sp.id("Ar+")]                 # the neutral is skipped
+    p["IC"] = ic
+    p["DTRIM"] = w.cfg.dt
+    w.particles = p
+    wl.apply(oracle, w)
+    rhs = oracle.deposit_charge(m.nn)
+    K = QE / (EPS0 * w.cfg.eps_scaling ** 2)
+    rho_q = K * float(sp.charge[sp.id("Ar+") - 1]) * w.cfg.fnum
+    want = np.zeros(m.nn)
+    R = basis_tet_reading(xyz[:, cn[:, ic - 1]].T, float(m.cell_volumes[ic - 1]))
+    for pp in range(4):
+        psip = R[0][pp] * xp[0] + R[1][pp] * xp[1] + R[2][pp] * xp[2] + R[3][pp]
+        want[cn[pp, ic - 1]] = 0.0 + rho_q * psip
+    assert np.array_equal(rhs, want) and np.count_nonzero(rhs) == 4
+    assert np.allclose(want[cn[:, ic - 1]] / rho_q, lam, atol=1e-9)          # the weights are the barycentric coordinates
+    # ---- segments
+    w = wl.c4_ccp_1d(ncells=9, n_per_species=1)
+    m = w.mesh
+    x = np.asarray(m.node_coords)[0]
+    cn = np.asarray(m.cell_nodes) - 1
+    B = np.asarray(m.basis_coeffs)
+    for c in range(m.nc):
+        x1, x2 = float(x[cn[0, c]]), float(x[cn[1, c]])
+        length = abs(x2 - x1)
+        want_b = [[-1.0 / length, 1.0 / length], [x2 / length, -x1 / length]]      # BASIS_COEFFS(j, i), :970-977
+        assert np.array_equal(B[:, :, c], np.array(want_b)), c
+    w.cfg.collision_type = capi.NO_COLL
+    w.cfg.fnum = 4.0e9
+    w.cfg.ymin, w.cfg.ymax, w.cfg.zmin, w.cfg.zmax = 0.0, 0.02, 0.0, 0.05
+    ic = 4
+    xp = float(0.3 * x[cn[0, ic - 1]] + 0.7 * x[cn[1, ic - 1]])
+    p = w.particles[:1].copy()
+    p["X"], p["IC"], p["S_ID"] = xp, ic, w.species.id("e")
+    w.particles = p
+    w.efield = None
+    wl.apply(oracle, w)
+    rhs = oracle.deposit_charge(m.nn)
+    rho_q = (QE / (EPS0 * 1.0 ** 2)) * float(w.species.charge[w.species.id("e") - 1]) * w.cfg.fnum / (w.cfg.ymax - w.cfg.ymin) / (w.cfg.zmax - w.cfg.zmin)
+    want = np.zeros(m.nn)
+    for pp in range(2):
+        want[cn[pp, ic - 1]] = 0.0 + rho_q * (float(B[0, pp, ic - 1]) * xp + float(B[1, pp, ic - 1]))
+    assert np.array_equal(rhs, want) and np.count_nonzero(rhs) == 2
