@@ -681,3 +681,62 @@ def test_basis_coeffs_and_deposit_on_tets_and_segments_match_fortran_reading(ora
     for pp in range(2):
         want[cn[pp, ic - 1]] = 0.0 + rho_q * (float(B[0, pp, ic - 1]) * xp + float(B[1, pp, ic - 1]))
     assert np.array_equal(rhs, want) and np.count_nonzero(rhs) == 2
+
+
+# ---- dielectric surface charging ---------------------------------------------------------------------------------------------
+def test_dielectric_surface_charge_oracle_matches_fortran_reading(oracle):
+    """An ion and an electron reach the face z = 0 of the pin tetrahedron, whose group is a DIELECTRIC_BC for the field and a
+    specular wall for the particles: SURFACE_CHARGE(VP) += K*CHARGE*FNUM * PSI_P(hit point) on the four nodes of the cell
+    (src/timecycle.f90:1398-1430), PSI from BASIS_COEFFS as the Fortran evaluates them; a neutral leaves no charge."""
+    import test_fortran_pins as t1
+    QE, EPS0 = 1.602176634e-19, 8.8541878128e-12
+    mesh = t1.PINS["tet_mesh"]
+    m = t1.pin_tet_mesh()
+    nodes, cells = np.array(mesh["nodes"]), np.array(mesh["cells"])
+    B = np.zeros((4, 4, m.nc))
+    for c in range(m.nc):
+        B[:, :, c] = np.array(basis_tet_reading(nodes[cells[c] - 1], float(m.cell_volumes[c])))
+    m.basis_coeffs = np.asfortranarray(B)
+    sp = wl.load_species("ar", ["Ar+", "e", "Ar"])
+    dt = 1.0e-3
+    cfg = capi.make_config(dims=3, grid_type=capi.UNSTRUCTURED, nx=1, ny=1, xmin=0.0, xmax=2.0, ymin=0.0, ymax=2.0, zmin=0.0, zmax=2.0,
+                           dt=dt, fnum=6.0e7, collision_type=capi.NO_COLL, dump_bound_avg_every=0, eps_scaling=1.5)
+    starts = [("Ar+", [0.3, 0.2, 0.2], [210.0, -95.0, -480.0]), ("e", [0.25, 0.3, 0.15], [-130.0, 60.0, -520.0]),
+              ("Ar", [0.2, 0.25, 0.1], [50.0, 40.0, -400.0])]
+    p = wl.new_particles(3)
+    for k, (name, x, v) in enumerate(starts):
+        p["X"][k], p["Y"][k], p["Z"][k] = x
+        p["VX"][k], p["VY"][k], p["VZ"][k] = v
+        p["S_ID"][k] = sp.id(name)
+    p["IC"] = 1
+    p["DTRIM"] = dt
+    bcs = dict(particle_bc=[capi.SPECULAR] * 4, field_bc=[capi.DIELECTRIC_BC, capi.NO_BC, capi.NO_BC, capi.NO_BC],
+               wall_temp=[300.0] * 4, acc_n=[1.0] * 4, acc_t=[1.0] * 4)
+    w = wl.Workload("pin dielectric", cfg, sp, p, mesh=m, bcs=bcs)
+    wl.apply(oracle, w)
+    oracle.advect(1)
+    got = np.zeros(m.nn)
+    oracle._call("get_surface_charge", got.ctypes.data_as(__import__("ctypes").c_void_p), __import__("ctypes").c_int64(m.nn))
+    want = np.zeros(m.nn)
+    K = QE / (EPS0 * cfg.eps_scaling ** 2)
+    for name, x, v in starts:
+        ic = 1
+        # first crossing: the face loop of src/timecycle.f90:1257-1305 in cell 1
+        dtcoll, boundcoll = dt, -1
+        for i in range(1, 5):
+            n = mesh["normal"][ic - 1][i - 1]
+            P = mesh["nodes"][mesh["cells"][ic - 1][i - 1] - 1]
+            vn = v[0] * n[0] + v[1] * n[1] + v[2] * n[2]
+            dx = (P[0] - x[0]) * n[0] + (P[1] - x[1]) * n[1] + (P[2] - x[2]) * n[2]
+            if vn >= 0.0 and vn * dtcoll >= dx:
+                dtcoll, boundcoll = dx / vn, i
+        assert boundcoll == 1 and mesh["faces_pg"][0][0] == 1
+        hit = [x[k] + v[k] * dtcoll for k in range(3)]
+        charge = float(sp.charge[sp.id(name) - 1])
+        if abs(charge) >= 1.0e-6:
+            rho_q = K * charge * cfg.fnum
+            for i in range(4):
+                vp = cells[ic - 1][i]
+                psip = B[0, i, ic - 1] * hit[0] + B[1, i, ic - 1] * hit[1] + B[2, i, ic - 1] * hit[2] + B[3, i, ic - 1]
+                want[vp - 1] = want[vp - 1] + rho_q * psip
+    assert np.count_nonzero(want) >= 3 and np.array_equal(got, want), (got, want)   # (the basis function of the opposite node vanishes on the face)
