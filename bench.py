@@ -162,6 +162,8 @@ ALT = {
                "(north_star's single-GPU target configuration; particles streamed in from the host in batches)", 280.0),
     "c2-cyl": ("C2 air flow around a cylinder: 2-D half annulus of 2e5 triangles, N2/O2 free stream at 7 km/s emitted from the outer "
                "boundary on the device every step (BOUNDARIES_EMIT), diffuse cylinder at 1000 K, TCE reactions + Borgnakke-Larsen", 312.0),
+    "c3": ("C3 axisymmetric converging-diverging nozzle: 2e5 triangles (y = radius), N2/O2 inflow emitted at the inlet on the device every "
+           "step, CLL nozzle wall (300 K, 0.8/0.8), vacuum outlet, TCE reactions + Borgnakke-Larsen", 312.0),
     "c5-open": ("C5 3-D unstructured argon channel, open variant: vacuum end caps, inflow emitted at x = 0 on the device every step "
                 "(BOUNDARIES_EMIT), diffuse y-walls, specular z", 280.0),
     "c4": ("C4 1-D argon PIC-MCC (Vahedi null collision, LXCat-format tables), 512 segments: DEPOSIT_CHARGE + Poisson + "
@@ -169,13 +171,17 @@ ALT = {
 }
 
 
-EMITTING = ("c2-cyl", "c5-open")   # workloads whose timed step starts with BOUNDARIES_EMIT on the device
+EMITTING = ("c2-cyl", "c3", "c5-open")   # workloads whose timed step starts with BOUNDARIES_EMIT on the device
 
 
 def build_alt(name, n, small=False):
     from pantera_pic_dsmc_b200 import capi, workloads as wl
     if name == "c2-cyl":
         w = wl.c2_cylinder(n, ni=50, nj=80) if small else wl.c2_cylinder(n, ni=250, nj=400)
+        w.cfg.capacity = int(1.5 * n) + 65536
+        return w
+    if name == "c3":
+        w = wl.c3_nozzle(n, ni=100, nj=40) if small else wl.c3_nozzle(n)
         w.cfg.capacity = int(1.5 * n) + 65536
         return w
     if name == "c5-open":
@@ -249,7 +255,7 @@ def run_alt(args):
     name = args.workload
     desc, b_alg = ALT[name]
     n = args.particles if args.particles != 125_000_000 else {"c1": 10_000_000, "c1-grid": 100_000_000, "c2": 50_000_000, "c4": 10_000_000,
-                                                              "c5-1e9": 1_000_000_000, "c2-cyl": 20_000_000, "c5-open": 125_000_000}[name]
+                                                              "c5-1e9": 1_000_000_000, "c2-cyl": 20_000_000, "c3": 20_000_000, "c5-open": 125_000_000}[name]
     w = build_alt(name, n)
     gpu = capi.load_gpu(0)
     if name == "c5-1e9":
@@ -323,7 +329,7 @@ def run_alt(args):
     cpu = None
     if not args.no_cpu:
         if name in EMITTING:
-            ws = build_alt(name, 500_000 if name == "c2-cyl" else 491_520, small=True)
+            ws = build_alt(name, 491_520 if name == "c5-open" else 500_000, small=True)
         else:
             ws = build_alt(name, {"c1": 200_000, "c1-grid": 1_000_000, "c2": 500_000, "c4": 400_000}[name]) if name != "c1-grid" else wl.c1_argon_box(1_000_000, nx=128, ny=128)
         if name == "c2":

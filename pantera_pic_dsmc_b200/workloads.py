@@ -451,6 +451,63 @@ def c2_cylinder(n: int = 10_000_000, ni: int = 250, nj: int = 400, r_in: float =
     return w
 
 
+def c3_nozzle(n: int = 20_000_000, ni: int = 500, nj: int = 200, length: float = 0.3, r_in: float = 0.05, r_throat: float = 0.02,
+              r_out: float = 0.08, u_in: float = 400.0, T_in: float = 1000.0, nrho: float = 2e20, T_wall: float = 300.0,
+              acc: float = 0.8, dt: float = 2e-7, seed: int = 8, with_reactions: bool = True, rng_seed_global: int = 65644) -> Workload:
+    """C3 of SURVEY 8(d): axisymmetric converging-diverging nozzle, ni x nj quads cut into 2 ni nj triangles (y is the
+    radius; the axis y = 0 is a mesh boundary that an axisymmetric trajectory never reaches unless VZ = 0: specular).
+    Physical groups: 1 inlet (vacuum + EMIT tasks: N2 0.79 / O2 0.21 at u_in, T_in), 2 outlet (vacuum), 3 axis (specular),
+    4 nozzle wall (CLL at T_wall with accommodation acc/acc).  TCE + Borgnakke-Larsen collisions.  Starts filled with the
+    inlet gas at rest."""
+    sp = load_species("air", ["O2", "N2", "O", "N", "NO"])
+    reactions = df.read_reactions(os.path.join(DATA_DIR, "air.tce"), sp) if with_reactions else []
+    xs = np.linspace(0.0, length, ni + 1)
+    xt = 0.4 * length                                            # throat position
+    conv = r_throat + (r_in - r_throat) * np.cos(0.5 * np.pi * np.clip(xs / xt, 0.0, 1.0)) ** 2
+    div = r_throat + (r_out - r_throat) * np.sin(0.5 * np.pi * np.clip((xs - xt) / (length - xt), 0.0, 1.0)) ** 2
+    radius = np.where(xs <= xt, conv, div)
+    X = np.repeat(xs[:, None], nj + 1, axis=1)
+    Y = radius[:, None] * np.linspace(0.0, 1.0, nj + 1)[None, :]
+    Y[:, 0] = 0.0
+    mesh = mg.mapped_quads_to_tris(X, Y, zmin=0.0, zmax=1.0, axi=True)
+    mesh.pg_names = {"inlet": 1, "outlet": 2, "axis": 3, "wall": 4}
+    vol = float(np.sum(mesh.cell_volumes))
+    fnum = nrho * vol / n
+    cfg = capi.make_config(dims=2, axi=1, grid_type=capi.UNSTRUCTURED, nx=1, ny=1, xmin=0.0, xmax=length, ymin=0.0,
+                           ymax=float(radius.max()), zmin=0.0, zmax=1.0, dt=dt, fnum=fnum, collision_type=capi.DSMC,
+                           bool_z_periodic=0, rng_seed_global=rng_seed_global, dump_bound_avg_every=0)
+    bcs = dict(particle_bc=[capi.VACUUM, capi.VACUUM, capi.SPECULAR, capi.CLL], wall_temp=[T_wall] * 4, acc_n=[acc] * 4, acc_t=[acc] * 4)
+    rng = np.random.default_rng(seed)
+    cum = np.cumsum(mesh.cell_volumes)
+    cells0 = np.minimum(np.searchsorted(cum, rng.random(n) * cum[-1]), mesh.nc - 1).astype(np.int64)
+    # uniform in the VOLUME of an axisymmetric cell ~ uniform in the triangle weighted by the radius: rejection on y / y_max
+    xyz = sample_in_tets(rng, mesh, cells0)
+    ymax_cell = np.asarray(mesh.node_coords)[1, np.asarray(mesh.cell_nodes) - 1].max(axis=0)[cells0]
+    for _ in range(6):
+        bad = rng.random(n) * ymax_cell > xyz[:, 1]
+        if not bad.any():
+            break
+        idx = np.nonzero(bad)[0]
+        xyz[idx] = sample_in_tets(rng, mesh, cells0[idx])
+    p = new_particles(n)
+    p["X"], p["Y"] = xyz[:, 0], np.maximum(xyz[:, 1], 1e-9)
+    p["Z"] = 0.0
+    sid = np.where(rng.random(n) < 0.79, sp.id("N2"), sp.id("O2")).astype(np.int32)
+    v = maxwellian(rng, n, sp.mass[sid - 1], T_in)
+    p["VX"], p["VY"], p["VZ"] = v[:, 0], v[:, 1], v[:, 2]
+    p["S_ID"] = sid
+    for name, dofs in (("EROT", sp.rotdof), ("EVIB", sp.vibdof)):
+        has = dofs[sid - 1] == 2
+        p[name][has] = rng.exponential(KB * T_in, size=int(has.sum()))
+    p["DTRIM"] = dt
+    p["IC"] = cells0 + 1
+    w = Workload("C3 axisymmetric converging-diverging nozzle (triangles, CLL wall, inflow emitted at the inlet, TCE + Borgnakke-Larsen)",
+                 cfg, sp, p, mesh=mesh, bcs=bcs, reactions=reactions)
+    w.mixtures = [[(sp.id("N2"), 0.79), (sp.id("O2"), 0.21)]]
+    w.emit_tasks = emit_tasks_for_group(mesh, cfg, sp, w.mixtures[0], pg=1, nrho=nrho, u=(u_in, 0.0, 0.0), ttra=T_in, trot=T_in, tvib=T_in)
+    return w
+
+
 def open_channel(w: Workload, nrho: float = 1e20, u: float = 300.0, T0: float = 300.0) -> Workload:
     """The open variant of a C5 channel workload: vacuum end caps in x, Boundary_emit at x = 0."""
     w.bcs["particle_bc"][0] = capi.VACUUM
