@@ -21,6 +21,9 @@ Covered reference lines:
                  P = 1 - exp(-DT n VR sigma (VR/CREF)^(1-2 omega)), partner created in the store, TCE test over the reaction list
                  with the ORIGINAL species ids, 3-product redistribution, Borgnakke-Larsen selector, VSS deflection; loop
                  over the NP_PROC present at entry and over the components of the background mixture)
+  structured_axi  src/timecycle.f90:1662-1729 (box sides of an axisymmetric rectilinear grid: vertical sides by division, the
+                 horizontal ones by the quadratic in the radius, roots >= 0 here -- no TOL --, trial moves), :1762-1838 (interior
+                 walls, axisymmetric: the cone quadratic, hit parameter along the segment), :1885-1935, :1944-1957
   dsmc_order     src/collisions.f90:37-149 (DSMC_COLLISIONS: INDALL is a stable counting sort by cell, cells are visited in
                  ascending order), :259-271 (INT(NPC*rf()) picks into that order)
   cell_nonuniform  src/grid_and_partition.f90:34-96 (CELL_FROM_POSITION on RECTILINEAR_NONUNIFORM grids), src/tools.f90:1499-1535
@@ -313,6 +316,105 @@ def advect_structured(g, walls, species, parts, dt, rf):
     return out
 
 
+def advect_structured_axi(g, walls, parts, dt):
+    """ADVECT on a uniform rectilinear AXISYMMETRIC grid, specular sides and specular (non-porous) walls only: no draw
+    changes the outcome (the rf() of a specular wall is consumed and ignored).  Same containers as advect_structured."""
+    normx, normy = [1.0, -1.0, 0.0, 0.0], [0.0, 0.0, 1.0, -1.0]
+    boundpos = [g["xmin"], g["xmax"], g["ymin"], g["ymax"]]
+    out = []
+    for p in parts:
+        q = dict(x=p["x"], y=p["y"], z=p["z"], vx=p["vx"], vy=p["vy"], vz=p["vz"])
+        dtrim = dt
+        events = []
+        while dtrim > 0.0:
+            dtcoll = dtrim
+            boundcoll = -1
+            for i in range(1, 5):
+                test = []
+                if i <= 2:
+                    sol1 = (boundpos[i - 1] - q["x"]) / q["vx"]
+                    if sol1 >= 0 and sol1 < dtcoll:
+                        test = [sol1]
+                else:
+                    coefa = q["vy"] * q["vy"] + q["vz"] * q["vz"]
+                    coefb = q["y"] * q["vy"]
+                    coefc = q["y"] * q["y"] - boundpos[i - 1] * boundpos[i - 1]
+                    delta = coefb * coefb - coefa * coefc
+                    if delta >= 0:
+                        sol1 = (-coefb - math.sqrt(delta)) / coefa
+                        sol2 = (-coefb + math.sqrt(delta)) / coefa
+                        ok1 = sol1 >= 0 and sol1 < dtcoll
+                        ok2 = sol2 >= 0 and sol2 < dtcoll
+                        if ok1:
+                            test = ([sol1, sol2] if sol1 <= sol2 else [sol2, sol1]) if ok2 else [sol1]
+                        elif ok2:
+                            test = [sol2]
+                for t in test:
+                    move_axi(q, t)
+                    if (q["vx"] * normx[i - 1] + q["vy"] * normy[i - 1]) < 0:
+                        dtcoll = t
+                        boundcoll = i
+                    move_axi(q, -t)
+            wallcoll = -1
+            for k, w in enumerate(walls):
+                test = []
+                if w["x1"] == w["x2"]:
+                    sol1 = (w["x1"] - q["x"]) / q["vx"]
+                    if sol1 >= 0 and sol1 < dtcoll:
+                        test = [sol1]
+                else:
+                    alpha = (w["y2"] - w["y1"]) / (w["x2"] - w["x1"])
+                    beta = (q["x"] - w["x1"]) * alpha
+                    coefa = q["vy"] * q["vy"] + q["vz"] * q["vz"] - alpha * alpha * (q["vx"] * q["vx"])
+                    coefb = q["y"] * q["vy"] - (beta + w["y1"]) * alpha * q["vx"]
+                    coefc = q["y"] * q["y"] - (beta + w["y1"]) * (beta + w["y1"])
+                    delta = coefb * coefb - coefa * coefc
+                    if delta >= 0:
+                        sol1 = (-coefb - math.sqrt(delta)) / coefa
+                        sol2 = (-coefb + math.sqrt(delta)) / coefa
+                        ok1 = sol1 >= 0 and sol1 < dtcoll and beta + alpha * q["vx"] * sol1 + w["y1"] >= 0
+                        ok2 = sol2 >= 0 and sol2 < dtcoll and beta + alpha * q["vx"] * sol2 + w["y1"] >= 0
+                        if ok1:
+                            test = ([sol1, sol2] if sol1 <= sol2 else [sol2, sol1]) if ok2 else [sol1]
+                        elif ok2:
+                            test = [sol2]
+                for t in test:
+                    move_axi(q, t)
+                    if (q["vx"] * w["normx"] + q["vy"] * w["normy"]) < 0:
+                        colldist = ((q["x"] - w["x1"]) * (w["x2"] - w["x1"]) + (q["y"] - w["y1"]) * (w["y2"] - w["y1"])) / \
+                                   ((w["x2"] - w["x1"]) * (w["x2"] - w["x1"]) + (w["y2"] - w["y1"]) * (w["y2"] - w["y1"]))
+                        if colldist >= 0 and colldist <= 1:
+                            dtcoll = t
+                            boundcoll = -1
+                            wallcoll = k + 1
+                    move_axi(q, -t)
+            if boundcoll != -1:
+                events.append(["side", boundcoll])
+                assert g["specular"][boundcoll - 1]
+                move_axi(q, dtcoll)
+                if boundcoll <= 2:
+                    q["vx"] = -q["vx"]
+                else:
+                    q["vy"] = -q["vy"]
+                dtrim = dtrim - dtcoll
+            elif wallcoll != -1:
+                w = walls[wallcoll - 1]
+                events.append(["wall", wallcoll])
+                move_axi(q, dtcoll)
+                vdotn = q["vx"] * w["normx"] + q["vy"] * w["normy"]
+                q["vx"] = q["vx"] - 2.0 * vdotn * w["normx"]
+                q["vy"] = q["vy"] - 2.0 * vdotn * w["normy"]
+                dtrim = dtrim - dtcoll
+            else:
+                move_axi(q, dtrim)
+                dtrim = 0.0
+        ddx = (g["xmax"] - g["xmin"]) / g["nx"]
+        ddy = (g["ymax"] - g["ymin"]) / g["ny"]
+        q["ic"] = int((q["x"] - g["xmin"]) / ddx) + g["nx"] * int((q["y"] - g["ymin"]) / ddy) + 1
+        out.append((q, events))
+    return out
+
+
 # ------------------------------------------------------------------------------------------ MCC_COLLISIONS
 def mcc_collisions(species, parts, reactions, bg_mix, bg_dens, bg_ttra, dt, rf):
     """src/collisions.f90:1261-1595 with BOOL_BG_DENSITY_FILE = .FALSE.  parts: dicts pos, v, erot, evib, sid (name), in store
@@ -570,6 +672,24 @@ def main():
     assert res[0][0] is None and res[1][0] is not None and res[2][1][0] == ["side", 4] and res[3][1][0] == ["wall", 3], [ev for _, ev in res]
     out["structured_walk"]["sto"] = dict(draws=draws[:s.k], used=s.k,
                                           cases=[dict(inp=pdict(p), out=(pdict(q) if q else None), events=ev) for p, (q, ev) in zip(sto, res)])
+
+    # ---- structured_axi: 4 x 3 cells on [0, 0.4] x [0.02, 0.17] (y = radius), every side specular; wall 1 a cone segment,
+    # wall 2 a vertical disc
+    ga = dict(xmin=0.0, xmax=0.4, ymin=0.02, ymax=0.17, zmin=0.0, zmax=1.0, nx=4, ny=3, periodic=[0, 0, 0, 0], specular=[1, 1, 1, 1],
+              diffuse=[0, 0, 0, 0], boundtemp=300.0, z_periodic=0)
+    s45 = math.sqrt(0.5)
+    wa = [dict(x1=0.1, y1=0.05, x2=0.2, y2=0.15, normx=-s45, normy=s45, specular=1, diffuse=0, porous=0, transm=0.0, temp=300.0),
+          dict(x1=0.3, y1=0.03, x2=0.3, y2=0.1, normx=-1.0, normy=0.0, specular=1, diffuse=0, porous=0, transm=0.0, temp=300.0)]
+    dta = 2.0e-4
+    ax_cases = [dict(x=0.05, y=0.12, z=0.0, vx=300.0, vy=500.0, vz=420.0),        # outer radius (side 4), swirl
+                dict(x=0.35, y=0.05, z=0.0, vx=700.0, vy=-250.0, vz=90.0),         # inner radius (side 3) and x = 0.4
+                dict(x=0.1, y=0.14, z=0.0, vx=450.0, vy=-350.0, vz=60.0),          # the cone wall from above
+                dict(x=0.22, y=0.06, z=0.0, vx=600.0, vy=40.0, vz=-30.0),          # the disc at x = 0.3
+                dict(x=0.02, y=0.09, z=0.0, vx=-500.0, vy=15.0, vz=800.0)]         # x = 0 with a large azimuthal velocity
+    resa = advect_structured_axi(ga, wa, ax_cases, dta)
+    seen = {tuple(e) for _, ev in resa for e in ev}
+    assert {("side", 1), ("side", 2), ("side", 3), ("side", 4), ("wall", 1), ("wall", 2)} <= seen, seen
+    out["structured_axi"] = dict(grid=ga, walls=wa, dt=hx(dta), cases=[dict(inp=pdict(p), out=pdict(q), events=ev) for p, (q, ev) in zip(ax_cases, resa)])
 
     # ---- mcc_collisions: three test particles (a slow O2, a slow N2, a 14 km/s N2) in an O2 0.21 / N2 0.79 background at 800 K;
     # random script; the fast particle's collision energy is above the O2 dissociation threshold: N2 + O2 --> N2 + O + O can fire
