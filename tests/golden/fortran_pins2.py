@@ -24,6 +24,8 @@ Covered reference lines:
   structured_axi  src/timecycle.f90:1662-1729 (box sides of an axisymmetric rectilinear grid: vertical sides by division, the
                  horizontal ones by the quadratic in the radius, roots >= 0 here -- no TOL --, trial moves), :1762-1838 (interior
                  walls, axisymmetric: the cone quadratic, hit parameter along the segment), :1885-1935, :1944-1957
+  tri_walk_solid  src/timecycle.f90:1270-1285 (plane 2-D face test), :1308-1343 (a neighbour cell of a SOLID volume group is a
+                 boundary: FLUIDBOUNDARY, the wall model is that of the face's own physical group), :1433-1443, :1648-1657
   dsmc_order     src/collisions.f90:37-149 (DSMC_COLLISIONS: INDALL is a stable counting sort by cell, cells are visited in
                  ascending order), :259-271 (INT(NPC*rf()) picks into that order)
   cell_nonuniform  src/grid_and_partition.f90:34-96 (CELL_FROM_POSITION on RECTILINEAR_NONUNIFORM grids), src/tools.f90:1499-1535
@@ -183,6 +185,47 @@ def advect_axi(mesh, p, dt):
             dtrim = 0.0
     q["ic"] = ic
     return q, trace, ntrial
+
+
+def advect_tri_plane(mesh, p, dt, cell_pg, solid_groups):
+    """One particle through ADVECT on the plane (not axisymmetric) triangle mesh, every tagged face specular.  cell_pg[c] is
+    CELL_PG (-1 none); a neighbour whose group is in solid_groups is a wall (FLUIDBOUNDARY)."""
+    x, y, z, vx, vy, vz = p["x"], p["y"], p["z"], p["vx"], p["vy"], p["vz"]
+    ic = p["ic"]
+    dtrim = dt
+    trace = []
+    while dtrim > 0.0:
+        dtcoll = dtrim
+        boundcoll = -1
+        for i in range(1, 4):
+            n1, n2 = mesh["normal"][ic - 1][i - 1]
+            px, py = mesh["nodes"][mesh["cells"][ic - 1][i - 1] - 1]
+            vn = vx * n1 + vy * n2
+            dx = (px - x) * n1 + (py - y) * n2
+            if vn >= 0.0 and vn * dtcoll >= dx:
+                dtcoll = dx / vn
+                boundcoll = i
+        if boundcoll == -1:
+            x, y, z = x + vx * dtrim, y + vy * dtrim, z + vz * dtrim
+            dtrim = 0.0
+            continue
+        x, y, z = x + vx * dtcoll, y + vy * dtcoll, z + vz * dtcoll
+        dtrim = dtrim - dtcoll
+        neighbor = mesh["neighbors"][ic - 1][boundcoll - 1]
+        fluidboundary = neighbor == -1
+        if not fluidboundary and cell_pg[neighbor - 1] != -1 and cell_pg[neighbor - 1] in solid_groups:
+            fluidboundary = True
+        trace.append([ic, boundcoll, int(fluidboundary)])
+        if fluidboundary:
+            assert mesh["faces_pg"][ic - 1][boundcoll - 1] != -1
+            fn = [-mesh["normal"][ic - 1][boundcoll - 1][0], -mesh["normal"][ic - 1][boundcoll - 1][1]]
+            vdotn = vx * fn[0] + vy * fn[1] + vz * 0.0
+            vx = vx - 2.0 * vdotn * fn[0]
+            vy = vy - 2.0 * vdotn * fn[1]
+            vz = vz - 2.0 * vdotn * (-0.0)
+        else:
+            ic = neighbor
+    return dict(x=x, y=y, z=z, vx=vx, vy=vy, vz=vz, ic=ic), trace
 
 
 # ------------------------------------------------------------------------------------------ rectilinear grids
@@ -639,6 +682,34 @@ def main():
     pgs = {mesh["faces_pg"][c - 1][f - 1] for w in walk for c, f in w["trace"] if mesh["neighbors"][c - 1][f - 1] == -1}
     assert {1, 2, 3, 4} <= pgs, pgs                                          # every wall of the box was hit by some case
     out["axi_walk"] = dict(dt=hx(dt), cases=walk)
+
+    # ---- tri_walk_solid: the same triangles, plane geometry; cells 7 and 8 (the quad in the middle of the upper row) belong to
+    # a SOLID volume group 5 and their outer edges carry the specular group 6
+    solid_cells = [7, 8]
+    cell_pg = [-1] * len(mesh["cells"])
+    for c in solid_cells:
+        cell_pg[c - 1] = 5
+    faces_pg2 = [list(r) for r in mesh["faces_pg"]]
+    for c in range(len(mesh["cells"])):
+        for j in range(3):
+            nbc = mesh["neighbors"][c][j]
+            if nbc != -1 and ((c + 1 in solid_cells) != (nbc in solid_cells)):
+                faces_pg2[c][j] = 6
+    mesh2 = dict(mesh, faces_pg=faces_pg2)
+    out["tri_solid"] = dict(cell_pg=cell_pg, faces_pg=faces_pg2, solid_group=5, wall_group=6)
+    dtp = 8.0e-5
+    tri_cases = []
+    for p in [dict(x=0.012, y=0.018, z=0.1, vx=900.0, vy=150.0, vz=-420.0),
+              dict(x=0.085, y=0.03, z=-0.2, vx=-1100.0, vy=-250.0, vz=300.0),
+              dict(x=0.045, y=0.015, z=0.0, vx=60.0, vy=1300.0, vz=50.0),
+              dict(x=0.02, y=0.04, z=0.3, vx=700.0, vy=100.0, vz=10.0)]:
+        p["ic"] = locate(p["x"], p["y"])
+        assert p["ic"] not in solid_cells
+        q, trace = advect_tri_plane(mesh2, p, dtp, cell_pg, {5})
+        tri_cases.append(dict(inp=pdict(p), out=pdict(q), trace=trace))
+    hits_solid = sum(1 for c in tri_cases for (cc, f, fb) in c["trace"] if fb and mesh["neighbors"][cc - 1][f - 1] != -1)
+    assert hits_solid >= 2 and all(c["out"]["ic"] not in solid_cells for c in tri_cases), (hits_solid, [c["trace"] for c in tri_cases])
+    out["tri_walk_solid"] = dict(dt=hx(dtp), cases=tri_cases)
 
     # ---- structured_walk: 4 x 3 cells on [0, 0.4] x [0, 0.3]; x periodic, ymin specular, ymax diffuse at 450 K; wall 1 a plain
     # specular segment at x = 0.2 facing -x, wall 2 a porous specular segment at y = 0.15 facing +y, wall 3 diffuse at x = 0.3

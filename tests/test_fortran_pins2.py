@@ -781,3 +781,46 @@ def test_structured_axisymmetric_walk_oracle_matches_fortran_reading(oracle):
         for f in ("x", "y", "z", "vx", "vy", "vz"):
             got = float(out[f.upper()][k])
             assert got == fh(e[f]), (k, f, got.hex(), e[f], c["events"])
+
+
+# ---- plane triangles with a SOLID block --------------------------------------------------------------------------------------
+def test_plane_triangle_walk_with_a_solid_block_oracle_matches_fortran_reading(oracle):
+    """The DIMS == 2 face test and the FLUIDBOUNDARY rule: a face towards a cell of a SOLID volume group is a wall with the
+    model of the face's own physical group (src/timecycle.f90:1270-1285, 1327-1338), hops, specular walls: bit-identical."""
+    t, ts = PINS["tri_walk_solid"], PINS["tri_solid"]
+    m = pin_tri_mesh()
+    m.cell_faces_pg = np.asfortranarray(np.array(ts["faces_pg"], dtype=np.int32).T)
+    m.cell_pg = np.array(ts["cell_pg"], dtype=np.int32)
+    xy = np.array(PINS["tri_mesh"]["nodes"])
+    tri = np.array(PINS["tri_mesh"]["cells"]) - 1
+    a, b, c = xy[tri[:, 0]], xy[tri[:, 1]], xy[tri[:, 2]]
+    m.cell_volumes = 0.5 * np.abs(a[:, 0] * (b[:, 1] - c[:, 1]) + b[:, 0] * (c[:, 1] - a[:, 1]) + c[:, 0] * (a[:, 1] - b[:, 1]))
+    sp = wl.load_species("air", ["N2", "O2"])
+    dt = fh(t["dt"])
+    cfg = capi.make_config(dims=2, grid_type=capi.UNSTRUCTURED, nx=1, ny=1, xmin=0.0, xmax=0.09, ymin=0.01, ymax=0.05, zmin=-0.5, zmax=0.5,
+                           dt=dt, fnum=1.0, collision_type=capi.NO_COLL, dump_bound_avg_every=0, bool_z_periodic=0)
+    p = wl.new_particles(len(t["cases"]))
+    for k, cse in enumerate(t["cases"]):
+        q = cse["inp"]
+        for f in ("x", "y", "z", "vx", "vy", "vz"):
+            p[f.upper()][k] = fh(q[f])
+        p["IC"][k] = q["ic"]
+    p["S_ID"] = 1
+    p["DTRIM"] = dt
+    nb = 6
+    volume_bc = [capi.FLUID] * nb
+    volume_bc[ts["solid_group"] - 1] = capi.SOLID
+    bcs = dict(particle_bc=[capi.SPECULAR] * nb, volume_bc=volume_bc, wall_temp=[300.0] * nb, acc_n=[1.0] * nb, acc_t=[1.0] * nb)
+    w = wl.Workload("pin plane triangles + solid block", cfg, sp, p, mesh=m, bcs=bcs)
+    w.cfg.track_id = 1
+    wl.apply(oracle, w)
+    oracle.advect(1)
+    out = util.by_id(oracle.download_particles())
+    assert len(out) == len(t["cases"])
+    assert sum(1 for cse in t["cases"] for (cc, f, fb) in cse["trace"] if fb and PINS["tri_mesh"]["neighbors"][cc - 1][f - 1] != -1) >= 2
+    for k, cse in enumerate(t["cases"]):
+        e = cse["out"]
+        assert out["IC"][k] == e["ic"], (k, out["IC"][k], e["ic"], cse["trace"])
+        for f in ("x", "y", "z", "vx", "vy", "vz"):
+            got = float(out[f.upper()][k])
+            assert got == fh(e[f]), (k, f, got.hex(), e[f], cse["trace"])
