@@ -26,6 +26,8 @@ Covered reference lines:
                  walls, axisymmetric: the cone quadratic, hit parameter along the segment), :1885-1935, :1944-1957
   tri_walk_solid  src/timecycle.f90:1270-1285 (plane 2-D face test), :1308-1343 (a neighbour cell of a SOLID volume group is a
                  boundary: FLUIDBOUNDARY, the wall model is that of the face's own physical group), :1433-1443, :1648-1657
+  emit_2d        src/timecycle.f90:368-547 (BOUNDARIES_EMIT, DIMS == 2: FACE_TANG1 = (-n_y, n_x, 0), the point on the edge -- plane:
+                 linear in R and a Z draw; axisymmetric: Y = SQRT(Y1^2 + R (Y2^2 - Y1^2)) with the three orderings of Y1, Y2)
   dsmc_order     src/collisions.f90:37-149 (DSMC_COLLISIONS: INDALL is a stable counting sort by cell, cells are visited in
                  ascending order), :259-271 (INT(NPC*rf()) picks into that order)
   cell_nonuniform  src/grid_and_partition.f90:34-96 (CELL_FROM_POSITION on RECTILINEAR_NONUNIFORM grids), src/tools.f90:1499-1535
@@ -458,6 +460,53 @@ def advect_structured_axi(g, walls, parts, dt):
     return out
 
 
+def boundaries_emit_2d(mesh, species, mix, tasks, dt, rf, axi, zmin, zmax):
+    """src/timecycle.f90:368-547, DIMS == 2, no colocated electrons; tasks in order, one rf() stream.  task: dict ic, iface,
+    iv1, iv2, nfs[], ux, uy, uz, u_norm, ttra, trot, tvib.  Returns the particles in creation order."""
+    made = []
+    for task in tasks:
+        ic = task["ic"]
+        x1, y1 = mesh["nodes"][task["iv1"] - 1]
+        x2, y2 = mesh["nodes"][task["iv2"] - 1]
+        n = mesh["normal"][ic - 1][task["iface"] - 1]
+        fn = [n[0], n[1], 0.0]
+        t1 = [-fn[1], fn[0], 0.0]
+        t2 = [0.0, 0.0, 1.0]
+        for k, (name, _) in enumerate(mix):
+            m = species[name]["mass"]
+            nfs = math.floor(task["nfs"][k])
+            if task["nfs"][k] - float(nfs) >= rf():
+                nfs = nfs + 1
+            beta = 0.0 if task["ttra"] == 0 else 1.0 / math.sqrt(2.0 * fp1.KB / m * task["ttra"])
+            for _ip in range(nfs):
+                _, v_tang1, v_tang2 = fp1.maxwell(rf, 0.0, 0.0, 0.0, task["ttra"], task["ttra"], task["ttra"], m)
+                erot = fp1.internal_energy(rf, species[name]["rotdof"], task["trot"])
+                evib = fp1.internal_energy(rf, species[name]["vibdof"], task["tvib"])
+                v_norm = 0.0 if task["ttra"] == 0 else fp1.flx(rf, task["u_norm"] * beta, task["ttra"], m)
+                vx = task["ux"] - v_norm * fn[0] - v_tang1 * t1[0] - v_tang2 * t2[0]
+                vy = task["uy"] - v_norm * fn[1] - v_tang1 * t1[1] - v_tang2 * t2[1]
+                vz = task["uz"] - v_norm * fn[2] - v_tang1 * t1[2] - v_tang2 * t2[2]
+                dtfrac = rf() * dt
+                r = rf()
+                if axi:
+                    if y1 == y2:
+                        y = y1
+                        x = x1 + r * (x2 - x1)
+                    elif y1 < y2:
+                        y = math.sqrt(y1 * y1 + r * (y2 * y2 - y1 * y1))
+                        x = x1 + (y - y1) / (y2 - y1) * (x2 - x1)
+                    else:
+                        y = math.sqrt(y2 * y2 + r * (y1 * y1 - y2 * y2))
+                        x = x2 + (y - y2) / (y1 - y2) * (x1 - x2)
+                    z = 0.0
+                else:
+                    x = x1 + r * (x2 - x1)
+                    y = y1 + r * (y2 - y1)
+                    z = zmin + (zmax - zmin) * rf()
+                made.append(dict(x=x, y=y, z=z, vx=vx, vy=vy, vz=vz, erot=erot, evib=evib, sid=name, ic=ic, dtrim=dtfrac))
+    return made
+
+
 # ------------------------------------------------------------------------------------------ MCC_COLLISIONS
 def mcc_collisions(species, parts, reactions, bg_mix, bg_dens, bg_ttra, dt, rf):
     """src/collisions.f90:1261-1595 with BOOL_BG_DENSITY_FILE = .FALSE.  parts: dicts pos, v, erot, evib, sid (name), in store
@@ -648,7 +697,9 @@ def pdict(q):
 
 
 def main():
+    import random
     out = {}
+    air = fp1.read_species("air")
     # ---- axi_walk
     mesh = tri_mesh()
     out["tri_mesh"] = mesh
@@ -711,9 +762,34 @@ def main():
     assert hits_solid >= 2 and all(c["out"]["ic"] not in solid_cells for c in tri_cases), (hits_solid, [c["trace"] for c in tri_cases])
     out["tri_walk_solid"] = dict(dt=hx(dtp), cases=tri_cases)
 
+    # ---- emit_2d: three tasks on boundary edges of the pin triangles -- x = 0 traversed with Y1 > Y2, x = 0.09 with Y1 < Y2,
+    # y = 0.01 with Y1 == Y2 -- N2/O2 mixture, plane and axisymmetric
+    def edge_task(cell, face, **kw):
+        cn = mesh["cells"][cell - 1]
+        return dict(ic=cell, iface=face, iv1=cn[face - 1], iv2=cn[face % 3], **kw)
+    etasks = []
+    for cell, faces in enumerate(mesh["faces_pg"], start=1):
+        for face, pg in enumerate(faces, start=1):
+            if pg in (1, 2, 3) and not any(mesh["faces_pg"][t["ic"] - 1][t["iface"] - 1] == pg for t in etasks):
+                n = mesh["normal"][cell - 1][face - 1]
+                u = (120.0, -40.0, 15.0)
+                etasks.append(edge_task(cell, face, nfs=[2.3, 1.6], ux=u[0], uy=u[1], uz=u[2], u_norm=-(u[0] * n[0] + u[1] * n[1]),
+                                        ttra=700.0, trot=500.0, tvib=900.0))
+    ys = [(mesh["nodes"][t["iv1"] - 1][1], mesh["nodes"][t["iv2"] - 1][1]) for t in etasks]
+    assert len(etasks) == 3 and any(a > b for a, b in ys) and any(a < b for a, b in ys) and any(a == b for a, b in ys), ys
+    mixe = [("N2", 0.79), ("O2", 0.21)]
+    out["emit_2d"] = {}
+    for label, axi_flag, (zlo, zhi) in (("plane", False, (-0.5, 0.5)), ("axi", True, (0.0, 1.0))):
+        rr = random.Random(4242 + int(axi_flag))
+        draws = [rr.random() for _ in range(400)]
+        s = Script(draws)
+        made = boundaries_emit_2d(mesh, air, mixe, etasks, 3.0e-6, s, axi_flag, zlo, zhi)
+        assert len(made) >= 9
+        out["emit_2d"][label] = dict(tasks=etasks, mix=mixe, dt=hx(3.0e-6), zmin=zlo, zmax=zhi, draws=[hx(v) for v in draws[:s.k]], used=s.k,
+                                     out=[dict(pdict(q), dtrim=hx(q["dtrim"])) for q in made])
+
     # ---- structured_walk: 4 x 3 cells on [0, 0.4] x [0, 0.3]; x periodic, ymin specular, ymax diffuse at 450 K; wall 1 a plain
     # specular segment at x = 0.2 facing -x, wall 2 a porous specular segment at y = 0.15 facing +y, wall 3 diffuse at x = 0.3
-    air = fp1.read_species("air")
     g = dict(xmin=0.0, xmax=0.4, ymin=0.0, ymax=0.3, zmin=-0.5, zmax=0.5, nx=4, ny=3, periodic=[1, 1, 0, 0], specular=[0, 0, 1, 0],
              diffuse=[0, 0, 0, 1], boundtemp=450.0, z_periodic=1)
     walls = [dict(x1=0.2, y1=0.05, x2=0.2, y2=0.2, normx=-1.0, normy=0.0, specular=1, diffuse=0, porous=0, transm=0.0, temp=300.0),
@@ -764,7 +840,6 @@ def main():
 
     # ---- mcc_collisions: three test particles (a slow O2, a slow N2, a 14 km/s N2) in an O2 0.21 / N2 0.79 background at 800 K;
     # random script; the fast particle's collision energy is above the O2 dissociation threshold: N2 + O2 --> N2 + O + O can fire
-    import random
     names5 = ["O2", "N2", "O", "N", "NO"]
     tce = fp1.read_tce(air)
     reactions = []

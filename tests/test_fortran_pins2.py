@@ -824,3 +824,37 @@ def test_plane_triangle_walk_with_a_solid_block_oracle_matches_fortran_reading(o
         for f in ("x", "y", "z", "vx", "vy", "vz"):
             got = float(out[f.upper()][k])
             assert got == fh(e[f]), (k, f, got.hex(), e[f], cse["trace"])
+
+
+# ---- BOUNDARIES_EMIT on 2-D meshes -------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("label", ["plane", "axi"])
+def test_boundaries_emit_2d_oracle_matches_fortran_reading(oracle, label):
+    """src/timecycle.f90:368-547 (DIMS == 2) on scripted draws: the tangent (-n_y, n_x, 0), the point on the edge (plane: linear,
+    Z drawn; axisymmetric: area-weighted radius with Y1 < Y2, Y1 > Y2 and Y1 == Y2), creation order over tasks / components."""
+    t = PINS["emit_2d"][label]
+    axi = label == "axi"
+    m = pin_tri_mesh()
+    if not axi:
+        xy = np.array(PINS["tri_mesh"]["nodes"])
+        tri = np.array(PINS["tri_mesh"]["cells"]) - 1
+        a, b, c = xy[tri[:, 0]], xy[tri[:, 1]], xy[tri[:, 2]]
+        m.cell_volumes = 0.5 * np.abs(a[:, 0] * (b[:, 1] - c[:, 1]) + b[:, 0] * (c[:, 1] - a[:, 1]) + c[:, 0] * (a[:, 1] - b[:, 1]))
+    sp = wl.load_species("air", ["N2", "O2"])
+    cfg = capi.make_config(dims=2, axi=int(axi), grid_type=capi.UNSTRUCTURED, nx=1, ny=1, xmin=0.0, xmax=0.09, ymin=0.01, ymax=0.05,
+                           zmin=t["zmin"], zmax=t["zmax"], dt=fh(t["dt"]), fnum=1.0, collision_type=capi.NO_COLL, dump_bound_avg_every=0)
+    cfg.capacity = 256
+    bcs = dict(particle_bc=[capi.SPECULAR] * 4, wall_temp=[300.0] * 4, acc_n=[1.0] * 4, acc_t=[1.0] * 4)
+    w = wl.Workload("pin emit 2-D", cfg, sp, wl.new_particles(0), mesh=m, bcs=bcs)
+    wl.apply(oracle, w)
+    oracle.set_mixtures([[(sp.id(name), frac) for name, frac in t["mix"]]])
+    oracle.set_species_weights([1.0] * len(sp.mass))
+    oracle.set_emit_tasks([dict(task, mix_id=0) for task in t["tasks"]])
+    script(oracle, [fh(v) for v in t["draws"]])
+    oracle.boundaries_emit(1)
+    assert script_used(oracle) == t["used"]
+    out = oracle.download_particles()
+    assert len(out) == len(t["out"]) >= 9
+    for k, e in enumerate(t["out"]):
+        assert out["S_ID"][k] == sp.id(e["sid"]) and out["IC"][k] == e["ic"], k
+        for f in ("x", "y", "z", "vx", "vy", "vz", "erot", "evib", "dtrim"):
+            assert float(out[f.upper()][k]) == pytest.approx(fh(e[f]), rel=1e-13, abs=1e-300), (k, f)
