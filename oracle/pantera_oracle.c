@@ -1,8 +1,11 @@
 /*
  * pantera_oracle.c -- CPU ORACLE (TEST INFRASTRUCTURE ONLY).  See pantera_oracle.h.
  *
- * PARITY UNPINNED by the reference's own tests (it has none); pinned by RNG known-answer
- * vectors, closed forms and analytic kinetic theory in tests/.
+ * PARITY UNPINNED in the sense of the task brief: the reference ships no tests or golden vectors and cannot be built
+ * here (Fortran + MPI + PETSc, no Fortran compiler in the image), so nothing below has been compared with output of the
+ * reference itself.  What pins it instead: the RNG known-answer vectors, closed forms and kinetic theory in tests/, and
+ * the INDEPENDENT pins -- a second, plain-Python reading of the Fortran, procedure by procedure, on scripted draws
+ * (tests/golden/fortran_pins.py, fortran_pins2.py; the table in DESIGN.md section 5 lists the reference lines each covers).
  *
  * Sequential, AoS (96-byte records), double precision, no FMA contraction (build with
  * -ffp-contract=off, mirroring gfortran -O3 on baseline x86-64: SURVEY App. B3).
