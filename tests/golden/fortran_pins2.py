@@ -28,6 +28,9 @@ Covered reference lines:
                  boundary: FLUIDBOUNDARY, the wall model is that of the face's own physical group), :1433-1443, :1648-1657
   emit_2d        src/timecycle.f90:368-547 (BOUNDARIES_EMIT, DIMS == 2: FACE_TANG1 = (-n_y, n_x, 0), the point on the edge -- plane:
                  linear in R and a Z draw; axisymmetric: Y = SQRT(Y1^2 + R (Y2^2 - Y1^2)) with the three orderings of Y1, Y2)
+  seed_2d_1d     src/initialization.f90:2062-2141 (INITIAL_SEED on triangles -- plane and axisymmetric: the (S, T) fold, Z drawn
+                 or zero, U always drawn -- and on segments: X from S, Y from T, Z from U), CELL_VOLUMES src/grid_and_partition.f90
+                 :1315-1323 (triangles) / :870-871 (segments)
   dsmc_order     src/collisions.f90:37-149 (DSMC_COLLISIONS: INDALL is a stable counting sort by cell, cells are visited in
                  ascending order), :259-271 (INT(NPC*rf()) picks into that order)
   cell_nonuniform  src/grid_and_partition.f90:34-96 (CELL_FROM_POSITION on RECTILINEAR_NONUNIFORM grids), src/tools.f90:1499-1535
@@ -507,6 +510,38 @@ def boundaries_emit_2d(mesh, species, mix, tasks, dt, rf, axi, zmin, zmax):
     return made
 
 
+def initial_seed_12d(d, nodes, cells, vols, species, mixtures, spwt, tasks, fnum, rf, axi, lim):
+    """src/initialization.f90:2017-2233, GRID_TYPE == UNSTRUCTURED, DIMS == 1 or 2, one rank, no solid cells.  lim = (ymin,
+    ymax, zmin, zmax).  Loops: task, mixture component, cell."""
+    ymin, ymax, zmin, zmax = lim
+    made = []
+    for task in tasks:
+        for name, molfrac in mixtures[task["mix_id"]]:
+            for ic in range(1, len(cells) + 1):
+                np_init = fp1.randint(rf, task["nrho"] / (fnum * spwt[name]) * vols[ic - 1] * molfrac)
+                if np_init == 0:
+                    continue
+                v = [nodes[k - 1] for k in cells[ic - 1]]
+                for _ip in range(np_init):
+                    sd, td, ud = rf(), rf(), rf()
+                    if sd + td > 1:
+                        sd, td = 1 - sd, 1 - td
+                    if d == 1:
+                        xp = v[0][0] + (v[1][0] - v[0][0]) * sd
+                        yp = ymin + (ymax - ymin) * td
+                        zp = zmin + (zmax - zmin) * ud
+                    else:
+                        xp = v[0][0] + (v[1][0] - v[0][0]) * sd + (v[2][0] - v[0][0]) * td
+                        yp = v[0][1] + (v[1][1] - v[0][1]) * sd + (v[2][1] - v[0][1]) * td
+                        zp = 0.0 if axi else zmin + (zmax - zmin) * ud
+                    m = species[name]["mass"]
+                    vx, vy, vz = fp1.maxwell(rf, task["ux"], task["uy"], task["uz"], task["ttrax"], task["ttray"], task["ttraz"], m)
+                    erot = fp1.internal_energy(rf, species[name]["rotdof"], task["trot"])
+                    evib = fp1.internal_energy(rf, species[name]["vibdof"], task["tvib"])
+                    made.append(dict(x=xp, y=yp, z=zp, vx=vx, vy=vy, vz=vz, erot=erot, evib=evib, sid=name, ic=ic))
+    return made
+
+
 # ------------------------------------------------------------------------------------------ MCC_COLLISIONS
 def mcc_collisions(species, parts, reactions, bg_mix, bg_dens, bg_ttra, dt, rf):
     """src/collisions.f90:1261-1595 with BOOL_BG_DENSITY_FILE = .FALSE.  parts: dicts pos, v, erot, evib, sid (name), in store
@@ -787,6 +822,38 @@ def main():
         assert len(made) >= 9
         out["emit_2d"][label] = dict(tasks=etasks, mix=mixe, dt=hx(3.0e-6), zmin=zlo, zmax=zhi, draws=[hx(v) for v in draws[:s.k]], used=s.k,
                                      out=[dict(pdict(q), dtrim=hx(q["dtrim"])) for q in made])
+
+    # ---- seed_2d_1d: INITIAL_SEED on the pin triangles (plane, axisymmetric) and on a 5-segment line
+    def tri_vols(axi_flag, depth):
+        v = []
+        for cn in mesh["cells"]:
+            (ax_, ay), (bx, by), (cx, cy) = (mesh["nodes"][k - 1] for k in cn)
+            area = 0.5 * abs(ax_ * (by - cy) + bx * (cy - ay) + cx * (ay - by))
+            v.append(area * depth * ((ay + by + cy) / 3.0) if axi_flag else area * depth)     # grid_and_partition.f90:1315-1323
+        return v
+    seed_tasks = [dict(mix_id=0, nrho=8.0e3, ux=30.0, uy=-20.0, uz=5.0, ttrax=400.0, ttray=0.0, ttraz=650.0, trot=500.0, tvib=300.0),
+                  dict(mix_id=1, nrho=3.0e3, ux=0.0, uy=0.0, uz=0.0, ttrax=900.0, ttray=900.0, ttraz=900.0, trot=0.0, tvib=1200.0)]
+    seed_mix = [[("N2", 0.79), ("O2", 0.21)], [("O2", 1.0)]]
+    seed_spwt = {"N2": 1.0, "O2": 2.0}
+    out["seed_2d_1d"] = {}
+    for label, dsz, axi_flag, lim in (("plane", 2, False, (0.01, 0.05, -0.5, 0.5)), ("axi", 2, True, (0.01, 0.05, 0.0, 1.0)), ("line", 1, False, (0.0, 0.2, -0.1, 0.3))):
+        rr = random.Random(99 + len(label))
+        draws = [rr.random() for _ in range(4000)]
+        if dsz == 2:
+            nds, cls, vls = mesh["nodes"], mesh["cells"], tri_vols(axi_flag, lim[3] - lim[2])
+            fn = 1.0 if not axi_flag else 0.03
+        else:
+            xs = [0.0, 0.011, 0.019, 0.034, 0.041, 0.05]
+            nds = [[x, 0.0] for x in xs]
+            cls = [[k + 1, k + 2] for k in range(5)]
+            vls = [abs(xs[k + 1] - xs[k]) * (lim[1] - lim[0]) * (lim[3] - lim[2]) for k in range(5)]     # LENGTH*(YMAX-YMIN)*(ZMAX-ZMIN), :870-871
+            fn = 2.0
+        s = Script(draws)
+        made = initial_seed_12d(dsz, nds, cls, vls, air, seed_mix, seed_spwt, seed_tasks, fn, s, axi_flag, lim)
+        assert 10 <= len(made) <= 200, (label, len(made))
+        out["seed_2d_1d"][label] = dict(dims=dsz, axi=axi_flag, lim=lim, fnum=hx(fn), nodes=nds, cells=cls, vols=[hx(v) for v in vls],
+                                        tasks=seed_tasks, mixtures=seed_mix, spwt=seed_spwt, draws=[hx(v) for v in draws[:s.k]], used=s.k,
+                                        out=[pdict(q) for q in made])
 
     # ---- structured_walk: 4 x 3 cells on [0, 0.4] x [0, 0.3]; x periodic, ymin specular, ymax diffuse at 450 K; wall 1 a plain
     # specular segment at x = 0.2 facing -x, wall 2 a porous specular segment at y = 0.15 facing +y, wall 3 diffuse at x = 0.3

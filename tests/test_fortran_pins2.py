@@ -858,3 +858,46 @@ def test_boundaries_emit_2d_oracle_matches_fortran_reading(oracle, label):
         assert out["S_ID"][k] == sp.id(e["sid"]) and out["IC"][k] == e["ic"], k
         for f in ("x", "y", "z", "vx", "vy", "vz", "erot", "evib", "dtrim"):
             assert float(out[f.upper()][k]) == pytest.approx(fh(e[f]), rel=1e-13, abs=1e-300), (k, f)
+
+
+# ---- INITIAL_SEED on triangles and segments ----------------------------------------------------------------------------------
+@pytest.mark.parametrize("label", ["plane", "axi", "line"])
+def test_initial_seed_2d_1d_oracle_matches_fortran_reading(oracle, label):
+    """src/initialization.f90:2062-2141 on scripted draws: RANDINT per (task, component, cell), the (S, T) fold, the point in
+    the triangle (Z drawn, or 0 when axisymmetric -- U is drawn either way) or on the segment (Y from T, Z from U), MAXWELL
+    with a zero temperature component, INTERNAL_ENERGY with a zero temperature, SPWT; creation order."""
+    t = PINS["seed_2d_1d"][label]
+    d = t["dims"]
+    ymin, ymax, zmin, zmax = t["lim"]
+    nn, nc = len(t["nodes"]), len(t["cells"])
+    if d == 2:
+        m = pin_tri_mesh()
+    else:
+        from pantera_pic_dsmc_b200 import meshgen as mg
+        m = mg.line_1d(nc, 0.0, 1.0)
+        xyz = np.zeros((3, nn))
+        xyz[0] = [n[0] for n in t["nodes"]]
+        m.node_coords = np.asfortranarray(xyz)
+        assert [list(c) for c in (np.asarray(m.cell_nodes).T)] == t["cells"]
+    m.cell_volumes = np.array([fh(v) for v in t["vols"]])
+    sp = wl.load_species("air", ["N2", "O2"])
+    xs = [n[0] for n in t["nodes"]]
+    cfg = capi.make_config(dims=d, axi=int(t["axi"]), grid_type=capi.UNSTRUCTURED, nx=1, ny=1, xmin=min(xs), xmax=max(xs), ymin=ymin, ymax=ymax,
+                           zmin=zmin, zmax=zmax, dt=1.0e-6, fnum=fh(t["fnum"]), collision_type=capi.NO_COLL, dump_bound_avg_every=0)
+    cfg.capacity = 512
+    nb = 4 if d == 2 else 2
+    bcs = dict(particle_bc=[capi.SPECULAR] * nb, wall_temp=[300.0] * nb, acc_n=[1.0] * nb, acc_t=[1.0] * nb)
+    w = wl.Workload("pin seed", cfg, sp, wl.new_particles(0), mesh=m, bcs=bcs)
+    wl.apply(oracle, w)
+    oracle.set_mixtures([[(sp.id(name), frac) for name, frac in mix] for mix in t["mixtures"]])
+    oracle.set_species_weights([t["spwt"][n] for n in ("N2", "O2")])
+    oracle.set_initial_particles_tasks([dict(q, rate=q["nrho"]) for q in t["tasks"]])
+    script(oracle, [fh(v) for v in t["draws"]])
+    oracle.initial_seed()
+    assert script_used(oracle) == t["used"]
+    out = oracle.download_particles()
+    assert len(out) == len(t["out"]) >= 10
+    for k, e in enumerate(t["out"]):
+        assert out["S_ID"][k] == sp.id(e["sid"]) and out["IC"][k] == e["ic"], k
+        for f in ("x", "y", "z", "vx", "vy", "vz", "erot", "evib"):
+            assert float(out[f.upper()][k]) == pytest.approx(fh(e[f]), rel=1e-13, abs=1e-300), (k, f)
