@@ -31,6 +31,8 @@ Covered reference lines:
   seed_2d_1d     src/initialization.f90:2062-2141 (INITIAL_SEED on triangles -- plane and axisymmetric: the (S, T) fold, Z drawn
                  or zero, U always drawn -- and on segments: X from S, Y from T, Z from U), CELL_VOLUMES src/grid_and_partition.f90
                  :1315-1323 (triangles) / :870-871 (segments)
+  vinject_tri    src/timecycle.f90:553-670 (VOLUME_INJECT, unstructured branch: DT*NRHODOT/(FNUM*SPWT)*VOL*MOLFRAC/N_MPI_THREADS
+                 per cell, every cell -- no ownership test --, the same point / velocity / energy draws as INITIAL_SEED, DTRIM = DT)
   dsmc_order     src/collisions.f90:37-149 (DSMC_COLLISIONS: INDALL is a stable counting sort by cell, cells are visited in
                  ascending order), :259-271 (INT(NPC*rf()) picks into that order)
   cell_nonuniform  src/grid_and_partition.f90:34-96 (CELL_FROM_POSITION on RECTILINEAR_NONUNIFORM grids), src/tools.f90:1499-1535
@@ -854,6 +856,19 @@ def main():
         out["seed_2d_1d"][label] = dict(dims=dsz, axi=axi_flag, lim=lim, fnum=hx(fn), nodes=nds, cells=cls, vols=[hx(v) for v in vls],
                                         tasks=seed_tasks, mixtures=seed_mix, spwt=seed_spwt, draws=[hx(v) for v in draws[:s.k]], used=s.k,
                                         out=[pdict(q) for q in made])
+
+    # ---- vinject_tri: VOLUME_INJECT on the plane pin triangles (the loop body is INITIAL_SEED's with the rate DT*NRHODOT)
+    dtv = 2.0e-6
+    vtasks = [dict(mix_id=0, nrhodot=5.0e9, ux=-15.0, uy=25.0, uz=0.0, ttrax=300.0, ttray=450.0, ttraz=600.0, trot=350.0, tvib=0.0)]
+    rr = random.Random(5150)
+    draws = [rr.random() for _ in range(3000)]
+    s = Script(draws)
+    lim = (0.01, 0.05, -0.5, 0.5)
+    made = initial_seed_12d(2, mesh["nodes"], mesh["cells"], tri_vols(False, 1.0), air, seed_mix, seed_spwt,
+                            [dict(t, nrho=dtv * t["nrhodot"]) for t in vtasks], 1.0, s, False, lim)
+    assert 10 <= len(made) <= 150, len(made)
+    out["vinject_tri"] = dict(dt=hx(dtv), lim=lim, tasks=vtasks, mixtures=seed_mix, spwt=seed_spwt, vols=[hx(v) for v in tri_vols(False, 1.0)],
+                              draws=[hx(v) for v in draws[:s.k]], used=s.k, out=[pdict(q) for q in made])
 
     # ---- structured_walk: 4 x 3 cells on [0, 0.4] x [0, 0.3]; x periodic, ymin specular, ymax diffuse at 450 K; wall 1 a plain
     # specular segment at x = 0.2 facing -x, wall 2 a porous specular segment at y = 0.15 facing +y, wall 3 diffuse at x = 0.3

@@ -901,3 +901,33 @@ def test_initial_seed_2d_1d_oracle_matches_fortran_reading(oracle, label):
         assert out["S_ID"][k] == sp.id(e["sid"]) and out["IC"][k] == e["ic"], k
         for f in ("x", "y", "z", "vx", "vy", "vz", "erot", "evib"):
             assert float(out[f.upper()][k]) == pytest.approx(fh(e[f]), rel=1e-13, abs=1e-300), (k, f)
+
+
+def test_volume_inject_on_triangles_oracle_matches_fortran_reading(oracle):
+    """src/timecycle.f90:553-670 (unstructured branch) on scripted draws: RANDINT(DT*NRHODOT/(FNUM*SPWT)*VOL*MOLFRAC/N) per
+    (task, component, cell), the triangle point, MAXWELL with a drift, INTERNAL_ENERGY (TVIB = 0: no draw), DTRIM = DT."""
+    t = PINS["vinject_tri"]
+    ymin, ymax, zmin, zmax = t["lim"]
+    m = pin_tri_mesh()
+    m.cell_volumes = np.array([fh(v) for v in t["vols"]])
+    sp = wl.load_species("air", ["N2", "O2"])
+    dt = fh(t["dt"])
+    cfg = capi.make_config(dims=2, grid_type=capi.UNSTRUCTURED, nx=1, ny=1, xmin=0.0, xmax=0.09, ymin=ymin, ymax=ymax, zmin=zmin, zmax=zmax,
+                           dt=dt, fnum=1.0, collision_type=capi.NO_COLL, dump_bound_avg_every=0)
+    cfg.capacity = 512
+    bcs = dict(particle_bc=[capi.SPECULAR] * 4, wall_temp=[300.0] * 4, acc_n=[1.0] * 4, acc_t=[1.0] * 4)
+    w = wl.Workload("pin volume inject", cfg, sp, wl.new_particles(0), mesh=m, bcs=bcs)
+    wl.apply(oracle, w)
+    oracle.set_mixtures([[(sp.id(name), frac) for name, frac in mix] for mix in t["mixtures"]])
+    oracle.set_species_weights([t["spwt"][n] for n in ("N2", "O2")])
+    oracle.set_volume_inject_tasks([dict(q, rate=q["nrhodot"]) for q in t["tasks"]])
+    script(oracle, [fh(v) for v in t["draws"]])
+    oracle.volume_inject(3)
+    assert script_used(oracle) == t["used"]
+    out = oracle.download_particles()
+    assert len(out) == len(t["out"]) >= 10
+    for k, e in enumerate(t["out"]):
+        assert out["S_ID"][k] == sp.id(e["sid"]) and out["IC"][k] == e["ic"], k
+        for f in ("x", "y", "z", "vx", "vy", "vz", "erot", "evib"):
+            assert float(out[f.upper()][k]) == pytest.approx(fh(e[f]), rel=1e-13, abs=1e-300), (k, f)
+        assert float(out["DTRIM"][k]) == dt
