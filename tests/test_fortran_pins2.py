@@ -931,3 +931,28 @@ def test_volume_inject_on_triangles_oracle_matches_fortran_reading(oracle):
         for f in ("x", "y", "z", "vx", "vy", "vz", "erot", "evib"):
             assert float(out[f.upper()][k]) == pytest.approx(fh(e[f]), rel=1e-13, abs=1e-300), (k, f)
         assert float(out["DTRIM"][k]) == dt
+
+
+# ---- REMOVE_PARTICLES_OF_SPECIES ----------------------------------------------------------------------------------------------
+def test_remove_particles_of_species_store_order_matches_fortran_reading(oracle):
+    """src/timecycle.f90:2340-2367 with REMOVE_PARTICLE_ARRAY (src/particle.f90:142-179): reverse sweep, the last particle takes
+    the place of a removed one -- the surviving ORDER is what the next sequential MT draws act on."""
+    w = wl.c2_air_box(40, nx=2, ny=2, with_reactions=False)
+    rng = np.random.default_rng(3)
+    p = w.particles
+    p["S_ID"] = rng.integers(1, 4, len(p))
+    p["ID"] = 500 + np.arange(len(p))
+    w.particles = p
+    wl.apply(oracle, w)
+    store = [(int(i), int(s)) for i, s in zip(p["ID"], p["S_ID"])]
+    for sp_id in (2, 3):                                   # REMOVE_PARTICLES_IN_MIXTURE: component after component
+        oracle.remove_species(sp_id)
+        ip = len(store)
+        while ip >= 1:
+            if store[ip - 1][1] == sp_id:
+                store[ip - 1] = store[-1]
+                store.pop()
+            ip -= 1
+        got = oracle.download_particles()
+        assert [int(i) for i in got["ID"]] == [i for i, _ in store]
+    assert 0 < len(store) < 40 and all(s == 1 for _, s in store)
