@@ -41,3 +41,65 @@ def test_box_tets_geometry_invariants():
         want = np.zeros_like(psi)
         want[q] = 1.0
         assert np.abs(psi - want).max() < 1e-9
+
+
+def _fortran_quicksort(array, order, lo, hi):
+    """QUICKSORT, src/tools.f90:1314-1339 (Lomuto partition, 1-based bounds, sorts `array` and carries `order`)."""
+    if lo >= 1 and hi >= 1 and lo < hi:
+        pivot = array[hi - 1]
+        i = lo - 1
+        for j in range(lo, hi):
+            if array[j - 1] <= pivot:
+                i += 1
+                array[i - 1], array[j - 1] = array[j - 1], array[i - 1]
+                order[i - 1], order[j - 1] = order[j - 1], order[i - 1]
+        array[i], array[hi - 1] = array[hi - 1], array[i]
+        order[i], order[hi - 1] = order[hi - 1], order[i]
+        p = i + 1
+        _fortran_quicksort(array, order, lo, p - 1)
+        _fortran_quicksort(array, order, p + 1, hi)
+
+
+def test_partition_helpers_match_a_plain_reading_of_assign_cells_to_procs():
+    """ASSIGN_CELLS_TO_PROCS (src/grid_and_partition.f90:123-310) in plain Python, both branches, against the helpers the
+    multi-GPU tests and the bench use: uniform strips of the centroid coordinate, and the particle-weighted re-cut (weights =
+    particles per cell + 10 % of the mean, cells ordered by the reference's own QUICKSORT, greedy cut).  Jittered mesh: no two
+    centroids coincide, so the order of ties (which the reference leaves to its unstable sort) plays no role."""
+    import numpy as np
+    from pantera_pic_dsmc_b200 import meshgen as mg
+    m = mg.box_tets(6, 3, 2, lo=(0.0, 0.0, 0.0), hi=(3.0, 1.0, 0.7), jitter=0.2, seed=5)
+    xyz = np.asarray(m.node_coords).copy()
+    xyz += np.random.default_rng(1).random(xyz.shape) * 1e-3      # every node moved a little (only the centroids matter here)
+    m.node_coords = np.asfortranarray(xyz)
+    cn = np.asarray(m.cell_nodes) - 1
+    nr = 4
+    for style in (0, 1, 2):
+        cen = [float((xyz[style, cn[0, i]] + xyz[style, cn[1, i]] + xyz[style, cn[2, i]] + xyz[style, cn[3, i]]) / 4.0) for i in range(m.nc)]
+        cmax, cmin = max(cen), min(cen)
+        want = []
+        for i in range(m.nc):
+            p = int((cen[i] - cmin) / (cmax - cmin) * float(np.float32(nr)))
+            want.append(min(max(p, 0), nr - 1))
+        assert list(mg.assign_cells_to_procs(m, nr, style)) == want
+        assert len(set(cen)) == m.nc
+        rng = np.random.default_rng(style)
+        np_cells = rng.poisson(30.0 * (1.0 + 3.0 * (np.array(cen) - cmin) / (cmax - cmin)))   # more particles downstream
+        weight = [float(v) for v in np_cells]
+        tot = sum(weight)
+        weight = [v + float(np.float32(0.1)) * tot / float(m.nc) for v in weight]
+        per_proc = sum(weight) / float(nr)
+        arr, order = list(cen), list(range(1, m.nc + 1))
+        _fortran_quicksort(arr, order, 1, m.nc)
+        assert arr == sorted(cen)
+        want, iproc, cum = [0] * m.nc, 0, 0.0
+        for i in range(m.nc):
+            ic = order[i]
+            cum = cum + weight[ic - 1]
+            want[ic - 1] = iproc
+            if cum > per_proc:
+                iproc += 1
+                cum = 0.0
+        got = mg.load_balance_cut(m, np_cells, nr, style)
+        assert max(want) == nr - 1 and list(got) == want
+        loads = [float(np_cells[np.array(want) == r].sum()) for r in range(nr)]
+        assert max(loads) < 1.35 * (sum(loads) / nr)                                           # the re-cut balances the particles
