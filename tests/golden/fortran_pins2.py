@@ -33,6 +33,8 @@ Covered reference lines:
                  :1315-1323 (triangles) / :870-871 (segments)
   vinject_tri    src/timecycle.f90:553-670 (VOLUME_INJECT, unstructured branch: DT*NRHODOT/(FNUM*SPWT)*VOL*MOLFRAC/N_MPI_THREADS
                  per cell, every cell -- no ownership test --, the same point / velocity / energy draws as INITIAL_SEED, DTRIM = DT)
+  tri_diffuse    src/timecycle.f90:1327-1343 (2-D: FACE_NORMAL = -EDGE_NORMAL, FACE_TANG1 = (-FACE_NORMAL(2), FACE_NORMAL(1), 0),
+                 FACE_TANG2 = (0, 0, 1)), :1445-1476 (diffuse re-emission from a wall of the plane triangle mesh)
   dsmc_order     src/collisions.f90:37-149 (DSMC_COLLISIONS: INDALL is a stable counting sort by cell, cells are visited in
                  ascending order), :259-271 (INT(NPC*rf()) picks into that order)
   cell_nonuniform  src/grid_and_partition.f90:34-96 (CELL_FROM_POSITION on RECTILINEAR_NONUNIFORM grids), src/tools.f90:1499-1535
@@ -194,7 +196,7 @@ def advect_axi(mesh, p, dt):
     return q, trace, ntrial
 
 
-def advect_tri_plane(mesh, p, dt, cell_pg, solid_groups):
+def advect_tri_plane(mesh, p, dt, cell_pg, solid_groups, diffuse=None, species=None, rf=None):
     """One particle through ADVECT on the plane (not axisymmetric) triangle mesh, every tagged face specular.  cell_pg[c] is
     CELL_PG (-1 none); a neighbour whose group is in solid_groups is a wall (FLUIDBOUNDARY)."""
     x, y, z, vx, vy, vz = p["x"], p["y"], p["z"], p["vx"], p["vy"], p["vz"]
@@ -223,7 +225,20 @@ def advect_tri_plane(mesh, p, dt, cell_pg, solid_groups):
         if not fluidboundary and cell_pg[neighbor - 1] != -1 and cell_pg[neighbor - 1] in solid_groups:
             fluidboundary = True
         trace.append([ic, boundcoll, int(fluidboundary)])
-        if fluidboundary:
+        if fluidboundary and diffuse and mesh["faces_pg"][ic - 1][boundcoll - 1] in diffuse:
+            wall_temp = diffuse[mesh["faces_pg"][ic - 1][boundcoll - 1]]
+            fn = [-mesh["normal"][ic - 1][boundcoll - 1][0], -mesh["normal"][ic - 1][boundcoll - 1][1], -0.0]
+            t1 = [-fn[1], fn[0], 0.0]
+            t2 = [0.0, 0.0, 1.0]
+            sp = species[p["sid"]]
+            _, v_tang1, v_tang2 = fp1.maxwell(rf, 0.0, 0.0, 0.0, wall_temp, wall_temp, wall_temp, sp["mass"])
+            p["erot"] = fp1.internal_energy(rf, sp["rotdof"], wall_temp)
+            p["evib"] = fp1.internal_energy(rf, sp["vibdof"], wall_temp)
+            v_perp = fp1.flx(rf, 0.0, wall_temp, sp["mass"])
+            vx = v_perp * fn[0] + v_tang1 * t1[0] + v_tang2 * t2[0]
+            vy = v_perp * fn[1] + v_tang1 * t1[1] + v_tang2 * t2[1]
+            vz = v_perp * fn[2] + v_tang1 * t1[2] + v_tang2 * t2[2]
+        elif fluidboundary:
             assert mesh["faces_pg"][ic - 1][boundcoll - 1] != -1
             fn = [-mesh["normal"][ic - 1][boundcoll - 1][0], -mesh["normal"][ic - 1][boundcoll - 1][1]]
             vdotn = vx * fn[0] + vy * fn[1] + vz * 0.0
@@ -869,6 +884,22 @@ def main():
     assert 10 <= len(made) <= 150, len(made)
     out["vinject_tri"] = dict(dt=hx(dtv), lim=lim, tasks=vtasks, mixtures=seed_mix, spwt=seed_spwt, vols=[hx(v) for v in tri_vols(False, 1.0)],
                               draws=[hx(v) for v in draws[:s.k]], used=s.k, out=[pdict(q) for q in made])
+
+    # ---- tri_diffuse: plane triangles, the walls x = 0 (group 1, 800 K) and y = 0.01 (group 3, 450 K) diffuse, the others specular
+    dtd = 6.0e-5
+    rr = random.Random(31337)
+    draws = [rr.random() for _ in range(200)]
+    s = Script(draws)
+    dcases = []
+    for p in [dict(x=0.012, y=0.02, z=0.1, vx=-900.0, vy=150.0, vz=-420.0, erot=1.0e-21, evib=2.0e-21, sid="N2"),
+              dict(x=0.05, y=0.016, z=-0.2, vx=200.0, vy=-800.0, vz=300.0, erot=3.0e-21, evib=0.5e-21, sid="O2")]:
+        p["ic"] = locate(p["x"], p["y"])
+        pin = dict(p)
+        q, trace = advect_tri_plane(mesh, p, dtd, [-1] * len(mesh["cells"]), set(), diffuse={1: 800.0, 3: 450.0}, species=air, rf=s)
+        q["erot"], q["evib"] = p["erot"], p["evib"]
+        dcases.append(dict(inp=pdict(pin), out=pdict(q), trace=trace))
+    assert s.k >= 16 and all(any(fb for _, _, fb in c["trace"]) for c in dcases), (s.k, [c["trace"] for c in dcases])
+    out["tri_diffuse"] = dict(dt=hx(dtd), walls={"1": 800.0, "3": 450.0}, draws=[hx(v) for v in draws[:s.k]], used=s.k, cases=dcases)
 
     # ---- structured_walk: 4 x 3 cells on [0, 0.4] x [0, 0.3]; x periodic, ymin specular, ymax diffuse at 450 K; wall 1 a plain
     # specular segment at x = 0.2 facing -x, wall 2 a porous specular segment at y = 0.15 facing +y, wall 3 diffuse at x = 0.3

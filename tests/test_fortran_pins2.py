@@ -956,3 +956,46 @@ def test_remove_particles_of_species_store_order_matches_fortran_reading(oracle)
         got = oracle.download_particles()
         assert [int(i) for i in got["ID"]] == [i for i, _ in store]
     assert 0 < len(store) < 40 and all(s == 1 for _, s in store)
+
+
+# ---- diffuse wall on plane triangles --------------------------------------------------------------------------------------------
+def test_diffuse_wall_on_triangles_oracle_matches_fortran_reading(oracle):
+    """src/timecycle.f90:1327-1343, 1445-1476 on scripted draws: the 2-D wall frame (FACE_NORMAL = -EDGE_NORMAL, FACE_TANG1 =
+    (-n_y, n_x, 0), FACE_TANG2 = z) and the re-emission V = V_PERP n + V_TANG1 t1 + V_TANG2 t2 with MAXWELL / INTERNAL_ENERGY /
+    FLX at the wall temperature of the face's group; two particles share the stream in store order."""
+    t = PINS["tri_diffuse"]
+    m = pin_tri_mesh()
+    xy = np.array(PINS["tri_mesh"]["nodes"])
+    tri = np.array(PINS["tri_mesh"]["cells"]) - 1
+    a, b, c = xy[tri[:, 0]], xy[tri[:, 1]], xy[tri[:, 2]]
+    m.cell_volumes = 0.5 * np.abs(a[:, 0] * (b[:, 1] - c[:, 1]) + b[:, 0] * (c[:, 1] - a[:, 1]) + c[:, 0] * (a[:, 1] - b[:, 1]))
+    sp = wl.load_species("air", ["N2", "O2"])
+    dt = fh(t["dt"])
+    cfg = capi.make_config(dims=2, grid_type=capi.UNSTRUCTURED, nx=1, ny=1, xmin=0.0, xmax=0.09, ymin=0.01, ymax=0.05, zmin=-0.5, zmax=0.5,
+                           dt=dt, fnum=1.0, collision_type=capi.NO_COLL, dump_bound_avg_every=0, bool_z_periodic=0)
+    p = wl.new_particles(len(t["cases"]))
+    for k, cse in enumerate(t["cases"]):
+        q = cse["inp"]
+        for f in ("x", "y", "z", "vx", "vy", "vz", "erot", "evib"):
+            p[f.upper()][k] = fh(q[f])
+        p["IC"][k] = q["ic"]
+        p["S_ID"][k] = sp.id(q["sid"])
+    p["DTRIM"] = dt
+    kinds = [capi.SPECULAR] * 4
+    temps = [300.0] * 4
+    for g, tw in t["walls"].items():
+        kinds[int(g) - 1] = capi.DIFFUSE
+        temps[int(g) - 1] = tw
+    bcs = dict(particle_bc=kinds, wall_temp=temps, acc_n=[1.0] * 4, acc_t=[1.0] * 4)
+    w = wl.Workload("pin diffuse triangles", cfg, sp, p, mesh=m, bcs=bcs)
+    w.cfg.track_id = 1
+    wl.apply(oracle, w)
+    script(oracle, [fh(v) for v in t["draws"]])
+    oracle.advect(1)
+    assert script_used(oracle) == t["used"]
+    out = util.by_id(oracle.download_particles())
+    for k, cse in enumerate(t["cases"]):
+        e = cse["out"]
+        assert out["IC"][k] == e["ic"], (k, cse["trace"])
+        for f in ("x", "y", "z", "vx", "vy", "vz", "erot", "evib"):
+            assert float(out[f.upper()][k]) == pytest.approx(fh(e[f]), rel=1e-13, abs=1e-300), (k, f, cse["trace"])
