@@ -115,12 +115,15 @@ typedef struct pgpu_ctx pgpu_ctx;
 /* ---- life cycle ------------------------------------------------------------------------
  * created between INITFIELDS and TIME_LOOP in PROGRAM PANTERA (src/pantera.f90:51-87). */
 int pgpu_create(pgpu_ctx** ctx, int device);
+/* at the end of PROGRAM PANTERA (src/pantera.f90:91-98) */
 int pgpu_destroy(pgpu_ctx* ctx);
+/* text of the last error of this context; the shim passes it to ERROR_ABORT (src/screen.f90:113-124) */
 const char* pgpu_last_error(const pgpu_ctx* ctx);
 /* library/ABI version: major*1000+minor */
 int pgpu_version(void);
 
 /* ---- parameters (module globals the path reads) ---------------------------------------- */
+/* the scalars of src/global.f90 listed at struct pgpu_config above (set by READINPUT, src/initialization.f90:38-560) */
 int pgpu_set_config(pgpu_ctx* ctx, const pgpu_config* cfg);
 
 /* SPECIES(:) -- src/global.f90:488-508: MOLECULAR_MASS, CHARGE, ROTDOF, VIBDOF, ROTREL, VIBREL */
@@ -194,10 +197,12 @@ int pgpu_upload_particles(pgpu_ctx* ctx, const void* aos, int64_t n, int32_t str
 int pgpu_download_particles(pgpu_ctx* ctx, void* aos, int64_t capacity, int64_t* n, int32_t stride_bytes);
 /* ADD_PARTICLE_ARRAY for host-side injection (src/particle.f90:86-136) */
 int pgpu_append_particles(pgpu_ctx* ctx, const void* aos, int64_t n, int32_t stride_bytes);
+/* NP_PROC (src/global.f90:45) */
 int pgpu_num_particles(pgpu_ctx* ctx, int64_t* n);
 
 /* ---- fields ---------------------------------------------------------------------------- */
-/* E_FIELD: unstructured E_FIELD(3,1,NCELLS); structured E_FIELD(3,0:NPY-1,0:NPX-1)  (n doubles) */
+/* E_FIELD as APPLY_E_FIELD reads it (src/fields.f90:4194-4223): unstructured E_FIELD(3,1,NCELLS); structured
+ * E_FIELD(3,0:NPY-1,0:NPX-1)  (n doubles) */
 int pgpu_set_efield(pgpu_ctx* ctx, const double* e_field, int64_t n);
 /* B_FIELD(3,1,NNODES) (2-D unstructured nodal, src/fields.f90:4227-4249); NULL/0 clears */
 int pgpu_set_bfield(pgpu_ctx* ctx, const double* b_field, int64_t n);
@@ -363,11 +368,13 @@ int pgpu_get_boundary_counts(pgpu_ctx* ctx, int64_t* boundary_coll_count, int64_
 int pgpu_get_boundary_tallies(pgpu_ctx* ctx, double* tallies, int64_t n, int32_t reset);
 /* per-cell particle counts NPCALL(1:NCELLS) of the last sort (collisions.f90:63-68) */
 int pgpu_get_cell_counts(pgpu_ctx* ctx, int32_t* npc, int64_t nc);
-/* device-side time [ms] of the kernels of the last hot-path call, by group:
- * 0 move, 1 sort, 2 collide, 3 deposit, 4 exchange, 5 total; and launch count */
+/* device-side time [ms] of the kernels of the last hot-path call, by group (the sections of the reference's TIMER_START /
+ * TIMER_STOP, src/tools.f90:1342-1359, src/timecycle.f90:193-300): 0 move, 1 sort, 2 collide, 3 deposit, 4 exchange, 5 total;
+ * and launch count */
 int pgpu_get_timings(pgpu_ctx* ctx, double* ms, int32_t n, int64_t* launches);
 
-/* ---- multi-GPU plumbing (replaces MPI_COMM_WORLD for the path) ------------------------- */
+/* ---- multi-GPU plumbing (replaces MPI_COMM_WORLD for the path: MPI_INIT / MPI_COMM_SIZE / MPI_COMM_RANK of
+ * src/pantera.f90:35-37 stay with the host, which hands rank and size over in pgpu_config and here) ---- */
 /* rank 0 obtains a 128-byte NCCL unique id and the host broadcasts it (MPI_BCAST / torch) */
 int pgpu_comm_unique_id(char id128[128]);
 int pgpu_comm_init(pgpu_ctx* ctx, int nranks, int rank, const char id128[128]);
