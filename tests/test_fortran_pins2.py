@@ -999,3 +999,84 @@ def test_diffuse_wall_on_triangles_oracle_matches_fortran_reading(oracle):
         assert out["IC"][k] == e["ic"], (k, cse["trace"])
         for f in ("x", "y", "z", "vx", "vy", "vz", "erot", "evib"):
             assert float(out[f.upper()][k]) == pytest.approx(fh(e[f]), rel=1e-13, abs=1e-300), (k, f, cse["trace"])
+
+
+# ---- 1-D line mesh: the C4 geometry --------------------------------------------------------------------------------------------
+def test_line_mesh_walk_oracle_matches_fortran_reading(oracle):
+    """ADVECT on a 1-D unstructured mesh in plain Python: the DIMS == 1 face test (src/timecycle.f90:1257-1269), hops, a specular
+    electrode on the right, a vacuum one on the left (the particle is removed: :1611-1614), then the Y and Z periodic wraps
+    of 1-D runs (:2044-2066) -- bit-identical, survivors matched by ID (the removal sweep reorders the store)."""
+    xs = [0.0, 0.011, 0.019, 0.034, 0.041, 0.05]
+    nc = len(xs) - 1
+    from pantera_pic_dsmc_b200 import meshgen as mg
+    m = mg.line_1d(nc, 0.0, 1.0)
+    xyz = np.zeros((3, nc + 1))
+    xyz[0] = xs
+    m.node_coords = np.asfortranarray(xyz)
+    # EDGE_NORMAL of a segment: -1 at its first node, +1 at its second (src/grid_and_partition.f90:931-937); neighbours along the line
+    normal = [(-1.0, 1.0)] * nc
+    assert np.array_equal(np.asarray(m.face_normal)[0], np.array(normal).T)
+    sp = wl.load_species("ar", ["Ar", "Ar+", "e"])
+    dt = 4.0e-9
+    ymin, ymax, zmin, zmax = 0.0, 0.02, -0.01, 0.03
+    cfg = capi.make_config(dims=1, grid_type=capi.UNSTRUCTURED, nx=1, ny=1, xmin=0.0, xmax=0.05, ymin=ymin, ymax=ymax, zmin=zmin, zmax=zmax,
+                           dt=dt, fnum=1.0, collision_type=capi.NO_COLL, dump_bound_avg_every=0, bool_z_periodic=1, bool_y_periodic=1)
+    starts = [(0.013, 0.004, 0.0, 6.0e6, 9.0e6, -2.5e7),      # to the right: hops, specular electrode, back; y and z wrap several times
+              (0.03, 0.019, 0.02, -9.0e6, 1.0e6, 4.0e6),       # to the left: reaches x = 0 -> removed
+              (0.045, 0.01, 0.0, 1.0e5, -3.0e6, 1.0e6),         # stays in its cell; y wraps downwards
+              (0.02, 0.0, 0.029, -2.0e6, 0.0, 2.0e6)]           # one hop to the left, z wraps once
+    p = wl.new_particles(len(starts))
+    for k, (x, y, z, vx, vy, vz) in enumerate(starts):
+        p["X"][k], p["Y"][k], p["Z"][k], p["VX"][k], p["VY"][k], p["VZ"][k] = x, y, z, vx, vy, vz
+        p["IC"][k] = max(i for i in range(nc) if xs[i] <= x) + 1
+    p["S_ID"] = sp.id("Ar")
+    p["DTRIM"] = dt
+    p["ID"] = 70 + np.arange(len(starts))
+    bcs = dict(particle_bc=[capi.VACUUM, capi.SPECULAR], wall_temp=[300.0] * 2, acc_n=[1.0] * 2, acc_t=[1.0] * 2)
+    w = wl.Workload("pin line mesh", cfg, sp, p, mesh=m, bcs=bcs)
+    wl.apply(oracle, w)
+    oracle.advect(1)
+    got = {int(q["ID"]): q for q in oracle.download_particles()}
+    expect = {}
+    for k, (x, y, z, vx, vy, vz) in enumerate(starts):
+        ic = int(p["IC"][k])
+        dtrim = dt
+        removed = False
+        while dtrim > 0.0:
+            dtcoll, boundcoll = dtrim, -1
+            for i in (1, 2):
+                n = normal[ic - 1][i - 1]
+                vn = vx * n
+                dx = (xs[ic - 1 + (i - 1)] - x) * n
+                if vn >= 0.0 and vn * dtcoll >= dx:
+                    dtcoll, boundcoll = dx / vn, i
+            if boundcoll == -1:
+                x, y, z = x + vx * dtrim, y + vy * dtrim, z + vz * dtrim
+                dtrim = 0.0
+                continue
+            x, y, z = x + vx * dtcoll, y + vy * dtcoll, z + vz * dtcoll
+            dtrim = dtrim - dtcoll
+            neighbor = ic - 1 if boundcoll == 1 else ic + 1
+            if 1 <= neighbor <= nc:
+                ic = neighbor
+            elif boundcoll == 2:                                 # right electrode, group 2: specular
+                fn = -normal[ic - 1][1]
+                vdotn = vx * fn + vy * 0.0 + vz * 0.0
+                vx, vy, vz = vx - 2.0 * vdotn * fn, vy - 2.0 * vdotn * 0.0, vz - 2.0 * vdotn * 0.0
+            else:                                                # left electrode, group 1: vacuum
+                removed = True
+                dtrim = 0.0
+        while z > zmax:
+            z = zmin + (z - zmax)
+        while z < zmin:
+            z = zmax + (z - zmin)
+        while y > ymax:
+            y = ymin + (y - ymax)
+        while y < ymin:
+            y = ymax + (y - ymin)
+        if not removed:
+            expect[70 + k] = (x, y, z, vx, vy, vz, ic)
+    assert sorted(got) == sorted(expect) == [70, 72, 73]
+    for i, e in expect.items():
+        q = got[i]
+        assert (float(q["X"]), float(q["Y"]), float(q["Z"]), float(q["VX"]), float(q["VY"]), float(q["VZ"]), int(q["IC"])) == e, (i, e)
